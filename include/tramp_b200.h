@@ -1,0 +1,227 @@
+/* tramp_b200 -- C ABI of the B200-native expectation-propagation (EP) sweep.
+ *
+ * The reference (sphinxteam/tramp) is pure Python/numpy and has NO FFI: its
+ * plugin boundary is the Python factor protocol (compute_forward_posterior,
+ * compute_backward_message, ... -- tramp/base.py:329-365, docs/implementation
+ * .rst:41-147).  tramp_b200 keeps that protocol in Python (tramp_b200/*.py) and
+ * adds this thin C layer underneath; each entry point below cites the reference
+ * routine whose arithmetic it replaces.  INTEGRATION.md shows the ctypes stubs
+ * a tramp maintainer would add to call it.
+ *
+ * Conventions
+ *  - every function returns 0 on success, a negative trb_status otherwise;
+ *    trb_last_error() gives a thread-local message.  No C++ exception crosses.
+ *  - all buffers are CALLER-OWNED DEVICE pointers (FP64, contiguous,
+ *    batch-major); the library never frees or retains them past the call.
+ *  - `stream` is a cudaStream_t passed as void*; every call is asynchronous
+ *    on that stream.  One host thread per plan/device.
+ *  - a "batch" is B independent teacher-student instances: scalars are [B],
+ *    vectors [B, ld] with leading dimension ld >= n (ld % 2 == 0; padding
+ *    columns are ignored on input and left untouched on output).
+ */
+#ifndef TRAMP_B200_H
+#define TRAMP_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TRB_VERSION 100
+
+typedef enum {
+  TRB_OK = 0,
+  TRB_ERR_INVALID = -1,  /* bad argument */
+  TRB_ERR_CUDA = -2,     /* CUDA runtime error (message in trb_last_error) */
+  TRB_ERR_UNSUPPORTED = -3
+} trb_status;
+
+/* Separable factor kinds (priors and likelihoods share one moment engine). */
+typedef enum {
+  TRB_GAUSS_BERNOULLI_PRIOR = 0, /* priors/gauss_bernoulli_prior.py:70-83 + beliefs/sparse.py */
+  TRB_BINARY_PRIOR = 1,          /* priors/binary_prior.py:57-68 + beliefs/binary.py */
+  TRB_GAUSSIAN_PRIOR = 2,        /* priors/gaussian_prior.py:63-89 */
+  TRB_GAUSSIAN_LIKELIHOOD = 3,   /* likelihoods/gaussian_likelihood.py:43-71 */
+  TRB_SGN_LIKELIHOOD = 4,        /* likelihoods/sgn_likelihood.py:32-41 + beliefs/positive.py */
+  TRB_ABS_LIKELIHOOD = 5         /* likelihoods/abs_likelihood.py:31-40 */
+} trb_factor_kind;
+
+/* Natural parameters of one separable factor.
+ *   GAUSS_BERNOULLI: p0 = 1/var, p1 = mean/var, p2 = eta (gauss_bernoulli_prior.py:33-36),
+ *                    p3 = sparse.A(p0, p1, eta)  (the constant subtracted in :82)
+ *   BINARY:          p0 = 0.5*log(p_pos/p_neg) (binary_prior.py:28)
+ *   GAUSSIAN_PRIOR:  p0 = 1/var, p1 = mean/var
+ *   GAUSSIAN_LIKELIHOOD: p0 = 1/var
+ *   SGN, ABS: no parameters
+ * amin/amax: Factor.AMIN/AMAX (base.py:238-243). */
+typedef struct {
+  int32_t kind;
+  int32_t _pad;
+  double p0, p1, p2, p3;
+  double amin, amax;
+} trb_factor;
+
+/* flag bits written per instance by the message kernels
+ * (algos/message_passing.py:187-209 check_message) */
+#define TRB_FLAG_NAN_A 1
+#define TRB_FLAG_NAN_B 2
+#define TRB_FLAG_NEG_A 4
+/* set by the sweep's EarlyStoppingEP logic (callbacks.py:266-283) */
+#define TRB_FLAG_CONVERGED 8
+#define TRB_FLAG_DIVERGED 16
+
+const char* trb_last_error(void);
+int trb_version(void);
+size_t trb_sizeof_factor(void);
+size_t trb_sizeof_sweep(void);
+/* number of SMs of the current device (0 if no device) */
+int trb_device_sm_count(void);
+
+/* ---- elementwise moment kernels ------------------------------------------
+ * a_mode: 0 = one precision per instance a[B] (isotropic beliefs), 1 = one per
+ * element a[B, ld] (isotropic=False in the reference's unit tests).
+ * v_mode: 0 = v[B] is the per-instance MEAN of the elementwise variance
+ * (`vx.mean()`), 1 = v[B, ld] elementwise.  y is NULL for priors. */
+
+/* compute_forward_posterior / compute_backward_posterior of the factor kinds */
+int trb_factor_posterior(const trb_factor* f, int B, int n, int ld,
+                         const double* a, int a_mode, const double* b,
+                         const double* y, double* r, double* v, int v_mode,
+                         void* stream);
+
+/* compute_log_partition: A_mode 0 = per-instance MEAN A[B] (what the reference
+ * returns), 1 = elementwise A[B, ld] (scalar_log_partition vectorised). */
+int trb_factor_log_partition(const trb_factor* f, int B, int n, int ld,
+                             const double* a, int a_mode, const double* b,
+                             const double* y, double* A, int A_mode,
+                             void* stream);
+
+/* Whole factor->variable update in one pass over HBM:
+ * posterior -> mean variance -> compute_ab_new clip (base.py:250-255) ->
+ * constant damping against the stored message (message_passing.py:119-127).
+ * (a_io, b_io) hold the stored (old) message on entry and the new one on exit.
+ * Gaussian kinds emit their constant message (gaussian_prior.py:86-89,
+ * gaussian_likelihood.py:68-71), still damped.  a_copy (nullable) receives a
+ * copy of the new a (the SISOVariable pass-through, sub_variables.py:16-31).
+ * scratch: [B, ld] doubles.  flags (nullable): int[B], OR-ed TRB_FLAG_*.
+ * active (nullable): int[B], instances with 0 are skipped. */
+int trb_factor_message(const trb_factor* f, int B, int n, int ld,
+                       const double* a_in, const double* b_in, const double* y,
+                       double* a_io, double* b_io, double* a_copy,
+                       double damping, double* scratch, int* flags,
+                       const int* active, void* stream);
+
+/* Truncated-normal moments on [zmin, zmax] (utils/truncated_normal.py:234-298,
+ * all five F0/F1/F2 branches and the half-infinite erfcx fast path).  Any of
+ * the outputs may be NULL. r0, v0: [n]. */
+int trb_truncated_normal(int n, const double* r0, const double* v0,
+                         double zmin, double zmax, double* mean, double* var,
+                         double* logZ, double* proba, void* stream);
+
+/* Variable.posterior_rv (base.py:152-161): r = (b1+b2)/(a1+a2), v = 1/(a1+a2) */
+int trb_posterior_rv(int B, int n, int ld, const double* a1, const double* b1,
+                     const double* a2, const double* b2, double* r, double* v,
+                     void* stream);
+
+/* ---- LinearChannel in thin-SVD form --------------------------------------
+ * W = U_R diag(s) V_R^T.  Operators are stored TRANSPOSED, one singular vector
+ * per row: Vt[Bop, R, ldn] (rows = right singular vectors, length n = Nz) and
+ * Ut[Bop, R, ldm].  strideA = elements between instances (0: all instances
+ * share one operator).  impl: 0 = default, 1 = plain LDG kernels,
+ * 2 = TMA(cp.async.bulk)+mbarrier ring. */
+
+/* t[b, i] = sum_j A[b, i, j] * vec[b, j]      (U.T @ bx, V.T @ bz;
+ * channels/linear/linear_channel.py:72-73).  t: [B, R]. */
+int trb_lin_project(const double* A, int64_t strideA, int R, int n, int ld,
+                    int B, const double* vec, int ldvec, double* t,
+                    const int* active, int impl, void* stream);
+
+/* number of partial-sum slots trb_lin_expand writes per instance (>= 1) */
+int trb_lin_expand_slots(int B, int R);
+
+/* part[b, slot, j] = sum_{i in rows of CTA `slot`} coef[b, i] * A[b, i, j]
+ * (V @ rz_svd, linear_channel.py:78).  part: [B, nslots, ld]; slots beyond the
+ * ones an instance uses are not written -- reduce with trb_lin_reduce_slots or
+ * the fused sweep kernels. */
+int trb_lin_expand(const double* A, int64_t strideA, int R, int n, int ld,
+                   int B, const double* coef, double* part,
+                   const int* active, int impl, void* stream);
+
+/* out[b, j] = sum_slots part[b, slot, j] (+ add_scale[b] * add[b, j] if add) */
+int trb_lin_reduce_slots(int B, int R, int n, int ld, const double* part,
+                         const double* add, const double* add_scale_inv,
+                         double* out, void* stream);
+
+/* Spectrum rescale between the projections and the expansions, plus the
+ * variances (linear_channel.py:58-67, 74, 91-105).
+ *   dir = 0 (forward, x-side mean):  coef = s*res*(tz + s*tx),  v = forward variance
+ *   dir = 1 (backward, z-side mean): coef = res*(tz + s*tx)               if R == Nz
+ *                                    coef = res*(s*tx - (ax*s2/az)*tz)   if R <  Nz
+ *                                    (then rz = bz/az + V_R coef), v = backward variance
+ * with res = 1/(az + ax*s2).  s, s2: [Bop, R] (stride_s = 0 if shared);
+ * rank: singular = spectrum[:rank] (linear_channel.py:46). */
+int trb_lin_rescale(int dir, int B, int R, int Nz, int Nx, int rank,
+                    const double* s, const double* s2, int64_t stride_s,
+                    const double* az, const double* ax, const double* tz,
+                    const double* tx, double* coef, double* v,
+                    const int* active, void* stream);
+
+/* ---- device-resident sweep ------------------------------------------------
+ * algos/message_passing.py:330-357 (iterate) with :249-269 (forward_message,
+ * backward_message, update_variables), :70-127 (constant damping), :187-209
+ * (NaN check) and callbacks.py:250-286 (EarlyStoppingEP), for the chain
+ * prior -> x -> LinearChannel -> z -> likelihood, B instances in lock step,
+ * no host round trip inside. */
+typedef struct {
+  int32_t B, N, M, R, ldn, ldm, rank, nslots;
+  trb_factor prior, lik;
+  double lin_amin, lin_amax;
+  /* operators */
+  const double* Vt; int64_t strideV;
+  const double* Ut; int64_t strideU;
+  const double* s; const double* s2; int64_t stride_s;
+  /* observations and (optional) ground truth for the MSE trajectory */
+  const double* y;       /* [B, ldm] */
+  const double* x_true;  /* [B, ldn] or NULL */
+  /* messages: edge_a[8, B] = a of e1..e8 (SURVEY 3.3 numbering);
+   * b1,b7: [B, ldn]; b3,b5: [B, ldm].  e2=e1, e4=e3, e6=e5, e8=e7 are exact
+   * pass-throughs (sub_variables.py:16-31) and alias their source vector. */
+  double* edge_a;
+  double* b1; double* b3; double* b5; double* b7;
+  /* iteration-0 inputs when the initializer gave e6/e8 a value different from
+   * e5/e7 (NoisyInit); NULL = alias b5/b7 */
+  const double* b6_init; const double* b8_init;
+  /* damping of the factor->variable edges e1, e3, e5, e7 (0 = none) */
+  double damp1, damp3, damp5, damp7;
+  /* posteriors (update_variables): rx [B, ldn], rz [B, ldm], vx, vz [B] */
+  double* rx; double* rz; double* vx; double* vz;
+  /* scratch: tz, tx, coef: [B, R]; part: [B, nslots, max(ldn, ldm)];
+   * scr_n: [B, ldn]; scr_m: [B, ldm]; vlin: [B]; stats: [B, 4] */
+  double* tz; double* tx; double* coef; double* part;
+  double* scr_n; double* scr_m; double* vlin; double* stats;
+  /* per-instance control/status: active[B] (1 = iterate), flags[B],
+   * n_iter[B] (iterations completed) */
+  int32_t* active; int32_t* flags; int32_t* n_iter;
+  /* per-iteration records, [max_records, B] each (NULL = do not record):
+   * mse of x, sign-symmetric mse of x, v of x, v of z, EarlyStoppingEP tol */
+  double* rec_mse; double* rec_smse; double* rec_vx; double* rec_vz; double* rec_tol;
+  int32_t max_records;
+  /* EarlyStoppingEP(ids="all"): enabled if es_tol >= 0 */
+  double es_tol, es_max_increase; int32_t es_wait_increase;
+  int32_t gemv_impl;   /* 0 default, 1 LDG, 2 TMA ring */
+  int32_t _pad;
+} trb_sweep;
+
+/* Run `n_iter` EP iterations.  `it0` is the index, within the current
+ * iterate() call, of the first one (records go to row it0, it0+1, ...; the
+ * early-stopping test needs it > 0).  fresh = 1: the message buffers hold the
+ * initializer's values (b6_init / b8_init are honoured on the first iteration
+ * and tx is recomputed); fresh = 0: warm start / continuation. */
+int trb_sweep_run(const trb_sweep* sw, int it0, int n_iter, int fresh, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TRAMP_B200_H */

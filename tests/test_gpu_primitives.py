@@ -1,0 +1,178 @@
+"""GPU parity of the C-ABI primitives against the golden vectors of the
+reference and against the CPU oracle (bit-level tolerance noted per test)."""
+import os
+import numpy as np
+import pytest
+from numpy.testing import assert_allclose
+
+from tests.golden.make_golden_specs import PRIOR_SPECS, LIK_SPECS, TRUNC_CASES
+
+pytestmark = pytest.mark.gpu
+
+# FP64 special functions (erfcx, tanh, exp, log) of CUDA and of scipy agree to a
+# few ulp; 1e-11 relative leaves two decades of margin below the 1e-9 bar.
+RTOL = 1e-11
+
+
+@pytest.fixture(scope="module")
+def ops():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from tramp_b200 import ops as _ops
+    return _ops
+
+
+@pytest.fixture(scope="module")
+def el(golden_dir):
+    return np.load(os.path.join(golden_dir, "elementwise.npz"))
+
+
+@pytest.fixture(scope="module")
+def lin(golden_dir):
+    return np.load(os.path.join(golden_dir, "linear.npz"))
+
+
+def _np(t):
+    return t.detach().cpu().numpy()
+
+
+@pytest.mark.parametrize("i", range(len(PRIOR_SPECS)))
+def test_prior_posterior_and_log_partition(ops, el, i):
+    f = ops.factor_from_spec(PRIOR_SPECS[i])
+    a, b = el["grid_a"], el["grid_b"]
+    n = a.size
+    A = ops.padded(a[None, :])
+    Bv = ops.padded(b[None, :])
+    r, v = ops.factor_posterior(f, A, Bv, None, n, True, True)
+    assert_allclose(_np(r)[0, :n], el[f"prior{i}_r"], rtol=RTOL, atol=1e-300)
+    assert_allclose(_np(v)[0, :n], el[f"prior{i}_v"], rtol=RTOL, atol=1e-300)
+    Ael = ops.factor_log_partition(f, A, Bv, None, n, True, True)
+    assert_allclose(_np(Ael)[0, :n], el[f"prior{i}_A"], rtol=RTOL, atol=1e-13)
+    for j, a_s in enumerate(el["iso_a"]):
+        a1 = ops.to_dev(np.array([a_s]))
+        r, v = ops.factor_posterior(f, a1, Bv, None, n, False, False)
+        assert_allclose(_np(r)[0, :n], el[f"prior{i}_iso{j}_r"], rtol=RTOL, atol=1e-300)
+        assert_allclose(_np(v)[0], el[f"prior{i}_iso{j}_v"], rtol=RTOL)
+        Am = ops.factor_log_partition(f, a1, Bv, None, n, False, False)
+        assert_allclose(_np(Am)[0], el[f"prior{i}_iso{j}_A"], rtol=1e-10)
+        a_io = ops.zeros(1)
+        b_io = ops.zeros(1, Bv.shape[1])
+        ops.factor_message(f, a1, Bv, None, n, a_io, b_io)
+        assert_allclose(_np(a_io)[0], el[f"prior{i}_iso{j}_anew"], rtol=RTOL)
+        bn = el[f"prior{i}_iso{j}_bnew"]
+        assert_allclose(_np(b_io)[0, :n], bn, rtol=1e-10, atol=1e-10 * np.abs(bn).max())
+
+
+@pytest.mark.parametrize("i", range(len(LIK_SPECS)))
+def test_likelihood_posterior_and_log_partition(ops, el, i):
+    f = ops.factor_from_spec(dict(LIK_SPECS[i], role="likelihood"))
+    a, b, y = el["grid_a"], el["grid_b"], el[f"lik{i}_y"]
+    n = a.size
+    A, Bv, Y = ops.padded(a[None, :]), ops.padded(b[None, :]), ops.padded(y[None, :])
+    r, v = ops.factor_posterior(f, A, Bv, Y, n, True, True)
+    assert_allclose(_np(r)[0, :n], el[f"lik{i}_r"], rtol=RTOL, atol=1e-300)
+    assert_allclose(_np(v)[0, :n], el[f"lik{i}_v"], rtol=1e-10, atol=1e-300)
+    Ael = ops.factor_log_partition(f, A, Bv, Y, n, True, True)
+    assert_allclose(_np(Ael)[0, :n], el[f"lik{i}_A"], rtol=RTOL, atol=1e-13)
+    for j, a_s in enumerate(el["iso_a"]):
+        a1 = ops.to_dev(np.array([a_s]))
+        r, v = ops.factor_posterior(f, a1, Bv, Y, n, False, False)
+        assert_allclose(_np(r)[0, :n], el[f"lik{i}_iso{j}_r"], rtol=RTOL, atol=1e-300)
+        assert_allclose(_np(v)[0], el[f"lik{i}_iso{j}_v"], rtol=RTOL)
+        Am = ops.factor_log_partition(f, a1, Bv, Y, n, False, False)
+        assert_allclose(_np(Am)[0], el[f"lik{i}_iso{j}_A"], rtol=1e-10)
+        a_io = ops.zeros(1)
+        b_io = ops.zeros(1, Bv.shape[1])
+        ops.factor_message(f, a1, Bv, Y, n, a_io, b_io)
+        assert_allclose(_np(a_io)[0], el[f"lik{i}_iso{j}_anew"], rtol=RTOL)
+        bn = el[f"lik{i}_iso{j}_bnew"]
+        assert_allclose(_np(b_io)[0, :n], bn, rtol=1e-10, atol=1e-10 * np.abs(bn).max())
+
+
+@pytest.mark.parametrize("i", range(len(TRUNC_CASES)))
+def test_truncated_normal(ops, el, i):
+    a, lo, hi = TRUNC_CASES[i]
+    b = el["trunc_b"]
+    r0 = ops.to_dev(b / a)
+    v0 = ops.to_dev(np.full_like(b, 1 / a))
+    mean, var, logZ, proba = ops.truncated_normal(r0, v0, lo, hi)
+    # the "close" Taylor branch and near-cancelling tails lose digits in the
+    # reference itself; compare at 1e-9 there, nan == nan
+    kw = dict(rtol=1e-9, equal_nan=True)
+    assert_allclose(_np(mean), el[f"trunc{i}_r"], atol=1e-12, **kw)
+    assert_allclose(_np(var), el[f"trunc{i}_v"], atol=1e-12, **kw)
+    assert_allclose(_np(logZ), el[f"trunc{i}_A"], atol=1e-12, **kw)
+    assert_allclose(_np(proba), el[f"trunc{i}_p"], atol=1e-300, **kw)
+
+
+def _thin_svd(W):
+    U, s, Vt = np.linalg.svd(W, full_matrices=False)
+    return U, s, Vt
+
+
+@pytest.mark.parametrize("impl", [1, 2])
+def test_linear_channel_primitives(ops, lin, impl):
+    """rz, vz, rx, vx of LinearChannel through project -> rescale -> expand."""
+    for i in range(int(lin["lin_nW"])):
+        W = lin[f"lin{i}_W"]
+        M, N = W.shape
+        rank = int(lin[f"lin{i}_rank"])
+        U, s, Vt = _thin_svd(W)
+        R = s.size
+        Vt_d = ops.padded(Vt).unsqueeze(0).contiguous()      # [1, R, ldn]
+        Ut_d = ops.padded(U.T.copy()).unsqueeze(0).contiguous()  # [1, R, ldm]
+        s_d = ops.to_dev(s[None, :])
+        s2_d = ops.to_dev((s**2)[None, :])
+        bz, bx = lin[f"lin{i}_bz"], lin[f"lin{i}_bx"]
+        bz_d, bx_d = ops.padded(bz[None, :]), ops.padded(bx[None, :])
+        tz = ops.lin_project(Vt_d, R, N, bz_d, 1, impl)
+        tx = ops.lin_project(Ut_d, R, M, bx_d, 1, impl)
+        assert_allclose(_np(tz)[0], Vt @ bz, rtol=1e-12, atol=1e-13)
+        assert_allclose(_np(tx)[0], U.T @ bx, rtol=1e-12, atol=1e-13)
+        for j, (az, ax) in enumerate(lin["lin_ab"]):
+            if az == 0:
+                continue
+            az_d, ax_d = ops.to_dev(np.array([az])), ops.to_dev(np.array([ax]))
+            coef, vx = ops.lin_rescale(0, 1, R, N, M, rank, s_d, s2_d, az_d, ax_d, tz, tx)
+            rx = ops.lin_expand(Ut_d, R, M, coef, 1, impl)
+            assert_allclose(_np(vx)[0], lin[f"lin{i}_{j}_vx"], rtol=1e-12)
+            ref = lin[f"lin{i}_{j}_rx"]
+            assert_allclose(_np(rx)[0, :M], ref, rtol=1e-9, atol=1e-12 * max(1.0, np.abs(ref).max()))
+            coef, vz = ops.lin_rescale(1, 1, R, N, M, rank, s_d, s2_d, az_d, ax_d, tz, tx)
+            add = bz_d if R < N else None
+            rz = ops.lin_expand(Vt_d, R, N, coef, 1, impl, add=add, add_div=az_d if R < N else None)
+            assert_allclose(_np(vz)[0], lin[f"lin{i}_{j}_vz"], rtol=1e-12)
+            ref = lin[f"lin{i}_{j}_rz"]
+            assert_allclose(_np(rz)[0, :N], ref, rtol=1e-9, atol=1e-12 * max(1.0, np.abs(ref).max()))
+
+
+@pytest.mark.parametrize("impl", [1, 2])
+@pytest.mark.parametrize("shape", [(3, 40, 100), (5, 64, 1000), (2, 300, 2048), (2, 17, 4096),
+                                    (1, 9, 6000), (7, 33, 130)])
+def test_gemv_shapes_vs_numpy(ops, impl, shape):
+    """project / expand on ragged shapes (odd n, rows not a multiple of the
+    chunk, several instances per CTA and several CTAs per instance)."""
+    B, R, n = shape
+    rng = np.random.RandomState(B * 1000 + R)
+    A = rng.randn(B, R, n)
+    x = rng.randn(B, n)
+    c = rng.randn(B, R)
+    ld = ops.pad_ld(n)
+    import torch
+    A_d = torch.zeros((B, R, ld), dtype=torch.float64, device="cuda")
+    A_d[:, :, :n] = torch.as_tensor(A, device="cuda")
+    x_d = ops.padded(x)
+    t = ops.lin_project(A_d, R, n, x_d, B, impl)
+    assert_allclose(_np(t), np.einsum("brn,bn->br", A, x), rtol=1e-11, atol=1e-11)
+    out = ops.lin_expand(A_d, R, n, ops.to_dev(c), B, impl)
+    assert_allclose(_np(out)[:, :n], np.einsum("brn,br->bn", A, c), rtol=1e-11, atol=1e-11)
+    # shared operator (stride 0), config-4 style
+    t = ops.lin_project(A_d[:1].contiguous(), R, n, x_d, B, impl)
+    assert_allclose(_np(t), np.einsum("rn,bn->br", A[0], x), rtol=1e-11, atol=1e-11)
+    # masked instances are skipped
+    active = torch.ones(B, dtype=torch.int32, device="cuda")
+    active[0] = 0
+    t = ops.lin_project(A_d, R, n, x_d, B, impl, active=active)
+    assert np.all(_np(t)[0] == 0)
+    assert_allclose(_np(t)[1:], np.einsum("brn,bn->br", A, x)[1:], rtol=1e-11, atol=1e-11)

@@ -1,0 +1,147 @@
+// Shared device/host helpers for the tramp_b200 kernels (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include "../../include/tramp_b200.h"
+
+// ---------------------------------------------------------------- host side
+extern thread_local char trb_err_buf[512];
+int trb_set_error(int code, const char* fmt, ...);
+
+#define TRB_CHECK_ARG(cond, what)                                              \
+  do {                                                                         \
+    if (!(cond)) return trb_set_error(TRB_ERR_INVALID, "%s: %s", __func__, what); \
+  } while (0)
+
+#define TRB_CHECK_LAUNCH()                                                     \
+  do {                                                                         \
+    cudaError_t e_ = cudaGetLastError();                                       \
+    if (e_ != cudaSuccess)                                                     \
+      return trb_set_error(TRB_ERR_CUDA, "%s: %s", __func__, cudaGetErrorString(e_)); \
+  } while (0)
+
+int trb_sm_count_cached();
+
+// --------------------------------------------------------------- device side
+namespace trb {
+
+constexpr double kTwoPi = 6.283185307179586476925286766559;
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// Sum over the block; result valid in every thread.  `sh` holds >= 33 doubles.
+// Safe to call repeatedly with the same `sh` (leading barrier).
+__device__ __forceinline__ double block_sum(double v, double* sh) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int nwarp = (blockDim.x + 31) >> 5;
+  v = warp_sum(v);
+  __syncthreads();
+  if (lane == 0) sh[warp] = v;
+  __syncthreads();
+  if (warp == 0) {
+    double t = (lane < nwarp) ? sh[lane] : 0.0;
+    t = warp_sum(t);
+    if (lane == 0) sh[32] = t;
+  }
+  __syncthreads();
+  return sh[32];
+}
+
+__device__ __forceinline__ int block_or(int v, int* sh) {
+  v = __reduce_or_sync(0xffffffffu, v);
+  __syncthreads();
+  if (threadIdx.x == 0) *sh = 0;
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0 && v) atomicOr(sh, v);
+  __syncthreads();
+  return *sh;
+}
+
+// streaming 16-byte load that does not pollute L1 (operators are read once)
+__device__ __forceinline__ double2 ldg_stream(const double* p) {
+  double2 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0, %1}, [%2];"
+               : "=d"(r.x), "=d"(r.y)
+               : "l"(p));
+  return r;
+}
+
+// base.py:44-46 + 250-255.  np.maximum / np.clip propagate NaN whereas CUDA
+// fmax/fmin drop it, so NaN is routed around them: a NaN variance must surface
+// as a NaN message so that the check of message_passing.py:187-209 fires.
+__device__ __forceinline__ double clip_a_new(double v, double a, double amin, double amax) {
+  double vv = (v != v) ? v : fmax(v, 1e-20);
+  double an = 1.0 / vv - a;
+  if (an == an) an = fmin(fmax(an, amin), amax);
+  return an;
+}
+
+// message_passing.py:119-127; `if not damping: return data`
+__device__ __forceinline__ double damp(double d, double old_v, double new_v) {
+  return (d != 0.0) ? d * old_v + (1.0 - d) * new_v : new_v;
+}
+
+// ---- mbarrier + 1-D bulk copy (TMA) PTX wrappers --------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "LAB_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra DONE;\n"
+      "bra LAB_WAIT;\n"
+      "DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+// global -> shared bulk copy, completion signalled on `bar` (complete_tx).
+// dst/src 16-byte aligned, bytes % 16 == 0.
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes,
+                                         uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+          smem_u32(dst_smem)),
+      "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+      : "memory");
+}
+
+// Even split of T work items over G workers: worker k owns [part_begin(k), part_begin(k+1)).
+__host__ __device__ __forceinline__ int64_t part_begin(int64_t k, int64_t T, int64_t G) {
+  return (k * T) / G;
+}
+// worker that owns item g
+__host__ __device__ __forceinline__ int64_t part_owner(int64_t g, int64_t T, int64_t G) {
+  return ((g + 1) * G - 1) / T;
+}
+
+}  // namespace trb
+
+// Launch geometry shared by trb_lin_expand and the kernels that reduce its slots.
+struct trb_expand_geom {
+  int G;       // number of CTAs (workers) over the B*R row space
+  int nslots;  // max number of workers whose range touches one instance
+};
+trb_expand_geom trb_expand_geometry(int B, int R);

@@ -1,0 +1,232 @@
+// Elementwise moment kernels: separable priors / likelihoods, truncated
+// normal, Variable.posterior_rv.  One CTA per instance; FP64; coalesced
+// double2 where alignment allows.  See include/tramp_b200.h for the contract.
+#include <stdarg.h>
+#include "trb_moments.cuh"
+
+using namespace trb;
+
+thread_local char trb_err_buf[512] = "";
+
+int trb_set_error(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(trb_err_buf, sizeof(trb_err_buf), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+int trb_sm_count_cached() {
+  static int sm = -1;
+  if (sm < 0) {
+    int dev = 0, n = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess ||
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) {
+      cudaGetLastError();
+      return 0;
+    }
+    sm = n;
+  }
+  return sm;
+}
+
+extern "C" const char* trb_last_error(void) { return trb_err_buf; }
+extern "C" int trb_version(void) { return TRB_VERSION; }
+extern "C" size_t trb_sizeof_factor(void) { return sizeof(trb_factor); }
+extern "C" size_t trb_sizeof_sweep(void) { return sizeof(trb_sweep); }
+extern "C" int trb_device_sm_count(void) { return trb_sm_count_cached(); }
+
+namespace {
+
+constexpr int kEwThreads = 512;
+
+// ---- posterior: r, v (mean or elementwise) ---------------------------------
+__global__ void __launch_bounds__(kEwThreads)
+k_factor_posterior(trb_factor f, int n, int ld, const double* __restrict__ a, int a_mode,
+                   const double* __restrict__ b, const double* __restrict__ y,
+                   double* __restrict__ r, double* __restrict__ v, int v_mode) {
+  __shared__ double sh[33];
+  const int inst = blockIdx.x;
+  const size_t off = (size_t)inst * ld;
+  const double a_s = a_mode ? 0.0 : a[inst];
+  double vsum = 0.0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const double ai = a_mode ? a[off + i] : a_s;
+    const double yi = y ? y[off + i] : 0.0;
+    const RV m = factor_moments(f, ai, b[off + i], yi);
+    r[off + i] = m.r;
+    if (v_mode) v[off + i] = m.v;
+    vsum += m.v;
+  }
+  if (!v_mode) {
+    const double tot = block_sum(vsum, sh);
+    if (threadIdx.x == 0) v[inst] = tot / n;
+  }
+}
+
+__global__ void __launch_bounds__(kEwThreads)
+k_factor_log_partition(trb_factor f, int n, int ld, const double* __restrict__ a, int a_mode,
+                       const double* __restrict__ b, const double* __restrict__ y,
+                       double* __restrict__ A, int A_mode) {
+  __shared__ double sh[33];
+  const int inst = blockIdx.x;
+  const size_t off = (size_t)inst * ld;
+  const double a_s = a_mode ? 0.0 : a[inst];
+  double sum = 0.0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const double ai = a_mode ? a[off + i] : a_s;
+    const double yi = y ? y[off + i] : 0.0;
+    const double Ai = factor_log_partition(f, ai, b[off + i], yi);
+    if (A_mode) A[off + i] = Ai;
+    sum += Ai;
+  }
+  if (!A_mode) {
+    const double tot = block_sum(sum, sh);
+    if (threadIdx.x == 0) A[inst] = tot / n;
+  }
+}
+
+// ---- fused factor -> variable message --------------------------------------
+// posterior -> mean(v) -> clip -> b_new -> damping, one CTA per instance.
+// The moments are evaluated once; r is parked in `scratch` (same thread writes
+// and re-reads it, so it comes back from L1/L2, not HBM).
+__global__ void __launch_bounds__(kEwThreads)
+k_factor_message(trb_factor f, int n, int ld, const double* __restrict__ a_in,
+                 const double* __restrict__ b_in, const double* __restrict__ y, double* a_io,
+                 double* b_io, double* a_copy, double damping, double* __restrict__ scratch,
+                 int* flags, const int* __restrict__ active) {
+  __shared__ double sh[33];
+  __shared__ int sh_flag;
+  const int inst = blockIdx.x;
+  if (active && !active[inst]) return;
+  const size_t off = (size_t)inst * ld;
+  const double a = a_in[inst];
+  double a_new;
+  int flag = 0;
+  if (factor_is_constant_message(f.kind)) {
+    // gaussian_prior.py:86-89 / gaussian_likelihood.py:68-71: constants, no clip
+    a_new = f.p0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+      const double bn = (f.kind == TRB_GAUSSIAN_PRIOR) ? f.p1 : y[off + i] * f.p0;
+      const double bd = damp(damping, b_io[off + i], bn);
+      b_io[off + i] = bd;
+      if (bn != bn) flag |= TRB_FLAG_NAN_B;
+    }
+  } else {
+    double vsum = 0.0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+      const double yi = y ? y[off + i] : 0.0;
+      const RV m = factor_moments(f, a, b_in[off + i], yi);
+      scratch[off + i] = m.r;
+      vsum += m.v;
+    }
+    const double v = block_sum(vsum, sh) / n;
+    a_new = clip_a_new(v, a, f.amin, f.amax);
+    const double ainv = a + a_new;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+      const double bn = scratch[off + i] * ainv - b_in[off + i];
+      const double bd = damp(damping, b_io[off + i], bn);
+      b_io[off + i] = bd;
+      if (bn != bn) flag |= TRB_FLAG_NAN_B;
+    }
+  }
+  if (a_new != a_new) flag |= TRB_FLAG_NAN_A;
+  if (a_new < 0) flag |= TRB_FLAG_NEG_A;
+  const int all = block_or(flag, &sh_flag);
+  if (threadIdx.x == 0) {
+    const double ad = damp(damping, a_io[inst], a_new);
+    a_io[inst] = ad;
+    if (a_copy) a_copy[inst] = ad;
+    if (flags && all) atomicOr(&flags[inst], all);
+  }
+}
+
+__global__ void k_truncated_normal(int n, const double* __restrict__ r0,
+                                   const double* __restrict__ v0, double zmin, double zmax,
+                                   double* mean, double* var, double* logZ, double* proba) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const TruncMoments t = truncated_normal(r0[i], v0[i], zmin, zmax);
+  if (mean) mean[i] = t.mean;
+  if (var) var[i] = t.var;
+  if (logZ) logZ[i] = t.logZ;
+  if (proba) proba[i] = t.proba;
+}
+
+__global__ void __launch_bounds__(kEwThreads)
+k_posterior_rv(int n, int ld, const double* __restrict__ a1, const double* __restrict__ b1,
+               const double* __restrict__ a2, const double* __restrict__ b2,
+               double* __restrict__ r, double* __restrict__ v) {
+  const int inst = blockIdx.x;
+  const size_t off = (size_t)inst * ld;
+  const double a_hat = a1[inst] + a2[inst];
+  for (int i = threadIdx.x; i < n; i += blockDim.x)
+    r[off + i] = (b1[off + i] + b2[off + i]) / a_hat;
+  if (threadIdx.x == 0) v[inst] = 1. / a_hat;
+}
+
+bool needs_y(int kind) { return kind >= TRB_GAUSSIAN_LIKELIHOOD; }
+
+}  // namespace
+
+extern "C" int trb_factor_posterior(const trb_factor* f, int B, int n, int ld, const double* a,
+                                    int a_mode, const double* b, const double* y, double* r,
+                                    double* v, int v_mode, void* stream) {
+  TRB_CHECK_ARG(f && a && b && r && v, "null pointer");
+  TRB_CHECK_ARG(B > 0 && n > 0 && ld >= n, "bad shape");
+  TRB_CHECK_ARG(f->kind >= 0 && f->kind <= TRB_ABS_LIKELIHOOD, "unknown factor kind");
+  TRB_CHECK_ARG(!needs_y(f->kind) || y, "likelihood needs y");
+  k_factor_posterior<<<B, kEwThreads, 0, (cudaStream_t)stream>>>(*f, n, ld, a, a_mode, b, y, r, v,
+                                                                  v_mode);
+  TRB_CHECK_LAUNCH();
+  return TRB_OK;
+}
+
+extern "C" int trb_factor_log_partition(const trb_factor* f, int B, int n, int ld,
+                                        const double* a, int a_mode, const double* b,
+                                        const double* y, double* A, int A_mode, void* stream) {
+  TRB_CHECK_ARG(f && a && b && A, "null pointer");
+  TRB_CHECK_ARG(B > 0 && n > 0 && ld >= n, "bad shape");
+  TRB_CHECK_ARG(f->kind >= 0 && f->kind <= TRB_ABS_LIKELIHOOD, "unknown factor kind");
+  TRB_CHECK_ARG(!needs_y(f->kind) || y, "likelihood needs y");
+  k_factor_log_partition<<<B, kEwThreads, 0, (cudaStream_t)stream>>>(*f, n, ld, a, a_mode, b, y, A,
+                                                                      A_mode);
+  TRB_CHECK_LAUNCH();
+  return TRB_OK;
+}
+
+extern "C" int trb_factor_message(const trb_factor* f, int B, int n, int ld, const double* a_in,
+                                  const double* b_in, const double* y, double* a_io, double* b_io,
+                                  double* a_copy, double damping, double* scratch, int* flags,
+                                  const int* active, void* stream) {
+  TRB_CHECK_ARG(f && a_in && b_in && a_io && b_io && scratch, "null pointer");
+  TRB_CHECK_ARG(B > 0 && n > 0 && ld >= n, "bad shape");
+  TRB_CHECK_ARG(f->kind >= 0 && f->kind <= TRB_ABS_LIKELIHOOD, "unknown factor kind");
+  TRB_CHECK_ARG(!needs_y(f->kind) || y, "likelihood needs y");
+  k_factor_message<<<B, kEwThreads, 0, (cudaStream_t)stream>>>(
+      *f, n, ld, a_in, b_in, y, a_io, b_io, a_copy, damping, scratch, flags, active);
+  TRB_CHECK_LAUNCH();
+  return TRB_OK;
+}
+
+extern "C" int trb_truncated_normal(int n, const double* r0, const double* v0, double zmin,
+                                    double zmax, double* mean, double* var, double* logZ,
+                                    double* proba, void* stream) {
+  TRB_CHECK_ARG(r0 && v0, "null pointer");
+  TRB_CHECK_ARG(n > 0, "bad shape");
+  TRB_CHECK_ARG(zmin < zmax, "zmin must be < zmax");  // truncated_normal.py:236
+  k_truncated_normal<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(n, r0, v0, zmin, zmax, mean,
+                                                                        var, logZ, proba);
+  TRB_CHECK_LAUNCH();
+  return TRB_OK;
+}
+
+extern "C" int trb_posterior_rv(int B, int n, int ld, const double* a1, const double* b1,
+                                const double* a2, const double* b2, double* r, double* v,
+                                void* stream) {
+  TRB_CHECK_ARG(a1 && b1 && a2 && b2 && r && v, "null pointer");
+  TRB_CHECK_ARG(B > 0 && n > 0 && ld >= n, "bad shape");
+  k_posterior_rv<<<B, kEwThreads, 0, (cudaStream_t)stream>>>(n, ld, a1, b1, a2, b2, r, v);
+  TRB_CHECK_LAUNCH();
+  return TRB_OK;
+}

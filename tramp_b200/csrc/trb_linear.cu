@@ -1,0 +1,612 @@
+// LinearChannel in thin-SVD form: batched, HBM-bound FP64 GEMVs.
+//
+// reference: channels/linear/linear_channel.py:69-89 (compute_backward_mean /
+// compute_forward_mean) streams U, V (full), the dense S and W -- nine GEMVs
+// per iteration.  Here each instance's operators are stored as rows of
+// singular vectors (Vt[R, ldn], Ut[R, ldm]) and each is streamed ONCE per use:
+//   project:  t[i]  = <A[i, :], vec>            (U.T @ bx, V.T @ bz; :72-73)
+//   expand :  out[j] = sum_i coef[i] * A[i, j]   (V @ rz_svd, U-side of W @ rz; :78, :88)
+// Both walk the SAME partition of the B*R global row space: worker (CTA) k owns
+// the contiguous rows [k*T/G, (k+1)*T/G), so every SM streams an equal,
+// contiguous slab of HBM regardless of how instances fall on SMs.
+//
+// Two implementations, selected by `impl`:
+//   1  LDG : plain 16-byte streaming loads (no shared-memory staging)
+//   2  TMA : producer warp issues cp.async.bulk (1-D TMA) into a shared-memory
+//            ring guarded by mbarriers; 8 consumer warps own column slices
+//   0  default = TMA when the shape allows it, else LDG
+#include "trb_common.cuh"
+
+using namespace trb;
+
+namespace {
+
+constexpr int kMinRowsPerCta = 8;
+
+// ------------------------------------------------------------------ geometry
+struct Segment {
+  int b, i0, i1;
+};
+
+// Iterate the instance segments of worker range [g, g1); returns false when done.
+__device__ __forceinline__ bool next_segment(int64_t& g, int64_t g1, int R, Segment& s) {
+  if (g >= g1) return false;
+  s.b = (int)(g / R);
+  s.i0 = (int)(g - (int64_t)s.b * R);
+  const int64_t room = g1 - g;
+  s.i1 = (room < (int64_t)(R - s.i0)) ? (int)(s.i0 + room) : R;
+  g += (s.i1 - s.i0);
+  return true;
+}
+
+// =============================================================== LDG kernels
+constexpr int kLdgThreads = 512;
+
+// project: one warp per row, vec staged in shared memory per instance.
+__global__ void __launch_bounds__(kLdgThreads)
+k_project_ldg(const double* __restrict__ A, int64_t strideA, int R, int n, int ld, int B,
+              const double* __restrict__ vec, int ldvec, double* __restrict__ t,
+              const int* __restrict__ active) {
+  extern __shared__ __align__(16) double sh_vec[];  // ld doubles
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+  const int64_t T = (int64_t)B * R, G = gridDim.x;
+  int64_t g = part_begin(blockIdx.x, T, G);
+  const int64_t g1 = part_begin(blockIdx.x + 1, T, G);
+  Segment s;
+  const int npair = ld >> 1;
+  while (next_segment(g, g1, R, s)) {
+    if (active && !active[s.b]) continue;
+    __syncthreads();  // previous segment done with sh_vec
+    for (int j = threadIdx.x; j < ld; j += blockDim.x)
+      sh_vec[j] = (j < n) ? vec[(size_t)s.b * ldvec + j] : 0.0;
+    __syncthreads();
+    const double* Ab = A + (size_t)s.b * strideA;
+    const double2* xv = reinterpret_cast<const double2*>(sh_vec);
+    for (int i = s.i0 + 2 * warp; i < s.i1; i += 2 * nwarp) {
+      const bool two = (i + 1 < s.i1);
+      const double* r0 = Ab + (size_t)i * ld;
+      const double* r1 = two ? r0 + ld : r0;
+      double acc0 = 0.0, acc1 = 0.0;
+      int p = lane;
+      for (; p + 96 < npair; p += 128) {
+        double2 a0[4], a1[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          a0[u] = ldg_stream(r0 + 2 * (p + 32 * u));
+          a1[u] = ldg_stream(r1 + 2 * (p + 32 * u));
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const double2 x = xv[p + 32 * u];
+          acc0 = fma(a0[u].x, x.x, acc0);
+          acc0 = fma(a0[u].y, x.y, acc0);
+          acc1 = fma(a1[u].x, x.x, acc1);
+          acc1 = fma(a1[u].y, x.y, acc1);
+        }
+      }
+      for (; p < npair; p += 32) {
+        const double2 a0 = ldg_stream(r0 + 2 * p);
+        const double2 a1 = ldg_stream(r1 + 2 * p);
+        const double2 x = xv[p];
+        acc0 = fma(a0.x, x.x, acc0);
+        acc0 = fma(a0.y, x.y, acc0);
+        acc1 = fma(a1.x, x.x, acc1);
+        acc1 = fma(a1.y, x.y, acc1);
+      }
+      acc0 = warp_sum(acc0);
+      acc1 = warp_sum(acc1);
+      if (lane == 0) {
+        t[(size_t)s.b * R + i] = acc0;
+        if (two) t[(size_t)s.b * R + i + 1] = acc1;
+      }
+    }
+  }
+}
+
+// expand: thread owns NB column pairs for the whole segment; no reduction
+// until the segment ends, then one plain store per column into the slot.
+template <int NB>
+__global__ void __launch_bounds__(kLdgThreads)
+k_expand_ldg(const double* __restrict__ A, int64_t strideA, int R, int ld, int B,
+             const double* __restrict__ coef, double* __restrict__ part, int nslots,
+             const int* __restrict__ active) {
+  constexpr int UR = (NB >= 8) ? 2 : (16 / NB > 8 ? 8 : 16 / NB);  // rows in flight
+  const int64_t T = (int64_t)B * R, G = gridDim.x;
+  int64_t g = part_begin(blockIdx.x, T, G);
+  const int64_t g1 = part_begin(blockIdx.x + 1, T, G);
+  const int npair = ld >> 1;
+  Segment s;
+  while (next_segment(g, g1, R, s)) {
+    if (active && !active[s.b]) continue;
+    const double* Ab = A + (size_t)s.b * strideA;
+    const double* cb = coef + (size_t)s.b * R;
+    double2 acc[NB];
+#pragma unroll
+    for (int k = 0; k < NB; ++k) acc[k] = make_double2(0.0, 0.0);
+    int i = s.i0;
+    for (; i + UR <= s.i1; i += UR) {
+      double2 a[UR][NB];
+      double c[UR];
+#pragma unroll
+      for (int u = 0; u < UR; ++u) {
+        c[u] = __ldg(cb + i + u);
+#pragma unroll
+        for (int k = 0; k < NB; ++k) {
+          const int p = threadIdx.x + k * kLdgThreads;
+          a[u][k] = (p < npair) ? ldg_stream(Ab + (size_t)(i + u) * ld + 2 * p)
+                                : make_double2(0.0, 0.0);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < UR; ++u)
+#pragma unroll
+        for (int k = 0; k < NB; ++k) {
+          acc[k].x = fma(c[u], a[u][k].x, acc[k].x);
+          acc[k].y = fma(c[u], a[u][k].y, acc[k].y);
+        }
+    }
+    for (; i < s.i1; ++i) {
+      const double c = __ldg(cb + i);
+#pragma unroll
+      for (int k = 0; k < NB; ++k) {
+        const int p = threadIdx.x + k * kLdgThreads;
+        if (p < npair) {
+          const double2 a = ldg_stream(Ab + (size_t)i * ld + 2 * p);
+          acc[k].x = fma(c, a.x, acc[k].x);
+          acc[k].y = fma(c, a.y, acc[k].y);
+        }
+      }
+    }
+    const int slot = (int)(blockIdx.x - part_owner((int64_t)s.b * R, T, G));
+    double* out = part + ((size_t)s.b * nslots + slot) * ld;
+#pragma unroll
+    for (int k = 0; k < NB; ++k) {
+      const int p = threadIdx.x + k * kLdgThreads;
+      if (p < npair) *reinterpret_cast<double2*>(out + 2 * p) = acc[k];
+    }
+  }
+}
+
+// =============================================================== TMA kernels
+// 8 consumer warps (256 threads) + 1 producer warp.  Consumer thread t owns the
+// column pairs {t + 256*k, k < NB}.  A ring stage holds RC = max(1, 8/NB)
+// whole rows (<= 32 KiB, 64 KiB for NB = 16).
+constexpr int kConsumers = 256;
+constexpr int kTmaThreads = kConsumers + 32;
+constexpr int kMaxStages = 8;
+constexpr int kGroupRows = 8;  // project: rows reduced per block-level reduction
+
+template <int NB>
+struct TmaCfg {
+  static constexpr int RC = (NB >= 8) ? 1 : 8 / NB;
+};
+
+__device__ __forceinline__ void consumer_bar() {
+  asm volatile("bar.sync 1, %0;" ::"n"(kConsumers) : "memory");
+}
+
+template <int NB, bool EXPAND>
+__global__ void __launch_bounds__(kTmaThreads, 1)
+k_gemv_tma(const double* __restrict__ A, int64_t strideA, int R, int n, int ld, int B,
+           const double* __restrict__ vec, int ldvec,  // project: input vector; expand: coef [B,R]
+           double* __restrict__ out, int nslots,       // project: t [B,R]; expand: part
+           const int* __restrict__ active, int nstages, int stage_doubles) {
+  constexpr int RC = TmaCfg<NB>::RC;
+  extern __shared__ __align__(128) double ring[];  // nstages * stage_doubles
+  __shared__ __align__(8) uint64_t full_bar[kMaxStages];
+  __shared__ __align__(8) uint64_t empty_bar[kMaxStages];
+  __shared__ double red[2][kConsumers / 32][kGroupRows];
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) {
+    for (int s = 0; s < nstages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], kConsumers / 32);
+    }
+    fence_mbar_init();
+  }
+  __syncthreads();
+
+  const int64_t T = (int64_t)B * R, G = gridDim.x;
+  int64_t g = part_begin(blockIdx.x, T, G);
+  const int64_t g1 = part_begin(blockIdx.x + 1, T, G);
+  const int npair = ld >> 1;
+  Segment s;
+  int stage = 0;
+  uint32_t phase = 0;
+
+  if (warp == kConsumers / 32) {
+    // ------------------------------------------------------------ producer
+    if (lane == 0) {
+      while (next_segment(g, g1, R, s)) {
+        if (active && !active[s.b]) continue;
+        const double* Ab = A + (size_t)s.b * strideA;
+        for (int i = s.i0; i < s.i1; i += RC) {
+          const int rows = (s.i1 - i < RC) ? (s.i1 - i) : RC;
+          const uint32_t bytes = (uint32_t)rows * (uint32_t)ld * 8u;
+          mbar_wait(&empty_bar[stage], phase ^ 1u);
+          mbar_arrive_expect_tx(&full_bar[stage], bytes);
+          bulk_g2s(ring + (size_t)stage * stage_doubles, Ab + (size_t)i * ld, bytes,
+                   &full_bar[stage]);
+          if (++stage == nstages) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+      }
+    }
+    return;
+  }
+
+  // -------------------------------------------------------------- consumers
+  int red_buf = 0;
+  while (next_segment(g, g1, R, s)) {
+    if (active && !active[s.b]) continue;
+    if constexpr (!EXPAND) {
+      // ---- project: x slice in registers, 8-row groups, block reduction
+      double2 x[NB];
+#pragma unroll
+      for (int k = 0; k < NB; ++k) {
+        const int c = 2 * (tid + k * kConsumers);
+        const double* vp = vec + (size_t)s.b * ldvec;
+        x[k].x = (c < n) ? vp[c] : 0.0;
+        x[k].y = (c + 1 < n) ? vp[c + 1] : 0.0;
+      }
+      for (int ig = s.i0; ig < s.i1; ig += kGroupRows) {
+        double acc[kGroupRows];
+#pragma unroll
+        for (int q = 0; q < kGroupRows; ++q) acc[q] = 0.0;
+#pragma unroll
+        for (int c = 0; c < kGroupRows / RC; ++c) {
+          const int i = ig + c * RC;
+          if (i < s.i1) {
+            const int rows = (s.i1 - i < RC) ? (s.i1 - i) : RC;
+            mbar_wait(&full_bar[stage], phase);
+            const double2* st =
+                reinterpret_cast<const double2*>(ring + (size_t)stage * stage_doubles);
+#pragma unroll
+            for (int rr = 0; rr < RC; ++rr) {
+              if (rr < rows) {
+#pragma unroll
+                for (int k = 0; k < NB; ++k) {
+                  const int p = tid + k * kConsumers;
+                  if (p < npair) {
+                    const double2 a = st[rr * npair + p];
+                    acc[c * RC + rr] = fma(a.x, x[k].x, acc[c * RC + rr]);
+                    acc[c * RC + rr] = fma(a.y, x[k].y, acc[c * RC + rr]);
+                  }
+                }
+              }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty_bar[stage]);
+            if (++stage == nstages) {
+              stage = 0;
+              phase ^= 1u;
+            }
+          }
+        }
+#pragma unroll
+        for (int q = 0; q < kGroupRows; ++q) acc[q] = warp_sum(acc[q]);
+        if (lane == 0) {
+#pragma unroll
+          for (int q = 0; q < kGroupRows; ++q) red[red_buf][warp][q] = acc[q];
+        }
+        consumer_bar();
+        if (tid < kGroupRows && ig + tid < s.i1) {
+          double tot = 0.0;
+#pragma unroll
+          for (int w = 0; w < kConsumers / 32; ++w) tot += red[red_buf][w][tid];
+          out[(size_t)s.b * R + ig + tid] = tot;
+        }
+        red_buf ^= 1;
+      }
+    } else {
+      // ---- expand: column accumulators in registers for the whole segment
+      double2 acc[NB];
+#pragma unroll
+      for (int k = 0; k < NB; ++k) acc[k] = make_double2(0.0, 0.0);
+      const double* cb = vec + (size_t)s.b * R;
+      for (int i = s.i0; i < s.i1; i += RC) {
+        const int rows = (s.i1 - i < RC) ? (s.i1 - i) : RC;
+        double c[RC];
+#pragma unroll
+        for (int rr = 0; rr < RC; ++rr) c[rr] = (rr < rows) ? __ldg(cb + i + rr) : 0.0;
+        mbar_wait(&full_bar[stage], phase);
+        const double2* st = reinterpret_cast<const double2*>(ring + (size_t)stage * stage_doubles);
+#pragma unroll
+        for (int rr = 0; rr < RC; ++rr) {
+          if (rr < rows) {
+#pragma unroll
+            for (int k = 0; k < NB; ++k) {
+              const int p = tid + k * kConsumers;
+              if (p < npair) {
+                const double2 a = st[rr * npair + p];
+                acc[k].x = fma(c[rr], a.x, acc[k].x);
+                acc[k].y = fma(c[rr], a.y, acc[k].y);
+              }
+            }
+          }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty_bar[stage]);
+        if (++stage == nstages) {
+          stage = 0;
+          phase ^= 1u;
+        }
+      }
+      const int slot = (int)(blockIdx.x - part_owner((int64_t)s.b * R, T, G));
+      double* o = out + ((size_t)s.b * nslots + slot) * ld;
+#pragma unroll
+      for (int k = 0; k < NB; ++k) {
+        const int p = tid + k * kConsumers;
+        if (p < npair) *reinterpret_cast<double2*>(o + 2 * p) = acc[k];
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------- small ops
+__global__ void __launch_bounds__(256)
+k_reduce_slots(int R, int n, int ld, int B, int G, int nslots, const double* __restrict__ part,
+               const double* __restrict__ add, const double* __restrict__ add_div,
+               double* __restrict__ out) {
+  const int b = blockIdx.x;
+  const int64_t T = (int64_t)B * R;
+  const int kf = (int)part_owner((int64_t)b * R, T, G);
+  const int kl = (int)part_owner((int64_t)b * R + R - 1, T, G);
+  const int ns = kl - kf + 1;
+  const double div = add ? add_div[b] : 1.0;
+  for (int j = threadIdx.x; j < n; j += blockDim.x) {
+    double v = 0.0;
+    for (int sl = 0; sl < ns; ++sl) v += part[((size_t)b * nslots + sl) * ld + j];
+    if (add) v = add[(size_t)b * ld + j] / div + v;
+    out[(size_t)b * ld + j] = v;
+  }
+}
+
+// linear_channel.py:58-67 (compute_n_eff), :74 (resolvent), :91-105 (variances)
+__global__ void __launch_bounds__(256)
+k_lin_rescale(int dir, int R, int Nz, int Nx, int rank, const double* __restrict__ s,
+              const double* __restrict__ s2, int64_t stride_s, const double* __restrict__ az_arr,
+              const double* __restrict__ ax_arr, const double* __restrict__ tz,
+              const double* __restrict__ tx, double* __restrict__ coef, double* __restrict__ v_out,
+              const int* __restrict__ active) {
+  __shared__ double sh[33];
+  const int b = blockIdx.x;
+  if (active && !active[b]) return;
+  const double az = az_arr[b], ax = ax_arr[b];
+  const double* sb = s + (size_t)b * stride_s;
+  const double* s2b = s2 + (size_t)b * stride_s;
+  const size_t off = (size_t)b * R;
+  // ---- variance
+  double az_v = az;
+  if (dir == 1) az_v = (az != az) ? az : fmax(1e-11, az);  // :94 np.maximum(1e-11, az)
+  double v;
+  if (dir == 0 && ax == 0) {  // :100-102
+    double part = 0.0;
+    for (int i = threadIdx.x; i < rank; i += blockDim.x) part += s2b[i];
+    const double s_mean = block_sum(part, sh) / rank;
+    v = s_mean * rank / (Nx * az);
+  } else {
+    double n_eff;
+    if (ax == 0) {  // :60-62
+      n_eff = 0.;
+    } else {
+      const double ratio = az_v / ax;
+      if (ratio == 0) {  // :63-65
+        n_eff = (double)rank / Nz;
+      } else {  // :66-67
+        double part = 0.0;
+        for (int i = threadIdx.x; i < rank; i += blockDim.x) part += s2b[i] / (ratio + s2b[i]);
+        n_eff = block_sum(part, sh) / Nz;
+      }
+    }
+    if (dir == 0) {
+      const double alpha = (double)Nx / Nz;
+      v = n_eff / (alpha * ax);  // :103-105
+    } else {
+      v = (1 - n_eff) / az_v;  // :95-97
+    }
+  }
+  if (threadIdx.x == 0) v_out[b] = v;
+  // ---- coefficients in the singular basis
+  const bool null_space = (R < Nz);
+  for (int i = threadIdx.x; i < R; i += blockDim.x) {
+    const double si = sb[i], s2i = s2b[i];
+    const double res = 1 / (az + ax * s2i);  // :74
+    const double tzi = tz[off + i], txi = tx[off + i];
+    double c;
+    if (dir == 0) {
+      c = si * (res * (tzi + si * txi));
+    } else if (!null_space) {
+      c = res * (tzi + si * txi);
+    } else {
+      // res - 1/az = -(ax*s2/az)*res, applied to tz; the bz/az term is added
+      // by the consumer of the expansion
+      c = res * (si * txi - (ax * s2i / az) * tzi);
+    }
+    coef[off + i] = c;
+  }
+}
+
+int pick_nb(int ld, int threads, int max_nb) {
+  const int npair = ld >> 1;
+  int nb = 1;
+  while (nb * threads < npair) nb <<= 1;
+  return (nb <= max_nb) ? nb : -1;
+}
+
+struct TmaPlan {
+  int nb, stages, stage_doubles;
+  size_t smem;
+};
+
+bool plan_tma(int ld, TmaPlan& p) {
+  p.nb = pick_nb(ld, kConsumers, 16);
+  if (p.nb < 0) return false;
+  const int rc = (p.nb >= 8) ? 1 : 8 / p.nb;
+  p.stage_doubles = ((rc * ld + 15) / 16) * 16;  // keep every stage 128-byte aligned
+  const size_t budget = 200 * 1024;
+  int st = (int)(budget / ((size_t)p.stage_doubles * 8));
+  if (st > kMaxStages) st = kMaxStages;
+  if (st < 2) return false;
+  p.stages = st;
+  p.smem = (size_t)st * p.stage_doubles * 8;
+  return true;
+}
+
+template <int NB, bool EXPAND>
+int launch_tma(const TmaPlan& p, int G, const double* A, int64_t strideA, int R, int n, int ld,
+               int B, const double* vec, int ldvec, double* out, int nslots, const int* active,
+               cudaStream_t st) {
+  auto kern = k_gemv_tma<NB, EXPAND>;
+  static bool configured = false;  // per instantiation
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         200 * 1024);
+    if (e != cudaSuccess)
+      return trb_set_error(TRB_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    configured = true;
+  }
+  kern<<<G, kTmaThreads, p.smem, st>>>(A, strideA, R, n, ld, B, vec, ldvec, out, nslots, active,
+                                       p.stages, p.stage_doubles);
+  return TRB_OK;
+}
+
+template <bool EXPAND>
+int dispatch_tma(const TmaPlan& p, int G, const double* A, int64_t strideA, int R, int n, int ld,
+                 int B, const double* vec, int ldvec, double* out, int nslots, const int* active,
+                 cudaStream_t st) {
+  switch (p.nb) {
+    case 1: return launch_tma<1, EXPAND>(p, G, A, strideA, R, n, ld, B, vec, ldvec, out, nslots, active, st);
+    case 2: return launch_tma<2, EXPAND>(p, G, A, strideA, R, n, ld, B, vec, ldvec, out, nslots, active, st);
+    case 4: return launch_tma<4, EXPAND>(p, G, A, strideA, R, n, ld, B, vec, ldvec, out, nslots, active, st);
+    case 8: return launch_tma<8, EXPAND>(p, G, A, strideA, R, n, ld, B, vec, ldvec, out, nslots, active, st);
+    case 16: return launch_tma<16, EXPAND>(p, G, A, strideA, R, n, ld, B, vec, ldvec, out, nslots, active, st);
+  }
+  return trb_set_error(TRB_ERR_UNSUPPORTED, "no TMA GEMV instantiation for NB=%d", p.nb);
+}
+
+}  // namespace
+
+trb_expand_geom trb_expand_geometry(int B, int R) {
+  trb_expand_geom g;
+  const int64_t T = (int64_t)B * R;
+  int sm = trb_sm_count_cached();
+  if (sm <= 0) sm = 1;
+  int64_t G = sm;
+  const int64_t cap = T / kMinRowsPerCta;
+  if (G > cap) G = cap;
+  if (G < 1) G = 1;
+  g.G = (int)G;
+  int ns = 1;
+  for (int b = 0; b < B; ++b) {
+    const int kf = (int)part_owner((int64_t)b * R, T, G);
+    const int kl = (int)part_owner((int64_t)b * R + R - 1, T, G);
+    if (kl - kf + 1 > ns) ns = kl - kf + 1;
+  }
+  g.nslots = ns;
+  return g;
+}
+
+extern "C" int trb_lin_expand_slots(int B, int R) {
+  if (B <= 0 || R <= 0) return trb_set_error(TRB_ERR_INVALID, "trb_lin_expand_slots: bad shape");
+  return trb_expand_geometry(B, R).nslots;
+}
+
+static int check_gemv_args(const double* A, int R, int n, int ld, int B, const void* x,
+                           const void* y) {
+  TRB_CHECK_ARG(A && x && y, "null pointer");
+  TRB_CHECK_ARG(B > 0 && R > 0 && n > 0 && ld >= n, "bad shape");
+  TRB_CHECK_ARG(ld % 2 == 0, "ld must be even (16-byte rows)");
+  TRB_CHECK_ARG((reinterpret_cast<uintptr_t>(A) & 15) == 0, "operator must be 16-byte aligned");
+  return TRB_OK;
+}
+
+extern "C" int trb_lin_project(const double* A, int64_t strideA, int R, int n, int ld, int B,
+                               const double* vec, int ldvec, double* t, const int* active,
+                               int impl, void* stream) {
+  int rc = check_gemv_args(A, R, n, ld, B, vec, t);
+  if (rc) return rc;
+  TRB_CHECK_ARG(strideA % 2 == 0, "strideA must be even");
+  TRB_CHECK_ARG(ldvec >= n, "ldvec < n");
+  cudaStream_t st = (cudaStream_t)stream;
+  const trb_expand_geom geo = trb_expand_geometry(B, R);
+  TmaPlan p;
+  const bool tma_ok = plan_tma(ld, p);
+  if (impl == 0) impl = tma_ok ? 2 : 1;
+  if (impl == 2) {
+    if (!tma_ok) return trb_set_error(TRB_ERR_UNSUPPORTED, "trb_lin_project: ld=%d too large for the TMA ring", ld);
+    rc = dispatch_tma<false>(p, geo.G, A, strideA, R, n, ld, B, vec, ldvec, t, 0, active, st);
+    if (rc) return rc;
+  } else {
+    const size_t smem = (size_t)ld * 8;
+    if (smem > 200 * 1024)
+      return trb_set_error(TRB_ERR_UNSUPPORTED, "trb_lin_project: ld=%d too large", ld);
+    static bool configured = false;
+    if (!configured) {
+      cudaFuncSetAttribute(k_project_ldg, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+      configured = true;
+    }
+    k_project_ldg<<<geo.G, kLdgThreads, smem, st>>>(A, strideA, R, n, ld, B, vec, ldvec, t, active);
+  }
+  TRB_CHECK_LAUNCH();
+  return TRB_OK;
+}
+
+extern "C" int trb_lin_expand(const double* A, int64_t strideA, int R, int n, int ld, int B,
+                              const double* coef, double* part, const int* active, int impl,
+                              void* stream) {
+  int rc = check_gemv_args(A, R, n, ld, B, coef, part);
+  if (rc) return rc;
+  TRB_CHECK_ARG(strideA % 2 == 0, "strideA must be even");
+  cudaStream_t st = (cudaStream_t)stream;
+  const trb_expand_geom geo = trb_expand_geometry(B, R);
+  TmaPlan p;
+  const bool tma_ok = plan_tma(ld, p);
+  if (impl == 0) impl = tma_ok ? 2 : 1;
+  if (impl == 2) {
+    if (!tma_ok) return trb_set_error(TRB_ERR_UNSUPPORTED, "trb_lin_expand: ld=%d too large for the TMA ring", ld);
+    rc = dispatch_tma<true>(p, geo.G, A, strideA, R, n, ld, B, coef, 0, part, geo.nslots, active, st);
+    if (rc) return rc;
+  } else {
+    const int nb = pick_nb(ld, kLdgThreads, 8);
+    switch (nb) {
+      case 1: k_expand_ldg<1><<<geo.G, kLdgThreads, 0, st>>>(A, strideA, R, ld, B, coef, part, geo.nslots, active); break;
+      case 2: k_expand_ldg<2><<<geo.G, kLdgThreads, 0, st>>>(A, strideA, R, ld, B, coef, part, geo.nslots, active); break;
+      case 4: k_expand_ldg<4><<<geo.G, kLdgThreads, 0, st>>>(A, strideA, R, ld, B, coef, part, geo.nslots, active); break;
+      case 8: k_expand_ldg<8><<<geo.G, kLdgThreads, 0, st>>>(A, strideA, R, ld, B, coef, part, geo.nslots, active); break;
+      default:
+        return trb_set_error(TRB_ERR_UNSUPPORTED, "trb_lin_expand: ld=%d too large", ld);
+    }
+  }
+  TRB_CHECK_LAUNCH();
+  return TRB_OK;
+}
+
+extern "C" int trb_lin_reduce_slots(int B, int R, int n, int ld, const double* part,
+                                    const double* add, const double* add_div, double* out,
+                                    void* stream) {
+  TRB_CHECK_ARG(part && out, "null pointer");
+  TRB_CHECK_ARG(!add || add_div, "add needs add_div");
+  TRB_CHECK_ARG(B > 0 && R > 0 && n > 0 && ld >= n, "bad shape");
+  const trb_expand_geom geo = trb_expand_geometry(B, R);
+  k_reduce_slots<<<B, 256, 0, (cudaStream_t)stream>>>(R, n, ld, B, geo.G, geo.nslots, part, add,
+                                                       add_div, out);
+  TRB_CHECK_LAUNCH();
+  return TRB_OK;
+}
+
+extern "C" int trb_lin_rescale(int dir, int B, int R, int Nz, int Nx, int rank, const double* s,
+                               const double* s2, int64_t stride_s, const double* az,
+                               const double* ax, const double* tz, const double* tx, double* coef,
+                               double* v, const int* active, void* stream) {
+  TRB_CHECK_ARG(s && s2 && az && ax && tz && tx && coef && v, "null pointer");
+  TRB_CHECK_ARG(dir == 0 || dir == 1, "dir must be 0 or 1");
+  TRB_CHECK_ARG(B > 0 && R > 0 && R <= Nz && R <= Nx && rank >= 0 && rank <= R, "bad shape");
+  k_lin_rescale<<<B, 256, 0, (cudaStream_t)stream>>>(dir, R, Nz, Nx, rank, s, s2, stride_s, az, ax,
+                                                      tz, tx, coef, v, active);
+  TRB_CHECK_LAUNCH();
+  return TRB_OK;
+}

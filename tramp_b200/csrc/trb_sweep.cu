@@ -1,0 +1,264 @@
+// Device-resident EP sweep for the chain  prior -> x -> LinearChannel -> z -> likelihood.
+//
+// reference: algos/message_passing.py:330-357 (iterate), :249-269 (forward /
+// backward pass, update_variables), :70-127 (constant damping), :187-209 (NaN
+// check); algos/callbacks.py:250-286 (EarlyStoppingEP); algos/metrics.py:5-14.
+//
+// One iteration = 9 launches on one stream, B instances in lock step, no host
+// round trip (edge numbering e1..e8 as in SURVEY 3.3):
+//   F1  factor_message(prior)   e8 -> e1 (=e2)
+//   P1  project  V_R^T b2       -> tz
+//   S1  rescale fwd             -> coef, vx(lin)
+//   P2  expand   U_R coef       -> part
+//   Z   z_update: e3 (=e4), likelihood e5 (=e6), posterior of z
+//   P3  project  U_R^T b6       -> tx        (reused by the next iteration's S1)
+//   S2  rescale bwd             -> coef, vz(lin)
+//   P4  expand   V_R coef       -> part
+//   X   x_update: e7 (=e8), posterior of x, MSE / tolerance records, early stop
+// Each operator is streamed exactly twice per iteration (once as A^T x, once
+// as A c): 16*R*(N+M) bytes per instance-iteration.
+#include "trb_moments.cuh"
+
+using namespace trb;
+
+namespace {
+
+constexpr int kUpThreads = 512;
+
+struct SlotInfo {
+  int ns;
+};
+
+__device__ __forceinline__ int slots_of(int b, int R, int B, int G) {
+  const int64_t T = (int64_t)B * R;
+  const int kf = (int)part_owner((int64_t)b * R, T, G);
+  const int kl = (int)part_owner((int64_t)b * R + R - 1, T, G);
+  return kl - kf + 1;
+}
+
+// stats[b*4 + {0,1}] = sum (r_new - r_old)^2, sum r_new^2 for z; {2,3} for x
+__global__ void __launch_bounds__(kUpThreads)
+k_z_update(trb_sweep sw, int G, int first, double* __restrict__ stats) {
+  __shared__ double sh[33];
+  __shared__ int sh_flag;
+  const int b = blockIdx.x;
+  if (sw.active && !sw.active[b]) return;
+  const int B = sw.B, M = sw.M, ld = sw.ldm;
+  const size_t off = (size_t)b * ld;
+  double* ea = sw.edge_a;
+  const double a6 = ea[5 * B + b];
+  const double a3n = clip_a_new(sw.vlin[b], a6, sw.lin_amin, sw.lin_amax);  // base_channel.py:9-12
+  const double a3 = damp(sw.damp3, ea[2 * B + b], a3n);
+  const double ainv3 = a6 + a3n;
+  const int ns = slots_of(b, sw.R, B, G);
+  const double* part = sw.part + (size_t)b * sw.nslots * ld;
+  const double* b6 = (first && sw.b6_init) ? sw.b6_init : sw.b5;
+  const bool const_lik = factor_is_constant_message(sw.lik.kind);
+  int flag = 0;
+  double vsum = 0.0;
+  for (int i = threadIdx.x; i < M; i += blockDim.x) {
+    double rx = 0.0;
+    for (int sl = 0; sl < ns; ++sl) rx += part[(size_t)sl * ld + i];
+    const double b3n = rx * ainv3 - b6[off + i];
+    if (b3n != b3n) flag |= TRB_FLAG_NAN_B;
+    const double b3v = damp(sw.damp3, sw.b3[off + i], b3n);
+    sw.b3[off + i] = b3v;
+    if (!const_lik) {
+      const RV m = factor_moments(sw.lik, a3, b3v, sw.y[off + i]);
+      sw.scr_m[off + i] = m.r;
+      vsum += m.v;
+    }
+  }
+  double a5n;
+  if (const_lik) {
+    a5n = sw.lik.p0;  // gaussian_likelihood.py:68-71
+  } else {
+    const double v = block_sum(vsum, sh) / M;
+    a5n = clip_a_new(v, a3, sw.lik.amin, sw.lik.amax);  // base_likelihood.py:25-28
+  }
+  const double a5 = damp(sw.damp5, ea[4 * B + b], a5n);
+  const double ainv5 = a3 + a5n;
+  const double a_hat = a3 + a5;
+  double d2 = 0.0, n2 = 0.0;
+  for (int i = threadIdx.x; i < M; i += blockDim.x) {
+    const double b3v = sw.b3[off + i];
+    const double b5n = const_lik ? sw.y[off + i] * sw.lik.p0 : sw.scr_m[off + i] * ainv5 - b3v;
+    if (b5n != b5n) flag |= TRB_FLAG_NAN_B;
+    const double b5v = damp(sw.damp5, sw.b5[off + i], b5n);
+    sw.b5[off + i] = b5v;
+    const double rnew = (b3v + b5v) / a_hat;  // base.py:152-161
+    const double rold = sw.rz[off + i];
+    sw.rz[off + i] = rnew;
+    d2 += (rnew - rold) * (rnew - rold);
+    n2 += rnew * rnew;
+  }
+  d2 = block_sum(d2, sh);
+  n2 = block_sum(n2, sh);
+  if (a3n != a3n || a5n != a5n) flag |= TRB_FLAG_NAN_A;
+  if (a3n < 0 || a5n < 0) flag |= TRB_FLAG_NEG_A;
+  const int all = block_or(flag, &sh_flag);
+  if (threadIdx.x == 0) {
+    ea[2 * B + b] = a3;
+    ea[3 * B + b] = a3;  // e4 = e3 (sub_variables.py:21-25)
+    ea[4 * B + b] = a5;
+    ea[5 * B + b] = a5;  // e6 = e5 (sub_variables.py:27-31)
+    sw.vz[b] = 1. / a_hat;
+    stats[b * 4 + 0] = d2;
+    stats[b * 4 + 1] = n2;
+    if (all) atomicOr(&sw.flags[b], all);
+  }
+}
+
+__global__ void __launch_bounds__(kUpThreads)
+k_x_update(trb_sweep sw, int G, int it, double* __restrict__ stats) {
+  __shared__ double sh[33];
+  __shared__ int sh_flag;
+  const int b = blockIdx.x;
+  if (sw.active && !sw.active[b]) return;
+  const int B = sw.B, N = sw.N, ld = sw.ldn;
+  const size_t off = (size_t)b * ld;
+  double* ea = sw.edge_a;
+  const double a1 = ea[1 * B + b];  // e2 (= e1)
+  const double a7n = clip_a_new(sw.vlin[b], a1, sw.lin_amin, sw.lin_amax);  // base_channel.py:14-17
+  const double a7 = damp(sw.damp7, ea[6 * B + b], a7n);
+  const double ainv7 = a1 + a7n;
+  const double a_hat = a1 + a7;
+  const int ns = slots_of(b, sw.R, B, G);
+  const double* part = sw.part + (size_t)b * sw.nslots * ld;
+  const bool null_space = sw.R < N;
+  int flag = 0;
+  double d2 = 0.0, n2 = 0.0, e_pos = 0.0, e_neg = 0.0;
+  for (int i = threadIdx.x; i < N; i += blockDim.x) {
+    double rzv = 0.0;
+    for (int sl = 0; sl < ns; ++sl) rzv += part[(size_t)sl * ld + i];
+    const double b1v = sw.b1[off + i];
+    if (null_space) rzv = b1v / a1 + rzv;
+    const double b7n = rzv * ainv7 - b1v;
+    if (b7n != b7n) flag |= TRB_FLAG_NAN_B;
+    const double b7v = damp(sw.damp7, sw.b7[off + i], b7n);
+    sw.b7[off + i] = b7v;
+    const double rnew = (b1v + b7v) / a_hat;
+    const double rold = sw.rx[off + i];
+    sw.rx[off + i] = rnew;
+    d2 += (rnew - rold) * (rnew - rold);
+    n2 += rnew * rnew;
+    if (sw.x_true) {
+      const double xt = sw.x_true[off + i];
+      e_pos += (rnew - xt) * (rnew - xt);  // metrics.py:5-6
+      e_neg += (rnew + xt) * (rnew + xt);  // metrics.py:9-14
+    }
+  }
+  d2 = block_sum(d2, sh);
+  n2 = block_sum(n2, sh);
+  if (sw.x_true) {
+    e_pos = block_sum(e_pos, sh);
+    e_neg = block_sum(e_neg, sh);
+  }
+  if (a7n != a7n) flag |= TRB_FLAG_NAN_A;
+  if (a7n < 0) flag |= TRB_FLAG_NEG_A;
+  const int all = block_or(flag, &sh_flag);
+  if (threadIdx.x == 0) {
+    ea[6 * B + b] = a7;
+    ea[7 * B + b] = a7;  // e8 = e7
+    const double vx = 1. / a_hat;
+    sw.vx[b] = vx;
+    if (all) atomicOr(&sw.flags[b], all);
+    sw.n_iter[b] += 1;
+    const bool rec = it < sw.max_records;
+    if (rec && sw.rec_vx) sw.rec_vx[(size_t)it * B + b] = vx;
+    if (rec && sw.rec_vz) sw.rec_vz[(size_t)it * B + b] = sw.vz[b];
+    if (sw.x_true) {
+      const double mse = e_pos / N, mse_neg = e_neg / N;
+      if (rec && sw.rec_mse) sw.rec_mse[(size_t)it * B + b] = mse;
+      if (rec && sw.rec_smse) sw.rec_smse[(size_t)it * B + b] = fmin(mse, mse_neg);
+    }
+    // EarlyStoppingEP(ids="all"), callbacks.py:258-286: tol = rms(new-old)/rms(new),
+    // max over variables; needs a previous estimate, i.e. it > 0.
+    double tol = nan("");
+    if (it > 0) {
+      const double tol_x = sqrt(d2 / N) / sqrt(n2 / N);
+      const double tol_z = sqrt(stats[b * 4 + 0] / sw.M) / sqrt(stats[b * 4 + 1] / sw.M);
+      tol = (tol_z > tol_x) ? tol_z : tol_x;
+      if (sw.es_tol >= 0) {
+        if (tol < sw.es_tol) {
+          sw.active[b] = 0;
+          atomicOr(&sw.flags[b], TRB_FLAG_CONVERGED);
+        } else if (it > sw.es_wait_increase && tol > sw.es_max_increase) {
+          sw.active[b] = 0;
+          atomicOr(&sw.flags[b], TRB_FLAG_DIVERGED);
+        }
+      }
+    }
+    if (rec && sw.rec_tol) sw.rec_tol[(size_t)it * B + b] = tol;
+    if (all & (TRB_FLAG_NAN_A | TRB_FLAG_NAN_B)) sw.active[b] = 0;
+  }
+}
+
+}  // namespace
+
+#define TRB_TRY(expr)      \
+  do {                     \
+    int rc_ = (expr);      \
+    if (rc_) return rc_;   \
+  } while (0)
+
+extern "C" int trb_sweep_run(const trb_sweep* sw, int it0, int n_iter, int fresh, void* stream) {
+  TRB_CHECK_ARG(sw, "null sweep descriptor");
+  TRB_CHECK_ARG(sw->B > 0 && sw->N > 0 && sw->M > 0 && sw->R > 0, "bad shape");
+  TRB_CHECK_ARG(sw->R <= sw->N && sw->R <= sw->M, "R must be <= min(N, M)");
+  TRB_CHECK_ARG(sw->Vt && sw->Ut && sw->s && sw->s2 && sw->y, "null operator / observation");
+  TRB_CHECK_ARG(sw->edge_a && sw->b1 && sw->b3 && sw->b5 && sw->b7, "null message buffer");
+  TRB_CHECK_ARG(sw->rx && sw->rz && sw->vx && sw->vz, "null posterior buffer");
+  TRB_CHECK_ARG(sw->tz && sw->tx && sw->coef && sw->part && sw->scr_n && sw->scr_m && sw->vlin &&
+                    sw->stats,
+                "null scratch buffer");
+  TRB_CHECK_ARG(sw->active && sw->flags && sw->n_iter, "null status buffer");
+  TRB_CHECK_ARG(it0 >= 0 && n_iter >= 0, "bad iteration range");
+  const trb_expand_geom geo = trb_expand_geometry(sw->B, sw->R);
+  TRB_CHECK_ARG(sw->nslots >= geo.nslots, "nslots smaller than trb_lin_expand_slots(B, R)");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int B = sw->B;
+  double* ea = sw->edge_a;
+  // expand writes `geo.nslots`-strided slots; the update kernels read with sw->nslots
+  TRB_CHECK_ARG(sw->nslots == geo.nslots, "nslots must equal trb_lin_expand_slots(B, R)");
+  for (int k = 0; k < n_iter; ++k) {
+    const int it = it0 + k;
+    const int first = (fresh && k == 0) ? 1 : 0;
+    // F1: prior, reads e8, writes e1 and its pass-through copy e2
+    const double* b8 = (first && sw->b8_init) ? sw->b8_init : sw->b7;
+    TRB_TRY(trb_factor_message(&sw->prior, B, sw->N, sw->ldn, ea + 7 * B, b8, nullptr, ea + 0 * B,
+                               sw->b1, ea + 1 * B, sw->damp1, sw->scr_n, sw->flags, sw->active,
+                               stream));
+    // P1: tz = V_R^T b2
+    TRB_TRY(trb_lin_project(sw->Vt, sw->strideV, sw->R, sw->N, sw->ldn, B, sw->b1, sw->ldn, sw->tz,
+                            sw->active, sw->gemv_impl, stream));
+    if (first) {
+      // tx = U_R^T b6 for the initial e6 (later iterations reuse P3's result)
+      const double* b6 = sw->b6_init ? sw->b6_init : sw->b5;
+      TRB_TRY(trb_lin_project(sw->Ut, sw->strideU, sw->R, sw->M, sw->ldm, B, b6, sw->ldm, sw->tx,
+                              sw->active, sw->gemv_impl, stream));
+    }
+    // S1 + P2: rx = U_R [s res (tz + s tx)], forward variance
+    TRB_TRY(trb_lin_rescale(0, B, sw->R, sw->N, sw->M, sw->rank, sw->s, sw->s2, sw->stride_s,
+                            ea + 1 * B, ea + 5 * B, sw->tz, sw->tx, sw->coef, sw->vlin, sw->active,
+                            stream));
+    TRB_TRY(trb_lin_expand(sw->Ut, sw->strideU, sw->R, sw->M, sw->ldm, B, sw->coef, sw->part,
+                           sw->active, sw->gemv_impl, stream));
+    // Z: e3, likelihood e5, posterior z
+    k_z_update<<<B, kUpThreads, 0, st>>>(*sw, geo.G, first, sw->stats);
+    TRB_CHECK_LAUNCH();
+    // P3: tx = U_R^T b6 (new)
+    TRB_TRY(trb_lin_project(sw->Ut, sw->strideU, sw->R, sw->M, sw->ldm, B, sw->b5, sw->ldm, sw->tx,
+                            sw->active, sw->gemv_impl, stream));
+    // S2 + P4: rz = [b2/a2 +] V_R coef, backward variance
+    TRB_TRY(trb_lin_rescale(1, B, sw->R, sw->N, sw->M, sw->rank, sw->s, sw->s2, sw->stride_s,
+                            ea + 1 * B, ea + 5 * B, sw->tz, sw->tx, sw->coef, sw->vlin, sw->active,
+                            stream));
+    TRB_TRY(trb_lin_expand(sw->Vt, sw->strideV, sw->R, sw->N, sw->ldn, B, sw->coef, sw->part,
+                           sw->active, sw->gemv_impl, stream));
+    // X: e7, posterior x, records, early stopping
+    k_x_update<<<B, kUpThreads, 0, st>>>(*sw, geo.G, it, sw->stats);
+    TRB_CHECK_LAUNCH();
+  }
+  return TRB_OK;
+}

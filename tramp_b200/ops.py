@@ -1,0 +1,236 @@
+"""Host-side wrappers over the C ABI: device tensors in, device tensors out.
+
+PyTorch is used for device memory and streams only; all arithmetic on the EP
+path happens in libtramp_b200.so.  Vectors are batch-major float64 tensors
+`[B, ld]` with the leading dimension padded to a multiple of 16 doubles.
+"""
+import ctypes as C
+import numpy as np
+
+from . import _lib
+from ._lib import TrbFactor, ptr, check, current_stream
+
+AMIN = 1e-11  # Factor.AMIN, reference base.py:239
+AMAX = 1e+11  # Factor.AMAX, reference base.py:238
+LD_ALIGN = 16
+
+
+def torch():
+    import torch as _t
+    return _t
+
+
+def device():
+    _lib.require_cuda()
+    return torch().device("cuda", torch().cuda.current_device())
+
+
+def pad_ld(n):
+    return ((int(n) + LD_ALIGN - 1) // LD_ALIGN) * LD_ALIGN
+
+
+def is_tensor(x):
+    t = torch()
+    return isinstance(x, t.Tensor)
+
+
+def to_dev(x, dtype=None):
+    """numpy / scalar / tensor -> contiguous device tensor (float64 by default)."""
+    t = torch()
+    dtype = dtype or t.float64
+    if is_tensor(x):
+        return x.to(device=device(), dtype=dtype).contiguous()
+    return t.as_tensor(np.ascontiguousarray(np.asarray(x, dtype=np.float64)),
+                       device=device()).to(dtype).contiguous()
+
+
+def padded(x2d, ld=None):
+    """[B, n] (host or device) -> zero-padded device tensor [B, ld]."""
+    t = torch()
+    x = to_dev(x2d)
+    assert x.dim() == 2
+    B, n = x.shape
+    ld = ld or pad_ld(n)
+    if ld == n:
+        return x
+    out = t.zeros((B, ld), dtype=t.float64, device=x.device)
+    out[:, :n] = x
+    return out
+
+
+def zeros(*shape, dtype=None):
+    t = torch()
+    return t.zeros(*shape, dtype=dtype or t.float64, device=device())
+
+
+def make_factor(kind, p0=0.0, p1=0.0, p2=0.0, p3=0.0, amin=AMIN, amax=AMAX):
+    return TrbFactor(kind=kind, _pad=0, p0=float(p0), p1=float(p1), p2=float(p2), p3=float(p3),
+                     amin=float(amin), amax=float(amax))
+
+
+# ---------------------------------------------------------------------------
+# elementwise factors
+# ---------------------------------------------------------------------------
+def factor_posterior(f, a, b, y, n, a_elementwise, v_elementwise):
+    """a: [B] or [B, ld]; b, y: [B, ld] device tensors.  Returns r [B, ld], v [B] or [B, ld]."""
+    t = torch()
+    lib = _lib.load()
+    B, ld = b.shape
+    r = t.zeros_like(b)
+    v = t.zeros_like(b) if v_elementwise else t.zeros(B, dtype=t.float64, device=b.device)
+    check(lib.trb_factor_posterior(C.byref(f), B, n, ld, ptr(a), int(a_elementwise), ptr(b), ptr(y),
+                                   ptr(r), ptr(v), int(v_elementwise), current_stream()))
+    return r, v
+
+
+def factor_log_partition(f, a, b, y, n, a_elementwise, A_elementwise):
+    t = torch()
+    lib = _lib.load()
+    B, ld = b.shape
+    A = t.zeros_like(b) if A_elementwise else t.zeros(B, dtype=t.float64, device=b.device)
+    check(lib.trb_factor_log_partition(C.byref(f), B, n, ld, ptr(a), int(a_elementwise), ptr(b),
+                                       ptr(y), ptr(A), int(A_elementwise), current_stream()))
+    return A
+
+
+def factor_message(f, a_in, b_in, y, n, a_io, b_io, damping=0.0, a_copy=None, scratch=None,
+                   flags=None, active=None):
+    t = torch()
+    lib = _lib.load()
+    B, ld = b_in.shape
+    if scratch is None:
+        scratch = t.empty_like(b_in)
+    check(lib.trb_factor_message(C.byref(f), B, n, ld, ptr(a_in), ptr(b_in), ptr(y), ptr(a_io),
+                                 ptr(b_io), ptr(a_copy), float(damping or 0.0), ptr(scratch),
+                                 ptr(flags), ptr(active), current_stream()))
+    return a_io, b_io
+
+
+def truncated_normal(r0, v0, zmin, zmax):
+    """Elementwise truncated-normal (mean, var, logZ, proba) on device tensors."""
+    t = torch()
+    lib = _lib.load()
+    r0 = r0.contiguous()
+    v0 = v0.contiguous()
+    n = r0.numel()
+    outs = [t.empty_like(r0) for _ in range(4)]
+    check(lib.trb_truncated_normal(n, ptr(r0), ptr(v0), float(zmin), float(zmax),
+                                   *[ptr(o) for o in outs], current_stream()))
+    return outs
+
+
+def posterior_rv(a1, b1, a2, b2, n):
+    t = torch()
+    lib = _lib.load()
+    B, ld = b1.shape
+    r = t.zeros_like(b1)
+    v = t.zeros(B, dtype=t.float64, device=b1.device)
+    check(lib.trb_posterior_rv(B, n, ld, ptr(a1), ptr(b1), ptr(a2), ptr(b2), ptr(r), ptr(v),
+                               current_stream()))
+    return r, v
+
+
+# ---------------------------------------------------------------------------
+# linear channel primitives
+# ---------------------------------------------------------------------------
+def lin_project(A, R, n, vec, B, impl=0, active=None):
+    """A: [Bop, R, ld] device; vec: [B, ldvec].  Returns t [B, R]."""
+    t_ = torch()
+    lib = _lib.load()
+    ld = A.shape[-1]
+    stride = 0 if A.shape[0] == 1 and B > 1 else A.stride(0)
+    if A.shape[0] == 1:
+        stride = 0
+    out = t_.zeros((B, R), dtype=t_.float64, device=A.device)
+    check(lib.trb_lin_project(ptr(A), stride, R, n, ld, B, ptr(vec), vec.shape[-1], ptr(out),
+                              ptr(active), impl, current_stream()))
+    return out
+
+
+def lin_expand_slots(B, R):
+    return _lib.load().trb_lin_expand_slots(B, R)
+
+
+def lin_expand(A, R, n, coef, B, impl=0, active=None, add=None, add_div=None):
+    """Returns out[B, ld] = sum_i coef[b, i] A[b, i, :] (+ add / add_div[:, None])."""
+    t_ = torch()
+    lib = _lib.load()
+    ld = A.shape[-1]
+    stride = 0 if A.shape[0] == 1 else A.stride(0)
+    ns = lin_expand_slots(B, R)
+    part = t_.empty((B, ns, ld), dtype=t_.float64, device=A.device)
+    check(lib.trb_lin_expand(ptr(A), stride, R, n, ld, B, ptr(coef), ptr(part), ptr(active), impl,
+                             current_stream()))
+    out = t_.zeros((B, ld), dtype=t_.float64, device=A.device)
+    check(lib.trb_lin_reduce_slots(B, R, n, ld, ptr(part), ptr(add), ptr(add_div), ptr(out),
+                                   current_stream()))
+    return out
+
+
+def lin_rescale(direction, B, R, Nz, Nx, rank, s, s2, az, ax, tz, tx, active=None):
+    t_ = torch()
+    lib = _lib.load()
+    stride = 0 if s.shape[0] == 1 else s.stride(0)
+    coef = t_.zeros((B, R), dtype=t_.float64, device=s.device)
+    v = t_.zeros(B, dtype=t_.float64, device=s.device)
+    check(lib.trb_lin_rescale(direction, B, R, Nz, Nx, rank, ptr(s), ptr(s2), stride, ptr(az),
+                              ptr(ax), ptr(tz), ptr(tx), ptr(coef), ptr(v), ptr(active),
+                              current_stream()))
+    return coef, v
+
+
+# ---------------------------------------------------------------------------
+# natural parameters of the separable factors (host scalars, numpy)
+# ---------------------------------------------------------------------------
+def gauss_bernoulli_factor(rho, mean, var, amin=AMIN, amax=AMAX):
+    """reference priors/gauss_bernoulli_prior.py:33-36 (+ the constant of :82)."""
+    a0 = 1 / var
+    b0 = mean / var
+    normal_A0 = 0.5 * (b0**2 / a0 + np.log(2 * np.pi / a0))
+    eta = normal_A0 - np.log(rho / (1 - rho))
+    A0 = np.logaddexp(eta, normal_A0)
+    return make_factor(_lib.GAUSS_BERNOULLI_PRIOR, a0, b0, eta, A0, amin, amax)
+
+
+def binary_factor(p_pos, amin=AMIN, amax=AMAX):
+    """reference priors/binary_prior.py:26-28."""
+    b0 = 0.5 * np.log(p_pos / (1 - p_pos))
+    return make_factor(_lib.BINARY_PRIOR, b0, amin=amin, amax=amax)
+
+
+def gaussian_prior_factor(mean, var, amin=AMIN, amax=AMAX):
+    """reference priors/gaussian_prior.py:30-32."""
+    return make_factor(_lib.GAUSSIAN_PRIOR, 1 / var, mean / var, amin=amin, amax=amax)
+
+
+def gaussian_likelihood_factor(var, amin=AMIN, amax=AMAX):
+    """reference likelihoods/gaussian_likelihood.py:16."""
+    return make_factor(_lib.GAUSSIAN_LIKELIHOOD, 1 / var, amin=amin, amax=amax)
+
+
+def sgn_factor(amin=AMIN, amax=AMAX):
+    return make_factor(_lib.SGN_LIKELIHOOD, amin=amin, amax=amax)
+
+
+def abs_factor(amin=AMIN, amax=AMAX):
+    return make_factor(_lib.ABS_LIKELIHOOD, amin=amin, amax=amax)
+
+
+def factor_from_spec(spec):
+    """dict(kind=..., **params) -> TrbFactor (the spec format of oracle/ and tests/golden)."""
+    kind = spec["kind"]
+    amin, amax = spec.get("AMIN", AMIN), spec.get("AMAX", AMAX)
+    if kind == "gauss_bernoulli":
+        return gauss_bernoulli_factor(spec.get("rho", 0.5), spec.get("mean", 0),
+                                      spec.get("var", 1), amin, amax)
+    if kind == "binary":
+        return binary_factor(spec.get("p_pos", 0.5), amin, amax)
+    if kind == "gaussian":
+        if "y" in spec or spec.get("role") == "likelihood":
+            return gaussian_likelihood_factor(spec.get("var", 1), amin, amax)
+        return gaussian_prior_factor(spec.get("mean", 0), spec.get("var", 1), amin, amax)
+    if kind == "sgn":
+        return sgn_factor(amin, amax)
+    if kind == "abs":
+        return abs_factor(amin, amax)
+    raise ValueError(f"unknown factor kind {kind!r}")
