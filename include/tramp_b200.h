@@ -211,7 +211,7 @@ typedef struct {
   /* EarlyStoppingEP(ids="all"): enabled if es_tol >= 0 */
   double es_tol, es_max_increase; int32_t es_wait_increase;
   int32_t gemv_impl;   /* 0 default, 1 LDG, 2 TMA ring */
-  int32_t _pad;
+  int32_t es_vars;     /* variables the tolerance runs over: bit 0 = x, bit 1 = z (ids="all": 3) */
 } trb_sweep;
 
 /* Run `n_iter` EP iterations.  `it0` is the index, within the current

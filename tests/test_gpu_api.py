@@ -1,0 +1,351 @@
+"""GPU parity of the public (tramp-compatible) API against the golden vectors
+of the reference and the CPU oracle.  Tolerance: 1e-9 relative on posterior
+means / variances and on the MSE trajectory (BASELINE.json north star)."""
+import json
+import os
+import numpy as np
+import pytest
+from numpy.testing import assert_allclose
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _need_cuda():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+
+
+@pytest.fixture(scope="module")
+def sw(golden_dir):
+    return np.load(os.path.join(golden_dir, "sweeps.npz"))
+
+
+def _configs(sw):
+    return json.loads(str(sw["configs"]))
+
+
+def _build(cfg, sw, name, batch=None):
+    from tramp_b200.priors import get_prior
+    from tramp_b200.likelihoods import get_likelihood
+    from tramp_b200.channels import LinearChannel
+    from tramp_b200.variables import SISOVariable as V
+    pk = {k: v for k, v in cfg["prior"].items() if k != "kind"}
+    lk = {k: v for k, v in cfg["lik"].items() if k != "kind"}
+    prior = get_prior(size=cfg["N"], prior_type=cfg["prior"]["kind"], **pk)
+    lik = get_likelihood(y=sw[name + "_y"], likelihood_type=cfg["lik"]["kind"], **lk)
+    return (prior @ V("x") @ LinearChannel(sw[name + "_W"]) @ V("z") @ lik).to_model()
+
+
+class _SeqInit:
+    """Initializer replaying the eight per-edge initial messages NoisyInit drew
+    in the reference run (tests/golden/make_golden.py stores them as e1..e8)."""
+
+    def __init__(self, sw, name):
+        self.vals = {k: (float(sw[f"{name}_init_e{k}_a"]), sw[f"{name}_init_e{k}_b"]) for k in range(1, 9)}
+        self.calls = 0
+
+    def init(self, key, shape, id, direction):
+        edge = self.calls // 2 + 1          # init_message_dag asks a then b, edges e1..e8 in order
+        self.calls += 1
+        return self.vals[edge][0 if key == "a" else 1]
+
+
+@pytest.mark.parametrize("impl", [1, 2])
+@pytest.mark.parametrize("idx", range(9))
+def test_sweep_matches_reference(sw, idx, impl):
+    from tramp_b200.algos import ExpectationPropagation, TrackErrors, TrackEvolution, JoinCallback
+    cfg = _configs(sw)[idx]
+    name = cfg["name"]
+    model = _build(cfg, sw, name)
+    ep = ExpectationPropagation(model)
+    ep.gemv_impl = impl
+    track = TrackErrors({"x": sw[name + "_x"]})
+    evo = TrackEvolution()
+    init = _SeqInit(sw, name) if cfg.get("init") == "noisy" else None
+    ep.iterate(max_iter=cfg["n_iter"], callback=JoinCallback([track, evo]), initializer=init,
+               damping=cfg["damping"])
+    assert ep.n_iter == cfg["n_iter"]
+    mse = np.array([e["mse"] for e in track.errors])
+    df = evo.get_dataframe()
+    assert_allclose(mse, sw[name + "_mse"], rtol=1e-9, atol=1e-30)
+    assert_allclose(df[df.id == "x"].v.values, sw[name + "_vx"], rtol=1e-9)
+    assert_allclose(df[df.id == "z"].v.values, sw[name + "_vz"], rtol=1e-9)
+    d = ep.get_variables_data()
+    for vid, key in (("x", "_rx"), ("z", "_rz")):
+        ref = sw[name + key]
+        assert_allclose(d[vid]["r"], ref, rtol=1e-9, atol=1e-9 * np.abs(ref).max())
+    assert_allclose(d["x"]["v"], sw[name + "_vx_final"], rtol=1e-9)
+    assert_allclose(d["z"]["v"], sw[name + "_vz_final"], rtol=1e-9)
+    for k in range(1, 9):
+        a, b = ep._edge(f"e{k}")
+        ref_b = sw[f"{name}_e{k}_b"]
+        assert_allclose(a, sw[f"{name}_e{k}_a"], rtol=1e-9)
+        assert_allclose(b, ref_b, rtol=1e-9, atol=1e-9 * np.abs(ref_b).max())
+
+
+@pytest.mark.parametrize("idx", range(9))
+def test_log_evidence_matches_reference(sw, idx):
+    from tramp_b200.algos import ExpectationPropagation, PassCallback
+    cfg = _configs(sw)[idx]
+    name = cfg["name"]
+    ep = ExpectationPropagation(_build(cfg, sw, name))
+    init = _SeqInit(sw, name) if cfg.get("init") == "noisy" else None
+    ep.iterate(max_iter=cfg["n_iter"], callback=PassCallback(), initializer=init, damping=cfg["damping"])
+    with np.errstate(all="ignore"):
+        logZ = ep.log_evidence()
+    # saturated problems (a -> AMAX) make log Z a difference of ~1e13 terms
+    assert_allclose(logZ, sw[name + "_logZ"], rtol=1e-7)
+    assert_allclose(ep.A_nodes[ep.prior.id], sw[name + "_A_" + type(ep.prior).__name__], rtol=1e-8)
+    assert_allclose(ep.A_nodes[ep.lik.id], sw[name + "_A_" + type(ep.lik).__name__], rtol=1e-8)
+    assert_allclose(ep.A_nodes[ep.linear.id], sw[name + "_A_LinearChannel"], rtol=1e-8)
+
+
+@pytest.mark.parametrize("idx", range(3))
+def test_default_early_stopping(sw, idx):
+    """iterate() with the default EarlyStoppingEP stops at the reference's iteration."""
+    from tramp_b200.algos import ExpectationPropagation
+    cfg = _configs(sw)[idx]
+    name = cfg["name"] + "_early"
+    ep = ExpectationPropagation(_build(cfg, sw, name))
+    ep.iterate(max_iter=200, damping=cfg["damping"])
+    assert ep.n_iter == int(sw[name + "_n_iter"])
+    d = ep.get_variables_data()
+    ref = sw[name + "_rx"]
+    assert_allclose(d["x"]["r"], ref, rtol=1e-9, atol=1e-9 * np.abs(ref).max())
+    assert_allclose(d["x"]["v"], sw[name + "_vx_final"], rtol=1e-9)
+
+
+def test_synchronous_callback_path_equals_device_path(sw):
+    """An arbitrary callback (TrackEstimate needs r every iteration) forces the
+    per-iteration path; it must give the same trajectory as the device path."""
+    from tramp_b200.algos import (ExpectationPropagation, TrackErrors, TrackEstimate,
+                                  JoinCallback, EarlyStoppingEP)
+    cfg = _configs(sw)[1]
+    name = cfg["name"]
+    ep = ExpectationPropagation(_build(cfg, sw, name))
+    est = TrackEstimate(ids=["x"])
+    track = TrackErrors({"x": sw[name + "_x"]})
+    ep.iterate(max_iter=cfg["n_iter"], callback=JoinCallback([est, track]), damping=cfg["damping"])
+    mse = np.array([e["mse"] for e in track.errors])
+    assert_allclose(mse, sw[name + "_mse"], rtol=1e-9)
+    assert len(est.records) == cfg["n_iter"]
+    assert_allclose(est.records[-1]["r"], sw[name + "_rx"], rtol=1e-9, atol=1e-12)
+    # host-side EarlyStoppingEP (inside a join with a non-replayable callback)
+    name_e = cfg["name"] + "_early"
+    ep = ExpectationPropagation(_build(cfg, sw, name_e))
+    ep.iterate(max_iter=200, callback=JoinCallback([TrackEstimate(ids=["x"]), EarlyStoppingEP()]),
+               damping=cfg["damping"])
+    assert ep.n_iter == int(sw[name_e + "_n_iter"])
+
+
+def test_warm_start_continues(sw):
+    from tramp_b200.algos import ExpectationPropagation, PassCallback
+    cfg = _configs(sw)[0]
+    name = cfg["name"]
+    ep = ExpectationPropagation(_build(cfg, sw, name))
+    ep.iterate(max_iter=15, callback=PassCallback())
+    ep.iterate(max_iter=cfg["n_iter"] - 15, callback=PassCallback(), warm_start=True)
+    assert ep.n_iter == cfg["n_iter"]
+    ref = sw[name + "_rx"]
+    assert_allclose(ep.get_variables_data()["x"]["r"], ref, rtol=1e-9, atol=1e-9 * np.abs(ref).max())
+    ep2 = ExpectationPropagation(_build(cfg, sw, name))
+    with pytest.raises(ValueError):
+        ep2.iterate(max_iter=1, warm_start=True)
+
+
+def test_errors_mirror_reference(sw):
+    from tramp_b200.algos import ExpectationPropagation, PassCallback
+    from tramp_b200.priors import GaussBernoulliPrior
+    from tramp_b200.channels import LinearChannel, GaussianChannel
+    from tramp_b200.variables import SISOVariable as V, SILeafVariable as O
+    cfg = _configs(sw)[0]
+    ep = ExpectationPropagation(_build(cfg, sw, cfg["name"]))
+    with pytest.raises(ValueError):
+        ep.iterate(max_iter=1, callback=PassCallback(), damping=1)      # int, not float
+    with pytest.raises(ValueError):
+        ExpectationPropagation("not a model")
+    # un-observed generative model is not the EP chain
+    gen = (GaussBernoulliPrior(size=8) @ V("x") @ LinearChannel(np.eye(8)) @ V("z")
+           @ GaussianChannel(var=1.) @ O("y")).to_model()
+    with pytest.raises(NotImplementedError):
+        ExpectationPropagation(gen)
+    # NaN in a message surfaces as ValueError (message_passing.py:187-209)
+    name = cfg["name"]
+    y_bad = sw[name + "_y"].copy()
+    y_bad[3] = np.nan
+    from tramp_b200.likelihoods import GaussianLikelihood
+    m = (GaussBernoulliPrior(size=cfg["N"], rho=0.1) @ V("x") @ LinearChannel(sw[name + "_W"]) @ V("z")
+         @ GaussianLikelihood(y=y_bad, var=1e-2)).to_model()
+    with pytest.raises(ValueError, match="nan"):
+        ExpectationPropagation(m).iterate(max_iter=3, callback=PassCallback())
+
+
+@pytest.mark.parametrize("kinds", [("gauss_bernoulli", "gaussian"), ("gaussian", "sgn"),
+                                   ("binary", "abs")])
+def test_batched_instances_match_oracle(kinds):
+    """B independent instances in one launch == B oracle runs (north-star item 4),
+    incl. a batch that shares one W (config-4 style)."""
+    from oracle import tramp_oracle as orc
+    from tramp_b200.priors import get_prior
+    from tramp_b200.likelihoods import get_likelihood
+    from tramp_b200.channels import LinearChannel
+    from tramp_b200.variables import SISOVariable as V
+    from tramp_b200.algos import ExpectationPropagation, TrackErrors
+    pk, lk = kinds
+    rng = np.random.RandomState(5)
+    B, N, M, n_iter, damping = 5, 96, 144 if lk != "gaussian" else 48, 25, 0.3
+    pkw = dict(gauss_bernoulli=dict(rho=0.2), gaussian={}, binary=dict(p_pos=0.6))[pk]
+    lkw = dict(gaussian=dict(var=0.02), sgn={}, abs={})[lk]
+    for shared in (False, True):
+        W = rng.randn(*(() if shared else (B,)), M, N) / np.sqrt(N)
+        if pk == "gauss_bernoulli":
+            x = rng.randn(B, N) * (rng.rand(B, N) < 0.2)
+        elif pk == "binary":
+            x = np.where(rng.rand(B, N) < 0.6, 1.0, -1.0)
+        else:
+            x = rng.randn(B, N)
+        Wb = np.broadcast_to(W, (B, M, N))
+        z = np.einsum("bmn,bn->bm", Wb, x)
+        y = dict(gaussian=z + np.sqrt(0.02) * rng.randn(B, M), sgn=np.where(z >= 0, 1., -1.),
+                 abs=np.abs(z))[lk]
+        model = (get_prior(size=N, prior_type=pk, batch=B, **pkw) @ V("x") @ LinearChannel(W) @ V("z")
+                 @ get_likelihood(y=y, likelihood_type=lk, **lkw)).to_model()
+        ep = ExpectationPropagation(model)
+        track = TrackErrors({"x": x}, metrics=["mse", "sign_mse"])
+        ep.iterate(max_iter=n_iter, callback=track, damping=damping)
+        got = ep.get_variables_data()
+        assert got["x"]["r"].shape == (B, N) and got["x"]["v"].shape == (B,)
+        for b in range(B):
+            with np.errstate(all="ignore"):
+                ref = orc.ep_glm(dict(kind=pk, **pkw), Wb[b], dict(kind=lk, y=y[b], **lkw), n_iter,
+                                 damping=damping, x_true=x[b])
+            for vid, r in (("x", ref["r_x"]), ("z", ref["r_z"])):
+                assert_allclose(got[vid]["r"][b], r, rtol=1e-9, atol=1e-9 * np.abs(r).max())
+            assert_allclose(got["x"]["v"][b], ref["v_x"], rtol=1e-9)
+            assert_allclose(got["z"]["v"][b], ref["v_z"], rtol=1e-9)
+            mse = np.array([e["mse"][b] for e in track.errors])
+            assert_allclose(mse, ref["traj"]["mse_x"], rtol=1e-9, atol=1e-30)
+            smse = np.array([e["sign_mse"][b] for e in track.errors])
+            assert np.all(smse <= mse * (1 + 1e-12))
+
+
+def test_batched_early_stopping_per_instance():
+    """Each instance of a batch stops at the iteration its own oracle run stops."""
+    from oracle import tramp_oracle as orc
+    from tramp_b200.priors import GaussBernoulliPrior
+    from tramp_b200.likelihoods import GaussianLikelihood
+    from tramp_b200.channels import LinearChannel
+    from tramp_b200.variables import SISOVariable as V
+    from tramp_b200.algos import ExpectationPropagation
+    rng = np.random.RandomState(9)
+    B, N, M = 4, 120, 60
+    W = rng.randn(B, M, N) / np.sqrt(N)
+    x = rng.randn(B, N) * (rng.rand(B, N) < 0.1)
+    y = np.einsum("bmn,bn->bm", W, x) + 0.1 * rng.randn(B, M)
+    model = (GaussBernoulliPrior(size=N, rho=0.1, batch=B) @ V("x") @ LinearChannel(W) @ V("z")
+             @ GaussianLikelihood(y=y, var=1e-2)).to_model()
+    ep = ExpectationPropagation(model)
+    ep.iterate(max_iter=200)
+    got = ep.get_variables_data()
+    for b in range(B):
+        ref = orc.ep_glm(dict(kind="gauss_bernoulli", rho=0.1), W[b],
+                         dict(kind="gaussian", var=1e-2, y=y[b]), 200,
+                         early_stopping=dict(tol=1e-6))
+        assert ep.n_iter_per_instance[b] == ref["n_iter"]
+        assert_allclose(got["x"]["r"][b], ref["r_x"], rtol=1e-9, atol=1e-12)
+    assert ep.n_iter == ep.n_iter_per_instance.max()
+
+
+def test_factor_api_mirrors_reference_unit_tests():
+    """tramp/tests/test_priors.py:27-52 and test_likelihoods.py:52-86: vectorised
+    compute_*_posterior / compute_log_partition equal the scalar_* versions, with
+    isotropic=False and ax in linspace(1, 2), bx in linspace(-2, 2)."""
+    from tramp_b200.priors import GaussianPrior, GaussBernoulliPrior, BinaryPrior
+    from tramp_b200.likelihoods import GaussianLikelihood, AbsLikelihood, SgnLikelihood
+    ax = np.linspace(1, 2, 100)
+    bx = np.linspace(-2, 2, 100)
+    for prior in (GaussianPrior(size=100, isotropic=False), GaussBernoulliPrior(size=100, isotropic=False),
+                  BinaryPrior(size=100, isotropic=False)):
+        rx, vx = prior.compute_forward_posterior(ax, bx)
+        assert rx.shape == bx.shape and vx.shape == bx.shape
+        rx_ = np.array([prior.scalar_forward_mean(a, b) for a, b in zip(ax, bx)])
+        vx_ = np.array([prior.scalar_forward_variance(a, b) for a, b in zip(ax, bx)])
+        assert_allclose(rx, rx_)
+        assert_allclose(vx, vx_)
+        A = prior.compute_log_partition(ax, bx)
+        A_ = np.mean([prior.scalar_log_partition(a, b) for a, b in zip(ax, bx)])
+        assert_allclose(A, A_, rtol=1e-13)
+    z = np.linspace(-3, 3, 100)
+    for lik in (GaussianLikelihood(y=z, isotropic=False), AbsLikelihood(y=np.abs(z), isotropic=False),
+                SgnLikelihood(y=np.sign(z), isotropic=False)):
+        rz, vz = lik.compute_backward_posterior(ax, bx, lik.y)
+        assert rz.shape == bx.shape and vz.shape == bx.shape
+        rz_ = np.array([lik.scalar_backward_mean(a, b, y) for a, b, y in zip(ax, bx, lik.y)])
+        vz_ = np.array([lik.scalar_backward_variance(a, b, y) for a, b, y in zip(ax, bx, lik.y)])
+        assert_allclose(rz, rz_)
+        assert_allclose(vz, vz_)
+        A = lik.compute_log_partition(ax, bx, lik.y)
+        A_ = np.mean([lik.scalar_log_partition(a, b, y) for a, b, y in zip(ax, bx, lik.y)])
+        assert_allclose(A, A_, rtol=1e-13)
+
+
+def test_belief_gradients():
+    """tramp/tests/test_beliefs.py:11-23 (checks/check_gradients.py:44,70-90):
+    r = dA/db and v = d2A/db2 by central finite differences, eps = 1e-3, atol 1e-3."""
+    from tramp_b200.beliefs import binary, normal, sparse, positive, truncated
+    eps = 1e-3
+    b = np.linspace(-6, 6, 100)
+    cases = [(binary, {}), (normal, {"a": 1}), (sparse, {"a": 1, "eta": 1}), (positive, {"a": 1}),
+             (truncated, {"a": 1, "xmin": -1, "xmax": +1})]
+    for belief, kw in cases:
+        def A(bb):
+            return belief.A(b=bb, **kw)
+        A1 = (A(b + eps) - A(b - eps)) / (2 * eps)
+        A2 = (A(b + eps) - 2 * A(b) + A(b - eps)) / eps**2
+        assert_allclose(belief.r(b=b, **kw), A1, rtol=0, atol=eps)
+        assert_allclose(belief.v(b=b, **kw), A2, rtol=0, atol=eps)
+
+
+def test_linear_channel_factor_api(golden_dir):
+    """LinearChannel.compute_*_posterior / log_partition against the reference."""
+    from tramp_b200.channels import LinearChannel
+    lin = np.load(os.path.join(golden_dir, "linear.npz"))
+    for i in range(int(lin["lin_nW"])):
+        ch = LinearChannel(lin[f"lin{i}_W"])
+        bz, bx = lin[f"lin{i}_bz"], lin[f"lin{i}_bx"]
+        assert ch._setup() is None and ch.rank == int(lin[f"lin{i}_rank"])
+        for j, (az, ax) in enumerate(lin["lin_ab"]):
+            if az == 0:
+                continue
+            rz, vz = ch.compute_backward_posterior(az, bz, ax, bx)
+            rx, vx = ch.compute_forward_posterior(az, bz, ax, bx)
+            for got, key in ((rz, "rz"), (rx, "rx")):
+                ref = lin[f"lin{i}_{j}_{key}"]
+                assert_allclose(got, ref, rtol=1e-9, atol=1e-12 * max(1.0, np.abs(ref).max()))
+            assert_allclose(vz, lin[f"lin{i}_{j}_vz"], rtol=1e-12)
+            assert_allclose(vx, lin[f"lin{i}_{j}_vx"], rtol=1e-12)
+            assert_allclose(ch.compute_n_eff(az, ax), lin[f"lin{i}_{j}_neff"], rtol=1e-10)
+            with np.errstate(all="ignore"):
+                A = ch.compute_log_partition(az, bz, ax, bx)
+            assert_allclose(A, lin[f"lin{i}_{j}_A"], rtol=1e-9)
+
+
+def test_scenario_and_glm_generative():
+    """BayesOptimalScenario.setup/run_ep/ep_convergence on glm_generative
+    (reference experiments/teacher_student_scenario.py:45-115)."""
+    from tramp_b200.models import glm_generative
+    from tramp_b200.experiments import BayesOptimalScenario
+    np.random.seed(12)
+    model = glm_generative(N=200, alpha=0.6, ensemble_type="gaussian", prior_type="gauss_bernoulli",
+                           output_type="gaussian", prior_rho=0.1, output_var=1e-2)
+    scenario = BayesOptimalScenario(model, x_ids=["x"])
+    scenario.setup(seed=42)
+    x_data = scenario.run_ep(max_iter=200, damping=0.1)
+    mse = np.mean((x_data["x"]["r"] - scenario.x_true["x"])**2)
+    assert x_data["n_iter"] < 200
+    assert mse < 0.02 and abs(mse - x_data["x"]["v"]) < 0.01   # EP's v tracks the empirical mse
+    df = scenario.ep_convergence(metrics=["mse"], max_iter=30, damping=0.1)
+    assert list(df.columns) == ["id", "iter", "mse", "v"] and len(df) == 30
+    assert_allclose(scenario.compute_score(scenario.x_pred)["x"]["mse"], df.mse.values[-1], rtol=1e-9)

@@ -43,7 +43,7 @@ class TrbSweep(C.Structure):
         ("rec_vz", C.c_void_p), ("rec_tol", C.c_void_p),
         ("max_records", C.c_int32),
         ("es_tol", C.c_double), ("es_max_increase", C.c_double),
-        ("es_wait_increase", C.c_int32), ("gemv_impl", C.c_int32), ("_pad", C.c_int32),
+        ("es_wait_increase", C.c_int32), ("gemv_impl", C.c_int32), ("es_vars", C.c_int32),
     ]
 
 

@@ -1,0 +1,9 @@
+"""EP driver (reference tramp/algos/)."""
+from .expectation_propagation import ExpectationPropagation
+from .message_passing import MessagePassing
+from .callbacks import (
+    Callback, PassCallback, JoinCallback, LogProgress, TrackEvolution,
+    TrackEstimate, TrackErrors, EarlyStoppingEP, EarlyStopping,
+)
+from .initial_conditions import ConstantInit, NoisyInit, CustomInit
+from .metrics import METRICS, mean_squared_error, sign_symmetric_mse, overlap

@@ -1,0 +1,63 @@
+"""ExpectationPropagation (reference tramp/algos/expectation_propagation.py:5-32)."""
+import numpy as np
+
+from .message_passing import MessagePassing
+from .callbacks import EarlyStoppingEP
+
+
+def _variable_log_partition(ax, bx):
+    """reference base.py:146-150, vectorised over a leading batch dimension."""
+    ax = np.asarray(ax, dtype=float)
+    bx = np.asarray(bx, dtype=float)
+    a = ax[..., None] if bx.ndim > ax.ndim else ax
+    with np.errstate(all="ignore"):
+        logZ = 0.5 * np.sum(bx**2 / a + np.log(2 * np.pi / a), axis=-1)
+    return np.where(ax <= 0, np.inf, logZ) if ax.ndim else (np.inf if ax <= 0 else float(logZ))
+
+
+class ExpectationPropagation(MessagePassing):
+    def __init__(self, model):
+        model.init_shapes()
+        super().__init__(model, message_keys=["a", "b"])
+        self.default_stopping = EarlyStoppingEP()
+
+    def forward(self, node, message):
+        return node.forward_message(message)
+
+    def backward(self, node, message):
+        return node.backward_message(message)
+
+    def update(self, variable, message):
+        r, v = variable.posterior_rv(message)
+        return dict(r=r, v=v)
+
+    def node_objective(self, node, message):
+        return node.log_partition(message)
+
+    def update_objective(self):
+        """reference message_passing.py:306-328: A_model = sum_nodes A - sum_fwd-edges A.
+        Cold path: the factor log-partitions run on the device, the (tiny)
+        variable terms on the host."""
+        E = {name: self._edge(name) for name in ("e1", "e2", "e3", "e4", "e5", "e6", "e7", "e8")}
+        A = {}
+        A[self.prior.id] = self.prior.compute_log_partition(*E["e8"])
+        A[self.x_id] = _variable_log_partition(E["e1"][0] + E["e7"][0], E["e1"][1] + E["e7"][1])
+        A[self.linear.id] = self.linear.compute_log_partition(E["e2"][0], E["e2"][1],
+                                                              E["e6"][0], E["e6"][1])
+        A[self.z_id] = _variable_log_partition(E["e3"][0] + E["e5"][0], E["e3"][1] + E["e5"][1])
+        A[self.lik.id] = self.lik.compute_log_partition(E["e4"][0], E["e4"][1], self.lik.y)
+        self.A_nodes = A
+        pairs = [("e1", "e8"), ("e2", "e7"), ("e3", "e6"), ("e4", "e5")]
+        self.A_edges = {f: _variable_log_partition(E[f][0] + E[b][0], E[f][1] + E[b][1])
+                        for f, b in pairs}
+        self.A_model = sum(A.values()) - sum(self.A_edges.values())
+
+    def log_evidence(self, update=True):
+        if update:
+            self.update_objective()
+        return self.A_model
+
+    def surprisal(self, update=True):
+        if update:
+            self.update_objective()
+        return -self.A_model

@@ -1,0 +1,378 @@
+"""The message-schedule driver (reference tramp/algos/message_passing.py).
+
+`MessagePassing.iterate(max_iter, callback, initializer, damping, warm_start)`
+keeps the reference's signature and semantics for the chain
+`prior -> x -> LinearChannel -> z -> likelihood`, but the sweep itself is
+device resident: all eight edge messages, both posteriors and the per-iteration
+records live in HBM and one C call (`trb_sweep_run`) enqueues every kernel of
+every iteration; there is no per-factor host round trip (reference :249-269
+loops over nodes in Python).
+
+Edge numbering: e1 prior->x, e2 x->lin, e3 lin->z, e4 z->lik (fwd);
+e5 lik->z, e6 z->lin, e7 lin->x, e8 x->prior (bwd).
+"""
+import ctypes as C
+import logging
+import numpy as np
+
+from .callbacks import Callback
+from .initial_conditions import ConstantInit
+from ..models import Model
+from ..base import Variable, Factor
+from ..priors import Prior
+from ..likelihoods import Likelihood
+from ..channels import LinearChannel
+from ..variables import SISOVariable
+from .. import ops, _lib
+
+logger = logging.getLogger(__name__)
+
+# (edge name, variable role, direction, index into edge_a)
+EDGES = [("e1", "x", "fwd", 0), ("e2", "x", "fwd", 1), ("e3", "z", "fwd", 2), ("e4", "z", "fwd", 3),
+         ("e5", "z", "bwd", 4), ("e6", "z", "bwd", 5), ("e7", "x", "bwd", 6), ("e8", "x", "bwd", 7)]
+
+
+class MessageSnapshot:
+    """Copy of the device-resident message state (the role `message_dag.copy()`
+    plays in the reference, message_passing.py:356, callbacks.py:286)."""
+
+    def __init__(self, tensors, n_iter):
+        self.tensors = tensors
+        self.n_iter = n_iter
+
+
+class MessagePassing():
+
+    def __init__(self, model, message_keys):
+        if not isinstance(model, Model):
+            raise ValueError(f"model {model} is not a Model")
+        self.message_keys = message_keys
+        self.model = model
+        self.model_dag = model.dag
+        self.forward_ordering = model.forward_ordering
+        self.backward_ordering = list(reversed(model.forward_ordering))
+        self.variables = model.variables
+        self.n_iter = 0
+        self.gemv_impl = 0
+        self._state = None
+        self._has_messages = False
+        self._compile_chain()
+
+    # ------------------------------------------------------------------ model
+    def _compile_chain(self):
+        order = self.forward_ordering
+        ok = (len(order) == 5 and isinstance(order[0], Prior) and isinstance(order[1], SISOVariable)
+              and isinstance(order[2], LinearChannel) and isinstance(order[3], SISOVariable)
+              and isinstance(order[4], Likelihood))
+        if not ok:
+            raise NotImplementedError(
+                "tramp_b200 runs EP on the generalized linear model "
+                "prior @ V @ LinearChannel @ V @ likelihood (observed); got "
+                + " -> ".join(type(n).__name__ for n in order))
+        self.prior, self.x_var, self.linear, self.z_var, self.lik = order
+        self.x_id, self.z_id = self.x_var.id, self.z_var.id
+        self.variable_ids = [self.x_id, self.z_id]
+        if not getattr(self.prior, "isotropic", True) or not getattr(self.lik, "isotropic", True):
+            raise NotImplementedError("the EP sweep uses isotropic beliefs (one precision per edge)")
+        batches = {b for b in (self.prior.batch, self.linear.batch, self.lik.batch) if b is not None}
+        if len(batches) > 1:
+            raise ValueError(f"inconsistent batch sizes {sorted(batches)} in the model")
+        self.batched = bool(batches)
+        self.B = batches.pop() if batches else 1
+        if self.batched and (self.prior.batch is None or self.lik.batch is None):
+            raise ValueError("a batched model needs prior(batch=B) and y of shape (B, M)")
+        self.N, self.M = self.linear.Nz, self.linear.Nx
+        size = self.prior.size
+        if (size if isinstance(size, int) else int(np.prod(size))) != self.N:
+            raise ValueError(f"prior size {size} does not match W with Nz={self.N}")
+        if self.lik.y is None or np.shape(self.lik.y)[-1] != self.M:
+            raise ValueError(f"likelihood y must have last dimension Nx={self.M}")
+
+    def _var_shape(self, role):
+        n = self.N if role == "x" else self.M
+        return (self.B, n) if self.batched else (n,)
+
+    # ------------------------------------------------------------ device state
+    def _ensure_state(self):
+        if self._state is not None:
+            return self._state
+        t = ops.torch()
+        lin = self.linear
+        lin._setup()
+        if lin.s.shape[0] not in (1, self.B):
+            raise ValueError("operator batch does not match the model batch")
+        B, R, ldn, ldm = self.B, lin.R, lin.ldn, lin.ldm
+        f64 = dict(dtype=t.float64, device=lin.s.device)
+        i32 = dict(dtype=t.int32, device=lin.s.device)
+        st = dict(
+            edge_a=t.zeros((8, B), **f64),
+            b1=t.zeros((B, ldn), **f64), b7=t.zeros((B, ldn), **f64),
+            b3=t.zeros((B, ldm), **f64), b5=t.zeros((B, ldm), **f64),
+            rx=t.zeros((B, ldn), **f64), rz=t.zeros((B, ldm), **f64),
+            vx=t.zeros(B, **f64), vz=t.zeros(B, **f64),
+            tz=t.zeros((B, R), **f64), tx=t.zeros((B, R), **f64), coef=t.zeros((B, R), **f64),
+            scr_n=t.zeros((B, ldn), **f64), scr_m=t.zeros((B, ldm), **f64),
+            vlin=t.zeros(B, **f64), stats=t.zeros((B, 4), **f64),
+            active=t.ones(B, **i32), flags=t.zeros(B, **i32), n_iter=t.zeros(B, **i32),
+        )
+        st["nslots"] = ops.lin_expand_slots(B, R)
+        st["part"] = t.zeros((B, st["nslots"], max(ldn, ldm)), **f64)
+        y = np.asarray(self.lik.y, dtype=np.float64) if not ops.is_tensor(self.lik.y) else self.lik.y
+        y2 = y if len(y.shape) == 2 else y[None, :]
+        st["y"] = ops.padded(y2, ldm)
+        st["b6_init"] = None
+        st["b8_init"] = None
+        st["x_true"] = None
+        self._state = st
+        return st
+
+    def _vec_to_dev(self, value, role):
+        n, ld = (self.N, self.linear.ldn) if role == "x" else (self.M, self.linear.ldm)
+        v = ops.to_dev(value)
+        if v.dim() == 0:
+            v = v.expand(self.B, n)
+        elif v.dim() == 1:
+            v = v[None, :].expand(self.B, n)
+        return ops.padded(v.contiguous(), ld)
+
+    def init_message_dag(self, initializer):
+        """reference message_passing.py:211-232: every edge gets a, b from the initializer."""
+        st = self._ensure_state()
+        t = ops.torch()
+        ids = {"x": self.x_id, "z": self.z_id}
+        init_b = {}
+        for name, role, direction, idx in EDGES:
+            shape = self._var_shape(role)
+            a = initializer.init("a", shape, ids[role], direction)
+            b = initializer.init("b", shape, ids[role], direction)
+            st["edge_a"][idx] = ops.to_dev(np.broadcast_to(np.asarray(a, dtype=np.float64), (self.B,)).copy())
+            init_b[name] = self._vec_to_dev(b, role)
+        st["b1"].copy_(init_b["e1"])
+        st["b3"].copy_(init_b["e3"])
+        st["b5"].copy_(init_b["e5"])
+        st["b7"].copy_(init_b["e7"])
+        # e6 / e8 are read once (first F3 / F1) before the pass-through overwrites
+        # them; keep them separately only if they differ from e5 / e7
+        st["b6_init"] = None if t.equal(init_b["e6"], init_b["e5"]) else init_b["e6"]
+        st["b8_init"] = None if t.equal(init_b["e8"], init_b["e7"]) else init_b["e8"]
+        for k in ("rx", "rz", "vx", "vz"):
+            st[k].zero_()
+        self._has_messages = True
+
+    def configure_damping(self, damping):
+        """reference message_passing.py:70-106: None | float | list of
+        (variable.id, direction, damping) for the factor->variable edges."""
+        self.damp = dict(e1=0.0, e3=0.0, e5=0.0, e7=0.0)
+        if not damping:
+            self.damping = False
+            return
+        self.damping = True
+        if damping == "adaptive":
+            raise NotImplementedError(
+                "damping='adaptive' (message_passing.py:151-185) is not on the device path yet")
+        if not (isinstance(damping, float) or isinstance(damping, list)):
+            raise ValueError("damping must be 'adaptive', float or list")
+        if isinstance(damping, float):
+            damping = [(x_id, d, damping) for d in ("fwd", "bwd") for x_id in self.variable_ids]
+        into = {(self.x_id, "fwd"): "e1", (self.x_id, "bwd"): "e7",
+                (self.z_id, "fwd"): "e3", (self.z_id, "bwd"): "e5"}
+        for id, direction, damp in damping:
+            if (id, direction) not in into:
+                raise ValueError(f"no factor->variable edge into {id!r} with direction {direction!r}")
+            self.damp[into[(id, direction)]] = float(damp or 0.0)
+
+    def _descriptor(self, rec=None, max_records=0, early=None):
+        st = self._ensure_state()
+        lin = self.linear
+        p = _lib.ptr
+        sw = _lib.TrbSweep()
+        sw.B, sw.N, sw.M, sw.R = self.B, self.N, self.M, lin.R
+        sw.ldn, sw.ldm, sw.rank, sw.nslots = lin.ldn, lin.ldm, lin.rank, st["nslots"]
+        sw.prior = self.prior._trb_factor()
+        sw.lik = self.lik._trb_factor()
+        sw.lin_amin, sw.lin_amax = lin.AMIN, lin.AMAX
+        shared = lin.s.shape[0] == 1
+        sw.Vt, sw.strideV = p(lin.Vt), 0 if shared else lin.Vt.stride(0)
+        sw.Ut, sw.strideU = p(lin.Ut), 0 if shared else lin.Ut.stride(0)
+        sw.s, sw.s2, sw.stride_s = p(lin.s), p(lin.s2), 0 if shared else lin.s.stride(0)
+        sw.y, sw.x_true = p(st["y"]), p(st["x_true"])
+        sw.edge_a = p(st["edge_a"])
+        sw.b1, sw.b3, sw.b5, sw.b7 = p(st["b1"]), p(st["b3"]), p(st["b5"]), p(st["b7"])
+        sw.b6_init, sw.b8_init = p(st["b6_init"]), p(st["b8_init"])
+        sw.damp1, sw.damp3, sw.damp5, sw.damp7 = (self.damp[k] for k in ("e1", "e3", "e5", "e7"))
+        sw.rx, sw.rz, sw.vx, sw.vz = p(st["rx"]), p(st["rz"]), p(st["vx"]), p(st["vz"])
+        sw.tz, sw.tx, sw.coef, sw.part = p(st["tz"]), p(st["tx"]), p(st["coef"]), p(st["part"])
+        sw.scr_n, sw.scr_m, sw.vlin, sw.stats = p(st["scr_n"]), p(st["scr_m"]), p(st["vlin"]), p(st["stats"])
+        sw.active, sw.flags, sw.n_iter = p(st["active"]), p(st["flags"]), p(st["n_iter"])
+        rec = rec or {}
+        sw.rec_mse, sw.rec_smse = p(rec.get("mse")), p(rec.get("smse"))
+        sw.rec_vx, sw.rec_vz, sw.rec_tol = p(rec.get("vx")), p(rec.get("vz")), p(rec.get("tol"))
+        sw.max_records = max_records
+        if early is not None:
+            sw.es_tol, sw.es_max_increase = early.tol, early.max_increase
+            sw.es_wait_increase, sw.es_vars = early.wait_increase, early._var_mask(self)
+        else:
+            sw.es_tol, sw.es_max_increase, sw.es_wait_increase, sw.es_vars = -1.0, 0.0, 0, 3
+        sw.gemv_impl = self.gemv_impl
+        return sw
+
+    def _run(self, sw, it0, n_iter, fresh):
+        _lib.check(_lib.load().trb_sweep_run(C.byref(sw), it0, n_iter, int(fresh),
+                                             _lib.current_stream()))
+
+    def _raise_on_nan(self, flags):
+        """reference message_passing.py:187-209 (check_message)."""
+        bad = np.nonzero(flags & (_lib.FLAG_NAN_A | _lib.FLAG_NAN_B))[0]
+        if bad.size:
+            what = "a" if (flags[bad[0]] & _lib.FLAG_NAN_A) else "b"
+            where = f" in instance(s) {bad.tolist()}" if self.batched else ""
+            raise ValueError(f"EP message {what} is nan{where}")
+        if (flags & _lib.FLAG_NEG_A).any():
+            logger.warning("negative a in an EP message")
+
+    # ---------------------------------------------------------------- iterate
+    def iterate(self, max_iter=200, callback=None, initializer=None, damping=None,
+                warm_start=False, update_dA=False):
+        """reference message_passing.py:330-357."""
+        initializer = initializer or ConstantInit(a=0, b=0)
+        callback = callback or self.default_stopping
+        if update_dA:
+            raise NotImplementedError("update_dA is not on the device path yet")
+        if warm_start:
+            if not self._has_messages:
+                raise ValueError("message dag was never initialized")
+            logger.info(f"warm start with n_iter={self.n_iter} no initialization")
+        else:
+            logger.info(f"init message dag with {initializer}")
+            self.init_message_dag(initializer)
+            self.n_iter = 0
+        self.configure_damping(damping)
+        st = self._ensure_state()
+        st["active"].fill_(1)
+        st["flags"].zero_()
+        st["n_iter"].zero_()
+        fresh = not warm_start
+        if isinstance(callback, Callback) and callback.device_replayable(self):
+            self._iterate_device(max_iter, callback, fresh)
+        else:
+            self._iterate_synchronous(max_iter, callback, fresh)
+        logger.info(f"terminated after n_iter={self.n_iter} iterations")
+
+    def _iterate_device(self, max_iter, callback, fresh):
+        """Whole sweep on the device; the callbacks are fed the recorded trajectory."""
+        t = ops.torch()
+        st = self._state
+        cfg = {}
+        callback.device_config(cfg)
+        st["x_true"] = None
+        if cfg.get("x_true") is not None:
+            st["x_true"] = self._vec_to_dev(cfg["x_true"], "x")
+        early = cfg.get("early_stopping")
+        rec = {k: t.full((max(max_iter, 1), self.B), float("nan"), dtype=t.float64,
+                         device=st["vx"].device)
+               for k in ("mse", "smse", "vx", "vz", "tol")}
+        sw = self._descriptor(rec, max_iter, early)
+        chunk = max_iter if early is None else 16
+        it = 0
+        while it < max_iter:
+            k = min(chunk, max_iter - it)
+            self._run(sw, it, k, fresh and it == 0)
+            it += k
+            if early is not None and not bool(st["active"].any().item()):
+                break
+        n_iter = st["n_iter"].cpu().numpy()
+        flags = st["flags"].cpu().numpy()
+        self.flags = flags
+        self.n_iter_per_instance = self.n_iter + n_iter
+        n_done = int(n_iter.max()) if n_iter.size else 0
+        self.n_iter += n_done
+        self._raise_on_nan(flags)
+        if (flags & _lib.FLAG_DIVERGED).any():
+            logger.warning("EarlyStoppingEP: increase above max_increase in instance(s) "
+                           f"{np.nonzero(flags & _lib.FLAG_DIVERGED)[0].tolist()}")
+        rec_h = {k: v[:n_done].cpu().numpy() for k, v in rec.items()}
+        self.records = rec_h
+        for i in range(n_done):
+            callback.replay(self, i, max_iter, rec_h)
+
+    def _iterate_synchronous(self, max_iter, callback, fresh):
+        """Arbitrary user callback: one device sweep iteration, then the callback
+        (which may read any state through get_variables_data)."""
+        st = self._state
+        st["x_true"] = None
+        sw = self._descriptor()
+        for i in range(max_iter):
+            self._run(sw, i, 1, fresh and i == 0)
+            self._raise_on_nan(st["flags"].cpu().numpy())
+            self.n_iter += 1
+            stop = callback(self, i, max_iter)
+            if stop:
+                return
+        self.n_iter_per_instance = np.full(self.B, self.n_iter)
+
+    # ------------------------------------------------------------ inspection
+    def snapshot(self):
+        st = self._ensure_state()
+        keys = ("edge_a", "b1", "b3", "b5", "b7", "rx", "rz", "vx", "vz", "tx", "tz")
+        return MessageSnapshot({k: st[k].clone() for k in keys}, self.n_iter)
+
+    def reset_message_dag(self, snapshot):
+        """reference message_passing.py:234-239."""
+        st = self._ensure_state()
+        for k, v in snapshot.tensors.items():
+            st[k].copy_(v)
+
+    def _out(self, t, n=None):
+        x = t.cpu().numpy()
+        if n is not None:
+            x = x[:, :n]
+        if not self.batched:
+            x = x[0]
+            return float(x) if n is None else x
+        return x
+
+    def get_variables_data(self, ids="all"):
+        """reference message_passing.py:271-276: {id: dict(shape, r, v)}."""
+        st = self._ensure_state()
+        data = {}
+        if ids == "all" or self.x_id in ids:
+            data[self.x_id] = dict(shape=self._var_shape("x"), r=self._out(st["rx"], self.N),
+                                   v=self._out(st["vx"]))
+        if ids == "all" or self.z_id in ids:
+            data[self.z_id] = dict(shape=self._var_shape("z"), r=self._out(st["rz"], self.M),
+                                   v=self._out(st["vz"]))
+        return data
+
+    def get_variable_data(self, id):
+        data = self.get_variables_data([id])
+        if id not in data:
+            raise ValueError(f"id={id} not in variables")
+        return data[id]
+
+    def _edge(self, name):
+        """(a, b) of one edge as host arrays."""
+        st = self._ensure_state()
+        _, role, direction, idx = next(e for e in EDGES if e[0] == name)
+        src = {"e1": "b1", "e2": "b1", "e3": "b3", "e4": "b3",
+               "e5": "b5", "e6": "b5", "e7": "b7", "e8": "b7"}[name]
+        n = self.N if role == "x" else self.M
+        a = st["edge_a"][idx].cpu().numpy()
+        return (a if self.batched else float(a[0])), self._out(st[src], n)
+
+    def get_edges_data(self, keys):
+        """reference message_passing.py:278-287."""
+        factor_of = {"e1": self.prior, "e8": self.prior, "e2": self.linear, "e7": self.linear,
+                     "e3": self.linear, "e6": self.linear, "e4": self.lik, "e5": self.lik}
+        into = {"e1": "e1", "e3": "e3", "e5": "e5", "e7": "e7"}
+        records = []
+        for name, role, direction, idx in EDGES:
+            a, b = self._edge(name)
+            x_id = self.x_id if role == "x" else self.z_id
+            full = dict(a=a, b=b, direction=direction, n_iter=self.n_iter, tau=None,
+                        shape=self._var_shape(role),
+                        damping=(self.damp.get(into.get(name)) or None) if hasattr(self, "damp") else None)
+            record = dict(x_id=x_id, f_id=factor_of[name].id)
+            for key in keys:
+                record[key] = full.get(key)
+            records.append(record)
+        return records

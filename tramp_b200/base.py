@@ -1,0 +1,232 @@
+"""Base classes of the model/plugin API (mirrors reference tramp/base.py).
+
+`Variable` and `Factor` keep the reference's names, arities and message
+conventions (`message = [(source, target, data)]`, data = dict(a, b, direction)),
+so that user-written factors and the reference's own tests read the same.  The
+arithmetic behind the in-scope factors runs on the GPU through tramp_b200.ops.
+"""
+import logging
+import numpy as np
+
+from . import ops
+
+logger = logging.getLogger(__name__)
+
+
+class ReprMixin():
+    """reference base.py:10-32."""
+    _repr_initialized = False
+
+    def repr_init(self, pad=None, reinit=False):
+        if reinit or not self._repr_initialized:
+            self._repr_kwargs = self.__dict__.copy()
+            self._repr_pad = pad
+            self._repr_initialized = True
+
+    def __repr__(self):
+        pad = f"\n{self._repr_pad}" if self._repr_pad else ""
+        args = ",".join(f"{pad}{key}={val}" for key, val in self._repr_kwargs.items())
+        if self._repr_pad:
+            args += "\n"
+        return f"{self.__class__.__name__}({args})"
+
+
+def filter_message(message, direction):
+    """reference base.py:35-41."""
+    return [(s, t, d) for s, t, d in message if d["direction"] == direction]
+
+
+def inv(v):
+    """Numerically safe inverse (reference base.py:44-46)."""
+    if ops.is_tensor(v):
+        return 1 / v.clamp_min(1e-20)
+    return 1 / np.maximum(v, 1e-20)
+
+
+def _clip(x, lo, hi):
+    if ops.is_tensor(x):
+        return x.clamp(lo, hi)
+    return np.clip(x, lo, hi)
+
+
+class Variable(ReprMixin):
+    """reference base.py:49-233 (EP part)."""
+
+    def __init__(self, id, n_prev, n_next):
+        self.id = id
+        self.n_prev = n_prev
+        self.n_next = n_next
+        self.repr_init()
+
+    def __add__(self, other):
+        from .models.dag_algebra import DAG
+        return DAG(self) + other
+
+    def __matmul__(self, other):
+        from .models.dag_algebra import DAG
+        return DAG(self) @ other
+
+    def math(self):
+        return r"$" + self.id + r"$"
+
+    def posterior_ab(self, message):
+        """reference base.py:152-155."""
+        a_hat = sum(data["a"] for source, target, data in message)
+        b_hat = sum(data["b"] for source, target, data in message)
+        return a_hat, b_hat
+
+    def posterior_rv(self, message):
+        """reference base.py:157-161."""
+        a_hat, b_hat = self.posterior_ab(message)
+        return b_hat / a_hat, 1. / a_hat
+
+    def compute_log_partition(self, ax, bx):
+        """reference base.py:146-150 (a SUM over components; inf if ax <= 0)."""
+        if ax <= 0:
+            return np.inf
+        return 0.5 * np.sum(bx**2 / ax + np.log(2 * np.pi / ax))
+
+    def log_partition(self, message):
+        ax, bx = self.posterior_ab(message)
+        return self.compute_log_partition(ax, bx)
+
+
+class Factor(ReprMixin):
+    """reference base.py:236-365 (EP part)."""
+
+    AMAX = ops.AMAX
+    AMIN = ops.AMIN
+
+    def reset_precision_bounds(self, AMIN, AMAX):
+        """reference base.py:241-243."""
+        self.AMIN = AMIN
+        self.AMAX = AMAX
+
+    def compute_a_new(self, v, a):
+        return _clip(inv(v) - a, self.AMIN, self.AMAX)
+
+    def compute_ab_new(self, r, v, a, b):
+        """a_new clipped to [AMIN, AMAX]; b_new = r (a + a_new) - b (reference base.py:250-255)."""
+        a_new = _clip(inv(v) - a, self.AMIN, self.AMAX)
+        v_inv = (a + a_new)
+        if ops.is_tensor(r) and r.dim() == 2 and ops.is_tensor(v_inv) and v_inv.dim() == 1:
+            v_inv = v_inv[:, None]
+        elif isinstance(r, np.ndarray) and r.ndim == 2 and np.ndim(v_inv) == 1:
+            v_inv = np.asarray(v_inv)[:, None]
+        b_new = r * v_inv - b
+        return a_new, b_new
+
+    def __add__(self, other):
+        from .models.dag_algebra import DAG
+        return DAG(self) + other
+
+    def __matmul__(self, other):
+        from .models.dag_algebra import DAG
+        return DAG(self) @ other
+
+    def _parse_message_ab(self, message):
+        """reference base.py:285-306."""
+        z_message = filter_message(message, "fwd")
+        assert len(z_message) == self.n_prev
+        az = [data["a"] for source, target, data in z_message]
+        bz = [data["b"] for source, target, data in z_message]
+        z_source = [source for source, target, data in z_message]
+        if self.n_prev == 1:
+            az, bz, z_source = az[0], bz[0], z_source[0]
+        x_message = filter_message(message, "bwd")
+        assert len(x_message) == self.n_next
+        ax = [data["a"] for source, target, data in x_message]
+        bx = [data["b"] for source, target, data in x_message]
+        x_source = [source for source, target, data in x_message]
+        if self.n_next == 1:
+            ax, bx, x_source = ax[0], bx[0], x_source[0]
+        return z_source, x_source, az, bz, ax, bx
+
+    def forward_message(self, message):
+        """reference base.py:329-346 (single next variable)."""
+        if self.n_next == 0:
+            return []
+        z_source, x_source, az, bz, ax, bx = self._parse_message_ab(message)
+        if self.n_prev == 0:
+            ax_new, bx_new = self.compute_forward_message(ax, bx)
+        else:
+            ax_new, bx_new = self.compute_forward_message(az, bz, ax, bx)
+        if self.n_next != 1:
+            raise NotImplementedError("multi-edge factors are outside the EP hot path")
+        return [(self, x_source, dict(a=ax_new, b=bx_new, direction="fwd"))]
+
+    def backward_message(self, message):
+        """reference base.py:348-365 (single previous variable)."""
+        if self.n_prev == 0:
+            return []
+        z_source, x_source, az, bz, ax, bx = self._parse_message_ab(message)
+        if self.n_next == 0:
+            az_new, bz_new = self.compute_backward_message(az, bz)
+        else:
+            az_new, bz_new = self.compute_backward_message(az, bz, ax, bx)
+        if self.n_prev != 1:
+            raise NotImplementedError("multi-edge factors are outside the EP hot path")
+        return [(self, z_source, dict(a=az_new, b=bz_new, direction="bwd"))]
+
+    def log_partition(self, message):
+        """reference base.py:367-375."""
+        z_source, x_source, az, bz, ax, bx = self._parse_message_ab(message)
+        if self.n_prev == 0:
+            return self.compute_log_partition(ax, bx)
+        if self.n_next == 0:
+            return self.compute_log_partition(az, bz, self.y)
+        return self.compute_log_partition(az, bz, ax, bx)
+
+
+# ---------------------------------------------------------------------------
+# array plumbing shared by the separable factors
+# ---------------------------------------------------------------------------
+class _Arg:
+    """Normalises (a, b[, y]) arguments of the factor API to device tensors.
+
+    b: (n,) or (B, n) numpy array / tensor.  a: scalar, (B,), or same shape as b
+    (isotropic=False).  Results are returned in the caller's array type and
+    shape: numpy in -> numpy out, device tensor in -> device tensor out."""
+
+    def __init__(self, a, b, y=None):
+        self.numpy_out = not ops.is_tensor(b)
+        b_ = ops.to_dev(b)
+        self.batched = (b_.dim() == 2)
+        if b_.dim() > 2:
+            raise ValueError("b must be 1-d (one instance) or 2-d (batch, n)")
+        self.shape = tuple(b_.shape)
+        b2 = b_ if self.batched else b_[None, :]
+        self.B, self.n = b2.shape
+        self.b = ops.padded(b2)
+        self.ld = self.b.shape[1]
+        a_ = ops.to_dev(a)
+        if a_.numel() == 1 and not (a_.dim() >= 1 and self.n == 1 and not self.batched):
+            self.a_elementwise = False                      # one precision for everything
+            self.a = a_.reshape(1).expand(self.B).contiguous()
+        elif self.batched and tuple(a_.shape) == (self.B,):
+            self.a_elementwise = False                      # one precision per instance
+            self.a = a_
+        elif tuple(a_.shape) == self.shape:
+            self.a_elementwise = True                       # isotropic=False: one per component
+            self.a = ops.padded(a_ if self.batched else a_[None, :], self.ld)
+        else:
+            raise ValueError(f"a of shape {tuple(a_.shape)} does not match b of shape {self.shape}")
+        self.y = None
+        if y is not None:
+            y_ = ops.to_dev(y)
+            y2 = y_ if y_.dim() == 2 else y_[None, :]
+            if y2.shape[0] == 1 and self.B > 1:
+                y2 = y2.expand(self.B, -1)
+            self.y = ops.padded(y2.contiguous(), self.ld)
+
+    def vec_out(self, t):
+        t = t[:, :self.n]
+        if not self.batched:
+            t = t[0]
+        return t.cpu().numpy() if self.numpy_out else t.contiguous()
+
+    def scalar_out(self, t):
+        if self.numpy_out:
+            x = t.cpu().numpy()
+            return x if self.batched else float(x[0])
+        return t if self.batched else t[0]

@@ -1,0 +1,273 @@
+"""LinearChannel x = W z with the Gaussian posterior diagonalised by a THIN SVD.
+
+reference: channels/linear/linear_channel.py.  The reference keeps the full
+U (Nx x Nx), V (Nz x Nz) and a dense rectangular S and applies nine dense
+GEMVs per EP iteration.  Here W = U_R diag(s) V_R^T with R = min(Nx, Nz); the
+operators live on the GPU as rows of singular vectors (`Vt[B, R, ldn]`,
+`Ut[B, R, ldm]`) and every mean is  project -> spectrum rescale -> expand
+(tramp_b200/csrc/trb_linear.cu).  With bz fixed inside an iteration this
+streams each operator once per use.
+"""
+import logging
+import numpy as np
+
+from .base_channel import Channel
+from ..base import _Arg
+from .. import ops
+
+logger = logging.getLogger(__name__)
+
+
+def thin_svd_device(W, method="svd"):
+    """W: device tensor [B, M, N] -> (Ut [B,R,M], s [B,R], Vt [B,R,N]), s descending.
+
+    method "svd": cuSOLVER SVD through torch.linalg (any W).
+    method "gram": eigh of the smaller Gram matrix, for well-conditioned W only
+    (cond^2 must stay far below 1/eps): much cheaper for large batches.
+    Setup is outside the EP hot path (the reference reports it separately as
+    svd_time, examples/figures/compute_benchmark.py:27)."""
+    t = ops.torch()
+    B, M, N = W.shape
+    if method == "svd":
+        U, s, Vh = t.linalg.svd(W, full_matrices=False)
+        return U.transpose(1, 2).contiguous(), s.contiguous(), Vh.contiguous()
+    if method != "gram":
+        raise ValueError(f"unknown svd method {method!r}")
+    if M <= N:
+        G = W @ W.transpose(1, 2)
+        ev, U = t.linalg.eigh(G)
+        ev, U = ev.flip(-1), U.flip(-1)
+        s = ev.clamp_min(0).sqrt()
+        Ut = U.transpose(1, 2).contiguous()
+        Vt = (Ut @ W) / s[:, :, None]
+        return Ut, s, Vt.contiguous()
+    G = W.transpose(1, 2) @ W
+    ev, V = t.linalg.eigh(G)
+    ev, V = ev.flip(-1), V.flip(-1)
+    s = ev.clamp_min(0).sqrt()
+    Vt = V.transpose(1, 2).contiguous()
+    Ut = (Vt @ W.transpose(1, 2)) / s[:, :, None]
+    return Ut.contiguous(), s, Vt
+
+
+class LinearChannel(Channel):
+    """Linear channel x = W z.
+
+    Parameters
+    ----------
+    - W: array of shape (Nx, Nz), or (B, Nx, Nz) for B independent instances
+      (numpy array or device tensor)
+    - precompute_svd: kept for signature compatibility; the SVD form is the
+      only one implemented (the reference's `False` branch solves a dense
+      system per call and is not on the benchmarked path)
+    - name: str, name of weight matrix W for display
+    - svd_method: "svd" | "gram" (extension, see thin_svd_device)
+    """
+
+    def __init__(self, W, precompute_svd=True, name="W", svd_method="svd", keep_W=True):
+        self.name = name
+        self.Nx = int(W.shape[-2])
+        self.Nz = int(W.shape[-1])
+        self.precompute_svd = precompute_svd
+        self.repr_init()
+        if not precompute_svd:
+            raise NotImplementedError("LinearChannel(precompute_svd=False) is not on the EP hot path")
+        self.batch = int(W.shape[0]) if len(W.shape) == 3 else None
+        self.W = W if keep_W else None
+        self.alpha = self.Nx / self.Nz
+        self._ops_ready = False
+        self._svd_method = svd_method
+        self._W_for_setup = W
+
+    # ---- device setup (lazy: building a model never needs the GPU) ----------
+    @classmethod
+    def from_factors(cls, Ut, s, Vt, Nx, Nz, rank=None, name="W"):
+        """Build from thin-SVD factors already on the device:
+        Ut [Bop, R, ldm], s [Bop, R], Vt [Bop, R, ldn] (rows zero-padded)."""
+        self = cls.__new__(cls)
+        self.name, self.Nx, self.Nz, self.precompute_svd = name, int(Nx), int(Nz), True
+        self.repr_init()
+        self.batch = int(Ut.shape[0]) if Ut.shape[0] > 1 else None
+        self.W = None
+        self.alpha = self.Nx / self.Nz
+        self._install(Ut, s, Vt, rank)
+        return self
+
+    def _install(self, Ut, s, Vt, rank=None):
+        t = ops.torch()
+        self.R = int(s.shape[-1])
+        self.ldn, self.ldm = int(Vt.shape[-1]), int(Ut.shape[-1])
+        self.Ut, self.Vt = Ut, Vt
+        self.s = s.contiguous()
+        self.s2 = (self.s * self.s).contiguous()
+        if rank is None:
+            # np.linalg.matrix_rank: s > s.max() * max(M, N) * eps (reference :37)
+            tol = self.s.max(dim=-1, keepdim=True).values * max(self.Nx, self.Nz) * np.finfo(float).eps
+            ranks = (self.s > tol).sum(dim=-1)
+            rank = int(ranks.min().item())
+            if int(ranks.max().item()) != rank:
+                raise NotImplementedError("instances of one batch must share the same rank")
+        self.rank = int(rank)
+        self._ops_ready = True
+
+    def _setup(self):
+        if self._ops_ready:
+            return
+        t = ops.torch()
+        W = ops.to_dev(self._W_for_setup)
+        if W.dim() == 2:
+            W = W[None]
+        Ut, s, Vt = thin_svd_device(W, self._svd_method)
+        B, R = s.shape
+        Vt_p = t.zeros((B, R, ops.pad_ld(self.Nz)), dtype=t.float64, device=W.device)
+        Vt_p[:, :, :self.Nz] = Vt
+        Ut_p = t.zeros((B, R, ops.pad_ld(self.Nx)), dtype=t.float64, device=W.device)
+        Ut_p[:, :, :self.Nx] = Ut
+        self._install(Ut_p, s, Vt_p)
+        self._W_for_setup = None
+
+    # ---- reference attributes ----------------------------------------------
+    @property
+    def spectrum(self):
+        """diag(S^T S), length Nz with zeros beyond R (reference :41)."""
+        self._setup()
+        s2 = self.s2.cpu().numpy()
+        out = np.zeros(s2.shape[:-1] + (self.Nz,))
+        out[..., :self.R] = s2
+        return out[0] if self.batch is None else out
+
+    @property
+    def singular(self):
+        return self.spectrum[..., :self.rank]
+
+    def _dense_W(self):
+        if self.W is not None:
+            return np.asarray(self.W.cpu().numpy() if ops.is_tensor(self.W) else self.W)
+        self._setup()
+        t = ops.torch()
+        W = t.einsum("brm,br,brn->bmn", self.Ut[:, :, :self.Nx], self.s, self.Vt[:, :, :self.Nz])
+        W = W.cpu().numpy()
+        return W[0] if self.batch is None else W
+
+    def sample(self, Z):
+        """X = W Z (reference :48-50); host-side, used only to draw teacher data
+        and to infer shapes."""
+        W = self._dense_W()
+        Z = np.asarray(Z)
+        if W.ndim == 3:
+            return np.einsum("bmn,bn->bm", W, Z)
+        if Z.ndim == 2:       # shared W, batch of signals
+            return Z @ W.T
+        return W @ Z
+
+    def math(self):
+        return r"$" + self.name + "$"
+
+    def second_moment(self, tau_z):
+        return tau_z * self.spectrum.sum(axis=-1) / self.Nx
+
+    # ---- EP factor API --------------------------------------------------------
+    def _args(self, az, bz, ax, bx):
+        self._setup()
+        az_arg = _Arg(az, bz)
+        ax_arg = _Arg(ax, bx)
+        if az_arg.a_elementwise or ax_arg.a_elementwise:
+            raise ValueError("LinearChannel needs scalar precisions az, ax (isotropic beliefs)")
+        if az_arg.n != self.Nz or ax_arg.n != self.Nx:
+            raise ValueError(f"expected bz of size {self.Nz} and bx of size {self.Nx}")
+        if az_arg.B != ax_arg.B:
+            raise ValueError("bz and bx disagree on the batch size")
+        return az_arg, ax_arg
+
+    def _means(self, az, bz, ax, bx, want):
+        zarg, xarg = self._args(az, bz, ax, bx)
+        B = zarg.B
+        bz_d = ops.padded(zarg.b[:, :self.Nz], self.ldn)
+        bx_d = ops.padded(xarg.b[:, :self.Nx], self.ldm)
+        tz = ops.lin_project(self.Vt, self.R, self.Nz, bz_d, B)     # V.T @ bz  (:73)
+        tx = ops.lin_project(self.Ut, self.R, self.Nx, bx_d, B)     # U.T @ bx  (:72)
+        out = {}
+        if "rz" in want or "vz" in want:
+            coef, vz = ops.lin_rescale(1, B, self.R, self.Nz, self.Nx, self.rank, self.s, self.s2,
+                                       zarg.a, xarg.a, tz, tx)
+            null = self.R < self.Nz
+            rz = ops.lin_expand(self.Vt, self.R, self.Nz, coef, B,
+                                add=bz_d if null else None, add_div=zarg.a if null else None)
+            out["rz"], out["vz"] = zarg.vec_out(rz), zarg.scalar_out(vz)
+        if "rx" in want or "vx" in want:
+            coef, vx = ops.lin_rescale(0, B, self.R, self.Nz, self.Nx, self.rank, self.s, self.s2,
+                                       zarg.a, xarg.a, tz, tx)
+            rx = ops.lin_expand(self.Ut, self.R, self.Nx, coef, B)
+            out["rx"], out["vx"] = xarg.vec_out(rx), xarg.scalar_out(vx)
+        out["_tz"], out["_tx"], out["_zarg"], out["_xarg"] = tz, tx, zarg, xarg
+        return out
+
+    def compute_backward_mean(self, az, bz, ax, bx):
+        """reference :69-83."""
+        return self._means(az, bz, ax, bx, ("rz",))["rz"]
+
+    def compute_forward_mean(self, az, bz, ax, bx):
+        """reference :85-89."""
+        return self._means(az, bz, ax, bx, ("rx",))["rx"]
+
+    def _variance(self, direction, az, ax):
+        self._setup()
+        t = ops.torch()
+        az_d, ax_d = ops.to_dev(az).reshape(-1), ops.to_dev(ax).reshape(-1)
+        B = max(az_d.numel(), ax_d.numel())
+        az_d, ax_d = az_d.expand(B).contiguous(), ax_d.expand(B).contiguous()
+        if self.s.shape[0] not in (1, B):
+            raise ValueError("az/ax batch does not match the operator batch")
+        zero = t.zeros((B, self.R), dtype=t.float64, device=self.s.device)
+        _, v = ops.lin_rescale(direction, B, self.R, self.Nz, self.Nx, self.rank, self.s, self.s2,
+                               az_d, ax_d, zero, zero)
+        numpy_out = not (ops.is_tensor(az) or ops.is_tensor(ax))
+        if numpy_out:
+            v = v.cpu().numpy()
+            return float(v[0]) if (np.ndim(az) == 0 and np.ndim(ax) == 0) else v
+        return v
+
+    def compute_backward_variance(self, az, ax):
+        """reference :91-97."""
+        return self._variance(1, az, ax)
+
+    def compute_forward_variance(self, az, ax):
+        """reference :99-105."""
+        return self._variance(0, az, ax)
+
+    def compute_n_eff(self, az, ax):
+        """reference :58-67, recovered from the backward variance identity is
+        avoided: evaluated directly on the host copy of the spectrum (cold path)."""
+        if ax == 0:
+            return 0.
+        if az / ax == 0:
+            return self.rank / self.Nz
+        singular = self.singular
+        return np.sum(singular / (az / ax + singular), axis=-1) / self.Nz
+
+    def compute_backward_posterior(self, az, bz, ax, bx):
+        """reference :107-111."""
+        o = self._means(az, bz, ax, bx, ("rz", "vz"))
+        return o["rz"], o["vz"]
+
+    def compute_forward_posterior(self, az, bz, ax, bx):
+        """reference :113-117."""
+        o = self._means(az, bz, ax, bx, ("rx", "vx"))
+        return o["rx"], o["vx"]
+
+    def compute_log_partition(self, az, bz, ax, bx):
+        """reference :127-132 (a SUM): 0.5 sum(b rz) + 0.5 sum log(2 pi / a) with
+        b = bz + W^T bx, a = az + ax spectrum.  Cold path (log_evidence): the
+        GEMVs run in the CUDA kernels, the final dot/log-sum in torch."""
+        t = ops.torch()
+        o = self._means(az, bz, ax, bx, ("rz",))
+        zarg, xarg = o["_zarg"], o["_xarg"]
+        B = zarg.B
+        rz = ops.to_dev(o["rz"]).reshape(B, self.Nz)
+        wt_bx = ops.lin_expand(self.Vt, self.R, self.Nz,
+                               (self.s * o["_tx"]).contiguous(), B)[:, :self.Nz]
+        b = zarg.b[:, :self.Nz] + wt_bx
+        a = zarg.a[:, None] + xarg.a[:, None] * self.s2
+        logZ = 0.5 * (b * rz).sum(-1) + 0.5 * t.log(2 * np.pi / a).sum(-1) \
+            + 0.5 * (self.Nz - self.R) * t.log(2 * np.pi / zarg.a)
+        return zarg.scalar_out(logZ)

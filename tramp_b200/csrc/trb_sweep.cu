@@ -178,7 +178,9 @@ k_x_update(trb_sweep sw, int G, int it, double* __restrict__ stats) {
     if (it > 0) {
       const double tol_x = sqrt(d2 / N) / sqrt(n2 / N);
       const double tol_z = sqrt(stats[b * 4 + 0] / sw.M) / sqrt(stats[b * 4 + 1] / sw.M);
-      tol = (tol_z > tol_x) ? tol_z : tol_x;
+      const int vars = sw.es_vars ? sw.es_vars : 3;
+      tol = (vars & 1) ? tol_x : tol_z;
+      if ((vars & 2) && tol_z > tol) tol = tol_z;
       if (sw.es_tol >= 0) {
         if (tol < sw.es_tol) {
           sw.active[b] = 0;
