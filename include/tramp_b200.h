@@ -79,6 +79,15 @@ size_t trb_sizeof_sweep(void);
 /* number of SMs of the current device (0 if no device) */
 int trb_device_sm_count(void);
 
+/* Launch accounting for benchmarks: trb_profile_reset(enable_events) zeroes the
+ * counters (and, if enable_events, brackets every GEMV launch with CUDA events
+ * on its stream); trb_profile_launches(kind) = kernels launched since then
+ * (kind 0 elementwise/update, 1 GEMV, -1 all); trb_profile_gemv_ms sums the
+ * event-timed GEMV durations and returns how many launches were timed. */
+void trb_profile_reset(int enable_events);
+long long trb_profile_launches(int kind);
+int trb_profile_gemv_ms(double* total_ms);
+
 /* ---- elementwise moment kernels ------------------------------------------
  * a_mode: 0 = one precision per instance a[B] (isotropic beliefs), 1 = one per
  * element a[B, ld] (isotropic=False in the reference's unit tests).

@@ -140,6 +140,18 @@ class MessagePassing():
         st = self._ensure_state()
         t = ops.torch()
         ids = {"x": self.x_id, "z": self.z_id}
+        if type(initializer) is ConstantInit and np.ndim(initializer.a) == 0 \
+                and np.ndim(initializer.b) == 0:
+            # same messages as the generic path below, without shipping
+            # B x N constants over PCIe
+            st["edge_a"].fill_(float(initializer.a))
+            for k in ("b1", "b3", "b5", "b7"):
+                st[k].fill_(float(initializer.b))
+            st["b6_init"] = st["b8_init"] = None
+            for k in ("rx", "rz", "vx", "vz"):
+                st[k].zero_()
+            self._has_messages = True
+            return
         init_b = {}
         for name, role, direction, idx in EDGES:
             shape = self._var_shape(role)

@@ -160,6 +160,11 @@ class LinearChannel(Channel):
             return Z @ W.T
         return W @ Z
 
+    def infer_shape(self, z_shape):
+        """Output shape without forming W z (sample() draws nothing from the RNG,
+        so skipping it in Model.init_shapes keeps seed parity)."""
+        return [tuple(z_shape[:-1]) + (self.Nx,)]
+
     def math(self):
         return r"$" + self.name + "$"
 

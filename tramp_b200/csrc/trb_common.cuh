@@ -24,6 +24,16 @@ int trb_set_error(int code, const char* fmt, ...);
 
 int trb_sm_count_cached();
 
+// Launch accounting / optional per-kernel CUDA-event timing (trb_profile_*).
+// kind: 0 = elementwise / update kernels, 1 = GEMV (project / expand).
+void trb_note_launch(int kind, cudaStream_t st, bool before);
+struct trb_launch_scope {
+  int kind;
+  cudaStream_t st;
+  trb_launch_scope(int k, cudaStream_t s) : kind(k), st(s) { trb_note_launch(kind, st, true); }
+  ~trb_launch_scope() { trb_note_launch(kind, st, false); }
+};
+
 // --------------------------------------------------------------- device side
 namespace trb {
 

@@ -30,6 +30,65 @@ int trb_sm_count_cached() {
   return sm;
 }
 
+// ---- launch accounting -------------------------------------------------------
+#include <vector>
+namespace {
+struct ProfileState {
+  bool enabled = false;
+  long long launches[2] = {0, 0};
+  std::vector<cudaEvent_t> pool;         // recycled events
+  std::vector<cudaEvent_t> begin[2], end[2];
+};
+ProfileState g_prof;
+cudaEvent_t prof_event() {
+  if (!g_prof.pool.empty()) {
+    cudaEvent_t e = g_prof.pool.back();
+    g_prof.pool.pop_back();
+    return e;
+  }
+  cudaEvent_t e;
+  cudaEventCreate(&e);
+  return e;
+}
+}  // namespace
+
+void trb_note_launch(int kind, cudaStream_t st, bool before) {
+  if (before) g_prof.launches[kind] += 1;
+  if (!g_prof.enabled || kind != 1) return;
+  cudaEvent_t e = prof_event();
+  cudaEventRecord(e, st);
+  (before ? g_prof.begin[kind] : g_prof.end[kind]).push_back(e);
+}
+
+extern "C" void trb_profile_reset(int enable_events) {
+  for (int k = 0; k < 2; ++k) {
+    g_prof.launches[k] = 0;
+    for (auto e : g_prof.begin[k]) g_prof.pool.push_back(e);
+    for (auto e : g_prof.end[k]) g_prof.pool.push_back(e);
+    g_prof.begin[k].clear();
+    g_prof.end[k].clear();
+  }
+  g_prof.enabled = enable_events != 0;
+}
+
+extern "C" long long trb_profile_launches(int kind) {
+  return (kind == 0 || kind == 1) ? g_prof.launches[kind] : g_prof.launches[0] + g_prof.launches[1];
+}
+
+// Sum of the CUDA-event durations of the GEMV launches recorded since the last
+// reset; waits for the last one to finish.  Returns the number of timed launches.
+extern "C" int trb_profile_gemv_ms(double* total_ms) {
+  double tot = 0.0;
+  const size_t n = g_prof.end[1].size();
+  if (n) cudaEventSynchronize(g_prof.end[1][n - 1]);
+  for (size_t i = 0; i < n && i < g_prof.begin[1].size(); ++i) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, g_prof.begin[1][i], g_prof.end[1][i]) == cudaSuccess) tot += ms;
+  }
+  if (total_ms) *total_ms = tot;
+  return (int)n;
+}
+
 extern "C" const char* trb_last_error(void) { return trb_err_buf; }
 extern "C" int trb_version(void) { return TRB_VERSION; }
 extern "C" size_t trb_sizeof_factor(void) { return sizeof(trb_factor); }
@@ -176,6 +235,7 @@ extern "C" int trb_factor_posterior(const trb_factor* f, int B, int n, int ld, c
   TRB_CHECK_ARG(B > 0 && n > 0 && ld >= n, "bad shape");
   TRB_CHECK_ARG(f->kind >= 0 && f->kind <= TRB_ABS_LIKELIHOOD, "unknown factor kind");
   TRB_CHECK_ARG(!needs_y(f->kind) || y, "likelihood needs y");
+  trb_launch_scope scope_(0, (cudaStream_t)stream);
   k_factor_posterior<<<B, kEwThreads, 0, (cudaStream_t)stream>>>(*f, n, ld, a, a_mode, b, y, r, v,
                                                                   v_mode);
   TRB_CHECK_LAUNCH();
@@ -189,6 +249,7 @@ extern "C" int trb_factor_log_partition(const trb_factor* f, int B, int n, int l
   TRB_CHECK_ARG(B > 0 && n > 0 && ld >= n, "bad shape");
   TRB_CHECK_ARG(f->kind >= 0 && f->kind <= TRB_ABS_LIKELIHOOD, "unknown factor kind");
   TRB_CHECK_ARG(!needs_y(f->kind) || y, "likelihood needs y");
+  trb_launch_scope scope_(0, (cudaStream_t)stream);
   k_factor_log_partition<<<B, kEwThreads, 0, (cudaStream_t)stream>>>(*f, n, ld, a, a_mode, b, y, A,
                                                                       A_mode);
   TRB_CHECK_LAUNCH();
@@ -203,6 +264,7 @@ extern "C" int trb_factor_message(const trb_factor* f, int B, int n, int ld, con
   TRB_CHECK_ARG(B > 0 && n > 0 && ld >= n, "bad shape");
   TRB_CHECK_ARG(f->kind >= 0 && f->kind <= TRB_ABS_LIKELIHOOD, "unknown factor kind");
   TRB_CHECK_ARG(!needs_y(f->kind) || y, "likelihood needs y");
+  trb_launch_scope scope_(0, (cudaStream_t)stream);
   k_factor_message<<<B, kEwThreads, 0, (cudaStream_t)stream>>>(
       *f, n, ld, a_in, b_in, y, a_io, b_io, a_copy, damping, scratch, flags, active);
   TRB_CHECK_LAUNCH();
@@ -215,6 +277,7 @@ extern "C" int trb_truncated_normal(int n, const double* r0, const double* v0, d
   TRB_CHECK_ARG(r0 && v0, "null pointer");
   TRB_CHECK_ARG(n > 0, "bad shape");
   TRB_CHECK_ARG(zmin < zmax, "zmin must be < zmax");  // truncated_normal.py:236
+  trb_launch_scope scope_(0, (cudaStream_t)stream);
   k_truncated_normal<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(n, r0, v0, zmin, zmax, mean,
                                                                         var, logZ, proba);
   TRB_CHECK_LAUNCH();
@@ -226,6 +289,7 @@ extern "C" int trb_posterior_rv(int B, int n, int ld, const double* a1, const do
                                 void* stream) {
   TRB_CHECK_ARG(a1 && b1 && a2 && b2 && r && v, "null pointer");
   TRB_CHECK_ARG(B > 0 && n > 0 && ld >= n, "bad shape");
+  trb_launch_scope scope_(0, (cudaStream_t)stream);
   k_posterior_rv<<<B, kEwThreads, 0, (cudaStream_t)stream>>>(n, ld, a1, b1, a2, b2, r, v);
   TRB_CHECK_LAUNCH();
   return TRB_OK;

@@ -536,6 +536,7 @@ extern "C" int trb_lin_project(const double* A, int64_t strideA, int R, int n, i
   TmaPlan p;
   const bool tma_ok = plan_tma(ld, p);
   if (impl == 0) impl = tma_ok ? 2 : 1;
+  trb_launch_scope scope_(1, st);
   if (impl == 2) {
     if (!tma_ok) return trb_set_error(TRB_ERR_UNSUPPORTED, "trb_lin_project: ld=%d too large for the TMA ring", ld);
     rc = dispatch_tma<false>(p, geo.G, A, strideA, R, n, ld, B, vec, ldvec, t, 0, active, st);
@@ -566,6 +567,7 @@ extern "C" int trb_lin_expand(const double* A, int64_t strideA, int R, int n, in
   TmaPlan p;
   const bool tma_ok = plan_tma(ld, p);
   if (impl == 0) impl = tma_ok ? 2 : 1;
+  trb_launch_scope scope_(1, st);
   if (impl == 2) {
     if (!tma_ok) return trb_set_error(TRB_ERR_UNSUPPORTED, "trb_lin_expand: ld=%d too large for the TMA ring", ld);
     rc = dispatch_tma<true>(p, geo.G, A, strideA, R, n, ld, B, coef, 0, part, geo.nslots, active, st);
@@ -592,6 +594,7 @@ extern "C" int trb_lin_reduce_slots(int B, int R, int n, int ld, const double* p
   TRB_CHECK_ARG(!add || add_div, "add needs add_div");
   TRB_CHECK_ARG(B > 0 && R > 0 && n > 0 && ld >= n, "bad shape");
   const trb_expand_geom geo = trb_expand_geometry(B, R);
+  trb_launch_scope scope_(0, (cudaStream_t)stream);
   k_reduce_slots<<<B, 256, 0, (cudaStream_t)stream>>>(R, n, ld, B, geo.G, geo.nslots, part, add,
                                                        add_div, out);
   TRB_CHECK_LAUNCH();
@@ -605,6 +608,7 @@ extern "C" int trb_lin_rescale(int dir, int B, int R, int Nz, int Nx, int rank, 
   TRB_CHECK_ARG(s && s2 && az && ax && tz && tx && coef && v, "null pointer");
   TRB_CHECK_ARG(dir == 0 || dir == 1, "dir must be 0 or 1");
   TRB_CHECK_ARG(B > 0 && R > 0 && R <= Nz && R <= Nx && rank >= 0 && rank <= R, "bad shape");
+  trb_launch_scope scope_(0, (cudaStream_t)stream);
   k_lin_rescale<<<B, 256, 0, (cudaStream_t)stream>>>(dir, R, Nz, Nx, rank, s, s2, stride_s, az, ax,
                                                       tz, tx, coef, v, active);
   TRB_CHECK_LAUNCH();

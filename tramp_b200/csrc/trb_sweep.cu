@@ -247,7 +247,10 @@ extern "C" int trb_sweep_run(const trb_sweep* sw, int it0, int n_iter, int fresh
     TRB_TRY(trb_lin_expand(sw->Ut, sw->strideU, sw->R, sw->M, sw->ldm, B, sw->coef, sw->part,
                            sw->active, sw->gemv_impl, stream));
     // Z: e3, likelihood e5, posterior z
-    k_z_update<<<B, kUpThreads, 0, st>>>(*sw, geo.G, first, sw->stats);
+    {
+      trb_launch_scope scope_(0, st);
+      k_z_update<<<B, kUpThreads, 0, st>>>(*sw, geo.G, first, sw->stats);
+    }
     TRB_CHECK_LAUNCH();
     // P3: tx = U_R^T b6 (new)
     TRB_TRY(trb_lin_project(sw->Ut, sw->strideU, sw->R, sw->M, sw->ldm, B, sw->b5, sw->ldm, sw->tx,
@@ -259,7 +262,10 @@ extern "C" int trb_sweep_run(const trb_sweep* sw, int it0, int n_iter, int fresh
     TRB_TRY(trb_lin_expand(sw->Vt, sw->strideV, sw->R, sw->N, sw->ldn, B, sw->coef, sw->part,
                            sw->active, sw->gemv_impl, stream));
     // X: e7, posterior x, records, early stopping
-    k_x_update<<<B, kUpThreads, 0, st>>>(*sw, geo.G, it, sw->stats);
+    {
+      trb_launch_scope scope_(0, st);
+      k_x_update<<<B, kUpThreads, 0, st>>>(*sw, geo.G, it, sw->stats);
+    }
     TRB_CHECK_LAUNCH();
   }
   return TRB_OK;

@@ -23,10 +23,13 @@ class Likelihood(Factor):
     def _trb_factor(self):
         raise NotImplementedError
 
+    def infer_shape(self, z_shape):
+        return None if self.batch is None else []
+
     @property
     def batch(self):
         y = self.y
-        return None if (y is None or np.ndim(y) < 2) else int(np.shape(y)[0])
+        return None if (y is None or len(np.shape(y)) < 2) else int(np.shape(y)[0])
 
     def compute_backward_posterior(self, az, bz, y):
         arg = _Arg(az, bz, y)

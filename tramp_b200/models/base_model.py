@@ -56,10 +56,14 @@ class Model(ReprMixin):
     def init_shapes(self):
         "Compute variable shapes in place (reference :96-109; calls every factor.sample, so it advances the RNG)"
         for factor in self.factors:
-            X_prev = [np.ones(self.dag.node[v]["shape"]) for v in self.dag.predecessors(factor)]
-            X_next = to_list(factor.sample(*X_prev))
-            for x, variable in zip(X_next, self.dag.successors(factor)):
-                self.dag.node[variable].update(shape=x.shape)
+            prev_shapes = [self.dag.node[v]["shape"] for v in self.dag.predecessors(factor)]
+            infer = getattr(factor, "infer_shape", None)
+            shapes = infer(*prev_shapes) if infer is not None else None
+            if shapes is None:
+                X_next = to_list(factor.sample(*[np.ones(s) for s in prev_shapes]))
+                shapes = [x.shape for x in X_next]
+            for shape, variable in zip(shapes, self.dag.successors(factor)):
+                self.dag.node[variable].update(shape=tuple(shape))
 
     def get_shapes(self):
         return {v.id: self.dag.node[v]["shape"] for v in self.variables}

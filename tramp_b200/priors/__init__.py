@@ -23,6 +23,13 @@ class Prior(Factor):
         size = self.size if isinstance(self.size, tuple) else (self.size,)
         return size if self.batch is None else (self.batch,) + size
 
+    def infer_shape(self):
+        """Batched priors (an extension with no reference RNG stream to preserve)
+        report their shape directly; un-batched ones return None so that
+        Model.init_shapes calls sample() exactly as the reference does
+        (base_model.py:96-109 advances the global RNG)."""
+        return None if self.batch is None else [self._sample_shape()]
+
     def compute_forward_posterior(self, ax, bx):
         """(rx, vx); vx is the mean over components when isotropic."""
         arg = _Arg(ax, bx)
