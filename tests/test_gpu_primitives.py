@@ -74,7 +74,10 @@ def test_likelihood_posterior_and_log_partition(ops, el, i):
     A, Bv, Y = ops.padded(a[None, :]), ops.padded(b[None, :]), ops.padded(y[None, :])
     r, v = ops.factor_posterior(f, A, Bv, Y, n, True, True)
     assert_allclose(_np(r)[0, :n], el[f"lik{i}_r"], rtol=RTOL, atol=1e-300)
-    assert_allclose(_np(v)[0, :n], el[f"lik{i}_v"], rtol=1e-10, atol=1e-15 * max(1.0, np.abs(y).max()**2))
+    # strict on the reference's own test inputs (first 100 grid points); on the
+    # stress grid v0*(1 + g2 - g1^2) cancels by up to 1e7, in the reference too
+    assert_allclose(_np(v)[0, :100], el[f"lik{i}_v"][:100], rtol=1e-11, atol=1e-15)
+    assert_allclose(_np(v)[0, :n], el[f"lik{i}_v"], rtol=1e-7, atol=1e-15 * max(1.0, np.abs(y).max()**2))
     Ael = ops.factor_log_partition(f, A, Bv, Y, n, True, True)
     assert_allclose(_np(Ael)[0, :n], el[f"lik{i}_A"], rtol=RTOL, atol=1e-13)
     for j, a_s in enumerate(el["iso_a"]):
@@ -105,7 +108,9 @@ def test_truncated_normal(ops, el, i):
     assert_allclose(_np(mean), el[f"trunc{i}_r"], atol=1e-12, **kw)
     assert_allclose(_np(var), el[f"trunc{i}_v"], atol=1e-12, **kw)
     assert_allclose(_np(logZ), el[f"trunc{i}_A"], atol=1e-12, **kw)
-    assert_allclose(_np(proba), el[f"trunc{i}_p"], atol=1e-300, **kw)
+    # proba = Phi(ymax) - Phi(ymin) (utils/misc.py:50-52) cancels in the tails:
+    # both implementations carry an absolute error of a few ulp of 1.0
+    assert_allclose(_np(proba), el[f"trunc{i}_p"], atol=1e-15, **kw)
 
 
 def _thin_svd(W):
@@ -140,7 +145,11 @@ def test_linear_channel_primitives(ops, lin, impl):
             rx = ops.lin_expand(Ut_d, R, M, coef, 1, impl)
             assert_allclose(_np(vx)[0], lin[f"lin{i}_{j}_vx"], rtol=1e-12)
             ref = lin[f"lin{i}_{j}_rx"]
-            assert_allclose(_np(rx)[0, :M], ref, rtol=1e-9, atol=1e-12 * max(1.0, np.abs(ref).max()))
+            # the reference forms rx = W @ rz (linear_channel.py:88); when az << ax the
+            # null-space part of rz is ~bz/az and W annihilates it only to roundoff, so
+            # its rx carries an absolute error ~eps*|rz|; the thin-SVD form has no such term
+            noise = 64 * np.finfo(float).eps * np.abs(lin[f"lin{i}_{j}_rz"]).max()
+            assert_allclose(_np(rx)[0, :M], ref, rtol=1e-9, atol=max(noise, 1e-12 * max(1.0, np.abs(ref).max())))
             coef, vz = ops.lin_rescale(1, 1, R, N, M, rank, s_d, s2_d, az_d, ax_d, tz, tx)
             add = bz_d if R < N else None
             rz = ops.lin_expand(Vt_d, R, N, coef, 1, impl, add=add, add_div=az_d if R < N else None)
