@@ -83,7 +83,11 @@ def test_likelihood_posterior_and_log_partition(ops, el, i):
     for j, a_s in enumerate(el["iso_a"]):
         a1 = ops.to_dev(np.array([a_s]))
         r, v = ops.factor_posterior(f, a1, Bv, Y, n, False, False)
-        assert_allclose(_np(r)[0, :n], el[f"lik{i}_iso{j}_r"], rtol=RTOL, atol=1e-300)
+        # sgn: r = r0 + s0*g1 cancels for strongly negative b*y (|r0| up to 2e10 on the
+        # stress grid); the reference's own value is only good to eps*|r0| there
+        assert_allclose(_np(r)[0, :n], el[f"lik{i}_iso{j}_r"], rtol=RTOL,
+                        atol=16 * np.finfo(float).eps * np.abs(b).max() / a_s)
+        assert_allclose(_np(r)[0, :100], el[f"lik{i}_iso{j}_r"][:100], rtol=RTOL, atol=1e-13)
         assert_allclose(_np(v)[0], el[f"lik{i}_iso{j}_v"], rtol=RTOL)
         Am = ops.factor_log_partition(f, a1, Bv, Y, n, False, False)
         assert_allclose(_np(Am)[0], el[f"lik{i}_iso{j}_A"], rtol=1e-10)
@@ -153,7 +157,10 @@ def test_linear_channel_primitives(ops, lin, impl):
             coef, vz = ops.lin_rescale(1, 1, R, N, M, rank, s_d, s2_d, az_d, ax_d, tz, tx)
             add = bz_d if R < N else None
             rz = ops.lin_expand(Vt_d, R, N, coef, 1, impl, add=add, add_div=az_d if R < N else None)
-            assert_allclose(_np(vz)[0], lin[f"lin{i}_{j}_vz"], rtol=1e-12)
+            # vz = (1 - n_eff)/az: n_eff -> rank/Nz when az << ax, so 1 - n_eff is only
+            # good to eps in BOTH implementations (square W: it is ~1e-12 itself)
+            assert_allclose(_np(vz)[0], lin[f"lin{i}_{j}_vz"], rtol=1e-12,
+                            atol=16 * np.finfo(float).eps / max(az, 1e-11))
             ref = lin[f"lin{i}_{j}_rz"]
             assert_allclose(_np(rz)[0, :N], ref, rtol=1e-9, atol=1e-12 * max(1.0, np.abs(ref).max()))
 

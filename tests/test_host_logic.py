@@ -1,0 +1,205 @@
+"""CPU tests: the C-ABI library loads and exports every declared symbol, and
+the host-side mirror of the reference API (DAG algebra, Model, initial
+conditions, damping configuration, callbacks) behaves like the reference."""
+import ctypes
+import os
+import re
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    from tramp_b200 import _lib
+    lib = _lib.load()
+    header = open(os.path.join(ROOT, "include", "tramp_b200.h")).read()
+    declared = set(re.findall(r"\b(trb_[a-z_0-9]+)\s*\(", header))
+    assert len(declared) >= 18
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in include/tramp_b200.h but not exported"
+        assert name in _lib.SIGNATURES, f"{name} has no ctypes signature in tramp_b200/_lib.py"
+    assert lib.trb_version() >= 100
+    assert lib.trb_sizeof_factor() == ctypes.sizeof(_lib.TrbFactor)
+    assert lib.trb_sizeof_sweep() == ctypes.sizeof(_lib.TrbSweep)
+
+
+def test_argument_errors_do_not_need_a_gpu():
+    """Bad arguments are rejected before any launch, with a message."""
+    from tramp_b200 import _lib
+    lib = _lib.load()
+    rc = lib.trb_lin_project(None, 0, 4, 4, 4, 1, None, 4, None, None, 0, None)
+    assert rc == -1 and b"null pointer" in lib.trb_last_error()
+    f = _lib.TrbFactor(kind=99)
+    rc = lib.trb_factor_posterior(ctypes.byref(f), 1, 4, 4, 1, 0, 1, None, 1, 1, 0, None)
+    assert rc == -1 and b"unknown factor kind" in lib.trb_last_error()
+    rc = lib.trb_truncated_normal(4, 1, 1, 2.0, 1.0, None, None, None, None, None)
+    assert rc == -1 and b"zmin" in lib.trb_last_error()
+    assert lib.trb_lin_expand_slots(0, 4) == -1
+
+
+def test_no_cpu_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from tramp_b200.priors import GaussBernoulliPrior
+    from tramp_b200._lib import TrbError
+    with pytest.raises(TrbError, match="no CPU fallback"):
+        GaussBernoulliPrior(size=4).compute_forward_posterior(1.0, np.zeros(4))
+
+
+def _glm(N=12, M=6, batch=None, seed=0):
+    from tramp_b200.priors import GaussBernoulliPrior
+    from tramp_b200.channels import LinearChannel, GaussianChannel
+    from tramp_b200.variables import SISOVariable as V, SILeafVariable as O
+    rng = np.random.RandomState(seed)
+    W = rng.randn(*((batch,) if batch else ()), M, N)
+    return (GaussBernoulliPrior(size=N, rho=0.3, batch=batch) @ V("x") @ LinearChannel(W) @ V("z")
+            @ GaussianChannel(var=0.1) @ O("y")).to_model()
+
+
+def test_dag_algebra_and_model():
+    from tramp_b200.likelihoods import GaussianLikelihood
+    from tramp_b200.models import Model
+    m = _glm()
+    names = [type(n).__name__ for n in m.forward_ordering]
+    assert names == ["GaussBernoulliPrior", "SISOVariable", "LinearChannel", "SISOVariable",
+                     "GaussianChannel", "SILeafVariable"]
+    assert m.variable_ids == ["x", "z", "y"] and m.factor_ids == ["f_0", "f_1", "f_2"]
+    s = m.sample(seed=3)
+    assert s["x"].shape == (12,) and s["z"].shape == (6,) and s["y"].shape == (6,)
+    # seed != 0 reseeds the global RNG (base_model.py:73-74): same draw twice
+    assert np.array_equal(m.sample(seed=3)["y"], s["y"])
+    obs = m.to_observed({"y": s["y"]})
+    assert isinstance(obs, Model)
+    assert isinstance(obs.forward_ordering[-1], GaussianLikelihood)
+    assert obs.forward_ordering[-1].var == 0.1 and obs.variable_ids == ["x", "z"]
+    obs.init_shapes()
+    assert obs.get_shapes() == {"x": (12,), "z": (6,)}
+    with pytest.raises(NotImplementedError):
+        m.model_dag + m.model_dag
+
+
+def test_arity_is_checked():
+    from tramp_b200.priors import GaussBernoulliPrior
+    from tramp_b200.variables import SISOVariable as V
+    from tramp_b200.models.dag_algebra import DAG
+    dag = GaussBernoulliPrior(size=4) @ V("x")
+    with pytest.raises(ValueError):
+        dag.to_model()          # dangling placeholder is not a Factor/Variable
+    assert isinstance(dag, DAG)
+
+
+def test_batched_model_sampling_and_shapes():
+    m = _glm(batch=3)
+    s = m.sample(seed=5)
+    assert s["x"].shape == (3, 12) and s["y"].shape == (3, 6)
+    obs = m.to_observed({"y": s["y"]})
+    obs.init_shapes()
+    assert obs.get_shapes() == {"x": (3, 12), "z": (3, 6)}
+
+
+def test_sampling_matches_reference_rng_order():
+    """GaussBernoulliPrior.sample / GaussianChannel.sample consume numpy's global
+    RNG exactly as the reference does (gauss_bernoulli_prior.py:38-42,
+    gaussian_channel.py:12-15)."""
+    m = _glm(N=10, M=5)
+    W = m.forward_ordering[2].W
+    s = m.sample(seed=11)
+    np.random.seed(11)
+    xg = np.random.standard_normal(10)
+    xb = np.random.binomial(n=1, size=10, p=0.3)
+    x = xg * xb
+    z = W @ x
+    y = z + np.sqrt(0.1) * np.random.standard_normal(5)
+    assert np.array_equal(s["x"], x) and np.allclose(s["z"], z) and np.allclose(s["y"], y)
+
+
+def test_glm_generative_draws_W_first():
+    from tramp_b200.models import glm_generative
+    np.random.seed(7)
+    m = glm_generative(N=8, alpha=0.5, ensemble_type="gaussian", prior_type="binary",
+                       output_type="sgn", prior_p_pos=0.6)
+    np.random.seed(7)
+    W = (1 / np.sqrt(8)) * np.random.randn(4, 8)      # gaussian_ensemble.py:19-20
+    assert np.array_equal(m.forward_ordering[2].W, W)
+    y = m.sample()["y"]
+    assert set(np.unique(y)) <= {-1.0, 1.0}
+
+
+def test_initial_conditions():
+    from tramp_b200.algos import ConstantInit, NoisyInit, CustomInit
+    assert ConstantInit(a=2, b=3).init("a", (4,), "x", "fwd") == 2
+    assert np.array_equal(ConstantInit(a=2, b=3).init("b", (4,), "x", "fwd"), 3 * np.ones(4))
+    np.random.seed(0)
+    b = NoisyInit(b_var=4).init("b", (1000,), "x", "fwd")
+    assert abs(b.std() - 2) < 0.2
+    c = CustomInit(a_init=[("x", "bwd", 5.0)], b_init=[("x", "bwd", np.arange(4.))], a=1, b=0)
+    assert c.init("a", (4,), "x", "bwd") == 5.0 and c.init("a", (4,), "x", "fwd") == 1
+    assert np.array_equal(c.init("b", (4,), "x", "bwd"), np.arange(4.))
+    assert np.array_equal(c.init("b", (4,), "z", "bwd"), np.zeros(4))
+
+
+def test_damping_configuration_and_chain_validation():
+    from tramp_b200.algos import ExpectationPropagation
+    from tramp_b200.priors import GaussBernoulliPrior
+    from tramp_b200.channels import LinearChannel
+    from tramp_b200.likelihoods import GaussianLikelihood
+    from tramp_b200.variables import SISOVariable as V
+    W, y = np.random.randn(5, 10), np.random.randn(5)
+    m = (GaussBernoulliPrior(size=10) @ V("x") @ LinearChannel(W) @ V("z")
+         @ GaussianLikelihood(y=y, var=0.1)).to_model()
+    ep = ExpectationPropagation(m)
+    assert (ep.N, ep.M, ep.B, ep.batched) == (10, 5, 1, False)
+    ep.configure_damping(None)
+    assert ep.damp == dict(e1=0.0, e3=0.0, e5=0.0, e7=0.0)
+    ep.configure_damping(0.5)
+    assert ep.damp == dict(e1=0.5, e3=0.5, e5=0.5, e7=0.5)
+    ep.configure_damping([("x", "fwd", 0.1), ("z", "bwd", 0.9)])   # message_passing.py:100-105
+    assert ep.damp == dict(e1=0.1, e3=0.0, e5=0.9, e7=0.0)
+    with pytest.raises(ValueError, match="damping must be"):
+        ep.configure_damping(1)
+    with pytest.raises(NotImplementedError):
+        ep.configure_damping("adaptive")
+    with pytest.raises(ValueError):
+        ep.iterate(max_iter=1, warm_start=True)        # message dag was never initialized
+    bad = (GaussBernoulliPrior(size=9) @ V("x") @ LinearChannel(W) @ V("z")
+           @ GaussianLikelihood(y=y, var=0.1)).to_model()
+    with pytest.raises(ValueError, match="does not match"):
+        ExpectationPropagation(bad)
+
+
+def test_callbacks_replay_records_like_the_reference():
+    from tramp_b200.algos import TrackErrors, TrackEvolution, JoinCallback, EarlyStoppingEP, TrackEstimate
+
+    class Algo:
+        batched, x_id, z_id, variable_ids = False, "x", "z", ["x", "z"]
+    rec = dict(mse=np.array([[0.5], [0.25]]), smse=np.array([[0.4], [0.2]]),
+               vx=np.array([[1.0], [0.5]]), vz=np.array([[2.0], [1.0]]))
+    track = TrackErrors({"x": np.zeros(3)}, metrics=["mse", "sign_mse"])
+    evo = TrackEvolution()
+    join = JoinCallback([track, evo])
+    assert join.device_replayable(Algo)
+    for i in range(2):
+        join.replay(Algo, i, 2, rec)
+    assert track.get_dataframe().to_dict("list") == {"id": ["x", "x"], "iter": [0, 1],
+                                                     "mse": [0.5, 0.25], "sign_mse": [0.4, 0.2]}
+    df = evo.get_dataframe()
+    assert list(df[df.id == "z"].v) == [2.0, 1.0]
+    assert not JoinCallback([track, TrackEstimate()]).device_replayable(Algo)
+    assert EarlyStoppingEP()._var_mask(Algo) == 3 and EarlyStoppingEP(ids=["x"])._var_mask(Algo) == 1
+    assert not TrackErrors({"z": np.zeros(3)}).device_replayable(Algo)
+
+
+def test_wishart_singular_values_follow_the_gaussian_ensemble():
+    """The bidiagonal model used for synthetic data reproduces the singular-value
+    law of a Gaussian matrix (compared with direct SVDs, Marchenko-Pastur edges)."""
+    from tramp_b200.synthetic import gaussian_singular_values
+    M, N = 100, 200
+    s = gaussian_singular_values(40, M, N, seed=1, workers=2)
+    assert s.shape == (40, M) and np.all(np.diff(s, axis=1) <= 0)
+    rng = np.random.RandomState(2)
+    d = np.stack([np.linalg.svd(rng.randn(M, N) / np.sqrt(N), compute_uv=False) for _ in range(40)])
+    assert abs((s**2).mean() - (d**2).mean()) < 0.01          # E tr(W W^T)/M = 1
+    assert abs(s[:, 0].mean() - d[:, 0].mean()) < 0.02 and abs(s[:, -1].mean() - d[:, -1].mean()) < 0.02
+    assert abs((s**4).mean() - (d**4).mean()) < 0.05
