@@ -8,7 +8,7 @@ configs[2]: GaussBernoulliPrior(N=4096, rho=0.1) @ LinearChannel(Gaussian W,
 M=2048, alpha=0.5) @ GaussianLikelihood(var=1e-2), Bayes-optimal student,
 ConstantInit(0, 0), no damping, fixed iteration count, 4096 instances over 8
 GPUs = 512 independent instances per GPU (weak scaling; 4096 instances do not fit
-one GPU: 412 GB of operators).  A "step" is one EP sweep of ITERS iterations
+one GPU: 412 GB of operators).  A "step" is one EP sweep of ITERS = 100 iterations
 over the rank's 512 instances, general 4-pass schedule (16*R*(N+M) algorithmic
 bytes per instance-iteration).  Metric: instance-EP-iterations/s,
 whole job.
@@ -34,7 +34,7 @@ sys.path.insert(0, ROOT)
 
 N_DEFAULT, ALPHA, RHO, NOISE_VAR = 4096, 0.5, 0.1, 1e-2
 INSTANCES_PER_GPU = 512
-ITERS_PER_STEP = 10
+ITERS_PER_STEP = 100   # fixed 100 iterations per sweep
 METRIC = "instance-EP-iterations/s, sparse GLM N=4096 alpha=0.5"
 UNIT = "instance-iterations/s"
 
@@ -315,15 +315,22 @@ def run_ours(args):
     peak = peaks.get("hbm_gbs", 6650.0)
     peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"
     bytes_per_inst_iter = 16 * R * (N + M)           # four operator passes
-    gemv_bytes = bytes_per_inst_iter * B * iters * args.steps   # this rank, all timed GEMV launches
-    n_main = 4 * iters * args.steps                  # excludes the first-iteration tx = U^T b6 launch
-    # the extra projection of iteration 0 (one per step) streams U once more
-    gemv_bytes += 8 * R * M * B * args.steps
+    # this rank, all timed GEMV launches: 4 per iteration (ConstantInit b = 0 makes the
+    # first-iteration U^T b6 a memset, so there is no fifth pass)
+    gemv_bytes = bytes_per_inst_iter * B * iters * args.steps
+    assert n_gemv == 4 * iters * args.steps, (n_gemv, iters, args.steps)
     achieved = gemv_bytes / (gemv_ms.value / 1e3) / 1e9
+    traffic = None
+    try:   # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu capture
+        prof = json.load(open(os.path.join(ROOT, "profiles", "ncu_gemv_traffic.json")))
+        if prof.get("instances_per_gpu") == B and prof.get("N") == N:
+            traffic = prof["dram_bytes_per_launch_avg"]
+    except Exception:
+        pass
     roofline = {
         "bound": "hbm", "kernel": "k_gemv_tma (project / expand, cp.async.bulk ring)",
         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-        "peak_source": peak_src, "traffic": None,
+        "peak_source": peak_src, "traffic": traffic,
         "launches_timed": n_gemv, "avg_launch_ms": gemv_ms.value / max(n_gemv, 1),
         "algorithmic_bytes_per_launch": gemv_bytes / max(n_gemv, 1),
         "kernel_share_of_step": gemv_ms.value / dev_ms if world == 1 else gemv_ms_max / dev_ms,

@@ -71,6 +71,9 @@ typedef struct {
 /* set by the sweep's EarlyStoppingEP logic (callbacks.py:266-283) */
 #define TRB_FLAG_CONVERGED 8
 #define TRB_FLAG_DIVERGED 16
+/* the instance's messages were rolled back to the end of the previous iteration
+ * (message_passing.py:196-197, callbacks.py:281-283 reset_message_dag) */
+#define TRB_FLAG_RESTORED 32
 
 const char* trb_last_error(void);
 int trb_version(void);
@@ -166,12 +169,15 @@ int trb_lin_reduce_slots(int B, int R, int n, int ld, const double* part,
 /* Spectrum rescale between the projections and the expansions, plus the
  * variances (linear_channel.py:58-67, 74, 91-105).
  *   dir = 0 (forward, x-side mean):  coef = s*res*(tz + s*tx),  v = forward variance
- *   dir = 1 (backward, z-side mean): coef = res*(tz + s*tx)               if R == Nz
- *                                    coef = res*(s*tx - (ax*s2/az)*tz)   if R <  Nz
+ *   dir = 1 (backward, z-side mean): coef = res*(tz + s*tx)               if !null_space
+ *                                    coef = res*(s*tx - (ax*s2/az)*tz)   if  null_space
  *                                    (then rz = bz/az + V_R coef), v = backward variance
- * with res = 1/(az + ax*s2).  s, s2: [Bop, R] (stride_s = 0 if shared);
- * rank: singular = spectrum[:rank] (linear_channel.py:46). */
-int trb_lin_rescale(int dir, int B, int R, int Nz, int Nx, int rank,
+ * with res = 1/(az + ax*s2).  null_space = (min(Nx, Nz) < Nz), passed explicitly
+ * because R may be a row shard of the spectrum.  s, s2: [Bop, R] (stride_s = 0
+ * if shared); rank: singular = spectrum[:rank] (linear_channel.py:46).  Either
+ * of coef / v may be NULL (a row-sharded operator computes the variance from
+ * the full spectrum and the coefficients from its shard). */
+int trb_lin_rescale(int dir, int B, int R, int Nz, int Nx, int rank, int null_space,
                     const double* s, const double* s2, int64_t stride_s,
                     const double* az, const double* ax, const double* tz,
                     const double* tx, double* coef, double* v,
@@ -221,13 +227,43 @@ typedef struct {
   double es_tol, es_max_increase; int32_t es_wait_increase;
   int32_t gemv_impl;   /* 0 default, 1 LDG, 2 TMA ring */
   int32_t es_vars;     /* variables the tolerance runs over: bit 0 = x, bit 1 = z (ids="all": 3) */
+  /* one-iteration-back snapshot (`old_message_dag`, message_passing.py:356): same
+   * shapes as edge_a, b1, b3, b5, b7, rx, rz, vx, vz, tx.  NULL snap_edge_a = no
+   * snapshots (then a NaN / diverged instance is frozen but not rolled back). */
+  double* snap_edge_a; double* snap_b1; double* snap_b3; double* snap_b5; double* snap_b7;
+  double* snap_rx; double* snap_rz; double* snap_vx; double* snap_vz; double* snap_tx;
+  /* rank of the whole thin SVD when R is only this GPU's row shard (0: = R) */
+  int32_t R_total; int32_t _pad;
 } trb_sweep;
+
+/* Stages of one iteration, in order (trb_sweep_run loops over them).  Back ends
+ * that replace the GEMV stages (shared-W GEMM, multi-GPU row shards with an
+ * all-reduce) call the other stages one by one through trb_sweep_stage. */
+typedef enum {
+  TRB_STAGE_PRIOR = 0,          /* F1 */
+  TRB_STAGE_PROJECT_Z = 1,      /* P1: tz = V_R^T b2 */
+  TRB_STAGE_PROJECT_X_INIT = 2, /* first iteration only: tx = U_R^T b6 */
+  TRB_STAGE_RESCALE_FWD = 3,    /* S1 */
+  TRB_STAGE_EXPAND_X = 4,       /* P2 */
+  TRB_STAGE_Z_UPDATE = 5,       /* Z  */
+  TRB_STAGE_PROJECT_X = 6,      /* P3 */
+  TRB_STAGE_RESCALE_BWD = 7,    /* S2 */
+  TRB_STAGE_EXPAND_Z = 8,       /* P4 */
+  TRB_STAGE_X_UPDATE = 9,       /* X  */
+  TRB_STAGE_SNAPSHOT = 10
+} trb_stage;
+
+/* pre_reduced = 1: `part` holds the complete expansion result in slot 0
+ * ([B, 1, ld], nslots = 1) instead of per-CTA partial sums. */
+int trb_sweep_stage(const trb_sweep* sw, int stage, int it, int first, int pre_reduced,
+                    void* stream);
 
 /* Run `n_iter` EP iterations.  `it0` is the index, within the current
  * iterate() call, of the first one (records go to row it0, it0+1, ...; the
  * early-stopping test needs it > 0).  fresh = 1: the message buffers hold the
  * initializer's values (b6_init / b8_init are honoured on the first iteration
- * and tx is recomputed); fresh = 0: warm start / continuation. */
+ * and tx = U_R^T b6 is recomputed); fresh = 2: same, and the initial e6 has
+ * b = 0, so tx is simply zeroed; fresh = 0: warm start / continuation. */
 int trb_sweep_run(const trb_sweep* sw, int it0, int n_iter, int fresh, void* stream);
 
 #ifdef __cplusplus

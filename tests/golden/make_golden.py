@@ -75,6 +75,8 @@ def gen_elementwise(out):
     n = a.size
     out["grid_a"] = a
     out["grid_b"] = b
+    bnorm = b / np.sqrt(a)
+    out["grid_bnorm"] = bnorm
     rng = np.random.RandomState(7)
     z = np.concatenate([np.linspace(-3, 3, 100), rng.randn(n - 100) * 2])
     out["grid_z"] = z
@@ -87,7 +89,7 @@ def gen_elementwise(out):
         # isotropic, scalar a, several precisions
         p_iso = _prior_from(dict(spec, size=n, isotropic=True))
         for j, a_s in enumerate([1e-3, 0.7, 30.0]):
-            bb = b
+            bb = bnorm * np.sqrt(a_s)      # keep |b|/sqrt(a) <= 60 for the scalar precision too
             r, v = p_iso.compute_forward_posterior(a_s, bb)
             an, bn = p_iso.compute_forward_message(a_s, bb)
             out[f"prior{i}_iso{j}_r"] = r
@@ -106,13 +108,14 @@ def gen_elementwise(out):
         out[f"lik{i}_A"] = lk.scalar_log_partition(a, b, y)
         lk_iso = _lik_from(dict(spec, isotropic=True), y)
         for j, a_s in enumerate([1e-3, 0.7, 30.0]):
-            r, v = lk_iso.compute_backward_posterior(a_s, b, y)
-            an, bn = lk_iso.compute_backward_message(a_s, b)
+            bb = bnorm * np.sqrt(a_s)
+            r, v = lk_iso.compute_backward_posterior(a_s, bb, y)
+            an, bn = lk_iso.compute_backward_message(a_s, bb)
             out[f"lik{i}_iso{j}_r"] = r
             out[f"lik{i}_iso{j}_v"] = np.float64(v)
             out[f"lik{i}_iso{j}_anew"] = np.float64(an)
             out[f"lik{i}_iso{j}_bnew"] = bn * np.ones(n)
-            out[f"lik{i}_iso{j}_A"] = np.float64(lk_iso.compute_log_partition(a_s, b, y))
+            out[f"lik{i}_iso{j}_A"] = np.float64(lk_iso.compute_log_partition(a_s, bb, y))
 
 
 def gen_truncated(out):

@@ -238,8 +238,11 @@ def test_batched_instances_match_oracle(kinds):
         model = (get_prior(size=N, prior_type=pk, batch=B, **pkw) @ V("x") @ LinearChannel(W) @ V("z")
                  @ get_likelihood(y=y, likelihood_type=lk, **lkw)).to_model()
         ep = ExpectationPropagation(model)
+        if shared:
+            ep.linear_backend = "gemm"      # shared W: the four passes become FP64 GEMMs
         track = TrackErrors({"x": x}, metrics=["mse", "sign_mse"])
         ep.iterate(max_iter=n_iter, callback=track, damping=damping)
+        assert ep.backend == ("gemm" if shared else "gemv")
         got = ep.get_variables_data()
         assert got["x"]["r"].shape == (B, N) and got["x"]["v"].shape == (B,)
         for b in range(B):

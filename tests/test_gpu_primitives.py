@@ -53,6 +53,7 @@ def test_prior_posterior_and_log_partition(ops, el, i):
     assert_allclose(_np(Ael)[0, :n], el[f"prior{i}_A"], rtol=RTOL, atol=1e-13)
     for j, a_s in enumerate(el["iso_a"]):
         a1 = ops.to_dev(np.array([a_s]))
+        Bv = ops.padded((el["grid_bnorm"] * np.sqrt(a_s))[None, :])
         r, v = ops.factor_posterior(f, a1, Bv, None, n, False, False)
         assert_allclose(_np(r)[0, :n], el[f"prior{i}_iso{j}_r"], rtol=RTOL, atol=1e-300)
         assert_allclose(_np(v)[0], el[f"prior{i}_iso{j}_v"], rtol=RTOL)
@@ -82,6 +83,8 @@ def test_likelihood_posterior_and_log_partition(ops, el, i):
     assert_allclose(_np(Ael)[0, :n], el[f"lik{i}_A"], rtol=RTOL, atol=1e-13)
     for j, a_s in enumerate(el["iso_a"]):
         a1 = ops.to_dev(np.array([a_s]))
+        b = el["grid_bnorm"] * np.sqrt(a_s)
+        Bv = ops.padded(b[None, :])
         r, v = ops.factor_posterior(f, a1, Bv, Y, n, False, False)
         # sgn: r = r0 + s0*g1 cancels for strongly negative b*y (|r0| up to 2e10 on the
         # stress grid); the reference's own value is only good to eps*|r0| there
@@ -194,3 +197,22 @@ def test_gemv_shapes_vs_numpy(ops, impl, shape):
     t = ops.lin_project(A_d, R, n, x_d, B, impl, active=active)
     assert np.all(_np(t)[0] == 0)
     assert_allclose(_np(t)[1:], np.einsum("brn,bn->br", A, x)[1:], rtol=1e-11, atol=1e-11)
+
+
+@pytest.mark.parametrize("shape", [(2, 21, 9000), (1, 40, 20000), (3, 10, 16390)])
+def test_gemv_wide_operators_use_column_panels(ops, shape):
+    """ld > 8192 doubles exceeds one TMA ring stage: the operator is processed as
+    equal column panels (BASELINE config 5 has rows of 65536 doubles)."""
+    B, R, n = shape
+    rng = np.random.RandomState(R)
+    A = rng.randn(B, R, n)
+    x = rng.randn(B, n)
+    c = rng.randn(B, R)
+    ld = ops.pad_ld(n)
+    import torch
+    A_d = torch.zeros((B, R, ld), dtype=torch.float64, device="cuda")
+    A_d[:, :, :n] = torch.as_tensor(A, device="cuda")
+    t = ops.lin_project(A_d, R, n, ops.padded(x), B)
+    assert_allclose(_np(t), np.einsum("brn,bn->br", A, x), rtol=1e-11, atol=1e-10)
+    out = ops.lin_expand(A_d, R, n, ops.to_dev(c), B)
+    assert_allclose(_np(out)[:, :n], np.einsum("brn,br->bn", A, c), rtol=1e-11, atol=1e-10)

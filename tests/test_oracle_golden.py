@@ -37,6 +37,7 @@ def test_prior_elementwise(el, i):
     assert_allclose(v * np.ones_like(a), el[f"prior{i}_v"], rtol=RTOL, atol=1e-300)
     for j, a_s in enumerate(el["iso_a"]):
         spec = dict(PRIOR_SPECS[i], isotropic=True)
+        b = el["grid_bnorm"] * np.sqrt(a_s)
         r, v = orc.prior_forward_posterior(spec, a_s, b)
         an, bn = orc.prior_forward_message(spec, a_s, b)
         assert_allclose(r, el[f"prior{i}_iso{j}_r"], rtol=RTOL, atol=1e-300)
@@ -58,6 +59,7 @@ def test_likelihood_elementwise(el, i):
     assert_allclose(v * np.ones_like(a), el[f"lik{i}_v"], rtol=RTOL, atol=1e-300)
     for j, a_s in enumerate(el["iso_a"]):
         spec = dict(LIK_SPECS[i], y=y, isotropic=True)
+        b = el["grid_bnorm"] * np.sqrt(a_s)
         r, v = orc.likelihood_backward_posterior(spec, a_s, b)
         an, bn = orc.likelihood_backward_message(spec, a_s, b)
         assert_allclose(r, el[f"lik{i}_iso{j}_r"], rtol=RTOL, atol=1e-300)

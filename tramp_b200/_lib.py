@@ -44,6 +44,11 @@ class TrbSweep(C.Structure):
         ("max_records", C.c_int32),
         ("es_tol", C.c_double), ("es_max_increase", C.c_double),
         ("es_wait_increase", C.c_int32), ("gemv_impl", C.c_int32), ("es_vars", C.c_int32),
+        ("snap_edge_a", C.c_void_p), ("snap_b1", C.c_void_p), ("snap_b3", C.c_void_p),
+        ("snap_b5", C.c_void_p), ("snap_b7", C.c_void_p), ("snap_rx", C.c_void_p),
+        ("snap_rz", C.c_void_p), ("snap_vx", C.c_void_p), ("snap_vz", C.c_void_p),
+        ("snap_tx", C.c_void_p),
+        ("R_total", C.c_int32), ("_pad", C.c_int32),
     ]
 
 
@@ -51,7 +56,11 @@ class TrbSweep(C.Structure):
 GAUSS_BERNOULLI_PRIOR, BINARY_PRIOR, GAUSSIAN_PRIOR = 0, 1, 2
 GAUSSIAN_LIKELIHOOD, SGN_LIKELIHOOD, ABS_LIKELIHOOD = 3, 4, 5
 
-FLAG_NAN_A, FLAG_NAN_B, FLAG_NEG_A, FLAG_CONVERGED, FLAG_DIVERGED = 1, 2, 4, 8, 16
+(STAGE_PRIOR, STAGE_PROJECT_Z, STAGE_PROJECT_X_INIT, STAGE_RESCALE_FWD, STAGE_EXPAND_X,
+ STAGE_Z_UPDATE, STAGE_PROJECT_X, STAGE_RESCALE_BWD, STAGE_EXPAND_Z, STAGE_X_UPDATE,
+ STAGE_SNAPSHOT) = range(11)
+
+FLAG_NAN_A, FLAG_NAN_B, FLAG_NEG_A, FLAG_CONVERGED, FLAG_DIVERGED, FLAG_RESTORED = 1, 2, 4, 8, 16, 32
 
 _I, _L, _D, _P = C.c_int, C.c_int64, C.c_double, C.c_void_p
 _FP = C.POINTER(TrbFactor)
@@ -75,8 +84,9 @@ SIGNATURES = {
     "trb_lin_expand_slots": (_I, [_I, _I]),
     "trb_lin_expand": (_I, [_P, _L, _I, _I, _I, _I, _P, _P, _P, _I, _P]),
     "trb_lin_reduce_slots": (_I, [_I, _I, _I, _I, _P, _P, _P, _P, _P]),
-    "trb_lin_rescale": (_I, [_I, _I, _I, _I, _I, _I, _P, _P, _L, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "trb_lin_rescale": (_I, [_I, _I, _I, _I, _I, _I, _I, _P, _P, _L, _P, _P, _P, _P, _P, _P, _P, _P]),
     "trb_sweep_run": (_I, [C.POINTER(TrbSweep), _I, _I, _I, _P]),
+    "trb_sweep_stage": (_I, [C.POINTER(TrbSweep), _I, _I, _I, _I, _P]),
 }
 
 _lib = None

@@ -54,6 +54,10 @@ class MessagePassing():
         self.variables = model.variables
         self.n_iter = 0
         self.gemv_impl = 0
+        # how the four operator passes run: "gemv" (batched HBM-bound GEMVs, the
+        # default), "gemm" (cuBLAS FP64 GEMMs when a batch shares one W), "sharded"
+        # (rows of the operators split over ranks + all-reduce); None = pick
+        self.linear_backend = None
         self._state = None
         self._has_messages = False
         self._compile_chain()
@@ -115,8 +119,16 @@ class MessagePassing():
             vlin=t.zeros(B, **f64), stats=t.zeros((B, 4), **f64),
             active=t.ones(B, **i32), flags=t.zeros(B, **i32), n_iter=t.zeros(B, **i32),
         )
+        for k in ("edge_a", "b1", "b3", "b5", "b7", "rx", "rz", "vx", "vz", "tx"):
+            st["snap_" + k] = t.zeros_like(st[k])
+        self.backend = self._pick_backend()
         st["nslots"] = ops.lin_expand_slots(B, R)
         st["part"] = t.zeros((B, st["nslots"], max(ldn, ldm)), **f64)
+        if self.backend != "gemv":
+            # fully reduced expansion results, read by the update kernels as slot 0
+            st["red"] = t.zeros(B * max(ldn, ldm), **f64)
+            st["red_n"] = st["red"][:B * ldn].view(B, ldn)
+            st["red_m"] = st["red"][:B * ldm].view(B, ldm)
         y = np.asarray(self.lik.y, dtype=np.float64) if not ops.is_tensor(self.lik.y) else self.lik.y
         y2 = y if len(y.shape) == 2 else y[None, :]
         st["y"] = ops.padded(y2, ldm)
@@ -125,6 +137,17 @@ class MessagePassing():
         st["x_true"] = None
         self._state = st
         return st
+
+    def _pick_backend(self):
+        lin = self.linear
+        if self.linear_backend is not None:
+            return self.linear_backend
+        if getattr(lin, "group", None) is not None:
+            return "sharded"
+        # many instances sharing one W: the passes are dense [B, n] x [n, R] products
+        if lin.s.shape[0] == 1 and self.B >= 16:
+            return "gemm"
+        return "gemv"
 
     def _vec_to_dev(self, value, role):
         n, ld = (self.N, self.linear.ldn) if role == "x" else (self.M, self.linear.ldm)
@@ -148,6 +171,7 @@ class MessagePassing():
             for k in ("b1", "b3", "b5", "b7"):
                 st[k].fill_(float(initializer.b))
             st["b6_init"] = st["b8_init"] = None
+            st["b6_zero"] = float(initializer.b) == 0.0
             for k in ("rx", "rz", "vx", "vz"):
                 st[k].zero_()
             self._has_messages = True
@@ -165,6 +189,7 @@ class MessagePassing():
         st["b7"].copy_(init_b["e7"])
         # e6 / e8 are read once (first F3 / F1) before the pass-through overwrites
         # them; keep them separately only if they differ from e5 / e7
+        st["b6_zero"] = not bool(init_b["e6"].any().item())
         st["b6_init"] = None if t.equal(init_b["e6"], init_b["e5"]) else init_b["e6"]
         st["b8_init"] = None if t.equal(init_b["e8"], init_b["e7"]) else init_b["e8"]
         for k in ("rx", "rz", "vx", "vz"):
@@ -226,11 +251,85 @@ class MessagePassing():
         else:
             sw.es_tol, sw.es_max_increase, sw.es_wait_increase, sw.es_vars = -1.0, 0.0, 0, 3
         sw.gemv_impl = self.gemv_impl
+        sw.R_total = getattr(lin, "R_total", 0) or 0
+        for k in ("edge_a", "b1", "b3", "b5", "b7", "rx", "rz", "vx", "vz", "tx"):
+            setattr(sw, "snap_" + k, p(st["snap_" + k]))
         return sw
 
     def _run(self, sw, it0, n_iter, fresh):
-        _lib.check(_lib.load().trb_sweep_run(C.byref(sw), it0, n_iter, int(fresh),
-                                             _lib.current_stream()))
+        """Enqueue n_iter iterations.  fresh: the messages were just initialised."""
+        st = self._state
+        code = 0 if not fresh else (2 if st.get("b6_zero") else 1)
+        if self.backend == "gemv":
+            _lib.check(_lib.load().trb_sweep_run(C.byref(sw), it0, n_iter, code, _lib.current_stream()))
+        else:
+            self._run_staged(sw, it0, n_iter, code)
+
+    def _run_staged(self, sw, it0, n_iter, fresh):
+        """Same schedule as trb_sweep_run (tramp_b200/csrc/trb_sweep.cu) with the four
+        operator passes replaced by the back end: cuBLAS FP64 GEMMs on a shared W
+        ("gemm") or local GEMVs on this rank's row shard followed by an all-reduce
+        ("sharded").  Every other stage is the same CUDA kernel."""
+        t = ops.torch()
+        lib = _lib.load()
+        st, lin = self._state, self.linear
+        stream = _lib.current_stream()
+        B, N, M, R = self.B, self.N, self.M, lin.R
+        ea = st["edge_a"]
+        # descriptor whose `part` is the fully reduced buffer (slot 0, nslots = 1)
+        red = _lib.TrbSweep.from_buffer_copy(sw)
+        red.part, red.nslots = _lib.ptr(st["red"]), 1
+        sharded = self.backend == "sharded"
+
+        def stage(desc, which, it, first, pre=0):
+            _lib.check(lib.trb_sweep_stage(C.byref(desc), which, it, int(first), pre, stream))
+
+        def project(A, vec, out, n):
+            if sharded:
+                ops.lin_project(A, R, n, vec, B, self.gemv_impl, st["active"], out=out)
+            else:
+                t.matmul(vec, A[0].transpose(0, 1), out=out)
+
+        def expand(A, n, out):
+            """out[B, ld] = coef @ A (+ all-reduce over the row shards)."""
+            if sharded:
+                ops.lin_expand(A, R, n, st["coef"], B, self.gemv_impl, st["active"], out=out,
+                               part=st["part"][:, :, :A.shape[-1]] if st["part"].shape[-1] == A.shape[-1]
+                               else None)
+                lin.all_reduce(out)
+            else:
+                t.matmul(st["coef"], A[0], out=out)
+
+        def rescale(direction):
+            if sharded:
+                # variance from the full spectrum (replicated), coefficients from the shard
+                ops.lin_rescale(direction, B, lin.R_total, N, M, lin.rank, lin.s_full, lin.s2_full,
+                                ea[1], ea[5], None, None, st["active"], null_space=lin.R_total < N,
+                                want_coef=False, v=st["vlin"])
+                ops.lin_rescale(direction, B, R, N, M, lin.rank, lin.s, lin.s2, ea[1], ea[5],
+                                st["tz"], st["tx"], st["active"], null_space=lin.R_total < N,
+                                want_v=False, coef=st["coef"])
+            else:
+                stage(sw, _lib.STAGE_RESCALE_FWD if direction == 0 else _lib.STAGE_RESCALE_BWD, 0, 0)
+
+        for k in range(n_iter):
+            it, first = it0 + k, bool(fresh) and k == 0
+            stage(sw, _lib.STAGE_PRIOR, it, first)
+            project(lin.Vt, st["b1"], st["tz"], N)                          # P1
+            if first:
+                if fresh == 2:
+                    st["tx"].zero_()
+                else:
+                    project(lin.Ut, st["b6_init"] if st["b6_init"] is not None else st["b5"],
+                            st["tx"], M)
+            rescale(0)                                                      # S1
+            expand(lin.Ut, M, st["red_m"])                                  # P2
+            stage(red, _lib.STAGE_Z_UPDATE, it, first, 1)
+            project(lin.Ut, st["b5"], st["tx"], M)                          # P3
+            rescale(1)                                                      # S2
+            expand(lin.Vt, N, st["red_n"])                                  # P4
+            stage(red, _lib.STAGE_X_UPDATE, it, first, 1)
+            stage(sw, _lib.STAGE_SNAPSHOT, it, first)
 
     def _raise_on_nan(self, flags):
         """reference message_passing.py:187-209 (check_message)."""
@@ -300,8 +399,8 @@ class MessagePassing():
         self.n_iter += n_done
         self._raise_on_nan(flags)
         if (flags & _lib.FLAG_DIVERGED).any():
-            logger.warning("EarlyStoppingEP: increase above max_increase in instance(s) "
-                           f"{np.nonzero(flags & _lib.FLAG_DIVERGED)[0].tolist()}")
+            logger.info("EarlyStoppingEP: increase above max_increase in instance(s) "
+                        f"{np.nonzero(flags & _lib.FLAG_DIVERGED)[0].tolist()}; old messages restored")
         rec_h = {k: v[:n_done].cpu().numpy() for k, v in rec.items()}
         self.records = rec_h
         for i in range(n_done):

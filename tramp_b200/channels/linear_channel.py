@@ -73,6 +73,7 @@ class LinearChannel(Channel):
         if not precompute_svd:
             raise NotImplementedError("LinearChannel(precompute_svd=False) is not on the EP hot path")
         self.batch = int(W.shape[0]) if len(W.shape) == 3 else None
+        self.group = None
         self.W = W if keep_W else None
         self.alpha = self.Nx / self.Nz
         self._ops_ready = False
@@ -88,10 +89,32 @@ class LinearChannel(Channel):
         self.name, self.Nx, self.Nz, self.precompute_svd = name, int(Nx), int(Nz), True
         self.repr_init()
         self.batch = int(Ut.shape[0]) if Ut.shape[0] > 1 else None
+        self.group = None
         self.W = None
         self.alpha = self.Nx / self.Nz
         self._install(Ut, s, Vt, rank)
         return self
+
+    @classmethod
+    def from_sharded_factors(cls, Ut, s, Vt, s_full, Nx, Nz, group, rank=None, name="W"):
+        """Row shard of a single large operator (BASELINE config 5): this
+        rank holds the singular triplets `Ut [1, Rg, ldm], s [1, Rg], Vt [1, Rg, ldn]`
+        of W and the full spectrum `s_full [R_total]` (replicated).  Projections
+        and the spectrum rescale are local; the two expansions per iteration are
+        partial sums that `all_reduce` adds over `group` (NCCL over NVLink)."""
+        t = ops.torch()
+        self = cls.from_factors(Ut, s, Vt, Nx, Nz, rank=len(s_full) if rank is None else rank, name=name)
+        self.batch = None
+        self.group = group
+        self.s_full = ops.to_dev(s_full).reshape(1, -1).contiguous()
+        self.s2_full = (self.s_full * self.s_full).contiguous()
+        self.R_total = int(self.s_full.shape[1])
+        return self
+
+    def all_reduce(self, tensor):
+        import torch.distributed as dist
+        dist.all_reduce(tensor, op=dist.ReduceOp.SUM, group=self.group)
+        return tensor
 
     def _install(self, Ut, s, Vt, rank=None):
         t = ops.torch()
@@ -185,6 +208,9 @@ class LinearChannel(Channel):
         return az_arg, ax_arg
 
     def _means(self, az, bz, ax, bx, want):
+        if getattr(self, "group", None) is not None:
+            raise NotImplementedError("the factor-level API of a row-sharded LinearChannel is not "
+                                      "available; run it through ExpectationPropagation")
         zarg, xarg = self._args(az, bz, ax, bx)
         B = zarg.B
         bz_d = ops.padded(zarg.b[:, :self.Nz], self.ldn)

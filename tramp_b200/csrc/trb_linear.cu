@@ -190,7 +190,11 @@ __global__ void __launch_bounds__(kTmaThreads, 1)
 k_gemv_tma(const double* __restrict__ A, int64_t strideA, int R, int n, int ld, int B,
            const double* __restrict__ vec, int ldvec,  // project: input vector; expand: coef [B,R]
            double* __restrict__ out, int nslots,       // project: t [B,R]; expand: part
-           const int* __restrict__ active, int nstages, int stage_doubles) {
+           const int* __restrict__ active, int nstages, int stage_doubles,
+           int row_stride,   // doubles between consecutive rows of A (>= ld; == ld unless this
+                             // launch handles one column panel of a wider operator, then RC == 1)
+           int out_ld,       // expand: leading dimension of `part`
+           int accumulate) { // project: add to t instead of overwriting (panels after the first)
   constexpr int RC = TmaCfg<NB>::RC;
   extern __shared__ __align__(128) double ring[];  // nstages * stage_doubles
   __shared__ __align__(8) uint64_t full_bar[kMaxStages];
@@ -226,7 +230,7 @@ k_gemv_tma(const double* __restrict__ A, int64_t strideA, int R, int n, int ld, 
           const uint32_t bytes = (uint32_t)rows * (uint32_t)ld * 8u;
           mbar_wait(&empty_bar[stage], phase ^ 1u);
           mbar_arrive_expect_tx(&full_bar[stage], bytes);
-          bulk_g2s(ring + (size_t)stage * stage_doubles, Ab + (size_t)i * ld, bytes,
+          bulk_g2s(ring + (size_t)stage * stage_doubles, Ab + (size_t)i * row_stride, bytes,
                    &full_bar[stage]);
           if (++stage == nstages) {
             stage = 0;
@@ -297,7 +301,8 @@ k_gemv_tma(const double* __restrict__ A, int64_t strideA, int R, int n, int ld, 
           double tot = 0.0;
 #pragma unroll
           for (int w = 0; w < kConsumers / 32; ++w) tot += red[red_buf][w][tid];
-          out[(size_t)s.b * R + ig + tid] = tot;
+          double* dst = out + (size_t)s.b * R + ig + tid;
+          *dst = accumulate ? *dst + tot : tot;
         }
         red_buf ^= 1;
       }
@@ -336,7 +341,7 @@ k_gemv_tma(const double* __restrict__ A, int64_t strideA, int R, int n, int ld, 
         }
       }
       const int slot = (int)(blockIdx.x - part_owner((int64_t)s.b * R, T, G));
-      double* o = out + ((size_t)s.b * nslots + slot) * ld;
+      double* o = out + ((size_t)s.b * nslots + slot) * out_ld;
 #pragma unroll
       for (int k = 0; k < NB; ++k) {
         const int p = tid + k * kConsumers;
@@ -367,7 +372,8 @@ k_reduce_slots(int R, int n, int ld, int B, int G, int nslots, const double* __r
 
 // linear_channel.py:58-67 (compute_n_eff), :74 (resolvent), :91-105 (variances)
 __global__ void __launch_bounds__(256)
-k_lin_rescale(int dir, int R, int Nz, int Nx, int rank, const double* __restrict__ s,
+k_lin_rescale(int dir, int R, int Nz, int Nx, int rank, int null_space_flag,
+              const double* __restrict__ s,
               const double* __restrict__ s2, int64_t stride_s, const double* __restrict__ az_arr,
               const double* __restrict__ ax_arr, const double* __restrict__ tz,
               const double* __restrict__ tx, double* __restrict__ coef, double* __restrict__ v_out,
@@ -409,9 +415,10 @@ k_lin_rescale(int dir, int R, int Nz, int Nx, int rank, const double* __restrict
       v = (1 - n_eff) / az_v;  // :95-97
     }
   }
-  if (threadIdx.x == 0) v_out[b] = v;
+  if (threadIdx.x == 0 && v_out) v_out[b] = v;
+  if (!coef) return;
   // ---- coefficients in the singular basis
-  const bool null_space = (R < Nz);
+  const bool null_space = null_space_flag != 0;
   for (int i = threadIdx.x; i < R; i += blockDim.x) {
     const double si = sb[i], s2i = s2b[i];
     const double res = 1 / (az + ax * s2i);  // :74
@@ -459,7 +466,7 @@ bool plan_tma(int ld, TmaPlan& p) {
 template <int NB, bool EXPAND>
 int launch_tma(const TmaPlan& p, int G, const double* A, int64_t strideA, int R, int n, int ld,
                int B, const double* vec, int ldvec, double* out, int nslots, const int* active,
-               cudaStream_t st) {
+               cudaStream_t st, int row_stride, int out_ld, int accumulate) {
   auto kern = k_gemv_tma<NB, EXPAND>;
   static bool configured = false;  // per instantiation
   if (!configured) {
@@ -470,25 +477,44 @@ int launch_tma(const TmaPlan& p, int G, const double* A, int64_t strideA, int R,
     configured = true;
   }
   kern<<<G, kTmaThreads, p.smem, st>>>(A, strideA, R, n, ld, B, vec, ldvec, out, nslots, active,
-                                       p.stages, p.stage_doubles);
+                                       p.stages, p.stage_doubles, row_stride, out_ld, accumulate);
   return TRB_OK;
 }
 
 template <bool EXPAND>
 int dispatch_tma(const TmaPlan& p, int G, const double* A, int64_t strideA, int R, int n, int ld,
                  int B, const double* vec, int ldvec, double* out, int nslots, const int* active,
-                 cudaStream_t st) {
+                 cudaStream_t st, int row_stride, int out_ld, int accumulate) {
+#define TRB_TMA_CASE(NB_)                                                                          \
+  case NB_:                                                                                        \
+    return launch_tma<NB_, EXPAND>(p, G, A, strideA, R, n, ld, B, vec, ldvec, out, nslots, active, \
+                                   st, row_stride, out_ld, accumulate);
   switch (p.nb) {
-    case 1: return launch_tma<1, EXPAND>(p, G, A, strideA, R, n, ld, B, vec, ldvec, out, nslots, active, st);
-    case 2: return launch_tma<2, EXPAND>(p, G, A, strideA, R, n, ld, B, vec, ldvec, out, nslots, active, st);
-    case 4: return launch_tma<4, EXPAND>(p, G, A, strideA, R, n, ld, B, vec, ldvec, out, nslots, active, st);
-    case 8: return launch_tma<8, EXPAND>(p, G, A, strideA, R, n, ld, B, vec, ldvec, out, nslots, active, st);
-    case 16: return launch_tma<16, EXPAND>(p, G, A, strideA, R, n, ld, B, vec, ldvec, out, nslots, active, st);
+    TRB_TMA_CASE(1)
+    TRB_TMA_CASE(2)
+    TRB_TMA_CASE(4)
+    TRB_TMA_CASE(8)
+    TRB_TMA_CASE(16)
   }
+#undef TRB_TMA_CASE
   return trb_set_error(TRB_ERR_UNSUPPORTED, "no TMA GEMV instantiation for NB=%d", p.nb);
 }
 
 }  // namespace
+
+// Operators wider than the TMA ring allows (ld > 8192 doubles) are processed as
+// column panels of equal width in (4096, 8192]: every panel then has NB = 16 and
+// one row per ring stage, so a stage is still one contiguous bulk copy.
+struct Panels {
+  int count, width;
+};
+static Panels plan_panels(int ld) {
+  Panels p;
+  const int kMax = 16 * kConsumers * 2;  // 8192
+  p.count = (ld + kMax - 1) / kMax;
+  p.width = ((ld + p.count - 1) / p.count + 1) & ~1;
+  return p;
+}
 
 trb_expand_geom trb_expand_geometry(int B, int R) {
   trb_expand_geom g;
@@ -535,11 +561,25 @@ extern "C" int trb_lin_project(const double* A, int64_t strideA, int R, int n, i
   const trb_expand_geom geo = trb_expand_geometry(B, R);
   TmaPlan p;
   const bool tma_ok = plan_tma(ld, p);
-  if (impl == 0) impl = tma_ok ? 2 : 1;
+  if (impl == 0) impl = 2;
   trb_launch_scope scope_(1, st);
-  if (impl == 2) {
-    if (!tma_ok) return trb_set_error(TRB_ERR_UNSUPPORTED, "trb_lin_project: ld=%d too large for the TMA ring", ld);
-    rc = dispatch_tma<false>(p, geo.G, A, strideA, R, n, ld, B, vec, ldvec, t, 0, active, st);
+  if (impl == 2 && !tma_ok) {
+    const Panels pan = plan_panels(ld);
+    for (int q = 0; q < pan.count; ++q) {
+      const int c0 = q * pan.width;
+      const int w = (ld - c0 < pan.width) ? ld - c0 : pan.width;
+      const int nq = (n - c0 < w) ? n - c0 : w;
+      if (nq <= 0) break;
+      TmaPlan pq;
+      if (!plan_tma(w, pq) || (pq.nb < 8 && w != ld))
+        return trb_set_error(TRB_ERR_UNSUPPORTED, "trb_lin_project: cannot panel ld=%d", ld);
+      rc = dispatch_tma<false>(pq, geo.G, A + c0, strideA, R, nq, w, B, vec + c0, ldvec, t, 0,
+                               active, st, ld, 0, q > 0);
+      if (rc) return rc;
+    }
+  } else if (impl == 2) {
+    rc = dispatch_tma<false>(p, geo.G, A, strideA, R, n, ld, B, vec, ldvec, t, 0, active, st, ld, 0,
+                             0);
     if (rc) return rc;
   } else {
     const size_t smem = (size_t)ld * 8;
@@ -566,11 +606,24 @@ extern "C" int trb_lin_expand(const double* A, int64_t strideA, int R, int n, in
   const trb_expand_geom geo = trb_expand_geometry(B, R);
   TmaPlan p;
   const bool tma_ok = plan_tma(ld, p);
-  if (impl == 0) impl = tma_ok ? 2 : 1;
+  if (impl == 0) impl = 2;
   trb_launch_scope scope_(1, st);
-  if (impl == 2) {
-    if (!tma_ok) return trb_set_error(TRB_ERR_UNSUPPORTED, "trb_lin_expand: ld=%d too large for the TMA ring", ld);
-    rc = dispatch_tma<true>(p, geo.G, A, strideA, R, n, ld, B, coef, 0, part, geo.nslots, active, st);
+  if (impl == 2 && !tma_ok) {
+    const Panels pan = plan_panels(ld);
+    for (int q = 0; q < pan.count; ++q) {
+      const int c0 = q * pan.width;
+      const int w = (ld - c0 < pan.width) ? ld - c0 : pan.width;
+      if (w <= 0) break;
+      TmaPlan pq;
+      if (!plan_tma(w, pq) || (pq.nb < 8 && w != ld))
+        return trb_set_error(TRB_ERR_UNSUPPORTED, "trb_lin_expand: cannot panel ld=%d", ld);
+      rc = dispatch_tma<true>(pq, geo.G, A + c0, strideA, R, w, w, B, coef, 0, part + c0,
+                              geo.nslots, active, st, ld, ld, 0);
+      if (rc) return rc;
+    }
+  } else if (impl == 2) {
+    rc = dispatch_tma<true>(p, geo.G, A, strideA, R, n, ld, B, coef, 0, part, geo.nslots, active, st,
+                            ld, ld, 0);
     if (rc) return rc;
   } else {
     const int nb = pick_nb(ld, kLdgThreads, 8);
@@ -601,16 +654,18 @@ extern "C" int trb_lin_reduce_slots(int B, int R, int n, int ld, const double* p
   return TRB_OK;
 }
 
-extern "C" int trb_lin_rescale(int dir, int B, int R, int Nz, int Nx, int rank, const double* s,
-                               const double* s2, int64_t stride_s, const double* az,
-                               const double* ax, const double* tz, const double* tx, double* coef,
-                               double* v, const int* active, void* stream) {
-  TRB_CHECK_ARG(s && s2 && az && ax && tz && tx && coef && v, "null pointer");
+extern "C" int trb_lin_rescale(int dir, int B, int R, int Nz, int Nx, int rank, int null_space,
+                               const double* s, const double* s2, int64_t stride_s,
+                               const double* az, const double* ax, const double* tz,
+                               const double* tx, double* coef, double* v, const int* active,
+                               void* stream) {
+  TRB_CHECK_ARG(s && s2 && az && ax && (coef || v), "null pointer");
+  TRB_CHECK_ARG(!coef || (tz && tx), "coef needs tz and tx");
   TRB_CHECK_ARG(dir == 0 || dir == 1, "dir must be 0 or 1");
   TRB_CHECK_ARG(B > 0 && R > 0 && R <= Nz && R <= Nx && rank >= 0 && rank <= R, "bad shape");
   trb_launch_scope scope_(0, (cudaStream_t)stream);
-  k_lin_rescale<<<B, 256, 0, (cudaStream_t)stream>>>(dir, R, Nz, Nx, rank, s, s2, stride_s, az, ax,
-                                                      tz, tx, coef, v, active);
+  k_lin_rescale<<<B, 256, 0, (cudaStream_t)stream>>>(dir, R, Nz, Nx, rank, null_space, s, s2,
+                                                      stride_s, az, ax, tz, tx, coef, v, active);
   TRB_CHECK_LAUNCH();
   return TRB_OK;
 }

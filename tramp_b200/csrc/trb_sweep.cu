@@ -30,6 +30,7 @@ struct SlotInfo {
 };
 
 __device__ __forceinline__ int slots_of(int b, int R, int B, int G) {
+  if (G <= 0) return 1;  // pre-reduced: the full sum sits in slot 0
   const int64_t T = (int64_t)B * R;
   const int kf = (int)part_owner((int64_t)b * R, T, G);
   const int kl = (int)part_owner((int64_t)b * R + R - 1, T, G);
@@ -125,7 +126,7 @@ k_x_update(trb_sweep sw, int G, int it, double* __restrict__ stats) {
   const double a_hat = a1 + a7;
   const int ns = slots_of(b, sw.R, B, G);
   const double* part = sw.part + (size_t)b * sw.nslots * ld;
-  const bool null_space = sw.R < N;
+  const bool null_space = (sw.R_total > 0 ? sw.R_total : sw.R) < N;
   int flag = 0;
   double d2 = 0.0, n2 = 0.0, e_pos = 0.0, e_neg = 0.0;
   for (int i = threadIdx.x; i < N; i += blockDim.x) {
@@ -196,6 +197,40 @@ k_x_update(trb_sweep sw, int G, int it, double* __restrict__ stats) {
   }
 }
 
+// One-iteration-back snapshot of the message state, per instance:
+//   active instance                      -> save   (old_message_dag = message_dag.copy(), :356)
+//   stopped on NaN / divergence, once    -> restore (reset_message_dag, :196-197, callbacks.py:281-283)
+__global__ void __launch_bounds__(256)
+k_snapshot(trb_sweep sw) {
+  const int b = blockIdx.x;
+  const int B = sw.B;
+  const int flags = sw.flags[b];
+  const bool save = sw.active[b] != 0;
+  const bool restore = !save && (flags & (TRB_FLAG_DIVERGED | TRB_FLAG_NAN_A | TRB_FLAG_NAN_B)) &&
+                       !(flags & TRB_FLAG_RESTORED);
+  if (!save && !restore) return;
+  auto copy = [&](double* live, double* snap, size_t n) {
+    double* dst = save ? snap : live;
+    const double* src = save ? live : snap;
+    for (size_t i = threadIdx.x; i < n; i += blockDim.x) dst[i] = src[i];
+  };
+  copy(sw.b1 + (size_t)b * sw.ldn, sw.snap_b1 + (size_t)b * sw.ldn, sw.N);
+  copy(sw.b7 + (size_t)b * sw.ldn, sw.snap_b7 + (size_t)b * sw.ldn, sw.N);
+  copy(sw.rx + (size_t)b * sw.ldn, sw.snap_rx + (size_t)b * sw.ldn, sw.N);
+  copy(sw.b3 + (size_t)b * sw.ldm, sw.snap_b3 + (size_t)b * sw.ldm, sw.M);
+  copy(sw.b5 + (size_t)b * sw.ldm, sw.snap_b5 + (size_t)b * sw.ldm, sw.M);
+  copy(sw.rz + (size_t)b * sw.ldm, sw.snap_rz + (size_t)b * sw.ldm, sw.M);
+  copy(sw.tx + (size_t)b * sw.R, sw.snap_tx + (size_t)b * sw.R, sw.R);
+  if (threadIdx.x < 8) {
+    double* live = sw.edge_a + (size_t)threadIdx.x * B + b;
+    double* snap = sw.snap_edge_a + (size_t)threadIdx.x * B + b;
+    if (save) *snap = *live; else *live = *snap;
+  }
+  if (threadIdx.x == 8) { if (save) sw.snap_vx[b] = sw.vx[b]; else sw.vx[b] = sw.snap_vx[b]; }
+  if (threadIdx.x == 9) { if (save) sw.snap_vz[b] = sw.vz[b]; else sw.vz[b] = sw.snap_vz[b]; }
+  if (restore && threadIdx.x == 0) atomicOr(&sw.flags[b], TRB_FLAG_RESTORED);
+}
+
 }  // namespace
 
 #define TRB_TRY(expr)      \
@@ -204,69 +239,136 @@ k_x_update(trb_sweep sw, int G, int it, double* __restrict__ stats) {
     if (rc_) return rc_;   \
   } while (0)
 
-extern "C" int trb_sweep_run(const trb_sweep* sw, int it0, int n_iter, int fresh, void* stream) {
+static int check_sweep(const trb_sweep* sw) {
   TRB_CHECK_ARG(sw, "null sweep descriptor");
   TRB_CHECK_ARG(sw->B > 0 && sw->N > 0 && sw->M > 0 && sw->R > 0, "bad shape");
   TRB_CHECK_ARG(sw->R <= sw->N && sw->R <= sw->M, "R must be <= min(N, M)");
-  TRB_CHECK_ARG(sw->Vt && sw->Ut && sw->s && sw->s2 && sw->y, "null operator / observation");
+  TRB_CHECK_ARG(sw->y, "null observation");
   TRB_CHECK_ARG(sw->edge_a && sw->b1 && sw->b3 && sw->b5 && sw->b7, "null message buffer");
   TRB_CHECK_ARG(sw->rx && sw->rz && sw->vx && sw->vz, "null posterior buffer");
   TRB_CHECK_ARG(sw->tz && sw->tx && sw->coef && sw->part && sw->scr_n && sw->scr_m && sw->vlin &&
                     sw->stats,
                 "null scratch buffer");
   TRB_CHECK_ARG(sw->active && sw->flags && sw->n_iter, "null status buffer");
-  TRB_CHECK_ARG(it0 >= 0 && n_iter >= 0, "bad iteration range");
-  const trb_expand_geom geo = trb_expand_geometry(sw->B, sw->R);
-  TRB_CHECK_ARG(sw->nslots >= geo.nslots, "nslots smaller than trb_lin_expand_slots(B, R)");
+  TRB_CHECK_ARG(!sw->snap_edge_a || (sw->snap_b1 && sw->snap_b3 && sw->snap_b5 && sw->snap_b7 &&
+                                     sw->snap_rx && sw->snap_rz && sw->snap_vx && sw->snap_vz &&
+                                     sw->snap_tx),
+                "incomplete snapshot buffers");
+  return TRB_OK;
+}
+
+// One stage of the iteration (see the header comment of this file).  `first`:
+// this is the first iteration after the messages were initialised.
+// pre_reduced: the expansion result already sits, fully summed, in slot 0 of
+// `part` (GEMM / multi-GPU back ends) instead of in per-CTA slots.
+extern "C" int trb_sweep_stage(const trb_sweep* sw, int stage, int it, int first, int pre_reduced,
+                               void* stream) {
+  int rc = check_sweep(sw);
+  if (rc) return rc;
   cudaStream_t st = (cudaStream_t)stream;
   const int B = sw->B;
   double* ea = sw->edge_a;
-  // expand writes `geo.nslots`-strided slots; the update kernels read with sw->nslots
-  TRB_CHECK_ARG(sw->nslots == geo.nslots, "nslots must equal trb_lin_expand_slots(B, R)");
+  const bool needs_ops = (stage == TRB_STAGE_PROJECT_Z || stage == TRB_STAGE_PROJECT_X_INIT ||
+                          stage == TRB_STAGE_EXPAND_X || stage == TRB_STAGE_PROJECT_X ||
+                          stage == TRB_STAGE_EXPAND_Z);
+  TRB_CHECK_ARG(!needs_ops || (sw->Vt && sw->Ut), "null operator");
+  const bool needs_s = (stage == TRB_STAGE_RESCALE_FWD || stage == TRB_STAGE_RESCALE_BWD);
+  TRB_CHECK_ARG(!needs_s || (sw->s && sw->s2), "null spectrum");
+  const int R_total = sw->R_total > 0 ? sw->R_total : sw->R;
+  const int null_space = R_total < sw->N;
+  int G = 0;
+  if (stage == TRB_STAGE_Z_UPDATE || stage == TRB_STAGE_X_UPDATE) {
+    if (pre_reduced) {
+      G = 0;  // ns = 1
+    } else {
+      const trb_expand_geom geo = trb_expand_geometry(B, sw->R);
+      TRB_CHECK_ARG(sw->nslots == geo.nslots, "nslots must equal trb_lin_expand_slots(B, R)");
+      G = geo.G;
+    }
+  }
+  switch (stage) {
+    case TRB_STAGE_PRIOR: {  // F1: reads e8, writes e1 and its pass-through copy e2
+      const double* b8 = (first && sw->b8_init) ? sw->b8_init : sw->b7;
+      return trb_factor_message(&sw->prior, B, sw->N, sw->ldn, ea + 7 * B, b8, nullptr, ea + 0 * B,
+                                sw->b1, ea + 1 * B, sw->damp1, sw->scr_n, sw->flags, sw->active,
+                                stream);
+    }
+    case TRB_STAGE_PROJECT_Z:  // P1: tz = V_R^T b2
+      return trb_lin_project(sw->Vt, sw->strideV, sw->R, sw->N, sw->ldn, B, sw->b1, sw->ldn,
+                             sw->tz, sw->active, sw->gemv_impl, stream);
+    case TRB_STAGE_PROJECT_X_INIT: {  // tx = U_R^T b6 for the initial e6
+      const double* b6 = sw->b6_init ? sw->b6_init : sw->b5;
+      return trb_lin_project(sw->Ut, sw->strideU, sw->R, sw->M, sw->ldm, B, b6, sw->ldm, sw->tx,
+                             sw->active, sw->gemv_impl, stream);
+    }
+    case TRB_STAGE_RESCALE_FWD:  // S1: coef = s res (tz + s tx), forward variance
+      return trb_lin_rescale(0, B, sw->R, sw->N, sw->M, sw->rank, null_space, sw->s, sw->s2,
+                             sw->stride_s, ea + 1 * B, ea + 5 * B, sw->tz, sw->tx, sw->coef,
+                             sw->vlin, sw->active, stream);
+    case TRB_STAGE_EXPAND_X:  // P2: rx = U_R coef
+      return trb_lin_expand(sw->Ut, sw->strideU, sw->R, sw->M, sw->ldm, B, sw->coef, sw->part,
+                            sw->active, sw->gemv_impl, stream);
+    case TRB_STAGE_Z_UPDATE: {  // Z: e3, likelihood e5, posterior z
+      trb_launch_scope scope_(0, st);
+      k_z_update<<<B, kUpThreads, 0, st>>>(*sw, G, first, sw->stats);
+      TRB_CHECK_LAUNCH();
+      return TRB_OK;
+    }
+    case TRB_STAGE_PROJECT_X:  // P3: tx = U_R^T b6 (new)
+      return trb_lin_project(sw->Ut, sw->strideU, sw->R, sw->M, sw->ldm, B, sw->b5, sw->ldm,
+                             sw->tx, sw->active, sw->gemv_impl, stream);
+    case TRB_STAGE_RESCALE_BWD:  // S2: coef for rz, backward variance
+      return trb_lin_rescale(1, B, sw->R, sw->N, sw->M, sw->rank, null_space, sw->s, sw->s2,
+                             sw->stride_s, ea + 1 * B, ea + 5 * B, sw->tz, sw->tx, sw->coef,
+                             sw->vlin, sw->active, stream);
+    case TRB_STAGE_EXPAND_Z:  // P4: rz = [b2/a2 +] V_R coef
+      return trb_lin_expand(sw->Vt, sw->strideV, sw->R, sw->N, sw->ldn, B, sw->coef, sw->part,
+                            sw->active, sw->gemv_impl, stream);
+    case TRB_STAGE_X_UPDATE: {  // X: e7, posterior x, records, early stopping
+      trb_launch_scope scope_(0, st);
+      k_x_update<<<B, kUpThreads, 0, st>>>(*sw, G, it, sw->stats);
+      TRB_CHECK_LAUNCH();
+      return TRB_OK;
+    }
+    case TRB_STAGE_SNAPSHOT: {
+      if (!sw->snap_edge_a) return TRB_OK;
+      trb_launch_scope scope_(0, st);
+      k_snapshot<<<B, 256, 0, st>>>(*sw);
+      TRB_CHECK_LAUNCH();
+      return TRB_OK;
+    }
+  }
+  return trb_set_error(TRB_ERR_INVALID, "trb_sweep_stage: unknown stage %d", stage);
+}
+
+extern "C" int trb_sweep_run(const trb_sweep* sw, int it0, int n_iter, int fresh, void* stream) {
+  int rc = check_sweep(sw);
+  if (rc) return rc;
+  TRB_CHECK_ARG(it0 >= 0 && n_iter >= 0, "bad iteration range");
+  TRB_CHECK_ARG(fresh >= 0 && fresh <= 2, "fresh must be 0, 1 or 2");
   for (int k = 0; k < n_iter; ++k) {
     const int it = it0 + k;
     const int first = (fresh && k == 0) ? 1 : 0;
-    // F1: prior, reads e8, writes e1 and its pass-through copy e2
-    const double* b8 = (first && sw->b8_init) ? sw->b8_init : sw->b7;
-    TRB_TRY(trb_factor_message(&sw->prior, B, sw->N, sw->ldn, ea + 7 * B, b8, nullptr, ea + 0 * B,
-                               sw->b1, ea + 1 * B, sw->damp1, sw->scr_n, sw->flags, sw->active,
-                               stream));
-    // P1: tz = V_R^T b2
-    TRB_TRY(trb_lin_project(sw->Vt, sw->strideV, sw->R, sw->N, sw->ldn, B, sw->b1, sw->ldn, sw->tz,
-                            sw->active, sw->gemv_impl, stream));
+    TRB_TRY(trb_sweep_stage(sw, TRB_STAGE_PRIOR, it, first, 0, stream));
+    TRB_TRY(trb_sweep_stage(sw, TRB_STAGE_PROJECT_Z, it, first, 0, stream));
     if (first) {
-      // tx = U_R^T b6 for the initial e6 (later iterations reuse P3's result)
-      const double* b6 = sw->b6_init ? sw->b6_init : sw->b5;
-      TRB_TRY(trb_lin_project(sw->Ut, sw->strideU, sw->R, sw->M, sw->ldm, B, b6, sw->ldm, sw->tx,
-                              sw->active, sw->gemv_impl, stream));
+      if (fresh == 2) {  // e6 was initialised to b = 0: U_R^T 0 = 0, no pass over U needed
+        cudaError_t e = cudaMemsetAsync(sw->tx, 0, sizeof(double) * (size_t)sw->B * sw->R,
+                                        (cudaStream_t)stream);
+        if (e != cudaSuccess)
+          return trb_set_error(TRB_ERR_CUDA, "trb_sweep_run: %s", cudaGetErrorString(e));
+      } else {
+        TRB_TRY(trb_sweep_stage(sw, TRB_STAGE_PROJECT_X_INIT, it, first, 0, stream));
+      }
     }
-    // S1 + P2: rx = U_R [s res (tz + s tx)], forward variance
-    TRB_TRY(trb_lin_rescale(0, B, sw->R, sw->N, sw->M, sw->rank, sw->s, sw->s2, sw->stride_s,
-                            ea + 1 * B, ea + 5 * B, sw->tz, sw->tx, sw->coef, sw->vlin, sw->active,
-                            stream));
-    TRB_TRY(trb_lin_expand(sw->Ut, sw->strideU, sw->R, sw->M, sw->ldm, B, sw->coef, sw->part,
-                           sw->active, sw->gemv_impl, stream));
-    // Z: e3, likelihood e5, posterior z
-    {
-      trb_launch_scope scope_(0, st);
-      k_z_update<<<B, kUpThreads, 0, st>>>(*sw, geo.G, first, sw->stats);
-    }
-    TRB_CHECK_LAUNCH();
-    // P3: tx = U_R^T b6 (new)
-    TRB_TRY(trb_lin_project(sw->Ut, sw->strideU, sw->R, sw->M, sw->ldm, B, sw->b5, sw->ldm, sw->tx,
-                            sw->active, sw->gemv_impl, stream));
-    // S2 + P4: rz = [b2/a2 +] V_R coef, backward variance
-    TRB_TRY(trb_lin_rescale(1, B, sw->R, sw->N, sw->M, sw->rank, sw->s, sw->s2, sw->stride_s,
-                            ea + 1 * B, ea + 5 * B, sw->tz, sw->tx, sw->coef, sw->vlin, sw->active,
-                            stream));
-    TRB_TRY(trb_lin_expand(sw->Vt, sw->strideV, sw->R, sw->N, sw->ldn, B, sw->coef, sw->part,
-                           sw->active, sw->gemv_impl, stream));
-    // X: e7, posterior x, records, early stopping
-    {
-      trb_launch_scope scope_(0, st);
-      k_x_update<<<B, kUpThreads, 0, st>>>(*sw, geo.G, it, sw->stats);
-    }
-    TRB_CHECK_LAUNCH();
+    TRB_TRY(trb_sweep_stage(sw, TRB_STAGE_RESCALE_FWD, it, first, 0, stream));
+    TRB_TRY(trb_sweep_stage(sw, TRB_STAGE_EXPAND_X, it, first, 0, stream));
+    TRB_TRY(trb_sweep_stage(sw, TRB_STAGE_Z_UPDATE, it, first, 0, stream));
+    TRB_TRY(trb_sweep_stage(sw, TRB_STAGE_PROJECT_X, it, first, 0, stream));
+    TRB_TRY(trb_sweep_stage(sw, TRB_STAGE_RESCALE_BWD, it, first, 0, stream));
+    TRB_TRY(trb_sweep_stage(sw, TRB_STAGE_EXPAND_Z, it, first, 0, stream));
+    TRB_TRY(trb_sweep_stage(sw, TRB_STAGE_X_UPDATE, it, first, 0, stream));
+    TRB_TRY(trb_sweep_stage(sw, TRB_STAGE_SNAPSHOT, it, first, 0, stream));
   }
   return TRB_OK;
 }

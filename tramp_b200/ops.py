@@ -133,15 +133,14 @@ def posterior_rv(a1, b1, a2, b2, n):
 # ---------------------------------------------------------------------------
 # linear channel primitives
 # ---------------------------------------------------------------------------
-def lin_project(A, R, n, vec, B, impl=0, active=None):
+def lin_project(A, R, n, vec, B, impl=0, active=None, out=None):
     """A: [Bop, R, ld] device; vec: [B, ldvec].  Returns t [B, R]."""
     t_ = torch()
     lib = _lib.load()
     ld = A.shape[-1]
-    stride = 0 if A.shape[0] == 1 and B > 1 else A.stride(0)
-    if A.shape[0] == 1:
-        stride = 0
-    out = t_.zeros((B, R), dtype=t_.float64, device=A.device)
+    stride = 0 if A.shape[0] == 1 else A.stride(0)
+    if out is None:
+        out = t_.zeros((B, R), dtype=t_.float64, device=A.device)
     check(lib.trb_lin_project(ptr(A), stride, R, n, ld, B, ptr(vec), vec.shape[-1], ptr(out),
                               ptr(active), impl, current_stream()))
     return out
@@ -151,31 +150,40 @@ def lin_expand_slots(B, R):
     return _lib.load().trb_lin_expand_slots(B, R)
 
 
-def lin_expand(A, R, n, coef, B, impl=0, active=None, add=None, add_div=None):
+def lin_expand(A, R, n, coef, B, impl=0, active=None, add=None, add_div=None, out=None, part=None):
     """Returns out[B, ld] = sum_i coef[b, i] A[b, i, :] (+ add / add_div[:, None])."""
     t_ = torch()
     lib = _lib.load()
     ld = A.shape[-1]
     stride = 0 if A.shape[0] == 1 else A.stride(0)
     ns = lin_expand_slots(B, R)
-    part = t_.empty((B, ns, ld), dtype=t_.float64, device=A.device)
+    if part is None:
+        part = t_.empty((B, ns, ld), dtype=t_.float64, device=A.device)
     check(lib.trb_lin_expand(ptr(A), stride, R, n, ld, B, ptr(coef), ptr(part), ptr(active), impl,
                              current_stream()))
-    out = t_.zeros((B, ld), dtype=t_.float64, device=A.device)
+    if out is None:
+        out = t_.zeros((B, ld), dtype=t_.float64, device=A.device)
     check(lib.trb_lin_reduce_slots(B, R, n, ld, ptr(part), ptr(add), ptr(add_div), ptr(out),
                                    current_stream()))
     return out
 
 
-def lin_rescale(direction, B, R, Nz, Nx, rank, s, s2, az, ax, tz, tx, active=None):
+def lin_rescale(direction, B, R, Nz, Nx, rank, s, s2, az, ax, tz, tx, active=None,
+                null_space=None, want_coef=True, want_v=True, coef=None, v=None):
+    """Spectrum rescale; null_space defaults to R < Nz (pass it explicitly when R
+    is a row shard)."""
     t_ = torch()
     lib = _lib.load()
     stride = 0 if s.shape[0] == 1 else s.stride(0)
-    coef = t_.zeros((B, R), dtype=t_.float64, device=s.device)
-    v = t_.zeros(B, dtype=t_.float64, device=s.device)
-    check(lib.trb_lin_rescale(direction, B, R, Nz, Nx, rank, ptr(s), ptr(s2), stride, ptr(az),
-                              ptr(ax), ptr(tz), ptr(tx), ptr(coef), ptr(v), ptr(active),
-                              current_stream()))
+    if want_coef and coef is None:
+        coef = t_.zeros((B, R), dtype=t_.float64, device=s.device)
+    if want_v and v is None:
+        v = t_.zeros(B, dtype=t_.float64, device=s.device)
+    if null_space is None:
+        null_space = R < Nz
+    check(lib.trb_lin_rescale(direction, B, R, Nz, Nx, rank, int(null_space), ptr(s), ptr(s2), stride,
+                              ptr(az), ptr(ax), ptr(tz), ptr(tx), ptr(coef if want_coef else None),
+                              ptr(v if want_v else None), ptr(active), current_stream()))
     return coef, v
 
 
