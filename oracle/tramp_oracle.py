@@ -609,13 +609,17 @@ def ep_glm(prior, W, lik, max_iter, damping=None, init=None, x_true=None,
                     break
                 if (i > early_stopping.get("wait_increase", 5)
                         and max(tols) > early_stopping.get("max_increase", 0.2)):
+                    # reset_message_dag(old_message_dag), callbacks.py:281-283: edges AND
+                    # the variables' r, v go back to the end of the previous iteration
                     E = old_E
+                    r_x, v_x, r_z, v_z = old_post
                     status = "diverged"
                     break
             else:
                 traj["tol"].append(np.nan)
             old_rs = new_rs
             old_E = {k: [v[0], v[1].copy()] for k, v in E.items()}
+            old_post = (r_x, v_x, r_z, v_z)
     return dict(edges=E, r_x=r_x, v_x=v_x, r_z=r_z, v_z=v_z, n_iter=n_iter,
                 status=status, traj=traj, op=op)
 

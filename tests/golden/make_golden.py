@@ -275,6 +275,28 @@ def run_sweep(cfg, out, early=False):
         out[name + "_A_" + tag] = np.float64(data["A"])
 
 
+def run_diverging(out):
+    """An instance on which the default EarlyStoppingEP takes its `max_increase`
+    branch (callbacks.py:275-283): restore the previous iteration and stop."""
+    name = "cs_diverges_early"
+    rng = np.random.RandomState(9)
+    B, N, M = 4, 120, 60
+    W = rng.randn(B, M, N) / np.sqrt(N)
+    x = rng.randn(B, N) * (rng.rand(B, N) < 0.1)
+    y = np.einsum("bmn,bn->bm", W, x) + 0.1 * rng.randn(B, M)
+    W, x, y = W[3], x[3], y[3]
+    model = (GaussBernoulliPrior(size=N, rho=0.1) @ V("x") @ LinearChannel(W) @ V("z")
+             @ GaussianLikelihood(y=y, var=1e-2)).to_model()
+    ep = ExpectationPropagation(model)
+    ep.iterate(max_iter=200)
+    d = ep.get_variables_data()
+    out[name + "_W"], out[name + "_y"], out[name + "_x"] = W, y, x
+    out[name + "_rx"], out[name + "_rz"] = d["x"]["r"], d["z"]["r"]
+    out[name + "_vx_final"], out[name + "_vz_final"] = np.float64(d["x"]["v"]), np.float64(d["z"]["v"])
+    out[name + "_n_iter"] = np.int64(ep.n_iter)
+    _dump_edges(ep, out, name)
+
+
 def _dump_edges(ep, out, name):
     """Store the 8 edges under the SURVEY 3.3 names e1..e8."""
     for s, t, data in ep.message_dag.edges(data=True):
@@ -311,6 +333,7 @@ def main():
             run_sweep(cfg, sw)
     for cfg in SWEEPS[:3]:
         run_sweep(cfg, sw, early=True)
+    run_diverging(sw)
     import json
     sw["configs"] = np.array(json.dumps(SWEEPS))
     np.savez_compressed(os.path.join(HERE, "sweeps.npz"), **sw)

@@ -141,6 +141,33 @@ def test_default_early_stopping(sw, idx):
     assert_allclose(d["x"]["v"], sw[name + "_vx_final"], rtol=1e-9)
 
 
+def test_early_stopping_divergence_restores_previous_iteration(sw):
+    """EarlyStoppingEP's max_increase branch (callbacks.py:275-283) on the device:
+    the instance is frozen AND rolled back to the end of the previous iteration."""
+    from tramp_b200.algos import ExpectationPropagation, TrackEstimate, JoinCallback, EarlyStoppingEP
+    from tramp_b200.priors import GaussBernoulliPrior
+    from tramp_b200.likelihoods import GaussianLikelihood
+    from tramp_b200.channels import LinearChannel
+    from tramp_b200.variables import SISOVariable as V
+    name = "cs_diverges_early"
+
+    def build():
+        return (GaussBernoulliPrior(size=120, rho=0.1) @ V("x") @ LinearChannel(sw[name + "_W"]) @ V("z")
+                @ GaussianLikelihood(y=sw[name + "_y"], var=1e-2)).to_model()
+    for callback in (None, JoinCallback([TrackEstimate(ids=["x"]), EarlyStoppingEP()])):   # device / host path
+        ep = ExpectationPropagation(build())
+        ep.iterate(max_iter=200, callback=callback)
+        assert ep.n_iter == int(sw[name + "_n_iter"]) == 7
+        d = ep.get_variables_data()
+        assert_allclose(d["x"]["r"], sw[name + "_rx"], rtol=1e-9, atol=1e-12)
+        assert_allclose(d["z"]["r"], sw[name + "_rz"], rtol=1e-9, atol=1e-12)
+        assert_allclose(d["x"]["v"], sw[name + "_vx_final"], rtol=1e-9)
+        for k in range(1, 9):
+            a, b = ep._edge(f"e{k}")
+            assert_allclose(a, sw[f"{name}_e{k}_a"], rtol=1e-9)
+            assert_allclose(b, sw[f"{name}_e{k}_b"], rtol=1e-9, atol=1e-12)
+
+
 def test_synchronous_callback_path_equals_device_path(sw):
     """An arbitrary callback (TrackEstimate needs r every iteration) forces the
     per-iteration path; it must give the same trajectory as the device path."""

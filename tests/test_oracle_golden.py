@@ -154,3 +154,18 @@ def test_sweep_early_stopping(sw, idx):
     assert out["status"] == "converged"
     assert_allclose(out["r_x"], sw[name + "_rx"], rtol=1e-9, atol=1e-12)
     assert_allclose(out["v_x"], sw[name + "_vx_final"], rtol=1e-9)
+
+
+def test_sweep_early_stopping_divergence_branch(sw):
+    """EarlyStoppingEP's max_increase branch: messages and estimates roll back one iteration."""
+    name = "cs_diverges_early"
+    lik = dict(kind="gaussian", var=1e-2, y=sw[name + "_y"])
+    out = orc.ep_glm(dict(kind="gauss_bernoulli", rho=0.1), sw[name + "_W"], lik, 200,
+                     early_stopping=dict(tol=1e-6))
+    assert out["status"] == "diverged" and out["n_iter"] == int(sw[name + "_n_iter"]) == 7
+    assert_allclose(out["r_x"], sw[name + "_rx"], rtol=1e-9, atol=1e-12)
+    assert_allclose(out["r_z"], sw[name + "_rz"], rtol=1e-9, atol=1e-12)
+    assert_allclose(out["v_x"], sw[name + "_vx_final"], rtol=1e-9)
+    for k in range(1, 9):
+        assert_allclose(out["edges"][f"e{k}"][0], sw[f"{name}_e{k}_a"], rtol=1e-9)
+        assert_allclose(out["edges"][f"e{k}"][1], sw[f"{name}_e{k}_b"], rtol=1e-9, atol=1e-12)
