@@ -306,7 +306,7 @@ class MessagePassing():
                 ops.lin_rescale(direction, B, lin.R_total, N, M, lin.rank, lin.s_full, lin.s2_full,
                                 ea[1], ea[5], None, None, st["active"], null_space=lin.R_total < N,
                                 want_coef=False, v=st["vlin"])
-                ops.lin_rescale(direction, B, R, N, M, lin.rank, lin.s, lin.s2, ea[1], ea[5],
+                ops.lin_rescale(direction, B, R, N, M, min(lin.rank, R), lin.s, lin.s2, ea[1], ea[5],
                                 st["tz"], st["tx"], st["active"], null_space=lin.R_total < N,
                                 want_v=False, coef=st["coef"])
             else:
