@@ -63,6 +63,33 @@ __device__ __forceinline__ double block_sum(double v, double* sh) {
   return sh[32];
 }
 
+// Sums K values over the block with one barrier round; results valid in every
+// thread.  `sh` holds >= 33*K doubles.
+template <int K>
+__device__ __forceinline__ void block_sum_n(double (&v)[K], double* sh) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int nwarp = (blockDim.x + 31) >> 5;
+#pragma unroll
+  for (int k = 0; k < K; ++k) v[k] = warp_sum(v[k]);
+  __syncthreads();
+  if (lane == 0) {
+#pragma unroll
+    for (int k = 0; k < K; ++k) sh[k * 33 + warp] = v[k];
+  }
+  __syncthreads();
+  if (warp == 0) {
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      double t = (lane < nwarp) ? sh[k * 33 + lane] : 0.0;
+      t = warp_sum(t);
+      if (lane == 0) sh[k * 33 + 32] = t;
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < K; ++k) v[k] = sh[k * 33 + 32];
+}
+
 __device__ __forceinline__ int block_or(int v, int* sh) {
   v = __reduce_or_sync(0xffffffffu, v);
   __syncthreads();

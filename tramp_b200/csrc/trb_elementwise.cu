@@ -172,21 +172,52 @@ k_factor_message(trb_factor f, int n, int ld, const double* __restrict__ a_in,
       if (bn != bn) flag |= TRB_FLAG_NAN_B;
     }
   } else {
+    constexpr int U = 4;  // elements per thread whose loads are issued together
+    const int step = blockDim.x * U;
     double vsum = 0.0;
-    for (int i = threadIdx.x; i < n; i += blockDim.x) {
-      const double yi = y ? y[off + i] : 0.0;
-      const RV m = factor_moments(f, a, b_in[off + i], yi);
-      scratch[off + i] = m.r;
-      vsum += m.v;
+    for (int base = threadIdx.x; base < n; base += step) {
+      double bv[U], yv[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int i = base + u * blockDim.x;
+        if (i < n) {
+          bv[u] = b_in[off + i];
+          yv[u] = y ? y[off + i] : 0.0;
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int i = base + u * blockDim.x;
+        if (i < n) {
+          const RV m = factor_moments(f, a, bv[u], yv[u]);
+          scratch[off + i] = m.r;
+          vsum += m.v;
+        }
+      }
     }
     const double v = block_sum(vsum, sh) / n;
     a_new = clip_a_new(v, a, f.amin, f.amax);
     const double ainv = a + a_new;
-    for (int i = threadIdx.x; i < n; i += blockDim.x) {
-      const double bn = scratch[off + i] * ainv - b_in[off + i];
-      const double bd = damp(damping, b_io[off + i], bn);
-      b_io[off + i] = bd;
-      if (bn != bn) flag |= TRB_FLAG_NAN_B;
+    for (int base = threadIdx.x; base < n; base += step) {
+      double rv[U], bv[U], bo[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int i = base + u * blockDim.x;
+        if (i < n) {
+          rv[u] = scratch[off + i];
+          bv[u] = b_in[off + i];
+          bo[u] = b_io[off + i];
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int i = base + u * blockDim.x;
+        if (i < n) {
+          const double bn = rv[u] * ainv - bv[u];
+          b_io[off + i] = damp(damping, bo[u], bn);
+          if (bn != bn) flag |= TRB_FLAG_NAN_B;
+        }
+      }
     }
   }
   if (a_new != a_new) flag |= TRB_FLAG_NAN_A;

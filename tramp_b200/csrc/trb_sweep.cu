@@ -37,10 +37,12 @@ __device__ __forceinline__ int slots_of(int b, int R, int B, int G) {
   return kl - kf + 1;
 }
 
-// stats[b*4 + {0,1}] = sum (r_new - r_old)^2, sum r_new^2 for z; {2,3} for x
+constexpr int kUnroll = 4;  // elements per thread whose loads are issued together
+
+// stats[b*4 + {0,1}] = sum (r_new - r_old)^2, sum r_new^2 for z
 __global__ void __launch_bounds__(kUpThreads)
 k_z_update(trb_sweep sw, int G, int first, double* __restrict__ stats) {
-  __shared__ double sh[33];
+  __shared__ double sh[33 * 2];
   __shared__ int sh_flag;
   const int b = blockIdx.x;
   if (sw.active && !sw.active[b]) return;
@@ -53,21 +55,44 @@ k_z_update(trb_sweep sw, int G, int first, double* __restrict__ stats) {
   const double ainv3 = a6 + a3n;
   const int ns = slots_of(b, sw.R, B, G);
   const double* part = sw.part + (size_t)b * sw.nslots * ld;
-  const double* b6 = (first && sw.b6_init) ? sw.b6_init : sw.b5;
+  const double* b6 = ((first && sw.b6_init) ? sw.b6_init : sw.b5) + off;
+  double* b3 = sw.b3 + off;
+  double* b5 = sw.b5 + off;
+  double* rz = sw.rz + off;
+  double* scr = sw.scr_m + off;
+  const double* y = sw.y + off;
   const bool const_lik = factor_is_constant_message(sw.lik.kind);
+  const int step = blockDim.x * kUnroll;
   int flag = 0;
   double vsum = 0.0;
-  for (int i = threadIdx.x; i < M; i += blockDim.x) {
-    double rx = 0.0;
-    for (int sl = 0; sl < ns; ++sl) rx += part[(size_t)sl * ld + i];
-    const double b3n = rx * ainv3 - b6[off + i];
-    if (b3n != b3n) flag |= TRB_FLAG_NAN_B;
-    const double b3v = damp(sw.damp3, sw.b3[off + i], b3n);
-    sw.b3[off + i] = b3v;
-    if (!const_lik) {
-      const RV m = factor_moments(sw.lik, a3, b3v, sw.y[off + i]);
-      sw.scr_m[off + i] = m.r;
-      vsum += m.v;
+  // pass 1: e3 (= e4) and the likelihood moments at (a3, b3)
+  for (int base = threadIdx.x; base < M; base += step) {
+    double rx[kUnroll], b6v[kUnroll], b3o[kUnroll], yv[kUnroll];
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) {
+      const int i = base + u * blockDim.x;
+      rx[u] = 0.0;
+      if (i < M) {
+        for (int sl = 0; sl < ns; ++sl) rx[u] += part[(size_t)sl * ld + i];
+        b6v[u] = b6[i];
+        b3o[u] = b3[i];
+        yv[u] = y[i];
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) {
+      const int i = base + u * blockDim.x;
+      if (i < M) {
+        const double b3n = rx[u] * ainv3 - b6v[u];
+        if (b3n != b3n) flag |= TRB_FLAG_NAN_B;
+        const double b3v = damp(sw.damp3, b3o[u], b3n);
+        b3[i] = b3v;
+        if (!const_lik) {
+          const RV m = factor_moments(sw.lik, a3, b3v, yv[u]);
+          scr[i] = m.r;
+          vsum += m.v;
+        }
+      }
     }
   }
   double a5n;
@@ -80,21 +105,36 @@ k_z_update(trb_sweep sw, int G, int first, double* __restrict__ stats) {
   const double a5 = damp(sw.damp5, ea[4 * B + b], a5n);
   const double ainv5 = a3 + a5n;
   const double a_hat = a3 + a5;
-  double d2 = 0.0, n2 = 0.0;
-  for (int i = threadIdx.x; i < M; i += blockDim.x) {
-    const double b3v = sw.b3[off + i];
-    const double b5n = const_lik ? sw.y[off + i] * sw.lik.p0 : sw.scr_m[off + i] * ainv5 - b3v;
-    if (b5n != b5n) flag |= TRB_FLAG_NAN_B;
-    const double b5v = damp(sw.damp5, sw.b5[off + i], b5n);
-    sw.b5[off + i] = b5v;
-    const double rnew = (b3v + b5v) / a_hat;  // base.py:152-161
-    const double rold = sw.rz[off + i];
-    sw.rz[off + i] = rnew;
-    d2 += (rnew - rold) * (rnew - rold);
-    n2 += rnew * rnew;
+  double red[2] = {0.0, 0.0};
+  // pass 2: e5 (= e6) and the posterior of z
+  for (int base = threadIdx.x; base < M; base += step) {
+    double b3v[kUnroll], src[kUnroll], b5o[kUnroll], ro[kUnroll];
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) {
+      const int i = base + u * blockDim.x;
+      if (i < M) {
+        b3v[u] = b3[i];
+        src[u] = const_lik ? y[i] : scr[i];
+        b5o[u] = b5[i];
+        ro[u] = rz[i];
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) {
+      const int i = base + u * blockDim.x;
+      if (i < M) {
+        const double b5n = const_lik ? src[u] * sw.lik.p0 : src[u] * ainv5 - b3v[u];
+        if (b5n != b5n) flag |= TRB_FLAG_NAN_B;
+        const double b5v = damp(sw.damp5, b5o[u], b5n);
+        b5[i] = b5v;
+        const double rnew = (b3v[u] + b5v) / a_hat;  // base.py:152-161
+        rz[i] = rnew;
+        red[0] += (rnew - ro[u]) * (rnew - ro[u]);
+        red[1] += rnew * rnew;
+      }
+    }
   }
-  d2 = block_sum(d2, sh);
-  n2 = block_sum(n2, sh);
+  block_sum_n<2>(red, sh);
   if (a3n != a3n || a5n != a5n) flag |= TRB_FLAG_NAN_A;
   if (a3n < 0 || a5n < 0) flag |= TRB_FLAG_NEG_A;
   const int all = block_or(flag, &sh_flag);
@@ -104,15 +144,15 @@ k_z_update(trb_sweep sw, int G, int first, double* __restrict__ stats) {
     ea[4 * B + b] = a5;
     ea[5 * B + b] = a5;  // e6 = e5 (sub_variables.py:27-31)
     sw.vz[b] = 1. / a_hat;
-    stats[b * 4 + 0] = d2;
-    stats[b * 4 + 1] = n2;
+    stats[b * 4 + 0] = red[0];
+    stats[b * 4 + 1] = red[1];
     if (all) atomicOr(&sw.flags[b], all);
   }
 }
 
 __global__ void __launch_bounds__(kUpThreads)
 k_x_update(trb_sweep sw, int G, int it, double* __restrict__ stats) {
-  __shared__ double sh[33];
+  __shared__ double sh[33 * 4];
   __shared__ int sh_flag;
   const int b = blockIdx.x;
   if (sw.active && !sw.active[b]) return;
@@ -127,34 +167,49 @@ k_x_update(trb_sweep sw, int G, int it, double* __restrict__ stats) {
   const int ns = slots_of(b, sw.R, B, G);
   const double* part = sw.part + (size_t)b * sw.nslots * ld;
   const bool null_space = (sw.R_total > 0 ? sw.R_total : sw.R) < N;
+  const double* b1 = sw.b1 + off;
+  double* b7 = sw.b7 + off;
+  double* rx = sw.rx + off;
+  const double* xt = sw.x_true ? sw.x_true + off : nullptr;
+  const int step = blockDim.x * kUnroll;
   int flag = 0;
-  double d2 = 0.0, n2 = 0.0, e_pos = 0.0, e_neg = 0.0;
-  for (int i = threadIdx.x; i < N; i += blockDim.x) {
-    double rzv = 0.0;
-    for (int sl = 0; sl < ns; ++sl) rzv += part[(size_t)sl * ld + i];
-    const double b1v = sw.b1[off + i];
-    if (null_space) rzv = b1v / a1 + rzv;
-    const double b7n = rzv * ainv7 - b1v;
-    if (b7n != b7n) flag |= TRB_FLAG_NAN_B;
-    const double b7v = damp(sw.damp7, sw.b7[off + i], b7n);
-    sw.b7[off + i] = b7v;
-    const double rnew = (b1v + b7v) / a_hat;
-    const double rold = sw.rx[off + i];
-    sw.rx[off + i] = rnew;
-    d2 += (rnew - rold) * (rnew - rold);
-    n2 += rnew * rnew;
-    if (sw.x_true) {
-      const double xt = sw.x_true[off + i];
-      e_pos += (rnew - xt) * (rnew - xt);  // metrics.py:5-6
-      e_neg += (rnew + xt) * (rnew + xt);  // metrics.py:9-14
+  double red[4] = {0.0, 0.0, 0.0, 0.0};  // sum dr^2, sum r^2, sum (r-x)^2, sum (r+x)^2
+  for (int base = threadIdx.x; base < N; base += step) {
+    double rzv[kUnroll], b1v[kUnroll], b7o[kUnroll], ro[kUnroll], xv[kUnroll];
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) {
+      const int i = base + u * blockDim.x;
+      rzv[u] = 0.0;
+      xv[u] = 0.0;
+      if (i < N) {
+        for (int sl = 0; sl < ns; ++sl) rzv[u] += part[(size_t)sl * ld + i];
+        b1v[u] = b1[i];
+        b7o[u] = b7[i];
+        ro[u] = rx[i];
+        if (xt) xv[u] = xt[i];
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) {
+      const int i = base + u * blockDim.x;
+      if (i < N) {
+        double r = rzv[u];
+        if (null_space) r = b1v[u] / a1 + r;
+        const double b7n = r * ainv7 - b1v[u];
+        if (b7n != b7n) flag |= TRB_FLAG_NAN_B;
+        const double b7v = damp(sw.damp7, b7o[u], b7n);
+        b7[i] = b7v;
+        const double rnew = (b1v[u] + b7v) / a_hat;
+        rx[i] = rnew;
+        red[0] += (rnew - ro[u]) * (rnew - ro[u]);
+        red[1] += rnew * rnew;
+        red[2] += (rnew - xv[u]) * (rnew - xv[u]);  // metrics.py:5-6
+        red[3] += (rnew + xv[u]) * (rnew + xv[u]);  // metrics.py:9-14
+      }
     }
   }
-  d2 = block_sum(d2, sh);
-  n2 = block_sum(n2, sh);
-  if (sw.x_true) {
-    e_pos = block_sum(e_pos, sh);
-    e_neg = block_sum(e_neg, sh);
-  }
+  block_sum_n<4>(red, sh);
+  const double d2 = red[0], n2 = red[1], e_pos = red[2], e_neg = red[3];
   if (a7n != a7n) flag |= TRB_FLAG_NAN_A;
   if (a7n < 0) flag |= TRB_FLAG_NEG_A;
   const int all = block_or(flag, &sh_flag);
@@ -173,8 +228,8 @@ k_x_update(trb_sweep sw, int G, int it, double* __restrict__ stats) {
       if (rec && sw.rec_mse) sw.rec_mse[(size_t)it * B + b] = mse;
       if (rec && sw.rec_smse) sw.rec_smse[(size_t)it * B + b] = fmin(mse, mse_neg);
     }
-    // EarlyStoppingEP(ids="all"), callbacks.py:258-286: tol = rms(new-old)/rms(new),
-    // max over variables; needs a previous estimate, i.e. it > 0.
+    // EarlyStoppingEP, callbacks.py:258-286: tol = rms(new-old)/rms(new), max over the
+    // tracked variables; needs a previous estimate, i.e. it > 0.
     double tol = nan("");
     if (it > 0) {
       const double tol_x = sqrt(d2 / N) / sqrt(n2 / N);
