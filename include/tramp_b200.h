@@ -85,8 +85,9 @@ int trb_device_sm_count(void);
 /* Launch accounting for benchmarks: trb_profile_reset(enable_events) zeroes the
  * counters (and, if enable_events, brackets every GEMV launch with CUDA events
  * on its stream); trb_profile_launches(kind) = kernels launched since then
- * (kind 0 elementwise/update, 1 GEMV, -1 all); trb_profile_gemv_ms sums the
- * event-timed GEMV durations and returns how many launches were timed. */
+ * (kind 0 elementwise/update, 1 operator pass = GEMV or shared-operator GEMM,
+ * -1 all); trb_profile_gemv_ms sums the event-timed operator-pass durations and
+ * returns how many launches were timed. */
 void trb_profile_reset(int enable_events);
 long long trb_profile_launches(int kind);
 int trb_profile_gemv_ms(double* total_ms);
@@ -166,6 +167,21 @@ int trb_lin_reduce_slots(int B, int R, int n, int ld, const double* part,
                          const double* add, const double* add_scale_inv,
                          double* out, void* stream);
 
+/* The same two passes for B >= 1 instances that SHARE one operator A[R, ld]
+ * (2-D W in LinearChannel), as dense FP64 tensor-core GEMMs (DMMA m8n8k4):
+ *   trb_lin_project_gemm: t[B, R]       = vec[B, n] . A^T     (linear_channel.py:72-73)
+ *   trb_lin_expand_gemm : out[B, ldout] = coef[B, R] . A      (linear_channel.py:78, :88)
+ * `out` is the complete sum (no slots); columns >= n of out are left untouched. */
+int trb_lin_project_gemm(const double* A, int R, int n, int ld, int B,
+                         const double* vec, int ldvec, double* t, void* stream);
+int trb_lin_expand_gemm(const double* A, int R, int n, int ld, int B,
+                        const double* coef, double* out, int ldout, void* stream);
+/* kernel behind the two calls above: 0 (default) = TMA + mbarrier pipeline when
+ * the operands are 16-byte aligned, else the cp.async one; 1 = always cp.async;
+ * 2 / 4 = measurement probes that do NOT compute the product (MMA loop without
+ * loads / loads without MMA), used by tools/bench_gemm.py only */
+void trb_gemm_set_variant(int variant);
+
 /* Spectrum rescale between the projections and the expansions, plus the
  * variances (linear_channel.py:58-67, 74, 91-105).
  *   dir = 0 (forward, x-side mean):  coef = s*res*(tz + s*tx),  v = forward variance
@@ -225,7 +241,9 @@ typedef struct {
   int32_t max_records;
   /* EarlyStoppingEP(ids="all"): enabled if es_tol >= 0 */
   double es_tol, es_max_increase; int32_t es_wait_increase;
-  int32_t gemv_impl;   /* 0 default, 1 LDG, 2 TMA ring */
+  int32_t gemv_impl;   /* operator passes: 0 default (DMMA GEMM if the batch shares one operator
+                        * and B >= 16, else TMA-ring GEMV), 1 LDG GEMV, 2 TMA-ring GEMV, 3 DMMA GEMM
+                        * (needs strideV == strideU == 0) */
   int32_t es_vars;     /* variables the tolerance runs over: bit 0 = x, bit 1 = z (ids="all": 3) */
   /* one-iteration-back snapshot (`old_message_dag`, message_passing.py:356): same
    * shapes as edge_a, b1, b3, b5, b7, rx, rz, vx, vz, tx.  NULL snap_edge_a = no

@@ -250,7 +250,7 @@ def test_batched_instances_match_oracle(kinds):
     B, N, M, n_iter, damping = 5, 96, 144 if lk != "gaussian" else 48, 25, 0.3
     pkw = dict(gauss_bernoulli=dict(rho=0.2), gaussian={}, binary=dict(p_pos=0.6))[pk]
     lkw = dict(gaussian=dict(var=0.02), sgn={}, abs={})[lk]
-    for shared in (False, True):
+    for shared in (False, "gemm", "cublas"):
         W = rng.randn(*(() if shared else (B,)), M, N) / np.sqrt(N)
         if pk == "gauss_bernoulli":
             x = rng.randn(B, N) * (rng.rand(B, N) < 0.2)
@@ -266,10 +266,12 @@ def test_batched_instances_match_oracle(kinds):
                  @ get_likelihood(y=y, likelihood_type=lk, **lkw)).to_model()
         ep = ExpectationPropagation(model)
         if shared:
-            ep.linear_backend = "gemm"      # shared W: the four passes become FP64 GEMMs
+            # shared W: the four passes become FP64 GEMMs -- "gemm" = the DMMA kernels
+            # of trb_gemm.cu inside trb_sweep_run, "cublas" = the library baseline
+            ep.linear_backend = shared
         track = TrackErrors({"x": x}, metrics=["mse", "sign_mse"])
         ep.iterate(max_iter=n_iter, callback=track, damping=damping)
-        assert ep.backend == ("gemm" if shared else "gemv")
+        assert ep.backend == (shared or "gemv")
         got = ep.get_variables_data()
         assert got["x"]["r"].shape == (B, N) and got["x"]["v"].shape == (B,)
         for b in range(B):

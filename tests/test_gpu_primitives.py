@@ -199,6 +199,48 @@ def test_gemv_shapes_vs_numpy(ops, impl, shape):
     assert_allclose(_np(t)[1:], np.einsum("brn,bn->br", A, x)[1:], rtol=1e-11, atol=1e-11)
 
 
+@pytest.mark.parametrize("shape", [(1, 5, 7), (16, 40, 100), (5, 64, 1000), (70, 129, 131), (130, 17, 257),
+                                    (200, 300, 2048), (33, 255, 77), (128, 128, 128), (300, 130, 272),
+                                    (64, 256, 160)])
+@pytest.mark.parametrize("variant", [0, 1])
+def test_shared_operator_dmma_gemm_vs_numpy(ops, shape, variant):
+    """The FP64 tensor-core (DMMA m8n8k4) GEMMs of a batch that shares one
+    operator: ragged B / R / n (odd sizes, tile tails, 8-byte-aligned coef rows),
+    padding columns holding garbage on input and untouched on output.  variant 0 =
+    TMA/mbarrier kernel (cp.async one when R is odd), 1 = cp.async kernel."""
+    from tramp_b200 import _lib
+    _lib.load().trb_gemm_set_variant(variant)
+    try:
+        _check_dmma_gemm(ops, shape)
+    finally:
+        _lib.load().trb_gemm_set_variant(0)
+
+
+def _check_dmma_gemm(ops, shape):
+    B, R, n = shape
+    rng = np.random.RandomState(B * 1000 + R)
+    A = rng.randn(R, n)
+    x = rng.randn(B, n)
+    c = rng.randn(B, R)
+    ld = ops.pad_ld(n)
+    import torch
+    A_d = torch.full((1, R, ld), float("nan"), dtype=torch.float64, device="cuda")
+    A_d[0, :, :n] = torch.as_tensor(A, device="cuda")
+    x_d = torch.full((B, ld), float("nan"), dtype=torch.float64, device="cuda")
+    x_d[:, :n] = torch.as_tensor(x, device="cuda")
+    t = ops.lin_project_gemm(A_d, R, n, x_d, B)
+    assert_allclose(_np(t), x @ A.T, rtol=1e-11, atol=1e-11)
+    out = torch.full((B, ld), 7.0, dtype=torch.float64, device="cuda")
+    ops.lin_expand_gemm(A_d, R, n, ops.to_dev(c), B, out=out)
+    assert_allclose(_np(out)[:, :n], c @ A, rtol=1e-11, atol=1e-11)
+    assert np.all(_np(out)[:, n:] == 7.0)
+    # same numbers as the GEMV path on the shared operator, to summation-order round-off
+    A0 = A_d.clone()
+    A0[0, :, n:] = 0
+    t2 = ops.lin_project(A0, R, n, ops.padded(x), B, 2)
+    assert_allclose(_np(t), _np(t2), rtol=1e-12, atol=1e-12)
+
+
 @pytest.mark.parametrize("shape", [(2, 21, 9000), (1, 40, 20000), (3, 10, 16390)])
 def test_gemv_wide_operators_use_column_panels(ops, shape):
     """ld > 8192 doubles exceeds one TMA ring stage: the operator is processed as

@@ -83,6 +83,9 @@ SIGNATURES = {
     "trb_lin_project": (_I, [_P, _L, _I, _I, _I, _I, _P, _I, _P, _P, _I, _P]),
     "trb_lin_expand_slots": (_I, [_I, _I]),
     "trb_lin_expand": (_I, [_P, _L, _I, _I, _I, _I, _P, _P, _P, _I, _P]),
+    "trb_lin_project_gemm": (_I, [_P, _I, _I, _I, _I, _P, _I, _P, _P]),
+    "trb_lin_expand_gemm": (_I, [_P, _I, _I, _I, _I, _P, _P, _I, _P]),
+    "trb_gemm_set_variant": (None, [_I]),
     "trb_lin_reduce_slots": (_I, [_I, _I, _I, _I, _P, _P, _P, _P, _P]),
     "trb_lin_rescale": (_I, [_I, _I, _I, _I, _I, _I, _I, _P, _P, _L, _P, _P, _P, _P, _P, _P, _P, _P]),
     "trb_sweep_run": (_I, [C.POINTER(TrbSweep), _I, _I, _I, _P]),

@@ -55,8 +55,10 @@ class MessagePassing():
         self.n_iter = 0
         self.gemv_impl = 0
         # how the four operator passes run: "gemv" (batched HBM-bound GEMVs, the
-        # default), "gemm" (cuBLAS FP64 GEMMs when a batch shares one W), "sharded"
-        # (rows of the operators split over ranks + all-reduce); None = pick
+        # default), "gemm" (hand-written FP64 tensor-core DMMA GEMMs when a batch
+        # shares one W), "sharded" (rows of the operators split over ranks +
+        # all-reduce), "cublas" (torch.matmul, kept only as the library baseline the
+        # DMMA kernel is measured against); None = pick
         self.linear_backend = None
         self._state = None
         self._has_messages = False
@@ -124,7 +126,7 @@ class MessagePassing():
         self.backend = self._pick_backend()
         st["nslots"] = ops.lin_expand_slots(B, R)
         st["part"] = t.zeros((B, st["nslots"], max(ldn, ldm)), **f64)
-        if self.backend != "gemv":
+        if self.backend not in ("gemv", "gemm"):
             # fully reduced expansion results, read by the update kernels as slot 0
             st["red"] = t.zeros(B * max(ldn, ldm), **f64)
             st["red_n"] = st["red"][:B * ldn].view(B, ldn)
@@ -250,7 +252,7 @@ class MessagePassing():
             sw.es_wait_increase, sw.es_vars = early.wait_increase, early._var_mask(self)
         else:
             sw.es_tol, sw.es_max_increase, sw.es_wait_increase, sw.es_vars = -1.0, 0.0, 0, 3
-        sw.gemv_impl = self.gemv_impl
+        sw.gemv_impl = 3 if self.backend == "gemm" else (self.gemv_impl or 2)
         sw.R_total = getattr(lin, "R_total", 0) or 0
         for k in ("edge_a", "b1", "b3", "b5", "b7", "rx", "rz", "vx", "vz", "tx"):
             setattr(sw, "snap_" + k, p(st["snap_" + k]))
@@ -260,7 +262,7 @@ class MessagePassing():
         """Enqueue n_iter iterations.  fresh: the messages were just initialised."""
         st = self._state
         code = 0 if not fresh else (2 if st.get("b6_zero") else 1)
-        if self.backend == "gemv":
+        if self.backend in ("gemv", "gemm"):
             _lib.check(_lib.load().trb_sweep_run(C.byref(sw), it0, n_iter, code, _lib.current_stream()))
         else:
             self._run_staged(sw, it0, n_iter, code)
@@ -268,7 +270,7 @@ class MessagePassing():
     def _run_staged(self, sw, it0, n_iter, fresh):
         """Same schedule as trb_sweep_run (tramp_b200/csrc/trb_sweep.cu) with the four
         operator passes replaced by the back end: cuBLAS FP64 GEMMs on a shared W
-        ("gemm") or local GEMVs on this rank's row shard followed by an all-reduce
+        ("cublas") or local GEMVs on this rank's row shard followed by an all-reduce
         ("sharded").  Every other stage is the same CUDA kernel."""
         t = ops.torch()
         lib = _lib.load()

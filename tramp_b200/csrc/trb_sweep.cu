@@ -331,6 +331,12 @@ extern "C" int trb_sweep_stage(const trb_sweep* sw, int stage, int it, int first
   TRB_CHECK_ARG(!needs_s || (sw->s && sw->s2), "null spectrum");
   const int R_total = sw->R_total > 0 ? sw->R_total : sw->R;
   const int null_space = R_total < sw->N;
+  // operator passes as shared-operator DMMA GEMMs (trb_gemm.cu): the expansion
+  // lands fully summed in slot 0 of `part`, like a pre-reduced back end
+  const bool shared_ops = sw->strideV == 0 && sw->strideU == 0;
+  TRB_CHECK_ARG(sw->gemv_impl != 3 || shared_ops, "gemv_impl 3 (GEMM) needs a shared operator");
+  const bool gemm = shared_ops && (sw->gemv_impl == 3 || (sw->gemv_impl == 0 && B >= 16));
+  if (gemm) pre_reduced = 1;
   int G = 0;
   if (stage == TRB_STAGE_Z_UPDATE || stage == TRB_STAGE_X_UPDATE) {
     if (pre_reduced) {
@@ -349,10 +355,15 @@ extern "C" int trb_sweep_stage(const trb_sweep* sw, int stage, int it, int first
                                 stream);
     }
     case TRB_STAGE_PROJECT_Z:  // P1: tz = V_R^T b2
+      if (gemm)
+        return trb_lin_project_gemm(sw->Vt, sw->R, sw->N, sw->ldn, B, sw->b1, sw->ldn, sw->tz,
+                                    stream);
       return trb_lin_project(sw->Vt, sw->strideV, sw->R, sw->N, sw->ldn, B, sw->b1, sw->ldn,
                              sw->tz, sw->active, sw->gemv_impl, stream);
     case TRB_STAGE_PROJECT_X_INIT: {  // tx = U_R^T b6 for the initial e6
       const double* b6 = sw->b6_init ? sw->b6_init : sw->b5;
+      if (gemm)
+        return trb_lin_project_gemm(sw->Ut, sw->R, sw->M, sw->ldm, B, b6, sw->ldm, sw->tx, stream);
       return trb_lin_project(sw->Ut, sw->strideU, sw->R, sw->M, sw->ldm, B, b6, sw->ldm, sw->tx,
                              sw->active, sw->gemv_impl, stream);
     }
@@ -361,6 +372,9 @@ extern "C" int trb_sweep_stage(const trb_sweep* sw, int stage, int it, int first
                              sw->stride_s, ea + 1 * B, ea + 5 * B, sw->tz, sw->tx, sw->coef,
                              sw->vlin, sw->active, stream);
     case TRB_STAGE_EXPAND_X:  // P2: rx = U_R coef
+      if (gemm)
+        return trb_lin_expand_gemm(sw->Ut, sw->R, sw->M, sw->ldm, B, sw->coef, sw->part,
+                                   sw->nslots * sw->ldm, stream);
       return trb_lin_expand(sw->Ut, sw->strideU, sw->R, sw->M, sw->ldm, B, sw->coef, sw->part,
                             sw->active, sw->gemv_impl, stream);
     case TRB_STAGE_Z_UPDATE: {  // Z: e3, likelihood e5, posterior z
@@ -370,6 +384,9 @@ extern "C" int trb_sweep_stage(const trb_sweep* sw, int stage, int it, int first
       return TRB_OK;
     }
     case TRB_STAGE_PROJECT_X:  // P3: tx = U_R^T b6 (new)
+      if (gemm)
+        return trb_lin_project_gemm(sw->Ut, sw->R, sw->M, sw->ldm, B, sw->b5, sw->ldm, sw->tx,
+                                    stream);
       return trb_lin_project(sw->Ut, sw->strideU, sw->R, sw->M, sw->ldm, B, sw->b5, sw->ldm,
                              sw->tx, sw->active, sw->gemv_impl, stream);
     case TRB_STAGE_RESCALE_BWD:  // S2: coef for rz, backward variance
@@ -377,6 +394,9 @@ extern "C" int trb_sweep_stage(const trb_sweep* sw, int stage, int it, int first
                              sw->stride_s, ea + 1 * B, ea + 5 * B, sw->tz, sw->tx, sw->coef,
                              sw->vlin, sw->active, stream);
     case TRB_STAGE_EXPAND_Z:  // P4: rz = [b2/a2 +] V_R coef
+      if (gemm)
+        return trb_lin_expand_gemm(sw->Vt, sw->R, sw->N, sw->ldn, B, sw->coef, sw->part,
+                                   sw->nslots * sw->ldn, stream);
       return trb_lin_expand(sw->Vt, sw->strideV, sw->R, sw->N, sw->ldn, B, sw->coef, sw->part,
                             sw->active, sw->gemv_impl, stream);
     case TRB_STAGE_X_UPDATE: {  // X: e7, posterior x, records, early stopping

@@ -168,6 +168,27 @@ def lin_expand(A, R, n, coef, B, impl=0, active=None, add=None, add_div=None, ou
     return out
 
 
+def lin_project_gemm(A, R, n, vec, B, out=None):
+    """Shared operator A: [1, R, ld] or [R, ld]; vec: [B, ldvec].  t[B, R] = vec @ A^T (DMMA GEMM)."""
+    t_ = torch()
+    if out is None:
+        out = t_.zeros((B, R), dtype=t_.float64, device=A.device)
+    check(_lib.load().trb_lin_project_gemm(ptr(A), R, n, A.shape[-1], B, ptr(vec), vec.shape[-1],
+                                           ptr(out), current_stream()))
+    return out
+
+
+def lin_expand_gemm(A, R, n, coef, B, out=None):
+    """out[B, ld] = coef[B, R] @ A[R, ld] (DMMA GEMM); columns >= n are not written."""
+    t_ = torch()
+    ld = A.shape[-1]
+    if out is None:
+        out = t_.zeros((B, ld), dtype=t_.float64, device=A.device)
+    check(_lib.load().trb_lin_expand_gemm(ptr(A), R, n, ld, B, ptr(coef), ptr(out), out.shape[-1],
+                                          current_stream()))
+    return out
+
+
 def lin_rescale(direction, B, R, Nz, Nx, rank, s, s2, az, ax, tz, tx, active=None,
                 null_space=None, want_coef=True, want_v=True, coef=None, v=None):
     """Spectrum rescale; null_space defaults to R < Nz (pass it explicitly when R
