@@ -251,7 +251,21 @@ typedef struct {
   double* snap_edge_a; double* snap_b1; double* snap_b3; double* snap_b5; double* snap_b7;
   double* snap_rx; double* snap_rz; double* snap_vx; double* snap_vz; double* snap_tx;
   /* rank of the whole thin SVD when R is only this GPU's row shard (0: = R) */
-  int32_t R_total; int32_t _pad;
+  int32_t R_total;
+  /* Operator passes per iteration, used by trb_sweep_run:
+   *  0  general: 4 passes, 16 R (N+M) bytes per instance-iteration, any likelihood;
+   *  1  Gaussian likelihood, 3 passes, 8 R (2N+M) bytes: its message is the constant
+   *     (1/var, y/var) (gaussian_likelihood.py:68-71), so with constant damping d5
+   *     b5' = d5 b5 + (1-d5) y/var and U_R^T b5' = d5 tx + (1-d5) ty/var exactly:
+   *     the pass U_R^T b6 becomes an R-vector recurrence on the cached ty = U_R^T y;
+   *  2  as 1, and the z branch (U_R coef -> e3, posterior of z), which feeds nothing
+   *     back when the likelihood message is constant, is evaluated only in the LAST
+   *     iteration of each trb_sweep_run call: 2 passes, 16 R N bytes.  Needs damp3 = 0
+   *     and no early stopping; the records of v_z stay exact, rec_tol covers x only.
+   * 1 and 2 need lik.kind = TRB_GAUSSIAN_LIKELIHOOD, b6_init = NULL and `ty` filled by
+   * trb_sweep_stage(TRB_STAGE_PROJECT_Y). */
+  int32_t schedule;
+  double* ty;  /* [B, R], U_R^T y (schedules 1, 2); else may be NULL */
 } trb_sweep;
 
 /* Stages of one iteration, in order (trb_sweep_run loops over them).  Back ends
@@ -268,7 +282,10 @@ typedef enum {
   TRB_STAGE_RESCALE_BWD = 7,    /* S2 */
   TRB_STAGE_EXPAND_Z = 8,       /* P4 */
   TRB_STAGE_X_UPDATE = 9,       /* X  */
-  TRB_STAGE_SNAPSHOT = 10
+  TRB_STAGE_SNAPSHOT = 10,
+  TRB_STAGE_Z_UPDATE_LIGHT = 11, /* schedule 2: scalar part of Z and e5 only */
+  TRB_STAGE_TX_RECUR = 12,       /* schedules 1, 2: tx = d5 tx + (1-d5) ty/var replaces P3 */
+  TRB_STAGE_PROJECT_Y = 13       /* ty = U_R^T y, once per model */
 } trb_stage;
 
 /* pre_reduced = 1: `part` holds the complete expansion result in slot 0

@@ -52,21 +52,28 @@ class _SeqInit:
         return self.vals[edge][0 if key == "a" else 1]
 
 
-@pytest.mark.parametrize("impl", [1, 2])
+@pytest.mark.parametrize("impl,schedule", [(1, "general"), (2, "general"), (2, "auto")])
 @pytest.mark.parametrize("idx", range(9))
-def test_sweep_matches_reference(sw, idx, impl):
+def test_sweep_matches_reference(sw, idx, impl, schedule):
+    """schedule "general" = 4 operator passes per iteration; "auto" picks the exact
+    3-pass (damped) / 2-pass (undamped) schedules when the likelihood is Gaussian."""
     from tramp_b200.algos import ExpectationPropagation, TrackErrors, TrackEvolution, JoinCallback
     cfg = _configs(sw)[idx]
     name = cfg["name"]
     model = _build(cfg, sw, name)
     ep = ExpectationPropagation(model)
     ep.gemv_impl = impl
+    ep.schedule = schedule
     track = TrackErrors({"x": sw[name + "_x"]})
     evo = TrackEvolution()
     init = _SeqInit(sw, name) if cfg.get("init") == "noisy" else None
     ep.iterate(max_iter=cfg["n_iter"], callback=JoinCallback([track, evo]), initializer=init,
                damping=cfg["damping"])
     assert ep.n_iter == cfg["n_iter"]
+    if schedule == "general":
+        assert ep.last_schedule == 0
+    elif cfg["lik"]["kind"] == "gaussian" and cfg.get("init") != "noisy":
+        assert ep.last_schedule == (1 if cfg["damping"] else 2)
     mse = np.array([e["mse"] for e in track.errors])
     df = evo.get_dataframe()
     x, W = sw[name + "_x"], sw[name + "_W"]

@@ -48,7 +48,8 @@ class TrbSweep(C.Structure):
         ("snap_b5", C.c_void_p), ("snap_b7", C.c_void_p), ("snap_rx", C.c_void_p),
         ("snap_rz", C.c_void_p), ("snap_vx", C.c_void_p), ("snap_vz", C.c_void_p),
         ("snap_tx", C.c_void_p),
-        ("R_total", C.c_int32), ("_pad", C.c_int32),
+        ("R_total", C.c_int32), ("schedule", C.c_int32),
+        ("ty", C.c_void_p),
     ]
 
 
@@ -58,7 +59,7 @@ GAUSSIAN_LIKELIHOOD, SGN_LIKELIHOOD, ABS_LIKELIHOOD = 3, 4, 5
 
 (STAGE_PRIOR, STAGE_PROJECT_Z, STAGE_PROJECT_X_INIT, STAGE_RESCALE_FWD, STAGE_EXPAND_X,
  STAGE_Z_UPDATE, STAGE_PROJECT_X, STAGE_RESCALE_BWD, STAGE_EXPAND_Z, STAGE_X_UPDATE,
- STAGE_SNAPSHOT) = range(11)
+ STAGE_SNAPSHOT, STAGE_Z_UPDATE_LIGHT, STAGE_TX_RECUR, STAGE_PROJECT_Y) = range(14)
 
 FLAG_NAN_A, FLAG_NAN_B, FLAG_NEG_A, FLAG_CONVERGED, FLAG_DIVERGED, FLAG_RESTORED = 1, 2, 4, 8, 16, 32
 

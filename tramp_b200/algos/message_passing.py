@@ -60,6 +60,11 @@ class MessagePassing():
         # all-reduce), "cublas" (torch.matmul, kept only as the library baseline the
         # DMMA kernel is measured against); None = pick
         self.linear_backend = None
+        # operator passes per iteration: "general" (4, any likelihood), "gauss3" /
+        # "gauss2" (3 / 2 passes, exact for a Gaussian likelihood, see
+        # include/tramp_b200.h trb_sweep.schedule), "auto" = the cheapest one the
+        # model, the damping and the callback allow
+        self.schedule = "auto"
         self._state = None
         self._has_messages = False
         self._compile_chain()
@@ -220,7 +225,7 @@ class MessagePassing():
                 raise ValueError(f"no factor->variable edge into {id!r} with direction {direction!r}")
             self.damp[into[(id, direction)]] = float(damp or 0.0)
 
-    def _descriptor(self, rec=None, max_records=0, early=None):
+    def _descriptor(self, rec=None, max_records=0, early=None, synchronous=False):
         st = self._ensure_state()
         lin = self.linear
         p = _lib.ptr
@@ -254,9 +259,42 @@ class MessagePassing():
             sw.es_tol, sw.es_max_increase, sw.es_wait_increase, sw.es_vars = -1.0, 0.0, 0, 3
         sw.gemv_impl = 3 if self.backend == "gemm" else (self.gemv_impl or 2)
         sw.R_total = getattr(lin, "R_total", 0) or 0
+        sw.schedule = self.last_schedule = self._pick_schedule(early, synchronous)
+        if sw.schedule:
+            if "ty" not in st:     # ty = U_R^T y, once per model (y is fixed)
+                st["ty"] = ops.torch().zeros_like(st["tx"])
+                sw.ty = p(st["ty"])
+                _lib.check(_lib.load().trb_sweep_stage(C.byref(sw), _lib.STAGE_PROJECT_Y, 0, 0, 0,
+                                                       _lib.current_stream()))
+            sw.ty = p(st["ty"])
+            if sw.schedule == 2:
+                sw.es_vars = 1     # the recorded tolerance covers x only
         for k in ("edge_a", "b1", "b3", "b5", "b7", "rx", "rz", "vx", "vz", "tx"):
             setattr(sw, "snap_" + k, p(st["snap_" + k]))
         return sw
+
+    def _pick_schedule(self, early, synchronous=False):
+        """0 general / 1 gauss3 / 2 gauss2 (trb_sweep.schedule)."""
+        from ..likelihoods import GaussianLikelihood
+        want = self.schedule
+        if want not in ("auto", "general", "gauss3", "gauss2"):
+            raise ValueError(f"unknown schedule {want!r}")
+        st = self._state
+        ok3 = (type(self.lik) is GaussianLikelihood and self.backend in ("gemv", "gemm")
+               and st.get("b6_init") is None)
+        ok2 = ok3 and self.damp["e3"] == 0.0 and early is None and not synchronous
+        if want == "general":
+            return 0
+        if want == "gauss3":
+            if not ok3:
+                raise ValueError("schedule 'gauss3' needs a Gaussian likelihood and e6 initialised like e5")
+            return 1
+        if want == "gauss2":
+            if not ok2:
+                raise ValueError("schedule 'gauss2' needs a Gaussian likelihood, no damping of the "
+                                 "linear->z edge, no early stopping and a replayable callback")
+            return 2
+        return 2 if ok2 else (1 if ok3 else 0)
 
     def _run(self, sw, it0, n_iter, fresh):
         """Enqueue n_iter iterations.  fresh: the messages were just initialised."""
@@ -413,7 +451,7 @@ class MessagePassing():
         (which may read any state through get_variables_data)."""
         st = self._state
         st["x_true"] = None
-        sw = self._descriptor()
+        sw = self._descriptor(synchronous=True)
         for i in range(max_iter):
             self._run(sw, i, 1, fresh and i == 0)
             self._raise_on_nan(st["flags"].cpu().numpy())

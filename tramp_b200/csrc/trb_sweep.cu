@@ -40,8 +40,11 @@ __device__ __forceinline__ int slots_of(int b, int R, int B, int G) {
 constexpr int kUnroll = 4;  // elements per thread whose loads are issued together
 
 // stats[b*4 + {0,1}] = sum (r_new - r_old)^2, sum r_new^2 for z
+// light (schedule 2): only the scalars of e3 and the constant Gaussian-likelihood
+// message e5 are updated; e3's vector, the posterior mean of z and its tolerance
+// statistics wait for the last iteration of the run.
 __global__ void __launch_bounds__(kUpThreads)
-k_z_update(trb_sweep sw, int G, int first, double* __restrict__ stats) {
+k_z_update(trb_sweep sw, int G, int first, int light, double* __restrict__ stats) {
   __shared__ double sh[33 * 2];
   __shared__ int sh_flag;
   const int b = blockIdx.x;
@@ -66,7 +69,7 @@ k_z_update(trb_sweep sw, int G, int first, double* __restrict__ stats) {
   int flag = 0;
   double vsum = 0.0;
   // pass 1: e3 (= e4) and the likelihood moments at (a3, b3)
-  for (int base = threadIdx.x; base < M; base += step) {
+  for (int base = threadIdx.x; base < (light ? 0 : M); base += step) {
     double rx[kUnroll], b6v[kUnroll], b3o[kUnroll], yv[kUnroll];
 #pragma unroll
     for (int u = 0; u < kUnroll; ++u) {
@@ -127,6 +130,7 @@ k_z_update(trb_sweep sw, int G, int first, double* __restrict__ stats) {
         if (b5n != b5n) flag |= TRB_FLAG_NAN_B;
         const double b5v = damp(sw.damp5, b5o[u], b5n);
         b5[i] = b5v;
+        if (light) continue;
         const double rnew = (b3v[u] + b5v) / a_hat;  // base.py:152-161
         rz[i] = rnew;
         red[0] += (rnew - ro[u]) * (rnew - ro[u]);
@@ -144,8 +148,10 @@ k_z_update(trb_sweep sw, int G, int first, double* __restrict__ stats) {
     ea[4 * B + b] = a5;
     ea[5 * B + b] = a5;  // e6 = e5 (sub_variables.py:27-31)
     sw.vz[b] = 1. / a_hat;
-    stats[b * 4 + 0] = red[0];
-    stats[b * 4 + 1] = red[1];
+    if (!light) {
+      stats[b * 4 + 0] = red[0];
+      stats[b * 4 + 1] = red[1];
+    }
     if (all) atomicOr(&sw.flags[b], all);
   }
 }
@@ -286,6 +292,18 @@ k_snapshot(trb_sweep sw) {
   if (restore && threadIdx.x == 0) atomicOr(&sw.flags[b], TRB_FLAG_RESTORED);
 }
 
+// Schedules 1, 2: U_R^T b5' for the Gaussian-likelihood message b5' = d5 b5 + (1-d5) y/var
+// (gaussian_likelihood.py:68-71, message_passing.py:119-127), from tx = U_R^T b5.
+__global__ void __launch_bounds__(256)
+k_tx_recur(trb_sweep sw) {
+  const int b = blockIdx.y;
+  if (sw.active && !sw.active[b]) return;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= sw.R) return;
+  const size_t o = (size_t)b * sw.R + i;
+  sw.tx[o] = damp(sw.damp5, sw.tx[o], sw.lik.p0 * sw.ty[o]);
+}
+
 }  // namespace
 
 #define TRB_TRY(expr)      \
@@ -325,7 +343,7 @@ extern "C" int trb_sweep_stage(const trb_sweep* sw, int stage, int it, int first
   double* ea = sw->edge_a;
   const bool needs_ops = (stage == TRB_STAGE_PROJECT_Z || stage == TRB_STAGE_PROJECT_X_INIT ||
                           stage == TRB_STAGE_EXPAND_X || stage == TRB_STAGE_PROJECT_X ||
-                          stage == TRB_STAGE_EXPAND_Z);
+                          stage == TRB_STAGE_EXPAND_Z || stage == TRB_STAGE_PROJECT_Y);
   TRB_CHECK_ARG(!needs_ops || (sw->Vt && sw->Ut), "null operator");
   const bool needs_s = (stage == TRB_STAGE_RESCALE_FWD || stage == TRB_STAGE_RESCALE_BWD);
   TRB_CHECK_ARG(!needs_s || (sw->s && sw->s2), "null spectrum");
@@ -338,7 +356,8 @@ extern "C" int trb_sweep_stage(const trb_sweep* sw, int stage, int it, int first
   const bool gemm = shared_ops && (sw->gemv_impl == 3 || (sw->gemv_impl == 0 && B >= 16));
   if (gemm) pre_reduced = 1;
   int G = 0;
-  if (stage == TRB_STAGE_Z_UPDATE || stage == TRB_STAGE_X_UPDATE) {
+  if (stage == TRB_STAGE_Z_UPDATE || stage == TRB_STAGE_Z_UPDATE_LIGHT ||
+      stage == TRB_STAGE_X_UPDATE) {
     if (pre_reduced) {
       G = 0;  // ns = 1
     } else {
@@ -377,11 +396,31 @@ extern "C" int trb_sweep_stage(const trb_sweep* sw, int stage, int it, int first
                                    sw->nslots * sw->ldm, stream);
       return trb_lin_expand(sw->Ut, sw->strideU, sw->R, sw->M, sw->ldm, B, sw->coef, sw->part,
                             sw->active, sw->gemv_impl, stream);
-    case TRB_STAGE_Z_UPDATE: {  // Z: e3, likelihood e5, posterior z
+    case TRB_STAGE_Z_UPDATE:          // Z: e3, likelihood e5, posterior z
+    case TRB_STAGE_Z_UPDATE_LIGHT: {  // schedule 2: scalars and e5 only
+      const int light = stage == TRB_STAGE_Z_UPDATE_LIGHT;
+      TRB_CHECK_ARG(!light || sw->lik.kind == TRB_GAUSSIAN_LIKELIHOOD,
+                    "the light z update needs a Gaussian likelihood");
       trb_launch_scope scope_(0, st);
-      k_z_update<<<B, kUpThreads, 0, st>>>(*sw, G, first, sw->stats);
+      k_z_update<<<B, kUpThreads, 0, st>>>(*sw, G, first, light, sw->stats);
       TRB_CHECK_LAUNCH();
       return TRB_OK;
+    }
+    case TRB_STAGE_TX_RECUR: {
+      TRB_CHECK_ARG(sw->ty && sw->lik.kind == TRB_GAUSSIAN_LIKELIHOOD,
+                    "the tx recurrence needs ty and a Gaussian likelihood");
+      trb_launch_scope scope_(0, st);
+      k_tx_recur<<<dim3((sw->R + 255) / 256, B), 256, 0, st>>>(*sw);
+      TRB_CHECK_LAUNCH();
+      return TRB_OK;
+    }
+    case TRB_STAGE_PROJECT_Y: {  // ty = U_R^T y
+      TRB_CHECK_ARG(sw->ty, "null ty");
+      if (gemm)
+        return trb_lin_project_gemm(sw->Ut, sw->R, sw->M, sw->ldm, B, sw->y, sw->ldm, sw->ty,
+                                    stream);
+      return trb_lin_project(sw->Ut, sw->strideU, sw->R, sw->M, sw->ldm, B, sw->y, sw->ldm, sw->ty,
+                             nullptr, sw->gemv_impl, stream);
     }
     case TRB_STAGE_PROJECT_X:  // P3: tx = U_R^T b6 (new)
       if (gemm)
@@ -421,9 +460,18 @@ extern "C" int trb_sweep_run(const trb_sweep* sw, int it0, int n_iter, int fresh
   if (rc) return rc;
   TRB_CHECK_ARG(it0 >= 0 && n_iter >= 0, "bad iteration range");
   TRB_CHECK_ARG(fresh >= 0 && fresh <= 2, "fresh must be 0, 1 or 2");
+  const int schedule = sw->schedule;
+  TRB_CHECK_ARG(schedule >= 0 && schedule <= 2, "schedule must be 0, 1 or 2");
+  if (schedule) {
+    TRB_CHECK_ARG(sw->lik.kind == TRB_GAUSSIAN_LIKELIHOOD, "schedules 1, 2 need a Gaussian likelihood");
+    TRB_CHECK_ARG(sw->ty && !sw->b6_init, "schedules 1, 2 need ty and e6 initialised like e5");
+    TRB_CHECK_ARG(schedule == 1 || (sw->damp3 == 0.0 && sw->es_tol < 0),
+                  "schedule 2 needs damp3 = 0 and no early stopping");
+  }
   for (int k = 0; k < n_iter; ++k) {
     const int it = it0 + k;
     const int first = (fresh && k == 0) ? 1 : 0;
+    const bool light = schedule == 2 && k + 1 < n_iter;  // z branch deferred to the last iteration
     TRB_TRY(trb_sweep_stage(sw, TRB_STAGE_PRIOR, it, first, 0, stream));
     TRB_TRY(trb_sweep_stage(sw, TRB_STAGE_PROJECT_Z, it, first, 0, stream));
     if (first) {
@@ -437,9 +485,11 @@ extern "C" int trb_sweep_run(const trb_sweep* sw, int it0, int n_iter, int fresh
       }
     }
     TRB_TRY(trb_sweep_stage(sw, TRB_STAGE_RESCALE_FWD, it, first, 0, stream));
-    TRB_TRY(trb_sweep_stage(sw, TRB_STAGE_EXPAND_X, it, first, 0, stream));
-    TRB_TRY(trb_sweep_stage(sw, TRB_STAGE_Z_UPDATE, it, first, 0, stream));
-    TRB_TRY(trb_sweep_stage(sw, TRB_STAGE_PROJECT_X, it, first, 0, stream));
+    if (!light) TRB_TRY(trb_sweep_stage(sw, TRB_STAGE_EXPAND_X, it, first, 0, stream));
+    TRB_TRY(trb_sweep_stage(sw, light ? TRB_STAGE_Z_UPDATE_LIGHT : TRB_STAGE_Z_UPDATE, it, first, 0,
+                            stream));
+    TRB_TRY(trb_sweep_stage(sw, schedule ? TRB_STAGE_TX_RECUR : TRB_STAGE_PROJECT_X, it, first, 0,
+                            stream));
     TRB_TRY(trb_sweep_stage(sw, TRB_STAGE_RESCALE_BWD, it, first, 0, stream));
     TRB_TRY(trb_sweep_stage(sw, TRB_STAGE_EXPAND_Z, it, first, 0, stream));
     TRB_TRY(trb_sweep_stage(sw, TRB_STAGE_X_UPDATE, it, first, 0, stream));
