@@ -297,7 +297,55 @@ def run_diverging(out):
     _dump_edges(ep, out, name)
 
 
-def _dump_edges(ep, out, name):
+# --------------------------------------------------------------------------
+# D. adaptive damping (message_passing.py:151-185), update_dA (:129-149),
+#    TrackObjective (callbacks.py:63-85)
+# --------------------------------------------------------------------------
+ADAPTIVE = [
+    dict(name="ad_gb_sgn", N=60, M=80, prior=dict(kind="gauss_bernoulli", rho=0.3), lik=dict(kind="sgn"),
+         damping="adaptive", update_dA=False, n_iter=8, seed=61),
+    dict(name="ad_gb_gauss", N=64, M=32, prior=dict(kind="gauss_bernoulli", rho=0.1),
+         lik=dict(kind="gaussian", var=1e-2), damping="adaptive", update_dA=False, n_iter=8, seed=62),
+    dict(name="dA_gb_sgn", N=60, M=80, prior=dict(kind="gauss_bernoulli", rho=0.3), lik=dict(kind="sgn"),
+         damping=0.2, update_dA=True, n_iter=8, seed=63),
+    dict(name="dA_gauss_sgn", N=48, M=96, prior=dict(kind="gaussian"), lik=dict(kind="sgn"),
+         damping=None, update_dA=True, n_iter=6, seed=64),
+]
+
+
+class _Objective:
+    def __init__(self, x_true):
+        self.x_true, self.mse, self.vx, self.vz, self.A = x_true, [], [], [], []
+
+    def __call__(self, algo, i, max_iter):
+        d = algo.get_variables_data()
+        self.mse.append(np.mean((d["x"]["r"] - self.x_true)**2))
+        self.vx.append(float(d["x"]["v"]))
+        self.vz.append(float(d["z"]["v"]))
+        algo.update_objective()
+        self.A.append(float(algo.A_model))
+
+
+def run_adaptive(cfg, out):
+    name, N, M = cfg["name"], cfg["N"], cfg["M"]
+    np.random.seed(cfg["seed"])
+    W = np.random.randn(M, N) / np.sqrt(N)
+    x = _sample_prior(cfg["prior"], N).astype(float)
+    y = _observe(cfg["lik"]["kind"], W @ x, cfg["lik"].get("var", 1), np.random.standard_normal(M))
+    model = (_prior_from(dict(cfg["prior"], size=N)) @ V("x") @ LinearChannel(W) @ V("z")
+             @ _lik_from(cfg["lik"], y)).to_model()
+    ep = ExpectationPropagation(model)
+    cb = _Objective(x)
+    ep.iterate(max_iter=cfg["n_iter"], callback=cb, damping=cfg["damping"], update_dA=cfg["update_dA"])
+    out[name + "_W"], out[name + "_y"], out[name + "_x"] = W, y, x
+    out[name + "_mse"], out[name + "_vx"], out[name + "_vz"] = np.array(cb.mse), np.array(cb.vx), np.array(cb.vz)
+    out[name + "_A_model"] = np.array(cb.A)
+    d = ep.get_variables_data()
+    out[name + "_rx"], out[name + "_rz"] = d["x"]["r"], d["z"]["r"]
+    _dump_edges(ep, out, name, extra=("dA", "beta", "n_iter"))
+
+
+def _dump_edges(ep, out, name, extra=()):
     """Store the 8 edges under the SURVEY 3.3 names e1..e8."""
     for s, t, data in ep.message_dag.edges(data=True):
         var = s if isinstance(s, Variable) else t
@@ -317,6 +365,9 @@ def _dump_edges(ep, out, name):
         out[f"{name}_{e}_a"] = np.float64(data["a"])
         out[f"{name}_{e}_b"] = np.asarray(data["b"], dtype=float) * np.ones(
             ep.model_dag.node[var]["shape"])
+        for key in extra:
+            val = data.get(key)
+            out[f"{name}_{e}_{key}"] = np.float64(np.nan if val is None else val)
 
 
 def main():
@@ -337,7 +388,13 @@ def main():
     import json
     sw["configs"] = np.array(json.dumps(SWEEPS))
     np.savez_compressed(os.path.join(HERE, "sweeps.npz"), **sw)
-    for f in ("elementwise.npz", "linear.npz", "sweeps.npz"):
+    ad = {}
+    for cfg in ADAPTIVE:
+        with np.errstate(all="ignore"):
+            run_adaptive(cfg, ad)
+    ad["configs"] = np.array(json.dumps(ADAPTIVE))
+    np.savez_compressed(os.path.join(HERE, "adaptive.npz"), **ad)
+    for f in ("elementwise.npz", "linear.npz", "sweeps.npz", "adaptive.npz"):
         print(f, os.path.getsize(os.path.join(HERE, f)) // 1024, "KiB")
 
 

@@ -419,3 +419,111 @@ def test_scenario_and_glm_generative():
     df = scenario.ep_convergence(metrics=["mse"], max_iter=30, damping=0.1)
     assert list(df.columns) == ["id", "iter", "mse", "v"] and len(df) == 30
     assert_allclose(scenario.compute_score(scenario.x_pred)["x"]["mse"], df.mse.values[-1], rtol=1e-9)
+
+
+# ---------------------------------------------------------------------------
+# host-driven factor-by-factor schedule: damping="adaptive", update_dA, TrackObjective
+# ---------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def ad(golden_dir):
+    return np.load(os.path.join(golden_dir, "adaptive.npz"))
+
+
+@pytest.mark.parametrize("idx", range(4))
+def test_adaptive_damping_and_dA_match_reference(ad, idx):
+    """reference message_passing.py:129-185 run through the unmodified reference
+    (tests/golden/make_golden.py section D): trajectories, per-iteration A_model
+    (update_objective), final messages with their dA / beta / n_iter."""
+    from tramp_b200.algos import ExpectationPropagation, TrackObjective, TrackMessages, JoinCallback
+    cfg = json.loads(str(ad["configs"]))[idx]
+    name = cfg["name"]
+    ep = ExpectationPropagation(_build(cfg, ad, name))
+    x = ad[name + "_x"]
+    rows = []
+
+    def record(algo, i, max_iter):
+        d = algo.get_variables_data()
+        rows.append((np.mean((d["x"]["r"] - x)**2), d["x"]["v"], d["z"]["v"]))
+
+    obj, msgs = TrackObjective(), TrackMessages(keys=["a", "n_iter", "direction", "dA", "beta"])
+    ep.iterate(max_iter=cfg["n_iter"], callback=JoinCallback([record, obj, msgs]),
+               damping=cfg["damping"], update_dA=cfg["update_dA"])
+    assert ep.n_iter == cfg["n_iter"]
+    mse, vx, vz = (np.array(c) for c in zip(*rows))
+    assert_allclose(mse, ad[name + "_mse"], rtol=1e-9)
+    assert_allclose(vx, ad[name + "_vx"], rtol=1e-9)
+    assert_allclose(vz, ad[name + "_vz"], rtol=1e-9)
+    edge_df, node_df, model_df = obj.get_dataframe()
+    A_ref = ad[name + "_A_model"]
+    # A_model = sum(nodes) - sum(edges) of terms ~1e2..1e3: tolerance relative to their size
+    assert_allclose(model_df.A.values, A_ref, rtol=1e-9, atol=1e-9 * 1e3)
+    assert len(node_df) == 5 * cfg["n_iter"] and len(edge_df) == 8 * cfg["n_iter"]
+    d = ep.get_variables_data()
+    for vid, key in (("x", "_rx"), ("z", "_rz")):
+        ref = ad[name + key]
+        assert_allclose(d[vid]["r"], ref, rtol=1e-9, atol=1e-9 * np.abs(ref).max())
+    last = {}
+    for rec in msgs.get_dataframe().to_dict("records")[-8:]:
+        last[(rec["x_id"], rec["f_id"], rec["direction"])] = rec
+    for k in range(1, 9):
+        a, b = ep._edge(f"e{k}")
+        assert_allclose(a, ad[f"{name}_e{k}_a"], rtol=1e-9)
+        ref_b = ad[f"{name}_e{k}_b"]
+        assert_allclose(b, ref_b, rtol=1e-9, atol=1e-9 * max(np.abs(ref_b).max(), 1e-300))
+        data = ep._host.edges[f"e{k}"]
+        assert data["n_iter"] == int(ad[f"{name}_e{k}_n_iter"])
+        if cfg["damping"] == "adaptive":
+            assert data["beta"] == float(ad[f"{name}_e{k}_beta"])
+        ref_dA = float(ad[f"{name}_e{k}_dA"])
+        # dA is a difference of objectives of size ~|A_model|
+        assert abs(data["dA"] - ref_dA) <= 1e-9 * max(1.0, np.abs(A_ref).max())
+    assert len(last) == 8
+
+
+def test_host_path_then_device_warm_start(ad):
+    """update_dA (host path) for a few iterations, then a plain warm-started
+    device sweep continues from the same messages: equals one uninterrupted run."""
+    from tramp_b200.algos import ExpectationPropagation, PassCallback
+    cfg = json.loads(str(ad["configs"]))[2]
+    name = cfg["name"]
+    ep = ExpectationPropagation(_build(cfg, ad, name))
+    ep.iterate(max_iter=3, callback=PassCallback(), damping=0.2, update_dA=True)
+    ep.iterate(max_iter=5, callback=PassCallback(), damping=0.2, warm_start=True)
+    assert ep.n_iter == 8
+    d = ep.get_variables_data()
+    ref = ad[name + "_rx"]
+    assert_allclose(d["x"]["r"], ref, rtol=1e-9, atol=1e-9 * np.abs(ref).max())
+    assert_allclose(d["x"]["v"], ad[name + "_vx"][-1], rtol=1e-9)
+
+
+def test_adaptive_damping_rejects_batches():
+    from tramp_b200.priors import GaussBernoulliPrior
+    from tramp_b200.likelihoods import GaussianLikelihood
+    from tramp_b200.channels import LinearChannel
+    from tramp_b200.variables import SISOVariable as V
+    from tramp_b200.algos import ExpectationPropagation
+    rng = np.random.RandomState(0)
+    W, y = rng.randn(3, 8, 16), rng.randn(3, 8)
+    model = (GaussBernoulliPrior(size=16, batch=3) @ V("x") @ LinearChannel(W) @ V("z")
+             @ GaussianLikelihood(y=y, var=0.1)).to_model()
+    with pytest.raises(NotImplementedError):
+        ExpectationPropagation(model).iterate(max_iter=2, damping="adaptive")
+
+
+def test_track_overlaps_and_objective_on_device_path(sw):
+    """TrackOverlaps / TrackObjective are ordinary (synchronous) callbacks on the
+    device path; A_model equals log_evidence()."""
+    from tramp_b200.algos import ExpectationPropagation, TrackOverlaps, TrackObjective, JoinCallback
+    cfg = _configs(sw)[0]
+    name = cfg["name"]
+    ep = ExpectationPropagation(_build(cfg, sw, name))
+    x = sw[name + "_x"]
+    ov, obj = TrackOverlaps({"x": x}, ids=["x"]), TrackObjective()
+    ep.iterate(max_iter=cfg["n_iter"], callback=JoinCallback([ov, obj]), damping=cfg["damping"])
+    df = ov.get_dataframe()
+    r = ep.get_variables_data()["x"]["r"]
+    assert_allclose(df.m.values[-1], r @ x / x.size, rtol=1e-12)
+    assert_allclose(df.Q.values[-1], x @ x / x.size, rtol=1e-12)
+    _, node_df, model_df = obj.get_dataframe()
+    scale = np.abs(node_df.A.values[-5:].astype(float)).sum()
+    assert abs(model_df.A.values[-1] - sw[name + "_logZ"]) <= 1e-9 * scale

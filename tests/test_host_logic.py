@@ -159,8 +159,10 @@ def test_damping_configuration_and_chain_validation():
     assert ep.damp == dict(e1=0.1, e3=0.0, e5=0.9, e7=0.0)
     with pytest.raises(ValueError, match="damping must be"):
         ep.configure_damping(1)
-    with pytest.raises(NotImplementedError):
-        ep.configure_damping("adaptive")
+    ep.configure_damping("adaptive")               # message_passing.py:84-88: host-driven schedule
+    assert ep.damping and ep.adaptive_damping
+    ep.configure_damping(0.5)
+    assert not ep.adaptive_damping
     with pytest.raises(ValueError):
         ep.iterate(max_iter=1, warm_start=True)        # message dag was never initialized
     bad = (GaussBernoulliPrior(size=9) @ V("x") @ LinearChannel(W) @ V("z")

@@ -4,6 +4,7 @@ from .message_passing import MessagePassing
 from .callbacks import (
     Callback, PassCallback, JoinCallback, LogProgress, TrackEvolution,
     TrackEstimate, TrackErrors, EarlyStoppingEP, EarlyStopping,
+    TrackMessages, TrackObjective, TrackOverlaps,
 )
 from .initial_conditions import ConstantInit, NoisyInit, CustomInit
 from .metrics import METRICS, mean_squared_error, sign_symmetric_mse, overlap

@@ -76,6 +76,73 @@ class LogProgress(Callback):
                 logger.info(f"id={variable_id} v={np.mean(data['v']):.3f}")
 
 
+class TrackMessages(Callback):
+    """reference callbacks.py:49-60."""
+
+    def __init__(self, keys=["a", "n_iter", "direction"]):
+        self.keys = keys
+        self.records = []
+
+    def __call__(self, algo, i, max_iter):
+        if (i == 0):
+            self.records = []
+        self.records += algo.get_edges_data(self.keys)
+
+    def get_dataframe(self):
+        return pd.DataFrame(self.records)
+
+
+class TrackObjective(Callback):
+    """reference callbacks.py:63-85."""
+
+    def __init__(self):
+        self.edge_records = []
+        self.node_records = []
+        self.model_records = []
+
+    def __call__(self, algo, i, max_iter):
+        if (i == 0):
+            self.records = []
+        algo.update_objective()
+        self.model_records.append(dict(A=algo.A_model, n_iter=algo.n_iter))
+        self.edge_records += algo.get_edges_data(["A", "n_iter", "direction"])
+        self.node_records += algo.get_nodes_data(["A", "n_iter"])
+
+    def get_dataframe(self):
+        return (pd.DataFrame(self.edge_records), pd.DataFrame(self.node_records),
+                pd.DataFrame(self.model_records))
+
+
+class TrackOverlaps(Callback):
+    """reference callbacks.py:165-192: m = <r, x>/N, q = <r, r>/N, Q = <x, x>/N."""
+
+    def __init__(self, true_values, ids="all", every=1, verbose=False):
+        self.ids = ids
+        self.every = every
+        self.repr_init()
+        self.X_true = true_values
+        self.records = []
+        self.verbose = verbose
+
+    def __call__(self, algo, i, max_iter):
+        if (i == 0):
+            self.records = []
+        if (i % self.every == 0):
+            variables_data = algo.get_variables_data(self.ids)
+            for variable_id, data in variables_data.items():
+                x = np.asarray(self.X_true[variable_id])
+                r = np.asarray(data["r"])
+                n = x.shape[-1] if x.ndim > 1 else x.shape[0]
+                record = dict(id=variable_id, m=(r * x).sum(-1) / n, q=(r * r).sum(-1) / n,
+                              Q=(x * x).sum(-1) / n, iter=i)
+                self.records.append(record)
+                if self.verbose:
+                    print(record)
+
+    def get_dataframe(self):
+        return pd.DataFrame(self.records)
+
+
 def _squeeze(algo, row):
     """(B,) device record -> float for an un-batched model, array otherwise."""
     return float(row[0]) if not algo.batched else np.array(row)

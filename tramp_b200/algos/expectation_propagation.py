@@ -38,6 +38,12 @@ class ExpectationPropagation(MessagePassing):
         """reference message_passing.py:306-328: A_model = sum_nodes A - sum_fwd-edges A.
         Cold path: the factor log-partitions run on the device, the (tiny)
         variable terms on the host."""
+        if self._host is not None:      # un-aliased host messages (adaptive damping / update_dA)
+            self.A_model = self._host.update_objective()
+            ids = dict(prior=self.prior.id, x=self.x_id, lin=self.linear.id, z=self.z_id, lik=self.lik.id)
+            self.A_nodes = {ids[k]: v for k, v in self._host.node_A.items()}
+            self.A_edges = {n: self._host.edges[n]["A"] for n in ("e1", "e2", "e3", "e4")}
+            return
         E = {name: self._edge(name) for name in ("e1", "e2", "e3", "e4", "e5", "e6", "e7", "e8")}
         A = {}
         A[self.prior.id] = self.prior.compute_log_partition(*E["e8"])
@@ -50,6 +56,9 @@ class ExpectationPropagation(MessagePassing):
         pairs = [("e1", "e8"), ("e2", "e7"), ("e3", "e6"), ("e4", "e5")]
         self.A_edges = {f: _variable_log_partition(E[f][0] + E[b][0], E[f][1] + E[b][1])
                         for f, b in pairs}
+        self.A_edge_by_name = {}
+        for f, b in pairs:
+            self.A_edge_by_name[f] = self.A_edge_by_name[b] = self.A_edges[f]
         self.A_model = sum(A.values()) - sum(self.A_edges.values())
 
     def log_evidence(self, update=True):

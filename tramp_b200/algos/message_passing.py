@@ -67,6 +67,9 @@ class MessagePassing():
         self.schedule = "auto"
         self._state = None
         self._has_messages = False
+        self._host = None            # FactorSchedule while the host-driven path owns the messages
+        self.update_dA = False
+        self.adaptive_damping = False
         self._compile_chain()
 
     # ------------------------------------------------------------------ model
@@ -207,13 +210,16 @@ class MessagePassing():
         """reference message_passing.py:70-106: None | float | list of
         (variable.id, direction, damping) for the factor->variable edges."""
         self.damp = dict(e1=0.0, e3=0.0, e5=0.0, e7=0.0)
+        self.adaptive_damping = False
         if not damping:
             self.damping = False
             return
         self.damping = True
-        if damping == "adaptive":
-            raise NotImplementedError(
-                "damping='adaptive' (message_passing.py:151-185) is not on the device path yet")
+        if isinstance(damping, str) and damping == "adaptive":
+            # :151-185 -- needs the objective after every message: host-driven
+            # factor-by-factor schedule (algos/factor_schedule.py)
+            self.adaptive_damping = True
+            return
         if not (isinstance(damping, float) or isinstance(damping, list)):
             raise ValueError("damping must be 'adaptive', float or list")
         if isinstance(damping, float):
@@ -300,6 +306,8 @@ class MessagePassing():
         """Enqueue n_iter iterations.  fresh: the messages were just initialised."""
         st = self._state
         code = 0 if not fresh else (2 if st.get("b6_zero") else 1)
+        if getattr(self, "_tx_stale", False):
+            code, self._tx_stale = 1, False
         if self.backend in ("gemv", "gemm"):
             _lib.check(_lib.load().trb_sweep_run(C.byref(sw), it0, n_iter, code, _lib.current_stream()))
         else:
@@ -387,8 +395,8 @@ class MessagePassing():
         """reference message_passing.py:330-357."""
         initializer = initializer or ConstantInit(a=0, b=0)
         callback = callback or self.default_stopping
-        if update_dA:
-            raise NotImplementedError("update_dA is not on the device path yet")
+        self.update_dA = bool(update_dA)
+        host_prev = self._host
         if warm_start:
             if not self._has_messages:
                 raise ValueError("message dag was never initialized")
@@ -403,6 +411,13 @@ class MessagePassing():
         st["flags"].zero_()
         st["n_iter"].zero_()
         fresh = not warm_start
+        if self.adaptive_damping or self.update_dA:
+            self._iterate_host(max_iter, callback, host_prev if warm_start else None)
+            logger.info(f"terminated after n_iter={self.n_iter} iterations")
+            return
+        if warm_start and host_prev is not None:
+            self._leave_host_path(host_prev)
+        self._host = None
         if isinstance(callback, Callback) and callback.device_replayable(self):
             self._iterate_device(max_iter, callback, fresh)
         else:
@@ -461,17 +476,92 @@ class MessagePassing():
                 return
         self.n_iter_per_instance = np.full(self.B, self.n_iter)
 
+    # ------------------------------------------- host-driven factor-by-factor path
+    def _iterate_host(self, max_iter, callback, previous):
+        """damping="adaptive" / update_dA (reference :129-185): the reference's
+        node-by-node loop on the host, every factor evaluated by the CUDA kernels
+        through the factor API (algos/factor_schedule.py)."""
+        from .factor_schedule import FactorSchedule
+        if self.batched:
+            raise NotImplementedError("adaptive damping / update_dA run one instance at a time")
+        if getattr(self.linear, "group", None) is not None:
+            raise NotImplementedError("adaptive damping / update_dA on a row-sharded operator")
+        st = self._state
+        if previous is not None:
+            host = previous
+            for name in host.edges:      # a new iterate() may change the constant damping
+                host.edges[name]["damping"] = self.damp.get(name) or None
+        else:
+            edges = {}
+            src = {"e1": "b1", "e2": "b1", "e3": "b3", "e4": "b3", "e5": "b5", "e6": "b6_init",
+                   "e7": "b7", "e8": "b8_init"}
+            a_all = st["edge_a"][:, 0].cpu().numpy()
+            for name, role, direction, idx in EDGES:
+                t = st.get(src[name])
+                if t is None:
+                    t = st["b5" if name == "e6" else "b7"]
+                n = self.N if role == "x" else self.M
+                edges[name] = dict(a=float(a_all[idx]), b=t[0, :n].cpu().numpy().copy(),
+                                   direction=direction, n_iter=0,
+                                   damping=self.damp.get(name) or None)
+            host = FactorSchedule(self, edges)
+        self._host = host
+        for i in range(max_iter):
+            host.sweep()
+            self._host_to_device(host)
+            self.n_iter += 1
+            stop = callback(self, i, max_iter)
+            if stop:
+                return
+            host.old = host.copy_state()
+        self.n_iter_per_instance = np.full(self.B, self.n_iter)
+
+    def _host_to_device(self, host):
+        """Mirror the host messages and posteriors into the device state, so that
+        get_variables_data / snapshots / a later device-path warm start see them."""
+        st = self._state
+        t = ops.torch()
+        e = host.edges
+        st["edge_a"][:, 0] = t.as_tensor([e[n]["a"] for n, _, _, _ in EDGES], dtype=t.float64)
+        for buf, name, n in (("b1", "e1", self.N), ("b3", "e3", self.M), ("b5", "e5", self.M),
+                             ("b7", "e7", self.N)):
+            st[buf][0, :n] = ops.to_dev(e[name]["b"])
+        for role, n, rk, vk in (("x", self.N, "rx", "vx"), ("z", self.M, "rz", "vz")):
+            d = host.variables[role]
+            if d:
+                st[rk][0, :n] = ops.to_dev(np.asarray(d["r"], dtype=np.float64))
+                st[vk][0] = float(d["v"])
+
+    def _leave_host_path(self, host):
+        """Warm start of the device sweep from messages the host path produced: the
+        pass-through edges must again be copies of their sources (they always are
+        unless adaptive damping held one of them back)."""
+        e = host.edges
+        for cp, srcn in (("e2", "e1"), ("e4", "e3"), ("e6", "e5"), ("e8", "e7")):
+            if e[cp]["a"] != e[srcn]["a"] or not np.array_equal(e[cp]["b"], e[srcn]["b"]):
+                raise NotImplementedError(
+                    f"device-path warm start needs {cp} == {srcn}; adaptive damping left them different")
+        self._host_to_device(host)
+        st = self._state
+        st["b6_init"] = st["b8_init"] = None
+        st["b6_zero"] = False
+        self._tx_stale = True     # tx = U_R^T b6 is recomputed by the first device iteration
+
     # ------------------------------------------------------------ inspection
     def snapshot(self):
         st = self._ensure_state()
         keys = ("edge_a", "b1", "b3", "b5", "b7", "rx", "rz", "vx", "vz", "tx", "tz")
-        return MessageSnapshot({k: st[k].clone() for k in keys}, self.n_iter)
+        snap = MessageSnapshot({k: st[k].clone() for k in keys}, self.n_iter)
+        snap.host = self._host.copy_state() if self._host is not None else None
+        return snap
 
     def reset_message_dag(self, snapshot):
         """reference message_passing.py:234-239."""
         st = self._ensure_state()
         for k, v in snapshot.tensors.items():
             st[k].copy_(v)
+        if self._host is not None and getattr(snapshot, "host", None) is not None:
+            self._host.restore_state(snapshot.host)
 
     def _out(self, t, n=None):
         x = t.cpu().numpy()
@@ -502,6 +592,9 @@ class MessagePassing():
 
     def _edge(self, name):
         """(a, b) of one edge as host arrays."""
+        if self._host is not None:
+            d = self._host.edges[name]
+            return d["a"], d["b"]
         st = self._ensure_state()
         _, role, direction, idx = next(e for e in EDGES if e[0] == name)
         src = {"e1": "b1", "e2": "b1", "e3": "b3", "e4": "b3",
@@ -509,6 +602,22 @@ class MessagePassing():
         n = self.N if role == "x" else self.M
         a = st["edge_a"][idx].cpu().numpy()
         return (a if self.batched else float(a[0])), self._out(st[src], n)
+
+    def get_nodes_data(self, keys):
+        """reference message_passing.py:289-298 (after update_objective: key "A")."""
+        records = []
+        A = getattr(self, "A_nodes", {})
+        for node in self.forward_ordering:
+            is_var = isinstance(node, Variable)
+            full = dict(A=A.get(node.id))
+            if is_var:
+                full.update(self.get_variable_data(node.id))
+            record = dict(id=node.id, type="variable" if is_var else "factor")
+            for key in keys:
+                record[key] = full.get(key)
+            record["n_iter"] = self.n_iter
+            records.append(record)
+        return records
 
     def get_edges_data(self, keys):
         """reference message_passing.py:278-287."""
@@ -522,6 +631,10 @@ class MessagePassing():
             full = dict(a=a, b=b, direction=direction, n_iter=self.n_iter, tau=None,
                         shape=self._var_shape(role),
                         damping=(self.damp.get(into.get(name)) or None) if hasattr(self, "damp") else None)
+            if self._host is not None:       # per-edge n_iter, A, dA, beta of the host path
+                full.update({k: v for k, v in self._host.edges[name].items() if k not in ("a", "b")})
+            elif hasattr(self, "A_edge_by_name"):
+                full["A"] = self.A_edge_by_name.get(name)
             record = dict(x_id=x_id, f_id=factor_of[name].id)
             for key in keys:
                 record[key] = full.get(key)
