@@ -39,6 +39,10 @@ namespace trb {
 
 constexpr double kTwoPi = 6.283185307179586476925286766559;
 
+__device__ __forceinline__ uint32_t smem_u32_(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -90,6 +94,60 @@ __device__ __forceinline__ void block_sum_n(double (&v)[K], double* sh) {
   for (int k = 0; k < K; ++k) v[k] = sh[k * 33 + 32];
 }
 
+// ---- thread-block clusters: one instance may span C CTAs (grid = (C, B), cluster
+// = (C, 1, 1)); a kernel launched without the cluster attribute sees C = 1.
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t cluster_nctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n"
+               "barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// the double at the address of local shared variable `p` in CTA `rank` of the cluster (DSMEM)
+__device__ __forceinline__ double dsmem_ld(const double* p, uint32_t rank) {
+  uint32_t remote;
+  double v;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32_(p)), "r"(rank));
+  asm volatile("ld.shared::cluster.f64 %0, [%1];" : "=d"(v) : "r"(remote) : "memory");
+  return v;
+}
+__device__ __forceinline__ int dsmem_ld_int(const int* p, uint32_t rank) {
+  uint32_t remote;
+  int v;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32_(p)), "r"(rank));
+  asm volatile("ld.shared::cluster.s32 %0, [%1];" : "=r"(v) : "r"(remote) : "memory");
+  return v;
+}
+
+// Sums K values over all CTAs of the cluster (over the block when C = 1), in
+// CTA-rank order, so every CTA gets the same bits.  `sh` holds >= 33*K doubles.
+template <int K>
+__device__ __forceinline__ void cluster_sum_n(double (&v)[K], double* sh) {
+  block_sum_n<K>(v, sh);  // leaves the block totals in sh[k*33 + 32]
+  const uint32_t C = cluster_nctarank();
+  if (C == 1) return;
+  cluster_sync();
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    double t = 0.0;
+    for (uint32_t r = 0; r < C; ++r) t += dsmem_ld(&sh[k * 33 + 32], r);
+    v[k] = t;
+  }
+  cluster_sync();  // nobody reuses sh while a peer is still reading it
+}
+__device__ __forceinline__ double cluster_sum(double v, double* sh) {
+  double a[1] = {v};
+  cluster_sum_n<1>(a, sh);
+  return a[0];
+}
+
 __device__ __forceinline__ int block_or(int v, int* sh) {
   v = __reduce_or_sync(0xffffffffu, v);
   __syncthreads();
@@ -98,6 +156,17 @@ __device__ __forceinline__ int block_or(int v, int* sh) {
   if ((threadIdx.x & 31) == 0 && v) atomicOr(sh, v);
   __syncthreads();
   return *sh;
+}
+// OR over all CTAs of the cluster
+__device__ __forceinline__ int cluster_or(int v, int* sh) {
+  int all = block_or(v, sh);
+  const uint32_t C = cluster_nctarank();
+  if (C == 1) return all;
+  cluster_sync();
+  all = 0;
+  for (uint32_t r = 0; r < C; ++r) all |= dsmem_ld_int(sh, r);
+  cluster_sync();
+  return all;
 }
 
 // streaming 16-byte load that does not pollute L1 (operators are read once)
@@ -176,9 +245,38 @@ __host__ __device__ __forceinline__ int64_t part_owner(int64_t g, int64_t T, int
 
 }  // namespace trb
 
+// Number of CTAs (a thread-block cluster, <= 8 = the portable maximum) that share
+// one instance in the per-instance update kernels: 1 when the batch alone fills
+// the GPU, more for a few large instances (BASELINE config 5: B = 1, N = 65536).
+int trb_cluster_size(int B, int n);
+
+// kernel<<<(C, B), threads, 0, st>>> with cluster dimension (C, 1, 1)
+template <typename... KArgs, typename... Args>
+cudaError_t trb_launch_cluster(void (*kernel)(KArgs...), int C, int B, int threads, cudaStream_t st,
+                               Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(C, B, 1);
+  cfg.blockDim = dim3(threads, 1, 1);
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = C;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 // Launch geometry shared by trb_lin_expand and the kernels that reduce its slots.
 struct trb_expand_geom {
   int G;       // number of CTAs (workers) over the B*R row space
   int nslots;  // max number of workers whose range touches one instance
 };
 trb_expand_geom trb_expand_geometry(int B, int R);
+// part[b, 0, :] = sum of the slots of instance b (in place)
+int trb_reduce_slots_inplace(int B, int R, int n, int ld, double* part, void* stream);
+// the update kernels add up to this many slots themselves; beyond it (few instances
+// spread over many CTAs) the sweep reduces the slots first
+constexpr int kTrbDirectSlots = 4;

@@ -95,6 +95,15 @@ extern "C" size_t trb_sizeof_factor(void) { return sizeof(trb_factor); }
 extern "C" size_t trb_sizeof_sweep(void) { return sizeof(trb_sweep); }
 extern "C" int trb_device_sm_count(void) { return trb_sm_count_cached(); }
 
+int trb_cluster_size(int B, int n) {
+  int sm = trb_sm_count_cached();
+  if (sm <= 0) sm = 1;
+  int c = 1;
+  // double while the batch leaves SMs idle and every CTA keeps >= 2048 elements
+  while (c < 8 && (long long)B * c * 2 <= sm && n / (c * 2) >= 2048) c *= 2;
+  return c;
+}
+
 namespace {
 
 constexpr int kEwThreads = 512;
@@ -146,9 +155,11 @@ k_factor_log_partition(trb_factor f, int n, int ld, const double* __restrict__ a
 }
 
 // ---- fused factor -> variable message --------------------------------------
-// posterior -> mean(v) -> clip -> b_new -> damping, one CTA per instance.
-// The moments are evaluated once; r is parked in `scratch` (same thread writes
-// and re-reads it, so it comes back from L1/L2, not HBM).
+// posterior -> mean(v) -> clip -> b_new -> damping.  One CTA per instance, or a
+// thread-block cluster of C CTAs (grid (C, B)) when few large instances would
+// leave the GPU idle; the mean runs over the cluster through distributed
+// shared memory.  The moments are evaluated once; r is parked in `scratch`
+// (same thread writes and re-reads it, so it comes back from L1/L2, not HBM).
 __global__ void __launch_bounds__(kEwThreads)
 k_factor_message(trb_factor f, int n, int ld, const double* __restrict__ a_in,
                  const double* __restrict__ b_in, const double* __restrict__ y, double* a_io,
@@ -156,8 +167,10 @@ k_factor_message(trb_factor f, int n, int ld, const double* __restrict__ a_in,
                  int* flags, const int* __restrict__ active) {
   __shared__ double sh[33];
   __shared__ int sh_flag;
-  const int inst = blockIdx.x;
-  if (active && !active[inst]) return;
+  const int inst = blockIdx.y;
+  if (active && !active[inst]) return;  // uniform over the cluster
+  const int T = blockDim.x * cluster_nctarank();
+  const int gtid = cluster_ctarank() * blockDim.x + threadIdx.x;
   const size_t off = (size_t)inst * ld;
   const double a = a_in[inst];
   double a_new;
@@ -165,7 +178,7 @@ k_factor_message(trb_factor f, int n, int ld, const double* __restrict__ a_in,
   if (factor_is_constant_message(f.kind)) {
     // gaussian_prior.py:86-89 / gaussian_likelihood.py:68-71: constants, no clip
     a_new = f.p0;
-    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    for (int i = gtid; i < n; i += T) {
       const double bn = (f.kind == TRB_GAUSSIAN_PRIOR) ? f.p1 : y[off + i] * f.p0;
       const double bd = damp(damping, b_io[off + i], bn);
       b_io[off + i] = bd;
@@ -173,13 +186,13 @@ k_factor_message(trb_factor f, int n, int ld, const double* __restrict__ a_in,
     }
   } else {
     constexpr int U = 4;  // elements per thread whose loads are issued together
-    const int step = blockDim.x * U;
+    const int step = T * U;
     double vsum = 0.0;
-    for (int base = threadIdx.x; base < n; base += step) {
+    for (int base = gtid; base < n; base += step) {
       double bv[U], yv[U];
 #pragma unroll
       for (int u = 0; u < U; ++u) {
-        const int i = base + u * blockDim.x;
+        const int i = base + u * T;
         if (i < n) {
           bv[u] = b_in[off + i];
           yv[u] = y ? y[off + i] : 0.0;
@@ -187,7 +200,7 @@ k_factor_message(trb_factor f, int n, int ld, const double* __restrict__ a_in,
       }
 #pragma unroll
       for (int u = 0; u < U; ++u) {
-        const int i = base + u * blockDim.x;
+        const int i = base + u * T;
         if (i < n) {
           const RV m = factor_moments(f, a, bv[u], yv[u]);
           scratch[off + i] = m.r;
@@ -195,14 +208,14 @@ k_factor_message(trb_factor f, int n, int ld, const double* __restrict__ a_in,
         }
       }
     }
-    const double v = block_sum(vsum, sh) / n;
+    const double v = cluster_sum(vsum, sh) / n;
     a_new = clip_a_new(v, a, f.amin, f.amax);
     const double ainv = a + a_new;
-    for (int base = threadIdx.x; base < n; base += step) {
+    for (int base = gtid; base < n; base += step) {
       double rv[U], bv[U], bo[U];
 #pragma unroll
       for (int u = 0; u < U; ++u) {
-        const int i = base + u * blockDim.x;
+        const int i = base + u * T;
         if (i < n) {
           rv[u] = scratch[off + i];
           bv[u] = b_in[off + i];
@@ -211,7 +224,7 @@ k_factor_message(trb_factor f, int n, int ld, const double* __restrict__ a_in,
       }
 #pragma unroll
       for (int u = 0; u < U; ++u) {
-        const int i = base + u * blockDim.x;
+        const int i = base + u * T;
         if (i < n) {
           const double bn = rv[u] * ainv - bv[u];
           b_io[off + i] = damp(damping, bo[u], bn);
@@ -222,8 +235,8 @@ k_factor_message(trb_factor f, int n, int ld, const double* __restrict__ a_in,
   }
   if (a_new != a_new) flag |= TRB_FLAG_NAN_A;
   if (a_new < 0) flag |= TRB_FLAG_NEG_A;
-  const int all = block_or(flag, &sh_flag);
-  if (threadIdx.x == 0) {
+  const int all = cluster_or(flag, &sh_flag);
+  if (gtid == 0) {
     const double ad = damp(damping, a_io[inst], a_new);
     a_io[inst] = ad;
     if (a_copy) a_copy[inst] = ad;
@@ -296,8 +309,11 @@ extern "C" int trb_factor_message(const trb_factor* f, int B, int n, int ld, con
   TRB_CHECK_ARG(f->kind >= 0 && f->kind <= TRB_ABS_LIKELIHOOD, "unknown factor kind");
   TRB_CHECK_ARG(!needs_y(f->kind) || y, "likelihood needs y");
   trb_launch_scope scope_(0, (cudaStream_t)stream);
-  k_factor_message<<<B, kEwThreads, 0, (cudaStream_t)stream>>>(
-      *f, n, ld, a_in, b_in, y, a_io, b_io, a_copy, damping, scratch, flags, active);
+  cudaError_t le = trb_launch_cluster(k_factor_message, trb_cluster_size(B, n), B, kEwThreads,
+                                      (cudaStream_t)stream, *f, n, ld, a_in, b_in, y, a_io, b_io,
+                                      a_copy, damping, scratch, flags, active);
+  if (le != cudaSuccess)
+    return trb_set_error(TRB_ERR_CUDA, "trb_factor_message: %s", cudaGetErrorString(le));
   TRB_CHECK_LAUNCH();
   return TRB_OK;
 }

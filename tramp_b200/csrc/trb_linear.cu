@@ -353,20 +353,20 @@ k_gemv_tma(const double* __restrict__ A, int64_t strideA, int R, int n, int ld, 
 
 // ---------------------------------------------------------------- small ops
 __global__ void __launch_bounds__(256)
-k_reduce_slots(int R, int n, int ld, int B, int G, int nslots, const double* __restrict__ part,
+k_reduce_slots(int R, int n, int ld, int B, int G, int nslots, const double* part,
                const double* __restrict__ add, const double* __restrict__ add_div,
-               double* __restrict__ out) {
-  const int b = blockIdx.x;
+               double* out, size_t out_stride) {  // out may alias slot 0 of part (in-place)
+  const int b = blockIdx.y;  // grid (chunks, B)
   const int64_t T = (int64_t)B * R;
   const int kf = (int)part_owner((int64_t)b * R, T, G);
   const int kl = (int)part_owner((int64_t)b * R + R - 1, T, G);
   const int ns = kl - kf + 1;
   const double div = add ? add_div[b] : 1.0;
-  for (int j = threadIdx.x; j < n; j += blockDim.x) {
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
     double v = 0.0;
     for (int sl = 0; sl < ns; ++sl) v += part[((size_t)b * nslots + sl) * ld + j];
     if (add) v = add[(size_t)b * ld + j] / div + v;
-    out[(size_t)b * ld + j] = v;
+    out[(size_t)b * out_stride + j] = v;
   }
 }
 
@@ -379,8 +379,10 @@ k_lin_rescale(int dir, int R, int Nz, int Nx, int rank, int null_space_flag,
               const double* __restrict__ tx, double* __restrict__ coef, double* __restrict__ v_out,
               const int* __restrict__ active) {
   __shared__ double sh[33];
-  const int b = blockIdx.x;
+  const int b = blockIdx.y;  // grid (C, B): a cluster of C CTAs per instance
   if (active && !active[b]) return;
+  const int T_ = blockDim.x * cluster_nctarank();
+  const int gtid = cluster_ctarank() * blockDim.x + threadIdx.x;
   const double az = az_arr[b], ax = ax_arr[b];
   const double* sb = s + (size_t)b * stride_s;
   const double* s2b = s2 + (size_t)b * stride_s;
@@ -391,8 +393,8 @@ k_lin_rescale(int dir, int R, int Nz, int Nx, int rank, int null_space_flag,
   double v;
   if (dir == 0 && ax == 0) {  // :100-102
     double part = 0.0;
-    for (int i = threadIdx.x; i < rank; i += blockDim.x) part += s2b[i];
-    const double s_mean = block_sum(part, sh) / rank;
+    for (int i = gtid; i < rank; i += T_) part += s2b[i];
+    const double s_mean = cluster_sum(part, sh) / rank;
     v = s_mean * rank / (Nx * az);
   } else {
     double n_eff;
@@ -404,8 +406,8 @@ k_lin_rescale(int dir, int R, int Nz, int Nx, int rank, int null_space_flag,
         n_eff = (double)rank / Nz;
       } else {  // :66-67
         double part = 0.0;
-        for (int i = threadIdx.x; i < rank; i += blockDim.x) part += s2b[i] / (ratio + s2b[i]);
-        n_eff = block_sum(part, sh) / Nz;
+        for (int i = gtid; i < rank; i += T_) part += s2b[i] / (ratio + s2b[i]);
+        n_eff = cluster_sum(part, sh) / Nz;
       }
     }
     if (dir == 0) {
@@ -415,11 +417,11 @@ k_lin_rescale(int dir, int R, int Nz, int Nx, int rank, int null_space_flag,
       v = (1 - n_eff) / az_v;  // :95-97
     }
   }
-  if (threadIdx.x == 0 && v_out) v_out[b] = v;
+  if (gtid == 0 && v_out) v_out[b] = v;
   if (!coef) return;
   // ---- coefficients in the singular basis
   const bool null_space = null_space_flag != 0;
-  for (int i = threadIdx.x; i < R; i += blockDim.x) {
+  for (int i = gtid; i < R; i += T_) {
     const double si = sb[i], s2i = s2b[i];
     const double res = 1 / (az + ax * s2i);  // :74
     const double tzi = tz[off + i], txi = tx[off + i];
@@ -640,18 +642,35 @@ extern "C" int trb_lin_expand(const double* A, int64_t strideA, int R, int n, in
   return TRB_OK;
 }
 
+static int reduce_slots_launch(int B, int R, int n, int ld, const double* part, const double* add,
+                               const double* add_div, double* out, size_t out_stride,
+                               cudaStream_t st) {
+  const trb_expand_geom geo = trb_expand_geometry(B, R);
+  trb_launch_scope scope_(0, st);
+  int chunks = (n + 1023) / 1024;  // >= 4 columns per thread, enough CTAs to fill the GPU
+  const int cap = (4 * trb_sm_count_cached() + B - 1) / B;
+  if (chunks > cap) chunks = cap < 1 ? 1 : cap;
+  k_reduce_slots<<<dim3(chunks, B), 256, 0, st>>>(R, n, ld, B, geo.G, geo.nslots, part, add, add_div,
+                                                 out, out_stride);
+  TRB_CHECK_LAUNCH();
+  return TRB_OK;
+}
+
+// Sums the per-CTA slots of every instance into slot 0 (used by the sweep when an
+// instance spans many CTAs, so that the update kernels read one vector, not nslots).
+int trb_reduce_slots_inplace(int B, int R, int n, int ld, double* part, void* stream) {
+  const trb_expand_geom geo = trb_expand_geometry(B, R);
+  return reduce_slots_launch(B, R, n, ld, part, nullptr, nullptr, part, (size_t)geo.nslots * ld,
+                             (cudaStream_t)stream);
+}
+
 extern "C" int trb_lin_reduce_slots(int B, int R, int n, int ld, const double* part,
                                     const double* add, const double* add_div, double* out,
                                     void* stream) {
   TRB_CHECK_ARG(part && out, "null pointer");
   TRB_CHECK_ARG(!add || add_div, "add needs add_div");
   TRB_CHECK_ARG(B > 0 && R > 0 && n > 0 && ld >= n, "bad shape");
-  const trb_expand_geom geo = trb_expand_geometry(B, R);
-  trb_launch_scope scope_(0, (cudaStream_t)stream);
-  k_reduce_slots<<<B, 256, 0, (cudaStream_t)stream>>>(R, n, ld, B, geo.G, geo.nslots, part, add,
-                                                       add_div, out);
-  TRB_CHECK_LAUNCH();
-  return TRB_OK;
+  return reduce_slots_launch(B, R, n, ld, part, add, add_div, out, (size_t)ld, (cudaStream_t)stream);
 }
 
 extern "C" int trb_lin_rescale(int dir, int B, int R, int Nz, int Nx, int rank, int null_space,
@@ -664,8 +683,11 @@ extern "C" int trb_lin_rescale(int dir, int B, int R, int Nz, int Nx, int rank, 
   TRB_CHECK_ARG(dir == 0 || dir == 1, "dir must be 0 or 1");
   TRB_CHECK_ARG(B > 0 && R > 0 && R <= Nz && R <= Nx && rank >= 0 && rank <= R, "bad shape");
   trb_launch_scope scope_(0, (cudaStream_t)stream);
-  k_lin_rescale<<<B, 256, 0, (cudaStream_t)stream>>>(dir, R, Nz, Nx, rank, null_space, s, s2,
-                                                      stride_s, az, ax, tz, tx, coef, v, active);
+  cudaError_t le = trb_launch_cluster(k_lin_rescale, trb_cluster_size(B, R), B, 256,
+                                      (cudaStream_t)stream, dir, R, Nz, Nx, rank, null_space, s, s2,
+                                      stride_s, az, ax, tz, tx, coef, v, active);
+  if (le != cudaSuccess)
+    return trb_set_error(TRB_ERR_CUDA, "trb_lin_rescale: %s", cudaGetErrorString(le));
   TRB_CHECK_LAUNCH();
   return TRB_OK;
 }

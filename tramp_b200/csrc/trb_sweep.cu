@@ -47,8 +47,10 @@ __global__ void __launch_bounds__(kUpThreads)
 k_z_update(trb_sweep sw, int G, int first, int light, double* __restrict__ stats) {
   __shared__ double sh[33 * 2];
   __shared__ int sh_flag;
-  const int b = blockIdx.x;
+  const int b = blockIdx.y;  // grid (C, B): a cluster of C CTAs per instance
   if (sw.active && !sw.active[b]) return;
+  const int T = blockDim.x * cluster_nctarank();
+  const int gtid = cluster_ctarank() * blockDim.x + threadIdx.x;
   const int B = sw.B, M = sw.M, ld = sw.ldm;
   const size_t off = (size_t)b * ld;
   double* ea = sw.edge_a;
@@ -65,15 +67,15 @@ k_z_update(trb_sweep sw, int G, int first, int light, double* __restrict__ stats
   double* scr = sw.scr_m + off;
   const double* y = sw.y + off;
   const bool const_lik = factor_is_constant_message(sw.lik.kind);
-  const int step = blockDim.x * kUnroll;
+  const int step = T * kUnroll;
   int flag = 0;
   double vsum = 0.0;
   // pass 1: e3 (= e4) and the likelihood moments at (a3, b3)
-  for (int base = threadIdx.x; base < (light ? 0 : M); base += step) {
+  for (int base = gtid; base < (light ? 0 : M); base += step) {
     double rx[kUnroll], b6v[kUnroll], b3o[kUnroll], yv[kUnroll];
 #pragma unroll
     for (int u = 0; u < kUnroll; ++u) {
-      const int i = base + u * blockDim.x;
+      const int i = base + u * T;
       rx[u] = 0.0;
       if (i < M) {
         for (int sl = 0; sl < ns; ++sl) rx[u] += part[(size_t)sl * ld + i];
@@ -84,7 +86,7 @@ k_z_update(trb_sweep sw, int G, int first, int light, double* __restrict__ stats
     }
 #pragma unroll
     for (int u = 0; u < kUnroll; ++u) {
-      const int i = base + u * blockDim.x;
+      const int i = base + u * T;
       if (i < M) {
         const double b3n = rx[u] * ainv3 - b6v[u];
         if (b3n != b3n) flag |= TRB_FLAG_NAN_B;
@@ -102,7 +104,7 @@ k_z_update(trb_sweep sw, int G, int first, int light, double* __restrict__ stats
   if (const_lik) {
     a5n = sw.lik.p0;  // gaussian_likelihood.py:68-71
   } else {
-    const double v = block_sum(vsum, sh) / M;
+    const double v = cluster_sum(vsum, sh) / M;
     a5n = clip_a_new(v, a3, sw.lik.amin, sw.lik.amax);  // base_likelihood.py:25-28
   }
   const double a5 = damp(sw.damp5, ea[4 * B + b], a5n);
@@ -110,11 +112,11 @@ k_z_update(trb_sweep sw, int G, int first, int light, double* __restrict__ stats
   const double a_hat = a3 + a5;
   double red[2] = {0.0, 0.0};
   // pass 2: e5 (= e6) and the posterior of z
-  for (int base = threadIdx.x; base < M; base += step) {
+  for (int base = gtid; base < M; base += step) {
     double b3v[kUnroll], src[kUnroll], b5o[kUnroll], ro[kUnroll];
 #pragma unroll
     for (int u = 0; u < kUnroll; ++u) {
-      const int i = base + u * blockDim.x;
+      const int i = base + u * T;
       if (i < M) {
         b3v[u] = b3[i];
         src[u] = const_lik ? y[i] : scr[i];
@@ -124,7 +126,7 @@ k_z_update(trb_sweep sw, int G, int first, int light, double* __restrict__ stats
     }
 #pragma unroll
     for (int u = 0; u < kUnroll; ++u) {
-      const int i = base + u * blockDim.x;
+      const int i = base + u * T;
       if (i < M) {
         const double b5n = const_lik ? src[u] * sw.lik.p0 : src[u] * ainv5 - b3v[u];
         if (b5n != b5n) flag |= TRB_FLAG_NAN_B;
@@ -138,11 +140,11 @@ k_z_update(trb_sweep sw, int G, int first, int light, double* __restrict__ stats
       }
     }
   }
-  block_sum_n<2>(red, sh);
+  cluster_sum_n<2>(red, sh);
   if (a3n != a3n || a5n != a5n) flag |= TRB_FLAG_NAN_A;
   if (a3n < 0 || a5n < 0) flag |= TRB_FLAG_NEG_A;
-  const int all = block_or(flag, &sh_flag);
-  if (threadIdx.x == 0) {
+  const int all = cluster_or(flag, &sh_flag);
+  if (gtid == 0) {
     ea[2 * B + b] = a3;
     ea[3 * B + b] = a3;  // e4 = e3 (sub_variables.py:21-25)
     ea[4 * B + b] = a5;
@@ -160,8 +162,10 @@ __global__ void __launch_bounds__(kUpThreads)
 k_x_update(trb_sweep sw, int G, int it, double* __restrict__ stats) {
   __shared__ double sh[33 * 4];
   __shared__ int sh_flag;
-  const int b = blockIdx.x;
+  const int b = blockIdx.y;  // grid (C, B): a cluster of C CTAs per instance
   if (sw.active && !sw.active[b]) return;
+  const int T = blockDim.x * cluster_nctarank();
+  const int gtid = cluster_ctarank() * blockDim.x + threadIdx.x;
   const int B = sw.B, N = sw.N, ld = sw.ldn;
   const size_t off = (size_t)b * ld;
   double* ea = sw.edge_a;
@@ -177,14 +181,14 @@ k_x_update(trb_sweep sw, int G, int it, double* __restrict__ stats) {
   double* b7 = sw.b7 + off;
   double* rx = sw.rx + off;
   const double* xt = sw.x_true ? sw.x_true + off : nullptr;
-  const int step = blockDim.x * kUnroll;
+  const int step = T * kUnroll;
   int flag = 0;
   double red[4] = {0.0, 0.0, 0.0, 0.0};  // sum dr^2, sum r^2, sum (r-x)^2, sum (r+x)^2
-  for (int base = threadIdx.x; base < N; base += step) {
+  for (int base = gtid; base < N; base += step) {
     double rzv[kUnroll], b1v[kUnroll], b7o[kUnroll], ro[kUnroll], xv[kUnroll];
 #pragma unroll
     for (int u = 0; u < kUnroll; ++u) {
-      const int i = base + u * blockDim.x;
+      const int i = base + u * T;
       rzv[u] = 0.0;
       xv[u] = 0.0;
       if (i < N) {
@@ -197,7 +201,7 @@ k_x_update(trb_sweep sw, int G, int it, double* __restrict__ stats) {
     }
 #pragma unroll
     for (int u = 0; u < kUnroll; ++u) {
-      const int i = base + u * blockDim.x;
+      const int i = base + u * T;
       if (i < N) {
         double r = rzv[u];
         if (null_space) r = b1v[u] / a1 + r;
@@ -214,12 +218,12 @@ k_x_update(trb_sweep sw, int G, int it, double* __restrict__ stats) {
       }
     }
   }
-  block_sum_n<4>(red, sh);
+  cluster_sum_n<4>(red, sh);
   const double d2 = red[0], n2 = red[1], e_pos = red[2], e_neg = red[3];
   if (a7n != a7n) flag |= TRB_FLAG_NAN_A;
   if (a7n < 0) flag |= TRB_FLAG_NEG_A;
-  const int all = block_or(flag, &sh_flag);
-  if (threadIdx.x == 0) {
+  const int all = cluster_or(flag, &sh_flag);
+  if (gtid == 0) {
     ea[6 * B + b] = a7;
     ea[7 * B + b] = a7;  // e8 = e7
     const double vx = 1. / a_hat;
@@ -263,8 +267,10 @@ k_x_update(trb_sweep sw, int G, int it, double* __restrict__ stats) {
 //   stopped on NaN / divergence, once    -> restore (reset_message_dag, :196-197, callbacks.py:281-283)
 __global__ void __launch_bounds__(256)
 k_snapshot(trb_sweep sw) {
-  const int b = blockIdx.x;
+  const int b = blockIdx.y;  // grid (chunks, B), plain CTAs: pure copies
   const int B = sw.B;
+  const size_t gtid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t T = (size_t)gridDim.x * blockDim.x;
   const int flags = sw.flags[b];
   const bool save = sw.active[b] != 0;
   const bool restore = !save && (flags & (TRB_FLAG_DIVERGED | TRB_FLAG_NAN_A | TRB_FLAG_NAN_B)) &&
@@ -273,7 +279,7 @@ k_snapshot(trb_sweep sw) {
   auto copy = [&](double* live, double* snap, size_t n) {
     double* dst = save ? snap : live;
     const double* src = save ? live : snap;
-    for (size_t i = threadIdx.x; i < n; i += blockDim.x) dst[i] = src[i];
+    for (size_t i = gtid; i < n; i += T) dst[i] = src[i];
   };
   copy(sw.b1 + (size_t)b * sw.ldn, sw.snap_b1 + (size_t)b * sw.ldn, sw.N);
   copy(sw.b7 + (size_t)b * sw.ldn, sw.snap_b7 + (size_t)b * sw.ldn, sw.N);
@@ -282,6 +288,7 @@ k_snapshot(trb_sweep sw) {
   copy(sw.b5 + (size_t)b * sw.ldm, sw.snap_b5 + (size_t)b * sw.ldm, sw.M);
   copy(sw.rz + (size_t)b * sw.ldm, sw.snap_rz + (size_t)b * sw.ldm, sw.M);
   copy(sw.tx + (size_t)b * sw.R, sw.snap_tx + (size_t)b * sw.R, sw.R);
+  if (blockIdx.x != 0) return;
   if (threadIdx.x < 8) {
     double* live = sw.edge_a + (size_t)threadIdx.x * B + b;
     double* snap = sw.snap_edge_a + (size_t)threadIdx.x * B + b;
@@ -289,7 +296,16 @@ k_snapshot(trb_sweep sw) {
   }
   if (threadIdx.x == 8) { if (save) sw.snap_vx[b] = sw.vx[b]; else sw.vx[b] = sw.snap_vx[b]; }
   if (threadIdx.x == 9) { if (save) sw.snap_vz[b] = sw.vz[b]; else sw.vz[b] = sw.snap_vz[b]; }
-  if (restore && threadIdx.x == 0) atomicOr(&sw.flags[b], TRB_FLAG_RESTORED);
+}
+
+// after every CTA of k_snapshot is done: remember which instances were rolled back
+__global__ void k_snapshot_mark(trb_sweep sw) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= sw.B) return;
+  const int flags = sw.flags[b];
+  if (sw.active[b] == 0 && (flags & (TRB_FLAG_DIVERGED | TRB_FLAG_NAN_A | TRB_FLAG_NAN_B)) &&
+      !(flags & TRB_FLAG_RESTORED))
+    sw.flags[b] = flags | TRB_FLAG_RESTORED;
 }
 
 // Schedules 1, 2: U_R^T b5' for the Gaussian-likelihood message b5' = d5 b5 + (1-d5) y/var
@@ -355,6 +371,9 @@ extern "C" int trb_sweep_stage(const trb_sweep* sw, int stage, int it, int first
   TRB_CHECK_ARG(sw->gemv_impl != 3 || shared_ops, "gemv_impl 3 (GEMM) needs a shared operator");
   const bool gemm = shared_ops && (sw->gemv_impl == 3 || (sw->gemv_impl == 0 && B >= 16));
   if (gemm) pre_reduced = 1;
+  // few instances over many CTAs: the expansion stages leave the slot sum in slot 0
+  const bool reduce_first = !pre_reduced && sw->nslots > kTrbDirectSlots;
+  if (reduce_first && (stage == TRB_STAGE_Z_UPDATE || stage == TRB_STAGE_X_UPDATE)) pre_reduced = 1;
   int G = 0;
   if (stage == TRB_STAGE_Z_UPDATE || stage == TRB_STAGE_Z_UPDATE_LIGHT ||
       stage == TRB_STAGE_X_UPDATE) {
@@ -394,15 +413,20 @@ extern "C" int trb_sweep_stage(const trb_sweep* sw, int stage, int it, int first
       if (gemm)
         return trb_lin_expand_gemm(sw->Ut, sw->R, sw->M, sw->ldm, B, sw->coef, sw->part,
                                    sw->nslots * sw->ldm, stream);
-      return trb_lin_expand(sw->Ut, sw->strideU, sw->R, sw->M, sw->ldm, B, sw->coef, sw->part,
-                            sw->active, sw->gemv_impl, stream);
+      rc = trb_lin_expand(sw->Ut, sw->strideU, sw->R, sw->M, sw->ldm, B, sw->coef, sw->part,
+                          sw->active, sw->gemv_impl, stream);
+      if (rc || !reduce_first) return rc;
+      return trb_reduce_slots_inplace(B, sw->R, sw->M, sw->ldm, sw->part, stream);
     case TRB_STAGE_Z_UPDATE:          // Z: e3, likelihood e5, posterior z
     case TRB_STAGE_Z_UPDATE_LIGHT: {  // schedule 2: scalars and e5 only
       const int light = stage == TRB_STAGE_Z_UPDATE_LIGHT;
       TRB_CHECK_ARG(!light || sw->lik.kind == TRB_GAUSSIAN_LIKELIHOOD,
                     "the light z update needs a Gaussian likelihood");
       trb_launch_scope scope_(0, st);
-      k_z_update<<<B, kUpThreads, 0, st>>>(*sw, G, first, light, sw->stats);
+      cudaError_t le = trb_launch_cluster(k_z_update, trb_cluster_size(B, sw->M), B, kUpThreads, st,
+                                          *sw, G, first, light, sw->stats);
+      if (le != cudaSuccess)
+        return trb_set_error(TRB_ERR_CUDA, "k_z_update: %s", cudaGetErrorString(le));
       TRB_CHECK_LAUNCH();
       return TRB_OK;
     }
@@ -436,18 +460,25 @@ extern "C" int trb_sweep_stage(const trb_sweep* sw, int stage, int it, int first
       if (gemm)
         return trb_lin_expand_gemm(sw->Vt, sw->R, sw->N, sw->ldn, B, sw->coef, sw->part,
                                    sw->nslots * sw->ldn, stream);
-      return trb_lin_expand(sw->Vt, sw->strideV, sw->R, sw->N, sw->ldn, B, sw->coef, sw->part,
-                            sw->active, sw->gemv_impl, stream);
+      rc = trb_lin_expand(sw->Vt, sw->strideV, sw->R, sw->N, sw->ldn, B, sw->coef, sw->part,
+                          sw->active, sw->gemv_impl, stream);
+      if (rc || !reduce_first) return rc;
+      return trb_reduce_slots_inplace(B, sw->R, sw->N, sw->ldn, sw->part, stream);
     case TRB_STAGE_X_UPDATE: {  // X: e7, posterior x, records, early stopping
       trb_launch_scope scope_(0, st);
-      k_x_update<<<B, kUpThreads, 0, st>>>(*sw, G, it, sw->stats);
+      cudaError_t le = trb_launch_cluster(k_x_update, trb_cluster_size(B, sw->N), B, kUpThreads, st,
+                                          *sw, G, it, sw->stats);
+      if (le != cudaSuccess)
+        return trb_set_error(TRB_ERR_CUDA, "k_x_update: %s", cudaGetErrorString(le));
       TRB_CHECK_LAUNCH();
       return TRB_OK;
     }
     case TRB_STAGE_SNAPSHOT: {
       if (!sw->snap_edge_a) return TRB_OK;
       trb_launch_scope scope_(0, st);
-      k_snapshot<<<B, 256, 0, st>>>(*sw);
+      const int big = sw->N > sw->M ? sw->N : sw->M;
+      k_snapshot<<<dim3(trb_cluster_size(B, big), B), 256, 0, st>>>(*sw);
+      k_snapshot_mark<<<(B + 255) / 256, 256, 0, st>>>(*sw);
       TRB_CHECK_LAUNCH();
       return TRB_OK;
     }
