@@ -74,6 +74,8 @@ typedef struct {
 /* the instance's messages were rolled back to the end of the previous iteration
  * (message_passing.py:196-197, callbacks.py:281-283 reset_message_dag) */
 #define TRB_FLAG_RESTORED 32
+/* a rank of a row-sharded operator waited > ~1 s for a peer's partial sums */
+#define TRB_FLAG_COMM_TIMEOUT 64
 
 const char* trb_last_error(void);
 int trb_version(void);
@@ -199,6 +201,26 @@ int trb_lin_rescale(int dir, int B, int R, int Nz, int Nx, int rank, int null_sp
                     const double* tx, double* coef, double* v,
                     const int* active, void* stream);
 
+/* ---- peer-memory exchange for a row-sharded operator ----------------------
+ * One process per GPU of one NVLink / NVSwitch node (<= TRB_MAX_RANKS).  Every
+ * rank calls trb_comm_create (allocates its exchange buffer, returns a 64-byte
+ * CUDA IPC handle), the caller all-gathers the handles by any out-of-band means
+ * (torch.distributed in tramp_b200) and passes the nranks*64 bytes to
+ * trb_comm_connect, which maps every peer's buffer.  Inside the sweep a rank
+ * writes its partial expansion into its own buffer, publishes a sequence number
+ * into every peer's flag array, and the consumer kernel adds the peers' vectors
+ * with loads over NVLink, in rank order (bit-identical on all ranks).
+ * trb_comm_all_reduce exposes the same protocol as a stand-alone sum; every rank
+ * must issue the same sequence of exchanges.  timeout_flag (nullable, device
+ * int) is set to 1 if a peer did not publish within ~1 s. */
+#define TRB_MAX_RANKS 8
+typedef struct trb_comm trb_comm;
+int trb_comm_create(int rank, int nranks, size_t vec_doubles, trb_comm** out,
+                    unsigned char* handle64);
+int trb_comm_connect(trb_comm* c, const unsigned char* handles);
+int trb_comm_destroy(trb_comm* c);
+int trb_comm_all_reduce(trb_comm* c, double* vec, size_t n, int* timeout_flag, void* stream);
+
 /* ---- device-resident sweep ------------------------------------------------
  * algos/message_passing.py:330-357 (iterate) with :249-269 (forward_message,
  * backward_message, update_variables), :70-127 (constant damping), :187-209
@@ -266,6 +288,13 @@ typedef struct {
    * trb_sweep_stage(TRB_STAGE_PROJECT_Y). */
   int32_t schedule;
   double* ty;  /* [B, R], U_R^T y (schedules 1, 2); else may be NULL */
+  /* Row-sharded operator (one instance over several GPUs): R is this
+   * rank's block of singular triplets, R_total the whole rank, s_full / s2_full
+   * the whole spectrum [R_total] (replicated; the variances need all of it) and
+   * comm the peer-memory exchange of the expansions (trb_comm_*).  NULL comm =
+   * not sharded. */
+  struct trb_comm* comm;
+  const double* s_full; const double* s2_full;
 } trb_sweep;
 
 /* Stages of one iteration, in order (trb_sweep_run loops over them).  Back ends

@@ -1,8 +1,8 @@
 """Multi-GPU parity (needs >= 2 GPUs: `gpurun --gpus 2 -- python -m pytest tests/test_gpu_multi.py`).
 
 BASELINE config 5 in miniature: ONE instance whose thin-SVD operators are row
-sharded over the ranks; the two expansions per iteration are all-reduced over
-NCCL.  Every rank must reproduce the reference's golden sweep."""
+sharded over the ranks; the two expansions per iteration are summed over the
+ranks through peer memory (or, as a baseline, all-reduced by NCCL).  Every rank must reproduce the reference's golden sweep."""
 import json
 import os
 import numpy as np
@@ -11,7 +11,7 @@ import pytest
 pytestmark = pytest.mark.gpu
 
 
-def _worker(rank, world, port, golden, name, out_path):
+def _worker(rank, world, port, golden, name, out_path, backend):
     import torch
     import torch.distributed as dist
     os.environ["MASTER_ADDR"] = "127.0.0.1"
@@ -38,18 +38,29 @@ def _worker(rank, world, port, golden, name, out_path):
     lk = {k: v for k, v in cfg["lik"].items() if k != "kind"}
     model = (get_prior(size=N, prior_type=cfg["prior"]["kind"], **pk) @ V("x") @ lin @ V("z")
              @ get_likelihood(y=sw[name + "_y"], likelihood_type=cfg["lik"]["kind"], **lk)).to_model()
+    # the stand-alone sum over the same peer-memory protocol agrees with NCCL's
+    v = torch.arange(64, dtype=torch.float64, device="cuda") * (rank + 1) + 0.25 * rank
+    v_nccl = v.clone()
+    lin.exchange.all_reduce(v)
+    dist.all_reduce(v_nccl)
+    assert torch.equal(v, v_nccl) and int(lin.exchange.timeout.item()) == 0
     ep = ExpectationPropagation(model)
+    ep.linear_backend = backend
     track = TrackErrors({"x": sw[name + "_x"]})
     ep.iterate(max_iter=cfg["n_iter"], callback=track, damping=cfg["damping"])
-    assert ep.backend == "sharded"
+    assert ep.backend == backend
     d = ep.get_variables_data()
     np.savez(out_path % rank, rx=d["x"]["r"], rz=d["z"]["r"], vx=d["x"]["v"], vz=d["z"]["v"],
              mse=np.array([e["mse"] for e in track.errors]))
     dist.destroy_process_group()
 
 
+@pytest.mark.parametrize("backend", ["sharded", "sharded_nccl"])
 @pytest.mark.parametrize("name", ["cs_gb_gauss", "perceptron_gauss_sgn", "gb_sgn_damped"])
-def test_row_sharded_instance_matches_reference(golden_dir, tmp_path, name):
+def test_row_sharded_instance_matches_reference(golden_dir, tmp_path, name, backend):
+    """backend "sharded": expansions exchanged through peer memory inside the update
+    kernels (trb_comm.cu), whole sweep in one trb_sweep_run; "sharded_nccl": the
+    library baseline (local GEMVs + NCCL all-reduce, staged from Python)."""
     import torch
     import torch.multiprocessing as mp
     if not torch.cuda.is_available() or torch.cuda.device_count() < 2:
@@ -57,7 +68,8 @@ def test_row_sharded_instance_matches_reference(golden_dir, tmp_path, name):
     world = 2
     golden = os.path.join(golden_dir, "sweeps.npz")
     out = str(tmp_path / "rank%d.npz")
-    mp.spawn(_worker, args=(world, 29600 + os.getpid() % 300, golden, name, out), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, 29600 + os.getpid() % 300, golden, name, out, backend), nprocs=world,
+             join=True)
     sw = np.load(golden)
     res = [np.load(out % r) for r in range(world)]
     for r in res:
@@ -66,5 +78,5 @@ def test_row_sharded_instance_matches_reference(golden_dir, tmp_path, name):
             np.testing.assert_allclose(r[key], ref, rtol=1e-9, atol=1e-9 * np.abs(ref).max())
         np.testing.assert_allclose(r["vx"], sw[name + "_vx_final"], rtol=1e-9)
         np.testing.assert_allclose(r["vz"], sw[name + "_vz_final"], rtol=1e-9)
-    # the replicated state is bit-identical across ranks (NCCL all-reduce gives every rank the same sum)
+    # the replicated state is bit-identical across ranks (every rank adds the same vectors in rank order)
     assert np.array_equal(res[0]["rx"], res[1]["rx"]) and np.array_equal(res[0]["mse"], res[1]["mse"])

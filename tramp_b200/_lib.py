@@ -50,6 +50,7 @@ class TrbSweep(C.Structure):
         ("snap_tx", C.c_void_p),
         ("R_total", C.c_int32), ("schedule", C.c_int32),
         ("ty", C.c_void_p),
+        ("comm", C.c_void_p), ("s_full", C.c_void_p), ("s2_full", C.c_void_p),
     ]
 
 
@@ -62,6 +63,8 @@ GAUSSIAN_LIKELIHOOD, SGN_LIKELIHOOD, ABS_LIKELIHOOD = 3, 4, 5
  STAGE_SNAPSHOT, STAGE_Z_UPDATE_LIGHT, STAGE_TX_RECUR, STAGE_PROJECT_Y) = range(14)
 
 FLAG_NAN_A, FLAG_NAN_B, FLAG_NEG_A, FLAG_CONVERGED, FLAG_DIVERGED, FLAG_RESTORED = 1, 2, 4, 8, 16, 32
+FLAG_COMM_TIMEOUT = 64
+MAX_RANKS = 8
 
 _I, _L, _D, _P = C.c_int, C.c_int64, C.c_double, C.c_void_p
 _FP = C.POINTER(TrbFactor)
@@ -89,6 +92,10 @@ SIGNATURES = {
     "trb_gemm_set_variant": (None, [_I]),
     "trb_lin_reduce_slots": (_I, [_I, _I, _I, _I, _P, _P, _P, _P, _P]),
     "trb_lin_rescale": (_I, [_I, _I, _I, _I, _I, _I, _I, _P, _P, _L, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "trb_comm_create": (_I, [_I, _I, C.c_size_t, C.POINTER(C.c_void_p), C.c_char_p]),
+    "trb_comm_connect": (_I, [_P, C.c_char_p]),
+    "trb_comm_destroy": (_I, [_P]),
+    "trb_comm_all_reduce": (_I, [_P, _P, C.c_size_t, _P, _P]),
     "trb_sweep_run": (_I, [C.POINTER(TrbSweep), _I, _I, _I, _P]),
     "trb_sweep_stage": (_I, [C.POINTER(TrbSweep), _I, _I, _I, _I, _P]),
 }

@@ -56,9 +56,11 @@ class MessagePassing():
         self.gemv_impl = 0
         # how the four operator passes run: "gemv" (batched HBM-bound GEMVs, the
         # default), "gemm" (hand-written FP64 tensor-core DMMA GEMMs when a batch
-        # shares one W), "sharded" (rows of the operators split over ranks +
-        # all-reduce), "cublas" (torch.matmul, kept only as the library baseline the
-        # DMMA kernel is measured against); None = pick
+        # shares one W), "sharded" (rows of the operators split over ranks, the
+        # expansions exchanged through peer memory inside the update kernels),
+        # "cublas" (torch.matmul) and "sharded_nccl" (local GEMVs + NCCL all-reduce)
+        # are kept only as the library baselines the native paths are measured
+        # against; None = pick
         self.linear_backend = None
         # operator passes per iteration: "general" (4, any likelihood), "gauss3" /
         # "gauss2" (3 / 2 passes, exact for a Gaussian likelihood, see
@@ -134,7 +136,7 @@ class MessagePassing():
         self.backend = self._pick_backend()
         st["nslots"] = ops.lin_expand_slots(B, R)
         st["part"] = t.zeros((B, st["nslots"], max(ldn, ldm)), **f64)
-        if self.backend not in ("gemv", "gemm"):
+        if self.backend not in ("gemv", "gemm", "sharded"):
             # fully reduced expansion results, read by the update kernels as slot 0
             st["red"] = t.zeros(B * max(ldn, ldm), **f64)
             st["red_n"] = st["red"][:B * ldn].view(B, ldn)
@@ -265,6 +267,9 @@ class MessagePassing():
             sw.es_tol, sw.es_max_increase, sw.es_wait_increase, sw.es_vars = -1.0, 0.0, 0, 3
         sw.gemv_impl = 3 if self.backend == "gemm" else (self.gemv_impl or 2)
         sw.R_total = getattr(lin, "R_total", 0) or 0
+        if self.backend == "sharded":
+            sw.comm = lin.exchange.ptr
+            sw.s_full, sw.s2_full = p(lin.s_full), p(lin.s2_full)
         sw.schedule = self.last_schedule = self._pick_schedule(early, synchronous)
         if sw.schedule:
             if "ty" not in st:     # ty = U_R^T y, once per model (y is fixed)
@@ -286,7 +291,7 @@ class MessagePassing():
         if want not in ("auto", "general", "gauss3", "gauss2"):
             raise ValueError(f"unknown schedule {want!r}")
         st = self._state
-        ok3 = (type(self.lik) is GaussianLikelihood and self.backend in ("gemv", "gemm")
+        ok3 = (type(self.lik) is GaussianLikelihood and self.backend in ("gemv", "gemm", "sharded")
                and st.get("b6_init") is None)
         ok2 = ok3 and self.damp["e3"] == 0.0 and early is None and not synchronous
         if want == "general":
@@ -308,7 +313,7 @@ class MessagePassing():
         code = 0 if not fresh else (2 if st.get("b6_zero") else 1)
         if getattr(self, "_tx_stale", False):
             code, self._tx_stale = 1, False
-        if self.backend in ("gemv", "gemm"):
+        if self.backend in ("gemv", "gemm", "sharded"):
             _lib.check(_lib.load().trb_sweep_run(C.byref(sw), it0, n_iter, code, _lib.current_stream()))
         else:
             self._run_staged(sw, it0, n_iter, code)
@@ -327,7 +332,7 @@ class MessagePassing():
         # descriptor whose `part` is the fully reduced buffer (slot 0, nslots = 1)
         red = _lib.TrbSweep.from_buffer_copy(sw)
         red.part, red.nslots = _lib.ptr(st["red"]), 1
-        sharded = self.backend == "sharded"
+        sharded = self.backend == "sharded_nccl"
 
         def stage(desc, which, it, first, pre=0):
             _lib.check(lib.trb_sweep_stage(C.byref(desc), which, it, int(first), pre, stream))
@@ -381,6 +386,9 @@ class MessagePassing():
 
     def _raise_on_nan(self, flags):
         """reference message_passing.py:187-209 (check_message)."""
+        if (flags & _lib.FLAG_COMM_TIMEOUT).any():
+            raise _lib.TrbError("a rank of the row-sharded operator did not publish its partial sums "
+                                "within the time-out; the ranks are out of step")
         bad = np.nonzero(flags & (_lib.FLAG_NAN_A | _lib.FLAG_NAN_B))[0]
         if bad.size:
             what = "a" if (flags[bad[0]] & _lib.FLAG_NAN_A) else "b"

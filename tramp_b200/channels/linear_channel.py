@@ -109,6 +109,9 @@ class LinearChannel(Channel):
         self.s_full = ops.to_dev(s_full).reshape(1, -1).contiguous()
         self.s2_full = (self.s_full * self.s_full).contiguous()
         self.R_total = int(self.s_full.shape[1])
+        # peer-memory exchange of the two expansions per iteration (trb_comm_*)
+        from ..distributed import PeerExchange
+        self.exchange = PeerExchange(max(self.ldn, self.ldm), group)
         return self
 
     def all_reduce(self, tensor):

@@ -234,6 +234,57 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
       : "memory");
 }
 
+}  // namespace trb
+
+// ---- peer-memory exchange of a row-sharded operator (trb_comm.cu) ------------
+struct trb_peers {
+  int n;                                          // ranks; 0 = not sharded
+  unsigned long long seq;                         // exchange the consumer waits for
+  const double* data[TRB_MAX_RANKS];              // every rank's vector of this exchange
+  unsigned long long* flags_of[TRB_MAX_RANKS];    // every rank's flag array (publish side)
+  const unsigned long long* my_flags;             // this rank's flag array (wait side)
+};
+double* trb_comm_local_vector(trb_comm* c);
+size_t trb_comm_capacity(const trb_comm* c);
+int trb_comm_publish(trb_comm* c, trb_peers* peers, cudaStream_t st);
+const trb_peers* trb_comm_last(const trb_comm* c);
+
+namespace trb {
+
+// Block-wide wait until every rank has published exchange p.seq.  Returns false
+// if a peer stayed silent for ~1 s (the caller flags the instance and goes on
+// rather than hanging the GPU).
+__device__ __forceinline__ bool peers_wait(const trb_peers& p) {
+  __shared__ int peers_ok;
+  if (threadIdx.x == 0) peers_ok = 1;
+  __syncthreads();
+  if ((int)threadIdx.x < p.n) {
+    const unsigned long long* f = p.my_flags + threadIdx.x;
+    const long long t0 = clock64();
+    for (;;) {
+      unsigned long long v;
+      asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(f) : "memory");
+      if (v >= p.seq) break;
+      if (clock64() - t0 > 2000000000LL) {
+        peers_ok = 0;
+        break;
+      }
+    }
+  }
+  __syncthreads();
+  return peers_ok != 0;
+}
+// sum over the ranks, in rank order, of element i of the exchanged vectors
+__device__ __forceinline__ double peers_sum(const trb_peers& p, size_t i) {
+  double s = 0.0;
+  for (int r = 0; r < p.n; ++r) {
+    double v;
+    asm volatile("ld.volatile.global.f64 %0, [%1];" : "=d"(v) : "l"(p.data[r] + i) : "memory");
+    s += v;
+  }
+  return s;
+}
+
 // Even split of T work items over G workers: worker k owns [part_begin(k), part_begin(k+1)).
 __host__ __device__ __forceinline__ int64_t part_begin(int64_t k, int64_t T, int64_t G) {
   return (k * T) / G;

@@ -664,6 +664,11 @@ int trb_reduce_slots_inplace(int B, int R, int n, int ld, double* part, void* st
                              (cudaStream_t)stream);
 }
 
+// out[b, :] (leading dimension ld) = sum of the slots of instance b
+int trb_reduce_slots_to(int B, int R, int n, int ld, const double* part, double* out, void* stream) {
+  return reduce_slots_launch(B, R, n, ld, part, nullptr, nullptr, out, (size_t)ld, (cudaStream_t)stream);
+}
+
 extern "C" int trb_lin_reduce_slots(int B, int R, int n, int ld, const double* part,
                                     const double* add, const double* add_div, double* out,
                                     void* stream) {

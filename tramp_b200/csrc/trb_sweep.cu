@@ -44,7 +44,7 @@ constexpr int kUnroll = 4;  // elements per thread whose loads are issued togeth
 // message e5 are updated; e3's vector, the posterior mean of z and its tolerance
 // statistics wait for the last iteration of the run.
 __global__ void __launch_bounds__(kUpThreads)
-k_z_update(trb_sweep sw, int G, int first, int light, double* __restrict__ stats) {
+k_z_update(trb_sweep sw, int G, int first, int light, double* __restrict__ stats, trb_peers peers) {
   __shared__ double sh[33 * 2];
   __shared__ int sh_flag;
   const int b = blockIdx.y;  // grid (C, B): a cluster of C CTAs per instance
@@ -70,6 +70,10 @@ k_z_update(trb_sweep sw, int G, int first, int light, double* __restrict__ stats
   const int step = T * kUnroll;
   int flag = 0;
   double vsum = 0.0;
+  // row-sharded operator: the expansion is the sum of the ranks' vectors, read
+  // from peer memory once every rank has published this exchange (trb_comm.cu)
+  const bool use_peers = peers.n > 0 && !light;
+  if (use_peers && !peers_wait(peers)) flag |= TRB_FLAG_COMM_TIMEOUT;
   // pass 1: e3 (= e4) and the likelihood moments at (a3, b3)
   for (int base = gtid; base < (light ? 0 : M); base += step) {
     double rx[kUnroll], b6v[kUnroll], b3o[kUnroll], yv[kUnroll];
@@ -78,7 +82,8 @@ k_z_update(trb_sweep sw, int G, int first, int light, double* __restrict__ stats
       const int i = base + u * T;
       rx[u] = 0.0;
       if (i < M) {
-        for (int sl = 0; sl < ns; ++sl) rx[u] += part[(size_t)sl * ld + i];
+        if (use_peers) rx[u] = peers_sum(peers, off + i);
+        else for (int sl = 0; sl < ns; ++sl) rx[u] += part[(size_t)sl * ld + i];
         b6v[u] = b6[i];
         b3o[u] = b3[i];
         yv[u] = y[i];
@@ -159,7 +164,7 @@ k_z_update(trb_sweep sw, int G, int first, int light, double* __restrict__ stats
 }
 
 __global__ void __launch_bounds__(kUpThreads)
-k_x_update(trb_sweep sw, int G, int it, double* __restrict__ stats) {
+k_x_update(trb_sweep sw, int G, int it, double* __restrict__ stats, trb_peers peers) {
   __shared__ double sh[33 * 4];
   __shared__ int sh_flag;
   const int b = blockIdx.y;  // grid (C, B): a cluster of C CTAs per instance
@@ -183,6 +188,8 @@ k_x_update(trb_sweep sw, int G, int it, double* __restrict__ stats) {
   const double* xt = sw.x_true ? sw.x_true + off : nullptr;
   const int step = T * kUnroll;
   int flag = 0;
+  const bool use_peers = peers.n > 0;  // row-sharded operator, see k_z_update
+  if (use_peers && !peers_wait(peers)) flag |= TRB_FLAG_COMM_TIMEOUT;
   double red[4] = {0.0, 0.0, 0.0, 0.0};  // sum dr^2, sum r^2, sum (r-x)^2, sum (r+x)^2
   for (int base = gtid; base < N; base += step) {
     double rzv[kUnroll], b1v[kUnroll], b7o[kUnroll], ro[kUnroll], xv[kUnroll];
@@ -192,7 +199,8 @@ k_x_update(trb_sweep sw, int G, int it, double* __restrict__ stats) {
       rzv[u] = 0.0;
       xv[u] = 0.0;
       if (i < N) {
-        for (int sl = 0; sl < ns; ++sl) rzv[u] += part[(size_t)sl * ld + i];
+        if (use_peers) rzv[u] = peers_sum(peers, off + i);
+        else for (int sl = 0; sl < ns; ++sl) rzv[u] += part[(size_t)sl * ld + i];
         b1v[u] = b1[i];
         b7o[u] = b7[i];
         ro[u] = rx[i];
@@ -346,6 +354,18 @@ static int check_sweep(const trb_sweep* sw) {
   return TRB_OK;
 }
 
+// Row-sharded operator: reduce this rank's slots straight into its exchange buffer
+// and publish it; the following update kernel adds the ranks' vectors (trb_comm.cu).
+int trb_reduce_slots_to(int B, int R, int n, int ld, const double* part, double* out, void* stream);
+static int exchange_expansion(const trb_sweep* sw, int n, int ld, cudaStream_t st) {
+  trb_comm* comm = sw->comm;
+  TRB_CHECK_ARG((size_t)sw->B * ld <= trb_comm_capacity(comm), "exchange buffer too small");
+  int rc = trb_reduce_slots_to(sw->B, sw->R, n, ld, sw->part, trb_comm_local_vector(comm), st);
+  if (rc) return rc;
+  trb_peers peers;
+  return trb_comm_publish(comm, &peers, st);
+}
+
 // One stage of the iteration (see the header comment of this file).  `first`:
 // this is the first iteration after the messages were initialised.
 // pre_reduced: the expansion result already sits, fully summed, in slot 0 of
@@ -371,8 +391,11 @@ extern "C" int trb_sweep_stage(const trb_sweep* sw, int stage, int it, int first
   TRB_CHECK_ARG(sw->gemv_impl != 3 || shared_ops, "gemv_impl 3 (GEMM) needs a shared operator");
   const bool gemm = shared_ops && (sw->gemv_impl == 3 || (sw->gemv_impl == 0 && B >= 16));
   if (gemm) pre_reduced = 1;
+  trb_comm* comm = sw->comm;
+  TRB_CHECK_ARG(!comm || (!gemm && sw->s_full && sw->s2_full && sw->R_total >= sw->R),
+                "a row-sharded sweep needs GEMV operator passes, s_full, s2_full and R_total");
   // few instances over many CTAs: the expansion stages leave the slot sum in slot 0
-  const bool reduce_first = !pre_reduced && sw->nslots > kTrbDirectSlots;
+  const bool reduce_first = !pre_reduced && !comm && sw->nslots > kTrbDirectSlots;
   if (reduce_first && (stage == TRB_STAGE_Z_UPDATE || stage == TRB_STAGE_X_UPDATE)) pre_reduced = 1;
   int G = 0;
   if (stage == TRB_STAGE_Z_UPDATE || stage == TRB_STAGE_Z_UPDATE_LIGHT ||
@@ -406,6 +429,21 @@ extern "C" int trb_sweep_stage(const trb_sweep* sw, int stage, int it, int first
                              sw->active, sw->gemv_impl, stream);
     }
     case TRB_STAGE_RESCALE_FWD:  // S1: coef = s res (tz + s tx), forward variance
+    case TRB_STAGE_RESCALE_BWD:  // S2: coef for rz, backward variance
+      if (comm) {  // variance from the whole (replicated) spectrum, coefficients from the shard
+        const int dir = stage == TRB_STAGE_RESCALE_BWD;
+        rc = trb_lin_rescale(dir, B, R_total, sw->N, sw->M, sw->rank, null_space, sw->s_full,
+                             sw->s2_full, 0, ea + 1 * B, ea + 5 * B, nullptr, nullptr, nullptr,
+                             sw->vlin, sw->active, stream);
+        if (rc) return rc;
+        return trb_lin_rescale(dir, B, sw->R, sw->N, sw->M, sw->rank < sw->R ? sw->rank : sw->R,
+                               null_space, sw->s, sw->s2, sw->stride_s, ea + 1 * B, ea + 5 * B,
+                               sw->tz, sw->tx, sw->coef, nullptr, sw->active, stream);
+      }
+      if (stage == TRB_STAGE_RESCALE_BWD)
+        return trb_lin_rescale(1, B, sw->R, sw->N, sw->M, sw->rank, null_space, sw->s, sw->s2,
+                               sw->stride_s, ea + 1 * B, ea + 5 * B, sw->tz, sw->tx, sw->coef,
+                               sw->vlin, sw->active, stream);
       return trb_lin_rescale(0, B, sw->R, sw->N, sw->M, sw->rank, null_space, sw->s, sw->s2,
                              sw->stride_s, ea + 1 * B, ea + 5 * B, sw->tz, sw->tx, sw->coef,
                              sw->vlin, sw->active, stream);
@@ -415,7 +453,9 @@ extern "C" int trb_sweep_stage(const trb_sweep* sw, int stage, int it, int first
                                    sw->nslots * sw->ldm, stream);
       rc = trb_lin_expand(sw->Ut, sw->strideU, sw->R, sw->M, sw->ldm, B, sw->coef, sw->part,
                           sw->active, sw->gemv_impl, stream);
-      if (rc || !reduce_first) return rc;
+      if (rc) return rc;
+      if (comm) return exchange_expansion(sw, sw->M, sw->ldm, st);
+      if (!reduce_first) return rc;
       return trb_reduce_slots_inplace(B, sw->R, sw->M, sw->ldm, sw->part, stream);
     case TRB_STAGE_Z_UPDATE:          // Z: e3, likelihood e5, posterior z
     case TRB_STAGE_Z_UPDATE_LIGHT: {  // schedule 2: scalars and e5 only
@@ -423,8 +463,10 @@ extern "C" int trb_sweep_stage(const trb_sweep* sw, int stage, int it, int first
       TRB_CHECK_ARG(!light || sw->lik.kind == TRB_GAUSSIAN_LIKELIHOOD,
                     "the light z update needs a Gaussian likelihood");
       trb_launch_scope scope_(0, st);
+      trb_peers peers = {};
+      if (comm && !light) peers = *trb_comm_last(comm);
       cudaError_t le = trb_launch_cluster(k_z_update, trb_cluster_size(B, sw->M), B, kUpThreads, st,
-                                          *sw, G, first, light, sw->stats);
+                                          *sw, G, first, light, sw->stats, peers);
       if (le != cudaSuccess)
         return trb_set_error(TRB_ERR_CUDA, "k_z_update: %s", cudaGetErrorString(le));
       TRB_CHECK_LAUNCH();
@@ -452,22 +494,22 @@ extern "C" int trb_sweep_stage(const trb_sweep* sw, int stage, int it, int first
                                     stream);
       return trb_lin_project(sw->Ut, sw->strideU, sw->R, sw->M, sw->ldm, B, sw->b5, sw->ldm,
                              sw->tx, sw->active, sw->gemv_impl, stream);
-    case TRB_STAGE_RESCALE_BWD:  // S2: coef for rz, backward variance
-      return trb_lin_rescale(1, B, sw->R, sw->N, sw->M, sw->rank, null_space, sw->s, sw->s2,
-                             sw->stride_s, ea + 1 * B, ea + 5 * B, sw->tz, sw->tx, sw->coef,
-                             sw->vlin, sw->active, stream);
-    case TRB_STAGE_EXPAND_Z:  // P4: rz = [b2/a2 +] V_R coef
+case TRB_STAGE_EXPAND_Z:  // P4: rz = [b2/a2 +] V_R coef
       if (gemm)
         return trb_lin_expand_gemm(sw->Vt, sw->R, sw->N, sw->ldn, B, sw->coef, sw->part,
                                    sw->nslots * sw->ldn, stream);
       rc = trb_lin_expand(sw->Vt, sw->strideV, sw->R, sw->N, sw->ldn, B, sw->coef, sw->part,
                           sw->active, sw->gemv_impl, stream);
-      if (rc || !reduce_first) return rc;
+      if (rc) return rc;
+      if (comm) return exchange_expansion(sw, sw->N, sw->ldn, st);
+      if (!reduce_first) return rc;
       return trb_reduce_slots_inplace(B, sw->R, sw->N, sw->ldn, sw->part, stream);
     case TRB_STAGE_X_UPDATE: {  // X: e7, posterior x, records, early stopping
       trb_launch_scope scope_(0, st);
+      trb_peers peers = {};
+      if (comm) peers = *trb_comm_last(comm);
       cudaError_t le = trb_launch_cluster(k_x_update, trb_cluster_size(B, sw->N), B, kUpThreads, st,
-                                          *sw, G, it, sw->stats);
+                                          *sw, G, it, sw->stats, peers);
       if (le != cudaSuccess)
         return trb_set_error(TRB_ERR_CUDA, "k_x_update: %s", cudaGetErrorString(le));
       TRB_CHECK_LAUNCH();

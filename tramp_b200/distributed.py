@@ -5,6 +5,48 @@ collective.  torch.distributed (NCCL over NVLink on the box, gloo in the CPU
 tests) is used only to gather the per-iteration records at the end."""
 
 
+class PeerExchange:
+    """The peer-memory exchange of a row-sharded operator (include/tramp_b200.h
+    trb_comm_*): every rank's buffer is mapped into every other rank over NVLink
+    (CUDA IPC); torch.distributed only carries the 64-byte handles, once."""
+
+    def __init__(self, vec_doubles, group=None):
+        import ctypes as C
+        import torch
+        import torch.distributed as dist
+        from . import _lib
+        lib = _lib.load()
+        self.group = group
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        if self.world > _lib.MAX_RANKS:
+            raise ValueError(f"a peer exchange spans at most {_lib.MAX_RANKS} GPUs of one node")
+        handle = C.create_string_buffer(64)
+        ptr = C.c_void_p()
+        _lib.check(lib.trb_comm_create(self.rank, self.world, int(vec_doubles), C.byref(ptr), handle))
+        self.ptr = ptr
+        mine = torch.tensor(list(handle.raw), dtype=torch.uint8, device="cuda")
+        every = [torch.zeros_like(mine) for _ in range(self.world)]
+        dist.all_gather(every, mine, group=group)
+        blob = b"".join(bytes(t.cpu().tolist()) for t in every)
+        _lib.check(lib.trb_comm_connect(self.ptr, blob))
+        dist.barrier(group=group)           # nobody publishes before everyone is mapped
+        self.timeout = torch.zeros(1, dtype=torch.int32, device="cuda")
+
+    def all_reduce(self, tensor):
+        """In-place sum over the ranks (same protocol as inside the sweep)."""
+        from . import _lib
+        assert tensor.is_contiguous() and tensor.dtype.itemsize == 8
+        _lib.check(_lib.load().trb_comm_all_reduce(self.ptr, tensor.data_ptr(), tensor.numel(),
+                                                   self.timeout.data_ptr(), _lib.current_stream()))
+        return tensor
+
+    def close(self):
+        from . import _lib
+        if self.ptr:
+            _lib.load().trb_comm_destroy(self.ptr)
+            self.ptr = None
+
+
 def instance_shard(n_instances, rank, world):
     """Contiguous block [start, stop) of the rank: instance i lives on GPU
     floor(i * world / n_instances)."""
