@@ -330,6 +330,11 @@ int trb_sweep_stage(const trb_sweep* sw, int stage, int it, int first, int pre_r
  * b = 0, so tx is simply zeroed; fresh = 0: warm start / continuation. */
 int trb_sweep_run(const trb_sweep* sw, int it0, int n_iter, int fresh, void* stream);
 
+/* trb_sweep_run replays the identical middle iterations of a launch-bound sweep
+ * (less than ~1 GB of operator traffic per iteration) as a CUDA graph; 0 turns
+ * that off (default on; the environment variable TRB_CUDA_GRAPHS=0 does the same). */
+void trb_set_cuda_graphs(int enabled);
+
 #ifdef __cplusplus
 }
 #endif

@@ -527,3 +527,31 @@ def test_track_overlaps_and_objective_on_device_path(sw):
     _, node_df, model_df = obj.get_dataframe()
     scale = np.abs(node_df.A.values[-5:].astype(float)).sum()
     assert abs(model_df.A.values[-1] - sw[name + "_logZ"]) <= 1e-9 * scale
+
+
+def test_cuda_graph_replay_is_bitwise_identical_to_plain_launches(sw):
+    """Small sweeps replay their middle iterations as a CUDA graph (trb_sweep_run);
+    the kernels and their order are the same, so the results are bit-identical."""
+    from tramp_b200 import _lib
+    from tramp_b200.algos import ExpectationPropagation, TrackErrors
+    lib = _lib.load()
+    for idx in (0, 2, 4):
+        cfg = _configs(sw)[idx]
+        name = cfg["name"]
+        out = []
+        for graphs in (1, 0):
+            lib.trb_set_cuda_graphs(graphs)
+            try:
+                ep = ExpectationPropagation(_build(cfg, sw, name))
+                track = TrackErrors({"x": sw[name + "_x"]})
+                lib.trb_profile_reset(0)
+                ep.iterate(max_iter=cfg["n_iter"], callback=track, damping=cfg["damping"])
+                d = ep.get_variables_data()
+                out.append((d["x"]["r"], d["z"]["r"], d["x"]["v"], d["z"]["v"],
+                            np.array([e["mse"] for e in track.errors]),
+                            int(lib.trb_profile_launches(-1))))
+            finally:
+                lib.trb_set_cuda_graphs(1)
+        for a, b in zip(out[0][:5], out[1][:5]):
+            assert np.array_equal(a, b)
+        assert out[0][5] == out[1][5]      # the launch accounting counts replayed kernels too

@@ -60,6 +60,13 @@ void trb_note_launch(int kind, cudaStream_t st, bool before) {
   (before ? g_prof.begin[kind] : g_prof.end[kind]).push_back(e);
 }
 
+bool trb_profile_events_enabled() { return g_prof.enabled; }
+void trb_profile_add_launches(long long n0, long long n1) {
+  g_prof.launches[0] += n0;
+  g_prof.launches[1] += n1;
+}
+long long trb_profile_launch_count(int kind) { return g_prof.launches[kind]; }
+
 extern "C" void trb_profile_reset(int enable_events) {
   for (int k = 0; k < 2; ++k) {
     g_prof.launches[k] = 0;

@@ -164,11 +164,14 @@ k_z_update(trb_sweep sw, int G, int first, int light, double* __restrict__ stats
 }
 
 __global__ void __launch_bounds__(kUpThreads)
-k_x_update(trb_sweep sw, int G, int it, double* __restrict__ stats, trb_peers peers) {
+k_x_update(trb_sweep sw, int G, int it_host, double* __restrict__ stats, trb_peers peers) {
   __shared__ double sh[33 * 4];
   __shared__ int sh_flag;
   const int b = blockIdx.y;  // grid (C, B): a cluster of C CTAs per instance
   if (sw.active && !sw.active[b]) return;
+  // it < 0 (replayed CUDA graph): the iteration index is the instance's own count of
+  // completed iterations, which equals the host's index while the instance is active
+  const int it = it_host >= 0 ? it_host : sw.n_iter[b];
   const int T = blockDim.x * cluster_nctarank();
   const int gtid = cluster_ctarank() * blockDim.x + threadIdx.x;
   const int B = sw.B, N = sw.N, ld = sw.ldn;
@@ -528,6 +531,118 @@ case TRB_STAGE_EXPAND_Z:  // P4: rz = [b2/a2 +] V_R coef
   return trb_set_error(TRB_ERR_INVALID, "trb_sweep_stage: unknown stage %d", stage);
 }
 
+// One whole iteration, stage by stage (see the header comment of this file).
+static int enqueue_iteration(const trb_sweep* sw, int it, int first, int fresh, bool light,
+                             cudaStream_t st) {
+  void* stream = (void*)st;
+  const int schedule = sw->schedule;
+  TRB_TRY(trb_sweep_stage(sw, TRB_STAGE_PRIOR, it, first, 0, stream));
+  TRB_TRY(trb_sweep_stage(sw, TRB_STAGE_PROJECT_Z, it, first, 0, stream));
+  if (first) {
+    if (fresh == 2) {  // e6 was initialised to b = 0: U_R^T 0 = 0, no pass over U needed
+      cudaError_t e = cudaMemsetAsync(sw->tx, 0, sizeof(double) * (size_t)sw->B * sw->R, st);
+      if (e != cudaSuccess)
+        return trb_set_error(TRB_ERR_CUDA, "trb_sweep_run: %s", cudaGetErrorString(e));
+    } else {
+      TRB_TRY(trb_sweep_stage(sw, TRB_STAGE_PROJECT_X_INIT, it, first, 0, stream));
+    }
+  }
+  TRB_TRY(trb_sweep_stage(sw, TRB_STAGE_RESCALE_FWD, it, first, 0, stream));
+  if (!light) TRB_TRY(trb_sweep_stage(sw, TRB_STAGE_EXPAND_X, it, first, 0, stream));
+  TRB_TRY(trb_sweep_stage(sw, light ? TRB_STAGE_Z_UPDATE_LIGHT : TRB_STAGE_Z_UPDATE, it, first, 0,
+                          stream));
+  TRB_TRY(trb_sweep_stage(sw, schedule ? TRB_STAGE_TX_RECUR : TRB_STAGE_PROJECT_X, it, first, 0,
+                          stream));
+  TRB_TRY(trb_sweep_stage(sw, TRB_STAGE_RESCALE_BWD, it, first, 0, stream));
+  TRB_TRY(trb_sweep_stage(sw, TRB_STAGE_EXPAND_Z, it, first, 0, stream));
+  TRB_TRY(trb_sweep_stage(sw, TRB_STAGE_X_UPDATE, it, first, 0, stream));
+  TRB_TRY(trb_sweep_stage(sw, TRB_STAGE_SNAPSHOT, it, first, 0, stream));
+  return TRB_OK;
+}
+
+// ---- CUDA-graph replay of the identical middle iterations ----------------------
+// An iteration of a small instance is a dozen ~2 us kernels: launch latency, not
+// HBM, bounds it.  One iteration is captured (on a private stream: torch's
+// default stream is the legacy stream, which cannot be captured) with the
+// iteration index read from the device (k_x_update, it < 0) and replayed on the
+// caller's stream.  The last captured graph is cached per host thread, keyed by
+// the descriptor bytes.
+constexpr int kGraphMinIters = 4;
+constexpr double kGraphMaxBytes = 1e9;  // per iteration: beyond ~150 us of streaming, launches are hidden
+bool trb_profile_events_enabled();
+void trb_profile_add_launches(long long n0, long long n1);
+long long trb_profile_launch_count(int kind);
+static int g_graphs_enabled = -1;
+
+static bool graph_eligible(const trb_sweep* sw) {
+  if (g_graphs_enabled < 0) {
+    const char* e = getenv("TRB_CUDA_GRAPHS");
+    g_graphs_enabled = (e && e[0] == '0') ? 0 : 1;
+  }
+  if (!g_graphs_enabled || sw->comm || trb_profile_events_enabled()) return false;
+  const bool shared = sw->strideV == 0 && sw->strideU == 0;
+  const double bytes = 16.0 * sw->R * ((double)sw->N + sw->M) * (shared ? 1 : sw->B);
+  return bytes <= kGraphMaxBytes;
+}
+
+struct GraphCache {
+  trb_sweep key;
+  int light = 0;
+  cudaGraphExec_t exec = nullptr;
+  long long launches[2] = {0, 0};
+  cudaStream_t capture_stream = nullptr;
+};
+static thread_local GraphCache g_graph;
+
+static int run_graph(const trb_sweep* sw, bool light, int count, cudaStream_t st) {
+  GraphCache& gc = g_graph;
+  if (!gc.exec || gc.light != (int)light || memcmp(&gc.key, sw, sizeof(trb_sweep)) != 0) {
+    if (gc.exec) {
+      cudaGraphExecDestroy(gc.exec);
+      gc.exec = nullptr;
+    }
+    if (!gc.capture_stream &&
+        cudaStreamCreateWithFlags(&gc.capture_stream, cudaStreamNonBlocking) != cudaSuccess) {
+      cudaGetLastError();
+      return TRB_ERR_UNSUPPORTED;
+    }
+    const long long n0 = trb_profile_launch_count(0), n1 = trb_profile_launch_count(1);
+    if (cudaStreamBeginCapture(gc.capture_stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+      cudaGetLastError();
+      return TRB_ERR_UNSUPPORTED;
+    }
+    const int rc = enqueue_iteration(sw, -1, 0, 0, light, gc.capture_stream);
+    cudaGraph_t graph = nullptr;
+    const cudaError_t ce = cudaStreamEndCapture(gc.capture_stream, &graph);
+    gc.launches[0] = trb_profile_launch_count(0) - n0;
+    gc.launches[1] = trb_profile_launch_count(1) - n1;
+    trb_profile_add_launches(-gc.launches[0], -gc.launches[1]);  // captured, not launched
+    if (rc != TRB_OK || ce != cudaSuccess || !graph) {
+      if (graph) cudaGraphDestroy(graph);
+      cudaGetLastError();
+      return rc != TRB_OK ? rc : TRB_ERR_UNSUPPORTED;
+    }
+    const cudaError_t ie = cudaGraphInstantiate(&gc.exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (ie != cudaSuccess) {
+      gc.exec = nullptr;
+      cudaGetLastError();
+      return TRB_ERR_UNSUPPORTED;
+    }
+    gc.key = *sw;
+    gc.light = (int)light;
+  }
+  for (int i = 0; i < count; ++i) {
+    const cudaError_t le = cudaGraphLaunch(gc.exec, st);
+    if (le != cudaSuccess)
+      return trb_set_error(TRB_ERR_CUDA, "trb_sweep_run: graph launch: %s", cudaGetErrorString(le));
+  }
+  trb_profile_add_launches(gc.launches[0] * count, gc.launches[1] * count);
+  return TRB_OK;
+}
+
+extern "C" void trb_set_cuda_graphs(int enabled) { g_graphs_enabled = enabled ? 1 : 0; }
+
 extern "C" int trb_sweep_run(const trb_sweep* sw, int it0, int n_iter, int fresh, void* stream) {
   int rc = check_sweep(sw);
   if (rc) return rc;
@@ -541,32 +656,28 @@ extern "C" int trb_sweep_run(const trb_sweep* sw, int it0, int n_iter, int fresh
     TRB_CHECK_ARG(schedule == 1 || (sw->damp3 == 0.0 && sw->es_tol < 0),
                   "schedule 2 needs damp3 = 0 and no early stopping");
   }
-  for (int k = 0; k < n_iter; ++k) {
-    const int it = it0 + k;
+  cudaStream_t st = (cudaStream_t)stream;
+  int k = 0;
+  while (k < n_iter) {
     const int first = (fresh && k == 0) ? 1 : 0;
     const bool light = schedule == 2 && k + 1 < n_iter;  // z branch deferred to the last iteration
-    TRB_TRY(trb_sweep_stage(sw, TRB_STAGE_PRIOR, it, first, 0, stream));
-    TRB_TRY(trb_sweep_stage(sw, TRB_STAGE_PROJECT_Z, it, first, 0, stream));
-    if (first) {
-      if (fresh == 2) {  // e6 was initialised to b = 0: U_R^T 0 = 0, no pass over U needed
-        cudaError_t e = cudaMemsetAsync(sw->tx, 0, sizeof(double) * (size_t)sw->B * sw->R,
-                                        (cudaStream_t)stream);
-        if (e != cudaSuccess)
-          return trb_set_error(TRB_ERR_CUDA, "trb_sweep_run: %s", cudaGetErrorString(e));
-      } else {
-        TRB_TRY(trb_sweep_stage(sw, TRB_STAGE_PROJECT_X_INIT, it, first, 0, stream));
+    // launch-bound sweeps (small instances): the identical middle iterations are
+    // captured once into a CUDA graph and replayed
+    if (!first) {
+      int last = n_iter;                 // iterations [k, last) are identical
+      if (schedule == 2) last = light ? n_iter - 1 : k;
+      const int count = last - k;
+      if (count >= kGraphMinIters && graph_eligible(sw)) {
+        int rc_g = run_graph(sw, light, count, st);
+        if (rc_g == TRB_OK) {
+          k += count;
+          continue;
+        }
+        if (rc_g != TRB_ERR_UNSUPPORTED) return rc_g;  // else: fall through to plain launches
       }
     }
-    TRB_TRY(trb_sweep_stage(sw, TRB_STAGE_RESCALE_FWD, it, first, 0, stream));
-    if (!light) TRB_TRY(trb_sweep_stage(sw, TRB_STAGE_EXPAND_X, it, first, 0, stream));
-    TRB_TRY(trb_sweep_stage(sw, light ? TRB_STAGE_Z_UPDATE_LIGHT : TRB_STAGE_Z_UPDATE, it, first, 0,
-                            stream));
-    TRB_TRY(trb_sweep_stage(sw, schedule ? TRB_STAGE_TX_RECUR : TRB_STAGE_PROJECT_X, it, first, 0,
-                            stream));
-    TRB_TRY(trb_sweep_stage(sw, TRB_STAGE_RESCALE_BWD, it, first, 0, stream));
-    TRB_TRY(trb_sweep_stage(sw, TRB_STAGE_EXPAND_Z, it, first, 0, stream));
-    TRB_TRY(trb_sweep_stage(sw, TRB_STAGE_X_UPDATE, it, first, 0, stream));
-    TRB_TRY(trb_sweep_stage(sw, TRB_STAGE_SNAPSHOT, it, first, 0, stream));
+    TRB_TRY(enqueue_iteration(sw, it0 + k, first, fresh, light, st));
+    ++k;
   }
   return TRB_OK;
 }
