@@ -207,9 +207,10 @@ int trb_lin_rescale(int dir, int B, int R, int Nz, int Nx, int rank, int null_sp
  * CUDA IPC handle), the caller all-gathers the handles by any out-of-band means
  * (torch.distributed in tramp_b200) and passes the nranks*64 bytes to
  * trb_comm_connect, which maps every peer's buffer.  Inside the sweep a rank
- * writes its partial expansion into its own buffer, publishes a sequence number
- * into every peer's flag array, and the consumer kernel adds the peers' vectors
- * with loads over NVLink, in rank order (bit-identical on all ranks).
+ * pushes its partial expansion into its slot of every rank's buffer (posted
+ * stores over NVLink from the slot-reduction kernel), publishes a sequence number
+ * into every rank's flag array, and the consumer kernel adds the ranks' vectors
+ * from its own memory, in rank order (bit-identical on all ranks).
  * trb_comm_all_reduce exposes the same protocol as a stand-alone sum; every rank
  * must issue the same sequence of exchanges.  timeout_flag (nullable, device
  * int) is set to 1 if a peer did not publish within ~1 s. */

@@ -31,7 +31,10 @@ rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_S
 torch.cuda.set_device(local)
 dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 t0 = time.time()
-r0, r1 = instance_shard(R, rank, world); Rg = r1 - r0
+# rank g owns the singular triplets g, g + world, g + 2 world, ...: every shard then sees
+# the same spectrum distribution (a contiguous block would give rank 0 all the large ones,
+# and the isotropic EP variances would be inconsistent across the blocks)
+idx = np.arange(rank, R, world); Rg = idx.size
 gen = torch.Generator(device="cuda"); gen.manual_seed(100 + rank)
 ldn, ldm = ops.pad_ld(N), ops.pad_ld(M)
 
@@ -48,7 +51,7 @@ def block_rows(Rg, n, ld, rank, world):
 Vt = block_rows(Rg, N, ldn, rank, world)
 Ut = block_rows(Rg, M, ldm, rank, world)
 s_full = synthetic.gaussian_singular_values(1, M, N, seed=5, workers=1)[0]     # same on every rank
-s_loc = torch.as_tensor(s_full[r0:r1].copy(), device="cuda")[None]
+s_loc = torch.as_tensor(s_full[idx].copy(), device="cuda")[None]
 g2 = torch.Generator(device="cuda"); g2.manual_seed(7)                         # same on every rank
 x = torch.randn(N, dtype=torch.float64, device="cuda", generator=g2)
 x = x * (torch.rand(N, dtype=torch.float64, device="cuda", generator=g2) < rho)

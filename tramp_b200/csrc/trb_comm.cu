@@ -2,16 +2,17 @@
 // config 5): one process per GPU, every rank owns a block of singular triplets.
 // The two expansions of an iteration are partial sums over the ranks.  Instead
 // of a library all-reduce between two kernels, each rank
-//   1. reduces its per-CTA slots straight into a buffer that every peer has
-//      mapped (CUDA IPC over NVLink / NVSwitch),
+//   1. reduces its per-CTA slots and, in the same grid-wide kernel, PUSHES the
+//      reduced vector into slot `rank` of every peer's exchange buffer (posted
+//      stores over NVLink / NVSwitch on pointers mapped with CUDA IPC; a push
+//      has no round trip, unlike a pull),
 //   2. publishes a sequence number into every peer's flag array
 //      (st.release.sys), and
 //   3. the CONSUMER kernel (k_z_update / k_x_update, trb_sweep.cu) waits for the
-//      flags (ld.acquire.sys) and adds the peers' vectors itself, in rank
-//      order, with plain loads on the mapped pointers -- the transfer overlaps
-//      the update arithmetic, every rank gets bit-identical sums, and there is
-//      no separate all-reduce pass over HBM.
-// Buffers are double buffered by the parity of the exchange counter: a rank
+//      flags (ld.acquire.sys) and adds the ranks' vectors itself, in rank order,
+//      from its own memory -- every rank gets bit-identical sums, and there is no
+//      separate all-reduce kernel nor a reduced copy written back to HBM.
+// Slots are double buffered by the parity of the exchange counter: a rank
 // rewrites parity p two exchanges later, by which time every peer has published
 // (hence finished reading) the exchange in between.
 #include "trb_common.cuh"
@@ -32,7 +33,13 @@ namespace {
 
 constexpr size_t kFlagBytes = 256;  // TRB_MAX_RANKS x u64, padded
 
-size_t comm_bytes(size_t vec_doubles) { return kFlagBytes + 2 * vec_doubles * sizeof(double); }
+// layout of one rank's buffer: flags | data[parity 0..1][source rank 0..TRB_MAX_RANKS-1][vec]
+size_t comm_bytes(size_t vec_doubles) {
+  return kFlagBytes + 2 * TRB_MAX_RANKS * vec_doubles * sizeof(double);
+}
+double* slot_ptr(unsigned char* base, size_t vec, unsigned long long parity, int src_rank) {
+  return reinterpret_cast<double*>(base + kFlagBytes) + (parity * TRB_MAX_RANKS + src_rank) * vec;
+}
 
 __global__ void k_comm_signal(trb_peers peers, int rank) {
   const int p = threadIdx.x;
@@ -100,9 +107,34 @@ extern "C" int trb_comm_destroy(trb_comm* c) {
   return TRB_OK;
 }
 
-// this rank's exchange vector for the NEXT publish
-double* trb_comm_local_vector(trb_comm* c) {
-  return reinterpret_cast<double*>(c->base + kFlagBytes) + (c->seq & 1) * c->vec_doubles;
+// where this rank's vector of the NEXT exchange goes: its slot in every rank's buffer
+void trb_comm_push_targets(trb_comm* c, trb_push* push) {
+  push->n = c->nranks;
+  push->counter = nullptr;
+  push->seq = 0;
+  push->rank = c->rank;
+  for (int r = 0; r < c->nranks; ++r) {
+    push->dst[r] = slot_ptr(c->peer_base[r], c->vec_doubles, c->seq & 1, c->rank);
+    push->flags_of[r] = reinterpret_cast<unsigned long long*>(c->peer_base[r]);
+  }
+}
+
+// One exchange whose pushing kernel also publishes: fills `push` (targets, flags,
+// sequence number, arrival counter) and records the consumer's handles (trb_comm_last).
+void trb_comm_begin_exchange(trb_comm* c, trb_push* push) {
+  trb_comm_push_targets(c, push);
+  const unsigned long long parity = c->seq & 1;
+  c->seq += 1;
+  push->seq = c->seq;
+  push->counter = reinterpret_cast<unsigned int*>(c->base + kFlagBytes - 16);  // inside the flag block
+  trb_peers& p = c->last;
+  p.n = c->nranks;
+  p.seq = c->seq;
+  for (int r = 0; r < c->nranks; ++r) {
+    p.data[r] = slot_ptr(c->base, c->vec_doubles, parity, r);
+    p.flags_of[r] = reinterpret_cast<unsigned long long*>(c->peer_base[r]);
+  }
+  p.my_flags = reinterpret_cast<const unsigned long long*>(c->base);
 }
 
 size_t trb_comm_capacity(const trb_comm* c) { return c->vec_doubles; }
@@ -115,8 +147,7 @@ int trb_comm_publish(trb_comm* c, trb_peers* peers, cudaStream_t st) {
   peers->n = c->nranks;
   peers->seq = c->seq;
   for (int r = 0; r < c->nranks; ++r) {
-    peers->data[r] =
-        reinterpret_cast<const double*>(c->peer_base[r] + kFlagBytes) + parity * c->vec_doubles;
+    peers->data[r] = slot_ptr(c->base, c->vec_doubles, parity, r);  // local: rank r pushed it here
     peers->flags_of[r] = reinterpret_cast<unsigned long long*>(c->peer_base[r]);
   }
   peers->my_flags = reinterpret_cast<const unsigned long long*>(c->base);
@@ -133,9 +164,11 @@ const trb_peers* trb_comm_last(const trb_comm* c) { return &c->last; }
 // protocol (used by the tests and by callers outside the sweep).
 namespace {
 __global__ void __launch_bounds__(256)
-k_comm_copy_in(const double* __restrict__ src, double* __restrict__ dst, size_t n) {
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
-    dst[i] = src[i];
+k_comm_push(const double* __restrict__ src, trb_push push, size_t n) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const double v = src[i];
+    for (int r = 0; r < push.n; ++r) push.dst[r][i] = v;
+  }
 }
 __global__ void __launch_bounds__(256)
 k_comm_sum_out(trb_peers peers, double* __restrict__ out, size_t n, int* timeout_flag) {
@@ -152,8 +185,10 @@ extern "C" int trb_comm_all_reduce(trb_comm* c, double* vec, size_t n, int* time
   int blocks = (int)((n + 1023) / 1024);
   if (blocks > 4 * trb_sm_count_cached()) blocks = 4 * trb_sm_count_cached();
   {
+    trb_push push;
+    trb_comm_push_targets(c, &push);
     trb_launch_scope scope_(0, st);
-    k_comm_copy_in<<<blocks, 256, 0, st>>>(vec, trb_comm_local_vector(c), n);
+    k_comm_push<<<blocks, 256, 0, st>>>(vec, push, n);
   }
   trb_peers peers;
   int rc = trb_comm_publish(c, &peers, st);

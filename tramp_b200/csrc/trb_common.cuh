@@ -240,13 +240,25 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
 struct trb_peers {
   int n;                                          // ranks; 0 = not sharded
   unsigned long long seq;                         // exchange the consumer waits for
-  const double* data[TRB_MAX_RANKS];              // every rank's vector of this exchange
+  const double* data[TRB_MAX_RANKS];              // every rank's vector of this exchange, in LOCAL memory
   unsigned long long* flags_of[TRB_MAX_RANKS];    // every rank's flag array (publish side)
   const unsigned long long* my_flags;             // this rank's flag array (wait side)
 };
-double* trb_comm_local_vector(trb_comm* c);
+struct trb_push {
+  int n;
+  double* dst[TRB_MAX_RANKS];                     // this rank's slot in every rank's buffer
+  // publish from the pushing kernel itself (its last CTA), saving a launch: the
+  // sequence number goes to flags_of[r][rank]; counter is a zeroed device int
+  unsigned long long* flags_of[TRB_MAX_RANKS];
+  unsigned long long seq;
+  int rank;
+  unsigned int* counter;                          // NULL: the caller publishes separately
+};
+void trb_comm_push_targets(trb_comm* c, trb_push* push);
 size_t trb_comm_capacity(const trb_comm* c);
 int trb_comm_publish(trb_comm* c, trb_peers* peers, cudaStream_t st);
+// like trb_comm_push_targets + trb_comm_publish, but the pushing kernel publishes (no signal launch)
+void trb_comm_begin_exchange(trb_comm* c, trb_push* push);
 const trb_peers* trb_comm_last(const trb_comm* c);
 
 namespace trb {
@@ -274,14 +286,11 @@ __device__ __forceinline__ bool peers_wait(const trb_peers& p) {
   __syncthreads();
   return peers_ok != 0;
 }
-// sum over the ranks, in rank order, of element i of the exchanged vectors
+// sum over the ranks, in rank order, of element i of the exchanged vectors (the
+// peers wrote them into this rank's memory; L2 is the point of coherence)
 __device__ __forceinline__ double peers_sum(const trb_peers& p, size_t i) {
   double s = 0.0;
-  for (int r = 0; r < p.n; ++r) {
-    double v;
-    asm volatile("ld.volatile.global.f64 %0, [%1];" : "=d"(v) : "l"(p.data[r] + i) : "memory");
-    s += v;
-  }
+  for (int r = 0; r < p.n; ++r) s += __ldcg(p.data[r] + i);
   return s;
 }
 
@@ -296,15 +305,21 @@ __host__ __device__ __forceinline__ int64_t part_owner(int64_t g, int64_t T, int
 
 }  // namespace trb
 
-// Number of CTAs (a thread-block cluster, <= 8 = the portable maximum) that share
+// Number of CTAs (a thread-block cluster; 8 is the portable maximum, 16 is used for
+// a very large single instance) that share
 // one instance in the per-instance update kernels: 1 when the batch alone fills
 // the GPU, more for a few large instances (BASELINE config 5: B = 1, N = 65536).
 int trb_cluster_size(int B, int n);
 
-// kernel<<<(C, B), threads, 0, st>>> with cluster dimension (C, 1, 1)
+// opt a kernel into non-portable (16-CTA) clusters, once; false if the device refuses
+bool trb_allow_big_cluster(const void* kernel);
+
+// kernel<<<(C, B), threads, 0, st>>> with cluster dimension (C, 1, 1).  C = 16 is
+// the non-portable maximum: opted into per kernel, falling back to 8 if refused.
 template <typename... KArgs, typename... Args>
 cudaError_t trb_launch_cluster(void (*kernel)(KArgs...), int C, int B, int threads, cudaStream_t st,
                                Args... args) {
+  if (C > 8 && !trb_allow_big_cluster(reinterpret_cast<const void*>(kernel))) C = 8;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(C, B, 1);
   cfg.blockDim = dim3(threads, 1, 1);
@@ -317,7 +332,14 @@ cudaError_t trb_launch_cluster(void (*kernel)(KArgs...), int C, int B, int threa
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+  if (e != cudaSuccess && C > 8) {  // the device refused a 16-CTA cluster
+    cudaGetLastError();
+    cfg.gridDim = dim3(8, B, 1);
+    attr[0].val.clusterDim.x = 8;
+    e = cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+  }
+  return e;
 }
 
 // Launch geometry shared by trb_lin_expand and the kernels that reduce its slots.

@@ -102,12 +102,29 @@ extern "C" size_t trb_sizeof_factor(void) { return sizeof(trb_factor); }
 extern "C" size_t trb_sizeof_sweep(void) { return sizeof(trb_sweep); }
 extern "C" int trb_device_sm_count(void) { return trb_sm_count_cached(); }
 
+bool trb_allow_big_cluster(const void* kernel) {
+  static const void* known[16];
+  static bool ok[16];
+  static int count = 0;
+  for (int i = 0; i < count; ++i)
+    if (known[i] == kernel) return ok[i];
+  const bool allowed =
+      cudaFuncSetAttribute(kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess;
+  cudaGetLastError();
+  if (count < 16) {
+    known[count] = kernel;
+    ok[count] = allowed;
+    ++count;
+  }
+  return allowed;
+}
+
 int trb_cluster_size(int B, int n) {
   int sm = trb_sm_count_cached();
   if (sm <= 0) sm = 1;
   int c = 1;
   // double while the batch leaves SMs idle and every CTA keeps >= 2048 elements
-  while (c < 8 && (long long)B * c * 2 <= sm && n / (c * 2) >= 2048) c *= 2;
+  while (c < 16 && (long long)B * c * 2 <= sm && n / (c * 2) >= 2048) c *= 2;
   return c;
 }
 

@@ -191,10 +191,11 @@ k_gemv_tma(const double* __restrict__ A, int64_t strideA, int R, int n, int ld, 
            const double* __restrict__ vec, int ldvec,  // project: input vector; expand: coef [B,R]
            double* __restrict__ out, int nslots,       // project: t [B,R]; expand: part
            const int* __restrict__ active, int nstages, int stage_doubles,
-           int row_stride,   // doubles between consecutive rows of A (>= ld; == ld unless this
-                             // launch handles one column panel of a wider operator, then RC == 1)
+           int row_stride,   // doubles between consecutive rows of A (>= ld)
            int out_ld,       // expand: leading dimension of `part`
-           int accumulate) { // project: add to t instead of overwriting (panels after the first)
+           int npanels,      // > 1: A is npanels column panels of `ld` doubles (the last one may be
+                             // narrower: full_ld, full_n); every CTA walks its rows once per panel
+           int full_ld, int full_n) {
   constexpr int RC = TmaCfg<NB>::RC;
   extern __shared__ __align__(128) double ring[];  // nstages * stage_doubles
   __shared__ __align__(8) uint64_t full_bar[kMaxStages];
@@ -212,9 +213,9 @@ k_gemv_tma(const double* __restrict__ A, int64_t strideA, int R, int n, int ld, 
   __syncthreads();
 
   const int64_t T = (int64_t)B * R, G = gridDim.x;
-  int64_t g = part_begin(blockIdx.x, T, G);
+  const int64_t g0 = part_begin(blockIdx.x, T, G);
   const int64_t g1 = part_begin(blockIdx.x + 1, T, G);
-  const int npair = ld >> 1;
+  const int panel_ld = ld;
   Segment s;
   int stage = 0;
   uint32_t phase = 0;
@@ -222,19 +223,24 @@ k_gemv_tma(const double* __restrict__ A, int64_t strideA, int R, int n, int ld, 
   if (warp == kConsumers / 32) {
     // ------------------------------------------------------------ producer
     if (lane == 0) {
-      while (next_segment(g, g1, R, s)) {
-        if (active && !active[s.b]) continue;
-        const double* Ab = A + (size_t)s.b * strideA;
-        for (int i = s.i0; i < s.i1; i += RC) {
-          const int rows = (s.i1 - i < RC) ? (s.i1 - i) : RC;
-          const uint32_t bytes = (uint32_t)rows * (uint32_t)ld * 8u;
-          mbar_wait(&empty_bar[stage], phase ^ 1u);
-          mbar_arrive_expect_tx(&full_bar[stage], bytes);
-          bulk_g2s(ring + (size_t)stage * stage_doubles, Ab + (size_t)i * row_stride, bytes,
-                   &full_bar[stage]);
-          if (++stage == nstages) {
-            stage = 0;
-            phase ^= 1u;
+      for (int pq = 0; pq < npanels; ++pq) {
+        const int c0 = pq * panel_ld;
+        const int ldq = (npanels > 1 && full_ld - c0 < panel_ld) ? full_ld - c0 : panel_ld;
+        int64_t g = g0;
+        while (next_segment(g, g1, R, s)) {
+          if (active && !active[s.b]) continue;
+          const double* Ab = A + (size_t)s.b * strideA + c0;
+          for (int i = s.i0; i < s.i1; i += RC) {
+            const int rows = (s.i1 - i < RC) ? (s.i1 - i) : RC;
+            const uint32_t bytes = (uint32_t)rows * (uint32_t)ldq * 8u;
+            mbar_wait(&empty_bar[stage], phase ^ 1u);
+            mbar_arrive_expect_tx(&full_bar[stage], bytes);
+            bulk_g2s(ring + (size_t)stage * stage_doubles, Ab + (size_t)i * row_stride, bytes,
+                     &full_bar[stage]);
+            if (++stage == nstages) {
+              stage = 0;
+              phase ^= 1u;
+            }
           }
         }
       }
@@ -244,6 +250,16 @@ k_gemv_tma(const double* __restrict__ A, int64_t strideA, int R, int n, int ld, 
 
   // -------------------------------------------------------------- consumers
   int red_buf = 0;
+  for (int pq = 0; pq < npanels; ++pq) {
+  const int c0 = pq * panel_ld;
+  if (npanels > 1) {  // this panel's extent
+    ld = (full_ld - c0 < panel_ld) ? full_ld - c0 : panel_ld;
+    n = (full_n - c0 < ld) ? full_n - c0 : ld;
+    if (n < 0) n = 0;
+  }
+  const int npair = ld >> 1;
+  const int accumulate = pq > 0;  // project: later panels add to t
+  int64_t g = g0;
   while (next_segment(g, g1, R, s)) {
     if (active && !active[s.b]) continue;
     if constexpr (!EXPAND) {
@@ -252,7 +268,7 @@ k_gemv_tma(const double* __restrict__ A, int64_t strideA, int R, int n, int ld, 
 #pragma unroll
       for (int k = 0; k < NB; ++k) {
         const int c = 2 * (tid + k * kConsumers);
-        const double* vp = vec + (size_t)s.b * ldvec;
+        const double* vp = vec + (size_t)s.b * ldvec + c0;
         x[k].x = (c < n) ? vp[c] : 0.0;
         x[k].y = (c + 1 < n) ? vp[c + 1] : 0.0;
       }
@@ -341,7 +357,7 @@ k_gemv_tma(const double* __restrict__ A, int64_t strideA, int R, int n, int ld, 
         }
       }
       const int slot = (int)(blockIdx.x - part_owner((int64_t)s.b * R, T, G));
-      double* o = out + ((size_t)s.b * nslots + slot) * out_ld;
+      double* o = out + ((size_t)s.b * nslots + slot) * out_ld + c0;
 #pragma unroll
       for (int k = 0; k < NB; ++k) {
         const int p = tid + k * kConsumers;
@@ -349,13 +365,15 @@ k_gemv_tma(const double* __restrict__ A, int64_t strideA, int R, int n, int ld, 
       }
     }
   }
+  }  // panels
 }
 
 // ---------------------------------------------------------------- small ops
 __global__ void __launch_bounds__(256)
 k_reduce_slots(int R, int n, int ld, int B, int G, int nslots, const double* part,
                const double* __restrict__ add, const double* __restrict__ add_div,
-               double* out, size_t out_stride) {  // out may alias slot 0 of part (in-place)
+               double* out, size_t out_stride,  // out may alias slot 0 of part (in-place)
+               trb_push push) {                 // push.n > 0: store to every rank's buffer instead
   const int b = blockIdx.y;  // grid (chunks, B)
   const int64_t T = (int64_t)B * R;
   const int kf = (int)part_owner((int64_t)b * R, T, G);
@@ -364,14 +382,45 @@ k_reduce_slots(int R, int n, int ld, int B, int G, int nslots, const double* par
   const double div = add ? add_div[b] : 1.0;
   for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
     double v = 0.0;
-    for (int sl = 0; sl < ns; ++sl) v += part[((size_t)b * nslots + sl) * ld + j];
+    const double* pj = part + (size_t)b * nslots * ld + j;
+    int sl = 0;
+    for (; sl + 8 <= ns; sl += 8) {  // eight loads in flight, added in slot order
+      double t[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) t[u] = pj[(size_t)(sl + u) * ld];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) v += t[u];
+    }
+    for (; sl < ns; ++sl) v += pj[(size_t)sl * ld];
     if (add) v = add[(size_t)b * ld + j] / div + v;
-    out[(size_t)b * out_stride + j] = v;
+    if (push.n > 0) {
+      for (int r = 0; r < push.n; ++r) push.dst[r][(size_t)b * out_stride + j] = v;
+    } else {
+      out[(size_t)b * out_stride + j] = v;
+    }
+  }
+  if (push.n > 0 && push.counter) {
+    // the last CTA to finish publishes the exchange to every rank (trb_comm.cu):
+    // CTA barrier, then one system-scope fence (cumulative over the pushes the barrier
+    // ordered before it), then the arrival count
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      __threadfence_system();
+      const unsigned int total = gridDim.x * gridDim.y;
+      if (atomicAdd(push.counter, 1u) == total - 1) {
+        *push.counter = 0;
+        __threadfence_system();
+        for (int r = 0; r < push.n; ++r)
+          asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(push.flags_of[r] + push.rank),
+                       "l"(push.seq)
+                       : "memory");
+      }
+    }
   }
 }
 
 // linear_channel.py:58-67 (compute_n_eff), :74 (resolvent), :91-105 (variances)
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(1024)
 k_lin_rescale(int dir, int R, int Nz, int Nx, int rank, int null_space_flag,
               const double* __restrict__ s,
               const double* __restrict__ s2, int64_t stride_s, const double* __restrict__ az_arr,
@@ -468,7 +517,7 @@ bool plan_tma(int ld, TmaPlan& p) {
 template <int NB, bool EXPAND>
 int launch_tma(const TmaPlan& p, int G, const double* A, int64_t strideA, int R, int n, int ld,
                int B, const double* vec, int ldvec, double* out, int nslots, const int* active,
-               cudaStream_t st, int row_stride, int out_ld, int accumulate) {
+               cudaStream_t st, int row_stride, int out_ld, int npanels, int full_ld, int full_n) {
   auto kern = k_gemv_tma<NB, EXPAND>;
   static bool configured = false;  // per instantiation
   if (!configured) {
@@ -479,18 +528,19 @@ int launch_tma(const TmaPlan& p, int G, const double* A, int64_t strideA, int R,
     configured = true;
   }
   kern<<<G, kTmaThreads, p.smem, st>>>(A, strideA, R, n, ld, B, vec, ldvec, out, nslots, active,
-                                       p.stages, p.stage_doubles, row_stride, out_ld, accumulate);
+                                       p.stages, p.stage_doubles, row_stride, out_ld, npanels, full_ld,
+                                       full_n);
   return TRB_OK;
 }
 
 template <bool EXPAND>
 int dispatch_tma(const TmaPlan& p, int G, const double* A, int64_t strideA, int R, int n, int ld,
                  int B, const double* vec, int ldvec, double* out, int nslots, const int* active,
-                 cudaStream_t st, int row_stride, int out_ld, int accumulate) {
+                 cudaStream_t st, int row_stride, int out_ld, int npanels, int full_ld, int full_n) {
 #define TRB_TMA_CASE(NB_)                                                                          \
   case NB_:                                                                                        \
     return launch_tma<NB_, EXPAND>(p, G, A, strideA, R, n, ld, B, vec, ldvec, out, nslots, active, \
-                                   st, row_stride, out_ld, accumulate);
+                                   st, row_stride, out_ld, npanels, full_ld, full_n);
   switch (p.nb) {
     TRB_TMA_CASE(1)
     TRB_TMA_CASE(2)
@@ -566,22 +616,17 @@ extern "C" int trb_lin_project(const double* A, int64_t strideA, int R, int n, i
   if (impl == 0) impl = 2;
   trb_launch_scope scope_(1, st);
   if (impl == 2 && !tma_ok) {
+    // rows wider than one ring stage: one launch, every CTA walks its rows once per column panel
     const Panels pan = plan_panels(ld);
-    for (int q = 0; q < pan.count; ++q) {
-      const int c0 = q * pan.width;
-      const int w = (ld - c0 < pan.width) ? ld - c0 : pan.width;
-      const int nq = (n - c0 < w) ? n - c0 : w;
-      if (nq <= 0) break;
-      TmaPlan pq;
-      if (!plan_tma(w, pq) || (pq.nb < 8 && w != ld))
-        return trb_set_error(TRB_ERR_UNSUPPORTED, "trb_lin_project: cannot panel ld=%d", ld);
-      rc = dispatch_tma<false>(pq, geo.G, A + c0, strideA, R, nq, w, B, vec + c0, ldvec, t, 0,
-                               active, st, ld, 0, q > 0);
-      if (rc) return rc;
-    }
+    TmaPlan pq;
+    if (!plan_tma(pan.width, pq) || pq.nb < 8)
+      return trb_set_error(TRB_ERR_UNSUPPORTED, "trb_lin_project: cannot panel ld=%d", ld);
+    rc = dispatch_tma<false>(pq, geo.G, A, strideA, R, n, pan.width, B, vec, ldvec, t, 0, active, st,
+                             ld, 0, pan.count, ld, n);
+    if (rc) return rc;
   } else if (impl == 2) {
     rc = dispatch_tma<false>(p, geo.G, A, strideA, R, n, ld, B, vec, ldvec, t, 0, active, st, ld, 0,
-                             0);
+                             1, ld, n);
     if (rc) return rc;
   } else {
     const size_t smem = (size_t)ld * 8;
@@ -612,20 +657,15 @@ extern "C" int trb_lin_expand(const double* A, int64_t strideA, int R, int n, in
   trb_launch_scope scope_(1, st);
   if (impl == 2 && !tma_ok) {
     const Panels pan = plan_panels(ld);
-    for (int q = 0; q < pan.count; ++q) {
-      const int c0 = q * pan.width;
-      const int w = (ld - c0 < pan.width) ? ld - c0 : pan.width;
-      if (w <= 0) break;
-      TmaPlan pq;
-      if (!plan_tma(w, pq) || (pq.nb < 8 && w != ld))
-        return trb_set_error(TRB_ERR_UNSUPPORTED, "trb_lin_expand: cannot panel ld=%d", ld);
-      rc = dispatch_tma<true>(pq, geo.G, A + c0, strideA, R, w, w, B, coef, 0, part + c0,
-                              geo.nslots, active, st, ld, ld, 0);
-      if (rc) return rc;
-    }
+    TmaPlan pq;
+    if (!plan_tma(pan.width, pq) || pq.nb < 8)
+      return trb_set_error(TRB_ERR_UNSUPPORTED, "trb_lin_expand: cannot panel ld=%d", ld);
+    rc = dispatch_tma<true>(pq, geo.G, A, strideA, R, n, pan.width, B, coef, 0, part, geo.nslots,
+                            active, st, ld, ld, pan.count, ld, ld);
+    if (rc) return rc;
   } else if (impl == 2) {
     rc = dispatch_tma<true>(p, geo.G, A, strideA, R, n, ld, B, coef, 0, part, geo.nslots, active, st,
-                            ld, ld, 0);
+                            ld, ld, 1, ld, n);
     if (rc) return rc;
   } else {
     const int nb = pick_nb(ld, kLdgThreads, 8);
@@ -644,14 +684,16 @@ extern "C" int trb_lin_expand(const double* A, int64_t strideA, int R, int n, in
 
 static int reduce_slots_launch(int B, int R, int n, int ld, const double* part, const double* add,
                                const double* add_div, double* out, size_t out_stride,
-                               cudaStream_t st) {
+                               cudaStream_t st, const trb_push* push = nullptr) {
   const trb_expand_geom geo = trb_expand_geometry(B, R);
   trb_launch_scope scope_(0, st);
-  int chunks = (n + 1023) / 1024;  // >= 4 columns per thread, enough CTAs to fill the GPU
-  const int cap = (4 * trb_sm_count_cached() + B - 1) / B;
+  int chunks = (n + 255) / 256;  // one column per thread while that still fits ~8 CTAs per SM
+  const int cap = (8 * trb_sm_count_cached() + B - 1) / B;
   if (chunks > cap) chunks = cap < 1 ? 1 : cap;
+  trb_push none;
+  none.n = 0;
   k_reduce_slots<<<dim3(chunks, B), 256, 0, st>>>(R, n, ld, B, geo.G, geo.nslots, part, add, add_div,
-                                                 out, out_stride);
+                                                 out, out_stride, push ? *push : none);
   TRB_CHECK_LAUNCH();
   return TRB_OK;
 }
@@ -664,9 +706,11 @@ int trb_reduce_slots_inplace(int B, int R, int n, int ld, double* part, void* st
                              (cudaStream_t)stream);
 }
 
-// out[b, :] (leading dimension ld) = sum of the slots of instance b
-int trb_reduce_slots_to(int B, int R, int n, int ld, const double* part, double* out, void* stream) {
-  return reduce_slots_launch(B, R, n, ld, part, nullptr, nullptr, out, (size_t)ld, (cudaStream_t)stream);
+// the sum of the slots of instance b goes to push->dst[r][b, :] (leading dimension ld) for every rank r
+int trb_reduce_slots_push(int B, int R, int n, int ld, const double* part, const trb_push* push,
+                          void* stream) {
+  return reduce_slots_launch(B, R, n, ld, part, nullptr, nullptr, nullptr, (size_t)ld,
+                             (cudaStream_t)stream, push);
 }
 
 extern "C" int trb_lin_reduce_slots(int B, int R, int n, int ld, const double* part,
@@ -688,7 +732,9 @@ extern "C" int trb_lin_rescale(int dir, int B, int R, int Nz, int Nx, int rank, 
   TRB_CHECK_ARG(dir == 0 || dir == 1, "dir must be 0 or 1");
   TRB_CHECK_ARG(B > 0 && R > 0 && R <= Nz && R <= Nx && rank >= 0 && rank <= R, "bad shape");
   trb_launch_scope scope_(0, (cudaStream_t)stream);
-  cudaError_t le = trb_launch_cluster(k_lin_rescale, trb_cluster_size(B, R), B, 256,
+  // division-heavy FP64 per element: a large single spectrum gets the widest CTAs
+  const int rs_threads = (R >= 8192 && B * 8 <= trb_sm_count_cached()) ? 1024 : 256;
+  cudaError_t le = trb_launch_cluster(k_lin_rescale, trb_cluster_size(B, R), B, rs_threads,
                                       (cudaStream_t)stream, dir, R, Nz, Nx, rank, null_space, s, s2,
                                       stride_s, az, ax, tz, tx, coef, v, active);
   if (le != cudaSuccess)

@@ -357,16 +357,17 @@ static int check_sweep(const trb_sweep* sw) {
   return TRB_OK;
 }
 
-// Row-sharded operator: reduce this rank's slots straight into its exchange buffer
-// and publish it; the following update kernel adds the ranks' vectors (trb_comm.cu).
-int trb_reduce_slots_to(int B, int R, int n, int ld, const double* part, double* out, void* stream);
+// Row-sharded operator: reduce this rank's slots and push the result into every
+// rank's exchange buffer, then publish; the following update kernel adds the
+// ranks' vectors from its own memory (trb_comm.cu).
+int trb_reduce_slots_push(int B, int R, int n, int ld, const double* part, const trb_push* push,
+                          void* stream);
 static int exchange_expansion(const trb_sweep* sw, int n, int ld, cudaStream_t st) {
   trb_comm* comm = sw->comm;
   TRB_CHECK_ARG((size_t)sw->B * ld <= trb_comm_capacity(comm), "exchange buffer too small");
-  int rc = trb_reduce_slots_to(sw->B, sw->R, n, ld, sw->part, trb_comm_local_vector(comm), st);
-  if (rc) return rc;
-  trb_peers peers;
-  return trb_comm_publish(comm, &peers, st);
+  trb_push push;
+  trb_comm_begin_exchange(comm, &push);  // the reduction kernel's last CTA publishes
+  return trb_reduce_slots_push(sw->B, sw->R, n, ld, sw->part, &push, st);
 }
 
 // One stage of the iteration (see the header comment of this file).  `first`:
@@ -522,7 +523,10 @@ case TRB_STAGE_EXPAND_Z:  // P4: rz = [b2/a2 +] V_R coef
       if (!sw->snap_edge_a) return TRB_OK;
       trb_launch_scope scope_(0, st);
       const int big = sw->N > sw->M ? sw->N : sw->M;
-      k_snapshot<<<dim3(trb_cluster_size(B, big), B), 256, 0, st>>>(*sw);
+      int chunks = (big + 511) / 512;  // plain copies: spread a large instance over many CTAs
+      const int cap = (4 * trb_device_sm_count() + B - 1) / B;
+      if (chunks > cap) chunks = cap < 1 ? 1 : cap;
+      k_snapshot<<<dim3(chunks, B), 256, 0, st>>>(*sw);
       k_snapshot_mark<<<(B + 255) / 256, 256, 0, st>>>(*sw);
       TRB_CHECK_LAUNCH();
       return TRB_OK;
