@@ -38,7 +38,8 @@ res = dict(N=N, R=R, B=B, reps=reps)
 _lib.load().trb_gemm_set_variant(1)
 res["project_dmma_cpasync"] = timed(lambda: ops.lin_project_gemm(A, R, N, X, B, out=T))
 res["expand_dmma_cpasync"] = timed(lambda: ops.lin_expand_gemm(A, R, N, Cf, B, out=O))
-for v, nm in ((2, "diag_noload"), (4, "loadonly")):
+probes = () if os.environ.get("BENCH_GEMM_NO_PROBES") else ((2, "diag_noload"), (4, "loadonly"))
+for v, nm in probes:
     _lib.load().trb_gemm_set_variant(v)
     res["project_dmma_" + nm] = timed(lambda: ops.lin_project_gemm(A, R, N, X, B, out=T))
     res["expand_dmma_" + nm] = timed(lambda: ops.lin_expand_gemm(A, R, N, Cf, B, out=O))
