@@ -336,6 +336,99 @@ int trb_sweep_run(const trb_sweep* sw, int it0, int n_iter, int fresh, void* str
  * that off (default on; the environment variable TRB_CUDA_GRAPHS=0 does the same). */
 void trb_set_cuda_graphs(int enabled);
 
+/* ---- State Evolution (SE): the scalar twin of the sweep ---------------------
+ * algos/state_evolution.py:5-27 runs the SAME schedule (message_passing.py:
+ * 249-269, 330-357) on the precisions `a` alone; every factor replaces its
+ * posterior by the AVERAGE of the posterior variance over the law of its
+ * incoming beliefs ("beliefs_measure"), a Gaussian integral that the reference
+ * evaluates with scipy.integrate.quad / dblquad over [-10, 10]
+ * (utils/integration.py:13-46).  Here the integrals are fixed-node Gauss-
+ * Legendre sums evaluated by one CTA per problem, and the whole SE recursion
+ * of G independent problems (a grid of alpha / rho / noise values) runs in one
+ * launch. */
+
+/* Quadrature rule for  integral over [-10, 10] of N(t) f(m + s t) dt
+ * (utils/integration.py:25-27).  The integrands of SE have their structure (the
+ * sigmoid / tanh / erfcx transitions of the posterior moments) around one point
+ * t = c, the image of b = -b0, at a scale that shrinks like 1/sqrt(a): scipy's
+ * adaptive quad finds it by bisection; a fixed rule must be told.  The rule is a
+ * composite Gauss-Legendre rule (P panels of Q nodes; template nodes x[Q] and
+ * weights w[Q] on [-1, 1], device arrays) in the variable u of the map
+ *     t = c + kappa sinh(u),   u in [asinh((-10 - c)/kappa), asinh((10 - c)/kappa)],
+ * i.e. node spacing ~kappa at c growing in proportion to |t - c| away from it:
+ * every feature whose width is not much smaller than its distance to c is
+ * resolved, at any precision a.  The kernels compute c per integral.  The 2-D
+ * measure of AbsLikelihood (abs_likelihood.py:56-65, gaussian_measure_2d) uses
+ * the tensor rule (P2, Q2, kappa2): outer variable z centred at its kink z = 0,
+ * inner variable centred on the line b_z = 0. */
+typedef struct {
+  const double* x; const double* w; int32_t Q; int32_t P; double kappa;
+  const double* x2; const double* w2; int32_t Q2; int32_t P2; double kappa2;
+} trb_quadrature;
+
+#define TRB_MEASURE_V 0 /* average posterior variance: compute_forward_error / compute_backward_error
+                         * (priors/base_prior.py:71-74, likelihoods/base_likelihood.py:78-81) */
+#define TRB_MEASURE_A 1 /* average log-partition: compute_free_energy
+                         * (base_prior.py:82-85, base_likelihood.py:88-92) */
+/* the belief law of a likelihood needs az > 1/tau_z (sgn_likelihood.py:80-81,
+ * abs_likelihood.py:57-58 `assert mz_hat > 0`); set instead of asserting */
+#define TRB_FLAG_SE_DOMAIN 128
+
+/* out[b] = factor.beliefs_measure(a[b] [, tau[b]], f) for f = scalar variance
+ * (TRB_MEASURE_V) or scalar log-partition (TRB_MEASURE_A):
+ *   GAUSS_BERNOULLI  priors/gauss_bernoulli_prior.py:112-118
+ *   BINARY           priors/binary_prior.py:80-84
+ *   SGN              likelihoods/sgn_likelihood.py:79-92
+ *   ABS              likelihoods/abs_likelihood.py:56-65
+ *   GAUSSIAN prior / likelihood: the closed forms the reference overrides with
+ *     (gaussian_prior.py:92-95, 134-138; gaussian_likelihood.py:57-60, 129-132).
+ * factors: DEVICE array, factors[b * factor_stride] (stride 0: one factor for all).
+ * tau: [B] second moment of the factor's variable (likelihoods and the Gaussian
+ * prior's free energy need it; NULL otherwise).  flags (nullable): int[B]. */
+int trb_se_measure(const trb_factor* factors, int factor_stride, int what, int B,
+                   const double* a, const double* tau, const trb_quadrature* q,
+                   double* out, int32_t* flags, void* stream);
+
+#define TRB_SE_MARCHENKO_PASTUR 0 /* channels/linear/analytical_linear_channel.py:25-51, 68-71 +
+                                   * ensembles/marchenko_pastur_ensemble.py:40-46 */
+#define TRB_SE_SPECTRUM 1         /* channels/linear/linear_channel.py:58-67, 91-105, 119-125 */
+
+/* G independent SE problems on the chain prior -> x -> linear -> z -> likelihood,
+ * one CTA each, all iterations inside one launch.  Edge numbering as trb_sweep. */
+typedef struct {
+  int32_t G;
+  int32_t channel;             /* TRB_SE_MARCHENKO_PASTUR | TRB_SE_SPECTRUM */
+  const trb_factor* prior;     /* device [G] */
+  const trb_factor* lik;       /* device [G] */
+  const double* tau_x;         /* [G] Prior.second_moment() */
+  const double* tau_z;         /* [G] channel.second_moment(tau_x) (base_model.py:111-124) */
+  /* Marchenko-Pastur channel */
+  const double* alpha;         /* [G] Nx / Nz of the channel */
+  const double* mean_spectrum; /* [G] marchenko_pastur_ensemble.py:13 */
+  /* empirical spectrum of a LinearChannel: s2[G or 1, R] = diag(S^T S)[:R] */
+  const double* s2; int64_t stride_s2; int32_t R, Nz, Nx, rank;
+  double lin_amin, lin_amax;   /* AMIN / AMAX of the channel */
+  double damp1, damp3, damp5, damp7;
+  double* edge_a;              /* [8, G] in: initial values (initializer), out: final */
+  double* vx; double* vz;      /* [G] Variable.posterior_v (base.py:167-170) */
+  int32_t* active;             /* [G] 1 = iterate; cleared when a problem stops */
+  int32_t* flags;              /* [G] TRB_FLAG_* */
+  int32_t* n_iter;             /* [G] iterations completed (accumulates) */
+  double* rec_vx; double* rec_vz; int32_t max_records;  /* [max_records, G] or NULL */
+  /* EarlyStopping(ids, tol, min_variance, wait_increase, max_increase)
+   * (callbacks.py:192-243); enabled if es_tol >= 0.  es_vars: bit 0 = x, bit 1 = z. */
+  double es_tol, es_min_variance, es_max_increase;
+  int32_t es_wait_increase, es_vars;
+  trb_quadrature quad;
+} trb_se;
+size_t trb_sizeof_se(void);
+
+/* Run `n_iter` SE iterations of every active problem; records go to rows it0,
+ * it0+1, ...  A NaN message (message_passing.py:187-198) or a failed EarlyStopping
+ * test rolls the problem back to the end of its previous iteration
+ * (`old_message_dag`) and clears its active flag. */
+int trb_se_run(const trb_se* se, int it0, int n_iter, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -24,14 +24,23 @@ def _make_networkx_veneer():
         def node(self):
             return self._node
 
+        # networkx 3 implements nodes / edges / in_edges as cached properties that
+        # store a view object in the instance __dict__, which would shadow these
+        # methods from the second call on; drop the cached view after each use.
         def nodes(self, data=False):
-            return list(super().nodes(data=data))
+            out = list(super().nodes(data=data))
+            self.__dict__.pop("nodes", None)
+            return out
 
         def edges(self, nbunch=None, data=False):
-            return list(super().edges(nbunch, data=data))
+            out = list(super().edges(nbunch, data=data))
+            self.__dict__.pop("edges", None)
+            return out
 
         def in_edges(self, nbunch=None, data=False):
-            return list(super().in_edges(nbunch, data=data))
+            out = list(super().in_edges(nbunch, data=data))
+            self.__dict__.pop("in_edges", None)
+            return out
 
         def predecessors(self, n):
             return list(super().predecessors(n))

@@ -54,6 +54,34 @@ class TrbSweep(C.Structure):
     ]
 
 
+class TrbQuadrature(C.Structure):
+    _fields_ = [
+        ("x", C.c_void_p), ("w", C.c_void_p), ("Q", C.c_int32), ("P", C.c_int32),
+        ("kappa", C.c_double),
+        ("x2", C.c_void_p), ("w2", C.c_void_p), ("Q2", C.c_int32), ("P2", C.c_int32),
+        ("kappa2", C.c_double),
+    ]
+
+
+class TrbSe(C.Structure):
+    _fields_ = [
+        ("G", C.c_int32), ("channel", C.c_int32),
+        ("prior", C.c_void_p), ("lik", C.c_void_p),
+        ("tau_x", C.c_void_p), ("tau_z", C.c_void_p),
+        ("alpha", C.c_void_p), ("mean_spectrum", C.c_void_p),
+        ("s2", C.c_void_p), ("stride_s2", C.c_int64),
+        ("R", C.c_int32), ("Nz", C.c_int32), ("Nx", C.c_int32), ("rank", C.c_int32),
+        ("lin_amin", C.c_double), ("lin_amax", C.c_double),
+        ("damp1", C.c_double), ("damp3", C.c_double), ("damp5", C.c_double), ("damp7", C.c_double),
+        ("edge_a", C.c_void_p), ("vx", C.c_void_p), ("vz", C.c_void_p),
+        ("active", C.c_void_p), ("flags", C.c_void_p), ("n_iter", C.c_void_p),
+        ("rec_vx", C.c_void_p), ("rec_vz", C.c_void_p), ("max_records", C.c_int32),
+        ("es_tol", C.c_double), ("es_min_variance", C.c_double), ("es_max_increase", C.c_double),
+        ("es_wait_increase", C.c_int32), ("es_vars", C.c_int32),
+        ("quad", TrbQuadrature),
+    ]
+
+
 # kinds (trb_factor_kind)
 GAUSS_BERNOULLI_PRIOR, BINARY_PRIOR, GAUSSIAN_PRIOR = 0, 1, 2
 GAUSSIAN_LIKELIHOOD, SGN_LIKELIHOOD, ABS_LIKELIHOOD = 3, 4, 5
@@ -64,6 +92,9 @@ GAUSSIAN_LIKELIHOOD, SGN_LIKELIHOOD, ABS_LIKELIHOOD = 3, 4, 5
 
 FLAG_NAN_A, FLAG_NAN_B, FLAG_NEG_A, FLAG_CONVERGED, FLAG_DIVERGED, FLAG_RESTORED = 1, 2, 4, 8, 16, 32
 FLAG_COMM_TIMEOUT = 64
+FLAG_SE_DOMAIN = 128
+MEASURE_V, MEASURE_A = 0, 1
+SE_MARCHENKO_PASTUR, SE_SPECTRUM = 0, 1
 MAX_RANKS = 8
 
 _I, _L, _D, _P = C.c_int, C.c_int64, C.c_double, C.c_void_p
@@ -99,6 +130,9 @@ SIGNATURES = {
     "trb_set_cuda_graphs": (None, [_I]),
     "trb_sweep_run": (_I, [C.POINTER(TrbSweep), _I, _I, _I, _P]),
     "trb_sweep_stage": (_I, [C.POINTER(TrbSweep), _I, _I, _I, _I, _P]),
+    "trb_sizeof_se": (C.c_size_t, []),
+    "trb_se_measure": (_I, [_P, _I, _I, _I, _P, _P, C.POINTER(TrbQuadrature), _P, _P, _P]),
+    "trb_se_run": (_I, [C.POINTER(TrbSe), _I, _I, _P]),
 }
 
 _lib = None
@@ -122,7 +156,8 @@ def load():
         fn = getattr(lib, name)
         fn.restype = res
         fn.argtypes = args
-    if lib.trb_sizeof_factor() != C.sizeof(TrbFactor) or lib.trb_sizeof_sweep() != C.sizeof(TrbSweep):
+    if (lib.trb_sizeof_factor() != C.sizeof(TrbFactor) or lib.trb_sizeof_sweep() != C.sizeof(TrbSweep)
+            or lib.trb_sizeof_se() != C.sizeof(TrbSe)):
         raise TrbError("tramp_b200._lib struct layout is out of sync with include/tramp_b200.h")
     _lib = lib
     return lib

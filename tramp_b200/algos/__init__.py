@@ -1,6 +1,7 @@
-"""EP driver (reference tramp/algos/)."""
+"""EP and State-Evolution drivers (reference tramp/algos/)."""
 from .expectation_propagation import ExpectationPropagation
 from .message_passing import MessagePassing
+from .state_evolution import StateEvolution
 from .callbacks import (
     Callback, PassCallback, JoinCallback, LogProgress, TrackEvolution,
     TrackEstimate, TrackErrors, EarlyStoppingEP, EarlyStopping,

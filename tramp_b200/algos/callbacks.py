@@ -311,6 +311,55 @@ class EarlyStoppingEP(Callback):
         cfg["early_stopping"] = self
 
 
-class EarlyStopping(EarlyStoppingEP):
-    """Alias kept for import compatibility (the reference's variance-based
-    EarlyStopping, callbacks.py:192-243, is the State-Evolution stopper)."""
+class EarlyStopping(Callback):
+    """reference callbacks.py:195-243: stop when every tracked variance moved by
+    less than `tol` (absolute), or dropped below `min_variance`; a NaN variance,
+    or an increase above `max_increase` after `wait_increase` iterations,
+    restores the previous messages and stops.  This is State Evolution's default
+    stopper; inside `StateEvolution.iterate` the test runs in the kernel
+    (`trb_se_run`), for EP it is an ordinary per-iteration callback."""
+
+    def __init__(self, ids="all", tol=1e-6, min_variance=-1, wait_increase=5, max_increase=0.2):
+        self.ids = ids
+        self.tol = tol
+        self.min_variance = min_variance
+        self.wait_increase = wait_increase
+        self.max_increase = max_increase
+        self.repr_init()
+        self.old_vs = None
+
+    def __call__(self, algo, i, max_iter):
+        if (i == 0):
+            self.old_vs = None
+        variables_data = algo.get_variables_data(self.ids)
+        new_vs = [data["v"] for variable_id, data in variables_data.items()]
+        if any(v < self.min_variance for v in new_vs):
+            logger.info(f"early stopping min variance {min(new_vs)}")
+            return True
+        if any(np.isnan(v) for v in new_vs):
+            logger.warning("early stopping nan values")
+            logger.info("restoring old message dag")
+            algo.reset_message_dag(self.old_message_dag)
+            return True
+        if self.old_vs:
+            tols = [np.abs(old_v - new_v) for old_v, new_v in zip(self.old_vs, new_vs)]
+            if max(tols) < self.tol:
+                logger.info(f"early stopping all tolerances (on v) are below tol={self.tol:.2e}")
+                return True
+            increase = [new_v - old_v for old_v, new_v in zip(self.old_vs, new_vs)]
+            if i > self.wait_increase and max(increase) > self.max_increase:
+                logger.info(f"increase={max(increase)} above max_increase={self.max_increase:.2e}")
+                logger.info("restoring old message dag")
+                algo.reset_message_dag(self.old_message_dag)
+                return True
+        self.old_vs = new_vs
+        self.old_message_dag = algo.snapshot()
+
+    _var_mask = EarlyStoppingEP._var_mask
+
+    def device_replayable(self, algo):
+        # only the State-Evolution kernel implements the variance test
+        return getattr(algo, "message_keys", None) == ["a"] and self._var_mask(algo) is not None
+
+    def device_config(self, cfg):
+        cfg["early_stopping"] = self

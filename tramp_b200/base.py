@@ -90,6 +90,45 @@ class Variable(ReprMixin):
         ax, bx = self.posterior_ab(message)
         return self.compute_log_partition(ax, bx)
 
+    # ---- State Evolution: precisions only (reference base.py:109-144, 163-178, 209-233)
+    def posterior_a(self, message):
+        return sum(data["a"] for source, target, data in message)
+
+    def posterior_v(self, message):
+        return 1. / self.posterior_a(message)
+
+    def _parse_tau(self, message):
+        return message[0][2]["tau"]
+
+    def compute_mutual_information(self, ax, tau_x):
+        return 0.5 * np.log(ax * tau_x)
+
+    def compute_free_energy(self, ax, tau_x):
+        I = self.compute_mutual_information(ax, tau_x)
+        return 0.5 * ax * tau_x - I + 0.5 * np.log(2 * np.pi * tau_x / np.e)
+
+    def compute_dual_mutual_information(self, vx, tau_x):
+        return 0.5 * np.log(tau_x / vx) - 0.5
+
+    def compute_dual_free_energy(self, mx, tau_x):
+        return 0.5 * np.log(2 * np.pi * (tau_x - mx))
+
+    def free_energy(self, message):
+        return self.compute_free_energy(self.posterior_a(message), self._parse_tau(message))
+
+    def _state_evolution(self, message, incoming, outgoing):
+        a_hat = self.posterior_a(message)
+        return [(target, source, dict(a=a_hat - data["a"], direction=outgoing))
+                for source, target, data in filter_message(message, incoming)]
+
+    def forward_state_evolution(self, message):
+        """to every next factor: the total precision minus what it sent (reference base.py:209-220)."""
+        return [] if self.n_next == 0 else self._state_evolution(message, "bwd", "fwd")
+
+    def backward_state_evolution(self, message):
+        """reference base.py:222-233."""
+        return [] if self.n_prev == 0 else self._state_evolution(message, "fwd", "bwd")
+
 
 class Factor(ReprMixin):
     """reference base.py:236-365 (EP part)."""
@@ -176,6 +215,70 @@ class Factor(ReprMixin):
         if self.n_next == 0:
             return self.compute_log_partition(az, bz, self.y)
         return self.compute_log_partition(az, bz, ax, bx)
+
+
+    # ---- State Evolution (reference base.py:308-327, 377-419) -----------------
+    def _parse_message_a(self, message):
+        z_message = filter_message(message, "fwd")
+        assert len(z_message) == self.n_prev
+        az = [data["a"] for source, target, data in z_message]
+        tau_z = [data["tau"] for source, target, data in z_message]
+        z_source = [source for source, target, data in z_message]
+        if self.n_prev == 1:
+            az, tau_z, z_source = az[0], tau_z[0], z_source[0]
+        x_message = filter_message(message, "bwd")
+        assert len(x_message) == self.n_next
+        ax = [data["a"] for source, target, data in x_message]
+        x_source = [source for source, target, data in x_message]
+        if self.n_next == 1:
+            ax, x_source = ax[0], x_source[0]
+        return z_source, x_source, az, ax, tau_z
+
+    def forward_state_evolution(self, message):
+        if self.n_next == 0:
+            return []
+        z_source, x_source, az, ax, tau_z = self._parse_message_a(message)
+        if self.n_prev == 0:
+            ax_new = self.compute_forward_state_evolution(ax)
+        else:
+            ax_new = self.compute_forward_state_evolution(az, ax, tau_z)
+        if self.n_next != 1:
+            raise NotImplementedError("multi-edge factors are outside the hot path")
+        return [(self, x_source, dict(a=ax_new, direction="fwd"))]
+
+    def backward_state_evolution(self, message):
+        if self.n_prev == 0:
+            return []
+        z_source, x_source, az, ax, tau_z = self._parse_message_a(message)
+        if self.n_next == 0:
+            az_new = self.compute_backward_state_evolution(az, tau_z)
+        else:
+            az_new = self.compute_backward_state_evolution(az, ax, tau_z)
+        if self.n_prev != 1:
+            raise NotImplementedError("multi-edge factors are outside the hot path")
+        return [(self, z_source, dict(a=az_new, direction="bwd"))]
+
+    def free_energy(self, message):
+        z_source, x_source, az, ax, tau_z = self._parse_message_a(message)
+        if self.n_prev == 0:
+            return self.compute_free_energy(ax)
+        if self.n_next == 0:
+            return self.compute_free_energy(az, tau_z)
+        return self.compute_free_energy(az, ax, tau_z)
+
+
+def se_domain_error(flags):
+    """The reference asserts `mz_hat > 0` inside Likelihood.beliefs_measure
+    (sgn_likelihood.py:80-81, abs_likelihood.py:57-58); the kernels flag it."""
+    from . import _lib
+    if int(flags.max().item()) & _lib.FLAG_SE_DOMAIN:
+        raise AssertionError("az must be greater than 1/ tau_z")
+
+
+def measure_out(out, like):
+    """Device [B] result -> float for scalar input, numpy array otherwise."""
+    x = out.cpu().numpy()
+    return float(x[0]) if np.ndim(like) == 0 else x.reshape(np.shape(like))
 
 
 # ---------------------------------------------------------------------------

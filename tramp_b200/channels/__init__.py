@@ -3,9 +3,11 @@ from .base_channel import Channel
 from .linear_channel import LinearChannel
 from .gaussian_channel import GaussianChannel
 from .activation import SgnChannel, AbsChannel
+from .analytical_linear_channel import AnalyticalLinearChannel, MarchenkoPasturChannel
 
 CHANNEL_CLASSES = {
     "linear": LinearChannel,
+    "marchenko": MarchenkoPasturChannel,
     "gaussian": GaussianChannel,
     "sgn": SgnChannel,
     "abs": AbsChannel,

@@ -305,3 +305,25 @@ class LinearChannel(Channel):
         logZ = 0.5 * (b * rz).sum(-1) + 0.5 * t.log(2 * np.pi / a).sum(-1) \
             + 0.5 * (self.Nz - self.R) * t.log(2 * np.pi / zarg.a)
         return zarg.scalar_out(logZ)
+
+    # ---- State Evolution (reference linear_channel.py:119-143) -----------------
+    def compute_backward_error(self, az, ax, tau_z):
+        return self.compute_backward_variance(az, ax)
+
+    def compute_forward_error(self, az, ax, tau_z):
+        return self.compute_forward_variance(az, ax)
+
+    def compute_mutual_information(self, az, ax, tau_z):
+        """mean over the Nz eigenvalues of 0.5 log((az + ax spectrum) tau_z) (:134-137);
+        cold path, reduced on the device copy of the spectrum."""
+        self._setup()
+        t = ops.torch()
+        if self.batch is not None:
+            raise NotImplementedError("free energies of a batched LinearChannel are not implemented")
+        logs = t.log((az + ax * self.s2[0]) * tau_z).sum() + (self.Nz - self.R) * np.log(az * tau_z)
+        return float(0.5 * logs.item() / self.Nz)
+
+    def compute_free_energy(self, az, ax, tau_z):
+        tau_x = self.second_moment(tau_z)
+        I = self.compute_mutual_information(az, ax, tau_z)
+        return 0.5 * (az * tau_z + self.alpha * ax * tau_x) - I + 0.5 * np.log(2 * np.pi * tau_z / np.e)

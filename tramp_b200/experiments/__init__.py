@@ -1,99 +1,14 @@
-"""Teacher-student scenarios (reference tramp/experiments/teacher_student_scenario.py)."""
-import logging
-import pandas as pd
-
-from ..algos.metrics import METRICS
-from ..models import Model
-from ..algos import TrackErrors, TrackEvolution, JoinCallback, ExpectationPropagation
-
-logger = logging.getLogger(__name__)
-
-
-class TeacherStudentScenario():
-    """Implements teacher student scenario (reference :10-141, EP part).
-
-    - teacher : Model instance or any object with a `.sample()` method
-    - student : Model instance, generative student model
-    - x_ids : ids of the variables to infer (signals)
-    - y_ids : ids of the observed variables (measurements)
-    """
-
-    def __init__(self, teacher, student, x_ids=["x"], y_ids=["y"]):
-        if not isinstance(student, Model):
-            raise ValueError("student not a Model")
-        try:
-            sample = teacher.sample()      # reference :27 (advances the RNG once)
-        except AttributeError:
-            raise ValueError("teacher does not have a .sample() method")
-        for x_id in x_ids:
-            if x_id not in student.variable_ids:
-                raise ValueError(f"x_id = {x_id} not in student variable_ids")
-            if x_id not in sample:
-                raise ValueError(f"x_id = {x_id} not in teacher variable_ids")
-        for y_id in y_ids:
-            if y_id not in student.variable_ids:
-                raise ValueError(f"y_id = {y_id} not in  student variable_ids")
-            if y_id not in sample:
-                raise ValueError(f"y_id = {y_id} not in teacher variable_ids")
-        self.x_ids = x_ids
-        self.y_ids = y_ids
-        self.teacher = teacher
-        self.generative_student = student
-
-    def setup(self, seed=0):
-        sample = self.teacher.sample(seed)
-        self.true_values = sample
-        self.x_true = {x_id: sample[x_id] for x_id in self.x_ids}
-        self.observations = {y_id: sample[y_id] for y_id in self.y_ids}
-        self.student = self.generative_student.to_observed(self.observations)
-
-    def run_all(self, source="EP", metrics=["mse"], **algo_kwargs):
-        "Get mse values as estimated by EP (State Evolution is outside the hot path)"
-        if "SE" in source:
-            raise NotImplementedError("State Evolution is scalar quadrature, outside tramp_b200's scope")
-        self.setup()
-        x_data = self.run_ep(**algo_kwargs)
-        records = [dict(source="EP", x_id=x_id, v=x_data[x_id]["v"], n_iter=x_data["n_iter"])
-                   for x_id in self.x_ids]
-        x_pred = {x_id: x_data[x_id]["r"] for x_id in self.x_ids}
-        score = self.compute_score(x_pred, metrics=metrics)
-        records += [dict(source=metric, x_id=x_id, v=score[x_id][metric])
-                    for metric in metrics for x_id in self.x_ids]
-        return records
-
-    def run_ep(self, **algo_kwargs):
-        ep = ExpectationPropagation(self.student)
-        ep.iterate(**algo_kwargs)
-        x_data = ep.get_variables_data(self.x_ids)
-        x_data["n_iter"] = ep.n_iter
-        self.x_pred = {x_id: x_data[x_id]["r"] for x_id in self.x_ids}
-        self.ep = ep
-        return x_data
-
-    def ep_convergence(self, metrics, **algo_kwargs):
-        track = TrackErrors(true_values=self.x_true, metrics=metrics)
-        evo = TrackEvolution(ids=self.x_ids)
-        callbacks = [track, evo]
-        if "callback" in algo_kwargs:
-            callbacks.append(algo_kwargs["callback"])
-        algo_kwargs["callback"] = JoinCallback(callbacks)
-        try:
-            self.run_ep(**algo_kwargs)
-        except Exception as e:
-            logger.error(e)
-        df = pd.merge(track.get_dataframe(), evo.get_dataframe(), on=["id", "iter"])
-        if not self.ep.batched:
-            for y in ["v"] + metrics:
-                df[y] = df[y].clip(0, 2)
-        return df
-
-    def compute_score(self, x_pred, metrics=["mse"]):
-        return {x_id: {metric: METRICS[metric](self.x_true[x_id], x_pred[x_id]) for metric in metrics}
-                for x_id in self.x_ids}
-
-
-class BayesOptimalScenario(TeacherStudentScenario):
-    """Same generative model for teacher and student (reference :143-155)."""
-
-    def __init__(self, model, x_ids=["x"], y_ids=["y"]):
-        super().__init__(teacher=model, student=model, x_ids=x_ids, y_ids=y_ids)
+"""Experiment helpers (reference tramp/experiments/): teacher-student
+scenarios, grid runner, critical-alpha search.  Plotting helpers are out of
+scope."""
+from .teacher_student_scenario import (
+    TeacherStudentScenario, BayesOptimalScenario, run_state_evolution,
+    run_state_evolution_grid,
+)
+from .multiple_experiments import (
+    run_experiments, simple_run_experiments, save_experiments, log_on_progress,
+    get_experiments_from_kwargs,
+)
+from .critical_alpha import (
+    binary_search, find_state_evolution_mse, find_critical_alpha,
+)

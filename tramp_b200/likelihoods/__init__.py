@@ -4,8 +4,8 @@
 """
 import numpy as np
 
-from ..base import Factor, _Arg
-from .. import ops
+from ..base import Factor, _Arg, measure_out, se_domain_error
+from .. import ops, _lib
 
 
 class Likelihood(Factor):
@@ -72,6 +72,40 @@ class Likelihood(Factor):
     def scalar_log_partition(self, az, bz, y):
         return self._scalar(az, bz, y, "A")
 
+    # ---- State Evolution (reference likelihoods/base_likelihood.py:73-98) ------
+    def beliefs_measure(self, az, tau_z, f):
+        """Average of f over the joint law of (b_z, y) at precision az and second
+        moment tau_z (sgn_likelihood.py:79-92, abs_likelihood.py:56-65); f = "v"
+        (scalar_backward_variance) or "A" (compute_log_partition), evaluated by
+        the device quadrature.  Raises AssertionError when az <= 1/tau_z, like
+        the reference's `assert mz_hat > 0`."""
+        what = {"v": _lib.MEASURE_V, "A": _lib.MEASURE_A}.get(f)
+        if what is None:
+            raise NotImplementedError('beliefs_measure runs on the device for f = "v" or "A" only')
+        az_ = np.atleast_1d(np.asarray(az, float))
+        tau = np.array(np.broadcast_to(np.asarray(tau_z, float), az_.shape))
+        out, flags = ops.se_measure(self._trb_factor(), what, az_, tau)
+        se_domain_error(flags)
+        return measure_out(out, az)
+
+    def compute_backward_error(self, az, tau_z):
+        return self.beliefs_measure(az, tau_z, "v")
+
+    def compute_backward_state_evolution(self, az, tau_z):
+        vz = self.compute_backward_error(az, tau_z)
+        return self.compute_a_new(vz, az)
+
+    def compute_backward_overlap(self, az, tau_z):
+        return tau_z - self.compute_backward_error(az, tau_z)
+
+    def compute_free_energy(self, az, tau_z):
+        return self.beliefs_measure(az, tau_z, "A")
+
+    def compute_mutual_information(self, az, tau_z):
+        "Note: returns H = mutual information I + noise entropy N (reference :94-98)"
+        A = self.compute_free_energy(az, tau_z)
+        return 0.5 * az * tau_z - A + 0.5 * np.log(2 * np.pi * tau_z / np.e)
+
 
 class GaussianLikelihood(Likelihood):
     """reference likelihoods/gaussian_likelihood.py:7-71."""
@@ -106,6 +140,10 @@ class GaussianLikelihood(Likelihood):
     def compute_backward_message(self, az, bz):
         """Constant, unclipped message (reference gaussian_likelihood.py:68-71)."""
         return self.a, self.b
+
+    def compute_backward_state_evolution(self, az, tau_z):
+        """Constant (reference gaussian_likelihood.py:66-68)."""
+        return self.a
 
 
 class SgnLikelihood(Likelihood):

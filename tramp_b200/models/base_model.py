@@ -65,5 +65,17 @@ class Model(ReprMixin):
             for shape, variable in zip(shapes, self.dag.successors(factor)):
                 self.dag.node[variable].update(shape=tuple(shape))
 
+    def init_second_moments(self):
+        "Second moment tau of every variable, in place (reference :111-124)"
+        for factor in self.factors:
+            if factor.n_next:
+                tau_prev = [self.dag.node[v]["tau"] for v in self.dag.predecessors(factor)]
+                tau_next = to_list(factor.second_moment(*tau_prev))
+                for tau, variable in zip(tau_next, self.dag.successors(factor)):
+                    self.dag.node[variable].update(tau=tau)
+
+    def get_second_moments(self):
+        return {v.id: self.dag.node[v]["tau"] for v in self.variables}
+
     def get_shapes(self):
         return {v.id: self.dag.node[v]["shape"] for v in self.variables}

@@ -1,7 +1,8 @@
-"""glm_generative (reference tramp/models/generalized_linear_model.py:8-35)."""
+"""glm_generative, glm_state_evolution (reference tramp/models/generalized_linear_model.py:8-55)."""
 from ..channels import get_channel
 from ..priors import get_prior
 from ..ensembles import get_ensemble
+from ..likelihoods import get_likelihood
 from ..variables import SISOVariable as V, SILeafVariable as O
 
 
@@ -19,3 +20,13 @@ def glm_generative(N, alpha, ensemble_type, prior_type, output_type, **kwargs):
     linear = get_channel("linear", W=F, name="F")
     output = get_channel(channel_type=output_type, **get_kwargs("output", kwargs))
     return (prior @ V(id="x") @ linear @ V(id="z") @ output @ O(id="y")).to_model()
+
+
+def glm_state_evolution(alpha, prior_type, output_type, **kwargs):
+    """GLM used only for State Evolution: the linear channel is known through the
+    Marchenko-Pastur law, the likelihood carries no data (reference :37-55)."""
+    prior = get_prior(size=None, prior_type=prior_type, **get_kwargs("prior", kwargs))
+    linear = get_channel("marchenko", alpha=alpha, name="F")
+    output = get_likelihood(y=None, y_name="y", likelihood_type=output_type,
+                            **get_kwargs("output", kwargs))
+    return (prior @ V(id="x") @ linear @ V(id="z") @ output).to_model()

@@ -263,3 +263,60 @@ def factor_from_spec(spec):
     if kind == "abs":
         return abs_factor(amin, amax)
     raise ValueError(f"unknown factor kind {kind!r}")
+
+
+# ---------------------------------------------------------------------------
+# State Evolution: quadrature rule and beliefs measures
+# ---------------------------------------------------------------------------
+QUAD_LIMIT = 10.0           # reference utils/integration.py:27, 45: quad(..., -10, 10)
+# (panels, order, kappa) of the sinh-mapped composite Gauss-Legendre rule, see
+# trb_quadrature in include/tramp_b200.h
+QUAD_1D = (160, 32, 1e-7)   # 5120 nodes per 1-D integral
+QUAD_2D = (48, 16, 1e-4)    # 768 x 768 nodes per 2-D integral
+
+_quad_cache = {}
+
+
+def quadrature(rule1=None, rule2=None):
+    """Device copy of the Gauss-Legendre templates + the C descriptor of the rule
+    (cached per device and size)."""
+    rule1, rule2 = tuple(rule1 or QUAD_1D), tuple(rule2 or QUAD_2D)
+    dev = device()
+    key = (str(dev), rule1, rule2)
+    if key not in _quad_cache:
+        x1, w1 = np.polynomial.legendre.leggauss(rule1[1])
+        x2, w2 = np.polynomial.legendre.leggauss(rule2[1])
+        tens = [to_dev(x) for x in (x1, w1, x2, w2)]
+        q = _lib.TrbQuadrature(x=ptr(tens[0]), w=ptr(tens[1]), Q=rule1[1], P=rule1[0], kappa=rule1[2],
+                               x2=ptr(tens[2]), w2=ptr(tens[3]), Q2=rule2[1], P2=rule2[0],
+                               kappa2=rule2[2])
+        _quad_cache[key] = (q, tens)
+    return _quad_cache[key][0]
+
+
+def factors_to_dev(factors):
+    """list of TrbFactor -> device byte tensor holding the C array."""
+    t = torch()
+    arr = (TrbFactor * len(factors))(*factors)
+    host = t.frombuffer(bytearray(bytes(arr)), dtype=t.uint8)
+    return host.to(device())
+
+
+def se_measure(factors, what, a, tau=None, quad=None):
+    """beliefs_measure of every factor at precision a[b] (and second moment tau[b]).
+    factors: one TrbFactor (shared) or a list of B.  Returns (out [B], flags [B]) on the device."""
+    t = torch()
+    lib = _lib.load()
+    a = to_dev(a).reshape(-1)
+    B = a.numel()
+    shared = isinstance(factors, TrbFactor)
+    fdev = factors_to_dev([factors] if shared else list(factors))
+    if not shared and len(factors) != B:
+        raise ValueError("one factor per precision expected")
+    tau_d = None if tau is None else to_dev(tau).reshape(-1).expand(B).contiguous()
+    out = t.zeros(B, dtype=t.float64, device=a.device)
+    flags = t.zeros(B, dtype=t.int32, device=a.device)
+    q = quad or quadrature()
+    check(lib.trb_se_measure(ptr(fdev), 0 if shared else 1, int(what), B, ptr(a), ptr(tau_d),
+                             C.byref(q), ptr(out), ptr(flags), current_stream()))
+    return out, flags

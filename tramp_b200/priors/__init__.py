@@ -7,8 +7,8 @@ become `a: (B,)`, `b: (B, N)`.
 """
 import numpy as np
 
-from ..base import Factor, _Arg
-from .. import ops
+from ..base import Factor, _Arg, measure_out
+from .. import ops, _lib
 
 
 class Prior(Factor):
@@ -71,6 +71,37 @@ class Prior(Factor):
 
     def scalar_log_partition(self, ax, bx):
         return self._scalar(ax, bx, "A")
+
+    # ---- State Evolution (reference priors/base_prior.py:66-90) ---------------
+    def beliefs_measure(self, ax, f):
+        """Average of f over the law of the incoming belief b_x at precision ax
+        (gauss_bernoulli_prior.py:112-118, binary_prior.py:80-84).  The reference
+        takes any Python callable and integrates it with scipy quad; on the device
+        f is one of the two functions SE needs: "v" (scalar_forward_variance) or
+        "A" (scalar_log_partition).  ax: scalar or array (one problem per entry)."""
+        what = {"v": _lib.MEASURE_V, "A": _lib.MEASURE_A}.get(f)
+        if what is None:
+            raise NotImplementedError('beliefs_measure runs on the device for f = "v" or "A" only')
+        ax_ = np.atleast_1d(np.asarray(ax, float))
+        tau = np.full(ax_.shape, float(self.second_moment()))
+        out, _ = ops.se_measure(self._trb_factor(), what, ax_, tau)
+        return measure_out(out, ax)
+
+    def compute_forward_error(self, ax):
+        return self.beliefs_measure(ax, "v")
+
+    def compute_forward_state_evolution(self, ax):
+        vx = self.compute_forward_error(ax)
+        return self.compute_a_new(vx, ax)
+
+    def compute_forward_overlap(self, ax):
+        return self.second_moment() - self.compute_forward_error(ax)
+
+    def compute_free_energy(self, ax):
+        return self.beliefs_measure(ax, "A")
+
+    def compute_mutual_information(self, ax):
+        return 0.5 * ax * self.second_moment() - self.compute_free_energy(ax)
 
 
 class GaussBernoulliPrior(Prior):
@@ -174,6 +205,10 @@ class GaussianPrior(Prior):
             t = ops.torch()
             return self.a * t.ones_like(ops.to_dev(ax)), self.b * t.ones_like(bx)
         return self.a * np.ones_like(ax), self.b * np.ones_like(bx)
+
+    def compute_forward_state_evolution(self, ax):
+        """Constant (reference gaussian_prior.py:102-104)."""
+        return self.a
 
 
 PRIOR_CLASSES = {
