@@ -19,7 +19,7 @@ using namespace trb;
 
 namespace {
 
-constexpr int kSeThreads = 256;
+constexpr int kSeThreads = 384;
 
 constexpr double kLimit = 10.0;                  // utils/integration.py:27, 45
 constexpr double kInvSqrt2Pi = 0.3989422804014327;  // utils/misc.py:46-47 (norm_pdf)
@@ -96,14 +96,16 @@ template <class F, class C2>
 __device__ __forceinline__ double measure_2d(double s1, F f, C2 c2, const Quad& q, double* sh) {
   const Map m1 = make_map(q.r2, 0.0);
   const int K = q.r2.P * q.r2.Q;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
   double acc = 0.0;
-  for (int i = 0; i < K; ++i) {
+  // one outer node per warp at a time, the inner rule spread over its lanes
+  for (int i = warp; i < K; i += nwarp) {
     double t1, w1;
     map_node(q.r2, m1, i, &t1, &w1);
     const double z = s1 * t1;
     const Map m2 = make_map(q.r2, c2(z));
     double inner = 0.0;
-    for (int j = threadIdx.x; j < K; j += blockDim.x) {
+    for (int j = lane; j < K; j += 32) {
       double t2, w2;
       map_node(q.r2, m2, j, &t2, &w2);
       inner += w2 * f(z, t2);
