@@ -336,6 +336,14 @@ int trb_sweep_run(const trb_sweep* sw, int it0, int n_iter, int fresh, void* str
  * that off (default on; the environment variable TRB_CUDA_GRAPHS=0 does the same). */
 void trb_set_cuda_graphs(int enabled);
 
+/* A single instance (B = 1) whose iteration is launch-bound runs ALL its
+ * iterations inside one cooperative launch of one CTA per SM, four grid-wide
+ * barriers per iteration (tramp_b200/csrc/trb_persist.cu); trb_sweep_run picks
+ * it automatically.  mode: -1 = automatic (default), 0 = never, 1 = whenever the
+ * hard limits allow (B = 1, snapshot buffers present, 2 max(ldn, ldm) + R doubles
+ * of shared memory).  Environment variable TRB_PERSISTENT_SWEEP sets the default. */
+void trb_set_persistent_sweep(int mode);
+
 /* ---- State Evolution (SE): the scalar twin of the sweep ---------------------
  * algos/state_evolution.py:5-27 runs the SAME schedule (message_passing.py:
  * 249-269, 330-357) on the precisions `a` alone; every factor replaces its

@@ -541,6 +541,7 @@ def test_cuda_graph_replay_is_bitwise_identical_to_plain_launches(sw):
         out = []
         for graphs in (1, 0):
             lib.trb_set_cuda_graphs(graphs)
+            lib.trb_set_persistent_sweep(0)      # the launch-per-stage path is the one under test
             try:
                 ep = ExpectationPropagation(_build(cfg, sw, name))
                 track = TrackErrors({"x": sw[name + "_x"]})
@@ -552,9 +553,126 @@ def test_cuda_graph_replay_is_bitwise_identical_to_plain_launches(sw):
                             int(lib.trb_profile_launches(-1))))
             finally:
                 lib.trb_set_cuda_graphs(1)
+                lib.trb_set_persistent_sweep(-1)
         for a, b in zip(out[0][:5], out[1][:5]):
             assert np.array_equal(a, b)
         assert out[0][5] == out[1][5]      # the launch accounting counts replayed kernels too
+
+
+@pytest.mark.parametrize("idx", range(9))
+def test_persistent_sweep_matches_launch_per_stage_path(sw, idx):
+    """One instance runs all its iterations inside ONE cooperative launch
+    (trb_persist.cu, four grid barriers per iteration).  Same arithmetic per element,
+    different summation order in the operator passes: 1e-11 against the
+    launch-per-stage path, and the golden vectors of the reference at 1e-9."""
+    from tramp_b200 import _lib
+    from tramp_b200.algos import ExpectationPropagation, TrackErrors, TrackEvolution, JoinCallback
+    lib = _lib.load()
+    cfg = _configs(sw)[idx]
+    name = cfg["name"]
+    out = {}
+    for mode in (1, 0):
+        lib.trb_set_persistent_sweep(mode)
+        try:
+            ep = ExpectationPropagation(_build(cfg, sw, name))
+            ep.schedule = "general"
+            track = TrackErrors({"x": sw[name + "_x"]}, metrics=["mse", "sign_mse"])
+            evo = TrackEvolution()
+            init = _SeqInit(sw, name) if cfg.get("init") == "noisy" else None
+            lib.trb_profile_reset(0)
+            ep.iterate(max_iter=cfg["n_iter"], callback=JoinCallback([track, evo]), initializer=init,
+                       damping=cfg["damping"])
+            launches = int(lib.trb_profile_launches(-1))
+            d = ep.get_variables_data()
+            df = evo.get_dataframe()
+            out[mode] = dict(rx=d["x"]["r"], rz=d["z"]["r"], vx=d["x"]["v"], vz=d["z"]["v"],
+                             mse=np.array([e["mse"] for e in track.errors]),
+                             smse=np.array([e["sign_mse"] for e in track.errors]),
+                             vxt=df[df.id == "x"].v.values, vzt=df[df.id == "z"].v.values,
+                             edges=[ep._edge(f"e{k}") for k in range(1, 9)], n_iter=ep.n_iter,
+                             launches=launches)
+        finally:
+            lib.trb_set_persistent_sweep(-1)
+    p, q = out[1], out[0]
+    assert p["launches"] == 1 and q["launches"] > 5 * cfg["n_iter"]
+    assert p["n_iter"] == q["n_iter"] == cfg["n_iter"]
+    x, W = sw[name + "_x"], sw[name + "_W"]
+    tau_x, tau_z = np.mean(x**2), np.mean((W @ x)**2)
+    saturated = max(float(sw[f"{name}_e{k}_a"]) for k in range(1, 9)) > 1e4
+    tol = 1e-9 if saturated else 1e-11          # ill-conditioned at exact recovery, see DESIGN "Parity"
+    for key, scale in (("rx", np.abs(q["rx"]).max()), ("rz", np.abs(q["rz"]).max()), ("vx", tau_x),
+                       ("vz", tau_z), ("vxt", tau_x), ("vzt", tau_z)):
+        assert_allclose(p[key], q[key], rtol=tol, atol=tol * scale)
+    for key in ("mse", "smse"):
+        assert np.all(np.abs(p[key] - q[key]) <= tol * q[key] + 2 * tol * np.sqrt(q[key] * tau_x))
+    if not saturated:
+        for (a1, b1), (a0, b0) in zip(p["edges"], q["edges"]):
+            assert_allclose(a1, a0, rtol=tol)
+            assert_allclose(b1, b0, rtol=tol, atol=tol * np.abs(b0).max())
+    # and the reference itself
+    ref = sw[name + "_mse"]
+    assert np.all(np.abs(p["mse"] - ref) <= 1e-9 * ref + 2e-9 * np.sqrt(ref * tau_x))
+    ref = sw[name + "_rx"]
+    assert_allclose(p["rx"], ref, rtol=1e-9, atol=1e-9 * np.abs(ref).max())
+    assert_allclose(p["vx"], sw[name + "_vx_final"], rtol=1e-9, atol=1e-9 * tau_x)
+
+
+def test_persistent_sweep_early_stopping_rollback_and_warm_start(sw):
+    """The persistent kernel takes the same EarlyStoppingEP decisions (convergence,
+    divergence with roll-back to the previous iteration), leaves live / snapshot
+    buffers consistent for a warm start, and reports NaN like the other path."""
+    from tramp_b200 import _lib
+    from tramp_b200.algos import ExpectationPropagation, PassCallback
+    from tramp_b200.priors import GaussBernoulliPrior
+    from tramp_b200.likelihoods import GaussianLikelihood
+    from tramp_b200.channels import LinearChannel
+    from tramp_b200.variables import SISOVariable as V
+    lib = _lib.load()
+    lib.trb_set_persistent_sweep(1)
+    try:
+        for idx in range(3):                                   # convergence at the reference's iteration
+            cfg = _configs(sw)[idx]
+            name = cfg["name"] + "_early"
+            ep = ExpectationPropagation(_build(cfg, sw, name))
+            ep.iterate(max_iter=200, damping=cfg["damping"])
+            assert ep.n_iter == int(sw[name + "_n_iter"])
+            ref = sw[name + "_rx"]
+            assert_allclose(ep.get_variables_data()["x"]["r"], ref, rtol=1e-9, atol=1e-9 * np.abs(ref).max())
+        name = "cs_diverges_early"                             # divergence: rolled back
+        model = (GaussBernoulliPrior(size=120, rho=0.1) @ V("x") @ LinearChannel(sw[name + "_W"])
+                 @ V("z") @ GaussianLikelihood(y=sw[name + "_y"], var=1e-2)).to_model()
+        ep = ExpectationPropagation(model)
+        ep.iterate(max_iter=200)
+        assert ep.n_iter == int(sw[name + "_n_iter"]) == 7
+        d = ep.get_variables_data()
+        assert_allclose(d["x"]["r"], sw[name + "_rx"], rtol=1e-9, atol=1e-12)
+        assert_allclose(d["z"]["r"], sw[name + "_rz"], rtol=1e-9, atol=1e-12)
+        for k in range(1, 9):
+            a, b = ep._edge(f"e{k}")
+            assert_allclose(a, sw[f"{name}_e{k}_a"], rtol=1e-9)
+            assert_allclose(b, sw[f"{name}_e{k}_b"], rtol=1e-9, atol=1e-12)
+        cfg = _configs(sw)[0]                                  # odd + even splits of a warm-started run
+        name = cfg["name"]
+        ep = ExpectationPropagation(_build(cfg, sw, name))
+        ep.iterate(max_iter=7, callback=PassCallback())
+        ep.iterate(max_iter=8, callback=PassCallback(), warm_start=True)
+        ep.iterate(max_iter=cfg["n_iter"] - 15, callback=PassCallback(), warm_start=True)
+        assert ep.n_iter == cfg["n_iter"]
+        ref = sw[name + "_rx"]
+        assert_allclose(ep.get_variables_data()["x"]["r"], ref, rtol=1e-9, atol=1e-9 * np.abs(ref).max())
+        y_bad = sw[name + "_y"].copy()                         # NaN surfaces as ValueError
+        y_bad[3] = np.nan
+        from tramp_b200.priors import get_prior
+        from tramp_b200.likelihoods import get_likelihood
+        pk = {k: v for k, v in cfg["prior"].items() if k != "kind"}
+        lk = {k: v for k, v in cfg["lik"].items() if k != "kind"}
+        bad = (get_prior(size=cfg["N"], prior_type=cfg["prior"]["kind"], **pk) @ V("x")
+               @ LinearChannel(sw[name + "_W"]) @ V("z")
+               @ get_likelihood(y=y_bad, likelihood_type=cfg["lik"]["kind"], **lk)).to_model()
+        with pytest.raises(ValueError, match="nan"):
+            ExpectationPropagation(bad).iterate(max_iter=5, callback=PassCallback())
+    finally:
+        lib.trb_set_persistent_sweep(-1)
 
 
 @pytest.mark.parametrize("lik_kind", ["gaussian", "sgn"])

@@ -1,9 +1,10 @@
 """BASELINE configs[0] and configs[1] as SINGLE instances (launch-bound on a GPU):
   0: GaussBernoulliPrior(N=1000, rho=0.1) @ LinearChannel(M=500) @ GaussianLikelihood(1e-2), 100 it
   1: GaussianPrior(N=2000) @ LinearChannel(alpha=2) @ SgnLikelihood, damping 0.5, 50 it
-Times iterate() through the public API (general schedule and the automatic one,
-CUDA-graph replay on / off) next to the CPU oracle on the same W, y, and checks
-parity.  -> gpurun_out/r01_small_configs.json"""
+Times iterate() through the public API (persistent whole-sweep kernel; and the
+launch-per-stage path with the general / automatic schedule, CUDA-graph replay
+on / off) next to the CPU oracle on the same W, y, and checks parity.
+-> gpurun_out/r01_small_configs.json"""
 import json, os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
@@ -40,9 +41,13 @@ for key, N, M, n_iter, damping in (("config0_sparse_regression", 1000, 500, 100,
     setup_s = time.perf_counter() - t0
     model = (prior @ V("x") @ lin @ V("z") @ lik).to_model()
     out = dict(N=N, M=M, n_iter=n_iter, damping=damping, gpu_setup_svd_s=setup_s)
-    for schedule in ("general", "auto"):
-        for graphs in (1, 0):
+    variants = [("persistent", "general", 1, 1)] + [
+        (f"{schedule}_graphs{graphs}", schedule, graphs, 0)
+        for schedule in ("general", "auto") for graphs in (1, 0)] + [("persistent_again", "auto", 1, 1)]
+    for label, schedule, graphs, persistent in variants:
+        if True:
             lib.trb_set_cuda_graphs(graphs)
+            lib.trb_set_persistent_sweep(persistent)
             ep = ExpectationPropagation(model)
             ep.schedule = schedule
             best = 1e30
@@ -53,9 +58,10 @@ for key, N, M, n_iter, damping in (("config0_sparse_regression", 1000, 500, 100,
                 ep.iterate(max_iter=n_iter, callback=track, damping=damping)
                 d = ep.get_variables_data(["x"])
                 best = min(best, time.perf_counter() - t0)
-            out[f"{schedule}_graphs{graphs}"] = dict(ms_per_sweep=best * 1e3, us_per_iter=best / n_iter * 1e6,
-                                                     iterations_per_s=n_iter / best)
+            out[label] = dict(ms_per_sweep=best * 1e3, us_per_iter=best / n_iter * 1e6,
+                              iterations_per_s=n_iter / best)
     lib.trb_set_cuda_graphs(1)
+    lib.trb_set_persistent_sweep(-1)
     t0 = time.perf_counter()
     op = orc.LinearOp(W)
     cpu_setup = time.perf_counter() - t0

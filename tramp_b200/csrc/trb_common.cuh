@@ -178,6 +178,13 @@ __device__ __forceinline__ double2 ldg_stream(const double* p) {
   return r;
 }
 
+// scalar version
+__device__ __forceinline__ double ldg_stream1(const double* p) {
+  double r;
+  asm volatile("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(r) : "l"(p));
+  return r;
+}
+
 // base.py:44-46 + 250-255.  np.maximum / np.clip propagate NaN whereas CUDA
 // fmax/fmin drop it, so NaN is routed around them: a NaN variance must surface
 // as a NaN message so that the check of message_passing.py:187-209 fires.

@@ -647,6 +647,8 @@ static int run_graph(const trb_sweep* sw, bool light, int count, cudaStream_t st
 
 extern "C" void trb_set_cuda_graphs(int enabled) { g_graphs_enabled = enabled ? 1 : 0; }
 
+int trb_sweep_run_persistent(const trb_sweep* sw, int it0, int n_iter, int fresh, cudaStream_t st);
+
 extern "C" int trb_sweep_run(const trb_sweep* sw, int it0, int n_iter, int fresh, void* stream) {
   int rc = check_sweep(sw);
   if (rc) return rc;
@@ -661,6 +663,11 @@ extern "C" int trb_sweep_run(const trb_sweep* sw, int it0, int n_iter, int fresh
                   "schedule 2 needs damp3 = 0 and no early stopping");
   }
   cudaStream_t st = (cudaStream_t)stream;
+  // one launch-bound instance: all iterations inside one cooperative launch (trb_persist.cu)
+  {
+    const int rc_p = trb_sweep_run_persistent(sw, it0, n_iter, fresh, st);
+    if (rc_p != TRB_ERR_UNSUPPORTED) return rc_p;
+  }
   int k = 0;
   while (k < n_iter) {
     const int first = (fresh && k == 0) ? 1 : 0;
