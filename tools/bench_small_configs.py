@@ -60,6 +60,17 @@ for key, N, M, n_iter, damping in (("config0_sparse_regression", 1000, 500, 100,
                 best = min(best, time.perf_counter() - t0)
             out[label] = dict(ms_per_sweep=best * 1e3, us_per_iter=best / n_iter * 1e6,
                               iterations_per_s=n_iter / best)
+            if label.startswith("persistent") or label == "auto_graphs1":
+                # marginal cost of an iteration: the same sweep 5x longer, host-side
+                # fixed costs (descriptor, record copies, callback replay set-up) cancel
+                long_best = 1e30
+                for rep in range(3):
+                    torch.cuda.synchronize()
+                    t0 = time.perf_counter()
+                    ep.iterate(max_iter=5 * n_iter, callback=TrackErrors({"x": x}), damping=damping)
+                    ep.get_variables_data(["x"])
+                    long_best = min(long_best, time.perf_counter() - t0)
+                out[label]["us_per_iter_marginal"] = (long_best - best) / (4 * n_iter) * 1e6
     lib.trb_set_cuda_graphs(1)
     lib.trb_set_persistent_sweep(-1)
     t0 = time.perf_counter()

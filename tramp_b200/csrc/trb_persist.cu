@@ -46,7 +46,6 @@ bool trb_profile_events_enabled();
 namespace {
 
 constexpr int kPsThreads = 512;
-constexpr int kRowBatch = 4;
 
 struct StateBuf {
   double* b1;
@@ -59,35 +58,68 @@ struct StateBuf {
 };
 
 // t[i] = A[i, :] . vec for rows [r0, r1); vec (length n) sits in shared memory.
-// kRowBatch rows per block reduction so that their loads are in flight together.
+// A row belongs to a group of `wpr` warps (wpr = 1 when the CTA owns at least as
+// many rows as it has warps), lanes stride over column pairs with 16-byte loads,
+// kProjUnroll of them in flight per lane; no block-wide barrier unless wpr > 1.
+constexpr int kProjUnroll = 8;
 __device__ __forceinline__ void project_rows(const double* __restrict__ A, int ld, int n, int r0,
                                              int r1, const double* vec, double* __restrict__ t,
-                                             double* sh) {
-  for (int i0 = r0; i0 < r1; i0 += kRowBatch) {
-    double p[kRowBatch];
+                                             double* red) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+  const int nrows = r1 - r0;
+  if (nrows <= 0) return;  // uniform over the CTA
+  int wpr = 1;
+  while (wpr * 2 * nrows <= nwarp) wpr *= 2;
+  const int rpr = nwarp / wpr;  // rows in flight per round
+  const int slot = warp / wpr, part = warp % wpr;
+  const int npair = n >> 1;
+  const double2* v2 = reinterpret_cast<const double2*>(vec);
+  for (int base = r0; base < r1; base += rpr) {
+    const int i = base + slot;
+    double acc = 0.0;
+    if (i < r1) {
+      const double* row = A + (size_t)i * ld;
+      const int stride = wpr * 32;
+      // every batch is fully predicated (no serial tail): a load whose result is
+      // not consumed for ~1 us is what this loop is bound by
+      for (int q0 = part * 32 + lane; q0 < npair; q0 += kProjUnroll * stride) {
+        double2 x[kProjUnroll];
 #pragma unroll
-    for (int u = 0; u < kRowBatch; ++u) p[u] = 0.0;
-    for (int j = threadIdx.x; j < n; j += blockDim.x) {
-      const double v = vec[j];
-      double av[kRowBatch];
+        for (int u = 0; u < kProjUnroll; ++u) {
+          const int q = q0 + u * stride;
+          x[u] = (q < npair) ? ldg_stream(row + 2 * q) : make_double2(0.0, 0.0);
+        }
 #pragma unroll
-      for (int u = 0; u < kRowBatch; ++u)
-        av[u] = (i0 + u < r1) ? ldg_stream1(A + (size_t)(i0 + u) * ld + j) : 0.0;
-#pragma unroll
-      for (int u = 0; u < kRowBatch; ++u) p[u] += av[u] * v;
+        for (int u = 0; u < kProjUnroll; ++u) {
+          const int q = q0 + u * stride;
+          if (q < npair) {
+            const double2 v = v2[q];
+            acc += x[u].x * v.x;
+            acc += x[u].y * v.y;
+          }
+        }
+      }
+      if ((n & 1) && part == 0 && lane == 0) acc += row[n - 1] * vec[n - 1];
+      acc = warp_sum(acc);
+      if (wpr == 1 && lane == 0) t[i] = acc;
     }
-    block_sum_n<kRowBatch>(p, sh);
-    if (threadIdx.x == 0) {
-#pragma unroll
-      for (int u = 0; u < kRowBatch; ++u)
-        if (i0 + u < r1) t[i0 + u] = p[u];
+    if (wpr > 1) {  // uniform over the CTA
+      __syncthreads();
+      if (lane == 0) red[warp] = acc;
+      __syncthreads();
+      if ((int)threadIdx.x < rpr && base + (int)threadIdx.x < r1) {
+        double sum = 0.0;
+        for (int p = 0; p < wpr; ++p) sum += red[threadIdx.x * wpr + p];
+        t[base + threadIdx.x] = sum;
+      }
     }
   }
 }
 
 // out[j] = sum_i coef[i] A[i, j] for columns [c0, c1); coef (length R) in shared
-// memory.  Threads form (row group, column) pairs; the row groups' partial sums
-// are added in a fixed order.
+// memory.  Threads form (row group, column) pairs, kExpUnroll loads in flight per
+// thread; the row groups' partial sums are added in a fixed order.
+constexpr int kExpUnroll = 16;
 __device__ __forceinline__ void expand_cols(const double* __restrict__ A, int ld, int R, int c0,
                                             int c1, const double* coef, double* __restrict__ out,
                                             double* red) {
@@ -98,23 +130,24 @@ __device__ __forceinline__ void expand_cols(const double* __restrict__ A, int ld
   const int T = blockDim.x;
   for (int cb = 0; cb < w; cb += T) {  // w > T only if there are fewer CTAs than n / T
     const int ww = min(w - cb, T);
-    int Wc = W < T ? W : T;
+    const int Wc = W < T ? W : T;
     const int tcol = threadIdx.x % Wc, trow = threadIdx.x / Wc, nrg = T / Wc;
     double acc = 0.0;
     if (tcol < ww) {
       const double* Ac = A + c0 + cb + tcol;
-      int i = trow;
-      for (; i + 3 * nrg < R; i += 4 * nrg) {
-        const double x0 = ldg_stream1(Ac + (size_t)i * ld);
-        const double x1 = ldg_stream1(Ac + (size_t)(i + nrg) * ld);
-        const double x2 = ldg_stream1(Ac + (size_t)(i + 2 * nrg) * ld);
-        const double x3 = ldg_stream1(Ac + (size_t)(i + 3 * nrg) * ld);
-        acc += coef[i] * x0;
-        acc += coef[i + nrg] * x1;
-        acc += coef[i + 2 * nrg] * x2;
-        acc += coef[i + 3 * nrg] * x3;
+      for (int i0 = trow; i0 < R; i0 += kExpUnroll * nrg) {  // fully predicated batches, no serial tail
+        double x[kExpUnroll];
+#pragma unroll
+        for (int u = 0; u < kExpUnroll; ++u) {
+          const int i = i0 + u * nrg;
+          x[u] = (i < R) ? ldg_stream1(Ac + (size_t)i * ld) : 0.0;
+        }
+#pragma unroll
+        for (int u = 0; u < kExpUnroll; ++u) {
+          const int i = i0 + u * nrg;
+          if (i < R) acc += coef[i] * x[u];
+        }
       }
-      for (; i < R; i += nrg) acc += coef[i] * ldg_stream1(Ac + (size_t)i * ld);
     }
     __syncthreads();
     red[threadIdx.x] = acc;
@@ -186,7 +219,7 @@ __device__ __forceinline__ double rescale_all(int dir, int R, int Nz, int Nx, in
 __global__ void __launch_bounds__(kPsThreads, 1)
 k_sweep_persistent(trb_sweep sw, int it0, int n_iter, int fresh, int ldmax) {
   cg::grid_group grid = cg::this_grid();
-  extern __shared__ double smem[];
+  extern __shared__ __align__(16) double smem[];
   double* sA = smem;              // [ldmax] moments r, then the vector being projected (b1 / b5)
   double* sB = smem + ldmax;      // [ldmax] e8 (= b7) carried from X to the next F1; b3 inside Z
   double* sC = smem + 2 * ldmax;  // [R] coefficients
@@ -227,7 +260,7 @@ k_sweep_persistent(trb_sweep sw, int it0, int n_iter, int fresh, int ldmax) {
       const double* b6 = sw.b6_init ? sw.b6_init : sw.b5;
       for (int i = tid; i < M; i += T) sA[i] = b6[i];
       __syncthreads();
-      project_rows(sw.Ut, ldm, M, r0, r1, sA, P[0].tx, sh);
+      project_rows(sw.Ut, ldm, M, r0, r1, sA, P[0].tx, red);
     }
     __syncthreads();
   }
@@ -279,7 +312,7 @@ k_sweep_persistent(trb_sweep sw, int it0, int n_iter, int fresh, int ldmax) {
     }
     __syncthreads();
     // ---- P1: tz = V_R^T b2
-    project_rows(sw.Vt, ldn, N, r0, r1, sA, tz, sh);
+    project_rows(sw.Vt, ldn, N, r0, r1, sA, tz, red);
     grid.sync();  // barrier 1: tz (and, in the first iteration, tx) complete
 
     // ---- S1 + P2: forward variance, r_x = U_R coef
@@ -348,7 +381,7 @@ k_sweep_persistent(trb_sweep sw, int it0, int n_iter, int fresh, int ldmax) {
     }
     __syncthreads();
     // ---- P3: tx = U_R^T b6
-    project_rows(sw.Ut, ldm, M, r0, r1, sA, nxt.tx, sh);
+    project_rows(sw.Ut, ldm, M, r0, r1, sA, nxt.tx, red);
     grid.sync();  // barrier 3: tx complete
 
     // ---- S2 + P4: backward variance, r_z = V_R coef
