@@ -165,6 +165,55 @@ def test_runs_match_reference(gold, gl, name):
                         rtol=1e-9, atol=1e-11)
 
 
+def test_node_protocol_walk_equals_kernel_iteration():
+    """The reference's node-by-node protocol (`forward_state_evolution` /
+    `backward_state_evolution` on factors and variables, base.py:209-233, 377-410,
+    sub_variables.py:33-43) walked by hand for two iterations gives the kernel's
+    trajectory: the factor-level API and `trb_se_run` share their device routines."""
+    from tramp_b200.algos import StateEvolution, PassCallback
+    case = SE_RUNS["perceptron_gb"]
+    model = make_model(case)
+    model.init_second_moments()
+    prior, x, lin, z, lik = model.forward_ordering
+    tau = model.get_second_moments()
+    a = {k: 0.0 for k in ("e1", "e2", "e3", "e4", "e5", "e6", "e7", "e8")}
+
+    def msg(source, target, key, direction, var):
+        return (source, target, dict(a=a[key], direction=direction, tau=tau[var]))
+    vs = []
+    for _ in range(2):
+        (_, _, d), = prior.forward_state_evolution([msg(x, prior, "e8", "bwd", "x")])
+        a["e1"] = d["a"]
+        (_, _, d), = x.forward_state_evolution([msg(prior, x, "e1", "fwd", "x"), msg(lin, x, "e7", "bwd", "x")])
+        a["e2"] = d["a"]
+        (_, _, d), = lin.forward_state_evolution([msg(x, lin, "e2", "fwd", "x"), msg(z, lin, "e6", "bwd", "z")])
+        a["e3"] = d["a"]
+        (_, _, d), = z.forward_state_evolution([msg(lin, z, "e3", "fwd", "z"), msg(lik, z, "e5", "bwd", "z")])
+        a["e4"] = d["a"]
+        assert lik.forward_state_evolution([msg(z, lik, "e4", "fwd", "z")]) == []
+        (_, _, d), = lik.backward_state_evolution([msg(z, lik, "e4", "fwd", "z")])
+        a["e5"] = d["a"]
+        (_, _, d), = z.backward_state_evolution([msg(lin, z, "e3", "fwd", "z"), msg(lik, z, "e5", "bwd", "z")])
+        a["e6"] = d["a"]
+        (_, _, d), = lin.backward_state_evolution([msg(x, lin, "e2", "fwd", "x"), msg(z, lin, "e6", "bwd", "z")])
+        a["e7"] = d["a"]
+        (_, _, d), = x.backward_state_evolution([msg(prior, x, "e1", "fwd", "x"), msg(lin, x, "e7", "bwd", "x")])
+        a["e8"] = d["a"]
+        assert prior.backward_state_evolution([msg(x, prior, "e8", "bwd", "x")]) == []
+        vs.append((x.posterior_v([msg(prior, x, "e1", "fwd", "x"), msg(lin, x, "e7", "bwd", "x")]),
+                   z.posterior_v([msg(lin, z, "e3", "fwd", "z"), msg(lik, z, "e5", "bwd", "z")])))
+    se = StateEvolution(make_model(case))
+    se.iterate(max_iter=2, callback=PassCallback())
+    assert_allclose(vs, np.stack([se.records["vx"][:, 0], se.records["vz"][:, 0]], axis=1), rtol=1e-12)
+    assert_allclose([a[f"e{k}"] for k in range(1, 9)], [r["a"] for r in se.get_edges_data(["a"])],
+                    rtol=1e-12)
+    # free energies through the same protocol (base.py:172-178, 412-419)
+    se.update_objective()
+    A_x = x.free_energy([msg(prior, x, "e1", "fwd", "x"), msg(lin, x, "e7", "bwd", "x")])
+    A_lin = lin.free_energy([msg(x, lin, "e2", "fwd", "x"), msg(z, lin, "e6", "bwd", "z")])
+    assert_allclose([A_x, A_lin], [se.A_nodes["x"], se.A_nodes[lin.id]], rtol=1e-12)
+
+
 def test_synchronous_callback_path_is_bitwise_identical(gold):
     """A callback the kernel cannot replay forces one launch per iteration; the
     trajectory must not change."""

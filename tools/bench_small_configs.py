@@ -45,7 +45,7 @@ for key, N, M, n_iter, damping in (("config0_sparse_regression", 1000, 500, 100,
         (f"{schedule}_graphs{graphs}", schedule, graphs, 0)
         for schedule in ("general", "auto") for graphs in (1, 0)] + [("persistent_again", "auto", 1, 1)]
     for label, schedule, graphs, persistent in variants:
-        if True:
+        for _ in (0,):
             lib.trb_set_cuda_graphs(graphs)
             lib.trb_set_persistent_sweep(persistent)
             ep = ExpectationPropagation(model)

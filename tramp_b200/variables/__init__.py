@@ -27,6 +27,21 @@ class SISOVariable(Variable):
         return [(self, k, dict(a=dl["a"], b=dl["b"], direction="bwd"))]
 
 
+    def forward_state_evolution(self, message):
+        "State Evolution: the precision passes through unchanged (reference sub_variables.py:33-37)"
+        from ..base import filter_message
+        (k, _, dk), = filter_message(message, "fwd")
+        (l, _, dl), = filter_message(message, "bwd")
+        return [(self, l, dict(a=dk["a"], direction="fwd"))]
+
+    def backward_state_evolution(self, message):
+        "reference sub_variables.py:39-43"
+        from ..base import filter_message
+        (k, _, dk), = filter_message(message, "fwd")
+        (l, _, dl), = filter_message(message, "bwd")
+        return [(self, k, dict(a=dl["a"], direction="bwd"))]
+
+
 class SILeafVariable(Variable):
     """Observed leaf (reference sub_variables.py:52-55)."""
 
