@@ -339,9 +339,13 @@ void trb_set_cuda_graphs(int enabled);
 /* A single instance (B = 1) whose iteration is launch-bound runs ALL its
  * iterations inside one cooperative launch of one CTA per SM, four grid-wide
  * barriers per iteration (tramp_b200/csrc/trb_persist.cu); trb_sweep_run picks
- * it automatically.  mode: -1 = automatic (default), 0 = never, 1 = whenever the
- * hard limits allow (B = 1, snapshot buffers present, 2 max(ldn, ldm) + R doubles
- * of shared memory).  Environment variable TRB_PERSISTENT_SWEEP sets the default. */
+ * it automatically.  The smallest instances (<= 5 MB of operator traffic per
+ * iteration) use a single 16-CTA thread-block cluster and the hardware cluster
+ * barrier instead of the whole grid.  mode: -1 = automatic (default), 0 = never,
+ * 1 = whenever the hard limits allow (B = 1, snapshot buffers present,
+ * 2 max(ldn, ldm) + R doubles of shared memory), 2 / 3 = as 1 but always the
+ * grid / the cluster variant.  Environment variable TRB_PERSISTENT_SWEEP sets the
+ * default. */
 void trb_set_persistent_sweep(int mode);
 
 /* ---- State Evolution (SE): the scalar twin of the sweep ---------------------

@@ -561,17 +561,19 @@ def test_cuda_graph_replay_is_bitwise_identical_to_plain_launches(sw):
 
 @pytest.mark.parametrize("idx", range(9))
 def test_persistent_sweep_matches_launch_per_stage_path(sw, idx):
-    """One instance runs all its iterations inside ONE cooperative launch
-    (trb_persist.cu, four grid barriers per iteration).  Same arithmetic per element,
-    different summation order in the operator passes: 1e-11 against the
-    launch-per-stage path, and the golden vectors of the reference at 1e-9."""
+    """One instance runs all its iterations inside ONE launch (trb_persist.cu, four
+    barriers per iteration): as a cooperative grid of one CTA per SM (mode 2) or,
+    for the smallest instances, as a single 16-CTA cluster with the hardware
+    cluster barrier (mode 3).  Same arithmetic per element, different summation
+    order in the operator passes: 1e-11 against the launch-per-stage path (mode
+    0), and the golden vectors of the reference at 1e-9."""
     from tramp_b200 import _lib
     from tramp_b200.algos import ExpectationPropagation, TrackErrors, TrackEvolution, JoinCallback
     lib = _lib.load()
     cfg = _configs(sw)[idx]
     name = cfg["name"]
     out = {}
-    for mode in (1, 0):
+    for mode in (3, 2, 0):
         lib.trb_set_persistent_sweep(mode)
         try:
             ep = ExpectationPropagation(_build(cfg, sw, name))
@@ -593,34 +595,39 @@ def test_persistent_sweep_matches_launch_per_stage_path(sw, idx):
                              launches=launches)
         finally:
             lib.trb_set_persistent_sweep(-1)
-    p, q = out[1], out[0]
-    assert p["launches"] == 1 and q["launches"] > 5 * cfg["n_iter"]
-    assert p["n_iter"] == q["n_iter"] == cfg["n_iter"]
+    q = out[0]
+    assert q["launches"] > 5 * cfg["n_iter"]
     x, W = sw[name + "_x"], sw[name + "_W"]
     tau_x, tau_z = np.mean(x**2), np.mean((W @ x)**2)
     saturated = max(float(sw[f"{name}_e{k}_a"]) for k in range(1, 9)) > 1e4
     tol = 1e-9 if saturated else 1e-11          # ill-conditioned at exact recovery, see DESIGN "Parity"
-    for key, scale in (("rx", np.abs(q["rx"]).max()), ("rz", np.abs(q["rz"]).max()), ("vx", tau_x),
-                       ("vz", tau_z), ("vxt", tau_x), ("vzt", tau_z)):
-        assert_allclose(p[key], q[key], rtol=tol, atol=tol * scale)
-    for key in ("mse", "smse"):
-        assert np.all(np.abs(p[key] - q[key]) <= tol * q[key] + 2 * tol * np.sqrt(q[key] * tau_x))
-    if not saturated:
-        for (a1, b1), (a0, b0) in zip(p["edges"], q["edges"]):
-            assert_allclose(a1, a0, rtol=tol)
-            assert_allclose(b1, b0, rtol=tol, atol=tol * np.abs(b0).max())
-    # and the reference itself
-    ref = sw[name + "_mse"]
-    assert np.all(np.abs(p["mse"] - ref) <= 1e-9 * ref + 2e-9 * np.sqrt(ref * tau_x))
-    ref = sw[name + "_rx"]
-    assert_allclose(p["rx"], ref, rtol=1e-9, atol=1e-9 * np.abs(ref).max())
-    assert_allclose(p["vx"], sw[name + "_vx_final"], rtol=1e-9, atol=1e-9 * tau_x)
+    for mode in (3, 2):
+        p = out[mode]
+        assert p["launches"] == 1
+        assert p["n_iter"] == q["n_iter"] == cfg["n_iter"]
+        for key, scale in (("rx", np.abs(q["rx"]).max()), ("rz", np.abs(q["rz"]).max()), ("vx", tau_x),
+                           ("vz", tau_z), ("vxt", tau_x), ("vzt", tau_z)):
+            assert_allclose(p[key], q[key], rtol=tol, atol=tol * scale)
+        for key in ("mse", "smse"):
+            assert np.all(np.abs(p[key] - q[key]) <= tol * q[key] + 2 * tol * np.sqrt(q[key] * tau_x))
+        if not saturated:
+            for (a1, b1), (a0, b0) in zip(p["edges"], q["edges"]):
+                assert_allclose(a1, a0, rtol=tol)
+                assert_allclose(b1, b0, rtol=tol, atol=tol * np.abs(b0).max())
+        # and the reference itself
+        ref = sw[name + "_mse"]
+        assert np.all(np.abs(p["mse"] - ref) <= 1e-9 * ref + 2e-9 * np.sqrt(ref * tau_x))
+        ref = sw[name + "_rx"]
+        assert_allclose(p["rx"], ref, rtol=1e-9, atol=1e-9 * np.abs(ref).max())
+        assert_allclose(p["vx"], sw[name + "_vx_final"], rtol=1e-9, atol=1e-9 * tau_x)
 
 
-def test_persistent_sweep_early_stopping_rollback_and_warm_start(sw):
-    """The persistent kernel takes the same EarlyStoppingEP decisions (convergence,
-    divergence with roll-back to the previous iteration), leaves live / snapshot
-    buffers consistent for a warm start, and reports NaN like the other path."""
+@pytest.mark.parametrize("mode", [2, 3])
+def test_persistent_sweep_early_stopping_rollback_and_warm_start(sw, mode):
+    """The persistent kernel (grid and cluster variants) takes the same
+    EarlyStoppingEP decisions (convergence, divergence with roll-back to the
+    previous iteration), leaves live / snapshot buffers consistent for a warm
+    start, and reports NaN like the other path."""
     from tramp_b200 import _lib
     from tramp_b200.algos import ExpectationPropagation, PassCallback
     from tramp_b200.priors import GaussBernoulliPrior
@@ -628,7 +635,7 @@ def test_persistent_sweep_early_stopping_rollback_and_warm_start(sw):
     from tramp_b200.channels import LinearChannel
     from tramp_b200.variables import SISOVariable as V
     lib = _lib.load()
-    lib.trb_set_persistent_sweep(1)
+    lib.trb_set_persistent_sweep(mode)
     try:
         for idx in range(3):                                   # convergence at the reference's iteration
             cfg = _configs(sw)[idx]

@@ -41,9 +41,9 @@ for key, N, M, n_iter, damping in (("config0_sparse_regression", 1000, 500, 100,
     setup_s = time.perf_counter() - t0
     model = (prior @ V("x") @ lin @ V("z") @ lik).to_model()
     out = dict(N=N, M=M, n_iter=n_iter, damping=damping, gpu_setup_svd_s=setup_s)
-    variants = [("persistent", "general", 1, 1)] + [
+    variants = [("persistent_grid", "general", 1, 2), ("persistent_cluster", "general", 1, 3)] + [
         (f"{schedule}_graphs{graphs}", schedule, graphs, 0)
-        for schedule in ("general", "auto") for graphs in (1, 0)] + [("persistent_again", "auto", 1, 1)]
+        for schedule in ("general", "auto") for graphs in (1, 0)] + [("persistent_auto", "auto", 1, 1)]
     for label, schedule, graphs, persistent in variants:
         for _ in (0,):
             lib.trb_set_cuda_graphs(graphs)

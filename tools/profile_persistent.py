@@ -24,7 +24,7 @@ W = rng.randn(M, N) / np.sqrt(N)
 x = rng.randn(N)
 y = np.where(W @ x >= 0, 1.0, -1.0)
 model = (GaussianPrior(size=N) @ V("x") @ LinearChannel(W) @ V("z") @ SgnLikelihood(y=y)).to_model()
-_lib.load().trb_set_persistent_sweep(1)
+_lib.load().trb_set_persistent_sweep(2)
 ep = ExpectationPropagation(model)
 track = TrackErrors({"x": x})
 ep.iterate(max_iter=50, callback=track, damping=0.5)

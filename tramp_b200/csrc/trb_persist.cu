@@ -216,9 +216,22 @@ __device__ __forceinline__ double rescale_all(int dir, int R, int Nz, int Nx, in
   return v;
 }
 
+// kCluster = false: one CTA per SM, cooperative launch, cg grid barrier.
+// kCluster = true : the whole grid is ONE thread-block cluster (16 CTAs) and the
+//   barrier is the hardware cluster barrier: for the smallest instances (N <~ 600)
+//   the four barriers, not the operator traffic, are the cost (18.5 vs 26 us per
+//   iteration measured); beyond, 16 SMs cannot pull the operators fast enough.
+template <bool kCluster>
 __global__ void __launch_bounds__(kPsThreads, 1)
 k_sweep_persistent(trb_sweep sw, int it0, int n_iter, int fresh, int ldmax) {
-  cg::grid_group grid = cg::this_grid();
+  auto sync_all = [&]() {
+    if constexpr (kCluster) {
+      __threadfence();  // global writes of this CTA before the release-arrive
+      cluster_sync();   // barrier.cluster.arrive.release + wait.acquire
+    } else {
+      cg::this_grid().sync();
+    }
+  };
   extern __shared__ __align__(16) double smem[];
   double* sA = smem;              // [ldmax] moments r, then the vector being projected (b1 / b5)
   double* sB = smem + ldmax;      // [ldmax] e8 (= b7) carried from X to the next F1; b3 inside Z
@@ -313,13 +326,13 @@ k_sweep_persistent(trb_sweep sw, int it0, int n_iter, int fresh, int ldmax) {
     __syncthreads();
     // ---- P1: tz = V_R^T b2
     project_rows(sw.Vt, ldn, N, r0, r1, sA, tz, red);
-    grid.sync();  // barrier 1: tz (and, in the first iteration, tx) complete
+    sync_all();  // barrier 1: tz (and, in the first iteration, tx) complete
 
     // ---- S1 + P2: forward variance, r_x = U_R coef
     const double vlin_f =
         rescale_all(0, R, N, M, sw.rank, null_space, sw.s, sw.s2, a[1], a[5], tz, cur.tx, sC, sh);
     expand_cols(sw.Ut, ldm, R, cm0, cm1, sC, rxl, red);
-    grid.sync();  // barrier 2: rxl complete
+    sync_all();  // barrier 2: rxl complete
 
     // ---- Z: e3 (= e4), likelihood e5 (= e6), posterior of z
     double dz2 = 0.0, nz2 = 0.0;
@@ -382,13 +395,13 @@ k_sweep_persistent(trb_sweep sw, int it0, int n_iter, int fresh, int ldmax) {
     __syncthreads();
     // ---- P3: tx = U_R^T b6
     project_rows(sw.Ut, ldm, M, r0, r1, sA, nxt.tx, red);
-    grid.sync();  // barrier 3: tx complete
+    sync_all();  // barrier 3: tx complete
 
     // ---- S2 + P4: backward variance, r_z = V_R coef
     const double vlin_b =
         rescale_all(1, R, N, M, sw.rank, null_space, sw.s, sw.s2, a[1], a[5], tz, nxt.tx, sC, sh);
     expand_cols(sw.Vt, ldn, R, cn0, cn1, sC, rzl, red);
-    grid.sync();  // barrier 4: rzl complete
+    sync_all();  // barrier 4: rzl complete
 
     // ---- X: e7 (= e8), posterior of x, records, early stopping
     {
@@ -476,7 +489,7 @@ k_sweep_persistent(trb_sweep sw, int it0, int n_iter, int fresh, int ldmax) {
   }
 
   // ---- epilogue: the final state into the live buffers, the other parity into the snapshot
-  grid.sync();
+  sync_all();
   if (par == 1) {
     const size_t gt = (size_t)cta * T + tid, GT = (size_t)G * T;
     auto swap = [&](double* x, double* yv, int n) {
@@ -508,7 +521,13 @@ k_sweep_persistent(trb_sweep sw, int it0, int n_iter, int fresh, int ldmax) {
 }
 
 int g_persistent_mode = -2;  // -2 unset (environment TRB_PERSISTENT_SWEEP, else auto), -1 auto, 0 off,
-                             // 1 on whenever the hard limits allow
+                             // 1 on whenever the hard limits allow, 2 / 3 = as 1 but always the
+                             // cooperative-grid / the single-cluster variant
+
+constexpr size_t kPsMaxSmem = 200 * 1024;
+// operator bytes per iteration up to which one cluster wins: measured crossover between 3.1 MB
+// (N = 512: 19.9 vs 26.2 us) and 7.1 MB (N = 768: 27.9 vs 26.1 us), profiles/r01f_persistent_sizes.json
+constexpr double kClusterMaxBytes = 5e6;
 
 }  // namespace
 
@@ -521,7 +540,7 @@ int trb_sweep_run_persistent(const trb_sweep* sw, int it0, int n_iter, int fresh
   if (g_persistent_mode == -2) {
     const char* e = getenv("TRB_PERSISTENT_SWEEP");
     g_persistent_mode = e ? atoi(e) : -1;
-    if (g_persistent_mode < -1 || g_persistent_mode > 1) g_persistent_mode = -1;
+    if (g_persistent_mode < -1 || g_persistent_mode > 3) g_persistent_mode = -1;
   }
   const int mode = g_persistent_mode;
   if (mode == 0 || trb_profile_events_enabled()) return TRB_ERR_UNSUPPORTED;
@@ -536,34 +555,64 @@ int trb_sweep_run_persistent(const trb_sweep* sw, int it0, int n_iter, int fresh
   // launches of trb_sweep.cu are hidden and its TMA-ring GEMVs are faster
   const double bytes = 16.0 * sw->R * ((double)sw->N + sw->M);
   if (mode < 0 && (bytes > 1.5e9 || n_iter < 2)) return TRB_ERR_UNSUPPORTED;
-  if (smem > 200 * 1024) return TRB_ERR_UNSUPPORTED;
-  static int coop = -1, sms = 0;
+  if (smem > kPsMaxSmem) return TRB_ERR_UNSUPPORTED;
+  static int coop = -1, sms = 0, cluster_ok = 0;
   if (coop < 0) {
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    if (cudaFuncSetAttribute(k_sweep_persistent, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             200 * 1024) != cudaSuccess) {
+    if (cudaFuncSetAttribute(k_sweep_persistent<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)kPsMaxSmem) != cudaSuccess) {
       cudaGetLastError();
       coop = 0;
     }
+    cluster_ok = cudaFuncSetAttribute(k_sweep_persistent<true>,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)kPsMaxSmem) == cudaSuccess &&
+                 cudaFuncSetAttribute(k_sweep_persistent<true>,
+                                      cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess;
+    cudaGetLastError();
+  }
+  trb_sweep desc = *sw;
+  int ld = ldmax;
+  const bool want_cluster = mode == 3 || (mode != 2 && bytes <= kClusterMaxBytes);
+  if (want_cluster && cluster_ok && sw->R >= 16) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(16, 1, 1);
+    cfg.blockDim = dim3(kPsThreads, 1, 1);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 16;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    trb_launch_scope scope_(0, st);
+    const cudaError_t e = cudaLaunchKernelEx(&cfg, k_sweep_persistent<true>, desc, it0, n_iter, fresh, ld);
+    if (e == cudaSuccess) return TRB_OK;
+    cudaGetLastError();
+    cluster_ok = 0;  // this device refuses the 16-CTA cluster: use the grid variant from now on
+    if (mode == 3)
+      return trb_set_error(TRB_ERR_CUDA, "k_sweep_persistent<cluster>: %s", cudaGetErrorString(e));
+  } else if (mode == 3) {
+    return TRB_ERR_UNSUPPORTED;
   }
   if (!coop || sms <= 0) return TRB_ERR_UNSUPPORTED;
   int per_sm = 0;
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_sweep_persistent, kPsThreads, smem) !=
-          cudaSuccess ||
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_sweep_persistent<false>, kPsThreads,
+                                                    smem) != cudaSuccess ||
       per_sm < 1) {
     cudaGetLastError();
     return TRB_ERR_UNSUPPORTED;
   }
   int grid = sms;
   if (grid > sw->R) grid = sw->R;  // at least one singular index per CTA
-  trb_sweep desc = *sw;
-  int ld = ldmax;
   void* args[] = {&desc, &it0, &n_iter, &fresh, &ld};
   trb_launch_scope scope_(0, st);
-  const cudaError_t e = cudaLaunchCooperativeKernel((void*)k_sweep_persistent, dim3(grid),
+  const cudaError_t e = cudaLaunchCooperativeKernel((void*)k_sweep_persistent<false>, dim3(grid),
                                                     dim3(kPsThreads), args, smem, st);
   if (e != cudaSuccess) {
     cudaGetLastError();
