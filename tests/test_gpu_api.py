@@ -402,6 +402,46 @@ def test_linear_channel_factor_api(golden_dir):
             assert_allclose(A, lin[f"lin{i}_{j}_A"], rtol=1e-9)
 
 
+@pytest.mark.parametrize("idx", [0, 2, 5])
+def test_gram_factorisation_matches_reference(sw, idx):
+    """svd_method="auto" factorises a well-conditioned W through the eigen-
+    decomposition of its smaller Gram matrix (cheaper set-up); the sweep still
+    matches the reference to 1e-9."""
+    from tramp_b200.algos import ExpectationPropagation, TrackErrors
+    from tramp_b200.priors import get_prior
+    from tramp_b200.likelihoods import get_likelihood
+    from tramp_b200.channels import LinearChannel
+    from tramp_b200.channels.linear_channel import thin_svd_device
+    from tramp_b200.variables import SISOVariable as V
+    from tramp_b200 import ops
+    cfg = _configs(sw)[idx]
+    name = cfg["name"]
+    W = sw[name + "_W"]
+    pk = {k: v for k, v in cfg["prior"].items() if k != "kind"}
+    lk = {k: v for k, v in cfg["lik"].items() if k != "kind"}
+    lin = LinearChannel(W, svd_method="auto")
+    model = (get_prior(size=cfg["N"], prior_type=cfg["prior"]["kind"], **pk) @ V("x") @ lin @ V("z")
+             @ get_likelihood(y=sw[name + "_y"], likelihood_type=cfg["lik"]["kind"], **lk)).to_model()
+    ep = ExpectationPropagation(model)
+    track = TrackErrors({"x": sw[name + "_x"]})
+    ep.iterate(max_iter=cfg["n_iter"], callback=track, damping=cfg["damping"])
+    s_ref = np.linalg.svd(W, compute_uv=False)
+    assert_allclose(lin.s.cpu().numpy()[0], s_ref, rtol=1e-12)
+    assert lin.rank == np.linalg.matrix_rank(W)
+    mse = np.array([e["mse"] for e in track.errors])
+    ref = sw[name + "_mse"]
+    tau_x = np.mean(sw[name + "_x"]**2)
+    assert np.all(np.abs(mse - ref) <= 1e-9 * ref + 2e-9 * np.sqrt(ref * tau_x))
+    ref = sw[name + "_rx"]
+    assert_allclose(ep.get_variables_data()["x"]["r"], ref, rtol=1e-9, atol=1e-9 * np.abs(ref).max())
+    # an ill-conditioned matrix falls back to the SVD
+    Wd = ops.to_dev(W.copy())[None]
+    Wd[0, -1] = Wd[0, 0] * (1 + 1e-9)
+    s_auto = thin_svd_device(Wd, "auto")[1]
+    s_svd = thin_svd_device(Wd, "svd")[1]
+    assert_allclose(s_auto.cpu().numpy(), s_svd.cpu().numpy(), rtol=1e-12, atol=1e-18)
+
+
 def test_scenario_and_glm_generative():
     """BayesOptimalScenario.setup/run_ep/ep_convergence on glm_generative
     (reference experiments/teacher_student_scenario.py:45-115)."""

@@ -33,12 +33,12 @@ N, RHO, NOISE = 1000, 0.05, 1e-2
 SEEDS = range(5)
 
 
-def run_gpu(alpha, seed):
+def run_gpu(alpha, seed, svd_method="svd"):
     M = int(alpha * N)
     A = GaussianEnsemble(M=M, N=N).generate()
     torch.cuda.synchronize()
     t0 = time.perf_counter()
-    lin = LinearChannel(A)
+    lin = LinearChannel(A, svd_method=svd_method)
     lin._setup()                      # the reference factorises in the constructor
     model = (GaussBernoulliPrior(size=N, rho=RHO) @ V("x") @ lin @ V("z")
              @ GaussianChannel(var=NOISE) @ O("y")).to_model()
@@ -77,12 +77,15 @@ def run_cpu(A, scenario):
 def main():
     torch.cuda.set_device(0)
     np.random.seed(123)
-    run_gpu(0.3, 0)                   # warm-up: CUDA context, cuSOLVER handle, module load
+    run_gpu(0.3, 0)                   # warm-up: CUDA context, cuSOLVER handles, module load
+    run_gpu(0.3, 0, "auto")
     out = dict(protocol="examples/figures/compute_benchmark.py", N=N, rho=RHO, noise_var=NOISE,
                seeds=len(SEEDS), device=torch.cuda.get_device_name(0), host_cores=os.cpu_count(), rows=[])
     for alpha, published in PUBLISHED:
-        gpu, cpu = [], []
+        gpu, cpu, auto = [], [], []
         for seed in SEEDS:
+            np.random.seed(1000 + seed)
+            auto.append(run_gpu(alpha, seed, "auto")[0])      # svd_method="auto": Gram + eigh when cond^2 <= 1e4
             np.random.seed(1000 + seed)
             rec, A, scenario = run_gpu(alpha, seed)
             gpu.append(rec)
@@ -97,6 +100,11 @@ def main():
                    cpu_port_total_s=med(cpu, lambda r: r["time"] + r["svd_time"]),
                    cpu_port_ep_s=med(cpu, lambda r: r["time"]), cpu_port_n_iter=med(cpu, lambda r: r["n_iter"]),
                    cpu_port_mse_over_rho=med(cpu, lambda r: r["mse"]) / RHO)
+        row.update(gpu_auto_total_s=med(auto, lambda r: r["time"] + r["svd_time"]),
+                   gpu_auto_svd_s=med(auto, lambda r: r["svd_time"]),
+                   gpu_auto_mse_over_rho=med(auto, lambda r: r["mse"]) / RHO,
+                   gpu_auto_n_iter=med(auto, lambda r: r["n_iter"]))
+        row["speedup_vs_published_auto"] = published / row["gpu_auto_total_s"]
         row["speedup_vs_published"] = published / row["gpu_total_s"]
         row["speedup_vs_cpu_port_same_host"] = row["cpu_port_total_s"] / row["gpu_total_s"]
         if alpha in PUBLISHED_MSE_OVER_RHO:
