@@ -205,3 +205,39 @@ def test_wishart_singular_values_follow_the_gaussian_ensemble():
     assert abs((s**2).mean() - (d**2).mean()) < 0.01          # E tr(W W^T)/M = 1
     assert abs(s[:, 0].mean() - d[:, 0].mean()) < 0.02 and abs(s[:, -1].mean() - d[:, -1].mean()) < 0.02
     assert abs((s**4).mean() - (d**4).mean()) < 0.05
+
+
+def test_thin_svd_methods_on_cpu_tensors():
+    """The set-up factorisations are plain tensor algebra (cuSOLVER through torch on
+    the GPU): "gram" loses orthogonality like eps * cond(W)^2, "auto" uses it only
+    when cond(W)^2 <= 1e4 and falls back to the SVD otherwise (also for
+    rank-deficient W, where the Gram matrix cannot resolve the numerical rank)."""
+    import torch
+    from tramp_b200.channels.linear_channel import thin_svd_device
+    rng = np.random.RandomState(0)
+
+    def quality(W, method):
+        Ut, s, Vt = thin_svd_device(torch.tensor(W)[None], method)
+        R = s.shape[1]
+        eye = torch.eye(R, dtype=torch.float64)
+        rec = (Ut.transpose(1, 2) * s[:, None, :]) @ Vt
+        return (s[0].numpy(), float((rec[0] - torch.tensor(W)).abs().max()),
+                float((Vt[0] @ Vt[0].T - eye).abs().max()), float((Ut[0] @ Ut[0].T - eye).abs().max()))
+    for M, N in ((60, 120), (120, 60)):
+        W = rng.randn(M, N) / np.sqrt(N)
+        s_ref = np.linalg.svd(W, compute_uv=False)
+        for method in ("svd", "gram", "auto"):
+            s, rec, orth_v, orth_u = quality(W, method)
+            np.testing.assert_allclose(s, s_ref, rtol=1e-12)
+            assert rec < 1e-13 and orth_v < 1e-12 and orth_u < 1e-12
+    W = rng.randn(80, 80) / np.sqrt(80)             # square Gaussian: cond^2 ~ 1e5 ... 1e7
+    s_svd = quality(W, "svd")
+    s_auto = quality(W, "auto")
+    assert (s_svd[0][0] / s_svd[0][-1])**2 > 1e4
+    np.testing.assert_array_equal(s_auto[0], s_svd[0])          # fell back: identical factorisation
+    W[-1] = W[0]                                    # rank deficient
+    s_auto, s_svd = quality(W, "auto"), quality(W, "svd")
+    np.testing.assert_array_equal(s_auto[0], s_svd[0])
+    assert s_auto[0][-1] < 1e-12
+    with pytest.raises(ValueError):
+        thin_svd_device(torch.tensor(W)[None], "qr")
