@@ -265,3 +265,7 @@ def test_early_stopping_callback_logic():
     assert drive([1, .9, .8, .7, .6, .5, .4, .9]) == (7, 6)                     # increase after wait
     assert drive([1, .9, .8, .7, 1.2, .5, .4, .3, .2, .1])[0] is None           # early increase tolerated
     assert drive([1.0, 0.5, 0.05, 0.01], min_variance=0.1) == (2, None)
+    # a batched algorithm hands one array per variable: every instance must satisfy the test
+    arr = lambda *rows: [np.array(r) for r in rows]
+    assert drive(arr([1.0, 1.0], [0.5, 0.5], [0.5 + 5e-7, 0.4], [0.5 + 6e-7, 0.4 + 1e-7])) == (3, None)
+    assert drive(arr([1.0, 1.0], [0.5, 0.5], [0.2, float("nan")])) == (2, 1)

@@ -332,23 +332,25 @@ class EarlyStopping(Callback):
         if (i == 0):
             self.old_vs = None
         variables_data = algo.get_variables_data(self.ids)
-        new_vs = [data["v"] for variable_id, data in variables_data.items()]
-        if any(v < self.min_variance for v in new_vs):
-            logger.info(f"early stopping min variance {min(new_vs)}")
+        # one float per variable (reference); a batched algorithm gives one array per
+        # variable and the tests below then hold for every instance at once
+        new_vs = [np.asarray(data["v"], dtype=float) for variable_id, data in variables_data.items()]
+        if any(np.any(v < self.min_variance) for v in new_vs):
+            logger.info(f"early stopping min variance {min(float(np.min(v)) for v in new_vs)}")
             return True
-        if any(np.isnan(v) for v in new_vs):
+        if any(np.any(np.isnan(v)) for v in new_vs):
             logger.warning("early stopping nan values")
             logger.info("restoring old message dag")
             algo.reset_message_dag(self.old_message_dag)
             return True
         if self.old_vs:
-            tols = [np.abs(old_v - new_v) for old_v, new_v in zip(self.old_vs, new_vs)]
-            if max(tols) < self.tol:
+            tol = max(float(np.max(np.abs(old_v - new_v))) for old_v, new_v in zip(self.old_vs, new_vs))
+            if tol < self.tol:
                 logger.info(f"early stopping all tolerances (on v) are below tol={self.tol:.2e}")
                 return True
-            increase = [new_v - old_v for old_v, new_v in zip(self.old_vs, new_vs)]
-            if i > self.wait_increase and max(increase) > self.max_increase:
-                logger.info(f"increase={max(increase)} above max_increase={self.max_increase:.2e}")
+            increase = max(float(np.max(new_v - old_v)) for old_v, new_v in zip(self.old_vs, new_vs))
+            if i > self.wait_increase and increase > self.max_increase:
+                logger.info(f"increase={increase} above max_increase={self.max_increase:.2e}")
                 logger.info("restoring old message dag")
                 algo.reset_message_dag(self.old_message_dag)
                 return True
