@@ -199,6 +199,12 @@ def run_reference(args):
     N = args.n
     M = int(ALPHA * N)
     W, x, y = oracle_instance(np, N, M, seed=1234)
+    try:
+        # torchrun exports OMP_NUM_THREADS=1 to its workers: give BLAS the whole host back
+        from threadpoolctl import threadpool_limits
+        threadpool_limits(limits=os.cpu_count(), user_api="blas")
+    except Exception:
+        pass
     res = time_oracle(np, W, x, y, args.iters, args.steps, args.warmup)
     total = sum(res["step_s"])
     value = args.iters * args.steps / total
