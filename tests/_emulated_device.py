@@ -121,15 +121,22 @@ class EmulatedLibrary:
         return 0
 
 
+def install(setattr_):
+    """Patch the loaded tramp_b200 modules through `setattr_(obj, name, value)`
+    (pytest's monkeypatch.setattr in the fixture, plain setattr in a spawned
+    worker process of a multi-rank test)."""
+    from tramp_b200 import _lib, ops
+    fake = EmulatedLibrary(_lib.load(), _lib)
+    setattr_(ops, "device", lambda: torch.device("cpu"))
+    setattr_(ops, "_quad_cache", {})
+    setattr_(_lib, "require_cuda", lambda: None)
+    setattr_(_lib, "current_stream", lambda: None)
+    setattr_(ops, "current_stream", lambda: None)
+    setattr_(_lib, "load", lambda: fake)
+    return fake
+
+
 @pytest.fixture
 def emulated_device(monkeypatch):
     """tramp_b200 with CPU tensors and the SE kernels emulated by the oracle."""
-    from tramp_b200 import _lib, ops
-    fake = EmulatedLibrary(_lib.load(), _lib)
-    monkeypatch.setattr(ops, "device", lambda: torch.device("cpu"))
-    monkeypatch.setattr(ops, "_quad_cache", {})
-    monkeypatch.setattr(_lib, "require_cuda", lambda: None)
-    monkeypatch.setattr(_lib, "current_stream", lambda: None)
-    monkeypatch.setattr(ops, "current_stream", lambda: None)
-    monkeypatch.setattr(_lib, "load", lambda: fake)
-    return fake
+    return install(monkeypatch.setattr)

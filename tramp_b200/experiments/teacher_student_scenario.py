@@ -138,10 +138,34 @@ def run_state_evolution(x_ids, model, **algo_kwargs):
     return [dict(x_id=x_id, v=x_data[x_id]["v"], n_iter=se.n_iter) for x_id in x_ids]
 
 
-def run_state_evolution_grid(x_ids, models, **algo_kwargs):
+def run_state_evolution_grid(x_ids, models, group=None, **algo_kwargs):
     """The same for a list of models (e.g. `glm_state_evolution` over a grid of
     alpha), all in ONE kernel launch: one CTA per model runs its whole recursion.
-    Returns one list of records per model, `n_iter` being that model's own count."""
+    Returns one list of records per model, `n_iter` being that model's own count.
+
+    Under `torch.distributed` (one process per GPU) the grid is sharded by
+    contiguous blocks of models, like EP instances: every rank runs
+    its block with no data-path collective and the records are all-gathered at
+    the end, so every rank returns the whole grid."""
+    models = list(models)
+    world, rank = 1, 0
+    try:
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized():
+            world, rank = dist.get_world_size(group), dist.get_rank(group)
+    except ImportError:
+        dist = None
+    if world > 1:
+        from ..distributed import instance_shard
+        start, stop = instance_shard(len(models), rank, world)
+        local = _state_evolution_records(x_ids, models[start:stop], **algo_kwargs) if stop > start else []
+        gathered = [None] * world
+        dist.all_gather_object(gathered, local, group=group)
+        return [records for block in gathered for records in block]
+    return _state_evolution_records(x_ids, models, **algo_kwargs)
+
+
+def _state_evolution_records(x_ids, models, **algo_kwargs):
     se = StateEvolution(list(models))
     se.iterate(**algo_kwargs)
     x_data = se.get_variables_data(ids=x_ids)
