@@ -151,3 +151,24 @@ def test_scenario_state_evolution_reproduces_the_reference_run(emulated_device):
     assert list(df.columns) == ["id", "v", "iter"] and len(df) == 30
     assert np.all(np.diff(df.v.values) < 1e-12)
     assert scenario.se.analytical is False and scenario.se.linear.rank == 280
+
+
+def test_tracking_callbacks_on_state_evolution(emulated_device):  # noqa: F811
+    """TrackObjective / TrackMessages (reference callbacks.py:49-85) work on the SE
+    driver through its update_objective / get_edges_data / get_nodes_data."""
+    from tramp_b200.algos import StateEvolution, TrackObjective, TrackMessages, JoinCallback
+    case = SE_RUNS["cs_damped"]
+    se = StateEvolution(make_model(case))
+    obj, msgs = TrackObjective(), TrackMessages(keys=["a", "n_iter", "direction", "damping"])
+    se.iterate(max_iter=4, callback=JoinCallback([obj, msgs]), damping=0.5)
+    edges, nodes, model = obj.get_dataframe()
+    assert len(model) == 4 and list(model.n_iter) == [1, 2, 3, 4]
+    assert np.all(np.isfinite(model.A.values)) and np.all(np.diff(model.A.values) != 0)
+    assert len(edges) == 4 * 8 and len(nodes) == 4 * 5
+    assert set(nodes.type) == {"factor", "variable"} and nodes.A.notna().all()
+    df = msgs.get_dataframe()
+    assert len(df) == 4 * 8 and set(df.direction) == {"fwd", "bwd"}
+    # constant damping sits on the four factor -> variable edges only
+    last = df.tail(8)
+    assert list(last.damping.fillna(0.0)) == [0.5, 0.0, 0.5, 0.0, 0.5, 0.0, 0.5, 0.0]
+    assert_allclose(-model.A.values[-1], se.entropy(), rtol=1e-12)
