@@ -4,7 +4,6 @@ import sys, os, json, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from tramp_b200 import ops, _lib
-import ctypes as C
 
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 128
 N, M = 4096, 2048

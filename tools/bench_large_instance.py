@@ -15,7 +15,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 import torch
 import torch.distributed as dist
-from tramp_b200 import synthetic, ops, _lib
+from tramp_b200 import synthetic, ops
 from tramp_b200.priors import GaussBernoulliPrior
 from tramp_b200.likelihoods import GaussianLikelihood
 from tramp_b200.channels import LinearChannel

@@ -8,7 +8,7 @@ import json, os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 import torch
-from tramp_b200 import synthetic, ops
+from tramp_b200 import synthetic
 from tramp_b200.priors import BinaryPrior
 from tramp_b200.likelihoods import AbsLikelihood
 from tramp_b200.channels import LinearChannel

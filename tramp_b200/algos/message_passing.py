@@ -18,7 +18,7 @@ import numpy as np
 from .callbacks import Callback
 from .initial_conditions import ConstantInit
 from ..models import Model
-from ..base import Variable, Factor
+from ..base import Variable
 from ..priors import Prior
 from ..likelihoods import Likelihood
 from ..channels import LinearChannel
