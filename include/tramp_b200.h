@@ -3,8 +3,8 @@
  * The reference (sphinxteam/tramp) is pure Python/numpy and has NO FFI: its
  * plugin boundary is the Python factor protocol (compute_forward_posterior,
  * compute_backward_message, ... -- tramp/base.py:329-365, docs/implementation
- * .rst:41-147).  tramp_b200 keeps that protocol in Python (tramp_b200/*.py) and
- * adds this thin C layer underneath; each entry point below cites the reference
+ * .rst:41-147).  tramp_b200 keeps that protocol in Python (the tramp_b200
+ * package) and adds this thin C layer underneath; each entry point below cites the reference
  * routine whose arithmetic it replaces.  INTEGRATION.md shows the ctypes stubs
  * a tramp maintainer would add to call it.
  *

@@ -241,3 +241,23 @@ def test_thin_svd_methods_on_cpu_tensors():
     assert s_auto[0][-1] < 1e-12
     with pytest.raises(ValueError):
         thin_svd_device(torch.tensor(W)[None], "qr")
+
+
+def test_c_abi_from_plain_c(tmp_path):
+    """include/tramp_b200.h is valid C99 (no C++-isms, no torch types) and a C
+    program links against the shared library with nothing else."""
+    import shutil
+    import subprocess
+    from tramp_b200 import _lib
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc")
+    _lib.load()
+    exe = str(tmp_path / "c_abi_client")
+    libdir = os.path.dirname(_lib.LIB_PATH)
+    cmd = ["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(ROOT, "include"),
+           os.path.join(ROOT, "tests", "c_abi_client.c"), "-o", exe, "-L", libdir, "-ltramp_b200",
+           "-Wl,-rpath," + libdir]
+    build = subprocess.run(cmd, capture_output=True, text=True)
+    assert build.returncode == 0, build.stderr
+    run = subprocess.run([exe], capture_output=True, text=True)
+    assert run.returncode == 0 and run.stdout.startswith("ok"), (run.returncode, run.stdout, run.stderr)
