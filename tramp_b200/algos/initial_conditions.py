@@ -1,88 +1,93 @@
-"""Initial conditions of the messages (reference tramp/algos/initial_conditions.py).
+"""Initial values of the messages (reference tramp/algos/initial_conditions.py).
 
-`shape` is the variable's shape: (N,) for one instance, (B, N) for a batch (then
-`a` may be a scalar shared by all instances or an array of B values)."""
+The driver asks `initializer.init(key, shape, variable_id, direction)` for every
+edge, `key` being "a" (precision) or "b" (natural mean); `shape` is the
+variable's shape -- (N,) for one instance, (B, N) for a batch -- and is None
+under State Evolution, which only asks for "a".  The eight edges are visited in
+the order e1..e8, "a" before "b", which fixes how `NoisyInit`
+consumes numpy's global random stream.
+"""
 import numpy as np
+
 from ..base import ReprMixin
 
 
+def _filled(shape, value):
+    if shape is None:
+        raise AssertionError("the shape of the variable is unknown (call model.init_shapes())")
+    return np.full(shape, value, dtype=float)
+
+
 class InitialConditions(ReprMixin):
+    """Dispatches `init("a" | "b", ...)` to `init_a` / `init_b` (reference :5-10)."""
+
     def init(self, message_key, shape, id, direction):
-        if message_key == "a":
-            return self.init_a(shape, id, direction)
-        if message_key == "b":
-            return self.init_b(shape, id, direction)
+        handler = {"a": self.init_a, "b": self.init_b}.get(message_key)
+        return None if handler is None else handler(shape, id, direction)
 
 
 class ConstantInit(InitialConditions):
-    """reference initial_conditions.py:13-24."""
+    """Every edge starts at the same (a, b) (reference :13-24)."""
 
     def __init__(self, a=0, b=0):
-        self.a = a
-        self.b = b
+        self.a, self.b = a, b
         self.repr_init()
 
     def init_a(self, shape, id, direction):
         return self.a
 
     def init_b(self, shape, id, direction):
-        assert shape is not None
-        return self.b * np.ones(shape)
+        return _filled(shape, self.b)
 
 
 class NoisyInit(InitialConditions):
-    """reference initial_conditions.py:27-42.  Draws use numpy's global RNG in
-    the edge order e1..e8, `a` then `b` for each edge."""
+    """Gaussian initial messages, a ~ N(a_mean, a_var) (one draw per edge) and
+    b ~ N(b_mean, b_var) elementwise, from numpy's global RNG (reference :27-42)."""
 
     def __init__(self, a_mean=0, a_var=0, b_mean=0, b_var=1):
-        self.a_mean = a_mean
-        self.a_var = a_var
-        self.b_mean = b_mean
-        self.b_var = b_var
+        self.a_mean, self.a_var = a_mean, a_var
+        self.b_mean, self.b_var = b_mean, b_var
         self.repr_init()
-        self.a_sigma = np.sqrt(a_var)
-        self.b_sigma = np.sqrt(b_var)
+        self.a_sigma, self.b_sigma = np.sqrt(a_var), np.sqrt(b_var)
 
     def init_a(self, shape, id, direction):
-        return self.a_mean + self.a_sigma * np.random.standard_normal()
+        noise = np.random.standard_normal()
+        return self.a_mean + self.a_sigma * noise
 
     def init_b(self, shape, id, direction):
-        assert shape is not None
-        return self.b_mean + self.b_sigma * np.random.standard_normal(shape)
+        if shape is None:
+            raise AssertionError("the shape of the variable is unknown (call model.init_shapes())")
+        noise = np.random.standard_normal(shape)
+        return self.b_mean + self.b_sigma * noise
 
 
 class CustomInit(InitialConditions):
-    """Custom init on variables (reference initial_conditions.py:45-85).
+    """Chosen values on chosen edges, constants elsewhere (reference :45-85).
 
-    - a_init: list of (variable.id, direction, a) tuples
-    - b_init: list of (variable.id, direction, b) tuples
-    - a, b : default constants
-    """
+    a_init / b_init: lists of (variable id, direction, value); an entry applies to
+    both edges of that variable with that direction (factor -> variable and
+    variable -> factor).  a, b: the constants used for every other edge."""
 
     def __init__(self, a_init=None, b_init=None, a=0, b=0):
-        a_init = a_init or []
-        self.a_init = {}
-        for id, direction, a_ in a_init:
-            self.a_init.setdefault(id, {})[direction] = a_
-        b_init = b_init or []
-        self.b_init = {}
-        for id, direction, b_ in b_init:
-            self.b_init.setdefault(id, {})[direction] = b_
-        self.a = a
-        self.b = b
+        self.a_init = self._table(a_init)
+        self.b_init = self._table(b_init)
+        self.a, self.b = a, b
         self.repr_init()
 
+    @staticmethod
+    def _table(entries):
+        table = {}
+        for variable_id, direction, value in (entries or []):
+            table.setdefault(variable_id, {})[direction] = value
+        return table
+
     def init_a(self, shape, id, direction):
-        try:
-            return self.a_init[id][direction]
-        except KeyError:
-            return self.a
+        return self.a_init.get(id, {}).get(direction, self.a)
 
     def init_b(self, shape, id, direction):
-        assert shape is not None
-        try:
-            b = self.b_init[id][direction]
-            assert b.shape == shape
-        except KeyError:
-            b = self.b * np.ones(shape)
-        return b
+        chosen = self.b_init.get(id, {}).get(direction)
+        if chosen is None:
+            return _filled(shape, self.b)
+        if shape is None or chosen.shape != shape:
+            raise AssertionError(f"b_init of {id!r} ({direction}) has shape {chosen.shape}, expected {shape}")
+        return chosen

@@ -1,25 +1,15 @@
-"""Positive (half-line truncated normal) belief (reference tramp/beliefs/positive.py:8-26)."""
-import numpy as np
-from ..utils.truncated_normal import (
-    truncated_normal_mean, truncated_normal_var, truncated_normal_logZ, truncated_normal_proba
-)
+"""Positive belief: the truncated normal on the half line [0, inf) (reference
+tramp/beliefs/positive.py:8-26), i.e. `truncated` with fixed bounds; the device
+routine takes its erfcx fast path for a half-infinite interval."""
+import functools
+import math
 
+from . import truncated
 
-def A(a, b):
-    return truncated_normal_logZ(b / a, 1 / a, 0, np.inf)
+_HALF_LINE = dict(xmin=0, xmax=math.inf)
 
-
-def r(a, b):
-    return truncated_normal_mean(b / a, 1 / a, 0, np.inf)
-
-
-def v(a, b):
-    return truncated_normal_var(b / a, 1 / a, 0, np.inf)
-
-
-def tau(a, b):
-    return r(a, b)**2 + v(a, b)
-
-
-def p(a, b):
-    return truncated_normal_proba(b / a, 1 / a, 0, np.inf)
+A = functools.partial(truncated.A, **_HALF_LINE)
+r = functools.partial(truncated.r, **_HALF_LINE)
+v = functools.partial(truncated.v, **_HALF_LINE)
+p = functools.partial(truncated.p, **_HALF_LINE)
+tau = functools.partial(truncated.tau, **_HALF_LINE)

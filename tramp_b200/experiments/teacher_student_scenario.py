@@ -1,5 +1,11 @@
-"""Teacher-student scenarios, EP and State Evolution (reference
-tramp/experiments/teacher_student_scenario.py)."""
+"""Teacher-student scenarios (reference tramp/experiments/teacher_student_scenario.py).
+
+A teacher model generates a signal and its measurements, a student model -- the
+same model in the Bayes-optimal case -- is given the measurements and estimates
+the signal, by Expectation Propagation on the instance (`run_ep`) and, for the
+average case, by State Evolution (`run_se`).  Both run on the GPU
+(tramp_b200.algos); this module is the glue the reference's examples call.
+"""
 import logging
 import pandas as pd
 
@@ -11,110 +17,107 @@ from ..algos import (TrackErrors, TrackEvolution, JoinCallback, ExpectationPropa
 logger = logging.getLogger(__name__)
 
 
-class TeacherStudentScenario():
-    """Implements teacher student scenario (reference :10-141, EP part).
+def _with_trackers(trackers, algo_kwargs):
+    """algo_kwargs with `trackers` joined in front of the caller's callback."""
+    callbacks = list(trackers)
+    if "callback" in algo_kwargs:
+        callbacks.append(algo_kwargs["callback"])
+    return dict(algo_kwargs, callback=JoinCallback(callbacks))
 
-    - teacher : Model instance or any object with a `.sample()` method
-    - student : Model instance, generative student model
-    - x_ids : ids of the variables to infer (signals)
-    - y_ids : ids of the observed variables (measurements)
-    """
+
+class TeacherStudentScenario():
+    """teacher : a Model, or any object with a `.sample()` method returning
+                {variable id: array}
+    student : Model, the generative model the student assumes
+    x_ids   : ids of the variables to infer (signals)
+    y_ids   : ids of the observed variables (measurements)
+    (reference :10-141)"""
 
     def __init__(self, teacher, student, x_ids=["x"], y_ids=["y"]):
         if not isinstance(student, Model):
             raise ValueError("student not a Model")
-        try:
-            sample = teacher.sample()      # reference :27 (advances the RNG once)
-        except AttributeError:
+        if not hasattr(teacher, "sample"):
             raise ValueError("teacher does not have a .sample() method")
-        for x_id in x_ids:
-            if x_id not in student.variable_ids:
-                raise ValueError(f"x_id = {x_id} not in student variable_ids")
-            if x_id not in sample:
-                raise ValueError(f"x_id = {x_id} not in teacher variable_ids")
-        for y_id in y_ids:
-            if y_id not in student.variable_ids:
-                raise ValueError(f"y_id = {y_id} not in  student variable_ids")
-            if y_id not in sample:
-                raise ValueError(f"y_id = {y_id} not in teacher variable_ids")
-        self.x_ids = x_ids
-        self.y_ids = y_ids
-        self.teacher = teacher
-        self.generative_student = student
+        # one draw, only to learn the teacher's variable ids: like the reference
+        # (:27) this advances numpy's global RNG before `setup`
+        known_to_teacher = teacher.sample()
+        for role, ids in (("x_id", x_ids), ("y_id", y_ids)):
+            for variable_id in ids:
+                if variable_id not in student.variable_ids:
+                    raise ValueError(f"{role} = {variable_id} not in student variable_ids")
+                if variable_id not in known_to_teacher:
+                    raise ValueError(f"{role} = {variable_id} not in teacher variable_ids")
+        self.x_ids, self.y_ids = x_ids, y_ids
+        self.teacher, self.generative_student = teacher, student
 
     def setup(self, seed=0):
-        sample = self.teacher.sample(seed)
-        self.true_values = sample
-        self.x_true = {x_id: sample[x_id] for x_id in self.x_ids}
-        self.observations = {y_id: sample[y_id] for y_id in self.y_ids}
+        "The teacher draws the instance; the student gets the measurements (reference :45-52)"
+        self.true_values = self.teacher.sample(seed)
+        self.x_true = {x_id: self.true_values[x_id] for x_id in self.x_ids}
+        self.observations = {y_id: self.true_values[y_id] for y_id in self.y_ids}
         self.student = self.generative_student.to_observed(self.observations)
 
+    # ---------------------------------------------------------------- one run
+    def _run(self, algo, algo_kwargs):
+        algo.iterate(**algo_kwargs)
+        x_data = algo.get_variables_data(self.x_ids)
+        x_data["n_iter"] = algo.n_iter
+        return x_data
+
+    def run_se(self, **algo_kwargs):
+        """State Evolution of the observed student -- its LinearChannel enters
+        through its own spectrum (reference :84-89)."""
+        self.se = StateEvolution(self.student)      # kept: a failed run can still be inspected
+        return self._run(self.se, algo_kwargs)
+
+    def run_ep(self, **algo_kwargs):
+        "Expectation Propagation on the instance (reference :91-97)"
+        self.ep = ExpectationPropagation(self.student)
+        x_data = self._run(self.ep, algo_kwargs)
+        self.x_pred = {x_id: x_data[x_id]["r"] for x_id in self.x_ids}
+        return x_data
+
     def run_all(self, source="EP,SE", metrics=["mse"], **algo_kwargs):
-        "Get mse values as estimated by EP or SE (reference :54-82)"
+        """Records of the variance predicted by SE, the variance EP reports and the
+        error EP actually makes (reference :54-82)."""
         self.setup()
         records = []
+
+        def variance_records(name, x_data):
+            return [dict(source=name, x_id=x_id, v=x_data[x_id]["v"], n_iter=x_data["n_iter"])
+                    for x_id in self.x_ids]
         if "SE" in source:
-            x_data = self.run_se(**algo_kwargs)
-            records += [dict(source="SE", x_id=x_id, v=x_data[x_id]["v"], n_iter=x_data["n_iter"])
-                        for x_id in self.x_ids]
+            records += variance_records("SE", self.run_se(**algo_kwargs))
         if "EP" in source:
-            x_data = self.run_ep(**algo_kwargs)
-            records += [dict(source="EP", x_id=x_id, v=x_data[x_id]["v"], n_iter=x_data["n_iter"])
-                        for x_id in self.x_ids]
-            x_pred = {x_id: x_data[x_id]["r"] for x_id in self.x_ids}
-            score = self.compute_score(x_pred, metrics=metrics)
+            records += variance_records("EP", self.run_ep(**algo_kwargs))
+            score = self.compute_score(self.x_pred, metrics=metrics)
             records += [dict(source=metric, x_id=x_id, v=score[x_id][metric])
                         for metric in metrics for x_id in self.x_ids]
         return records
 
-    def run_se(self, **algo_kwargs):
-        """State Evolution of the observed student (its LinearChannel enters
-        through its own spectrum); reference :84-89."""
-        se = StateEvolution(self.student)
-        se.iterate(**algo_kwargs)
-        x_data = se.get_variables_data(self.x_ids)
-        x_data["n_iter"] = se.n_iter
-        self.se = se
-        return x_data
-
-    def run_ep(self, **algo_kwargs):
-        ep = ExpectationPropagation(self.student)
-        ep.iterate(**algo_kwargs)
-        x_data = ep.get_variables_data(self.x_ids)
-        x_data["n_iter"] = ep.n_iter
-        self.x_pred = {x_id: x_data[x_id]["r"] for x_id in self.x_ids}
-        self.ep = ep
-        return x_data
-
+    # ----------------------------------------------------------- trajectories
     def ep_convergence(self, metrics, **algo_kwargs):
-        track = TrackErrors(true_values=self.x_true, metrics=metrics)
-        evo = TrackEvolution(ids=self.x_ids)
-        callbacks = [track, evo]
-        if "callback" in algo_kwargs:
-            callbacks.append(algo_kwargs["callback"])
-        algo_kwargs["callback"] = JoinCallback(callbacks)
+        "Per-iteration errors and variances of EP (reference :99-115)"
+        errors = TrackErrors(true_values=self.x_true, metrics=metrics)
+        evolution = TrackEvolution(ids=self.x_ids)
         try:
-            self.run_ep(**algo_kwargs)
+            self.run_ep(**_with_trackers([errors, evolution], algo_kwargs))
         except Exception as e:
             logger.error(e)
-        df = pd.merge(track.get_dataframe(), evo.get_dataframe(), on=["id", "iter"])
+        df = pd.merge(errors.get_dataframe(), evolution.get_dataframe(), on=["id", "iter"])
         if not self.ep.batched:
-            for y in ["v"] + metrics:
-                df[y] = df[y].clip(0, 2)
+            for column in ["v"] + metrics:
+                df[column] = df[column].clip(0, 2)
         return df
 
     def se_convergence(self, **algo_kwargs):
-        "v of the x_ids along the SE iterations (reference :117-130)"
-        evo = TrackEvolution(ids=self.x_ids)
-        callbacks = [evo]
-        if "callback" in algo_kwargs:
-            callbacks.append(algo_kwargs["callback"])
-        algo_kwargs["callback"] = JoinCallback(callbacks)
+        "Per-iteration variances of State Evolution (reference :117-130)"
+        evolution = TrackEvolution(ids=self.x_ids)
         try:
-            self.run_se(**algo_kwargs)
+            self.run_se(**_with_trackers([evolution], algo_kwargs))
         except Exception as e:
             logger.error(e)
-        df = evo.get_dataframe()
+        df = evolution.get_dataframe()
         df["v"] = df["v"].clip(0, 2)
         return df
 
@@ -124,7 +127,7 @@ class TeacherStudentScenario():
 
 
 class BayesOptimalScenario(TeacherStudentScenario):
-    """Same generative model for teacher and student (reference :143-155)."""
+    """The student knows the teacher's model (reference :143-155)."""
 
     def __init__(self, model, x_ids=["x"], y_ids=["y"]):
         super().__init__(teacher=model, student=model, x_ids=x_ids, y_ids=y_ids)

@@ -19,11 +19,22 @@ def _run(r0, v0, zmin, zmax, which):
         r0_d, v0_d = t.broadcast_tensors(ops.to_dev(r0), ops.to_dev(v0))
         shape = tuple(r0_d.shape)
         r0_d, v0_d = r0_d.reshape(-1).contiguous(), v0_d.reshape(-1).contiguous()
-    out = ops.truncated_normal(r0_d, v0_d, zmin, zmax)[which].reshape(shape)
-    if numpy_out:
-        out = out.cpu().numpy()
-        return float(out) if not shape else out
-    return out
+    outs = ops.truncated_normal(r0_d, v0_d, zmin, zmax)
+
+    def give(out):
+        out = out.reshape(shape)
+        if numpy_out:
+            out = out.cpu().numpy()
+            return float(out) if not shape else out
+        return out
+    if which is None:
+        return tuple(give(o) for o in outs)
+    return give(outs[which])
+
+
+def truncated_normal_moments(r0, v0, zmin, zmax, only=None):
+    """(mean, var, logZ, proba) from ONE launch; `only` = 0..3 returns that one."""
+    return _run(r0, v0, zmin, zmax, only)
 
 
 def truncated_normal_mean(r0, v0, zmin, zmax):
