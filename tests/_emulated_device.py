@@ -1,6 +1,8 @@
-"""Test infrastructure: run the HOST side of tramp_b200's State Evolution on CPU
-tensors, with the two C entry points it calls (`trb_se_run`, `trb_se_measure`)
-emulated by the oracle evaluated with the kernels' quadrature rule.
+"""Test infrastructure: run the HOST side of tramp_b200 on CPU tensors, with the C
+entry points of the two drivers emulated by the oracle: `trb_se_run` /
+`trb_se_measure` (State Evolution, oracle evaluated with the kernels' quadrature
+rule) and `trb_sweep_run` / `trb_sweep_stage` (the EP sweep, oracle `ep_glm` one
+iteration at a time with the kernels' early-stopping and roll-back decisions).
 
 This exists so that `-m "not gpu"` covers the Python glue around the kernels
 (initialisers, damping configuration, record replay into callbacks, snapshots,
@@ -15,6 +17,7 @@ import pytest
 import torch
 
 from oracle import se_oracle as S
+from oracle import tramp_oracle as O
 
 
 def _arr(ptr, n, dtype=np.float64):
@@ -48,7 +51,8 @@ class EmulatedLibrary:
     def __init__(self, real, lib_module):
         self._real, self._lib = real, lib_module
         self._gl = S.Integrator("gl")
-        self.calls = dict(trb_se_run=0, trb_se_measure=0)
+        self.calls = dict(trb_se_run=0, trb_se_measure=0, trb_sweep_run=0, sweep_iterations=0)
+        self._ops_cache = {}
 
     def __getattr__(self, name):
         return getattr(self._real, name)
@@ -133,7 +137,128 @@ def install(setattr_):
     setattr_(_lib, "current_stream", lambda: None)
     setattr_(ops, "current_stream", lambda: None)
     setattr_(_lib, "load", lambda: fake)
+    # `tensor.cpu().numpy()` copies from a GPU but ALIASES a CPU tensor: hand out copies,
+    # as a device read-back does, or a callback's "previous" estimate changes under it
+    from tramp_b200.algos import message_passing as mp
+    read_back = mp.MessagePassing._out
+
+    def read_back_copy(self, *args, **kwargs):
+        out = read_back(self, *args, **kwargs)
+        return out.copy() if isinstance(out, np.ndarray) else out
+    setattr_(mp.MessagePassing, "_out", read_back_copy)
     return fake
+
+
+# the EP sweep ---------------------------------------------------------------
+def _rms(x):
+    return np.sqrt(np.mean(x**2))
+
+
+def _sweep_run(self, sw_ref, it0, n_iter, fresh, stream):
+    """trb_sweep_run on host pointers: every iteration is one oracle iteration
+    started from the current messages; records, EarlyStoppingEP decisions, NaN
+    handling and the one-iteration-back roll-back follow k_x_update / k_snapshot."""
+    L = self._lib
+    sw = sw_ref._obj
+    self.calls["trb_sweep_run"] += 1
+    B, N, M, R, ldn, ldm = sw.B, sw.N, sw.M, sw.R, sw.ldn, sw.ldm
+    ea = _arr(sw.edge_a, 8 * B).reshape(8, B)
+    vec = {k: _arr(getattr(sw, k), B * ld).reshape(B, ld)
+           for k, ld in (("b1", ldn), ("b7", ldn), ("rx", ldn), ("b3", ldm), ("b5", ldm), ("rz", ldm))}
+    y = _arr(sw.y, B * ldm).reshape(B, ldm)
+    xt = _arr(sw.x_true, B * ldn).reshape(B, ldn) if sw.x_true else None
+    b6i = _arr(sw.b6_init, B * ldm).reshape(B, ldm) if sw.b6_init else None
+    b8i = _arr(sw.b8_init, B * ldn).reshape(B, ldn) if sw.b8_init else None
+    vx, vz = _arr(sw.vx, B), _arr(sw.vz, B)
+    act, fl, ni = (_arr(p, B, np.int32) for p in (sw.active, sw.flags, sw.n_iter))
+    rec = {k: (_arr(getattr(sw, "rec_" + k), sw.max_records * B).reshape(sw.max_records, B)
+               if getattr(sw, "rec_" + k) else None) for k in ("mse", "smse", "vx", "vz", "tol")}
+    shared = sw.strideV == 0
+    nop = 1 if shared else B
+    Vt = _arr(sw.Vt, nop * R * ldn).reshape(nop, R, ldn)
+    Ut = _arr(sw.Ut, nop * R * ldm).reshape(nop, R, ldm)
+    sv = _arr(sw.s, nop * R).reshape(nop, R)
+    prior, lik0 = _spec_of(sw.prior), _spec_of(sw.lik)
+    damping = dict(e1=sw.damp1, e3=sw.damp3, e5=sw.damp5, e7=sw.damp7)
+    vars_ = sw.es_vars or 3
+    for b in range(B):
+        if not act[b]:
+            continue
+        o = 0 if shared else b
+        key = (sw.Vt, sw.Ut, o)
+        if key not in self._ops_cache:
+            W = (Ut[o, :, :M].T * sv[o]) @ Vt[o, :, :N]
+            self._ops_cache[key] = (W, O.LinearOp(W))
+        W, op = self._ops_cache[key]
+        lik = dict(lik0, y=y[b, :M].copy())
+        for k in range(n_iter):
+            it = it0 + k
+            first = bool(fresh) and k == 0
+            old = {n: v[b].copy() for n, v in vec.items()}
+            old_a, old_v = ea[:, b].copy(), (vx[b], vz[b])
+            b6 = b6i[b, :M] if (first and b6i is not None) else vec["b5"][b, :M]
+            b8 = b8i[b, :N] if (first and b8i is not None) else vec["b7"][b, :N]
+            init = dict(e1=(ea[0, b], vec["b1"][b, :N]), e2=(ea[1, b], vec["b1"][b, :N]),
+                        e3=(ea[2, b], vec["b3"][b, :M]), e4=(ea[3, b], vec["b3"][b, :M]),
+                        e5=(ea[4, b], vec["b5"][b, :M]), e6=(ea[5, b], b6),
+                        e7=(ea[6, b], vec["b7"][b, :N]), e8=(ea[7, b], b8))
+            nan = 0
+            try:
+                with np.errstate(all="ignore"):
+                    r = O.ep_glm(prior, W, lik, 1, damping=damping, init=init, op=op)
+                E = r["edges"]
+                for idx, name in enumerate(("e1", "e2", "e3", "e4", "e5", "e6", "e7", "e8")):
+                    ea[idx, b] = E[name][0]
+                vec["b1"][b, :N], vec["b3"][b, :M] = E["e1"][1], E["e3"][1]
+                vec["b5"][b, :M], vec["b7"][b, :N] = E["e5"][1], E["e7"][1]
+                vec["rx"][b, :N], vec["rz"][b, :M] = r["r_x"], r["r_z"]
+                vx[b], vz[b] = r["v_x"], r["v_z"]
+            except ValueError as e:               # check_message: NaN in a or b
+                nan = L.FLAG_NAN_A if " a is nan" in str(e) else L.FLAG_NAN_B
+            ni[b] += 1
+            self.calls["sweep_iterations"] += 1
+            stop = 0
+            if not nan:
+                if it < sw.max_records:
+                    if rec["vx"] is not None:
+                        rec["vx"][it, b], rec["vz"][it, b] = vx[b], vz[b]
+                    if xt is not None and rec["mse"] is not None:
+                        mse = np.mean((vec["rx"][b, :N] - xt[b, :N])**2)
+                        rec["mse"][it, b] = mse
+                        if rec["smse"] is not None:
+                            rec["smse"][it, b] = min(mse, np.mean((vec["rx"][b, :N] + xt[b, :N])**2))
+                tol = np.nan
+                if it > 0:
+                    with np.errstate(all="ignore"):
+                        tx_ = _rms(vec["rx"][b, :N] - old["rx"][:N]) / _rms(vec["rx"][b, :N])
+                        tz_ = _rms(vec["rz"][b, :M] - old["rz"][:M]) / _rms(vec["rz"][b, :M])
+                    tol = tx_ if vars_ & 1 else tz_
+                    if (vars_ & 2) and tz_ > tol:
+                        tol = tz_
+                    if sw.es_tol >= 0:
+                        if tol < sw.es_tol:
+                            stop = L.FLAG_CONVERGED
+                        elif it > sw.es_wait_increase and tol > sw.es_max_increase:
+                            stop = L.FLAG_DIVERGED
+                if it < sw.max_records and rec["tol"] is not None:
+                    rec["tol"][it, b] = tol
+            if nan or stop == L.FLAG_DIVERGED:    # reset_message_dag(old_message_dag)
+                for n_, v_ in vec.items():
+                    v_[b] = old[n_]
+                ea[:, b] = old_a
+                vx[b], vz[b] = old_v
+                fl[b] |= (nan or stop) | L.FLAG_RESTORED
+                act[b] = 0
+                break
+            if stop:
+                fl[b] |= stop
+                act[b] = 0
+                break
+    return 0
+
+
+EmulatedLibrary.trb_sweep_run = _sweep_run
+EmulatedLibrary.trb_sweep_stage = lambda self, sw_ref, stage, it, first, pre, stream: 0
 
 
 @pytest.fixture

@@ -1,0 +1,112 @@
+"""CPU coverage of the Python side of the EP driver: the public-API calls of
+tests/test_gpu_api.py with `trb_sweep_run` emulated by the oracle
+(tests/_emulated_device.py).  Under test: model compilation, initialisers and
+damping maps into the descriptor, the device-replay and the synchronous callback
+paths, chunked early stopping, snapshots / roll-back, scenarios -- not kernels."""
+import json
+import os
+import numpy as np
+import pytest
+from numpy.testing import assert_allclose
+
+from tests._emulated_device import emulated_device  # noqa: F401  (fixture)
+from tests.test_gpu_api import _build, _configs, _SeqInit
+
+
+@pytest.fixture(scope="module")
+def sw(golden_dir):
+    return np.load(os.path.join(golden_dir, "sweeps.npz"))
+
+
+@pytest.mark.parametrize("idx", [0, 1, 2, 6, 8])
+def test_public_api_reproduces_golden_sweeps(emulated_device, sw, idx):  # noqa: F811
+    from tramp_b200.algos import ExpectationPropagation, TrackErrors, TrackEvolution, JoinCallback
+    cfg = _configs(sw)[idx]
+    name = cfg["name"]
+    ep = ExpectationPropagation(_build(cfg, sw, name))
+    track, evo = TrackErrors({"x": sw[name + "_x"]}), TrackEvolution()
+    init = _SeqInit(sw, name) if cfg.get("init") == "noisy" else None
+    ep.iterate(max_iter=cfg["n_iter"], callback=JoinCallback([track, evo]), initializer=init,
+               damping=cfg["damping"])
+    assert ep.n_iter == cfg["n_iter"] and emulated_device.calls["sweep_iterations"] == cfg["n_iter"]
+    mse = np.array([e["mse"] for e in track.errors])
+    assert_allclose(mse, sw[name + "_mse"], rtol=1e-9)
+    df = evo.get_dataframe()
+    assert_allclose(df[df.id == "x"].v.values, sw[name + "_vx"], rtol=1e-9)
+    assert_allclose(df[df.id == "z"].v.values, sw[name + "_vz"], rtol=1e-9)
+    d = ep.get_variables_data()
+    ref = sw[name + "_rx"]
+    assert_allclose(d["x"]["r"], ref, rtol=1e-9, atol=1e-9 * np.abs(ref).max())
+    assert d["x"]["r"].shape == (cfg["N"],) and isinstance(d["x"]["v"], float)
+    for k in range(1, 9):
+        a, b = ep._edge(f"e{k}")
+        assert_allclose(a, sw[f"{name}_e{k}_a"], rtol=1e-9)
+
+
+def test_early_stopping_chunks_and_rollback(emulated_device, sw):  # noqa: F811
+    from tramp_b200.algos import ExpectationPropagation, TrackEstimate, JoinCallback, EarlyStoppingEP
+    from tramp_b200.priors import GaussBernoulliPrior
+    from tramp_b200.likelihoods import GaussianLikelihood
+    from tramp_b200.channels import LinearChannel
+    from tramp_b200.variables import SISOVariable as V
+    for idx in range(3):                      # default EarlyStoppingEP, device path in chunks of 16
+        cfg = _configs(sw)[idx]
+        name = cfg["name"] + "_early"
+        ep = ExpectationPropagation(_build(cfg, sw, name))
+        ep.iterate(max_iter=200, damping=cfg["damping"])
+        assert ep.n_iter == int(sw[name + "_n_iter"])
+        ref = sw[name + "_rx"]
+        assert_allclose(ep.get_variables_data()["x"]["r"], ref, rtol=1e-9, atol=1e-9 * np.abs(ref).max())
+    name = "cs_diverges_early"                # divergence: rolled back to the previous iteration
+    for callback in (None, JoinCallback([TrackEstimate(ids=["x"]), EarlyStoppingEP()])):
+        model = (GaussBernoulliPrior(size=120, rho=0.1) @ V("x") @ LinearChannel(sw[name + "_W"])
+                 @ V("z") @ GaussianLikelihood(y=sw[name + "_y"], var=1e-2)).to_model()
+        ep = ExpectationPropagation(model)
+        ep.iterate(max_iter=200, callback=callback)
+        assert ep.n_iter == int(sw[name + "_n_iter"]) == 7
+        d = ep.get_variables_data()
+        assert_allclose(d["x"]["r"], sw[name + "_rx"], rtol=1e-9, atol=1e-12)
+        assert_allclose(d["x"]["v"], sw[name + "_vx_final"], rtol=1e-9)
+
+
+def test_warm_start_and_nan(emulated_device, sw):  # noqa: F811
+    from tramp_b200.algos import ExpectationPropagation, PassCallback
+    from tramp_b200.priors import GaussBernoulliPrior
+    from tramp_b200.likelihoods import GaussianLikelihood
+    from tramp_b200.channels import LinearChannel
+    from tramp_b200.variables import SISOVariable as V
+    cfg = _configs(sw)[0]
+    name = cfg["name"]
+    ep = ExpectationPropagation(_build(cfg, sw, name))
+    ep.iterate(max_iter=15, callback=PassCallback())
+    ep.iterate(max_iter=cfg["n_iter"] - 15, callback=PassCallback(), warm_start=True)
+    assert ep.n_iter == cfg["n_iter"]
+    ref = sw[name + "_rx"]
+    assert_allclose(ep.get_variables_data()["x"]["r"], ref, rtol=1e-9, atol=1e-9 * np.abs(ref).max())
+    y_bad = sw[name + "_y"].copy()
+    y_bad[3] = np.nan
+    bad = (GaussBernoulliPrior(size=cfg["N"], rho=0.1) @ V("x") @ LinearChannel(sw[name + "_W"]) @ V("z")
+           @ GaussianLikelihood(y=y_bad, var=1e-2)).to_model()
+    with pytest.raises(ValueError, match="nan"):
+        ExpectationPropagation(bad).iterate(max_iter=3, callback=PassCallback())
+
+
+def test_scenario_reproduces_the_reference_run(emulated_device):  # noqa: F811
+    """BayesOptimalScenario.run_all("EP,SE") with EarlyStopping, seed protocol of the
+    reference: the unmodified reference printed SE v = 0.009469020882561508 (14
+    iterations), EP v = 0.01149781034627002 (17 iterations), mse = 0.012888367874476584."""
+    from tramp_b200.models import glm_generative
+    from tramp_b200.experiments import BayesOptimalScenario
+    from tramp_b200.algos import EarlyStopping
+    np.random.seed(5)
+    model = glm_generative(N=400, alpha=0.7, ensemble_type="gaussian", prior_type="gauss_bernoulli",
+                           output_type="gaussian", prior_rho=0.2, output_var=1e-2)
+    scenario = BayesOptimalScenario(model, x_ids=["x"])
+    by = {r["source"]: r for r in scenario.run_all(metrics=["mse"], max_iter=100, callback=EarlyStopping())}
+    assert_allclose(by["SE"]["v"], 0.009469020882561508, rtol=1e-8)
+    assert_allclose(by["EP"]["v"], 0.01149781034627002, rtol=1e-8)
+    assert_allclose(by["mse"]["v"], 0.012888367874476584, rtol=1e-8)
+    assert by["SE"]["n_iter"] == 14 and by["EP"]["n_iter"] == 17
+    df = scenario.ep_convergence(metrics=["mse"], max_iter=12, damping=0.1)
+    assert list(df.columns) == ["id", "iter", "mse", "v"] and len(df) == 12
+    assert_allclose(scenario.compute_score(scenario.x_pred)["x"]["mse"], df.mse.values[-1], rtol=1e-9)
