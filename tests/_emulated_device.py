@@ -61,6 +61,15 @@ class EmulatedLibrary:
         size = C.sizeof(self._lib.TrbFactor)
         return [self._lib.TrbFactor.from_address(ptr + i * size) for i in range(n)]
 
+    def trb_truncated_normal(self, n, r0, v0, zmin, zmax, mean, var, logZ, proba, stream):
+        r, v = _arr(r0, n), _arr(v0, n)
+        with np.errstate(all="ignore"):
+            for ptr, fn in ((mean, O.truncated_normal_mean), (var, O.truncated_normal_var),
+                            (logZ, O.truncated_normal_logZ), (proba, O.truncated_normal_proba)):
+                if ptr:
+                    _arr(ptr, n)[:] = fn(r, v, zmin, zmax)
+        return 0
+
     def trb_se_measure(self, fptr, stride, what, B, a, tau, q, out, flags, stream):
         self.calls["trb_se_measure"] += 1
         fs = self._factors(fptr, B if stride else 1)

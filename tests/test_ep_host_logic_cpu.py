@@ -110,3 +110,20 @@ def test_scenario_reproduces_the_reference_run(emulated_device):  # noqa: F811
     df = scenario.ep_convergence(metrics=["mse"], max_iter=12, damping=0.1)
     assert list(df.columns) == ["id", "iter", "mse", "v"] and len(df) == 12
     assert_allclose(scenario.compute_score(scenario.x_pred)["x"]["mse"], df.mse.values[-1], rtol=1e-9)
+
+
+def test_belief_wrappers_route_to_the_device_routine(emulated_device, golden_dir):  # noqa: F811
+    """beliefs.truncated / beliefs.positive (reference beliefs/truncated.py, positive.py)
+    are thin natural-parameter wrappers over one device routine; with that routine
+    emulated by the oracle they must reproduce the reference's golden values."""
+    from tramp_b200.beliefs import truncated, positive
+    g = np.load(os.path.join(golden_dir, "elementwise.npz"))
+    b = g["trunc_b"]
+    for i, (a, lo, hi) in enumerate(g["trunc_cases"]):
+        for key, fn in (("A", truncated.A), ("r", truncated.r), ("v", truncated.v), ("p", truncated.p)):
+            assert_allclose(fn(a, b, lo, hi), g[f"trunc{i}_{key}"], rtol=1e-12, atol=1e-300)
+        assert_allclose(truncated.tau(a, b, lo, hi), g[f"trunc{i}_r"]**2 + g[f"trunc{i}_v"], rtol=1e-12)
+    for key, fn in (("A", positive.A), ("r", positive.r), ("v", positive.v)):
+        assert_allclose(fn(g["pos_a"], g["pos_b"]), g[f"pos_{key}"], rtol=1e-12)
+    assert isinstance(positive.r(1.0, 0.3), float)
+    assert_allclose(positive.tau(2.0, 0.5), positive.r(2.0, 0.5)**2 + positive.v(2.0, 0.5), rtol=1e-14)
