@@ -127,3 +127,19 @@ def test_belief_wrappers_route_to_the_device_routine(emulated_device, golden_dir
         assert_allclose(fn(g["pos_a"], g["pos_b"]), g[f"pos_{key}"], rtol=1e-12)
     assert isinstance(positive.r(1.0, 0.3), float)
     assert_allclose(positive.tau(2.0, 0.5), positive.r(2.0, 0.5)**2 + positive.v(2.0, 0.5), rtol=1e-14)
+
+
+def test_size_independent_properties_at_a_small_shape(emulated_device):  # noqa: F811
+    """The property checks tests/test_gpu_sizes.py runs on the GPU at N = 4096, here
+    at N = 96 through the emulated sweep: the closed forms, tolerances and API calls
+    of the checks themselves are pinned by the oracle."""
+    from tests import full_size_properties as P
+    import torch
+    torch.manual_seed(0)
+    data = P.make_batch(3, 96, 48, seed=11)
+    ref = P.schedules_agree(data, 25)
+    assert ref[0].shape == (3, 96) and ref[1].shape == (3,) and ref[2].shape == (25, 3)
+    P.oracle_sample(data, ref, b=1, n_iter=25)
+    P.instances_are_independent(data, ref, 1, 3, 25)
+    P.bayes_optimal_consistency(ref, rtol=2.0, gain=1.0)
+    P.linear_gaussian_closed_form(data)
