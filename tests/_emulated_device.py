@@ -194,7 +194,8 @@ def _sweep_run(self, sw_ref, it0, n_iter, fresh, stream):
         if not act[b]:
             continue
         o = 0 if shared else b
-        key = (sw.Vt, sw.Ut, o)
+        # addresses are reused once a model is freed: the operator's own bytes are the key
+        key = (R, N, M, sv[o].tobytes(), Vt[o, 0, :N].tobytes(), Ut[o, R - 1, :M].tobytes())
         if key not in self._ops_cache:
             W = (Ut[o, :, :M].T * sv[o]) @ Vt[o, :, :N]
             self._ops_cache[key] = (W, O.LinearOp(W))

@@ -95,6 +95,36 @@ def test_batched_models_stop_independently(emulated_device):  # noqa: F811
         assert one[0]["v"] == v[g] and one[0]["n_iter"] == se.n_iter_per_problem[g]
 
 
+def test_grid_keeps_its_valid_problems_when_one_leaves_the_domain(emulated_device):  # noqa: F811
+    """One run that violates az > 1/tau_z raises like the reference
+    (sgn_likelihood.py:80-81); inside a grid launched at once it reads v = NaN and
+    keeps its flag, the other problems are unaffected."""
+    from tramp_b200 import _lib
+    from tramp_b200.priors import GaussianPrior, BinaryPrior
+    from tramp_b200.likelihoods import SgnLikelihood
+    from tramp_b200.channels import MarchenkoPasturChannel
+    from tramp_b200.variables import SISOVariable as V
+    from tramp_b200.algos import StateEvolution
+    from tramp_b200.experiments import run_state_evolution_grid
+
+    def build(prior):
+        return (prior @ V(id="x") @ MarchenkoPasturChannel(alpha=2.0) @ V(id="z") @ SgnLikelihood(y=None)).to_model()
+    se = StateEvolution([build(GaussianPrior(size=None)), build(BinaryPrior(size=None, p_pos=0.6))])
+    se.iterate(max_iter=30)
+    v = se.get_variable_data("x")["v"]
+    assert np.isnan(v[0]) and 0 < v[1] < 1
+    assert se.flags[0] & _lib.FLAG_SE_DOMAIN and not se.flags[1] & _lib.FLAG_SE_DOMAIN
+    alone = StateEvolution(build(BinaryPrior(size=None, p_pos=0.6)))
+    alone.iterate(max_iter=30)
+    assert alone.get_variable_data("x")["v"] == v[1] and alone.n_iter == se.n_iter_per_problem[1]
+    grid = run_state_evolution_grid(["x"], [build(GaussianPrior(size=None)), build(BinaryPrior(size=None, p_pos=0.6))],
+                                    max_iter=30)
+    assert np.isnan(grid[0][0]["v"]) and grid[1][0]["v"] == v[1]
+    for models in ([build(GaussianPrior(size=None))] * 2, [build(GaussianPrior(size=None))]):
+        with pytest.raises(AssertionError, match="az must be greater"):
+            StateEvolution(models).iterate(max_iter=5)
+
+
 def test_errors_and_factor_level_api(emulated_device):  # noqa: F811
     from tramp_b200.priors import GaussianPrior, GaussBernoulliPrior
     from tramp_b200.likelihoods import SgnLikelihood

@@ -244,10 +244,21 @@ class StateEvolution():
             self._iterate_synchronous(max_iter, callback)
         logger.info(f"terminated after n_iter={self.n_iter} iterations")
 
-    def _raise_on_flags(self, flags):
-        if (flags & _lib.FLAG_SE_DOMAIN).any():
-            # sgn_likelihood.py:80-81 / abs_likelihood.py:57-58
-            raise AssertionError("az must be greater than 1/ tau_z")
+    def _raise_on_flags(self, flags, grid=False):
+        domain = (flags & _lib.FLAG_SE_DOMAIN) != 0
+        if domain.any():
+            # sgn_likelihood.py:80-81 / abs_likelihood.py:57-58.  One run: the reference's
+            # AssertionError.  A grid of runs in one launch (our addition): the other
+            # problems are valid results, so the failed ones read v = NaN (and keep
+            # their flag in `self.flags`) instead of discarding the whole grid.
+            if not (grid and self.batched) or domain.all():
+                raise AssertionError("az must be greater than 1/ tau_z")
+            bad = np.nonzero(domain)[0]
+            logger.warning(f"az must be greater than 1/ tau_z in problem(s) {bad.tolist()}: v = nan there")
+            t = ops.torch()
+            idx = t.as_tensor(bad, device=self._state["vx"].device)
+            for key in ("vx", "vz"):
+                self._state[key].index_fill_(0, idx, float("nan"))
         if (flags & _lib.FLAG_NAN_A).any():
             bad = np.nonzero(flags & _lib.FLAG_NAN_A)[0]
             where = f" in problem(s) {bad.tolist()}" if self.batched else ""
@@ -275,7 +286,7 @@ class StateEvolution():
         host_rec = {k: v[:max(done, 1)].cpu().numpy() for k, v in rec.items()}
         self.records = host_rec
         first = self.n_iter
-        self._raise_on_flags(flags)
+        self._raise_on_flags(flags, grid=True)
         for i in range(done):
             self.n_iter = first + i + 1
             callback.replay(self, i, max_iter, host_rec)
