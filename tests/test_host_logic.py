@@ -261,3 +261,20 @@ def test_c_abi_from_plain_c(tmp_path):
     assert build.returncode == 0, build.stderr
     run = subprocess.run([exe], capture_output=True, text=True)
     assert run.returncode == 0 and run.stdout.startswith("ok"), (run.returncode, run.stdout, run.stderr)
+
+
+def test_factories_name_what_this_build_covers():
+    """get_prior / get_likelihood / get_channel / get_ensemble (reference */__init__.py):
+    an unknown name is a KeyError as there, with the supported names in the message."""
+    from tramp_b200.priors import get_prior
+    from tramp_b200.likelihoods import get_likelihood
+    from tramp_b200.channels import get_channel
+    from tramp_b200.ensembles import get_ensemble
+    assert type(get_prior(size=3, prior_type="binary")).__name__ == "BinaryPrior"
+    assert type(get_channel("abs")).__name__ == "AbsChannel"
+    for call, kw in ((get_prior, dict(size=3, prior_type="exponential")),
+                     (get_likelihood, dict(y=None, likelihood_type="modulus")),
+                     (get_channel, dict(channel_type="relu")),
+                     (get_ensemble, dict(ensemble_type="binary"))):
+        with pytest.raises(KeyError, match="not part of tramp_b200"):
+            call(**kw)

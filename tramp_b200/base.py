@@ -31,6 +31,22 @@ class ReprMixin():
         return f"{self.__class__.__name__}({args})"
 
 
+
+class Registry(dict):
+    """name -> class table behind get_prior / get_likelihood / get_channel /
+    get_ensemble.  An unknown name is a KeyError as in the reference (a plain dict
+    lookup there); the message says what this build covers, because the reference
+    knows many more names (DESIGN 1 "Out of scope")."""
+
+    def __init__(self, what, classes):
+        super().__init__(classes)
+        self.what = what
+
+    def __missing__(self, name):
+        raise KeyError(f"{self.what} type {name!r} is not part of tramp_b200 "
+                       f"(the GLM expectation-propagation path: {', '.join(sorted(self))})")
+
+
 def filter_message(message, direction):
     """reference base.py:35-41."""
     return [(s, t, d) for s, t, d in message if d["direction"] == direction]

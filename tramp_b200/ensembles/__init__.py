@@ -1,6 +1,6 @@
 """Random matrix ensembles (reference tramp/ensembles/): Gaussian only."""
 import numpy as np
-from ..base import ReprMixin
+from ..base import ReprMixin, Registry
 
 
 class Ensemble(ReprMixin):
@@ -69,7 +69,7 @@ class MarchenkoPasturEnsemble(Ensemble):
                 + self.alpha * np.log(1 + gamma - F / 4) - F / (4 * gamma))
 
 
-ENSEMBLE_CLASSES = {"gaussian": GaussianEnsemble, "marchenko_pastur": MarchenkoPasturEnsemble}
+ENSEMBLE_CLASSES = Registry("ensemble", {"gaussian": GaussianEnsemble, "marchenko_pastur": MarchenkoPasturEnsemble})
 
 
 def get_ensemble(ensemble_type, **kwargs):

@@ -4,7 +4,7 @@
 """
 import numpy as np
 
-from ..base import Factor, _Arg, measure_out, se_domain_error
+from ..base import Factor, Registry, _Arg, measure_out, se_domain_error
 from .. import ops, _lib
 
 
@@ -186,11 +186,11 @@ class AbsLikelihood(Likelihood):
         return r"$\mathrm{abs}$"
 
 
-LIKELIHOOD_CLASSES = {
+LIKELIHOOD_CLASSES = Registry("likelihood", {
     "gaussian": GaussianLikelihood,
     "abs": AbsLikelihood,
     "sgn": SgnLikelihood,
-}
+})
 
 
 def get_likelihood(y, likelihood_type, **kwargs):

@@ -7,7 +7,7 @@ become `a: (B,)`, `b: (B, N)`.
 """
 import numpy as np
 
-from ..base import Factor, _Arg, measure_out
+from ..base import Factor, Registry, _Arg, measure_out
 from .. import ops, _lib
 
 
@@ -211,11 +211,11 @@ class GaussianPrior(Prior):
         return self.a
 
 
-PRIOR_CLASSES = {
+PRIOR_CLASSES = Registry("prior", {
     "gaussian": GaussianPrior,
     "gauss_bernoulli": GaussBernoulliPrior,
     "binary": BinaryPrior,
-}
+})
 
 
 def get_prior(size, prior_type, **kwargs):
