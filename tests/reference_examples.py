@@ -59,13 +59,17 @@ def check_sgn_mse_rows(rows, batched):
                 continue
             assert [d["x_id"] for d in rec] == ["x", "z"]
             recovered = min(r[4:6]) < 1e-8
+            # a run that creeps to its fixed point (|dv| shrinking by a few per cent per
+            # iteration) may cross EarlyStopping's tol = 1e-6 an iteration or two earlier
+            # or later under rounding-level differences; v then moves by less than tol
+            slow = int(r[3]) >= 30
             assert rec[0]["n_iter"] == rec[1]["n_iter"], tag
-            assert abs(rec[0]["n_iter"] - int(r[3])) <= (3 if recovered else 0), tag
+            assert abs(rec[0]["n_iter"] - int(r[3])) <= (3 if recovered else 2 if slow else 0), tag
             got = [rec[0]["v"], rec[1]["v"]]
             if recovered:
                 assert_allclose(got, r[4:6], rtol=0.6, atol=2e-8, err_msg=tag)
             else:
-                assert_allclose(got, r[4:6], rtol=1e-6, atol=2e-8, err_msg=tag)
+                assert_allclose(got, r[4:6], rtol=1e-6, atol=5e-6 if slow else 2e-8, err_msg=tag)
 
 
 # --- cs_critical_lines.py / sgn_retrieval_critical_lines.py: run_critical(...) ------------
