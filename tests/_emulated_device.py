@@ -1,8 +1,10 @@
 """Test infrastructure: run the HOST side of tramp_b200 on CPU tensors, with the C
 entry points of the two drivers emulated by the oracle: `trb_se_run` /
 `trb_se_measure` (State Evolution, oracle evaluated with the kernels' quadrature
-rule) and `trb_sweep_run` / `trb_sweep_stage` (the EP sweep, oracle `ep_glm` one
-iteration at a time with the kernels' early-stopping and roll-back decisions).
+rule), `trb_sweep_run` / `trb_sweep_stage` (the EP sweep, oracle `ep_glm` one
+iteration at a time with the kernels' early-stopping and roll-back decisions) and the
+per-factor primitives (`trb_factor_*`, `trb_lin_*`, `trb_posterior_rv`: the device
+moment routines compiled for the host, numpy for the operator products).
 
 This exists so that `-m "not gpu"` covers the Python glue around the kernels
 (initialisers, damping configuration, record replay into callbacks, snapshots,
@@ -266,6 +268,186 @@ def _sweep_run(self, sw_ref, it0, n_iter, fresh, stream):
                 break
     return 0
 
+
+# the C-ABI primitives behind the factor API ------------------------------------
+# (what `damping="adaptive"` / `update_dA` and the reference's unit-test mirrors call
+# one factor at a time).  Moments: the device routines themselves, compiled for the
+# host (tests/_device_math_host.py); linear algebra: numpy on the same operands.
+def _clip_a_new(v, a, amin, amax):
+    """clip_a_new of trb_common.cuh (base.py:44-46, 250-255), NaN kept."""
+    vv = v if v != v else max(v, 1e-20)
+    an = 1.0 / vv - a
+    return min(max(an, amin), amax) if an == an else an
+
+
+def _damp(d, old, new):
+    return d * old + (1.0 - d) * new if d != 0.0 else new
+
+
+def _obj(ref):
+    return ref._obj if hasattr(ref, "_obj") else ref.contents
+
+
+def _moments(f, n, ld, a, a_mode, b, y, inst):
+    from tests import _device_math_host as H
+    off = inst * ld
+    a_i = _arr(a, off + n)[off:off + n] if a_mode else _arr(a, inst + 1)[inst:inst + 1]
+    y_i = _arr(y, off + n)[off:off + n] if y else None
+    with np.errstate(all="ignore"):
+        return H.factor_elementwise(f, a_i, _arr(b, off + n)[off:off + n], y_i)
+
+
+def _factor_posterior(self, fref, B, n, ld, a, a_mode, b, y, r, v, v_mode, stream):
+    f = _obj(fref)
+    for i in range(B):
+        ri, vi, _ = _moments(f, n, ld, a, a_mode, b, y, i)
+        _arr(r, i * ld + n)[i * ld:] = ri
+        if v_mode:
+            _arr(v, i * ld + n)[i * ld:] = vi
+        else:
+            _arr(v, B)[i] = vi.sum() / n
+    return 0
+
+
+def _factor_log_partition(self, fref, B, n, ld, a, a_mode, b, y, A, A_mode, stream):
+    f = _obj(fref)
+    for i in range(B):
+        Ai = _moments(f, n, ld, a, a_mode, b, y, i)[2]
+        if A_mode:
+            _arr(A, i * ld + n)[i * ld:] = Ai
+        else:
+            _arr(A, B)[i] = Ai.sum() / n
+    return 0
+
+
+def _factor_message(self, fref, B, n, ld, a_in, b_in, y, a_io, b_io, a_copy, damping, scratch, flags,
+                    active, stream):
+    """k_factor_message: posterior -> mean(v) -> clip -> b_new -> damping."""
+    L, f = self._lib, _obj(fref)
+    act = _arr(active, B, np.int32) if active else None
+    fl = _arr(flags, B, np.int32) if flags else None
+    for i in range(B):
+        if act is not None and not act[i]:
+            continue
+        sl = slice(i * ld, i * ld + n)
+        a = _arr(a_in, B)[i]
+        b_old = _arr(b_io, i * ld + n)[sl]
+        if f.kind in (L.GAUSSIAN_PRIOR, L.GAUSSIAN_LIKELIHOOD):      # constants, no clip
+            a_new = f.p0
+            bn = np.full(n, f.p1) if f.kind == L.GAUSSIAN_PRIOR else _arr(y, i * ld + n)[sl] * f.p0
+        else:
+            ri, vi, _ = _moments(f, n, ld, a_in, 0, b_in, y, i)
+            a_new = _clip_a_new(vi.sum() / n, a, f.amin, f.amax)
+            bn = ri * (a + a_new) - _arr(b_in, i * ld + n)[sl]
+        b_old[:] = _damp(damping, b_old, bn)
+        flag = (L.FLAG_NAN_B if np.isnan(bn).any() else 0) | (L.FLAG_NAN_A if a_new != a_new else 0) \
+            | (L.FLAG_NEG_A if a_new < 0 else 0)
+        ad = _damp(damping, _arr(a_io, B)[i], a_new)
+        _arr(a_io, B)[i] = ad
+        if a_copy:
+            _arr(a_copy, B)[i] = ad
+        if fl is not None:
+            fl[i] |= flag
+    return 0
+
+
+def _posterior_rv(self, B, n, ld, a1, b1, a2, b2, r, v, stream):
+    for i in range(B):
+        sl = slice(i * ld, i * ld + n)
+        a_hat = _arr(a1, B)[i] + _arr(a2, B)[i]
+        with np.errstate(all="ignore"):
+            _arr(r, i * ld + n)[sl] = (_arr(b1, i * ld + n)[sl] + _arr(b2, i * ld + n)[sl]) / a_hat
+            _arr(v, B)[i] = 1.0 / a_hat
+    return 0
+
+
+def _operator(A, stride, R, n, ld, i):
+    base = i * stride
+    return _arr(A, base + R * ld)[base:].reshape(R, ld)[:, :n]
+
+
+def _lin_project(self, A, stride, R, n, ld, B, vec, ldvec, out, active, impl, stream):
+    act = _arr(active, B, np.int32) if active else None
+    for i in range(B):
+        if act is None or act[i]:
+            _arr(out, (i + 1) * R)[i * R:] = _operator(A, stride, R, n, ld, i) @ _arr(vec, i * ldvec + n)[i * ldvec:]
+    return 0
+
+
+def _lin_expand(self, A, stride, R, n, ld, B, coef, part, active, impl, stream):
+    """One slot per instance (trb_lin_expand_slots is 1 here)."""
+    act = _arr(active, B, np.int32) if active else None
+    for i in range(B):
+        if act is None or act[i]:
+            _arr(part, i * ld + n)[i * ld:] = _arr(coef, (i + 1) * R)[i * R:] @ _operator(A, stride, R, n, ld, i)
+    return 0
+
+
+def _lin_reduce_slots(self, B, R, n, ld, part, add, add_div, out, stream):
+    for i in range(B):
+        sl = slice(i * ld, i * ld + n)
+        v = _arr(part, i * ld + n)[sl].copy()
+        if add:
+            with np.errstate(all="ignore"):
+                v = _arr(add, i * ld + n)[sl] / _arr(add_div, B)[i] + v
+        _arr(out, i * ld + n)[sl] = v
+    return 0
+
+
+def _lin_project_gemm(self, A, R, n, ld, B, vec, ldvec, out, stream):
+    return _lin_project(self, A, 0, R, n, ld, B, vec, ldvec, out, None, 0, stream)
+
+
+def _lin_expand_gemm(self, A, R, n, ld, B, coef, out, ldout, stream):
+    for i in range(B):
+        _arr(out, i * ldout + n)[i * ldout:] = _arr(coef, (i + 1) * R)[i * R:] @ _operator(A, 0, R, n, ld, 0)
+    return 0
+
+
+def _lin_rescale(self, direction, B, R, Nz, Nx, rank, null_space, s, s2, stride, az, ax, tz, tx, coef, v,
+                 active, stream):
+    """k_lin_rescale: linear_channel.py:58-67 (n_eff), :74 (resolvent), :91-105 (variances)."""
+    act = _arr(active, B, np.int32) if active else None
+    for i in range(B):
+        if act is not None and not act[i]:
+            continue
+        a_z, a_x = _arr(az, B)[i], _arr(ax, B)[i]
+        sb = _arr(s, i * stride + R)[i * stride:]
+        s2b = _arr(s2, i * stride + R)[i * stride:]
+        with np.errstate(all="ignore"):
+            az_v = a_z if (direction == 0 or a_z != a_z) else max(1e-11, a_z)
+            if direction == 0 and a_x == 0:
+                var = s2b[:rank].sum() / rank * rank / (Nx * a_z)
+            else:
+                if a_x == 0:
+                    n_eff = 0.0
+                elif az_v / a_x == 0:
+                    n_eff = rank / Nz
+                else:
+                    n_eff = np.sum(s2b[:rank] / (az_v / a_x + s2b[:rank])) / Nz
+                var = n_eff / ((Nx / Nz) * a_x) if direction == 0 else (1 - n_eff) / az_v
+            if v:
+                _arr(v, B)[i] = var
+            if coef:
+                res = 1 / (a_z + a_x * s2b)
+                t_z, t_x = _arr(tz, (i + 1) * R)[i * R:], _arr(tx, (i + 1) * R)[i * R:]
+                if direction == 0:
+                    c = sb * (res * (t_z + sb * t_x))
+                elif not null_space:
+                    c = res * (t_z + sb * t_x)
+                else:
+                    c = res * (sb * t_x - (a_x * s2b / a_z) * t_z)
+                _arr(coef, (i + 1) * R)[i * R:] = c
+    return 0
+
+
+for _name, _fn in (("trb_factor_posterior", _factor_posterior), ("trb_factor_log_partition", _factor_log_partition),
+                   ("trb_factor_message", _factor_message), ("trb_posterior_rv", _posterior_rv),
+                   ("trb_lin_project", _lin_project), ("trb_lin_expand", _lin_expand),
+                   ("trb_lin_reduce_slots", _lin_reduce_slots), ("trb_lin_project_gemm", _lin_project_gemm),
+                   ("trb_lin_expand_gemm", _lin_expand_gemm), ("trb_lin_rescale", _lin_rescale)):
+    setattr(EmulatedLibrary, _name, _fn)
+EmulatedLibrary.trb_lin_expand_slots = lambda self, B, R: 1
 
 EmulatedLibrary.trb_sweep_run = _sweep_run
 EmulatedLibrary.trb_sweep_stage = lambda self, sw_ref, stage, it, first, pre, stream: 0

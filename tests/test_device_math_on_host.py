@@ -3,75 +3,28 @@ moments, log-partitions, truncated normal: SURVEY 8a rows a8-a16) compiled as HO
 functions and checked against the reference's golden vectors, so that the formulas
 the kernels evaluate are covered in the build container, which has no GPU.
 
-How: the text of the header, minus its include of the device helpers, is compiled
-by nvcc with `__device__` defined away; nvcc's host math library supplies erfcx.
-Host and device special functions differ by an ulp or two, which is what the
-tolerances of tests/test_gpu_primitives.py (repeated here) already allow.  Test
-infrastructure only: nothing in the package can load this library.
+The host build is tests/_device_math_host.py.  Host and device special functions
+differ by an ulp or two, which is what the tolerances of tests/test_gpu_primitives.py
+(repeated here) already allow.
 """
 import ctypes as C
 import os
-import re
-import shutil
-import subprocess
 
 import numpy as np
 import pytest
 from numpy.testing import assert_allclose
 
+from tests import _device_math_host as H
 from tests.golden.make_golden_specs import PRIOR_SPECS, LIK_SPECS, TRUNC_CASES
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-CSRC = os.path.join(ROOT, "tramp_b200", "csrc")
 RTOL = 1e-11
-
-WRAPPERS = r"""
-extern "C" {
-void hm_truncated_normal(long n, const double* r0, const double* v0, double zmin, double zmax,
-                         double* mean, double* var, double* logZ, double* proba) {
-  for (long i = 0; i < n; ++i) {
-    const trb::TruncMoments t = trb::truncated_normal(r0[i], v0[i], zmin, zmax);
-    mean[i] = t.mean; var[i] = t.var; logZ[i] = t.logZ; proba[i] = t.proba;
-  }
-}
-void hm_factor(const trb_factor* f, long n, const double* a, const double* b, const double* y,
-               double* r, double* v, double* logZ) {
-  for (long i = 0; i < n; ++i) {
-    const double yi = y ? y[i] : 0.0;
-    const trb::RV o = trb::factor_moments(*f, a[i], b[i], yi);
-    r[i] = o.r; v[i] = o.v;
-    logZ[i] = trb::factor_log_partition(*f, a[i], b[i], yi);
-  }
-}
-int hm_is_constant_message(int kind) { return trb::factor_is_constant_message(kind) ? 1 : 0; }
-}
-"""
 
 
 @pytest.fixture(scope="module")
-def host_math(tmp_path_factory):
-    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
-    if not os.path.exists(nvcc):
+def host_math():
+    lib = H.load()
+    if lib is None:
         pytest.skip("nvcc not available")
-    header = open(os.path.join(CSRC, "trb_moments.cuh")).read()
-    assert '#include "trb_common.cuh"' in header
-    body = header.replace("#pragma once", "").replace('#include "trb_common.cuh"', "")
-    two_pi = re.search(r"constexpr double kTwoPi = [^;]+;", open(os.path.join(CSRC, "trb_common.cuh")).read())
-    assert two_pi, "kTwoPi moved out of trb_common.cuh"
-    src = "\n".join([
-        "#include <cuda_runtime.h>", "#include <math.h>", '#include "tramp_b200.h"',
-        "#undef __device__", "#define __device__", "#undef __forceinline__", "#define __forceinline__ inline",
-        "namespace trb { " + two_pi.group(0) + " }", body, WRAPPERS])
-    d = tmp_path_factory.mktemp("host_math")
-    cu, so = str(d / "moments_host.cu"), str(d / "libmoments_host.so")
-    open(cu, "w").write(src)
-    subprocess.run([nvcc, "-O2", "-shared", "-Xcompiler", "-fPIC", "--fmad=false",
-                    "-Wno-deprecated-gpu-targets", "-I", os.path.join(ROOT, "include"), "-o", so, cu],
-                   check=True, capture_output=True)
-    lib = C.CDLL(so)
-    dp = C.POINTER(C.c_double)
-    lib.hm_truncated_normal.argtypes = [C.c_long, dp, dp, C.c_double, C.c_double, dp, dp, dp, dp]
-    lib.hm_factor.argtypes = [C.c_void_p, C.c_long, dp, dp, dp, dp, dp, dp]
     return lib
 
 
@@ -81,12 +34,7 @@ def _p(x):
 
 def _factor(lib, spec, a, b, y=None):
     from tramp_b200 import ops
-    f = ops.factor_from_spec(spec)
-    a, b = (np.ascontiguousarray(np.broadcast_to(np.asarray(t, float), np.shape(b))) for t in (a, b))
-    y = None if y is None else np.ascontiguousarray(y, float)
-    r, v, A = (np.empty_like(b) for _ in range(3))
-    lib.hm_factor(C.addressof(f), b.size, _p(a), _p(b), None if y is None else _p(y), _p(r), _p(v), _p(A))
-    return r, v, A
+    return H.factor_elementwise(ops.factor_from_spec(spec), a, np.asarray(b, float), y)
 
 
 @pytest.fixture(scope="module")
