@@ -290,6 +290,8 @@ def _obj(ref):
 
 def _moments(f, n, ld, a, a_mode, b, y, inst):
     from tests import _device_math_host as H
+    if H.load() is None:
+        pytest.skip("nvcc not available: the device moment routines cannot be compiled for the host")
     off = inst * ld
     a_i = _arr(a, off + n)[off:off + n] if a_mode else _arr(a, inst + 1)[inst:inst + 1]
     y_i = _arr(y, off + n)[off:off + n] if y else None
