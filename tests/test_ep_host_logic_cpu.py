@@ -143,3 +143,30 @@ def test_size_independent_properties_at_a_small_shape(emulated_device):  # noqa:
     P.instances_are_independent(data, ref, 1, 3, 25)
     P.bayes_optimal_consistency(ref, rtol=2.0, gain=1.0)
     P.linear_gaussian_closed_form(data)
+
+
+@pytest.mark.parametrize("idx", [0, 1])
+def test_jacobi_setup_feeds_the_same_sweep(emulated_device, sw, idx):  # noqa: F811
+    """LinearChannel(W, svd_method="jacobi"): the batched block-Jacobi factorisation
+    (wide and tall W) gives the reference's spectrum, rank and EP trajectory."""
+    from tramp_b200.algos import ExpectationPropagation, TrackErrors
+    from tramp_b200.priors import get_prior
+    from tramp_b200.likelihoods import get_likelihood
+    from tramp_b200.channels import LinearChannel
+    from tramp_b200.variables import SISOVariable as V
+    cfg = _configs(sw)[idx]
+    name = cfg["name"]
+    W = sw[name + "_W"]
+    pk = {k: v for k, v in cfg["prior"].items() if k != "kind"}
+    lk = {k: v for k, v in cfg["lik"].items() if k != "kind"}
+    lin = LinearChannel(W, svd_method="jacobi")
+    model = (get_prior(size=cfg["N"], prior_type=cfg["prior"]["kind"], **pk) @ V("x") @ lin @ V("z")
+             @ get_likelihood(y=sw[name + "_y"], likelihood_type=cfg["lik"]["kind"], **lk)).to_model()
+    ep = ExpectationPropagation(model)
+    track = TrackErrors({"x": sw[name + "_x"]})
+    ep.iterate(max_iter=cfg["n_iter"], callback=track, damping=cfg["damping"])
+    assert_allclose(lin.s.cpu().numpy()[0], np.linalg.svd(W, compute_uv=False), rtol=1e-11)
+    assert lin.rank == np.linalg.matrix_rank(W)
+    assert_allclose(np.array([e["mse"] for e in track.errors]), sw[name + "_mse"], rtol=1e-9)
+    ref = sw[name + "_rx"]
+    assert_allclose(ep.get_variables_data()["x"]["r"], ref, rtol=1e-9, atol=1e-9 * np.abs(ref).max())

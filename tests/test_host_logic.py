@@ -6,6 +6,7 @@ import os
 import re
 import numpy as np
 import pytest
+from numpy.testing import assert_allclose
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
@@ -278,3 +279,25 @@ def test_factories_name_what_this_build_covers():
                      (get_ensemble, dict(ensemble_type="binary"))):
         with pytest.raises(KeyError, match="not part of tramp_b200"):
             call(**kw)
+
+
+@pytest.mark.parametrize("shape,block", [((2, 64, 128), 8), ((1, 50, 120), 8), ((3, 48, 48), 16),
+                                         ((2, 120, 60), 16), ((1, 5, 9), 16), ((1, 1, 4), 16)])
+def test_block_jacobi_svd_on_cpu_tensors(shape, block):
+    """svd_method="jacobi" (opt-in set-up for large batches): batched one-sided block
+    Jacobi against LAPACK on wide, tall, square, ragged and tiny matrices."""
+    import torch
+    from tramp_b200.channels.linear_channel import block_jacobi_svd, thin_svd_device
+    B, M, N = shape
+    W = np.random.RandomState(3).randn(B, M, N) / np.sqrt(N)
+    Wt = torch.as_tensor(W)
+    Ut, s, Vt = block_jacobi_svd(Wt, block=block) if M <= N else thin_svd_device(Wt, "jacobi")
+    R = min(M, N)
+    assert Ut.shape == (B, R, M) and s.shape == (B, R) and Vt.shape == (B, R, N)
+    s_ref = np.linalg.svd(W, compute_uv=False)
+    assert_allclose(s.numpy(), s_ref, rtol=1e-11, atol=1e-13 * s_ref.max())
+    assert np.all(np.diff(s.numpy(), axis=-1) <= 0)
+    assert_allclose(torch.einsum("brm,br,brn->bmn", Ut, s, Vt).numpy(), W, atol=1e-13)
+    eye = np.eye(R)
+    assert_allclose((Ut @ Ut.transpose(1, 2)).numpy(), np.broadcast_to(eye, (B, R, R)), atol=1e-11)
+    assert_allclose((Vt @ Vt.transpose(1, 2)).numpy(), np.broadcast_to(eye, (B, R, R)), atol=1e-11)

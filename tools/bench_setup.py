@@ -12,6 +12,8 @@ find out what a hand-written batched eigensolver has to beat):
                  (syevd is latency-bound on one 2048 x 2048 matrix; independent matrices
                  can overlap)
   gram_parts     the three steps of "gram" timed separately (Gram DGEMM, eigh, back-multiply)
+  jacobi_b       block_jacobi_svd with blocks of b rows: every step a batched GEMM or a batched
+                 2b x 2b eigen-problem over all instances and block pairs (thin_svd_device "jacobi")
 
 Every variant is checked against the first: singular values to 1e-10 relative and
 ||Ut W - diag(s) Vt|| / ||W||.  Prints one JSON line; nothing here is on the EP path.
@@ -28,7 +30,7 @@ from concurrent.futures import ThreadPoolExecutor
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch  # noqa: E402
 
-from tramp_b200.channels.linear_channel import thin_svd_device  # noqa: E402
+from tramp_b200.channels.linear_channel import thin_svd_device, block_jacobi_svd  # noqa: E402
 
 
 def sync():
@@ -88,6 +90,7 @@ def main():
     ap.add_argument("--alpha", type=float, default=0.5)
     ap.add_argument("--streams", type=int, nargs="*", default=[2, 4, 8, 16])
     ap.add_argument("--repeat", type=int, default=2)
+    ap.add_argument("--jacobi-blocks", type=int, nargs="*", default=[16, 32])
     ap.add_argument("--skip-svd", action="store_true")
     ap.add_argument("--device", default="cuda", help='"cpu" only smoke-tests the script (no stream variant)')
     args = ap.parse_args()
@@ -116,6 +119,12 @@ def main():
         t_s, out = timed(lambda: gram_streams(W, S), args.repeat)
         line["variants"][f"gram_streams_{S}"] = {
             "s_per_instance": t_s / B, "residual": residual(W, *out),
+            "s_rel_dev": float(((out[1] - ref[1]).abs() / ref[1]).max().item())}
+
+    for b in args.jacobi_blocks:
+        t_j, out = timed(lambda: block_jacobi_svd(W, block=b), 1)
+        line["variants"][f"jacobi_{b}"] = {
+            "s_per_instance": t_j / B, "residual": residual(W, *out),
             "s_rel_dev": float(((out[1] - ref[1]).abs() / ref[1]).max().item())}
 
     if not args.skip_svd:
