@@ -117,6 +117,12 @@ def thin_svd_device(W, method="svd"):
         U, s, Vh = t.linalg.svd(W, full_matrices=False)
         return U.transpose(1, 2).contiguous(), s.contiguous(), Vh.contiguous()
     if method == "jacobi":
+        # a round gathers and rewrites every row of every instance: bound the temporaries
+        # (three copies of the chunk) to a few GB
+        chunk = max(1, int(2**32 // (8 * M * N)))
+        if B > chunk:
+            parts = [thin_svd_device(W[b0:b0 + chunk], "jacobi") for b0 in range(0, B, chunk)]
+            return tuple(t.cat([p[k] for p in parts]) for k in range(3))
         if M <= N:
             return block_jacobi_svd(W)
         Vt, sv, Ut = block_jacobi_svd(W.transpose(1, 2).contiguous())
