@@ -255,7 +255,8 @@ def workload_config(N, M, instances_per_gpu, iters, schedule="general"):
                         "auto": "cheapest exact schedule (2-pass)"}[schedule]),
         "N": N, "M": M, "alpha": ALPHA, "instances_per_gpu": instances_per_gpu,
         "ep_iterations_per_step": iters,
-        "l2": "inputs larger than L2 (operators of one rank: 51.5 GB >> 126 MB)",
+        "l2": ("inputs larger than L2 (operators of one rank: "
+               f"{instances_per_gpu * 8 * min(M, N) * (N + M) / 1e9:.1f} GB >> 126 MB)"),
     }
 
 
