@@ -233,7 +233,8 @@ def run_reference(args):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
-        "config": dict(workload_config(N, M, 1, args.iters), l2="not applicable (host CPU arm)"),
+        # the workload is our arm's; `cpu_baseline.sample` says which bounded part of it a step timed
+        "config": workload_config(N, M, args.instances, args.iters),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0, "setup_s": res["setup_s"], "modes_instance_iterations_per_s": modes,
