@@ -174,3 +174,70 @@ def _state_evolution_records(x_ids, models, **algo_kwargs):
     x_data = se.get_variables_data(ids=x_ids)
     return [[dict(x_id=x_id, v=float(x_data[x_id]["v"][g]), n_iter=int(se.n_iter_per_problem[g]))
              for x_id in x_ids] for g in range(se.G)]
+
+
+def run_ep_sharded(build_model, n_instances, x_true=None, group=None, **algo_kwargs):
+    """Expectation Propagation on `n_instances` independent instances sharded over the
+    ranks of `group` (one process per GPU) by contiguous blocks -- SURVEY 8e: instances
+    share nothing, so every rank runs the device-resident sweep on its own block with no
+    data-path collective, and only the results are all-gathered at the end.
+
+    build_model(start, stop) -> the batched, observed Model of instances [start, stop)
+        (each rank builds, factorises and keeps only its own block);
+    x_true(start, stop) -> their signals {"x": [stop - start, N]} for the per-iteration mse
+        (optional);
+    algo_kwargs -> `ExpectationPropagation.iterate` (max_iter, damping, callback, ...).
+
+    Returns, identical on every rank: dict(r={id: [n_instances, N_id]}, v={id:
+    [n_instances]}, n_iter=[n_instances], mse=[max_iter, n_instances] or None), an
+    instance's mse being NaN after it stopped.  Without torch.distributed it is the
+    plain single-GPU run."""
+    import numpy as np
+    from ..distributed import instance_shard, gather_records
+    from .. import ops
+    t = ops.torch()
+    world, rank = 1, 0
+    try:
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized():
+            world, rank = dist.get_world_size(group), dist.get_rank(group)
+    except ImportError:
+        pass
+    start, stop = instance_shard(n_instances, rank, world)
+    max_iter = int(algo_kwargs.get("max_iter", 200))
+    local = {}
+    if stop > start:
+        ep = ExpectationPropagation(build_model(start, stop))
+        if x_true is not None:
+            errors = TrackErrors(true_values=x_true(start, stop), metrics=["mse"])
+            if "callback" not in algo_kwargs:          # tracking must not switch the default stopper off
+                algo_kwargs = dict(algo_kwargs, callback=ep.default_stopping)
+            algo_kwargs = _with_trackers([errors], algo_kwargs)
+        ep.iterate(**algo_kwargs)
+        data = ep.get_variables_data()
+        for vid, d in data.items():
+            local["r_" + vid] = np.atleast_2d(d["r"]).T                       # instances last
+            local["v_" + vid] = np.atleast_1d(d["v"])[None, :]
+        n_iter = getattr(ep, "n_iter_per_instance", None)
+        local["n_iter"] = np.atleast_1d(ep.n_iter if n_iter is None else n_iter).astype(float)[None, :]
+        if x_true is not None:
+            mse = np.full((max_iter, stop - start), np.nan)
+            for e in errors.errors:
+                mse[e["iter"]] = e["mse"]
+            local["mse"] = mse
+    # a rank without instances still takes part in the gathers, with the shapes of the others
+    shapes = {k: v.shape[:-1] for k, v in local.items()}
+    if world > 1:
+        every = [None] * world
+        dist.all_gather_object(every, shapes, group=group)
+        shapes = next(s for s in every if s)
+    out = {}
+    for key in sorted(shapes):
+        mine = local.get(key)
+        if mine is None:
+            mine = np.zeros(tuple(shapes[key]) + (0,))
+        full = gather_records(t.as_tensor(mine, dtype=t.float64, device=ops.device()), group=group)
+        out[key] = full.cpu().numpy()
+    ids = sorted(k[2:] for k in out if k.startswith("r_"))
+    return dict(r={vid: out["r_" + vid].T for vid in ids}, v={vid: out["v_" + vid][0] for vid in ids},
+                n_iter=out["n_iter"][0].astype(int), mse=out.get("mse"))
