@@ -79,3 +79,43 @@ def test_likelihood_moments_fuzz(host_math, spec):
             A_ref = O.normal_A(a + ay, b + ay * y) - O.normal_A(ay, ay * y)
     _check(r, v, A, r_ref, np.broadcast_to(v_ref, r.shape), A_ref, a, b,
            unit=np.maximum(1.0, y**2) if kind == "abs" else 1 / a)
+
+
+@pytest.mark.parametrize("shape", ["half_line_up", "half_line_down", "narrow", "wide"])
+def test_truncated_normal_fuzz(host_math, shape):
+    """utils/truncated_normal.py:14-298 on random intervals: the erfcx half-line path and
+    the five finite-interval branches (inf / close / neg / pos / other) must be taken for
+    the same arguments as in the reference -- no NaN or infinity on one side only -- and
+    agree where the reference's own formulas are well conditioned.  Narrow intervals
+    (width down to 1e-9, the Taylor branch) lose digits in the variance in both."""
+    import ctypes as C
+    lib = H.load()
+    rng = np.random.RandomState({"half_line_up": 0, "half_line_down": 1, "narrow": 2, "wide": 3}[shape])
+
+    def p(x):
+        return x.ctypes.data_as(C.POINTER(C.c_double))
+    n = 20_000
+    for _ in range(8):
+        if shape == "half_line_up":
+            lo, hi = float(rng.randn()), np.inf
+        elif shape == "half_line_down":
+            lo, hi = -np.inf, float(rng.randn())
+        elif shape == "narrow":
+            lo = float(2 * rng.randn())
+            hi = lo + float(10 ** rng.uniform(-9, 1))
+        else:
+            lo, hi = float(-10 ** rng.uniform(-2, 1)), float(10 ** rng.uniform(-2, 1))
+        v0 = 10 ** rng.uniform(-4, 3, n)
+        edge = rng.choice([0.0, lo if np.isfinite(lo) else 0.0, hi if np.isfinite(hi) else 0.0], n)
+        r0 = edge + np.sqrt(v0) * rng.randn(n) * rng.choice([1.0, 3.0, 8.0], n)
+        got = [np.empty(n) for _ in range(4)]
+        lib.hm_truncated_normal(n, p(r0), p(v0), lo, hi, *[p(o) for o in got])
+        with np.errstate(all="ignore"):
+            want = [O.truncated_normal_mean(r0, v0, lo, hi), O.truncated_normal_var(r0, v0, lo, hi),
+                    O.truncated_normal_logZ(r0, v0, lo, hi), O.truncated_normal_proba(r0, v0, lo, hi)]
+        units = (np.sqrt(v0) + np.abs(r0), v0, np.ones(n), np.ones(n))
+        tols = (1e-6, 1e-2 if shape == "narrow" else 1e-6, 1e-6, 1e-11)
+        for g, w, unit, tol in zip(got, want, units, tols):
+            assert np.array_equal(np.isnan(g), np.isnan(w)) and np.array_equal(np.isinf(g), np.isinf(w))
+            ok = np.isfinite(w)
+            assert np.all(np.abs(g[ok] - w[ok]) <= tol * np.maximum(np.abs(w[ok]), 1e-3 * unit[ok]))
