@@ -170,3 +170,16 @@ def test_jacobi_setup_feeds_the_same_sweep(emulated_device, sw, idx):  # noqa: F
     assert_allclose(np.array([e["mse"] for e in track.errors]), sw[name + "_mse"], rtol=1e-9)
     ref = sw[name + "_rx"]
     assert_allclose(ep.get_variables_data()["x"]["r"], ref, rtol=1e-9, atol=1e-9 * np.abs(ref).max())
+
+
+def test_smoke_body_and_no_oracle_inside_the_package(emulated_device):  # noqa: F811
+    """__graft_entry__.smoke()'s body runs (emulated sweep), and nothing under
+    tramp_b200/ imports oracle/: the oracle is the checker, never the product path."""
+    import __graft_entry__ as entry
+    assert entry._run_smoke(np) < 1e-9
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for folder, _, files in os.walk(os.path.join(root, "tramp_b200")):
+        for name in files:
+            if name.endswith(".py"):
+                text = open(os.path.join(folder, name)).read()
+                assert "import oracle" not in text and "from oracle" not in text, os.path.join(folder, name)
