@@ -236,6 +236,9 @@ def test_thin_svd_methods_on_cpu_tensors():
     s_auto = quality(W, "auto")
     assert (s_svd[0][0] / s_svd[0][-1])**2 > 1e4
     np.testing.assert_array_equal(s_auto[0], s_svd[0])          # fell back: identical factorisation
+    Ww = rng.randn(60, 120) / np.sqrt(120)          # wide but ill conditioned: Gram attempted, rejected
+    Ww[-1] = Ww[0] * (1 + 1e-9)
+    np.testing.assert_array_equal(quality(Ww, "auto")[0], quality(Ww, "svd")[0])
     W[-1] = W[0]                                    # rank deficient
     s_auto, s_svd = quality(W, "auto"), quality(W, "svd")
     np.testing.assert_array_equal(s_auto[0], s_svd[0])

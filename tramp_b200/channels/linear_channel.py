@@ -102,7 +102,7 @@ def thin_svd_device(W, method="svd"):
     (cond^2 must stay far below 1/eps): much cheaper for large batches.
     method "auto": "gram" when every matrix of the batch has cond(W)^2 <= 1e4
     (the singular vectors then stay orthonormal to ~1e-12 and the numerical rank
-    is unambiguous), else "svd".
+    is unambiguous), else "svd"; nearly square matrices go to "svd" directly.
     method "jacobi": `block_jacobi_svd`, full-rank W only (opt-in; batched GEMMs and
     small eigen-problems over the whole batch -- see DESIGN 11).
     Setup is outside the EP hot path (the reference reports it separately as
@@ -110,6 +110,11 @@ def thin_svd_device(W, method="svd"):
     t = ops.torch()
     B, M, N = W.shape
     if method == "auto":
+        # a nearly square matrix with independent entries has cond ~ 1 / (1 - sqrt(aspect))
+        # (Marchenko-Pastur edge): beyond aspect 0.92 cond^2 exceeds 1e4 and the Gram attempt
+        # would only be paid for and thrown away
+        if min(M, N) > 0.92 * max(M, N):
+            return thin_svd_device(W, "svd")
         Ut, s, Vt = thin_svd_device(W, "gram")
         ok = t.isfinite(s).all() and bool(((s[:, -1] / s[:, 0])**2 >= 1e-4).all())
         return (Ut, s, Vt) if ok else thin_svd_device(W, "svd")
