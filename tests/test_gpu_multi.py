@@ -80,3 +80,42 @@ def test_row_sharded_instance_matches_reference(golden_dir, tmp_path, name, back
         np.testing.assert_allclose(r["vz"], sw[name + "_vz_final"], rtol=1e-9)
     # the replicated state is bit-identical across ranks (every rank adds the same vectors in rank order)
     assert np.array_equal(res[0]["rx"], res[1]["rx"]) and np.array_equal(res[0]["mse"], res[1]["mse"])
+
+
+def _instances_worker(rank, world, port, out_path):
+    import torch
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    from tramp_b200.experiments import run_ep_sharded
+    from tests.test_distributed_cpu import _ep_builders
+    build_model, x_true, B = _ep_builders()
+    res = run_ep_sharded(build_model, B, x_true=x_true, max_iter=40)
+    np.savez(out_path % rank, rx=res["r"]["x"], vx=res["v"]["x"], n_iter=res["n_iter"], mse=res["mse"])
+    dist.destroy_process_group()
+
+
+def test_instances_sharded_over_two_gpus_match_the_oracle(tmp_path):
+    """BASELINE config 3 in miniature: five independent instances as blocks of 3 and 2
+    on two GPUs (run_ep_sharded, no data-path collective, results gathered over NCCL);
+    every instance stops where its own oracle run stops, with the oracle's posterior."""
+    import torch
+    import torch.multiprocessing as mp
+    if not torch.cuda.is_available() or torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    from oracle import tramp_oracle as orc
+    from tests.test_distributed_cpu import _ep_problem
+    out = str(tmp_path / "inst_rank%d.npz")
+    mp.spawn(_instances_worker, args=(2, 29650 + os.getpid() % 300, out), nprocs=2, join=True)
+    r0, r1 = np.load(out % 0), np.load(out % 1)
+    for k in r0.files:
+        assert np.array_equal(r0[k], r1[k], equal_nan=True)
+    W, x, y = _ep_problem()
+    for b in range(W.shape[0]):
+        ref = orc.ep_glm(dict(kind="gauss_bernoulli", rho=0.2), W[b], dict(kind="gaussian", var=1e-2, y=y[b]),
+                         40, early_stopping=dict(tol=1e-6), x_true=x[b])
+        assert r0["n_iter"][b] == ref["n_iter"]
+        np.testing.assert_allclose(r0["rx"][b], ref["r_x"], rtol=1e-9, atol=1e-9 * np.abs(ref["r_x"]).max())
+        np.testing.assert_allclose(r0["vx"][b], ref["v_x"], rtol=1e-9)
