@@ -34,7 +34,6 @@ def check_sgn_mse_rows(rows, batched):
     * the uninformative fixed point (v_x = tau_x to 1e-7): az - 1/tau_z ~ 1e-8 decides
       the domain assertion of abs_likelihood.py:57-58; today's reference raises on one
       of the three such rows of its own table.  Either outcome is accepted there."""
-    import pytest
     from tramp_b200.experiments import run_state_evolution, run_state_evolution_grid
     from tramp_b200.algos import CustomInit
     rows = np.atleast_2d(rows)

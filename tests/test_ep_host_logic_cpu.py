@@ -3,7 +3,6 @@ tests/test_gpu_api.py with `trb_sweep_run` emulated by the oracle
 (tests/_emulated_device.py).  Under test: model compilation, initialisers and
 damping maps into the descriptor, the device-replay and the synchronous callback
 paths, chunked early stopping, snapshots / roll-back, scenarios -- not kernels."""
-import json
 import os
 import numpy as np
 import pytest
