@@ -16,7 +16,7 @@ from numpy.testing import assert_allclose
 def make_batch(B, N, M, rho=0.1, var_noise=1e-2, seed=0):
     """B teacher instances with exactly Gaussian W in factored form (tramp_b200/synthetic.py)."""
     from tramp_b200 import synthetic
-    return synthetic.gaussian_glm_batch(B, N, M, rho, var_noise, seed=seed, workers=4)
+    return synthetic.gaussian_glm_batch(B, N, M, rho, var_noise, seed=seed, workers=8)
 
 
 def _linear(data, lo=None, hi=None):

@@ -11,6 +11,9 @@ rm -f $S
 timeout 400 python -m pytest tests/test_gpu_sizes.py tests/test_gpu_se_reference_examples.py -m gpu -q -p no:cacheprovider \
     > gpurun_out/r02a_test_new.log 2>&1; echo "new tests rc=$?" >> $S
 timeout 600 python -m pytest tests -m gpu -q -p no:cacheprovider > gpurun_out/r02a_test_all.log 2>&1; echo "all tests rc=$?" >> $S
+# the north-star-shape checks again with 4 instances: CUDA-graph replay + 2-CTA clusters, a combination no other test reaches
+TRB_TEST_INSTANCES=4 timeout 300 python -m pytest tests/test_gpu_sizes.py -m gpu -q -p no:cacheprovider \
+    > gpurun_out/r02a_test_sizes_b4.log 2>&1; echo "sizes B=4 rc=$?" >> $S
 timeout 100 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/r02a_smoke.log 2>&1; echo "smoke rc=$?" >> $S
 timeout 400 python bench.py > gpurun_out/r02a_bench_1gpu.json 2> gpurun_out/r02a_bench.err; echo "bench rc=$?" >> $S
 timeout 300 python tools/bench_setup.py --batch 8 --n 4096 --alpha 0.5 --streams 2 4 8 --jacobi-blocks 16 \
