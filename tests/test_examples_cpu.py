@@ -48,5 +48,5 @@ def test_glm_ep_vs_se(emulated_device, examples_on_path, tmp_path):  # noqa: F81
     assert sorted(cs.columns) == ["N", "alpha", "ensemble_type", "n_iter", "prior_rho", "source", "v", "x_id"]
     assert len(cs) == 3 * 2 * 3 and set(cs.source) == {"SE", "EP", "mse"}
     pc = pd.read_csv(tmp_path / "perceptron_ep_vs_se.csv")
-    assert sorted(pc.columns) == ["N", "alpha", "n_iter", "p_pos", "source", "v", "x_id"]
-    assert len(pc) == 2 * 6 * 3
+    assert sorted(pc.columns) == ["N", "alpha", "n_iter", "prior_p_pos", "source", "v", "x_id"]
+    assert len(pc) == 2 * 4 * 3
