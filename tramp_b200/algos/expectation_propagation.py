@@ -16,23 +16,43 @@ def _variable_log_partition(ax, bx):
 
 
 class ExpectationPropagation(MessagePassing):
+    """EP = the message-passing driver with (a, b) messages: a node answers with its
+    moment-matched messages, a variable with its posterior (r, v), and the objective is
+    the sum of the log-partitions (reference expectation_propagation.py:5-32).  On the
+    device-resident path these bindings are what `trb_sweep_run` implements; they are
+    called node by node only by the host-driven schedule (adaptive damping, update_dA)."""
+
     def __init__(self, model):
-        model.init_shapes()
-        super().__init__(model, message_keys=["a", "b"])
+        model.init_shapes()                 # (a, b) messages need the shapes of the variables
+        MessagePassing.__init__(self, model, message_keys=["a", "b"])
         self.default_stopping = EarlyStoppingEP()
 
-    def forward(self, node, message):
+    # -- what the driver asks of a node ------------------------------------------------
+    @staticmethod
+    def forward(node, message):
         return node.forward_message(message)
 
-    def backward(self, node, message):
+    @staticmethod
+    def backward(node, message):
         return node.backward_message(message)
 
-    def update(self, variable, message):
-        r, v = variable.posterior_rv(message)
-        return dict(r=r, v=v)
+    @staticmethod
+    def update(variable, message):
+        return dict(zip(("r", "v"), variable.posterior_rv(message)))
 
-    def node_objective(self, node, message):
+    @staticmethod
+    def node_objective(node, message):
         return node.log_partition(message)
+
+    # -- objective -----------------------------------------------------------------------
+    def log_evidence(self, update=True):
+        "A_model = ln Z of the EP approximation (recomputed from the current messages by default)"
+        if update:
+            self.update_objective()
+        return self.A_model
+
+    def surprisal(self, update=True):
+        return -self.log_evidence(update)
 
     def update_objective(self):
         """reference message_passing.py:306-328: A_model = sum_nodes A - sum_fwd-edges A.
@@ -60,13 +80,3 @@ class ExpectationPropagation(MessagePassing):
         for f, b in pairs:
             self.A_edge_by_name[f] = self.A_edge_by_name[b] = self.A_edges[f]
         self.A_model = sum(A.values()) - sum(self.A_edges.values())
-
-    def log_evidence(self, update=True):
-        if update:
-            self.update_objective()
-        return self.A_model
-
-    def surprisal(self, update=True):
-        if update:
-            self.update_objective()
-        return -self.A_model

@@ -1,23 +1,32 @@
-"""Binary belief (reference tramp/beliefs/binary.py:4-17)."""
+"""Binary belief p(x) ~ exp(b x) on x = +-1 (reference tramp/beliefs/binary.py:4-17):
+log-partition ln 2cosh(b), mean tanh(b), variance 1 - tanh(b)^2, second moment 1.
+
+All three are evaluated by the moment routine of the BinaryPrior factor
+(tramp_b200/csrc/trb_moments.cuh) with a symmetric prior (b0 = 0): its scalar
+log-partition is A(b + b0) - A(b0) - a/2, so with a = 0 the belief's log-partition is
+that value plus A(0) = ln 2."""
+import math
+
 from . import _dev
 from .. import ops, _lib
 
-_F = lambda: ops.make_factor(_lib.BINARY_PRIOR)  # noqa: E731
+_LN2 = math.log(2.0)
+
+
+def _symmetric_prior(what, b, a):
+    return _dev.elementwise(ops.make_factor(_lib.BINARY_PRIOR), a, b, None, what)
 
 
 def A(b):
-    # binary_prior's scalar log-partition is A(b + b0) - A(b0) - a/2 with
-    # b0 = 0: A(0) = log 2 is added back and a = 0 drops the last term
-    import numpy as np
-    return _dev.elementwise(_F(), 0.0, b, None, "A") + np.log(2.0)
+    return _symmetric_prior("A", b, a=0.0) + _LN2
 
 
 def r(b):
-    return _dev.elementwise(_F(), 1.0, b, None, "r")
+    return _symmetric_prior("r", b, a=1.0)
 
 
 def v(b):
-    return _dev.elementwise(_F(), 1.0, b, None, "v")
+    return _symmetric_prior("v", b, a=1.0)
 
 
 def tau(b):
