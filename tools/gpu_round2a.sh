@@ -22,3 +22,6 @@ timeout 200 python tools/bench_setup.py --batch 64 --n 1000 --alpha 0.5 --stream
     > gpurun_out/r02a_setup_n1000.json 2>> gpurun_out/r02a_setup.err; echo "setup n1000 rc=$?" >> $S
 cat $S; tail -15 gpurun_out/r02a_test_new.log; tail -4 gpurun_out/r02a_test_all.log; tail -1 gpurun_out/r02a_smoke.log
 cut -c1-600 gpurun_out/r02a_bench_1gpu.json; cat gpurun_out/r02a_setup_n4096.json gpurun_out/r02a_setup_n1000.json
+# afterwards, on two GPUs (separate call):
+#   gpurun --gpus 2 --timeout 600 -- 'python -m pytest tests/test_gpu_multi.py -m gpu -q'
+# (row-sharded instance over peer memory / NCCL, and run_ep_sharded over NCCL, not yet run)
