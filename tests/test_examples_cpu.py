@@ -50,3 +50,11 @@ def test_glm_ep_vs_se(emulated_device, examples_on_path, tmp_path):  # noqa: F81
     pc = pd.read_csv(tmp_path / "perceptron_ep_vs_se.csv")
     assert sorted(pc.columns) == ["N", "alpha", "n_iter", "prior_p_pos", "source", "v", "x_id"]
     assert len(pc) == 2 * 4 * 3
+
+
+def test_sharded_instances_single_rank(emulated_device, examples_on_path, capsys):  # noqa: F811
+    import sharded_instances
+    res = sharded_instances.main(["--instances", "3", "--n", "64", "--max-iter", "30"])
+    assert res["r"]["x"].shape == (3, 64) and res["mse"].shape == (30, 3)
+    assert "3 instances on 1 rank(s)" in capsys.readouterr().out
+    sys.modules.pop("sharded_instances", None)
