@@ -421,6 +421,9 @@ class LinearOp:
     """State of `LinearChannel.__init__` (linear_channel.py:30-46): rank by
     matrix_rank, FULL svd with the dense rectangular S (:8-15)."""
 
+    AMIN, AMAX = AMIN, AMAX          # Factor.AMIN / AMAX (base.py:238-243), per instance after
+                                     # reset_precision_bounds
+
     def __init__(self, W):
         W = np.asarray(W, dtype=float)
         self.W = W
@@ -570,7 +573,7 @@ def ep_glm(prior, W, lik, max_iter, damping=None, init=None, x_true=None,
         E["e2"] = [E["e1"][0], E["e1"][1]]                                # F2
         az, bz, ax, bx = E["e2"][0], E["e2"][1], E["e6"][0], E["e6"][1]
         rx, vx = lin_forward_posterior(op, az, bz, ax, bx)               # F3
-        a, b = ab_new(rx, vx, ax, bx)
+        a, b = ab_new(rx, vx, ax, bx, op.AMIN, op.AMAX)
         check("e3", a, b)
         E["e3"] = [_damp(damp["e3"], E["e3"][0], a), _damp(damp["e3"], E["e3"][1], b)]
         E["e4"] = [E["e3"][0], E["e3"][1]]                                # F4
@@ -581,7 +584,7 @@ def ep_glm(prior, W, lik, max_iter, damping=None, init=None, x_true=None,
         E["e6"] = [E["e5"][0], E["e5"][1]]                                # B2
         az, bz, ax, bx = E["e2"][0], E["e2"][1], E["e6"][0], E["e6"][1]
         rz, vz = lin_backward_posterior(op, az, bz, ax, bx)              # B3
-        a, b = ab_new(rz, vz, az, bz)
+        a, b = ab_new(rz, vz, az, bz, op.AMIN, op.AMAX)
         check("e7", a, b)
         E["e7"] = [_damp(damp["e7"], E["e7"][0], a), _damp(damp["e7"], E["e7"][1], b)]
         E["e8"] = [E["e7"][0], E["e7"][1]]                                # B4

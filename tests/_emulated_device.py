@@ -202,6 +202,7 @@ def _sweep_run(self, sw_ref, it0, n_iter, fresh, stream):
             W = (Ut[o, :, :M].T * sv[o]) @ Vt[o, :, :N]
             self._ops_cache[key] = (W, O.LinearOp(W))
         W, op = self._ops_cache[key]
+        op.AMIN, op.AMAX = sw.lin_amin, sw.lin_amax          # LinearChannel.reset_precision_bounds
         lik = dict(lik0, y=y[b, :M].copy())
         for k in range(n_iter):
             it = it0 + k

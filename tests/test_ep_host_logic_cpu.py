@@ -276,7 +276,7 @@ def test_options_reach_the_right_edges(emulated_device, seed):  # noqa: F811
 
 def test_reset_precision_bounds_reaches_the_sweep(emulated_device, sw):  # noqa: F811
     """Factor.reset_precision_bounds (reference base.py:241-243): the clip bounds of the
-    prior's and the likelihood's new precisions travel in the factor descriptors."""
+    prior's, the channel's and the likelihood's new precisions travel in the descriptors."""
     from oracle import tramp_oracle as orc
     from tramp_b200.algos import ExpectationPropagation, PassCallback
     from tramp_b200.priors import GaussBernoulliPrior
@@ -290,21 +290,22 @@ def test_reset_precision_bounds_reaches_the_sweep(emulated_device, sw):  # noqa:
     y = np.where(W @ x >= 0, 1.0, -1.0)
     results = {}
     for bounds in (None, (1e-2, 3.0)):
-        prior, lik = GaussBernoulliPrior(size=N, rho=0.3), SgnLikelihood(y=y)
+        prior, lik, lin = GaussBernoulliPrior(size=N, rho=0.3), SgnLikelihood(y=y), LinearChannel(W)
         pspec, lspec = dict(kind="gauss_bernoulli", rho=0.3), dict(kind="sgn", y=y)
+        op = orc.LinearOp(W)
         if bounds:
-            prior.reset_precision_bounds(*bounds)
-            lik.reset_precision_bounds(*bounds)
+            for factor in (prior, lik, lin):
+                factor.reset_precision_bounds(*bounds)
             pspec.update(AMIN=bounds[0], AMAX=bounds[1])
             lspec.update(AMIN=bounds[0], AMAX=bounds[1])
-        ep = ExpectationPropagation((prior @ V("x") @ LinearChannel(W) @ V("z") @ lik).to_model())
+            op.AMIN, op.AMAX = bounds
+        ep = ExpectationPropagation((prior @ V("x") @ lin @ V("z") @ lik).to_model())
         ep.iterate(max_iter=12, callback=PassCallback(), damping=0.2)
         with np.errstate(all="ignore"):
-            ref = orc.ep_glm(pspec, W, lspec, 12, damping=0.2)
+            ref = orc.ep_glm(pspec, W, lspec, 12, damping=0.2, op=op)
         got = ep.get_variables_data()
         assert_allclose(got["x"]["r"], ref["r_x"], rtol=1e-9, atol=1e-12)
         assert_allclose(got["z"]["v"], ref["v_z"], rtol=1e-9)
-        a5 = float(ep._edge("e5")[0])
-        results[bounds] = (got["x"]["r"], a5)
-    assert results[(1e-2, 3.0)][1] <= 3.0 < results[None][1]          # the bound binds, and changes the run
+        results[bounds] = (got["x"]["r"], max(float(ep._edge(e)[0]) for e in ("e1", "e3", "e5", "e7")))
+    assert results[(1e-2, 3.0)][1] <= 3.0 < results[None][1]          # the bounds bind, and change the run
     assert np.abs(results[None][0] - results[(1e-2, 3.0)][0]).max() > 1e-3
