@@ -184,6 +184,38 @@ int trb_lin_expand_gemm(const double* A, int R, int n, int ld, int B,
  * loads / loads without MMA), used by tools/bench_gemm.py only */
 void trb_gemm_set_variant(int variant);
 
+/* ---- LinearChannel set-up: thin SVD by one-sided block Jacobi (trb_setup.cu) ----
+ * Replaces np.linalg.svd / np.linalg.matrix_rank of channels/linear/linear_channel.py:8-15,
+ * 36-46 (LAPACK gesdd on the host; counted in EP's total by examples/figures/benchmark.py:22).
+ *
+ * A[B, np, ld] (np % 32 == 0, ld % 64 == 0, 16-byte aligned, padding rows and columns
+ * zero) holds np vectors per instance, one per row: either the rows of the Gram matrix of
+ * the short side of W (then the rotated rows converge to lambda_i u_i^T) or the rows of the
+ * short side of W itself (-> s_i v_i^T).  One call = one sweep: every pair of 16-row blocks
+ * meets once (round-robin), A[b] <- Q^T A[b] in place with Q orthogonal, three launches per
+ * round over the whole batch (pair Gram on DMMA, 32 x 32 eigenvectors by cyclic Jacobi in
+ * shared memory, pair rotation on DMMA).
+ *   Swork  [B, np/32, trb_jacobi_zsplit(B, np, ld), 1024]   partial pair Grams
+ *   Jwork  [B, np/32, 1024]                                 pair rotations
+ *   rot_flag [B, np/32] int                                 0: pair already orthogonal, skipped
+ *   offmax [B]  out: largest |cos| between two rows of a pair BEFORE its rotation
+ *   skip_tol   pairs whose largest |cos| is <= skip_tol are left untouched
+ *   max_inner  sweeps of the inner 32 x 32 Jacobi (2 is enough: the outer sweeps converge
+ *              quadratically either way) */
+int trb_jacobi_zsplit(int B, int np, int ld);
+int trb_jacobi_sweep(double* A, int64_t strideA, int B, int np, int ld, double* Swork,
+                     double* Jwork, int* rot_flag, double* offmax, double skip_tol,
+                     int max_inner, void* stream);
+/* norms[b, i] = || A[b, i, :n] ||_2;  A: [B, rows, ld] (ld even, 16-byte aligned) */
+int trb_row_norms(const double* A, int64_t strideA, int B, int rows, int n, int ld,
+                  double* norms, void* stream);
+/* dst[b, i, :n] = scale[b, i] * src[b, perm[b, i], :n], i < R; columns n..ld_dst-1 of dst are
+ * zeroed.  perm (int64) and scale may be NULL (identity / 1); dst may be src when perm is
+ * NULL.  Used to sort, normalise and pad the singular vectors. */
+int trb_rows_gather_scale(const double* src, int64_t stride_src, int ld_src,
+                          const long long* perm, const double* scale, int B, int R, int n,
+                          double* dst, int64_t stride_dst, int ld_dst, void* stream);
+
 /* Spectrum rescale between the projections and the expansions, plus the
  * variances (linear_channel.py:58-67, 74, 91-105).
  *   dir = 0 (forward, x-side mean):  coef = s*res*(tz + s*tx),  v = forward variance

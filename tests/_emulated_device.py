@@ -444,13 +444,74 @@ def _lin_rescale(self, direction, B, R, Nz, Nx, rank, null_space, s, s2, stride,
     return 0
 
 
+def _rr_pair(nb, rnd, k):
+    m = nb - 1
+    return (m, rnd % m) if k == 0 else ((rnd + k) % m, (rnd - k + m) % m)
+
+
+def _jacobi_sweep(self, A, strideA, B, n_rows, ld, Swork, Jwork, rot_flag, offmax, skip_tol, max_inner, stream):
+    """trb_jacobi_sweep: one round-robin sweep over the pairs of 16-row blocks; the pair's
+    rotation comes from LAPACK here (eigenvectors ordered closest to the identity, which is
+    what the kernel's small-angle cyclic Jacobi produces)."""
+    nb = n_rows // 16
+    off_out = _arr(offmax, B)
+    for b in range(B):
+        Ab = _arr(A, b * strideA + n_rows * ld)[b * strideA:].reshape(n_rows, ld)
+        worst = 0.0
+        for rnd in range(nb - 1):
+            for k in range(nb // 2):
+                p, q = _rr_pair(nb, rnd, k)
+                idx = np.r_[p * 16:(p + 1) * 16, q * 16:(q + 1) * 16]
+                X = Ab[idx]
+                S = X @ X.T
+                d = np.sqrt(np.abs(np.diag(S)))
+                with np.errstate(all="ignore"):
+                    Cs = np.abs(S) / np.outer(d, d)
+                Cs[~np.isfinite(Cs)] = 0.0
+                np.fill_diagonal(Cs, 0.0)
+                off = Cs.max()
+                worst = max(worst, off)
+                if not off > skip_tol:
+                    continue
+                _, E = np.linalg.eigh(S)
+                where = np.abs(E).argmax(axis=0)
+                E = E[:, np.argsort(where - 0.5 * np.abs(E).max(axis=0), kind="stable")]
+                E = E * np.where(np.diag(E) < 0, -1.0, 1.0)[None, :]
+                Ab[idx] = E.T @ X
+        off_out[b] = worst
+    return 0
+
+
+def _row_norms(self, A, strideA, B, rows, n, ld, norms, stream):
+    for b in range(B):
+        Ab = _arr(A, b * strideA + rows * ld)[b * strideA:].reshape(rows, ld)
+        _arr(norms, (b + 1) * rows)[b * rows:] = np.linalg.norm(Ab[:, :n], axis=1)
+    return 0
+
+
+def _rows_gather_scale(self, src, stride_src, ld_src, perm, scale, B, R, n, dst, stride_dst, ld_dst, stream):
+    for b in range(B):
+        pr = np.ctypeslib.as_array(C.cast(perm, C.POINTER(C.c_int64)), shape=((b + 1) * R,))[b * R:] if perm else np.arange(R)
+        rows_src = int(pr.max()) + 1
+        Sb = _arr(src, b * stride_src + rows_src * ld_src)[b * stride_src:].reshape(rows_src, ld_src)
+        sc = _arr(scale, (b + 1) * R)[b * R:] if scale else np.ones(R)
+        vals = sc[:, None] * Sb[pr, :n]
+        Db = _arr(dst, b * stride_dst + R * ld_dst)[b * stride_dst:].reshape(R, ld_dst)
+        Db[:, :n] = vals
+        Db[:, n:] = 0.0
+    return 0
+
+
 for _name, _fn in (("trb_factor_posterior", _factor_posterior), ("trb_factor_log_partition", _factor_log_partition),
                    ("trb_factor_message", _factor_message), ("trb_posterior_rv", _posterior_rv),
                    ("trb_lin_project", _lin_project), ("trb_lin_expand", _lin_expand),
                    ("trb_lin_reduce_slots", _lin_reduce_slots), ("trb_lin_project_gemm", _lin_project_gemm),
-                   ("trb_lin_expand_gemm", _lin_expand_gemm), ("trb_lin_rescale", _lin_rescale)):
+                   ("trb_lin_expand_gemm", _lin_expand_gemm), ("trb_lin_rescale", _lin_rescale),
+                   ("trb_jacobi_sweep", _jacobi_sweep), ("trb_row_norms", _row_norms),
+                   ("trb_rows_gather_scale", _rows_gather_scale)):
     setattr(EmulatedLibrary, _name, _fn)
 EmulatedLibrary.trb_lin_expand_slots = lambda self, B, R: 1
+EmulatedLibrary.trb_jacobi_zsplit = lambda self, B, n_rows, ld: 1
 
 EmulatedLibrary.trb_sweep_run = _sweep_run
 EmulatedLibrary.trb_sweep_stage = lambda self, sw_ref, stage, it, first, pre, stream: 0

@@ -7,6 +7,7 @@ import re
 import numpy as np
 import pytest
 from numpy.testing import assert_allclose
+from tests._emulated_device import emulated_device  # noqa: F401
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
@@ -284,23 +285,13 @@ def test_factories_name_what_this_build_covers():
             call(**kw)
 
 
-@pytest.mark.parametrize("shape,block", [((2, 64, 128), 8), ((1, 50, 120), 8), ((3, 48, 48), 16),
-                                         ((2, 120, 60), 16), ((1, 5, 9), 16), ((1, 1, 4), 16)])
-def test_block_jacobi_svd_on_cpu_tensors(shape, block):
-    """svd_method="jacobi" (opt-in set-up for large batches): batched one-sided block
-    Jacobi against LAPACK on wide, tall, square, ragged and tiny matrices."""
-    import torch
-    from tramp_b200.channels.linear_channel import block_jacobi_svd, thin_svd_device
-    B, M, N = shape
-    W = np.random.RandomState(3).randn(B, M, N) / np.sqrt(N)
-    Wt = torch.as_tensor(W)
-    Ut, s, Vt = block_jacobi_svd(Wt, block=block) if M <= N else thin_svd_device(Wt, "jacobi")
-    R = min(M, N)
-    assert Ut.shape == (B, R, M) and s.shape == (B, R) and Vt.shape == (B, R, N)
-    s_ref = np.linalg.svd(W, compute_uv=False)
-    assert_allclose(s.numpy(), s_ref, rtol=1e-11, atol=1e-13 * s_ref.max())
-    assert np.all(np.diff(s.numpy(), axis=-1) <= 0)
-    assert_allclose(torch.einsum("brm,br,brn->bmn", Ut, s, Vt).numpy(), W, atol=1e-13)
-    eye = np.eye(R)
-    assert_allclose((Ut @ Ut.transpose(1, 2)).numpy(), np.broadcast_to(eye, (B, R, R)), atol=1e-11)
-    assert_allclose((Vt @ Vt.transpose(1, 2)).numpy(), np.broadcast_to(eye, (B, R, R)), atol=1e-11)
+@pytest.mark.parametrize("shape,method", [((2, 64, 128), "jacobi"), ((1, 50, 120), "jacobi"), ((3, 48, 48), "jacobi_direct"),
+                                          ((2, 120, 60), "jacobi"), ((1, 5, 9), "auto"), ((1, 1, 4), "auto"),
+                                          ((1, 40, 41), "auto"), ((2, 33, 70), "jacobi_direct")])
+def test_jacobi_thin_svd_host_logic(emulated_device, shape, method):
+    """The hand-written set-up (svd_method "auto" / "jacobi" / "jacobi_direct"): padding of the work
+    matrix, sweep loop and stopping rule, sorting, back-multiplication, tall / wide / odd shapes,
+    against LAPACK.  The kernels are emulated here (tests/_emulated_device.py); the same body runs
+    on the device in tests/test_gpu_setup.py."""
+    from tests.setup_properties import check_thin_svd
+    check_thin_svd(shape, method)

@@ -1,36 +1,35 @@
 """Set-up of LinearChannel (the factorisation the reference does in its constructor,
-channels/linear/linear_channel.py:8-15, 36-46), which DESIGN 11 names as the
-end-to-end cost once the sweep runs at the HBM roofline: how fast can B matrices of
-the north-star shape be brought into thin-SVD form on one B200?
+channels/linear/linear_channel.py:8-15, 36-46, and counts in EP's total time,
+examples/figures/benchmark.py:22): how fast are B matrices of the north-star shape brought
+into thin-SVD form on one B200?
 
-Variants timed on the same Gaussian W [B, M, N] (all library calls; the point is to
-find out what a hand-written batched eigensolver has to beat):
+Variants timed on the same real Gaussian W [B, M, N] = randn / sqrt(N):
 
-  svd            torch.linalg.svd on the batch                       (cuSOLVER gesvd/gesvdj)
-  gram           W W^T, torch.linalg.eigh on the batch, V = W^T U / s (thin_svd_device "gram")
-  gram_streams   the same, one matrix per task on S CUDA streams driven by S host threads
-                 (syevd is latency-bound on one 2048 x 2048 matrix; independent matrices
-                 can overlap)
-  gram_parts     the three steps of "gram" timed separately (Gram DGEMM, eigh, back-multiply)
-  jacobi_b       block_jacobi_svd with blocks of b rows: every step a batched GEMM or a batched
-                 2b x 2b eigen-problem over all instances and block pairs (thin_svd_device "jacobi")
+  jacobi         the hand-written set-up (thin_svd_device "jacobi": DMMA Gram, block-Jacobi
+                 sweeps of trb_setup.cu, DMMA back-multiplication), with the time of its
+                 parts, the number of sweeps and the FP64 rate of the Jacobi kernels
+  jacobi_direct  the same kernels on the rows of W itself (no Gram; what "auto" uses for
+                 nearly square W)
+  gram           round-1 baseline: W W^T, torch.linalg.eigh (cuSOLVER syevd), V = W^T U / s
+  svd            round-1 baseline: torch.linalg.svd (cuSOLVER gesvd), on <= 2 instances
 
-Every variant is checked against the first: singular values to 1e-10 relative and
-||Ut W - diag(s) Vt|| / ||W||.  Prints one JSON line; nothing here is on the EP path.
+Every variant is checked against LAPACK-quality references: singular values against the
+library's, orthonormality of both factors, ||Ut W - diag(s) Vt|| / ||W||.  Prints one JSON
+line; nothing here is on the EP sweep.
 
-    python tools/bench_setup.py --batch 16 --n 4096 --alpha 0.5 --streams 1 2 4 8 16
+    python tools/bench_setup.py --batch 16 --n 4096 --alpha 0.5
 """
 import argparse
 import json
 import os
 import sys
 import time
-from concurrent.futures import ThreadPoolExecutor
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch  # noqa: E402
 
-from tramp_b200.channels.linear_channel import thin_svd_device, block_jacobi_svd  # noqa: E402
+from tramp_b200 import ops  # noqa: E402
+from tramp_b200.channels import linear_channel as lc  # noqa: E402
 
 
 def sync():
@@ -50,37 +49,57 @@ def timed(fn, repeat):
     return best, out
 
 
-def gram_one(W):
-    """thin_svd_device(..., "gram") for one [M, N] matrix with M <= N."""
-    G = W @ W.T
-    ev, U = torch.linalg.eigh(G)
-    ev, U = ev.flip(-1), U.flip(-1)
-    s = ev.clamp_min(0).sqrt()
-    Ut = U.T.contiguous()
-    return Ut, s, (Ut @ W) / s[:, None]
+def quality(W, Ut, s, Vt, s_ref=None):
+    R = s.shape[-1]
+    eye = torch.eye(R, dtype=W.dtype, device=W.device)
+    q = {"residual": float(((Ut @ W - s[:, :, None] * Vt).norm() / W.norm()).item()),
+         "orth_U": float((Ut @ Ut.transpose(1, 2) - eye).abs().max().item()),
+         "orth_V": float((Vt @ Vt.transpose(1, 2) - eye).abs().max().item())}
+    if s_ref is not None:
+        q["s_rel_dev"] = float(((s - s_ref).abs() / s_ref).max().item())
+    return q
 
 
-def gram_streams(W, n_streams):
-    B = W.shape[0]
-    streams = [torch.cuda.Stream() for _ in range(n_streams)]
-    out = [None] * B
-    ready = torch.cuda.Event()
-    ready.record()
+def jacobi_parts(W, route):
+    """The stages of jacobi_thin_svd timed one by one (CUDA events around each), plus the
+    sweep history."""
+    B, M, N = W.shape
+    L = M if route == "gram" else N
+    n_rows, ld = lc._ceil_to(M, ops.JACOBI_ROWS), lc._ceil_to(L, ops.JACOBI_COLS)
 
-    def work(k):
-        with torch.cuda.stream(streams[k]):
-            streams[k].wait_event(ready)
-            for b in range(k, B, n_streams):
-                out[b] = gram_one(W[b])
-    with ThreadPoolExecutor(max_workers=n_streams) as pool:
-        list(pool.map(work, range(n_streams)))
-    for s in streams:
-        torch.cuda.current_stream().wait_stream(s)
-    return tuple(torch.stack([o[i] for o in out]) for i in range(3))
-
-
-def residual(W, Ut, s, Vt):
-    return float(((Ut @ W - s[:, :, None] * Vt).norm() / W.norm()).item())
+    def ev():
+        e = torch.cuda.Event(enable_timing=True)
+        e.record()
+        return e
+    A = torch.zeros((B, n_rows, ld), dtype=torch.float64, device=W.device)
+    e0 = ev()
+    if route == "gram":
+        for b in range(B):
+            lc._gram_rows(W[b], A[b])
+    else:
+        A[:, :M, :N] = W
+    e1 = ev()
+    work = ops.jacobi_workspace(B, n_rows, ld, W.device)
+    sweeps = []
+    marks = [e1]
+    for _ in range(40):
+        off = float(ops.jacobi_sweep(A, work, skip_tol=5e-15, max_inner=2).max().item())
+        marks.append(ev())
+        sweeps.append(off)
+        if off < 1e-13 or (len(sweeps) > 1 and off < 1e-10 and off > 0.5 * sweeps[-2]):
+            break
+    sync()
+    sweep_ms = [marks[i].elapsed_time(marks[i + 1]) for i in range(len(marks) - 1)]
+    pairs = (n_rows // 16) * (n_rows // 16 - 1) // 2
+    flops_sweep = pairs * 2.0 * 32 * 32 * ld * (10.0 / 16 + 1.0) * B    # Gram (upper tiles) + rotation
+    bytes_sweep = (n_rows // 16 - 1) * 3.0 * n_rows * ld * 8 * B        # rows: 2 reads + 1 write per round
+    full = [ms for ms in sweep_ms[:-2]] or sweep_ms
+    return {"gram_ms_per_instance": e0.elapsed_time(e1) / B,
+            "sweeps": len(sweeps), "off": sweeps, "sweep_ms": sweep_ms,
+            "jacobi_ms_per_instance": sum(sweep_ms) / B,
+            "full_sweep_tflops": flops_sweep / (sum(full) / len(full) * 1e-3) / 1e12,
+            "full_sweep_hbm_gbs": bytes_sweep / (sum(full) / len(full) * 1e-3) / 1e9,
+            "zsplit": int(work["S"].shape[2])}
 
 
 def main():
@@ -88,50 +107,40 @@ def main():
     ap.add_argument("--batch", type=int, default=16)
     ap.add_argument("--n", type=int, default=4096)
     ap.add_argument("--alpha", type=float, default=0.5)
-    ap.add_argument("--streams", type=int, nargs="*", default=[2, 4, 8, 16])
-    ap.add_argument("--repeat", type=int, default=2)
-    ap.add_argument("--jacobi-blocks", type=int, nargs="*", default=[16, 32])
+    ap.add_argument("--repeat", type=int, default=1)
     ap.add_argument("--skip-svd", action="store_true")
-    ap.add_argument("--device", default="cuda", help='"cpu" only smoke-tests the script (no stream variant)')
+    ap.add_argument("--skip-gram", action="store_true")
+    ap.add_argument("--direct", action="store_true", help="also time the route on W itself")
     args = ap.parse_args()
-    dev = args.device
-    assert dev == "cpu" or torch.cuda.is_available(), "needs a CUDA device"
+    assert torch.cuda.is_available(), "needs a CUDA device"
     B, N = args.batch, args.n
     M = int(args.alpha * N)
-    assert M <= N, "the stream variant is written for M <= N"
-    gen = torch.Generator(device=dev).manual_seed(0)
-    W = torch.randn((B, M, N), dtype=torch.float64, device=dev, generator=gen) / N**0.5
+    gen = torch.Generator(device="cuda").manual_seed(0)
+    W = torch.randn((B, M, N), dtype=torch.float64, device="cuda", generator=gen) / N**0.5
     line = {"tool": "bench_setup", "B": B, "M": M, "N": N, "variants": {}}
+    wide = W if M <= N else W.transpose(1, 2).contiguous()
 
-    t_gram, ref = timed(lambda: thin_svd_device(W, "gram"), args.repeat)
-    line["variants"]["gram"] = {"s_per_instance": t_gram / B, "residual": residual(W, *ref)}
-
-    # the three steps of "gram"
-    t_g, G = timed(lambda: W @ W.transpose(1, 2), args.repeat)
-    t_e, (ev, U) = timed(lambda: torch.linalg.eigh(G), args.repeat)
-    Ut = U.flip(-1).transpose(1, 2).contiguous()
-    s = ev.flip(-1).clamp_min(0).sqrt()
-    t_b, _ = timed(lambda: (Ut @ W) / s[:, :, None], args.repeat)
-    line["variants"]["gram_parts"] = {"gram_dgemm_s": t_g / B, "eigh_s": t_e / B, "back_multiply_s": t_b / B,
-                                      "dgemm_tflops": 2.0 * M * M * N * B / t_g / 1e12}
-
-    for S in (args.streams if dev != "cpu" else []):
-        t_s, out = timed(lambda: gram_streams(W, S), args.repeat)
-        line["variants"][f"gram_streams_{S}"] = {
-            "s_per_instance": t_s / B, "residual": residual(W, *out),
-            "s_rel_dev": float(((out[1] - ref[1]).abs() / ref[1]).max().item())}
-
-    for b in args.jacobi_blocks:
-        t_j, out = timed(lambda: block_jacobi_svd(W, block=b), 1)
-        line["variants"][f"jacobi_{b}"] = {
-            "s_per_instance": t_j / B, "residual": residual(W, *out),
-            "s_rel_dev": float(((out[1] - ref[1]).abs() / ref[1]).max().item())}
-
+    s_ref = None
+    if not args.skip_gram:
+        t_gram, ref = timed(lambda: lc.thin_svd_device(W, "gram"), args.repeat)
+        s_ref = ref[1]
+        line["variants"]["gram_cusolver_eigh"] = {"ms_per_instance": 1e3 * t_gram / B, **quality(W, *ref)}
+        del ref
+    t_j, out = timed(lambda: lc.thin_svd_device(W, "jacobi"), args.repeat)
+    line["variants"]["jacobi"] = {"ms_per_instance": 1e3 * t_j / B, **quality(W, *out, s_ref=s_ref),
+                                  "parts": jacobi_parts(wide, "gram")}
+    if s_ref is None:
+        s_ref = out[1]
+    del out
+    if args.direct:
+        t_d, out = timed(lambda: lc.thin_svd_device(W, "jacobi_direct"), args.repeat)
+        line["variants"]["jacobi_direct"] = {"ms_per_instance": 1e3 * t_d / B, **quality(W, *out, s_ref=s_ref),
+                                             "parts": jacobi_parts(wide, "direct")}
+        del out
     if not args.skip_svd:
-        t_svd, out = timed(lambda: thin_svd_device(W[:min(B, 4)], "svd"), 1)
-        line["variants"]["svd"] = {
-            "s_per_instance": t_svd / min(B, 4), "residual": residual(W[:min(B, 4)], *out),
-            "s_rel_dev": float(((out[1] - ref[1][:min(B, 4)]).abs() / ref[1][:min(B, 4)]).max().item())}
+        k = min(B, 2)
+        t_svd, out = timed(lambda: lc.thin_svd_device(W[:k], "svd"), 1)
+        line["variants"]["svd_cusolver"] = {"ms_per_instance": 1e3 * t_svd / k, **quality(W[:k], *out, s_ref=s_ref[:k])}
     print(json.dumps(line), flush=True)
 
 

@@ -121,6 +121,10 @@ SIGNATURES = {
     "trb_lin_project_gemm": (_I, [_P, _I, _I, _I, _I, _P, _I, _P, _P]),
     "trb_lin_expand_gemm": (_I, [_P, _I, _I, _I, _I, _P, _P, _I, _P]),
     "trb_gemm_set_variant": (None, [_I]),
+    "trb_jacobi_zsplit": (_I, [_I, _I, _I]),
+    "trb_jacobi_sweep": (_I, [_P, _L, _I, _I, _I, _P, _P, _P, _P, _D, _I, _P]),
+    "trb_row_norms": (_I, [_P, _L, _I, _I, _I, _I, _P, _P]),
+    "trb_rows_gather_scale": (_I, [_P, _L, _I, _P, _P, _I, _I, _I, _P, _L, _I, _P]),
     "trb_lin_reduce_slots": (_I, [_I, _I, _I, _I, _P, _P, _P, _P, _P]),
     "trb_lin_rescale": (_I, [_I, _I, _I, _I, _I, _I, _I, _P, _P, _L, _P, _P, _P, _P, _P, _P, _P, _P]),
     "trb_comm_create": (_I, [_I, _I, C.c_size_t, C.POINTER(C.c_void_p), C.c_char_p]),

@@ -18,120 +18,141 @@ from .. import ops
 logger = logging.getLogger(__name__)
 
 
-def _round_robin(nb):
-    """Pairings of a round-robin tournament of nb (even) players: nb - 1 rounds of
-    nb / 2 disjoint pairs, every pair met exactly once per sweep."""
-    ring = list(range(1, nb))
-    for _ in range(nb - 1):
-        line = [0] + ring
-        yield [(line[k], line[nb - 1 - k]) for k in range(nb // 2)]
-        ring = ring[-1:] + ring[:-1]
+def _ceil_to(n, m):
+    return -(-int(n) // m) * m
 
 
-def block_jacobi_svd(W, block=16, tol=1e-14, max_sweeps=24):
-    """Thin SVD of a batch of full-rank matrices by one-sided BLOCK Jacobi (Hestenes),
-    written for a large batch on one GPU: every step is a batched FP64 GEMM or a batched
-    eigen-decomposition of 2b x 2b matrices over ALL instances and all disjoint block
-    pairs at once, instead of one latency-bound dense factorisation per instance.
+def jacobi_orthogonalise_rows(A, tol=1e-13, max_sweeps=40, max_inner=2):
+    """Rows of A[b] <- Q_b^T A[b] (Q_b orthogonal) until the rows of every instance are mutually
+    orthogonal: one-sided block Jacobi, `trb_jacobi_sweep` (tramp_b200/csrc/trb_setup.cu).
 
-    W [B, M, N], M <= N.  The rows are split in blocks of b; a sweep visits every pair of
-    blocks once (round-robin).  For the pairs of one round, gathered as P [B, pairs, 2b, N]:
-    G = P P^T, G = E diag(lam) E^T, P <- E^T P makes the 2b rows mutually orthogonal; the
-    same rotation is accumulated in U^T.  At convergence the rows of the rotated W are
-    s_i v_i^T.  Stops when every cosine between two rows seen in a sweep is below tol
-    (or has stalled at the rounding floor).  Returns (Ut [B,M,M], s [B,M], Vt [B,M,N]), s descending.
-    """
+    A [B, n_rows, ld] with n_rows % 32 == 0, ld % 64 == 0, zero padded; rotated in place.
+    A sweep reports the largest cosine between two rows it met BEFORE rotating them; the
+    iteration stops when that is below `tol` (or has stalled at the rounding floor).  One
+    read-back per sweep.  Returns the list of the sweeps' measures."""
+    t = ops.torch()
+    B, n_rows, ld = A.shape
+    work = ops.jacobi_workspace(B, n_rows, ld, A.device)
+    history = []
+    for sweep in range(max_sweeps):
+        off = float(ops.jacobi_sweep(A, work, skip_tol=0.05 * tol, max_inner=max_inner).max().item())
+        history.append(off)
+        if off != off:
+            raise FloatingPointError("block Jacobi: NaN in the matrix being factorised")
+        if off < tol or (len(history) > 1 and off < 1e-10 and off > 0.5 * history[-2]):
+            break
+    else:
+        logger.warning(f"block Jacobi: largest cosine {history[-1]:.1e} after {max_sweeps} sweeps")
+    return history
+
+
+def _gram_rows(Wb, out):
+    """out[:M, :M] = Wb Wb^T for Wb [M, N] (DMMA GEMM of trb_gemm.cu)."""
+    M, N = Wb.shape
+    if out.shape[-1] == M and out.is_contiguous():
+        ops.lin_project_gemm(Wb, M, N, Wb, M, out=out[:M])
+    else:
+        out[:M, :M] = ops.lin_project_gemm(Wb, M, N, Wb, M)
+
+
+def jacobi_thin_svd(W, route="gram", tol=1e-13, stats=None):
+    """Thin SVD of a batch of WIDE full-rank matrices W [B, M, N], M <= N, with the hand-written
+    kernels only (reference: np.linalg.svd in channels/linear/linear_channel.py:8-15).
+
+    route "gram":   G = W W^T (DMMA GEMM), rows of G rotated by block Jacobi until orthogonal:
+                    they are then lambda_i u_i^T, so s_i = sqrt(lambda_i), u_i the normalised
+                    rows, and V^T = diag(1/s) U^T W (DMMA GEMM).  Squares cond(W): for
+                    well-conditioned W (cond^2 << 1/eps).
+    route "direct": the rows of W themselves are rotated until orthogonal: they are then
+                    s_i v_i^T; U^T = diag(1/s) V^T W^T (DMMA GEMM).  No squaring.
+    Returns (Ut [B, M, M], s [B, M], Vt [B, M, N]), s descending."""
     t = ops.torch()
     B, M, N = W.shape
     assert M <= N
-    b = int(min(block, max(1, M // 2)))
-    nb = -(-M // b)
-    nb += nb % 2                                   # an even number of blocks; padding rows are zero
-    Mp = nb * b
-    A = t.zeros((B, Mp, N), dtype=W.dtype, device=W.device)
-    A[:, :M] = W
-    Ut = t.eye(Mp, dtype=W.dtype, device=W.device).repeat(B, 1, 1)[:, :, :M].contiguous()
-    rows = t.arange(Mp, device=W.device).reshape(nb, b)
-    rounds = [t.as_tensor(r, device=W.device) for r in _round_robin(nb)]
-    previous = float("inf")
-    for sweep in range(max_sweeps):
-        worst = t.zeros((), dtype=W.dtype, device=W.device)      # stays on the device: one read-back per sweep
-        for pairs in rounds:
-            idx = t.cat([rows[pairs[:, 0]], rows[pairs[:, 1]]], dim=1)       # [pairs, 2b]
-            flat = idx.reshape(-1)
-            P = A.index_select(1, flat).reshape(B, -1, 2 * b, N)
-            G = P @ P.transpose(-1, -2)
-            # convergence measure: largest cosine between two rows (padding rows, of norm ~eps, left out)
-            d = t.diagonal(G, dim1=-2, dim2=-1).clamp_min(0).sqrt()
-            live = d > 1e-12 * d.amax(dim=(-1, -2), keepdim=True)
-            C = G / (d[..., :, None] * d[..., None, :]).clamp_min(1e-300)
-            C = C * (live[..., :, None] & live[..., None, :])
-            worst = t.maximum(worst, (C - t.diag_embed(t.diagonal(C, dim1=-2, dim2=-1))).abs().max())
-            _, E = t.linalg.eigh(G)
-            # Of all orderings of the eigenvectors take one close to the identity (each vector
-            # goes where its largest component sits): rotations then shrink with the
-            # off-diagonal part and the sweeps converge quadratically; sorting by eigenvalue
-            # keeps relabelling nearly degenerate directions and converges only linearly.
-            big, where = E.abs().max(dim=-2)
-            perm = (where.to(E.dtype) - 0.5 * big).argsort(dim=-1)
-            Et = E.gather(-1, perm[..., None, :].expand_as(E)).transpose(-1, -2)
-            A.index_copy_(1, flat, (Et @ P).reshape(B, -1, N))
-            Q = Ut.index_select(1, flat).reshape(B, -1, 2 * b, M)
-            Ut.index_copy_(1, flat, (Et @ Q).reshape(B, -1, M))
-        off = float(worst)
-        # done: orthogonal to tol, or stalled at the rounding floor eps * cond(W)
-        if off < tol or (off < 1e-10 and off > 0.25 * previous):
-            break
-        previous = off
+    W = W.contiguous()
+    if N % 2:                                     # the GEMM kernels want 16-byte rows
+        Wp = t.zeros((B, M, N + 1), dtype=t.float64, device=W.device)
+        Wp[:, :, :N] = W
+        W = Wp
+    n_rows = _ceil_to(M, ops.JACOBI_ROWS)
+    L = M if route == "gram" else N
+    ld = _ceil_to(L, ops.JACOBI_COLS)
+    A = t.zeros((B, n_rows, ld), dtype=t.float64, device=W.device)
+    if route == "gram":
+        for b in range(B):
+            _gram_rows(W[b], A[b])
     else:
-        logger.warning(f"block Jacobi SVD: off-diagonal {off:.1e} after {max_sweeps} sweeps")
-    s_all = A.norm(dim=-1)
-    s, order = s_all.sort(dim=-1, descending=True)
-    order = order[:, :M]                                                     # padding rows have s = 0
-    s = s[:, :M]
-    Vt = A.gather(1, order[:, :, None].expand(B, M, N)) / s[:, :, None]
-    Ut = Ut.gather(1, order[:, :, None].expand(B, M, M))
-    return Ut.contiguous(), s.contiguous(), Vt.contiguous()
+        A[:, :M, :N] = W[:, :, :N]
+    history = jacobi_orthogonalise_rows(A, tol=tol)
+    if stats is not None:
+        stats["sweeps"] = len(history)
+        stats["off"] = history
+    norms = ops.row_norms(A, L)
+    top, order = norms.sort(dim=-1, descending=True)
+    top, order = top[:, :M].contiguous(), order[:, :M].contiguous()      # padding rows have norm 0
+    inv = t.where(top > 0, 1.0 / top, t.zeros_like(top))
+    first = ops.rows_gather_scale(A, L, perm=order, scale=inv)           # unit rows, sorted
+    del A
+    if route == "gram":
+        Ut, s = first, top.sqrt()
+        inv_s = t.where(s > 0, 1.0 / s, t.zeros_like(s))
+        Vt = t.empty((B, M, N), dtype=t.float64, device=W.device)
+        for b in range(B):                                                # V^T = U^T W, then rows / s
+            ops.lin_expand_gemm(W[b], M, N, Ut[b], M, out=Vt[b])
+        ops.rows_gather_scale(Vt, N, scale=inv_s, out=Vt)
+        return Ut, s.contiguous(), Vt
+    Vt, s = first, top
+    inv_s = inv
+    Ut = t.empty((B, M, M), dtype=t.float64, device=W.device)
+    for b in range(B):                                                    # U^T = V^T W^T, then rows / s
+        ops.lin_project_gemm(W[b], M, N, Vt[b], M, out=Ut[b])
+    ops.rows_gather_scale(Ut, M, scale=inv_s, out=Ut)
+    return Ut, s.contiguous(), Vt
 
 
-def thin_svd_device(W, method="svd"):
+def thin_svd_device(W, method="auto"):
     """W: device tensor [B, M, N] -> (Ut [B,R,M], s [B,R], Vt [B,R,N]), s descending.
 
-    method "svd": cuSOLVER SVD through torch.linalg (any W).
-    method "gram": eigh of the smaller Gram matrix, for well-conditioned W only
-    (cond^2 must stay far below 1/eps): much cheaper for large batches.
-    method "auto": "gram" when every matrix of the batch has cond(W)^2 <= 1e4
-    (the singular vectors then stay orthonormal to ~1e-12 and the numerical rank
-    is unambiguous), else "svd"; nearly square matrices go to "svd" directly.
-    method "jacobi": `block_jacobi_svd`, full-rank W only (opt-in; batched GEMMs and
-    small eigen-problems over the whole batch -- see DESIGN 11).
-    Setup is outside the EP hot path (the reference reports it separately as
-    svd_time, examples/figures/compute_benchmark.py:27)."""
+    method "jacobi" / "jacobi_direct": the hand-written set-up (`jacobi_thin_svd`, block Jacobi
+    and GEMMs on the FP64 tensor cores, whole batch per launch), through the Gram matrix of
+    the short side / on W itself.  Full-rank W.
+    method "auto" (default): "jacobi" when W is far from square (cond(W)^2 <= 1e4: the
+    singular vectors stay orthonormal to ~1e-12 and the numerical rank is unambiguous),
+    "jacobi_direct" when it is nearly square or the Gram route turns out ill-conditioned, and
+    the library SVD only for a rank-deficient W.
+    method "svd": cuSOLVER SVD through torch.linalg (any W; the round-1 baseline).
+    method "gram": torch.linalg.eigh of the smaller Gram matrix (the round-1 baseline of
+    the Gram route, kept for tools/bench_setup.py).
+    Setup is outside the EP sweep (the reference reports it separately as svd_time,
+    examples/figures/compute_benchmark.py:27) but inside its end-to-end time
+    (examples/figures/benchmark.py:22)."""
     t = ops.torch()
     B, M, N = W.shape
+    if M > N and method in ("auto", "jacobi", "jacobi_direct"):
+        Vt, s, Ut = thin_svd_device(W.transpose(1, 2).contiguous(), method)
+        return Ut, s, Vt
     if method == "auto":
         # a nearly square matrix with independent entries has cond ~ 1 / (1 - sqrt(aspect))
-        # (Marchenko-Pastur edge): beyond aspect 0.92 cond^2 exceeds 1e4 and the Gram attempt
-        # would only be paid for and thrown away
-        if min(M, N) > 0.92 * max(M, N):
-            return thin_svd_device(W, "svd")
-        Ut, s, Vt = thin_svd_device(W, "gram")
-        ok = t.isfinite(s).all() and bool(((s[:, -1] / s[:, 0])**2 >= 1e-4).all())
-        return (Ut, s, Vt) if ok else thin_svd_device(W, "svd")
+        # (Marchenko-Pastur edge): beyond aspect 0.92 cond^2 exceeds 1e4
+        if M <= 0.92 * N:
+            Ut, s, Vt = jacobi_thin_svd(W, "gram")
+            if t.isfinite(s).all() and bool(((s[:, -1] / s[:, 0])**2 >= 1e-4).all()):
+                return Ut, s, Vt
+        Ut, s, Vt = jacobi_thin_svd(W, "direct")
+        if t.isfinite(s).all() and bool((s[:, -1] >= 1e-10 * s[:, 0]).all()):
+            return Ut, s, Vt
+        return thin_svd_device(W, "svd")            # rank deficient: U = W V / s is undefined
+    if method in ("jacobi", "jacobi_direct"):
+        # bound the work matrices of a chunk of instances to a few GB
+        side = M if method == "jacobi" else N
+        chunk = max(1, int(2**32 // (8 * _ceil_to(M, 32) * _ceil_to(side, 64))))
+        if B > chunk:
+            parts = [thin_svd_device(W[b0:b0 + chunk], method) for b0 in range(0, B, chunk)]
+            return tuple(t.cat([p[k] for p in parts]) for k in range(3))
+        return jacobi_thin_svd(W, "gram" if method == "jacobi" else "direct")
     if method == "svd":
         U, s, Vh = t.linalg.svd(W, full_matrices=False)
         return U.transpose(1, 2).contiguous(), s.contiguous(), Vh.contiguous()
-    if method == "jacobi":
-        # a round gathers and rewrites every row of every instance: bound the temporaries
-        # (three copies of the chunk) to a few GB
-        chunk = max(1, int(2**32 // (8 * M * N)))
-        if B > chunk:
-            parts = [thin_svd_device(W[b0:b0 + chunk], "jacobi") for b0 in range(0, B, chunk)]
-            return tuple(t.cat([p[k] for p in parts]) for k in range(3))
-        if M <= N:
-            return block_jacobi_svd(W)
-        Vt, sv, Ut = block_jacobi_svd(W.transpose(1, 2).contiguous())
-        return Ut, sv, Vt
     if method != "gram":
         raise ValueError(f"unknown svd method {method!r}")
     if M <= N:
@@ -162,7 +183,8 @@ class LinearChannel(Channel):
       only one implemented (the reference's `False` branch solves a dense
       system per call and is not on the benchmarked path)
     - name: str, name of weight matrix W for display
-    - svd_method: "svd" | "gram" | "auto" | "jacobi" (extension, see thin_svd_device)
+    - svd_method: "auto" | "jacobi" | "jacobi_direct" | "svd" | "gram" (extension, see
+      thin_svd_device; "auto" = the hand-written block-Jacobi set-up)
     """
 
     def __init__(self, W, precompute_svd=True, name="W", svd_method="auto", keep_W=True):

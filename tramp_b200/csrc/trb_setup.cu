@@ -1,0 +1,484 @@
+// LinearChannel set-up: batched symmetric eigen-decomposition / thin SVD by one-sided
+// BLOCK JACOBI (Hestenes) on FP64 tensor cores (DMMA, mma.sync m8n8k4 f64).
+//
+// reference: channels/linear/linear_channel.py:8-15 (`svd`: np.linalg.svd, LAPACK gesdd)
+// and :36-46 (`matrix_rank`, `spectrum`, `singular`); examples/figures/benchmark.py:22
+// counts this factorisation in EP's total time.
+//
+// What is factorised.  `A[B, np, ld]` holds np VECTORS of length <= ld per instance, one
+// per row.  Two uses (tramp_b200/channels/linear_channel.py):
+//   * A = G = W W^T (or W^T W, whichever is smaller; rows of a symmetric matrix): the
+//     rotated rows converge to lambda_i u_i^T, i.e. row norms are the eigenvalues of G
+//     (= squared singular values of W) and the normalised rows the singular vectors of
+//     the short side; the other side follows by one DMMA GEMM (trb_gemm.cu).
+//   * A = W (rows of the short side): the rotated rows converge to s_i v_i^T directly
+//     (no squaring of the condition number).
+// Both are the same iteration:  A <- Q^T A  with Q orthogonal, until the rows are
+// mutually orthogonal.
+//
+// One ROUND of a sweep treats np/32 disjoint pairs of 16-row blocks (round-robin
+// tournament, every pair of blocks meets once per sweep) with three launches over the
+// WHOLE batch:
+//   k_jacobi_gram   S = X X^T of the 32 rows X of a pair          (DMMA, 1-D TMA ring)
+//   k_jacobi_eig    S = J diag J^T, cyclic Jacobi in shared memory (FP64 ALU, latency)
+//   k_jacobi_rotate X <- J^T X in place                            (DMMA, 1-D TMA ring)
+// Both GEMM-shaped kernels read the pair's rows through a ring of shared-memory stages
+// filled by cp.async.bulk (mbarrier complete_tx), so the DMMA warps never wait on a
+// global load; the rows of a pair cross HBM twice in and once out per round:
+// arithmetic intensity 16/4 = 4 flop/B for the rotation (HBM-bound on B200 unless the
+// instance stays in L2) and (10/16)*4 for the Gram (upper-triangular tiles only).
+#include "trb_common.cuh"
+
+using namespace trb;
+
+namespace {
+
+constexpr int kBS = 16;                 // rows per block
+constexpr int kPV = 2 * kBS;            // rows per pair
+constexpr int kStagePos = 64;           // positions (columns) per ring stage
+constexpr int kMmaWarps = 4;            // each owns 16 positions of a stage
+constexpr int kSetupThreads = (kMmaWarps + 1) * 32;
+constexpr int kRingStages = 4;
+// Row strides of a stage in doubles.  The padding makes every LDS.128 of a fragment
+// conflict-free: the Gram reads 2 adjacent rows x 4 adjacent 32-byte columns per quarter
+// warp (row stride = 16 B mod 128), the rotation 4 adjacent rows x 2 adjacent 16-byte
+// columns (row stride = 32 B mod 128).
+constexpr int kGramStride = kStagePos + 2;
+constexpr int kRotStride = kStagePos + 4;
+
+// D(8x8) += A(8x4, row) * B(4x8, col).  lane = 4*g + t:
+//   a = A[g][t], b = B[t][g], {c0, c1} = C[g][2t], C[g][2t+1]
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+  asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+      : "+d"(c0), "+d"(c1)
+      : "d"(a), "d"(b));
+}
+
+// Round-robin tournament of nb (even) players: in round r (0 <= r < nb-1) pair k
+// (0 <= k < nb/2) is (nb-1, r) for k = 0 and (r+k, r-k) mod (nb-1) otherwise.
+__host__ __device__ __forceinline__ void rr_pair(int nb, int round, int k, int& p, int& q) {
+  const int m = nb - 1;
+  if (k == 0) {
+    p = m;
+    q = round % m;
+  } else {
+    p = (round + k) % m;
+    q = (round - k + m) % m;
+  }
+}
+
+// global row of local row v (0..31) of the pair (p, q)
+__device__ __forceinline__ int pair_row(int p, int q, int v) {
+  return (v < kBS) ? p * kBS + v : q * kBS + (v - kBS);
+}
+
+__device__ __forceinline__ void mma_bar() {
+  asm volatile("bar.sync 1, %0;" ::"n"(kMmaWarps * 32) : "memory");
+}
+
+// Producer warp: streams positions [c0, c1) of the 32 rows of the pair into the ring,
+// one 512-byte bulk copy per row and stage (lane r copies row r).
+template <int STRIDE>
+__device__ __forceinline__ void produce_pair(const double* Ab, int ld, int p, int q, int c0, int c1,
+                                             double* ring, uint64_t* full_bar, uint64_t* empty_bar) {
+  const int lane = threadIdx.x & 31;
+  const double* src = Ab + (size_t)pair_row(p, q, lane) * ld;
+  int stage = 0;
+  uint32_t phase = 0;
+  for (int c = c0; c < c1; c += kStagePos) {
+    if (lane == 0) {
+      mbar_wait(&empty_bar[stage], phase ^ 1u);
+      mbar_arrive_expect_tx(&full_bar[stage], kPV * kStagePos * 8u);
+    }
+    __syncwarp();
+    bulk_g2s(ring + ((size_t)stage * kPV + lane) * STRIDE, src + c, kStagePos * 8u, &full_bar[stage]);
+    if (++stage == kRingStages) {
+      stage = 0;
+      phase ^= 1u;
+    }
+  }
+}
+
+__device__ __forceinline__ void ring_init(uint64_t* full_bar, uint64_t* empty_bar) {
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kRingStages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], kMmaWarps);
+    }
+    fence_mbar_init();
+  }
+  __syncthreads();
+}
+
+// ------------------------------------------------------------------ Gram of a pair
+// grid (pairs, B, zsplit).  S[b, pair, z] (32 x 32, row-major, both triangles) = X X^T over
+// the positions of chunk z.
+__global__ void __launch_bounds__(kSetupThreads, 3)
+k_jacobi_gram(const double* __restrict__ A, int64_t strideA, int ld, int nb, int round, int chunk,
+              double* __restrict__ S) {
+  extern __shared__ __align__(128) double ring[];  // kRingStages * 32 * kGramStride; reused for the reduction
+  __shared__ __align__(8) uint64_t full_bar[kRingStages];
+  __shared__ __align__(8) uint64_t empty_bar[kRingStages];
+  ring_init(full_bar, empty_bar);
+
+  int p, q;
+  rr_pair(nb, round, blockIdx.x, p, q);
+  const int b = blockIdx.y;
+  const int c0 = blockIdx.z * chunk;
+  const int c1 = min(ld, c0 + chunk);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const double* Ab = A + (size_t)b * strideA;
+
+  if (warp == kMmaWarps) {
+    produce_pair<kGramStride>(Ab, ld, p, q, c0, c1, ring, full_bar, empty_bar);
+    return;
+  }
+  const int g = lane >> 2, t = lane & 3;
+  // upper-triangular 8x8 tiles (I <= J): 10 accumulator pairs
+  double acc[10][2];
+#pragma unroll
+  for (int k = 0; k < 10; ++k) acc[k][0] = acc[k][1] = 0.0;
+  int stage = 0;
+  uint32_t phase = 0;
+  for (int c = c0; c < c1; c += kStagePos) {
+    mbar_wait(&full_bar[stage], phase);
+    const double* st = ring + (size_t)stage * kPV * kGramStride + 16 * warp + 4 * t;
+    double x[4][4];
+#pragma unroll
+    for (int I = 0; I < 4; ++I) {
+      const double2 lo = *reinterpret_cast<const double2*>(st + (8 * I + g) * kGramStride);
+      const double2 hi = *reinterpret_cast<const double2*>(st + (8 * I + g) * kGramStride + 2);
+      x[I][0] = lo.x, x[I][1] = lo.y, x[I][2] = hi.x, x[I][3] = hi.y;
+    }
+    // the same register is the A fragment of its row tile and the B fragment of its
+    // column tile (X X^T); the 4 k-steps walk the thread's 4 consecutive positions
+#pragma unroll
+    for (int s = 0; s < 4; ++s) {
+      int k = 0;
+#pragma unroll
+      for (int I = 0; I < 4; ++I)
+#pragma unroll
+        for (int J = I; J < 4; ++J, ++k) dmma884(acc[k][0], acc[k][1], x[I][s], x[J][s]);
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty_bar[stage]);
+    if (++stage == kRingStages) {
+      stage = 0;
+      phase ^= 1u;
+    }
+  }
+  // ---- sum the 4 warps' partial tiles (the ring is drained: every stage was consumed)
+  mma_bar();
+  double* red = ring;  // [4][32][33]
+  {
+    int k = 0;
+#pragma unroll
+    for (int I = 0; I < 4; ++I)
+#pragma unroll
+      for (int J = I; J < 4; ++J, ++k) {
+        double* d = red + ((size_t)warp * kPV + 8 * I + g) * 33 + 8 * J + 2 * t;
+        d[0] = acc[k][0];
+        d[1] = acc[k][1];
+      }
+  }
+  mma_bar();
+  const int npairs = nb / 2;
+  double* out = S + (((size_t)b * npairs + blockIdx.x) * gridDim.z + blockIdx.z) * (kPV * kPV);
+  for (int e = tid; e < kPV * kPV; e += kMmaWarps * 32) {
+    int i = e >> 5, j = e & 31;
+    if ((i >> 3) > (j >> 3)) {  // lower tile: mirror
+      const int tmp = i;
+      i = j, j = tmp;
+    }
+    double v = 0.0;
+#pragma unroll
+    for (int w = 0; w < kMmaWarps; ++w) v += red[((size_t)w * kPV + i) * 33 + j];
+    out[e] = v;
+  }
+}
+
+// --------------------------------------------------- eigenvectors of a pair's Gram
+// grid (pairs, B), 256 threads.  Cyclic two-sided Jacobi on the 32 x 32 matrix in shared
+// memory with the round-robin parallel ordering: in a step the 16 disjoint index pairs
+// are rotated at once, thread (k, m) updating the 2 x 2 block (rows of pair k, columns of
+// pair m) of S and two rows of J.  Rotations are the small-angle ones (|tan| <= 1), so J
+// stays close to the identity once S is nearly diagonal and the outer sweeps converge
+// quadratically.  Also records the largest cosine between two rows of the pair BEFORE
+// the rotation (the sweep's convergence measure) and a skip flag.
+__device__ __forceinline__ unsigned long long as_ull(double v) {
+  return (unsigned long long)__double_as_longlong(v);
+}
+
+__global__ void __launch_bounds__(256)
+k_jacobi_eig(const double* __restrict__ S, int zsplit, double* __restrict__ Jm, int* __restrict__ rot_flag,
+             unsigned long long* __restrict__ offmax, double skip_tol, int max_inner) {
+  __shared__ double sS[kPV][kPV + 1];
+  __shared__ double sJ[kPV][kPV + 1];
+  __shared__ double sc[kBS], ss[kBS];
+  __shared__ double sred[8];
+  const int tid = threadIdx.x;
+  const int pair = blockIdx.x, b = blockIdx.y, npairs = gridDim.x;
+  const double* in = S + ((size_t)b * npairs + pair) * zsplit * (kPV * kPV);
+  for (int e = tid; e < kPV * kPV; e += 256) {
+    double v = 0.0;
+    for (int z = 0; z < zsplit; ++z) v += in[(size_t)z * (kPV * kPV) + e];
+    sS[e >> 5][e & 31] = v;
+    sJ[e >> 5][e & 31] = ((e >> 5) == (e & 31)) ? 1.0 : 0.0;
+  }
+  __syncthreads();
+  // largest |cos| between two rows
+  double off = 0.0;
+  for (int e = tid; e < kPV * kPV; e += 256) {
+    const int i = e >> 5, j = e & 31;
+    if (i < j) {
+      const double d = sS[i][i] * sS[j][j];
+      if (d > 0.0) off = fmax(off, fabs(sS[i][j]) * rsqrt(d));
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) off = fmax(off, __shfl_xor_sync(0xffffffffu, off, o));
+  if ((tid & 31) == 0) sred[tid >> 5] = off;
+  __syncthreads();
+  off = sred[0];
+#pragma unroll
+  for (int w = 1; w < 8; ++w) off = fmax(off, sred[w]);
+  if (tid == 0) {
+    atomicMax(offmax + b, as_ull(off));  // non-negative doubles order like their bit patterns
+    rot_flag[(size_t)b * npairs + pair] = (off > skip_tol) ? 1 : 0;
+  }
+  if (!(off > skip_tol)) return;
+
+  const int k = tid >> 4, m = tid & 15;
+  for (int sweep = 0; sweep < max_inner; ++sweep) {
+    int rotated = 0;
+    for (int step = 0; step < kPV - 1; ++step) {
+      int pk, qk, pm, qm;
+      rr_pair(kPV, step, k, pk, qk);
+      rr_pair(kPV, step, m, pm, qm);
+      if (tid < kBS) {
+        int p, q;
+        rr_pair(kPV, step, tid, p, q);
+        const double app = sS[p][p], aqq = sS[q][q], apq = sS[p][q];
+        double c = 1.0, s = 0.0;
+        if (fabs(apq) > 1.1e-16 * sqrt(fabs(app * aqq)) && apq != 0.0) {
+          const double tau = (aqq - app) / (2.0 * apq);
+          const double tt = copysign(1.0, tau) / (fabs(tau) + sqrt(1.0 + tau * tau));
+          c = 1.0 / sqrt(1.0 + tt * tt);
+          s = tt * c;
+          rotated = 1;
+        }
+        sc[tid] = c;
+        ss[tid] = s;
+      }
+      __syncthreads();
+      const double ck = sc[k], sk = ss[k], cm = sc[m], sm = ss[m];
+      // S' = R_k^T S R_m on the 2x2 block, R = [[c, s], [-s, c]]
+      const double a00 = sS[pk][pm], a01 = sS[pk][qm], a10 = sS[qk][pm], a11 = sS[qk][qm];
+      const double t00 = ck * a00 - sk * a10, t01 = ck * a01 - sk * a11;
+      const double t10 = sk * a00 + ck * a10, t11 = sk * a01 + ck * a11;
+      double n00 = cm * t00 - sm * t01, n01 = sm * t00 + cm * t01;
+      double n10 = cm * t10 - sm * t11, n11 = sm * t10 + cm * t11;
+      if (k == m && (ck != 1.0 || sk != 0.0)) n01 = n10 = 0.0;  // annihilated by construction
+      // J' = J R_m on rows 2k, 2k+1
+      const double j00 = sJ[2 * k][pm], j01 = sJ[2 * k][qm], j10 = sJ[2 * k + 1][pm], j11 = sJ[2 * k + 1][qm];
+      sS[pk][pm] = n00, sS[pk][qm] = n01, sS[qk][pm] = n10, sS[qk][qm] = n11;
+      sJ[2 * k][pm] = cm * j00 - sm * j01, sJ[2 * k][qm] = sm * j00 + cm * j01;
+      sJ[2 * k + 1][pm] = cm * j10 - sm * j11, sJ[2 * k + 1][qm] = sm * j10 + cm * j11;
+      __syncthreads();
+    }
+    if (!__syncthreads_or(rotated)) break;
+  }
+  double* out = Jm + ((size_t)b * npairs + pair) * (kPV * kPV);
+  for (int e = tid; e < kPV * kPV; e += 256) out[e] = sJ[e >> 5][e & 31];
+}
+
+// --------------------------------------------------------------- rotation of a pair
+// grid (pairs, B, zsplit).  X <- J^T X in place over the positions of chunk z.
+__global__ void __launch_bounds__(kSetupThreads, 2)
+k_jacobi_rotate(double* __restrict__ A, int64_t strideA, int ld, int nb, int round, int chunk,
+                const double* __restrict__ Jm, const int* __restrict__ rot_flag) {
+  extern __shared__ __align__(128) double ring[];  // kRingStages * 32 * kRotStride
+  __shared__ __align__(8) uint64_t full_bar[kRingStages];
+  __shared__ __align__(8) uint64_t empty_bar[kRingStages];
+  const int npairs = nb / 2;
+  const int b = blockIdx.y;
+  if (!rot_flag[(size_t)b * npairs + blockIdx.x]) return;  // rows already orthogonal
+  ring_init(full_bar, empty_bar);
+
+  int p, q;
+  rr_pair(nb, round, blockIdx.x, p, q);
+  const int c0 = blockIdx.z * chunk;
+  const int c1 = min(ld, c0 + chunk);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  double* Ab = A + (size_t)b * strideA;
+
+  if (warp == kMmaWarps) {
+    produce_pair<kRotStride>(Ab, ld, p, q, c0, c1, ring, full_bar, empty_bar);
+    return;
+  }
+  const int g = lane >> 2, t = lane & 3;
+  // A fragments of J^T: tile (I, K) element [g][t] = J[4K + t][8I + g]
+  const double* Jp = Jm + ((size_t)b * npairs + blockIdx.x) * (kPV * kPV);
+  double af[4][8];
+#pragma unroll
+  for (int I = 0; I < 4; ++I)
+#pragma unroll
+    for (int K = 0; K < 8; ++K) af[I][K] = __ldg(Jp + (4 * K + t) * kPV + 8 * I + g);
+  double* orow[4];
+#pragma unroll
+  for (int I = 0; I < 4; ++I) orow[I] = Ab + (size_t)pair_row(p, q, 8 * I + g) * ld + 16 * warp + 4 * t;
+
+  int stage = 0;
+  uint32_t phase = 0;
+  for (int c = c0; c < c1; c += kStagePos) {
+    mbar_wait(&full_bar[stage], phase);
+    const double* st = ring + (size_t)stage * kPV * kRotStride + 16 * warp + 2 * g;
+    double2 bf[8];
+#pragma unroll
+    for (int K = 0; K < 8; ++K) bf[K] = *reinterpret_cast<const double2*>(st + (4 * K + t) * kRotStride);
+    double acc[4][2][2];
+#pragma unroll
+    for (int I = 0; I < 4; ++I) acc[I][0][0] = acc[I][0][1] = acc[I][1][0] = acc[I][1][1] = 0.0;
+#pragma unroll
+    for (int K = 0; K < 8; ++K)
+#pragma unroll
+      for (int I = 0; I < 4; ++I) {
+        dmma884(acc[I][0][0], acc[I][0][1], af[I][K], bf[K].x);
+        dmma884(acc[I][1][0], acc[I][1][1], af[I][K], bf[K].y);
+      }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty_bar[stage]);
+    // n-tile e holds positions 2n + e of the warp's 16: the thread's two tiles cover 4
+    // consecutive positions {c0e0, c0e1, c1e0, c1e1}
+#pragma unroll
+    for (int I = 0; I < 4; ++I) {
+      double2* o = reinterpret_cast<double2*>(orow[I] + c);
+      o[0] = make_double2(acc[I][0][0], acc[I][1][0]);
+      o[1] = make_double2(acc[I][0][1], acc[I][1][1]);
+    }
+    if (++stage == kRingStages) {
+      stage = 0;
+      phase ^= 1u;
+    }
+  }
+}
+
+// ------------------------------------------------------------------ finishing ops
+// norms[b, i] = || A[b, i, :n] ||, one warp per row
+__global__ void __launch_bounds__(256)
+k_row_norms(const double* __restrict__ A, int64_t strideA, int rows, int n, int ld, double* __restrict__ norms) {
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5), b = blockIdx.y, lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const double* a = A + (size_t)b * strideA + (size_t)row * ld;
+  double s = 0.0;
+  for (int j = 2 * lane; j < n; j += 64) {
+    const double2 v = *reinterpret_cast<const double2*>(a + j);
+    s = fma(v.x, v.x, s);
+    if (j + 1 < n) s = fma(v.y, v.y, s);
+  }
+  s = warp_sum(s);
+  if (lane == 0) norms[(size_t)b * rows + row] = sqrt(s);
+}
+
+// dst[b, i, :n] = scale[b, i] * src[b, perm[b, i], :n]; columns n..ld_dst-1 are zeroed
+__global__ void __launch_bounds__(256)
+k_rows_gather_scale(const double* __restrict__ src, int64_t stride_src, int ld_src, const long long* __restrict__ perm,
+                    const double* __restrict__ scale, int R, int n, double* __restrict__ dst, int64_t stride_dst,
+                    int ld_dst) {
+  const int i = blockIdx.x, b = blockIdx.y;
+  const long long r = perm ? perm[(size_t)b * R + i] : i;
+  const double sc = scale ? scale[(size_t)b * R + i] : 1.0;
+  const double* s = src + (size_t)b * stride_src + (size_t)r * ld_src;
+  double* d = dst + (size_t)b * stride_dst + (size_t)i * ld_dst;
+  for (int j = threadIdx.x; j < ld_dst; j += blockDim.x) d[j] = (j < n) ? sc * s[j] : 0.0;
+}
+
+bool g_setup_attr_done = false;
+
+int setup_attrs() {
+  if (g_setup_attr_done) return TRB_OK;
+  cudaError_t e = cudaFuncSetAttribute(k_jacobi_gram, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       kRingStages * kPV * kGramStride * 8);
+  if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(k_jacobi_rotate, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             kRingStages * kPV * kRotStride * 8);
+  if (e != cudaSuccess) return trb_set_error(TRB_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+  g_setup_attr_done = true;
+  return TRB_OK;
+}
+
+}  // namespace
+
+extern "C" int trb_jacobi_zsplit(int B, int np, int ld) {
+  // enough CTAs for ~8 waves of 3 CTAs per SM, at least 4 stages per CTA
+  const int npairs = np / kPV;
+  const long long want = 8LL * 3 * trb_sm_count_cached();
+  long long z = (want + (long long)npairs * B - 1) / ((long long)npairs * B);
+  const int zmax = (ld / kStagePos) / 4;
+  if (z > zmax) z = zmax;
+  if (z > 8) z = 8;
+  if (z < 1) z = 1;
+  return (int)z;
+}
+
+extern "C" int trb_jacobi_sweep(double* A, int64_t strideA, int B, int np, int ld, double* Swork, double* Jwork,
+                                int* rot_flag, double* offmax, double skip_tol, int max_inner, void* stream) {
+  TRB_CHECK_ARG(A && Swork && Jwork && rot_flag && offmax, "null pointer");
+  TRB_CHECK_ARG(B > 0 && np >= kPV && np % kPV == 0, "np must be a positive multiple of 32");
+  TRB_CHECK_ARG(ld >= kStagePos && ld % kStagePos == 0, "ld must be a positive multiple of 64");
+  TRB_CHECK_ARG(strideA >= (int64_t)np * ld && (strideA % 2) == 0, "strideA too small");
+  TRB_CHECK_ARG(((uintptr_t)A % 16) == 0, "A must be 16-byte aligned");
+  TRB_CHECK_ARG(B <= 65535, "B > 65535");
+  int rc = setup_attrs();
+  if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int nb = np / kBS, npairs = nb / 2;
+  // Swork holds up to trb_jacobi_zsplit() partial Grams per pair
+  const int chunk = ((ld / kStagePos + trb_jacobi_zsplit(B, np, ld) - 1) / trb_jacobi_zsplit(B, np, ld)) * kStagePos;
+  const int zsplit = (ld + chunk - 1) / chunk;
+  const dim3 grid(npairs, B, zsplit);
+  cudaMemsetAsync(offmax, 0, sizeof(double) * B, st);
+  for (int round = 0; round < nb - 1; ++round) {
+    {
+      trb_launch_scope scope_(0, st);
+      k_jacobi_gram<<<grid, kSetupThreads, kRingStages * kPV * kGramStride * 8, st>>>(A, strideA, ld, nb, round, chunk,
+                                                                                     Swork);
+    }
+    {
+      trb_launch_scope scope_(0, st);
+      k_jacobi_eig<<<dim3(npairs, B), 256, 0, st>>>(Swork, zsplit, Jwork, rot_flag,
+                                                     reinterpret_cast<unsigned long long*>(offmax), skip_tol, max_inner);
+    }
+    {
+      trb_launch_scope scope_(0, st);
+      k_jacobi_rotate<<<grid, kSetupThreads, kRingStages * kPV * kRotStride * 8, st>>>(A, strideA, ld, nb, round, chunk,
+                                                                                      Jwork, rot_flag);
+    }
+  }
+  TRB_CHECK_LAUNCH();
+  return TRB_OK;
+}
+
+extern "C" int trb_row_norms(const double* A, int64_t strideA, int B, int rows, int n, int ld, double* norms,
+                             void* stream) {
+  TRB_CHECK_ARG(A && norms, "null pointer");
+  TRB_CHECK_ARG(B > 0 && B <= 65535 && rows > 0 && n > 0 && ld >= n && (ld % 2) == 0, "bad shape");
+  TRB_CHECK_ARG(((uintptr_t)A % 16) == 0 && (strideA % 2) == 0, "A must be 16-byte aligned");
+  cudaStream_t st = (cudaStream_t)stream;
+  trb_launch_scope scope_(0, st);
+  k_row_norms<<<dim3((rows + 7) / 8, B), 256, 0, st>>>(A, strideA, rows, n, ld, norms);
+  TRB_CHECK_LAUNCH();
+  return TRB_OK;
+}
+
+extern "C" int trb_rows_gather_scale(const double* src, int64_t stride_src, int ld_src, const long long* perm,
+                                     const double* scale, int B, int R, int n, double* dst, int64_t stride_dst,
+                                     int ld_dst, void* stream) {
+  TRB_CHECK_ARG(src && dst, "null pointer");
+  TRB_CHECK_ARG(B > 0 && B <= 65535 && R > 0 && n > 0 && ld_src >= n && ld_dst >= n, "bad shape");
+  cudaStream_t st = (cudaStream_t)stream;
+  trb_launch_scope scope_(0, st);
+  k_rows_gather_scale<<<dim3(R, B), 256, 0, st>>>(src, stride_src, ld_src, perm, scale, R, n, dst, stride_dst, ld_dst);
+  TRB_CHECK_LAUNCH();
+  return TRB_OK;
+}

@@ -209,6 +209,64 @@ def lin_rescale(direction, B, R, Nz, Nx, rank, s, s2, az, ax, tz, tx, active=Non
 
 
 # ---------------------------------------------------------------------------
+# LinearChannel set-up: block-Jacobi orthogonalisation of rows (trb_setup.cu)
+# ---------------------------------------------------------------------------
+JACOBI_ROWS = 32    # rows of a block pair: the row count of the work matrix is a multiple of it
+JACOBI_COLS = 64    # positions per ring stage: the leading dimension is a multiple of it
+
+
+def jacobi_workspace(B, n_rows, ld, dev):
+    """Scratch of trb_jacobi_sweep: partial Grams, rotations, rotate flags, convergence measure."""
+    t = torch()
+    lib = _lib.load()
+    pairs = n_rows // JACOBI_ROWS
+    z = lib.trb_jacobi_zsplit(B, n_rows, ld)
+    return dict(S=t.empty((B, pairs, z, JACOBI_ROWS * JACOBI_ROWS), dtype=t.float64, device=dev),
+                J=t.empty((B, pairs, JACOBI_ROWS * JACOBI_ROWS), dtype=t.float64, device=dev),
+                flag=t.zeros((B, pairs), dtype=t.int32, device=dev),
+                off=t.zeros(B, dtype=t.float64, device=dev))
+
+
+def jacobi_sweep(A, work, skip_tol, max_inner=2):
+    """One sweep (every pair of 16-row blocks once) of A[b] <- Q^T A[b], in place.
+    Returns the device tensor [B] of the largest |cos| between two rows seen BEFORE their
+    rotation in this sweep."""
+    lib = _lib.load()
+    B, n_rows, ld = A.shape
+    check(lib.trb_jacobi_sweep(ptr(A), A.stride(0), B, n_rows, ld, ptr(work["S"]), ptr(work["J"]),
+                               ptr(work["flag"]), ptr(work["off"]), float(skip_tol), int(max_inner),
+                               current_stream()))
+    return work["off"]
+
+
+def row_norms(A, n):
+    """A [B, rows, ld] -> euclidean norms of A[b, i, :n], [B, rows]."""
+    t = torch()
+    B, rows, ld = A.shape
+    out = t.empty((B, rows), dtype=t.float64, device=A.device)
+    check(_lib.load().trb_row_norms(ptr(A), A.stride(0), B, rows, n, ld, ptr(out), current_stream()))
+    return out
+
+
+def rows_gather_scale(src, n, perm=None, scale=None, R=None, ld_dst=None, out=None):
+    """out[b, i, :n] = scale[b, i] * src[b, perm[b, i], :n] (perm / scale optional), zero padded
+    to ld_dst columns.  `out` may be `src` itself when perm is None (in-place row scaling)."""
+    t = torch()
+    B, rows, ld_src = src.shape
+    R = int(R if R is not None else (perm.shape[1] if perm is not None else rows))
+    ld_dst = int(ld_dst or n)
+    if out is None:
+        out = t.empty((B, R, ld_dst), dtype=t.float64, device=src.device)
+    if perm is not None:
+        perm = perm.to(t.int64).contiguous()
+    if scale is not None:
+        scale = scale.contiguous()
+    check(_lib.load().trb_rows_gather_scale(ptr(src), src.stride(0), ld_src, ptr(perm), ptr(scale), B, R, n,
+                                            ptr(out), out.stride(0), out.shape[-1], current_stream()))
+    return out
+
+
+# ---------------------------------------------------------------------------
 # natural parameters of the separable factors (host scalars, numpy)
 # ---------------------------------------------------------------------------
 def gauss_bernoulli_factor(rho, mean, var, amin=AMIN, amax=AMAX):
