@@ -88,7 +88,8 @@ int trb_device_sm_count(void);
  * counters (and, if enable_events, brackets every GEMV launch with CUDA events
  * on its stream); trb_profile_launches(kind) = kernels launched since then
  * (kind 0 elementwise/update, 1 operator pass = GEMV or shared-operator GEMM,
- * -1 all); trb_profile_gemv_ms sums the event-timed operator-pass durations and
+ * 2 LinearChannel set-up kernels (trb_jacobi_sweep, ...), -1 = 0 and 1 together: the EP
+ * sweep); trb_profile_gemv_ms sums the event-timed operator-pass durations and
  * returns how many launches were timed. */
 void trb_profile_reset(int enable_events);
 long long trb_profile_launches(int kind);
@@ -98,7 +99,9 @@ int trb_profile_gemv_ms(double* total_ms);
  * a_mode: 0 = one precision per instance a[B] (isotropic beliefs), 1 = one per
  * element a[B, ld] (isotropic=False in the reference's unit tests).
  * v_mode: 0 = v[B] is the per-instance MEAN of the elementwise variance
- * (`vx.mean()`), 1 = v[B, ld] elementwise.  y is NULL for priors. */
+ * (`vx.mean()`), 1 = v[B, ld] elementwise, 2 (TRB_GAUSS_BERNOULLI_PRIOR only) =
+ * v[B, ld] receives the weight of the Gaussian component instead,
+ * expit(normal.A(a, b) - eta) (beliefs/sparse.py:9-12 `p`).  y is NULL for priors. */
 
 /* compute_forward_posterior / compute_backward_posterior of the factor kinds */
 int trb_factor_posterior(const trb_factor* f, int B, int n, int ld,

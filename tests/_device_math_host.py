@@ -40,6 +40,9 @@ void hm_factor(const trb_factor* f, long n, const double* a, long a_stride, cons
     logZ[i] = trb::factor_log_partition(*f, ai, b[i], yi);
   }
 }
+void hm_sparse_weight(const trb_factor* f, long n, const double* a, long a_stride, const double* b, double* p) {
+  for (long i = 0; i < n; ++i) p[i] = trb::sparse_weight(*f, a[i * a_stride], b[i]);
+}
 int hm_is_constant_message(int kind) { return trb::factor_is_constant_message(kind) ? 1 : 0; }
 }
 """
@@ -76,6 +79,7 @@ def load():
     dp = C.POINTER(C.c_double)
     lib.hm_truncated_normal.argtypes = [C.c_long, dp, dp, C.c_double, C.c_double, dp, dp, dp, dp]
     lib.hm_factor.argtypes = [C.c_void_p, C.c_long, dp, C.c_long, dp, dp, dp, dp, dp]
+    lib.hm_sparse_weight.argtypes = [C.c_void_p, C.c_long, dp, C.c_long, dp, dp]
     return lib
 
 
@@ -94,3 +98,14 @@ def factor_elementwise(f, a, b, y=None):
     r, v, A = (np.empty_like(b) for _ in range(3))
     load().hm_factor(C.addressof(f), b.size, _p(a.reshape(-1)), a_stride, _p(b), _p(y), _p(r), _p(v), _p(A))
     return r, v, A
+
+
+def sparse_weight(f, a, b):
+    """beliefs/sparse.py `p` elementwise through the device routine."""
+    import numpy as np
+    b = np.ascontiguousarray(b, dtype=float)
+    a = np.ascontiguousarray(a, dtype=float)
+    a_stride = 0 if a.size == 1 and b.size != 1 else 1
+    out = np.empty_like(b)
+    load().hm_sparse_weight(C.addressof(f), b.size, _p(a.reshape(-1)), a_stride, _p(b), _p(out))
+    return out

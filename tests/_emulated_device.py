@@ -305,7 +305,12 @@ def _factor_posterior(self, fref, B, n, ld, a, a_mode, b, y, r, v, v_mode, strea
     for i in range(B):
         ri, vi, _ = _moments(f, n, ld, a, a_mode, b, y, i)
         _arr(r, i * ld + n)[i * ld:] = ri
-        if v_mode:
+        if v_mode == 2:
+            from tests import _device_math_host as H
+            off = i * ld
+            a_i = _arr(a, off + n)[off:off + n] if a_mode else _arr(a, i + 1)[i:i + 1]
+            _arr(v, i * ld + n)[i * ld:] = H.sparse_weight(f, a_i, _arr(b, off + n)[off:off + n])
+        elif v_mode:
             _arr(v, i * ld + n)[i * ld:] = vi
         else:
             _arr(v, B)[i] = vi.sum() / n

@@ -136,6 +136,35 @@ def gen_truncated(out):
     out["pos_v"] = positive.v(a, bb)
 
 
+def gen_beliefs(out):
+    """Every function of tramp/beliefs/{sparse,binary,positive,truncated}.py on grids that
+    reach the small-weight regime of the sparse belief (p down to 1e-18)."""
+    a = np.array([0.5, 1.0, 3.0, 40.0])[:, None]
+    b = np.linspace(-9, 9, 73)[None, :]
+    out["bel_a"], out["bel_b"] = a, b
+    etas = np.array([-3.0, 0.4, 2.2, 8.0, 15.0, 22.0, 30.0, 40.0])
+    out["sparse_eta"] = etas
+    for k, eta in enumerate(etas):
+        for name in ("A", "p", "r", "v", "tau"):
+            out[f"sparse{k}_{name}"] = getattr(sparse, name)(a, b, eta)
+    bb = np.linspace(-45, 45, 181)
+    out["binary_b"] = bb
+    for name in ("A", "r", "v"):
+        out[f"binary_{name}"] = getattr(binary, name)(bb)
+    for name in ("A", "r", "v", "tau", "p"):
+        out[f"positive_{name}"] = getattr(positive, name)(a, b)
+    for i, (a_t, lo, hi) in enumerate(TRUNC_CASES):
+        bt = out_trunc_b()
+        out[f"trunc{i}_tau"] = truncated.tau(a_t, bt, lo, hi)
+        out[f"trunc{i}_p"] = truncated.p(a_t, bt, lo, hi)
+    out["trunc_b"] = out_trunc_b()
+    out["trunc_cases"] = np.array(TRUNC_CASES, dtype=float)
+
+
+def out_trunc_b():
+    return np.linspace(-6, 6, 121)
+
+
 # --------------------------------------------------------------------------
 # B. LinearChannel
 # --------------------------------------------------------------------------
@@ -375,6 +404,10 @@ def main():
     gen_elementwise(el)
     gen_truncated(el)
     np.savez_compressed(os.path.join(HERE, "elementwise.npz"), **el)
+    bel = {}
+    with np.errstate(all="ignore"):
+        gen_beliefs(bel)
+    np.savez_compressed(os.path.join(HERE, "beliefs.npz"), **bel)
     lin = {}
     gen_linear(lin)
     np.savez_compressed(os.path.join(HERE, "linear.npz"), **lin)
@@ -394,7 +427,7 @@ def main():
             run_adaptive(cfg, ad)
     ad["configs"] = np.array(json.dumps(ADAPTIVE))
     np.savez_compressed(os.path.join(HERE, "adaptive.npz"), **ad)
-    for f in ("elementwise.npz", "linear.npz", "sweeps.npz", "adaptive.npz"):
+    for f in ("elementwise.npz", "beliefs.npz", "linear.npz", "sweeps.npz", "adaptive.npz"):
         print(f, os.path.getsize(os.path.join(HERE, f)) // 1024, "KiB")
 
 

@@ -621,6 +621,7 @@ def test_persistent_sweep_matches_launch_per_stage_path(sw, idx):
             track = TrackErrors({"x": sw[name + "_x"]}, metrics=["mse", "sign_mse"])
             evo = TrackEvolution()
             init = _SeqInit(sw, name) if cfg.get("init") == "noisy" else None
+            ep.linear._setup()             # the factorisation's launches are not the sweep's
             lib.trb_profile_reset(0)
             ep.iterate(max_iter=cfg["n_iter"], callback=JoinCallback([track, evo]), initializer=init,
                        damping=cfg["damping"])

@@ -15,6 +15,8 @@ def elementwise(f, a, b, y, what):
     yv = flat[2] if y is not None else None
     if what == "A":
         out = ops.factor_log_partition(f, flat[0], flat[1], yv, n, True, True)
+    elif what == "p":
+        out = ops.factor_posterior(f, flat[0], flat[1], yv, n, True, 2)[1]
     else:
         r, v = ops.factor_posterior(f, flat[0], flat[1], yv, n, True, True)
         out = r if what == "r" else v

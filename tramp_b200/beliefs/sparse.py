@@ -23,9 +23,9 @@ def v(a, b, eta):
 
 
 def p(a, b, eta):
-    """s = expit(normal.A(a, b) - eta) (reference sparse.py:9-12) = exp(A_sparse... ) recovered
-    from the device log-partition: s = 1 - exp(eta - A(a, b, eta))."""
-    return 1.0 - np.exp(eta - A(a, b, eta))
+    """Weight of the Gaussian component, expit(normal.A(a, b) - eta) (reference sparse.py:9-12),
+    evaluated by the device moment routine (`sparse_weight`, trb_moments.cuh)."""
+    return _dev.elementwise(_F(eta), a, b, None, "p")
 
 
 def tau(a, b, eta):

@@ -35,7 +35,7 @@ int trb_sm_count_cached() {
 namespace {
 struct ProfileState {
   bool enabled = false;
-  long long launches[2] = {0, 0};
+  long long launches[3] = {0, 0, 0};  // update kernels, operator passes, set-up (trb_setup.cu)
   std::vector<cudaEvent_t> pool;         // recycled events
   std::vector<cudaEvent_t> begin[2], end[2];
 };
@@ -70,6 +70,7 @@ long long trb_profile_launch_count(int kind) { return g_prof.launches[kind]; }
 extern "C" void trb_profile_reset(int enable_events) {
   for (int k = 0; k < 2; ++k) {
     g_prof.launches[k] = 0;
+    g_prof.launches[2] = 0;
     for (auto e : g_prof.begin[k]) g_prof.pool.push_back(e);
     for (auto e : g_prof.end[k]) g_prof.pool.push_back(e);
     g_prof.begin[k].clear();
@@ -79,7 +80,7 @@ extern "C" void trb_profile_reset(int enable_events) {
 }
 
 extern "C" long long trb_profile_launches(int kind) {
-  return (kind == 0 || kind == 1) ? g_prof.launches[kind] : g_prof.launches[0] + g_prof.launches[1];
+  return (kind >= 0 && kind <= 2) ? g_prof.launches[kind] : g_prof.launches[0] + g_prof.launches[1];
 }
 
 // Sum of the CUDA-event durations of the GEMV launches recorded since the last
@@ -147,7 +148,8 @@ k_factor_posterior(trb_factor f, int n, int ld, const double* __restrict__ a, in
     const double yi = y ? y[off + i] : 0.0;
     const RV m = factor_moments(f, ai, b[off + i], yi);
     r[off + i] = m.r;
-    if (v_mode) v[off + i] = m.v;
+    if (v_mode == 2) v[off + i] = sparse_weight(f, ai, b[off + i]);
+    else if (v_mode) v[off + i] = m.v;
     vsum += m.v;
   }
   if (!v_mode) {
@@ -303,6 +305,8 @@ extern "C" int trb_factor_posterior(const trb_factor* f, int B, int n, int ld, c
   TRB_CHECK_ARG(B > 0 && n > 0 && ld >= n, "bad shape");
   TRB_CHECK_ARG(f->kind >= 0 && f->kind <= TRB_ABS_LIKELIHOOD, "unknown factor kind");
   TRB_CHECK_ARG(!needs_y(f->kind) || y, "likelihood needs y");
+  TRB_CHECK_ARG(v_mode >= 0 && v_mode <= 2, "v_mode must be 0, 1 or 2");
+  TRB_CHECK_ARG(v_mode != 2 || f->kind == TRB_GAUSS_BERNOULLI_PRIOR, "v_mode 2 (mixture weight) is for the sparse belief");
   trb_launch_scope scope_(0, (cudaStream_t)stream);
   k_factor_posterior<<<B, kEwThreads, 0, (cudaStream_t)stream>>>(*f, n, ld, a, a_mode, b, y, r, v,
                                                                   v_mode);

@@ -199,6 +199,12 @@ __device__ __forceinline__ RV factor_moments(const trb_factor& f, double a, doub
   return o;
 }
 
+// beliefs/sparse.py:9-12: weight of the Gaussian component, expit(normal.A(a, b) - eta)
+__device__ __forceinline__ double sparse_weight(const trb_factor& f, double a, double b) {
+  const double aa = a + f.p0, bb = b + f.p1;
+  return expit(normal_A(aa, bb) - f.p2);
+}
+
 // scalar_log_partition, elementwise (the reference's compute_log_partition is
 // its mean over components)
 __device__ __forceinline__ double factor_log_partition(const trb_factor& f, double a, double b,

@@ -440,17 +440,17 @@ extern "C" int trb_jacobi_sweep(double* A, int64_t strideA, int B, int np, int l
   cudaMemsetAsync(offmax, 0, sizeof(double) * B, st);
   for (int round = 0; round < nb - 1; ++round) {
     {
-      trb_launch_scope scope_(0, st);
+      trb_launch_scope scope_(2, st);
       k_jacobi_gram<<<grid, kSetupThreads, kRingStages * kPV * kGramStride * 8, st>>>(A, strideA, ld, nb, round, chunk,
                                                                                      Swork);
     }
     {
-      trb_launch_scope scope_(0, st);
+      trb_launch_scope scope_(2, st);
       k_jacobi_eig<<<dim3(npairs, B), 256, 0, st>>>(Swork, zsplit, Jwork, rot_flag,
                                                      reinterpret_cast<unsigned long long*>(offmax), skip_tol, max_inner);
     }
     {
-      trb_launch_scope scope_(0, st);
+      trb_launch_scope scope_(2, st);
       k_jacobi_rotate<<<grid, kSetupThreads, kRingStages * kPV * kRotStride * 8, st>>>(A, strideA, ld, nb, round, chunk,
                                                                                       Jwork, rot_flag);
     }
@@ -465,7 +465,7 @@ extern "C" int trb_row_norms(const double* A, int64_t strideA, int B, int rows, 
   TRB_CHECK_ARG(B > 0 && B <= 65535 && rows > 0 && n > 0 && ld >= n && (ld % 2) == 0, "bad shape");
   TRB_CHECK_ARG(((uintptr_t)A % 16) == 0 && (strideA % 2) == 0, "A must be 16-byte aligned");
   cudaStream_t st = (cudaStream_t)stream;
-  trb_launch_scope scope_(0, st);
+  trb_launch_scope scope_(2, st);
   k_row_norms<<<dim3((rows + 7) / 8, B), 256, 0, st>>>(A, strideA, rows, n, ld, norms);
   TRB_CHECK_LAUNCH();
   return TRB_OK;
@@ -477,7 +477,7 @@ extern "C" int trb_rows_gather_scale(const double* src, int64_t stride_src, int 
   TRB_CHECK_ARG(src && dst, "null pointer");
   TRB_CHECK_ARG(B > 0 && B <= 65535 && R > 0 && n > 0 && ld_src >= n && ld_dst >= n, "bad shape");
   cudaStream_t st = (cudaStream_t)stream;
-  trb_launch_scope scope_(0, st);
+  trb_launch_scope scope_(2, st);
   k_rows_gather_scale<<<dim3(R, B), 256, 0, st>>>(src, stride_src, ld_src, perm, scale, R, n, dst, stride_dst, ld_dst);
   TRB_CHECK_LAUNCH();
   return TRB_OK;
