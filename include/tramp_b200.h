@@ -206,6 +206,9 @@ void trb_gemm_set_variant(int variant);
  *   max_inner  sweeps of the inner 32 x 32 Jacobi (2 is enough: the outer sweeps converge
  *              quadratically either way) */
 int trb_jacobi_zsplit(int B, int np, int ld);
+/* tuning: the column range of a pair is split over CTAs until the grid holds about `waves`
+ * waves of resident CTAs (default 8; fewer waves = longer CTAs, more tail) */
+void trb_jacobi_set_waves(int waves);
 int trb_jacobi_sweep(double* A, int64_t strideA, int B, int np, int ld, double* Swork,
                      double* Jwork, int* rot_flag, double* offmax, double skip_tol,
                      int max_inner, void* stream);

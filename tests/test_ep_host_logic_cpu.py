@@ -68,6 +68,25 @@ def test_early_stopping_chunks_and_rollback(emulated_device, sw):  # noqa: F811
         assert_allclose(d["x"]["v"], sw[name + "_vx_final"], rtol=1e-9)
 
 
+def test_n_iter_per_instance_after_a_callback_stop(emulated_device, sw):  # noqa: F811
+    """A stopping callback that is not device-replayable takes the one-launch-per-iteration
+    path; its early return must still leave `n_iter_per_instance` describing THIS call (it used
+    to keep the previous call's value, which run_ep_sharded then gathered)."""
+    from tramp_b200.algos import ExpectationPropagation, PassCallback
+    cfg = _configs(sw)[0]
+    ep = ExpectationPropagation(_build(cfg, sw, cfg["name"]))
+    ep.iterate(max_iter=5, callback=PassCallback())
+    assert ep.n_iter_per_instance.tolist() == [5]
+
+    class StopAt:                               # a user callback: synchronous path
+        def __call__(self, algo, i, max_iter):
+            return i == 7
+    ep.iterate(max_iter=100, callback=StopAt())
+    assert ep.n_iter == 8 and ep.n_iter_per_instance.tolist() == [8]
+    ep.iterate(max_iter=3, callback=StopAt(), warm_start=True)
+    assert ep.n_iter == 11 and ep.n_iter_per_instance.tolist() == [11]
+
+
 def test_warm_start_and_nan(emulated_device, sw):  # noqa: F811
     from tramp_b200.algos import ExpectationPropagation, PassCallback
     from tramp_b200.priors import GaussBernoulliPrior

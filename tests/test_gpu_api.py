@@ -374,6 +374,39 @@ def test_belief_gradients():
         assert_allclose(belief.v(b=b, **kw), A2, rtol=0, atol=eps)
 
 
+def test_beliefs_against_reference(golden_dir):
+    """Every function of tramp/beliefs/{sparse,binary,positive,truncated}.py against the reference
+    (tests/golden/beliefs.npz), including the weight `sparse.p` down to 1e-18 (reference
+    beliefs/sparse.py:9-12: expit(normal.A - eta)), 1e-11 relative."""
+    from tramp_b200.beliefs import binary, sparse, positive, truncated
+    g = np.load(os.path.join(golden_dir, "beliefs.npz"))
+    a, b = g["bel_a"], g["bel_b"]
+    tiny = 1e-300
+    for k, eta in enumerate(g["sparse_eta"]):
+        for name in ("A", "p", "r", "v", "tau"):
+            ref = g[f"sparse{k}_{name}"]
+            got = getattr(sparse, name)(a, b, float(eta))
+            # v = s / a + s (1 - s) (b / a)^2 and tau are sums of positive terms: plain relative
+            assert_allclose(got, ref, rtol=1e-11, atol=tiny, err_msg=f"sparse.{name} eta={eta}")
+    assert g["sparse7_p"].min() < 1e-17                      # the regime 1 - exp(eta - A) cannot reach
+    bb = g["binary_b"]
+    assert_allclose(binary.A(bb), g["binary_A"], rtol=1e-13)
+    assert_allclose(binary.r(bb), g["binary_r"], rtol=1e-13)
+    # 1 - tanh^2 cancels for |b| >> 1: the reference's own rounding is eps absolute
+    assert_allclose(binary.v(bb), g["binary_v"], rtol=1e-11, atol=4 * np.finfo(float).eps)
+    for name in ("A", "r", "v", "tau", "p"):
+        ref = g[f"positive_{name}"]
+        got = getattr(positive, name)(a, b)
+        assert_allclose(got, ref, rtol=1e-10, atol=1e-13 * np.abs(ref).max(), err_msg=f"positive.{name}")
+    bt = g["trunc_b"]
+    for i, (a_t, lo, hi) in enumerate(g["trunc_cases"]):
+        for name in ("tau", "p"):
+            ref = g[f"trunc{i}_{name}"]
+            ok = np.isfinite(ref)
+            got = getattr(truncated, name)(a_t, bt, lo, hi)
+            assert_allclose(got[ok], ref[ok], rtol=1e-9, atol=1e-13, err_msg=f"truncated.{name} case {i}")
+
+
 def test_linear_channel_factor_api(golden_dir):
     """LinearChannel.compute_*_posterior / log_partition against the reference."""
     from tramp_b200.channels import LinearChannel

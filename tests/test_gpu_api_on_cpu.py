@@ -39,6 +39,10 @@ def test_belief_gradients(emulated_device):  # noqa: F811
     G.test_belief_gradients()
 
 
+def test_beliefs_against_reference(emulated_device, golden_dir):  # noqa: F811
+    G.test_beliefs_against_reference(golden_dir)
+
+
 def test_linear_channel_factor_api(emulated_device, golden_dir):  # noqa: F811
     G.test_linear_channel_factor_api(golden_dir)
 

@@ -83,7 +83,7 @@ def jacobi_parts(W, route):
     sweeps = []
     marks = [e1]
     for _ in range(40):
-        off = float(ops.jacobi_sweep(A, work, skip_tol=5e-15, max_inner=2).max().item())
+        off = float(ops.jacobi_sweep(A, work, skip_tol=5e-15, max_inner=lc.JACOBI_INNER_SWEEPS).max().item())
         marks.append(ev())
         sweeps.append(off)
         if off < 1e-13 or (len(sweeps) > 1 and off < 1e-10 and off > 0.5 * sweeps[-2]):
@@ -111,13 +111,21 @@ def main():
     ap.add_argument("--skip-svd", action="store_true")
     ap.add_argument("--skip-gram", action="store_true")
     ap.add_argument("--direct", action="store_true", help="also time the route on W itself")
+    ap.add_argument("--waves", type=int, default=0, help="trb_jacobi_set_waves (0: library default)")
+    ap.add_argument("--inner", type=int, default=0, help="sweeps of the inner 32 x 32 Jacobi (0: default)")
     args = ap.parse_args()
     assert torch.cuda.is_available(), "needs a CUDA device"
+    from tramp_b200 import _lib
+    if args.waves:
+        _lib.load().trb_jacobi_set_waves(args.waves)
+    if args.inner:
+        lc.JACOBI_INNER_SWEEPS = args.inner
     B, N = args.batch, args.n
     M = int(args.alpha * N)
     gen = torch.Generator(device="cuda").manual_seed(0)
     W = torch.randn((B, M, N), dtype=torch.float64, device="cuda", generator=gen) / N**0.5
-    line = {"tool": "bench_setup", "B": B, "M": M, "N": N, "variants": {}}
+    line = {"tool": "bench_setup", "B": B, "M": M, "N": N, "waves": args.waves, "inner": lc.JACOBI_INNER_SWEEPS,
+            "variants": {}}
     wide = W if M <= N else W.transpose(1, 2).contiguous()
 
     s_ref = None

@@ -414,6 +414,7 @@ class MessagePassing():
             self.init_message_dag(initializer)
             self.n_iter = 0
         self.configure_damping(damping)
+        self.n_iter_per_instance = None
         st = self._ensure_state()
         st["active"].fill_(1)
         st["flags"].zero_()
@@ -475,14 +476,16 @@ class MessagePassing():
         st = self._state
         st["x_true"] = None
         sw = self._descriptor(synchronous=True)
-        for i in range(max_iter):
-            self._run(sw, i, 1, fresh and i == 0)
-            self._raise_on_nan(st["flags"].cpu().numpy())
-            self.n_iter += 1
-            stop = callback(self, i, max_iter)
-            if stop:
-                return
-        self.n_iter_per_instance = np.full(self.B, self.n_iter)
+        try:
+            for i in range(max_iter):
+                self._run(sw, i, 1, fresh and i == 0)
+                self._raise_on_nan(st["flags"].cpu().numpy())
+                self.n_iter += 1
+                stop = callback(self, i, max_iter)
+                if stop:
+                    return
+        finally:      # also on a callback stop or an exception: never a stale count from an earlier call
+            self.n_iter_per_instance = np.full(self.B, self.n_iter)
 
     # ------------------------------------------- host-driven factor-by-factor path
     def _iterate_host(self, max_iter, callback, previous):
@@ -514,15 +517,17 @@ class MessagePassing():
                                    damping=self.damp.get(name) or None)
             host = FactorSchedule(self, edges)
         self._host = host
-        for i in range(max_iter):
-            host.sweep()
-            self._host_to_device(host)
-            self.n_iter += 1
-            stop = callback(self, i, max_iter)
-            if stop:
-                return
-            host.old = host.copy_state()
-        self.n_iter_per_instance = np.full(self.B, self.n_iter)
+        try:
+            for i in range(max_iter):
+                host.sweep()
+                self._host_to_device(host)
+                self.n_iter += 1
+                stop = callback(self, i, max_iter)
+                if stop:
+                    return
+                host.old = host.copy_state()
+        finally:
+            self.n_iter_per_instance = np.full(self.B, self.n_iter)
 
     def _host_to_device(self, host):
         """Mirror the host messages and posteriors into the device state, so that

@@ -22,7 +22,12 @@ def _ceil_to(n, m):
     return -(-int(n) // m) * m
 
 
-def jacobi_orthogonalise_rows(A, tol=1e-13, max_sweeps=40, max_inner=2):
+# sweeps of the 32 x 32 Jacobi that diagonalises a block pair's Gram matrix: the outer iteration
+# needs the same number of sweeps with 1 as with a fully converged inner solve (measured)
+JACOBI_INNER_SWEEPS = 1
+
+
+def jacobi_orthogonalise_rows(A, tol=1e-13, max_sweeps=40, max_inner=None):
     """Rows of A[b] <- Q_b^T A[b] (Q_b orthogonal) until the rows of every instance are mutually
     orthogonal: one-sided block Jacobi, `trb_jacobi_sweep` (tramp_b200/csrc/trb_setup.cu).
 
@@ -33,6 +38,7 @@ def jacobi_orthogonalise_rows(A, tol=1e-13, max_sweeps=40, max_inner=2):
     t = ops.torch()
     B, n_rows, ld = A.shape
     work = ops.jacobi_workspace(B, n_rows, ld, A.device)
+    max_inner = max_inner or JACOBI_INNER_SWEEPS
     history = []
     for sweep in range(max_sweeps):
         off = float(ops.jacobi_sweep(A, work, skip_tol=0.05 * tol, max_inner=max_inner).max().item())

@@ -209,7 +209,7 @@ __device__ __forceinline__ unsigned long long as_ull(double v) {
   return (unsigned long long)__double_as_longlong(v);
 }
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 7)
 k_jacobi_eig(const double* __restrict__ S, int zsplit, double* __restrict__ Jm, int* __restrict__ rot_flag,
              unsigned long long* __restrict__ offmax, double skip_tol, int max_inner) {
   __shared__ double sS[kPV][kPV + 1];
@@ -227,13 +227,16 @@ k_jacobi_eig(const double* __restrict__ S, int zsplit, double* __restrict__ Jm, 
   }
   __syncthreads();
   // largest |cos| between two rows
+  __shared__ double sinv[kPV];
+  if (tid < kPV) {
+    const double d = sS[tid][tid];
+    sinv[tid] = (d > 0.0) ? rsqrt(d) : 0.0;
+  }
+  __syncthreads();
   double off = 0.0;
   for (int e = tid; e < kPV * kPV; e += 256) {
     const int i = e >> 5, j = e & 31;
-    if (i < j) {
-      const double d = sS[i][i] * sS[j][j];
-      if (d > 0.0) off = fmax(off, fabs(sS[i][j]) * rsqrt(d));
-    }
+    if (i < j) off = fmax(off, fabs(sS[i][j]) * sinv[i] * sinv[j]);
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) off = fmax(off, __shfl_xor_sync(0xffffffffu, off, o));
@@ -248,22 +251,32 @@ k_jacobi_eig(const double* __restrict__ S, int zsplit, double* __restrict__ Jm, 
   }
   if (!(off > skip_tol)) return;
 
+  // the 31 x 16 index pairs of the inner round-robin, as (p, q) bytes
+  __shared__ uchar2 spair[kPV - 1][kBS];
+  for (int e = tid; e < (kPV - 1) * kBS; e += 256) {
+    int p, q;
+    rr_pair(kPV, e >> 4, e & 15, p, q);
+    spair[e >> 4][e & 15] = make_uchar2((unsigned char)p, (unsigned char)q);
+  }
+  __syncthreads();
   const int k = tid >> 4, m = tid & 15;
   for (int sweep = 0; sweep < max_inner; ++sweep) {
     int rotated = 0;
     for (int step = 0; step < kPV - 1; ++step) {
-      int pk, qk, pm, qm;
-      rr_pair(kPV, step, k, pk, qk);
-      rr_pair(kPV, step, m, pm, qm);
+      const uchar2 ik = spair[step][k], im = spair[step][m];
+      const int pk = ik.x, qk = ik.y, pm = im.x, qm = im.y;
       if (tid < kBS) {
-        int p, q;
-        rr_pair(kPV, step, tid, p, q);
+        const int p = pm, q = qm;  // tid < 16: m == tid
         const double app = sS[p][p], aqq = sS[q][q], apq = sS[p][q];
         double c = 1.0, s = 0.0;
         if (fabs(apq) > 1.1e-16 * sqrt(fabs(app * aqq)) && apq != 0.0) {
-          const double tau = (aqq - app) / (2.0 * apq);
-          const double tt = copysign(1.0, tau) / (fabs(tau) + sqrt(1.0 + tau * tau));
-          c = 1.0 / sqrt(1.0 + tt * tt);
+          // small root of t^2 + 2 tau t - 1 = 0, tau = (aqq - app) / (2 apq), written without
+          // forming tau: t = sgn(d h) |h| / (|d| + sqrt(d^2 + h^2)).  Only c has to be exact to
+          // the last bit (c^2 + s^2 = c^2 (1 + t^2) = 1 keeps J orthogonal); an ulp or two in t
+          // merely leaves |apq| * 1e-16 un-annihilated.
+          const double d = aqq - app, h = 2.0 * apq;
+          const double tt = copysign(fabs(h) / (fabs(d) + sqrt(fma(d, d, h * h))), (d >= 0.0) ? h : -h);
+          c = rsqrt(fma(tt, tt, 1.0));
           s = tt * c;
           rotated = 1;
         }
@@ -286,7 +299,7 @@ k_jacobi_eig(const double* __restrict__ S, int zsplit, double* __restrict__ Jm, 
       sJ[2 * k + 1][pm] = cm * j10 - sm * j11, sJ[2 * k + 1][qm] = sm * j10 + cm * j11;
       __syncthreads();
     }
-    if (!__syncthreads_or(rotated)) break;
+    if (sweep + 1 < max_inner && !__syncthreads_or(rotated)) break;
   }
   double* out = Jm + ((size_t)b * npairs + pair) * (kPV * kPV);
   for (int e = tid; e < kPV * kPV; e += 256) out[e] = sJ[e >> 5][e & 31];
@@ -409,10 +422,13 @@ int setup_attrs() {
 
 }  // namespace
 
+int g_jacobi_waves = 8;
+extern "C" void trb_jacobi_set_waves(int waves) { g_jacobi_waves = waves > 0 ? waves : 8; }
+
 extern "C" int trb_jacobi_zsplit(int B, int np, int ld) {
-  // enough CTAs for ~8 waves of 3 CTAs per SM, at least 4 stages per CTA
+  // enough CTAs for ~g_jacobi_waves waves of 3 CTAs per SM, at least 4 stages per CTA
   const int npairs = np / kPV;
-  const long long want = 8LL * 3 * trb_sm_count_cached();
+  const long long want = (long long)g_jacobi_waves * 3 * trb_sm_count_cached();
   long long z = (want + (long long)npairs * B - 1) / ((long long)npairs * B);
   const int zmax = (ld / kStagePos) / 4;
   if (z > zmax) z = zmax;
