@@ -207,7 +207,7 @@ void trb_gemm_set_variant(int variant);
  *              quadratically either way) */
 int trb_jacobi_zsplit(int B, int np, int ld);
 /* tuning: the column range of a pair is split over CTAs until the grid holds about `waves`
- * waves of resident CTAs (default 8; fewer waves = longer CTAs, more tail) */
+ * waves of resident CTAs (default 4; fewer waves = longer CTAs, more tail) */
 void trb_jacobi_set_waves(int waves);
 int trb_jacobi_sweep(double* A, int64_t strideA, int B, int np, int ld, double* Swork,
                      double* Jwork, int* rot_flag, double* offmax, double skip_tol,

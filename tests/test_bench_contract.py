@@ -31,6 +31,12 @@ def test_reference_arm_prints_the_contract_line():
     assert base["kind"] == "port" and base["cores"] >= 1 and base["value"] == line["value"] and base["sample"]
     assert line["e2e"] == {"value": line["value"], "unit": line["unit"], "h2d_bytes_per_step": 0,
                            "d2h_bytes_per_step": 0}
+    # the line describes what was timed: `steps` steps of the winning mode, ms_per_step their mean
+    # (the rate follows from the units of one step), and the same arm with the SVD counted
+    procs = os.cpu_count() or 1
+    units = 5 * (procs if "one process" in base["sample"] else 1)       # instance-iterations of one step
+    assert abs(line["value"] - units / (line["ms_per_step"] / 1e3)) <= 1e-6 * line["value"]
+    assert 0 < line["incl_setup"]["value"] < line["value"]
 
 
 def test_reference_arm_runs_on_rank_zero_only():

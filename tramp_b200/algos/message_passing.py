@@ -414,6 +414,12 @@ class MessagePassing():
             self.init_message_dag(initializer)
             self.n_iter = 0
         self.configure_damping(damping)
+        if getattr(self.linear, "group", None) is not None:
+            # the ranks of a row-sharded operator enter the sweep together: the peer exchange
+            # (trb_comm.cu) gives a silent peer one second before it flags a time-out, and host
+            # skew before the first exchange (module load, allocation) must not count against it
+            import torch.distributed as dist
+            dist.barrier(group=self.linear.group)
         self.n_iter_per_instance = None
         st = self._ensure_state()
         st["active"].fill_(1)

@@ -5,6 +5,14 @@ collective.  torch.distributed (NCCL over NVLink on the box, gloo in the CPU
 tests) is used only to gather the per-iteration records at the end."""
 
 
+def collective_device(group=None, fallback="cuda"):
+    """Device the tensors of a collective must live on: NCCL moves device memory, gloo (CPU
+    tests, or several ranks sharing ONE GPU, which NCCL refuses) wants host tensors for
+    all_gather."""
+    import torch.distributed as dist
+    return "cpu" if dist.get_backend(group) == "gloo" else fallback
+
+
 class PeerExchange:
     """The peer-memory exchange of a row-sharded operator (include/tramp_b200.h
     trb_comm_*): every rank's buffer is mapped into every other rank over NVLink
@@ -24,7 +32,7 @@ class PeerExchange:
         ptr = C.c_void_p()
         _lib.check(lib.trb_comm_create(self.rank, self.world, int(vec_doubles), C.byref(ptr), handle))
         self.ptr = ptr
-        mine = torch.tensor(list(handle.raw), dtype=torch.uint8, device="cuda")
+        mine = torch.tensor(list(handle.raw), dtype=torch.uint8, device=collective_device(group))
         every = [torch.zeros_like(mine) for _ in range(self.world)]
         dist.all_gather(every, mine, group=group)
         blob = b"".join(bytes(t.cpu().tolist()) for t in every)
@@ -65,6 +73,8 @@ def gather_records(local, group=None):
     if not dist.is_initialized() or dist.get_world_size(group) == 1:
         return local
     world = dist.get_world_size(group)
+    home = local.device
+    local = local.to(collective_device(group, fallback=home))
     n_local = torch.tensor([local.shape[-1]], dtype=torch.int64, device=local.device)
     sizes = [torch.zeros_like(n_local) for _ in range(world)]
     dist.all_gather(sizes, n_local, group=group)
@@ -74,7 +84,7 @@ def gather_records(local, group=None):
     pad[..., :local.shape[-1]] = local
     out = [torch.zeros_like(pad) for _ in range(world)]
     dist.all_gather(out, pad, group=group)
-    return torch.cat([o[..., :n] for o, n in zip(out, sizes)], dim=-1)
+    return torch.cat([o[..., :n] for o, n in zip(out, sizes)], dim=-1).to(home)
 
 
 def max_over_ranks(value, device, group=None):
@@ -84,5 +94,6 @@ def max_over_ranks(value, device, group=None):
     import torch.distributed as dist
     t = torch.tensor([float(value)], dtype=torch.float64, device=device)
     if dist.is_initialized() and dist.get_world_size(group) > 1:
+        t = t.to(collective_device(group, fallback=device))
         dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
     return float(t.item())
