@@ -209,13 +209,13 @@ def test_wishart_singular_values_follow_the_gaussian_ensemble():
     assert abs((s**4).mean() - (d**4).mean()) < 0.05
 
 
-def test_thin_svd_methods_on_cpu_tensors():
-    """The set-up factorisations are plain tensor algebra (cuSOLVER through torch on
-    the GPU): "gram" loses orthogonality like eps * cond(W)^2, "auto" uses it only
-    when cond(W)^2 <= 1e4 and falls back to the SVD otherwise (also for
-    rank-deficient W, where the Gram matrix cannot resolve the numerical rank)."""
+def test_thin_svd_methods_on_cpu_tensors(emulated_device):
+    """Routing of `thin_svd_device`: "auto" takes the hand-written block-Jacobi set-up through the
+    Gram matrix when cond(W)^2 <= 1e4 (orthogonality is lost like eps * cond(W)^2 there), on W
+    itself otherwise, and the library SVD only for a rank-deficient W.  (Kernels emulated; the
+    library baselines "svd" / "gram" are plain tensor algebra.)"""
     import torch
-    from tramp_b200.channels.linear_channel import thin_svd_device
+    from tramp_b200.channels.linear_channel import thin_svd_device, LAST_SETUP_STATS
     rng = np.random.RandomState(0)
 
     def quality(W, method):
@@ -228,17 +228,20 @@ def test_thin_svd_methods_on_cpu_tensors():
     for M, N in ((60, 120), (120, 60)):
         W = rng.randn(M, N) / np.sqrt(N)
         s_ref = np.linalg.svd(W, compute_uv=False)
-        for method in ("svd", "gram", "auto"):
+        for method in ("svd", "gram", "auto", "jacobi", "jacobi_direct"):
             s, rec, orth_v, orth_u = quality(W, method)
-            np.testing.assert_allclose(s, s_ref, rtol=1e-12)
-            assert rec < 1e-13 and orth_v < 1e-12 and orth_u < 1e-12
+            np.testing.assert_allclose(s, s_ref, rtol=1e-11)
+            assert rec < 1e-12 and orth_v < 1e-11 and orth_u < 1e-11
+        quality(W, "auto")
+        assert LAST_SETUP_STATS["route"] == "gram"
     W = rng.randn(80, 80) / np.sqrt(80)             # square Gaussian: cond^2 ~ 1e5 ... 1e7
     s_svd = quality(W, "svd")
     s_auto = quality(W, "auto")
-    assert (s_svd[0][0] / s_svd[0][-1])**2 > 1e4
-    np.testing.assert_array_equal(s_auto[0], s_svd[0])          # fell back: identical factorisation
-    Ww = rng.randn(60, 120) / np.sqrt(120)          # wide but ill conditioned: Gram attempted, rejected
-    Ww[-1] = Ww[0] * (1 + 1e-9)
+    assert (s_svd[0][0] / s_svd[0][-1])**2 > 1e4 and LAST_SETUP_STATS["route"] == "direct"
+    np.testing.assert_allclose(s_auto[0], s_svd[0], rtol=1e-9)
+    assert s_auto[1] < 1e-12 and s_auto[2] < 1e-11             # V from the rotations, U = W V / s
+    Ww = rng.randn(60, 120) / np.sqrt(120)          # rank deficient: both Jacobi routes rejected
+    Ww[-1] = Ww[0]
     np.testing.assert_array_equal(quality(Ww, "auto")[0], quality(Ww, "svd")[0])
     W[-1] = W[0]                                    # rank deficient
     s_auto, s_svd = quality(W, "auto"), quality(W, "svd")

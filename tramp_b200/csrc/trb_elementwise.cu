@@ -190,7 +190,10 @@ __global__ void __launch_bounds__(kEwThreads)
 k_factor_message(trb_factor f, int n, int ld, const double* __restrict__ a_in,
                  const double* __restrict__ b_in, const double* __restrict__ y, double* a_io,
                  double* b_io, double* a_copy, double damping, double* __restrict__ scratch,
-                 int* flags, const int* __restrict__ active) {
+                 int* flags, const int* __restrict__ active,
+                 // one-iteration-back copies of what is overwritten (nullable): the sweep's
+                 // `old_message_dag` (message_passing.py:356) costs one extra store, no copy kernel
+                 double* __restrict__ snap_b, double* __restrict__ snap_a, double* __restrict__ snap_a_copy) {
   __shared__ double sh[33];
   __shared__ int sh_flag;
   const int inst = blockIdx.y;
@@ -206,7 +209,9 @@ k_factor_message(trb_factor f, int n, int ld, const double* __restrict__ a_in,
     a_new = f.p0;
     for (int i = gtid; i < n; i += T) {
       const double bn = (f.kind == TRB_GAUSSIAN_PRIOR) ? f.p1 : y[off + i] * f.p0;
-      const double bd = damp(damping, b_io[off + i], bn);
+      const double bold = b_io[off + i];
+      if (snap_b) snap_b[off + i] = bold;
+      const double bd = damp(damping, bold, bn);
       b_io[off + i] = bd;
       if (bn != bn) flag |= TRB_FLAG_NAN_B;
     }
@@ -253,6 +258,7 @@ k_factor_message(trb_factor f, int n, int ld, const double* __restrict__ a_in,
         const int i = base + u * T;
         if (i < n) {
           const double bn = rv[u] * ainv - bv[u];
+          if (snap_b) snap_b[off + i] = bo[u];
           b_io[off + i] = damp(damping, bo[u], bn);
           if (bn != bn) flag |= TRB_FLAG_NAN_B;
         }
@@ -263,7 +269,10 @@ k_factor_message(trb_factor f, int n, int ld, const double* __restrict__ a_in,
   if (a_new < 0) flag |= TRB_FLAG_NEG_A;
   const int all = cluster_or(flag, &sh_flag);
   if (gtid == 0) {
-    const double ad = damp(damping, a_io[inst], a_new);
+    const double a_old = a_io[inst];
+    if (snap_a) snap_a[inst] = a_old;
+    if (snap_a_copy && a_copy) snap_a_copy[inst] = a_copy[inst];
+    const double ad = damp(damping, a_old, a_new);
     a_io[inst] = ad;
     if (a_copy) a_copy[inst] = ad;
     if (flags && all) atomicOr(&flags[inst], all);
@@ -328,10 +337,26 @@ extern "C" int trb_factor_log_partition(const trb_factor* f, int B, int n, int l
   return TRB_OK;
 }
 
+// trb_factor_message that also keeps the overwritten message (the sweep's one-iteration-back state)
+int trb_factor_message_snap(const trb_factor* f, int B, int n, int ld, const double* a_in,
+                            const double* b_in, const double* y, double* a_io, double* b_io,
+                            double* a_copy, double damping, double* scratch, int* flags,
+                            const int* active, double* snap_b, double* snap_a, double* snap_a_copy,
+                            void* stream);
+
 extern "C" int trb_factor_message(const trb_factor* f, int B, int n, int ld, const double* a_in,
                                   const double* b_in, const double* y, double* a_io, double* b_io,
                                   double* a_copy, double damping, double* scratch, int* flags,
                                   const int* active, void* stream) {
+  return trb_factor_message_snap(f, B, n, ld, a_in, b_in, y, a_io, b_io, a_copy, damping, scratch, flags,
+                                 active, nullptr, nullptr, nullptr, stream);
+}
+
+int trb_factor_message_snap(const trb_factor* f, int B, int n, int ld, const double* a_in,
+                            const double* b_in, const double* y, double* a_io, double* b_io,
+                            double* a_copy, double damping, double* scratch, int* flags,
+                            const int* active, double* snap_b, double* snap_a, double* snap_a_copy,
+                            void* stream) {
   TRB_CHECK_ARG(f && a_in && b_in && a_io && b_io && scratch, "null pointer");
   TRB_CHECK_ARG(B > 0 && n > 0 && ld >= n, "bad shape");
   TRB_CHECK_ARG(f->kind >= 0 && f->kind <= TRB_ABS_LIKELIHOOD, "unknown factor kind");
@@ -339,7 +364,7 @@ extern "C" int trb_factor_message(const trb_factor* f, int B, int n, int ld, con
   trb_launch_scope scope_(0, (cudaStream_t)stream);
   cudaError_t le = trb_launch_cluster(k_factor_message, trb_cluster_size(B, n), B, kEwThreads,
                                       (cudaStream_t)stream, *f, n, ld, a_in, b_in, y, a_io, b_io,
-                                      a_copy, damping, scratch, flags, active);
+                                      a_copy, damping, scratch, flags, active, snap_b, snap_a, snap_a_copy);
   if (le != cudaSuccess)
     return trb_set_error(TRB_ERR_CUDA, "trb_factor_message: %s", cudaGetErrorString(le));
   TRB_CHECK_LAUNCH();

@@ -426,7 +426,8 @@ k_lin_rescale(int dir, int R, int Nz, int Nx, int rank, int null_space_flag,
               const double* __restrict__ s2, int64_t stride_s, const double* __restrict__ az_arr,
               const double* __restrict__ ax_arr, const double* __restrict__ tz,
               const double* __restrict__ tx, double* __restrict__ coef, double* __restrict__ v_out,
-              const int* __restrict__ active) {
+              const int* __restrict__ active,
+              double* __restrict__ snap_tx) {  // nullable: receives a copy of tx (one-iteration-back state)
   __shared__ double sh[33];
   const int b = blockIdx.y;  // grid (C, B): a cluster of C CTAs per instance
   if (active && !active[b]) return;
@@ -474,6 +475,7 @@ k_lin_rescale(int dir, int R, int Nz, int Nx, int rank, int null_space_flag,
     const double si = sb[i], s2i = s2b[i];
     const double res = 1 / (az + ax * s2i);  // :74
     const double tzi = tz[off + i], txi = tx[off + i];
+    if (snap_tx) snap_tx[off + i] = txi;
     double c;
     if (dir == 0) {
       c = si * (res * (tzi + si * txi));
@@ -722,11 +724,24 @@ extern "C" int trb_lin_reduce_slots(int B, int R, int n, int ld, const double* p
   return reduce_slots_launch(B, R, n, ld, part, add, add_div, out, (size_t)ld, (cudaStream_t)stream);
 }
 
+int trb_lin_rescale_snap(int dir, int B, int R, int Nz, int Nx, int rank, int null_space,
+                         const double* s, const double* s2, int64_t stride_s, const double* az,
+                         const double* ax, const double* tz, const double* tx, double* coef, double* v,
+                         const int* active, double* snap_tx, void* stream);
+
 extern "C" int trb_lin_rescale(int dir, int B, int R, int Nz, int Nx, int rank, int null_space,
                                const double* s, const double* s2, int64_t stride_s,
                                const double* az, const double* ax, const double* tz,
                                const double* tx, double* coef, double* v, const int* active,
                                void* stream) {
+  return trb_lin_rescale_snap(dir, B, R, Nz, Nx, rank, null_space, s, s2, stride_s, az, ax, tz, tx, coef, v,
+                              active, nullptr, stream);
+}
+
+int trb_lin_rescale_snap(int dir, int B, int R, int Nz, int Nx, int rank, int null_space,
+                         const double* s, const double* s2, int64_t stride_s, const double* az,
+                         const double* ax, const double* tz, const double* tx, double* coef, double* v,
+                         const int* active, double* snap_tx, void* stream) {
   TRB_CHECK_ARG(s && s2 && az && ax && (coef || v), "null pointer");
   TRB_CHECK_ARG(!coef || (tz && tx), "coef needs tz and tx");
   TRB_CHECK_ARG(dir == 0 || dir == 1, "dir must be 0 or 1");
@@ -736,7 +751,7 @@ extern "C" int trb_lin_rescale(int dir, int B, int R, int Nz, int Nx, int rank, 
   const int rs_threads = (R >= 8192 && B * 8 <= trb_sm_count_cached()) ? 1024 : 256;
   cudaError_t le = trb_launch_cluster(k_lin_rescale, trb_cluster_size(B, R), B, rs_threads,
                                       (cudaStream_t)stream, dir, R, Nz, Nx, rank, null_space, s, s2,
-                                      stride_s, az, ax, tz, tx, coef, v, active);
+                                      stride_s, az, ax, tz, tx, coef, v, active, coef ? snap_tx : nullptr);
   if (le != cudaSuccess)
     return trb_set_error(TRB_ERR_CUDA, "trb_lin_rescale: %s", cudaGetErrorString(le));
   TRB_CHECK_LAUNCH();

@@ -37,13 +37,13 @@ __device__ __forceinline__ int slots_of(int b, int R, int B, int G) {
   return kl - kf + 1;
 }
 
-constexpr int kUnroll = 4;  // elements per thread whose loads are issued together
+constexpr int kUnroll = 2;  // elements per thread whose loads are issued together (2 CTAs of 512 threads per SM)
 
 // stats[b*4 + {0,1}] = sum (r_new - r_old)^2, sum r_new^2 for z
 // light (schedule 2): only the scalars of e3 and the constant Gaussian-likelihood
 // message e5 are updated; e3's vector, the posterior mean of z and its tolerance
 // statistics wait for the last iteration of the run.
-__global__ void __launch_bounds__(kUpThreads)
+__global__ void __launch_bounds__(kUpThreads, 2)
 k_z_update(trb_sweep sw, int G, int first, int light, double* __restrict__ stats, trb_peers peers) {
   __shared__ double sh[33 * 2];
   __shared__ int sh_flag;
@@ -67,6 +67,9 @@ k_z_update(trb_sweep sw, int G, int first, int light, double* __restrict__ stats
   double* scr = sw.scr_m + off;
   const double* y = sw.y + off;
   const bool const_lik = factor_is_constant_message(sw.lik.kind);
+  // every overwritten value is first copied to the one-iteration-back state (the reference's
+  // old_message_dag, message_passing.py:356): no separate copy kernel per iteration
+  const bool snap = sw.snap_edge_a != nullptr;
   const int step = T * kUnroll;
   int flag = 0;
   double vsum = 0.0;
@@ -96,6 +99,7 @@ k_z_update(trb_sweep sw, int G, int first, int light, double* __restrict__ stats
         const double b3n = rx[u] * ainv3 - b6v[u];
         if (b3n != b3n) flag |= TRB_FLAG_NAN_B;
         const double b3v = damp(sw.damp3, b3o[u], b3n);
+        if (snap) sw.snap_b3[off + i] = b3o[u];
         b3[i] = b3v;
         if (!const_lik) {
           const RV m = factor_moments(sw.lik, a3, b3v, yv[u]);
@@ -136,9 +140,11 @@ k_z_update(trb_sweep sw, int G, int first, int light, double* __restrict__ stats
         const double b5n = const_lik ? src[u] * sw.lik.p0 : src[u] * ainv5 - b3v[u];
         if (b5n != b5n) flag |= TRB_FLAG_NAN_B;
         const double b5v = damp(sw.damp5, b5o[u], b5n);
+        if (snap) sw.snap_b5[off + i] = b5o[u];
         b5[i] = b5v;
         if (light) continue;
         const double rnew = (b3v[u] + b5v) / a_hat;  // base.py:152-161
+        if (snap) sw.snap_rz[off + i] = ro[u];
         rz[i] = rnew;
         red[0] += (rnew - ro[u]) * (rnew - ro[u]);
         red[1] += rnew * rnew;
@@ -150,6 +156,10 @@ k_z_update(trb_sweep sw, int G, int first, int light, double* __restrict__ stats
   if (a3n < 0 || a5n < 0) flag |= TRB_FLAG_NEG_A;
   const int all = cluster_or(flag, &sh_flag);
   if (gtid == 0) {
+    if (snap) {
+      for (int e = 2; e < 6; ++e) sw.snap_edge_a[e * B + b] = ea[e * B + b];
+      sw.snap_vz[b] = sw.vz[b];
+    }
     ea[2 * B + b] = a3;
     ea[3 * B + b] = a3;  // e4 = e3 (sub_variables.py:21-25)
     ea[4 * B + b] = a5;
@@ -163,7 +173,7 @@ k_z_update(trb_sweep sw, int G, int first, int light, double* __restrict__ stats
   }
 }
 
-__global__ void __launch_bounds__(kUpThreads)
+__global__ void __launch_bounds__(kUpThreads, 2)
 k_x_update(trb_sweep sw, int G, int it_host, double* __restrict__ stats, trb_peers peers) {
   __shared__ double sh[33 * 4];
   __shared__ int sh_flag;
@@ -193,6 +203,7 @@ k_x_update(trb_sweep sw, int G, int it_host, double* __restrict__ stats, trb_pee
   int flag = 0;
   const bool use_peers = peers.n > 0;  // row-sharded operator, see k_z_update
   if (use_peers && !peers_wait(peers)) flag |= TRB_FLAG_COMM_TIMEOUT;
+  const bool snap = sw.snap_edge_a != nullptr;  // see k_z_update
   double red[4] = {0.0, 0.0, 0.0, 0.0};  // sum dr^2, sum r^2, sum (r-x)^2, sum (r+x)^2
   for (int base = gtid; base < N; base += step) {
     double rzv[kUnroll], b1v[kUnroll], b7o[kUnroll], ro[kUnroll], xv[kUnroll];
@@ -219,6 +230,10 @@ k_x_update(trb_sweep sw, int G, int it_host, double* __restrict__ stats, trb_pee
         const double b7n = r * ainv7 - b1v[u];
         if (b7n != b7n) flag |= TRB_FLAG_NAN_B;
         const double b7v = damp(sw.damp7, b7o[u], b7n);
+        if (snap) {
+          sw.snap_b7[off + i] = b7o[u];
+          sw.snap_rx[off + i] = ro[u];
+        }
         b7[i] = b7v;
         const double rnew = (b1v[u] + b7v) / a_hat;
         rx[i] = rnew;
@@ -235,6 +250,11 @@ k_x_update(trb_sweep sw, int G, int it_host, double* __restrict__ stats, trb_pee
   if (a7n < 0) flag |= TRB_FLAG_NEG_A;
   const int all = cluster_or(flag, &sh_flag);
   if (gtid == 0) {
+    if (snap) {
+      sw.snap_edge_a[6 * B + b] = ea[6 * B + b];
+      sw.snap_edge_a[7 * B + b] = ea[7 * B + b];
+      sw.snap_vx[b] = sw.vx[b];
+    }
     ea[6 * B + b] = a7;
     ea[7 * B + b] = a7;  // e8 = e7
     const double vx = 1. / a_hat;
@@ -276,14 +296,16 @@ k_x_update(trb_sweep sw, int G, int it_host, double* __restrict__ stats, trb_pee
 // One-iteration-back snapshot of the message state, per instance:
 //   active instance                      -> save   (old_message_dag = message_dag.copy(), :356)
 //   stopped on NaN / divergence, once    -> restore (reset_message_dag, :196-197, callbacks.py:281-283)
+// restore_only: the update kernels keep the one-iteration-back state themselves (every value
+// is copied to its snap_* buffer before it is overwritten), so nothing is saved here.
 __global__ void __launch_bounds__(256)
-k_snapshot(trb_sweep sw) {
+k_snapshot(trb_sweep sw, int restore_only) {
   const int b = blockIdx.y;  // grid (chunks, B), plain CTAs: pure copies
   const int B = sw.B;
   const size_t gtid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   const size_t T = (size_t)gridDim.x * blockDim.x;
   const int flags = sw.flags[b];
-  const bool save = sw.active[b] != 0;
+  const bool save = sw.active[b] != 0 && !restore_only;
   const bool restore = !save && (flags & (TRB_FLAG_DIVERGED | TRB_FLAG_NAN_A | TRB_FLAG_NAN_B)) &&
                        !(flags & TRB_FLAG_RESTORED);
   if (!save && !restore) return;
@@ -328,7 +350,9 @@ k_tx_recur(trb_sweep sw) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= sw.R) return;
   const size_t o = (size_t)b * sw.R + i;
-  sw.tx[o] = damp(sw.damp5, sw.tx[o], sw.lik.p0 * sw.ty[o]);
+  const double told = sw.tx[o];
+  if (sw.snap_tx) sw.snap_tx[o] = told;  // one-iteration-back state, see k_z_update
+  sw.tx[o] = damp(sw.damp5, told, sw.lik.p0 * sw.ty[o]);
 }
 
 }  // namespace
@@ -362,6 +386,15 @@ static int check_sweep(const trb_sweep* sw) {
 // ranks' vectors from its own memory (trb_comm.cu).
 int trb_reduce_slots_push(int B, int R, int n, int ld, const double* part, const trb_push* push,
                           void* stream);
+int trb_factor_message_snap(const trb_factor* f, int B, int n, int ld, const double* a_in,
+                            const double* b_in, const double* y, double* a_io, double* b_io,
+                            double* a_copy, double damping, double* scratch, int* flags,
+                            const int* active, double* snap_b, double* snap_a, double* snap_a_copy,
+                            void* stream);
+int trb_lin_rescale_snap(int dir, int B, int R, int Nz, int Nx, int rank, int null_space,
+                         const double* s, const double* s2, int64_t stride_s, const double* az,
+                         const double* ax, const double* tz, const double* tx, double* coef, double* v,
+                         const int* active, double* snap_tx, void* stream);
 static int exchange_expansion(const trb_sweep* sw, int n, int ld, cudaStream_t st) {
   trb_comm* comm = sw->comm;
   TRB_CHECK_ARG((size_t)sw->B * ld <= trb_comm_capacity(comm), "exchange buffer too small");
@@ -415,9 +448,10 @@ extern "C" int trb_sweep_stage(const trb_sweep* sw, int stage, int it, int first
   switch (stage) {
     case TRB_STAGE_PRIOR: {  // F1: reads e8, writes e1 and its pass-through copy e2
       const double* b8 = (first && sw->b8_init) ? sw->b8_init : sw->b7;
-      return trb_factor_message(&sw->prior, B, sw->N, sw->ldn, ea + 7 * B, b8, nullptr, ea + 0 * B,
-                                sw->b1, ea + 1 * B, sw->damp1, sw->scr_n, sw->flags, sw->active,
-                                stream);
+      double* sa = sw->snap_edge_a;
+      return trb_factor_message_snap(&sw->prior, B, sw->N, sw->ldn, ea + 7 * B, b8, nullptr, ea + 0 * B,
+                                     sw->b1, ea + 1 * B, sw->damp1, sw->scr_n, sw->flags, sw->active,
+                                     sa ? sw->snap_b1 : nullptr, sa, sa ? sa + 1 * B : nullptr, stream);
     }
     case TRB_STAGE_PROJECT_Z:  // P1: tz = V_R^T b2
       if (gemm)
@@ -440,17 +474,22 @@ extern "C" int trb_sweep_stage(const trb_sweep* sw, int stage, int it, int first
                              sw->s2_full, 0, ea + 1 * B, ea + 5 * B, nullptr, nullptr, nullptr,
                              sw->vlin, sw->active, stream);
         if (rc) return rc;
-        return trb_lin_rescale(dir, B, sw->R, sw->N, sw->M, sw->rank < sw->R ? sw->rank : sw->R,
-                               null_space, sw->s, sw->s2, sw->stride_s, ea + 1 * B, ea + 5 * B,
-                               sw->tz, sw->tx, sw->coef, nullptr, sw->active, stream);
+        return trb_lin_rescale_snap(dir, B, sw->R, sw->N, sw->M, sw->rank < sw->R ? sw->rank : sw->R,
+                                    null_space, sw->s, sw->s2, sw->stride_s, ea + 1 * B, ea + 5 * B,
+                                    sw->tz, sw->tx, sw->coef, nullptr, sw->active,
+                                    (dir == 0 && sw->schedule == 0 && sw->snap_edge_a) ? sw->snap_tx : nullptr,
+                                    stream);
       }
       if (stage == TRB_STAGE_RESCALE_BWD)
         return trb_lin_rescale(1, B, sw->R, sw->N, sw->M, sw->rank, null_space, sw->s, sw->s2,
                                sw->stride_s, ea + 1 * B, ea + 5 * B, sw->tz, sw->tx, sw->coef,
                                sw->vlin, sw->active, stream);
-      return trb_lin_rescale(0, B, sw->R, sw->N, sw->M, sw->rank, null_space, sw->s, sw->s2,
-                             sw->stride_s, ea + 1 * B, ea + 5 * B, sw->tz, sw->tx, sw->coef,
-                             sw->vlin, sw->active, stream);
+      // general schedule: P3 overwrites tx later in this iteration, so its old value is kept here
+      // (schedules 1 and 2 update tx in k_tx_recur, which keeps it)
+      return trb_lin_rescale_snap(0, B, sw->R, sw->N, sw->M, sw->rank, null_space, sw->s, sw->s2,
+                                  sw->stride_s, ea + 1 * B, ea + 5 * B, sw->tz, sw->tx, sw->coef,
+                                  sw->vlin, sw->active,
+                                  (sw->schedule == 0 && sw->snap_edge_a) ? sw->snap_tx : nullptr, stream);
     case TRB_STAGE_EXPAND_X:  // P2: rx = U_R coef
       if (gemm)
         return trb_lin_expand_gemm(sw->Ut, sw->R, sw->M, sw->ldm, B, sw->coef, sw->part,
@@ -526,7 +565,8 @@ case TRB_STAGE_EXPAND_Z:  // P4: rz = [b2/a2 +] V_R coef
       int chunks = (big + 511) / 512;  // plain copies: spread a large instance over many CTAs
       const int cap = (4 * trb_device_sm_count() + B - 1) / B;
       if (chunks > cap) chunks = cap < 1 ? 1 : cap;
-      k_snapshot<<<dim3(chunks, B), 256, 0, st>>>(*sw);
+      // it == -2: restore only (end of a trb_sweep_run whose update kernels kept the state)
+      k_snapshot<<<dim3(chunks, B), 256, 0, st>>>(*sw, it == -2 ? 1 : 0);
       k_snapshot_mark<<<(B + 255) / 256, 256, 0, st>>>(*sw);
       TRB_CHECK_LAUNCH();
       return TRB_OK;
@@ -560,7 +600,10 @@ static int enqueue_iteration(const trb_sweep* sw, int it, int first, int fresh, 
   TRB_TRY(trb_sweep_stage(sw, TRB_STAGE_RESCALE_BWD, it, first, 0, stream));
   TRB_TRY(trb_sweep_stage(sw, TRB_STAGE_EXPAND_Z, it, first, 0, stream));
   TRB_TRY(trb_sweep_stage(sw, TRB_STAGE_X_UPDATE, it, first, 0, stream));
-  TRB_TRY(trb_sweep_stage(sw, TRB_STAGE_SNAPSHOT, it, first, 0, stream));
+  // The update kernels copy every value they overwrite to the one-iteration-back state, so a
+  // stopped instance is rolled back once, at the end of trb_sweep_run.  Schedule 2 skips the z
+  // branch (b3, rz are not rewritten every iteration) and keeps the copy kernel.
+  if (schedule == 2) TRB_TRY(trb_sweep_stage(sw, TRB_STAGE_SNAPSHOT, it, first, 0, stream));
   return TRB_OK;
 }
 
@@ -690,5 +733,7 @@ extern "C" int trb_sweep_run(const trb_sweep* sw, int it0, int n_iter, int fresh
     TRB_TRY(enqueue_iteration(sw, it0 + k, first, fresh, light, st));
     ++k;
   }
+  // roll back the instances that stopped on NaN / divergence in this call (restore only)
+  if (schedule != 2 && n_iter > 0) TRB_TRY(trb_sweep_stage(sw, TRB_STAGE_SNAPSHOT, -2, 0, 0, stream));
   return TRB_OK;
 }
