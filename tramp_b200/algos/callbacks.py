@@ -33,22 +33,23 @@ class PassCallback(Callback):
         self.repr_init()
 
     def __call__(self, algo, i, max_iter):
-        pass
+        return None
 
     def device_replayable(self, algo):
         return True
 
 
 class JoinCallback(Callback):
-    """reference callbacks.py:22-32."""
+    """Several callbacks as one; stops as soon as any of them asks to (reference
+    callbacks.py:22-32).  Every member sees every iteration, also after another one voted to stop."""
 
     def __init__(self, callbacks):
         self.callbacks = callbacks
         self.repr_init(pad="\t")
 
     def __call__(self, algo, i, max_iter):
-        stops = [callback(algo, i, max_iter) for callback in self.callbacks]
-        return any(stops)
+        votes = [member(algo, i, max_iter) for member in self.callbacks]
+        return any(votes)
 
     def device_replayable(self, algo):
         return all(isinstance(c, Callback) and c.device_replayable(algo) for c in self.callbacks)
@@ -62,38 +63,67 @@ class JoinCallback(Callback):
             c.replay(algo, i, max_iter, rec)
 
 
+class _Recorder(Callback):
+    """What the tracking callbacks share: a list that restarts at iteration 0 and receives, every
+    `every` iterations, the rows `_rows(algo, i)` built from the live state -- or, when the sweep
+    ran on the device without host round trips, the rows `_rows_recorded(algo, i, rec)` built
+    from its recorded trajectory.  `store` names the attribute holding the list (the reference's
+    callbacks call it `records` or `errors`); `get_dataframe()` turns it into a DataFrame."""
+    store = "records"
+    every = 1
+    verbose = False
+
+    def _visit(self, i, rows_of):
+        if i == 0:
+            setattr(self, self.store, [])
+        if i % self.every:
+            return
+        rows = rows_of()
+        if self.verbose:
+            for row in rows:
+                print(row)
+        getattr(self, self.store).extend(rows)
+
+    def __call__(self, algo, i, max_iter):
+        self._visit(i, lambda: self._rows(algo, i))
+
+    def replay(self, algo, i, max_iter, rec):
+        self._visit(i, lambda: self._rows_recorded(algo, i, rec))
+
+    def get_dataframe(self):
+        return pd.DataFrame(getattr(self, self.store))
+
+
 class LogProgress(Callback):
+    """Logs the mean posterior variance of the tracked variables (reference callbacks.py:35-46)."""
+
     def __init__(self, ids="all", every=1):
         self.ids = ids
         self.every = every
         self.repr_init()
 
     def __call__(self, algo, i, max_iter):
-        if (i % self.every == 0):
-            variables_data = algo.get_variables_data(self.ids)
-            logger.info(f"iteration={i+1}/{max_iter}")
-            for variable_id, data in variables_data.items():
-                logger.info(f"id={variable_id} v={np.mean(data['v']):.3f}")
+        if i % self.every:
+            return
+        logger.info(f"iteration={i+1}/{max_iter}")
+        for variable_id, data in algo.get_variables_data(self.ids).items():
+            logger.info(f"id={variable_id} v={np.mean(data['v']):.3f}")
 
 
-class TrackMessages(Callback):
-    """reference callbacks.py:49-60."""
+class TrackMessages(_Recorder):
+    """One row per edge and iteration with the requested message keys (reference callbacks.py:49-60)."""
 
     def __init__(self, keys=["a", "n_iter", "direction"]):
         self.keys = keys
         self.records = []
 
-    def __call__(self, algo, i, max_iter):
-        if (i == 0):
-            self.records = []
-        self.records += algo.get_edges_data(self.keys)
-
-    def get_dataframe(self):
-        return pd.DataFrame(self.records)
+    def _rows(self, algo, i):
+        return algo.get_edges_data(self.keys)
 
 
 class TrackObjective(Callback):
-    """reference callbacks.py:63-85."""
+    """Per-iteration log-partitions of the edges, the nodes and the model (reference
+    callbacks.py:63-85); the three lists accumulate over successive `iterate` calls, as there."""
 
     def __init__(self):
         self.edge_records = []
@@ -101,19 +131,16 @@ class TrackObjective(Callback):
         self.model_records = []
 
     def __call__(self, algo, i, max_iter):
-        if (i == 0):
-            self.records = []
         algo.update_objective()
         self.model_records.append(dict(A=algo.A_model, n_iter=algo.n_iter))
-        self.edge_records += algo.get_edges_data(["A", "n_iter", "direction"])
-        self.node_records += algo.get_nodes_data(["A", "n_iter"])
+        self.edge_records.extend(algo.get_edges_data(["A", "n_iter", "direction"]))
+        self.node_records.extend(algo.get_nodes_data(["A", "n_iter"]))
 
     def get_dataframe(self):
-        return (pd.DataFrame(self.edge_records), pd.DataFrame(self.node_records),
-                pd.DataFrame(self.model_records))
+        return tuple(pd.DataFrame(rows) for rows in (self.edge_records, self.node_records, self.model_records))
 
 
-class TrackOverlaps(Callback):
+class TrackOverlaps(_Recorder):
     """reference callbacks.py:165-192: m = <r, x>/N, q = <r, r>/N, Q = <x, x>/N."""
 
     def __init__(self, true_values, ids="all", every=1, verbose=False):
@@ -124,23 +151,14 @@ class TrackOverlaps(Callback):
         self.records = []
         self.verbose = verbose
 
-    def __call__(self, algo, i, max_iter):
-        if (i == 0):
-            self.records = []
-        if (i % self.every == 0):
-            variables_data = algo.get_variables_data(self.ids)
-            for variable_id, data in variables_data.items():
-                x = np.asarray(self.X_true[variable_id])
-                r = np.asarray(data["r"])
-                n = x.shape[-1] if x.ndim > 1 else x.shape[0]
-                record = dict(id=variable_id, m=(r * x).sum(-1) / n, q=(r * r).sum(-1) / n,
-                              Q=(x * x).sum(-1) / n, iter=i)
-                self.records.append(record)
-                if self.verbose:
-                    print(record)
-
-    def get_dataframe(self):
-        return pd.DataFrame(self.records)
+    def _rows(self, algo, i):
+        rows = []
+        for variable_id, data in algo.get_variables_data(self.ids).items():
+            x, r = np.asarray(self.X_true[variable_id]), np.asarray(data["r"])
+            n = x.shape[-1]
+            rows.append(dict(id=variable_id, m=(r * x).sum(-1) / n, q=(r * r).sum(-1) / n,
+                             Q=(x * x).sum(-1) / n, iter=i))
+        return rows
 
 
 def _squeeze(algo, row):
@@ -148,8 +166,8 @@ def _squeeze(algo, row):
     return float(row[0]) if not algo.batched else np.array(row)
 
 
-class TrackEvolution(Callback):
-    """reference callbacks.py:88-108."""
+class TrackEvolution(_Recorder):
+    """Posterior variance of the tracked variables per iteration (reference callbacks.py:88-108)."""
 
     def __init__(self, ids="all", every=1, verbose=False):
         self.ids = ids
@@ -158,35 +176,21 @@ class TrackEvolution(Callback):
         self.records = []
         self.verbose = verbose
 
-    def __call__(self, algo, i, max_iter):
-        if (i == 0):
-            self.records = []
-        if (i % self.every == 0):
-            variables_data = algo.get_variables_data(self.ids)
-            for variable_id, data in variables_data.items():
-                record = dict(id=variable_id, v=data["v"], iter=i)
-                self.records.append(record)
-                if self.verbose:
-                    print(record)
+    def _rows(self, algo, i):
+        return [dict(id=variable_id, v=data["v"], iter=i)
+                for variable_id, data in algo.get_variables_data(self.ids).items()]
 
     def device_replayable(self, algo):
         return True
 
-    def replay(self, algo, i, max_iter, rec):
-        if (i == 0):
-            self.records = []
-        if (i % self.every == 0):
-            for variable_id in algo.variable_ids:
-                if self.ids == "all" or variable_id in self.ids:
-                    key = "vx" if variable_id == algo.x_id else "vz"
-                    self.records.append(dict(id=variable_id, v=_squeeze(algo, rec[key][i]), iter=i))
-
-    def get_dataframe(self):
-        return pd.DataFrame(self.records)
+    def _rows_recorded(self, algo, i, rec):
+        tracked = [v for v in algo.variable_ids if self.ids == "all" or v in self.ids]
+        return [dict(id=v, v=_squeeze(algo, rec["vx" if v == algo.x_id else "vz"][i]), iter=i) for v in tracked]
 
 
-class TrackEstimate(Callback):
-    """reference callbacks.py:111-128 (needs r every iteration: slow path)."""
+class TrackEstimate(_Recorder):
+    """Posterior mean of the tracked variables per iteration (reference callbacks.py:111-128);
+    needs r on the host every iteration, hence the one-launch-per-iteration path."""
 
     def __init__(self, ids="all", every=1):
         self.ids = ids
@@ -194,20 +198,15 @@ class TrackEstimate(Callback):
         self.repr_init()
         self.records = []
 
-    def __call__(self, algo, i, max_iter):
-        if (i == 0):
-            self.records = []
-        if (i % self.every == 0):
-            variables_data = algo.get_variables_data(self.ids)
-            for variable_id, data in variables_data.items():
-                self.records.append(dict(id=variable_id, r=data["r"], iter=i))
-
-    def get_dataframe(self):
-        return pd.DataFrame(self.records)
+    def _rows(self, algo, i):
+        return [dict(id=variable_id, r=data["r"], iter=i)
+                for variable_id, data in algo.get_variables_data(self.ids).items()]
 
 
-class TrackErrors(Callback):
-    """reference callbacks.py:131-162."""
+class TrackErrors(_Recorder):
+    """Error metrics of the estimates against the true signals (reference callbacks.py:131-162;
+    like there, the metric is called as metric(estimate, truth))."""
+    store = "errors"
 
     def __init__(self, true_values, metrics=["mse"], every=1, verbose=False):
         self.ids = true_values.keys()
@@ -218,22 +217,21 @@ class TrackErrors(Callback):
         self.errors = []
         self.verbose = verbose
 
-    def __call__(self, algo, i, max_iter):
-        if (i == 0):
-            self.errors = []
-        if (i % self.every == 0):
-            variables_data = algo.get_variables_data(self.ids)
-            X_pred = {variable_id: data["r"] for variable_id, data in variables_data.items()}
-            errors = []
-            for id in self.ids:
-                error = dict(id=id, iter=i)
-                for metric in self.metrics:
-                    func = METRICS.get(metric)
-                    error[metric] = func(X_pred[id], self.X_true[id])
-                errors.append(error)
-            if self.verbose:
-                print(errors)
-            self.errors += errors
+    def _rows(self, algo, i):
+        estimates = algo.get_variables_data(self.ids)
+        return [dict(id=vid, iter=i, **{m: METRICS.get(m)(estimates[vid]["r"], self.X_true[vid]) for m in self.metrics})
+                for vid in self.ids]
+
+    def _visit(self, i, rows_of):
+        # the reference prints the whole list of an iteration at once
+        verbose, self.verbose = self.verbose, False
+        try:
+            before = 0 if i == 0 else len(self.errors)
+            super()._visit(i, rows_of)
+        finally:
+            self.verbose = verbose
+        if verbose and i % self.every == 0:
+            print(self.errors[before:])
 
     def device_replayable(self, algo):
         return (list(self.ids) == [algo.x_id]
@@ -242,28 +240,30 @@ class TrackErrors(Callback):
     def device_config(self, cfg):
         cfg["x_true"] = self.X_true[list(self.ids)[0]]
 
-    def replay(self, algo, i, max_iter, rec):
-        if (i == 0):
-            self.errors = []
-        if (i % self.every == 0):
-            error = dict(id=algo.x_id, iter=i)
-            for metric in self.metrics:
-                error[metric] = _squeeze(algo, rec["mse" if metric == "mse" else "smse"][i])
-            self.errors.append(error)
-
-    def get_dataframe(self):
-        return pd.DataFrame(self.errors)
+    def _rows_recorded(self, algo, i, rec):
+        return [dict(id=algo.x_id, iter=i,
+                     **{m: _squeeze(algo, rec["mse" if m == "mse" else "smse"][i]) for m in self.metrics})]
 
 
 def norm(x):
     return np.sqrt(np.mean(x**2))
 
 
+def _rms(x):
+    """Root mean square over the components of every instance (last axis)."""
+    return np.sqrt(np.mean(np.square(x), axis=-1))
+
+
 class EarlyStoppingEP(Callback):
     """reference callbacks.py:250-286: stop when the relative change of every
     tracked estimate, rms(r_new - r_old) / rms(r_new), is below `tol`; if after
     `wait_increase` iterations it exceeds `max_increase`, restore the previous
-    messages and stop."""
+    messages and stop.
+
+    For a batched model the tolerance is taken per instance, like in the device sweep.  On the
+    device-replayable path every instance stops (or is rolled back) on its own; as a plain
+    per-iteration callback it can only stop the whole `iterate` call, which it does once EVERY
+    instance is below `tol` -- or as soon as ONE diverges, rolling all of them back."""
 
     def __init__(self, ids="all", tol=1e-6, wait_increase=5, max_increase=0.2):
         self.ids = ids
@@ -274,17 +274,17 @@ class EarlyStoppingEP(Callback):
         self.old_rs = None
 
     def __call__(self, algo, i, max_iter):
-        if (i == 0):
+        if i == 0:
             self.old_rs = None
-        variables_data = algo.get_variables_data(self.ids)
-        new_rs = [data["r"] for variable_id, data in variables_data.items()]
+        new_rs = [np.asarray(data["r"]) for data in algo.get_variables_data(self.ids).values()]
         if self.old_rs:
-            tols = [norm(new_r - old_r) / norm(new_r) for old_r, new_r in zip(self.old_rs, new_rs)]
-            if max(tols) < self.tol:
+            # worst tracked variable of the worst instance
+            change = max(float(np.max(_rms(new - old) / _rms(new))) for old, new in zip(self.old_rs, new_rs))
+            if change < self.tol:
                 logger.info(f"early stopping all tolerances (on r) are below tol={self.tol:.2e}")
                 return True
-            if i > self.wait_increase and max(tols) > self.max_increase:
-                logger.info(f"increase={max(tols)} above max_increase={self.max_increase:.2e}")
+            if i > self.wait_increase and change > self.max_increase:
+                logger.info(f"increase={change} above max_increase={self.max_increase:.2e}")
                 logger.info("restoring old message dag")
                 algo.reset_message_dag(self.old_message_dag)
                 return True
