@@ -470,9 +470,12 @@ def _jacobi_sweep(self, A, strideA, B, n_rows, ld, Swork, Jwork, rot_flag, offma
                 X = Ab[idx]
                 S = X @ X.T
                 d = np.sqrt(np.abs(np.diag(S)))
+                live = d > 1e-13 * d.max()                 # the kernel's rule: noise rows are left out
                 with np.errstate(all="ignore"):
                     Cs = np.abs(S) / np.outer(d, d)
                 Cs[~np.isfinite(Cs)] = 0.0
+                Cs[~live, :] = 0.0
+                Cs[:, ~live] = 0.0
                 np.fill_diagonal(Cs, 0.0)
                 off = Cs.max()
                 worst = max(worst, off)

@@ -569,18 +569,49 @@ def test_host_path_then_device_warm_start(ad):
     assert_allclose(d["x"]["v"], ad[name + "_vx"][-1], rtol=1e-9)
 
 
-def test_adaptive_damping_rejects_batches():
+@pytest.mark.parametrize("options", [dict(damping="adaptive"), dict(damping=0.2, update_dA=True)])
+def test_adaptive_damping_batched_equals_per_instance(options):
+    """damping="adaptive" / update_dA on a BATCH (reference message_passing.py:129-185 has no batches):
+    every instance takes its own step-halving decisions, so the batched run reproduces the
+    per-instance runs -- posteriors, messages, and the accepted step size beta of every edge."""
     from tramp_b200.priors import GaussBernoulliPrior
-    from tramp_b200.likelihoods import GaussianLikelihood
+    from tramp_b200.likelihoods import SgnLikelihood
     from tramp_b200.channels import LinearChannel
     from tramp_b200.variables import SISOVariable as V
-    from tramp_b200.algos import ExpectationPropagation
-    rng = np.random.RandomState(0)
-    W, y = rng.randn(3, 8, 16), rng.randn(3, 8)
-    model = (GaussBernoulliPrior(size=16, batch=3) @ V("x") @ LinearChannel(W) @ V("z")
-             @ GaussianLikelihood(y=y, var=0.1)).to_model()
-    with pytest.raises(NotImplementedError):
-        ExpectationPropagation(model).iterate(max_iter=2, damping="adaptive")
+    from tramp_b200.algos import ExpectationPropagation, PassCallback
+    rng = np.random.RandomState(5)
+    B, N, M, n_iter = 3, 40, 60, 6
+    W = rng.randn(B, M, N) / np.sqrt(N)
+    x = rng.randn(B, N) * (rng.rand(B, N) < 0.3)
+    y = np.sign(np.einsum("bmn,bn->bm", W, x))
+
+    def run(Wb, yb, batch):
+        model = (GaussBernoulliPrior(size=N, rho=0.3, batch=batch) @ V("x") @ LinearChannel(Wb) @ V("z")
+                 @ SgnLikelihood(y=yb)).to_model()
+        ep = ExpectationPropagation(model)
+        ep.iterate(max_iter=n_iter, callback=PassCallback(), **options)
+        return ep
+    whole = run(W, y, B)
+    assert whole.n_iter == n_iter and whole.n_iter_per_instance.tolist() == [n_iter] * B
+    d_all = whole.get_variables_data()
+    betas = []
+    for b in range(B):
+        one = run(W[b], y[b], None)
+        d = one.get_variables_data()
+        for vid in ("x", "z"):
+            assert_allclose(d_all[vid]["r"][b], d[vid]["r"], rtol=1e-10, atol=1e-12)
+            assert_allclose(d_all[vid]["v"][b], d[vid]["v"], rtol=1e-10)
+        for k in range(1, 9):
+            e_all, e_one = whole._host.edges[f"e{k}"], one._host.edges[f"e{k}"]
+            assert_allclose(e_all["a"][b], e_one["a"], rtol=1e-10)
+            assert_allclose(e_all["b"][b], e_one["b"], rtol=1e-10, atol=1e-12)
+            assert_allclose(np.asarray(e_all["dA"])[b] if np.ndim(e_all["dA"]) else e_all["dA"], e_one["dA"],
+                            rtol=1e-7, atol=1e-9)
+            if options["damping"] == "adaptive":
+                assert e_all["beta"][b] == e_one["beta"]
+                betas.append(e_one["beta"])
+    if options["damping"] == "adaptive":
+        assert min(betas) < 1.0 <= max(betas)       # the instances did take different step sizes
 
 
 def test_track_overlaps_and_objective_on_device_path(sw):

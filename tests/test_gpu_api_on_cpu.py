@@ -56,8 +56,9 @@ def test_host_path_then_device_warm_start(emulated_device, ad):  # noqa: F811
     G.test_host_path_then_device_warm_start(ad)
 
 
-def test_adaptive_damping_rejects_batches(emulated_device):  # noqa: F811
-    G.test_adaptive_damping_rejects_batches()
+@pytest.mark.parametrize("options", [dict(damping="adaptive"), dict(damping=0.2, update_dA=True)])
+def test_adaptive_damping_batched_equals_per_instance(emulated_device, options):  # noqa: F811
+    G.test_adaptive_damping_batched_equals_per_instance(options)
 
 
 @pytest.mark.parametrize("idx", range(9))

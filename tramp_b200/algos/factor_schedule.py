@@ -7,8 +7,13 @@ sweep of `trb_sweep_run`.  They take this path instead: the schedule of
 :249-269 is walked node by node on the host, and every factor evaluation
 (`compute_*_message`, `compute_log_partition`) still runs in the CUDA kernels
 through the factor API of tramp_b200.priors / likelihoods / channels.  Only
-the per-message decisions (`dA >= 0`, NaN checks) are host arithmetic on two
-scalars.  One instance at a time (un-batched models).
+the per-message decisions (`dA >= 0`, NaN checks) are host arithmetic on a few
+scalars per instance.
+
+Batched models run all their instances through every factor evaluation at once
+(`a` is then an array [B], `b` an array [B, n]); the decisions stay PER INSTANCE:
+each instance halves its own step until its own objective stops decreasing, so a
+batched run equals the per-instance runs.
 
 Chain and edge names:  prior -e1-> x -e2-> lin -e3-> z -e4-> lik,
 lik -e5-> z -e6-> lin -e7-> x -e8-> prior.
@@ -25,6 +30,12 @@ IN_EDGES = {"prior": ("e8",), "x": ("e1", "e7"), "lin": ("e2", "e6"), "z": ("e3"
 FORWARD_ORDER = ("prior", "x", "lin", "z", "lik")
 VARIABLES = ("x", "z")
 N_HALVINGS = 10   # message_passing.py:168
+
+
+def _per_instance(mask, like):
+    """Boolean [B] (or scalar) mask shaped to select whole rows of `like`."""
+    mask = np.asarray(mask)
+    return mask[..., None] if np.ndim(like) > mask.ndim else mask
 
 
 class FactorSchedule:
@@ -81,23 +92,37 @@ class FactorSchedule:
         return self.objective_around(name, data) - self.objective_around(name)
 
     def adaptive_damping(self, name, data):
-        """:151-185: halve the step until the local objective does not decrease."""
+        """:151-185: halve the step until the local objective does not decrease -- every
+        instance of a batch on its own (all of them are evaluated at every trial step; an
+        instance keeps the first step size that its own objective accepts)."""
         if self.mp.n_iter == 0:
             return data
         old = self.edges[name]
         step = {k: data[k] - old[k] for k in ("a", "b")}
         A_old = self.objective_around(name)
-        new = dict(data)
+        accepted = np.zeros(np.shape(A_old), dtype=bool)
+        # not accepted after N_HALVINGS trials: the old message, dA = 0, beta = 0 (:182-185)
+        kept = {k: np.array(old[k], dtype=float) for k in ("a", "b")}
+        dA_kept, beta_kept = np.zeros(np.shape(A_old)), np.zeros(np.shape(A_old))
         for n in range(N_HALVINGS):
             beta = 1 / 2**n
+            trial = dict(data)
             for k in ("a", "b"):
-                new[k] = old[k] + beta * step[k]
-            dA = self.objective_around(name, new) - A_old
-            if dA >= 0:
-                new.update(dA=dA, beta=beta)
-                return new
-        new = dict(old)
-        new.update(dA=0, beta=0)
+                trial[k] = old[k] + beta * step[k]
+            dA = self.objective_around(name, trial) - A_old
+            take = np.logical_and(np.asarray(dA) >= 0, ~accepted)       # NaN never passes, as in the reference
+            for k in ("a", "b"):
+                kept[k] = np.where(_per_instance(take, kept[k]), trial[k], kept[k])
+            dA_kept = np.where(take, dA, dA_kept)
+            beta_kept = np.where(take, beta, beta_kept)
+            accepted = accepted | take
+            if accepted.all():
+                break
+        new = dict(data)
+        if self.mp.batched:
+            new.update(a=kept["a"], b=kept["b"], dA=dA_kept, beta=beta_kept)
+        else:
+            new.update(a=float(kept["a"]), b=kept["b"], dA=float(dA_kept), beta=float(beta_kept))
         return new
 
     def constant_damping(self, name, data):
@@ -116,11 +141,11 @@ class FactorSchedule:
         """:187-209."""
         s, t = EDGE_ENDS[name]
         sid, tid = self.nodes[s].id, self.nodes[t].id
-        if np.isnan(data["a"]):
+        if np.any(np.isnan(data["a"])):
             logger.warning("restoring old message dag")
             self.restore_state(self.old)
             raise ValueError(f"{sid}->{tid} a is nan")
-        if data["a"] < 0:
+        if np.any(np.asarray(data["a"]) < 0):
             logger.warning(f"{sid}->{tid} negative a {data['a']}")
         if np.isnan(data["b"]).any():
             logger.warning("restoring old message dag")
@@ -133,7 +158,8 @@ class FactorSchedule:
             name = next(k for k, (s, t) in EDGE_ENDS.items()
                         if self.nodes[s] is source and self.nodes[t] is target)
             data = dict(data)
-            data["a"] = float(np.asarray(data["a"]))
+            data["a"] = (np.asarray(data["a"], dtype=np.float64).reshape(mp.B) if mp.batched
+                         else float(np.asarray(data["a"])))
             data["b"] = np.asarray(data["b"], dtype=np.float64)
             self.check(name, data)
             if mp.damping:

@@ -499,8 +499,6 @@ class MessagePassing():
         node-by-node loop on the host, every factor evaluated by the CUDA kernels
         through the factor API (algos/factor_schedule.py)."""
         from .factor_schedule import FactorSchedule
-        if self.batched:
-            raise NotImplementedError("adaptive damping / update_dA run one instance at a time")
         if getattr(self.linear, "group", None) is not None:
             raise NotImplementedError("adaptive damping / update_dA on a row-sharded operator")
         st = self._state
@@ -512,13 +510,15 @@ class MessagePassing():
             edges = {}
             src = {"e1": "b1", "e2": "b1", "e3": "b3", "e4": "b3", "e5": "b5", "e6": "b6_init",
                    "e7": "b7", "e8": "b8_init"}
-            a_all = st["edge_a"][:, 0].cpu().numpy()
+            a_all = st["edge_a"].cpu().numpy()
             for name, role, direction, idx in EDGES:
                 t = st.get(src[name])
                 if t is None:
                     t = st["b5" if name == "e6" else "b7"]
                 n = self.N if role == "x" else self.M
-                edges[name] = dict(a=float(a_all[idx]), b=t[0, :n].cpu().numpy().copy(),
+                b_host = t[:, :n].cpu().numpy().copy()
+                edges[name] = dict(a=a_all[idx].copy() if self.batched else float(a_all[idx, 0]),
+                                   b=b_host if self.batched else b_host[0],
                                    direction=direction, n_iter=0,
                                    damping=self.damp.get(name) or None)
             host = FactorSchedule(self, edges)
@@ -541,15 +541,16 @@ class MessagePassing():
         st = self._state
         t = ops.torch()
         e = host.edges
-        st["edge_a"][:, 0] = t.as_tensor([e[n]["a"] for n, _, _, _ in EDGES], dtype=t.float64)
+        st["edge_a"].copy_(t.as_tensor(np.stack([np.broadcast_to(np.asarray(e[n]["a"], dtype=np.float64), (self.B,))
+                                                  for n, _, _, _ in EDGES]), dtype=t.float64))
         for buf, name, n in (("b1", "e1", self.N), ("b3", "e3", self.M), ("b5", "e5", self.M),
                              ("b7", "e7", self.N)):
-            st[buf][0, :n] = ops.to_dev(e[name]["b"])
+            st[buf][:, :n] = ops.to_dev(np.asarray(e[name]["b"], dtype=np.float64).reshape(self.B, n))
         for role, n, rk, vk in (("x", self.N, "rx", "vx"), ("z", self.M, "rz", "vz")):
             d = host.variables[role]
             if d:
-                st[rk][0, :n] = ops.to_dev(np.asarray(d["r"], dtype=np.float64))
-                st[vk][0] = float(d["v"])
+                st[rk][:, :n] = ops.to_dev(np.asarray(d["r"], dtype=np.float64).reshape(self.B, n))
+                st[vk].copy_(ops.to_dev(np.broadcast_to(np.asarray(d["v"], dtype=np.float64), (self.B,)).copy()))
 
     def _leave_host_path(self, host):
         """Warm start of the device sweep from messages the host path produced: the
@@ -557,7 +558,7 @@ class MessagePassing():
         unless adaptive damping held one of them back)."""
         e = host.edges
         for cp, srcn in (("e2", "e1"), ("e4", "e3"), ("e6", "e5"), ("e8", "e7")):
-            if e[cp]["a"] != e[srcn]["a"] or not np.array_equal(e[cp]["b"], e[srcn]["b"]):
+            if np.any(e[cp]["a"] != e[srcn]["a"]) or not np.array_equal(e[cp]["b"], e[srcn]["b"]):
                 raise NotImplementedError(
                     f"device-path warm start needs {cp} == {srcn}; adaptive damping left them different")
         self._host_to_device(host)

@@ -92,15 +92,21 @@ class Variable(ReprMixin):
         return a_hat, b_hat
 
     def posterior_rv(self, message):
-        """reference base.py:157-161."""
+        """reference base.py:157-161 (a batch: one precision per instance, a_hat [B], b_hat [B, n])."""
         a_hat, b_hat = self.posterior_ab(message)
-        return b_hat / a_hat, 1. / a_hat
+        a_col = np.asarray(a_hat)[..., None] if np.ndim(a_hat) and np.ndim(b_hat) > np.ndim(a_hat) else a_hat
+        return b_hat / a_col, 1. / a_hat
 
     def compute_log_partition(self, ax, bx):
-        """reference base.py:146-150 (a SUM over components; inf if ax <= 0)."""
-        if ax <= 0:
-            return np.inf
-        return 0.5 * np.sum(bx**2 / ax + np.log(2 * np.pi / ax))
+        """reference base.py:146-150 (a SUM over components; inf if ax <= 0), per instance of a batch."""
+        if np.ndim(ax) == 0:
+            if ax <= 0:
+                return np.inf
+            return 0.5 * np.sum(bx**2 / ax + np.log(2 * np.pi / ax))
+        ax = np.asarray(ax, dtype=float)
+        with np.errstate(all="ignore"):
+            logZ = 0.5 * np.sum(bx**2 / ax[:, None] + np.log(2 * np.pi / ax[:, None]), axis=-1)
+        return np.where(ax <= 0, np.inf, logZ)
 
     def log_partition(self, message):
         ax, bx = self.posterior_ab(message)

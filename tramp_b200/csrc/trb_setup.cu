@@ -229,8 +229,14 @@ k_jacobi_eig(const double* __restrict__ S, int zsplit, double* __restrict__ Jm, 
   // largest |cos| between two rows
   __shared__ double sinv[kPV];
   if (tid < kPV) {
+    // rows whose norm is below 1e-13 of the pair's largest are rounding noise (padding rows, the
+    // null directions of a rank-deficient matrix): their direction means nothing and they are left
+    // out of the convergence measure
     const double d = sS[tid][tid];
-    sinv[tid] = (d > 0.0) ? rsqrt(d) : 0.0;
+    double dmax = d;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) dmax = fmax(dmax, __shfl_xor_sync(0xffffffffu, dmax, o));
+    sinv[tid] = (d > 1e-26 * dmax && d > 0.0) ? rsqrt(d) : 0.0;
   }
   __syncthreads();
   double off = 0.0;
