@@ -334,6 +334,14 @@ typedef struct {
    * not sharded. */
   struct trb_comm* comm;
   const double* s_full; const double* s2_full;
+  /* Which early-stopping test es_tol / es_max_increase / es_wait_increase drive:
+   *  0  EarlyStoppingEP (callbacks.py:250-286): relative change of the posterior means;
+   *  1  EarlyStopping (callbacks.py:195-243): absolute change of the posterior variances
+   *     of the tracked variables, stop also when one drops below es_min_variance; a NaN
+   *     variance or an increase above es_max_increase rolls back.  Needs the snapshot
+   *     buffers (the previous variances are read from snap_vx / snap_vz). */
+  int32_t es_mode; int32_t _pad_es;
+  double es_min_variance;
 } trb_sweep;
 
 /* Stages of one iteration, in order (trb_sweep_run loops over them).  Back ends

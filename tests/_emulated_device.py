@@ -241,7 +241,21 @@ def _sweep_run(self, sw_ref, it0, n_iter, fresh, stream):
                         if rec["smse"] is not None:
                             rec["smse"][it, b] = min(mse, np.mean((vec["rx"][b, :N] + xt[b, :N])**2))
                 tol = np.nan
-                if it > 0:
+                if getattr(sw, "es_mode", 0) == 1 and sw.es_tol >= 0:
+                    # EarlyStopping on the variances (early_stopping_variance, trb_common.cuh)
+                    new_vs = [v_ for bit, v_ in ((1, vx[b]), (2, vz[b])) if vars_ & bit]
+                    old_vs = [v_ for bit, v_ in ((1, old_v[0]), (2, old_v[1])) if vars_ & bit]
+                    if any(v_ < sw.es_min_variance for v_ in new_vs):
+                        stop = L.FLAG_CONVERGED
+                    elif any(np.isnan(v_) for v_ in new_vs):
+                        stop = L.FLAG_DIVERGED
+                    elif it > 0:
+                        tol = max(abs(o - n_) for o, n_ in zip(old_vs, new_vs))
+                        if tol < sw.es_tol:
+                            stop = L.FLAG_CONVERGED
+                        elif it > sw.es_wait_increase and max(n_ - o for o, n_ in zip(old_vs, new_vs)) > sw.es_max_increase:
+                            stop = L.FLAG_DIVERGED
+                elif it > 0:
                     with np.errstate(all="ignore"):
                         tx_ = _rms(vec["rx"][b, :N] - old["rx"][:N]) / _rms(vec["rx"][b, :N])
                         tz_ = _rms(vec["rz"][b, :M] - old["rz"][:M]) / _rms(vec["rz"][b, :M])

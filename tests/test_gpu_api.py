@@ -407,6 +407,50 @@ def test_beliefs_against_reference(golden_dir):
             assert_allclose(got[ok], ref[ok], rtol=1e-9, atol=1e-13, err_msg=f"truncated.{name} case {i}")
 
 
+def test_linear_channel_reference_signature_corners():
+    """The corners of the reference constructor / factor API (channels/linear/linear_channel.py):
+    `precompute_svd=False` (:43-45, :79-82: dense solve per call -- same numbers), `bz` of shape
+    [Nz, k] with one scalar precision (:75-76), and the free energies of a batched channel (:134-143)."""
+    from tramp_b200.channels import LinearChannel
+    rng = np.random.RandomState(9)
+    Nx, Nz, k = 30, 20, 3
+    W = rng.randn(Nx, Nz) / np.sqrt(Nz)
+    az, ax = 0.7, 2.5
+    bz, bx = rng.randn(Nz), rng.randn(Nx)
+    lazy, eager = LinearChannel(W, precompute_svd=False), LinearChannel(W)
+    assert lazy.precompute_svd is False and "precompute_svd=False" in repr(lazy)
+    C = W.T @ W
+    rz_ref = np.linalg.solve(az * np.identity(Nz) + ax * C, bz + W.T @ bx)            # reference :79-82
+    for ch in (lazy, eager):
+        assert_allclose(ch.compute_backward_mean(az, bz, ax, bx), rz_ref, rtol=1e-11, atol=1e-13)
+        assert_allclose(ch.compute_forward_mean(az, bz, ax, bx), W @ rz_ref, rtol=1e-11, atol=1e-13)
+    assert_allclose(np.sort(lazy.spectrum), np.linalg.eigvalsh(C), rtol=1e-11, atol=1e-14)
+    assert lazy.compute_backward_variance(az, ax) == eager.compute_backward_variance(az, ax)
+    # a block of k columns, one scalar az / ax (reference :75-76)
+    Bz, Bx = rng.randn(Nz, k), rng.randn(Nx, k)
+    Rz = eager.compute_backward_mean(az, Bz, ax, Bx)
+    assert Rz.shape == (Nz, k)
+    assert_allclose(Rz, np.linalg.solve(az * np.identity(Nz) + ax * C, Bz + W.T @ Bx), rtol=1e-11, atol=1e-13)
+    Rx, vx = eager.compute_forward_posterior(az, Bz, ax, Bx)
+    assert Rx.shape == (Nx, k) and np.ndim(vx) == 0
+    assert_allclose(Rx, W @ Rz, rtol=1e-11, atol=1e-13)
+    assert vx == eager.compute_forward_variance(az, ax)
+    with pytest.raises(ValueError, match="one scalar"):
+        eager.compute_backward_mean(np.array([0.5, 0.6, 0.7]), Bz, ax, Bx)
+    # batched channel: one mutual information / free energy per instance
+    Wb = rng.randn(3, Nx, Nz) / np.sqrt(Nz)
+    batch = LinearChannel(Wb)
+    I = batch.compute_mutual_information(az, ax, tau_z=1.3)
+    A = batch.compute_free_energy(az, ax, tau_z=1.3)
+    assert I.shape == (3,) and A.shape == (3,)
+    for b in range(3):
+        one = LinearChannel(Wb[b])
+        spectrum = np.linalg.eigvalsh(Wb[b].T @ Wb[b])
+        assert_allclose(I[b], np.mean(0.5 * np.log((az + ax * spectrum) * 1.3)), rtol=1e-11)    # reference :134-137
+        assert_allclose(I[b], one.compute_mutual_information(az, ax, 1.3), rtol=1e-13)
+        assert_allclose(A[b], one.compute_free_energy(az, ax, 1.3), rtol=1e-13)
+
+
 def test_linear_channel_factor_api(golden_dir):
     """LinearChannel.compute_*_posterior / log_partition against the reference."""
     from tramp_b200.channels import LinearChannel
@@ -612,6 +656,36 @@ def test_adaptive_damping_batched_equals_per_instance(options):
                 betas.append(e_one["beta"])
     if options["damping"] == "adaptive":
         assert min(betas) < 1.0 <= max(betas)       # the instances did take different step sizes
+
+
+@pytest.mark.parametrize("idx", [0, 1, 4])
+def test_variance_early_stopping_inside_the_sweep(sw, idx):
+    """`EarlyStopping` (reference callbacks.py:195-243: absolute change of the posterior variances)
+    as the EP callback: the test runs in the sweep kernels (trb_sweep.es_mode = 1, no host round
+    trip) and stops at the iteration, and in the state, of the same callback run the reference's
+    way -- called on the host after every iteration."""
+    from tramp_b200.algos import ExpectationPropagation, EarlyStopping, TrackEvolution, JoinCallback
+    cfg = _configs(sw)[idx]
+    name = cfg["name"]
+    tol = 1e-5
+    runs = []
+    for on_device in (True, False):
+        ep = ExpectationPropagation(_build(cfg, sw, name))
+        evo = TrackEvolution()
+        stopper = EarlyStopping(tol=tol)
+        members = [evo, stopper] if on_device else [evo, stopper, lambda algo, i, max_iter: False]
+        cb = JoinCallback(members)
+        assert cb.device_replayable(ep) == on_device
+        ep.iterate(max_iter=200, callback=cb, damping=cfg["damping"])
+        runs.append((ep.n_iter, ep.get_variables_data(), evo.get_dataframe()))
+    (n_dev, d_dev, df_dev), (n_host, d_host, df_host) = runs
+    assert 2 < n_dev == n_host < 200
+    for vid in ("x", "z"):
+        assert_allclose(d_dev[vid]["r"], d_host[vid]["r"], rtol=1e-12, atol=1e-14)
+        assert_allclose(d_dev[vid]["v"], d_host[vid]["v"], rtol=1e-12)
+        v = df_dev[df_dev.id == vid].v.values
+        assert len(v) == n_dev and abs(v[-1] - v[-2]) < tol
+        assert_allclose(v, df_host[df_host.id == vid].v.values, rtol=1e-12)
 
 
 def test_track_overlaps_and_objective_on_device_path(sw):

@@ -43,6 +43,15 @@ def test_beliefs_against_reference(emulated_device, golden_dir):  # noqa: F811
     G.test_beliefs_against_reference(golden_dir)
 
 
+@pytest.mark.parametrize("idx", [0, 1, 4])
+def test_variance_early_stopping_inside_the_sweep(emulated_device, sw, idx):  # noqa: F811
+    G.test_variance_early_stopping_inside_the_sweep(sw, idx)
+
+
+def test_linear_channel_reference_signature_corners(emulated_device):  # noqa: F811
+    G.test_linear_channel_reference_signature_corners()
+
+
 def test_linear_channel_factor_api(emulated_device, golden_dir):  # noqa: F811
     G.test_linear_channel_factor_api(golden_dir)
 

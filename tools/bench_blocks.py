@@ -148,6 +148,18 @@ def setup_block(N, M, K, iters, seed0, parity_instances=8, rank=0, world=1, svd_
         "e2e_incl_setup": {"value": world * K * iters / total, "unit": "instance-iterations/s",
                            "h2d_bytes": int(W_host.numel() + y_host.numel() + x_host.numel()) * 8},
     }
+    if rank == 0:
+        # the library route it replaces, on the same matrices (round-1 baseline: W W^T, cuSOLVER syevd
+        # through torch.linalg.eigh, V = W^T U / s), warm
+        k_lib = min(4, K)
+        W_lib = W_host[:k_lib].to("cuda")
+        lc.thin_svd_device(W_lib[:1], "gram")
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        lc.thin_svd_device(W_lib, "gram")
+        torch.cuda.synchronize()
+        block["library_gram_eigh_ms_per_instance"] = 1e3 * (time.perf_counter() - t0) / k_lib
+        del W_lib
     if rank == 0 and parity_instances > 0:
         P = min(parity_instances, K)
         t0 = time.perf_counter()

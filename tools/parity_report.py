@@ -21,7 +21,7 @@ for cfg in _configs(sw):
         mse = np.array([e["mse"] for e in track.errors]); df = evo.get_dataframe()
         d = ep.get_variables_data()
         rel = lambda a, b: float(np.max(np.abs(a - b) / np.maximum(np.abs(b), 1e-300)))
-        relmax = lambda a, b: float(np.max(np.abs(a - b)) / np.max(np.abs(b)))
+        relmax = lambda a, b: float(np.max(np.abs(a - b)) / (np.max(np.abs(b)) or 1.0))   # an all-zero reference: absolute
         x = sw[name + "_x"]
         r = dict(mse=rel(mse, sw[name + "_mse"]),
                  mse_cond=float(np.max(np.abs(mse - sw[name + "_mse"]) / (2 * np.sqrt(sw[name + "_mse"] * np.mean(x**2))))),

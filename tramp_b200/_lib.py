@@ -51,6 +51,7 @@ class TrbSweep(C.Structure):
         ("R_total", C.c_int32), ("schedule", C.c_int32),
         ("ty", C.c_void_p),
         ("comm", C.c_void_p), ("s_full", C.c_void_p), ("s2_full", C.c_void_p),
+        ("es_mode", C.c_int32), ("_pad_es", C.c_int32), ("es_min_variance", C.c_double),
     ]
 
 

@@ -317,7 +317,8 @@ class EarlyStopping(Callback):
     or an increase above `max_increase` after `wait_increase` iterations,
     restores the previous messages and stops.  This is State Evolution's default
     stopper; inside `StateEvolution.iterate` the test runs in the kernel
-    (`trb_se_run`), for EP it is an ordinary per-iteration callback."""
+    (`trb_se_run`), inside `ExpectationPropagation.iterate` in the sweep kernels
+    (`trb_sweep.es_mode = 1`), per instance."""
 
     def __init__(self, ids="all", tol=1e-6, min_variance=-1, wait_increase=5, max_increase=0.2):
         self.ids = ids
@@ -360,8 +361,9 @@ class EarlyStopping(Callback):
     _var_mask = EarlyStoppingEP._var_mask
 
     def device_replayable(self, algo):
-        # only the State-Evolution kernel implements the variance test
-        return getattr(algo, "message_keys", None) == ["a"] and self._var_mask(algo) is not None
+        # the State-Evolution kernel and (trb_sweep.es_mode = 1) the EP sweep kernels
+        # implement the variance test
+        return self._var_mask(algo) is not None
 
     def device_config(self, cfg):
         cfg["early_stopping"] = self

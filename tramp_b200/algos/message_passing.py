@@ -263,6 +263,9 @@ class MessagePassing():
         if early is not None:
             sw.es_tol, sw.es_max_increase = early.tol, early.max_increase
             sw.es_wait_increase, sw.es_vars = early.wait_increase, early._var_mask(self)
+            # EarlyStopping (variances) or EarlyStoppingEP (means): trb_sweep.es_mode
+            sw.es_mode = 1 if hasattr(early, "min_variance") else 0
+            sw.es_min_variance = getattr(early, "min_variance", -1.0)
         else:
             sw.es_tol, sw.es_max_increase, sw.es_wait_increase, sw.es_vars = -1.0, 0.0, 0, 3
         sw.gemv_impl = 3 if self.backend == "gemm" else (self.gemv_impl or 2)

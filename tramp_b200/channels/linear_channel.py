@@ -190,9 +190,14 @@ class LinearChannel(Channel):
     ----------
     - W: array of shape (Nx, Nz), or (B, Nx, Nz) for B independent instances
       (numpy array or device tensor)
-    - precompute_svd: kept for signature compatibility; the SVD form is the
-      only one implemented (the reference's `False` branch solves a dense
-      system per call and is not on the benchmarked path)
+    - precompute_svd: the reference's `False` branch keeps C = W^T W and solves the dense system
+      (az I + ax C) rz = bz + W^T bx at every call (:43-45, :79-82); the thin-SVD operators give the
+      same rz (it IS that solve, diagonalised), so both values take the same kernels here and the
+      flag only records the caller's choice.  The factorisation is lazy either way (first use).
+      One deliberate difference: for Nx < Nz the reference's `False` branch takes `singular` from the
+      ASCENDING eigenvalues of C (`eigvalsh`, :45-46), i.e. the rank smallest ones including the
+      Nz - Nx zeros, which makes its variances inconsistent with its own means; here `singular`
+      always holds the rank non-zero eigenvalues.
     - name: str, name of weight matrix W for display
     - svd_method: "auto" | "jacobi" | "jacobi_direct" | "svd" | "gram" (extension, see
       thin_svd_device; "auto" = the hand-written block-Jacobi set-up)
@@ -204,8 +209,6 @@ class LinearChannel(Channel):
         self.Nz = int(W.shape[-1])
         self.precompute_svd = precompute_svd
         self.repr_init()
-        if not precompute_svd:
-            raise NotImplementedError("LinearChannel(precompute_svd=False) is not on the EP hot path")
         self.batch = int(W.shape[0]) if len(W.shape) == 3 else None
         self.group = None
         self.W = W if keep_W else None
@@ -351,10 +354,30 @@ class LinearChannel(Channel):
             raise ValueError("bz and bx disagree on the batch size")
         return az_arg, ax_arg
 
+    def _column_block(self, bz, bx):
+        """reference :75-76: `bz` of shape [Nz, k] (and `bx` [Nx, k]) is a block of k right-hand sides
+        for ONE channel and ONE pair of scalar precisions -- not a batch of instances.  True for a
+        2-D `bz` whose FIRST axis is Nz when this channel is un-batched (a batch of instances is
+        [B, Nz]; a square [Nz, Nz] block is read as columns, like the reference would)."""
+        return (self.batch is None and np.ndim(bz) == 2 and np.shape(bz)[0] == self.Nz
+                and np.ndim(bx) == 2 and np.shape(bx)[0] == self.Nx and np.shape(bx)[1] == np.shape(bz)[1])
+
     def _means(self, az, bz, ax, bx, want):
         if getattr(self, "group", None) is not None:
             raise NotImplementedError("the factor-level API of a row-sharded LinearChannel is not "
                                       "available; run it through ExpectationPropagation")
+        if self._column_block(bz, bx):
+            if np.ndim(az) or np.ndim(ax):
+                raise ValueError("a block of columns bz [Nz, k] shares one scalar az and one scalar ax")
+            tr = (lambda v: v.t().contiguous()) if ops.is_tensor(bz) else (lambda v: np.ascontiguousarray(np.asarray(v).T))
+            out = self._means(az, tr(bz), ax, tr(bx), want)          # k rows through the shared operator
+            for key in ("rz", "rx"):
+                if key in out:
+                    out[key] = tr(out[key])
+            for key in ("vz", "vx"):                                  # one scalar for the block, as in the reference
+                if key in out:
+                    out[key] = out[key][0] if ops.is_tensor(out[key]) else float(np.asarray(out[key]).reshape(-1)[0])
+            return out
         zarg, xarg = self._args(az, bz, ax, bx)
         B = zarg.B
         bz_d = ops.padded(zarg.b[:, :self.Nz], self.ldn)
@@ -456,13 +479,17 @@ class LinearChannel(Channel):
 
     def compute_mutual_information(self, az, ax, tau_z):
         """mean over the Nz eigenvalues of 0.5 log((az + ax spectrum) tau_z) (:134-137);
-        cold path, reduced on the device copy of the spectrum."""
+        cold path, reduced on the device copy of the spectrum.  A batched channel returns one
+        value per instance (az, ax, tau_z scalars or arrays [B])."""
         self._setup()
         t = ops.torch()
-        if self.batch is not None:
-            raise NotImplementedError("free energies of a batched LinearChannel are not implemented")
-        logs = t.log((az + ax * self.s2[0]) * tau_z).sum() + (self.Nz - self.R) * np.log(az * tau_z)
-        return float(0.5 * logs.item() / self.Nz)
+        B = self.s2.shape[0]
+        col = lambda v: ops.to_dev(np.broadcast_to(np.asarray(v, dtype=float), (B,)).copy())   # noqa: E731
+        az_d, ax_d, tz_d = col(az), col(ax), col(tau_z)
+        logs = t.log((az_d[:, None] + ax_d[:, None] * self.s2) * tz_d[:, None]).sum(-1) \
+            + (self.Nz - self.R) * t.log(az_d * tz_d)
+        out = (0.5 * logs / self.Nz).cpu().numpy()
+        return float(out[0]) if self.batch is None else out
 
     def compute_free_energy(self, az, ax, tau_z):
         tau_x = self.second_moment(tau_z)

@@ -195,6 +195,34 @@ __device__ __forceinline__ double clip_a_new(double v, double a, double amin, do
   return an;
 }
 
+// EarlyStopping (callbacks.py:206-243) on the posterior variances of the tracked
+// variables (vars: bit 0 = x, bit 1 = z).  Returns 0 (go on), TRB_FLAG_CONVERGED
+// (stop, keep the state) or TRB_FLAG_DIVERGED (stop, roll back); *tol_out receives
+// max |dv| (NaN when there is no previous value yet).
+__device__ __forceinline__ int early_stopping_variance(int vars, int it, double vx, double vz,
+                                                       double vx_old, double vz_old, double es_tol,
+                                                       double es_min_variance, double es_max_increase,
+                                                       int es_wait_increase, double* tol_out) {
+  const bool ux = vars & 1, uz = vars & 2;
+  *tol_out = nan("");
+  if ((ux && vx < es_min_variance) || (uz && vz < es_min_variance)) return TRB_FLAG_CONVERGED;
+  if ((ux && vx != vx) || (uz && vz != vz)) return TRB_FLAG_DIVERGED;
+  if (it == 0) return 0;  // old_vs is None in the first call
+  double tol = 0.0, inc = -INFINITY;
+  if (ux) {
+    tol = fmax(tol, fabs(vx_old - vx));
+    inc = fmax(inc, vx - vx_old);
+  }
+  if (uz) {
+    tol = fmax(tol, fabs(vz_old - vz));
+    inc = fmax(inc, vz - vz_old);
+  }
+  *tol_out = tol;
+  if (tol < es_tol) return TRB_FLAG_CONVERGED;
+  if (it > es_wait_increase && inc > es_max_increase) return TRB_FLAG_DIVERGED;
+  return 0;
+}
+
 // message_passing.py:119-127; `if not damping: return data`
 __device__ __forceinline__ double damp(double d, double old_v, double new_v) {
   return (d != 0.0) ? d * old_v + (1.0 - d) * new_v : new_v;

@@ -441,10 +441,15 @@ k_sweep_persistent(trb_sweep sw, int it0, int n_iter, int fresh, int ldmax) {
       flag |= all;
       ++done;
       par ^= 1;
-      // EarlyStoppingEP, callbacks.py:258-286
+      // EarlyStoppingEP, callbacks.py:258-286 / EarlyStopping on the variances, :206-243
       double tol = nan("");
       int stop = 0;
-      if (it > 0) {
+      if (sw.es_mode == 1 && sw.es_tol >= 0) {
+        const int vars = sw.es_vars ? sw.es_vars : 3;
+        stop = early_stopping_variance(vars, it, vx, vz, vx_old, vz_old, sw.es_tol,
+                                       sw.es_min_variance, sw.es_max_increase, sw.es_wait_increase,
+                                       &tol);
+      } else if (it > 0) {
         const double tol_x = sqrt(rd[0] / N) / sqrt(rd[1] / N);
         const double tol_z = sqrt(dz2 / M) / sqrt(nz2 / M);
         const int vars = sw.es_vars ? sw.es_vars : 3;

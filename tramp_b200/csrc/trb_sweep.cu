@@ -272,7 +272,18 @@ k_x_update(trb_sweep sw, int G, int it_host, double* __restrict__ stats, trb_pee
     // EarlyStoppingEP, callbacks.py:258-286: tol = rms(new-old)/rms(new), max over the
     // tracked variables; needs a previous estimate, i.e. it > 0.
     double tol = nan("");
-    if (it > 0) {
+    if (sw.es_mode == 1 && sw.es_tol >= 0) {
+      // EarlyStopping on the variances (callbacks.py:206-243); the previous values are the
+      // one-iteration-back state's (snap_vx: saved above, snap_vz: saved by k_z_update)
+      const int vars = sw.es_vars ? sw.es_vars : 3;
+      const int stop = early_stopping_variance(vars, it, vx, sw.vz[b], sw.snap_vx[b], sw.snap_vz[b],
+                                               sw.es_tol, sw.es_min_variance, sw.es_max_increase,
+                                               sw.es_wait_increase, &tol);
+      if (stop) {
+        sw.active[b] = 0;
+        atomicOr(&sw.flags[b], stop);
+      }
+    } else if (it > 0) {
       const double tol_x = sqrt(d2 / N) / sqrt(n2 / N);
       const double tol_z = sqrt(stats[b * 4 + 0] / sw.M) / sqrt(stats[b * 4 + 1] / sw.M);
       const int vars = sw.es_vars ? sw.es_vars : 3;
@@ -374,6 +385,8 @@ static int check_sweep(const trb_sweep* sw) {
                     sw->stats,
                 "null scratch buffer");
   TRB_CHECK_ARG(sw->active && sw->flags && sw->n_iter, "null status buffer");
+  TRB_CHECK_ARG(sw->es_mode == 0 || (sw->es_mode == 1 && (sw->es_tol < 0 || sw->snap_edge_a)),
+                "the variance early stopping needs the snapshot buffers");
   TRB_CHECK_ARG(!sw->snap_edge_a || (sw->snap_b1 && sw->snap_b3 && sw->snap_b5 && sw->snap_b7 &&
                                      sw->snap_rx && sw->snap_rz && sw->snap_vx && sw->snap_vz &&
                                      sw->snap_tx),
