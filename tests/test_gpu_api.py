@@ -47,9 +47,35 @@ class _SeqInit:
         self.calls = 0
 
     def init(self, key, shape, id, direction):
-        edge = self.calls // 2 + 1          # init_message_dag asks a then b, edges e1..e8 in order
+        # init_message_dag asks a then b, edges in the reference's order (message_dag.edges())
+        edge = (1, 2, 8, 3, 7, 4, 6, 5)[(self.calls // 2) % 8]
         self.calls += 1
         return self.vals[edge][0 if key == "a" else 1]
+
+
+def test_noisy_init_consumes_the_random_stream_like_the_reference(sw):
+    """Same seed, same initial messages: NoisyInit is asked for the edges in the order of the
+    reference's `message_dag.edges()` (message_passing.py:223-230), so seeding numpy as the golden
+    run did reproduces the eight initial messages it recorded -- and hence its whole trajectory."""
+    from tramp_b200.algos import ExpectationPropagation, NoisyInit, TrackErrors
+    cfg = next(c for c in _configs(sw) if c.get("init") == "noisy")
+    name = cfg["name"]
+    ep = ExpectationPropagation(_build(cfg, sw, name))
+    init = NoisyInit(a_mean=0.5, a_var=0, b_mean=0, b_var=0.25)
+    np.random.seed(cfg["seed"] + 1000)
+    ep.init_message_dag(init)
+    for k in range(1, 9):
+        a, b = ep._edge(f"e{k}") if k in (1, 2, 3, 4, 5, 7) else (None, None)
+        if a is not None and k in (1, 3, 5, 7):
+            assert_allclose(a, float(sw[f"{name}_init_e{k}_a"]), rtol=0, atol=0)
+            assert np.array_equal(b, sw[f"{name}_init_e{k}_b"])
+    track = TrackErrors({"x": sw[name + "_x"]})
+    np.random.seed(cfg["seed"] + 1000)
+    ep.iterate(max_iter=cfg["n_iter"], callback=track, initializer=init, damping=cfg["damping"])
+    ref = sw[name + "_mse"]
+    tau_x = np.mean(sw[name + "_x"]**2)
+    mse = np.array([e["mse"] for e in track.errors])
+    assert np.all(np.abs(mse - ref) <= 1e-9 * ref + 2e-9 * np.sqrt(ref * tau_x))
 
 
 @pytest.mark.parametrize("impl,schedule", [(1, "general"), (2, "general"), (2, "auto")])

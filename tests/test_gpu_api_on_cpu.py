@@ -48,6 +48,10 @@ def test_variance_early_stopping_inside_the_sweep(emulated_device, sw, idx):  # 
     G.test_variance_early_stopping_inside_the_sweep(sw, idx)
 
 
+def test_noisy_init_consumes_the_random_stream_like_the_reference(emulated_device, sw):  # noqa: F811
+    G.test_noisy_init_consumes_the_random_stream_like_the_reference(sw)
+
+
 def test_linear_channel_reference_signature_corners(emulated_device):  # noqa: F811
     G.test_linear_channel_reference_signature_corners()
 

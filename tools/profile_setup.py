@@ -27,6 +27,6 @@ for b in range(B):
     lc._gram_rows(W[b], A[b])
 work = ops.jacobi_workspace(B, n_rows, ld, A.device)
 for _ in range(args.sweeps):
-    off = ops.jacobi_sweep(A, work, skip_tol=5e-15, max_inner=2)
+    off = ops.jacobi_sweep(A, work, skip_tol=5e-15, max_inner=lc.JACOBI_INNER_SWEEPS)
 torch.cuda.synchronize()
 print("off", float(off.max()))

@@ -4,8 +4,9 @@ The driver asks `initializer.init(key, shape, variable_id, direction)` for every
 edge, `key` being "a" (precision) or "b" (natural mean); `shape` is the
 variable's shape -- (N,) for one instance, (B, N) for a batch -- and is None
 under State Evolution, which only asks for "a".  The eight edges are visited in
-the order e1..e8, "a" before "b", which fixes how `NoisyInit`
-consumes numpy's global random stream.
+the reference's order -- `message_dag.edges()`, node by node: e1, e2, e8, e3, e7, e4, e6,
+e5 in the numbering of SURVEY 3.3 -- "a" before "b", so that `NoisyInit` consumes numpy's
+global random stream exactly as the reference does (same seed, same initial messages).
 """
 import numpy as np
 

@@ -41,6 +41,9 @@ class MessageSnapshot:
         self.n_iter = n_iter
 
 
+INIT_ORDER = ("e1", "e2", "e8", "e3", "e7", "e4", "e6", "e5")
+
+
 class MessagePassing():
 
     def __init__(self, model, message_keys):
@@ -189,7 +192,11 @@ class MessagePassing():
             self._has_messages = True
             return
         init_b = {}
-        for name, role, direction, idx in EDGES:
+        # The reference walks `message_dag.edges()` (message_passing.py:223-230), i.e. node by node
+        # in the order the nodes were added, out-edges in the order they were added (forward edges,
+        # then backward ones): e1, e2, e8, e3, e7, e4, e6, e5.  A NoisyInit seeded like the
+        # reference's therefore draws the same initial messages.
+        for name, role, direction, idx in sorted(EDGES, key=lambda e: INIT_ORDER.index(e[0])):
             shape = self._var_shape(role)
             a = initializer.init("a", shape, ids[role], direction)
             b = initializer.init("b", shape, ids[role], direction)
@@ -273,6 +280,8 @@ class MessagePassing():
         if self.backend == "sharded":
             sw.comm = lin.exchange.ptr
             sw.s_full, sw.s2_full = p(lin.s_full), p(lin.s2_full)
+        for k in ("edge_a", "b1", "b3", "b5", "b7", "rx", "rz", "vx", "vz", "tx"):
+            setattr(sw, "snap_" + k, p(st["snap_" + k]))
         sw.schedule = self.last_schedule = self._pick_schedule(early, synchronous)
         if sw.schedule:
             if "ty" not in st:     # ty = U_R^T y, once per model (y is fixed)
@@ -283,8 +292,6 @@ class MessagePassing():
             sw.ty = p(st["ty"])
             if sw.schedule == 2:
                 sw.es_vars = 1     # the recorded tolerance covers x only
-        for k in ("edge_a", "b1", "b3", "b5", "b7", "rx", "rz", "vx", "vz", "tx"):
-            setattr(sw, "snap_" + k, p(st["snap_" + k]))
         return sw
 
     def _pick_schedule(self, early, synchronous=False):

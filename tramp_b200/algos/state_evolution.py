@@ -178,7 +178,9 @@ class StateEvolution():
         st = self._ensure_state()
         ids = {"x": self.x_id, "z": self.z_id}
         a0 = np.zeros((8, self.G))
-        for i, (name, role, direction) in enumerate(EDGES):
+        from .message_passing import INIT_ORDER     # the reference's edge order (same random stream)
+        for name in INIT_ORDER:
+            i, (_, role, direction) = next((k, e) for k, e in enumerate(EDGES) if e[0] == name)
             a0[i, :] = initializer.init("a", None, ids[role], direction)
         st["edge_a"].copy_(ops.to_dev(a0))
         st["vx"].zero_()
