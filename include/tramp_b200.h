@@ -187,6 +187,36 @@ int trb_lin_expand_gemm(const double* A, int R, int n, int ld, int B,
  * loads / loads without MMA), used by tools/bench_gemm.py only */
 void trb_gemm_set_variant(int variant);
 
+/* ---- factor-by-factor schedule: adaptive damping, dA, the EP objective (trb_adaptive.cu) ----
+ * Device building blocks of algos/message_passing.py:129-185 (compute_dA, compute_adaptive_damping)
+ * and :306-328 (update_objective).  A message is (a[B], b[B, ld]); nothing is read back. */
+/* (a_out, b_out) = old + beta (new - old)  (:169-171); beta per instance (beta_arr[B]) or, if
+ * beta_arr is NULL, the scalar `beta`.  Outputs may alias neither input. */
+int trb_message_trial(int B, int n, int ld, const double* a_old, const double* b_old,
+                      const double* a_new, const double* b_new, const double* beta_arr,
+                      double beta, double* a_out, double* b_out, void* stream);
+/* Variable.compute_log_partition of the two messages meeting on a variable (base.py:146-155):
+ * A[b] = 0.5 sum((b1 + b2)^2 / (a1 + a2) + log(2 pi / (a1 + a2))), +inf if a1 + a2 <= 0 (a SUM) */
+int trb_variable_log_partition(int B, int n, int ld, const double* a1, const double* b1,
+                               const double* a2, const double* b2, double* A, void* stream);
+/* LinearChannel.compute_log_partition (linear_channel.py:127-132) from the singular-basis vectors
+ * tz = V_R^T bz, tx = U_R^T bx [B, R] and bz2[b] = |bz|^2 (needed when R < Nz: the part of bz in
+ * the null space of W).  s, s2: [Bop, R], stride_s = 0 when shared.  A[B] (a SUM). */
+int trb_lin_log_partition(int B, int R, int Nz, const double* s, const double* s2, int64_t stride_s,
+                          const double* az, const double* ax, const double* tz, const double* tx,
+                          const double* bz2, double* A, void* stream);
+/* out[b] = sum_i x[b, i] y[b, i] */
+int trb_row_dot(int B, int n, int ld, const double* x, const double* y, double* out, void* stream);
+/* Factor.compute_ab_new (base.py:250-255), the message of a channel from its posterior:
+ * a_new = clip(1 / max(v, 1e-20) - a_in, amin, amax), b_new = r (a_in + a_new) - b_in */
+int trb_message_from_posterior(int B, int n, int ld, const double* r, const double* v,
+                               const double* a_in, const double* b_in, double amin, double amax,
+                               double* a_new, double* b_new, void* stream);
+/* dst_b[b, :] = src_b[b, :] (and dst_a[b] = src_a[b] unless src_a is NULL) where mask[b] != 0:
+ * the per-instance "accept this step size" of the adaptive damping */
+int trb_rows_select(int B, int n, int ld, const int* mask, const double* src_a, const double* src_b,
+                    double* dst_a, double* dst_b, void* stream);
+
 /* ---- LinearChannel set-up: thin SVD by one-sided block Jacobi (trb_setup.cu) ----
  * Replaces np.linalg.svd / np.linalg.matrix_rank of channels/linear/linear_channel.py:8-15,
  * 36-46 (LAPACK gesdd on the host; counted in EP's total by examples/figures/benchmark.py:22).

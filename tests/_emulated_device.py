@@ -524,11 +524,76 @@ def _rows_gather_scale(self, src, stride_src, ld_src, perm, scale, B, R, n, dst,
     return 0
 
 
+# ---- factor-by-factor schedule on the device (trb_adaptive.cu) ----------------------------
+def _rows(ptr, B, ld, n):
+    return _arr(ptr, B * ld).reshape(B, ld)[:, :n]
+
+
+def _message_trial(self, B, n, ld, a_old, b_old, a_new, b_new, beta_arr, beta, a_out, b_out, stream):
+    bt = _arr(beta_arr, B).copy() if beta_arr else np.full(B, beta)
+    ao, an = _arr(a_old, B).copy(), _arr(a_new, B).copy()
+    bo, bn = _rows(b_old, B, ld, n).copy(), _rows(b_new, B, ld, n).copy()
+    with np.errstate(all="ignore"):
+        _rows(b_out, B, ld, n)[:] = bo + bt[:, None] * (bn - bo)
+        _arr(a_out, B)[:] = ao + bt * (an - ao)
+    return 0
+
+
+def _variable_log_partition(self, B, n, ld, a1, b1, a2, b2, A, stream):
+    with np.errstate(all="ignore"):
+        a = _arr(a1, B) + _arr(a2, B)
+        bb = _rows(b1, B, ld, n) + _rows(b2, B, ld, n)
+        val = 0.5 * np.sum(bb**2 / a[:, None] + np.log(2 * np.pi / a[:, None]), axis=1)
+    _arr(A, B)[:] = np.where(a <= 0, np.inf, val)
+    return 0
+
+
+def _lin_log_partition(self, B, R, Nz, s, s2, stride, az, ax, tz, tx, bz2, A, stream):
+    for i in range(B):
+        sb, s2b = _arr(s, i * stride + R)[i * stride:], _arr(s2, i * stride + R)[i * stride:]
+        a_z, a_x = _arr(az, B)[i], _arr(ax, B)[i]
+        t_z, t_x = _arr(tz, (i + 1) * R)[i * R:], _arr(tx, (i + 1) * R)[i * R:]
+        with np.errstate(all="ignore"):
+            a = a_z + a_x * s2b
+            quad = np.sum((t_z + sb * t_x)**2 / a)
+            lg = np.sum(np.log(2 * np.pi / a))
+            if R < Nz:
+                quad += (_arr(bz2, B)[i] - np.sum(t_z**2)) / a_z
+                lg += (Nz - R) * np.log(2 * np.pi / a_z)
+        _arr(A, B)[i] = 0.5 * quad + 0.5 * lg
+    return 0
+
+
+def _row_dot(self, B, n, ld, x, y, out, stream):
+    _arr(out, B)[:] = np.sum(_rows(x, B, ld, n) * _rows(y, B, ld, n), axis=1)
+    return 0
+
+
+def _message_from_posterior(self, B, n, ld, r, v, a_in, b_in, amin, amax, a_new, b_new, stream):
+    a = _arr(a_in, B).copy()
+    with np.errstate(all="ignore"):
+        an = np.array([_clip_a_new(vv, aa, amin, amax) for vv, aa in zip(_arr(v, B), a)])
+        _rows(b_new, B, ld, n)[:] = _rows(r, B, ld, n) * (a + an)[:, None] - _rows(b_in, B, ld, n)
+    _arr(a_new, B)[:] = an
+    return 0
+
+
+def _rows_select(self, B, n, ld, mask, src_a, src_b, dst_a, dst_b, stream):
+    m = _arr(mask, B, np.int32) != 0
+    _rows(dst_b, B, ld, n)[m] = _rows(src_b, B, ld, n)[m]
+    if src_a:
+        _arr(dst_a, B)[m] = _arr(src_a, B)[m]
+    return 0
+
+
 for _name, _fn in (("trb_factor_posterior", _factor_posterior), ("trb_factor_log_partition", _factor_log_partition),
                    ("trb_factor_message", _factor_message), ("trb_posterior_rv", _posterior_rv),
                    ("trb_lin_project", _lin_project), ("trb_lin_expand", _lin_expand),
                    ("trb_lin_reduce_slots", _lin_reduce_slots), ("trb_lin_project_gemm", _lin_project_gemm),
                    ("trb_lin_expand_gemm", _lin_expand_gemm), ("trb_lin_rescale", _lin_rescale),
+                   ("trb_message_trial", _message_trial), ("trb_variable_log_partition", _variable_log_partition),
+                   ("trb_lin_log_partition", _lin_log_partition), ("trb_row_dot", _row_dot),
+                   ("trb_message_from_posterior", _message_from_posterior), ("trb_rows_select", _rows_select),
                    ("trb_jacobi_sweep", _jacobi_sweep), ("trb_row_norms", _row_norms),
                    ("trb_rows_gather_scale", _rows_gather_scale)):
     setattr(EmulatedLibrary, _name, _fn)

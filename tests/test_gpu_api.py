@@ -714,6 +714,34 @@ def test_variance_early_stopping_inside_the_sweep(sw, idx):
         assert_allclose(v, df_host[df_host.id == vid].v.values, rtol=1e-12)
 
 
+@pytest.mark.parametrize("idx", [0, 2])
+def test_adaptive_schedule_device_and_host_backends_agree(ad, idx):
+    """The factor-by-factor schedule kept on the device (algos/device_schedule.py: messages resident,
+    objective and step-halving in kernels) against the same schedule through the numpy factor API
+    (algos/factor_schedule.py): same accepted step sizes, same messages."""
+    from tramp_b200.algos import ExpectationPropagation, PassCallback
+    cfg = json.loads(str(ad["configs"]))[idx]
+    name = cfg["name"]
+    out = {}
+    for backend in ("device", "host"):
+        ep = ExpectationPropagation(_build(cfg, ad, name))
+        ep.schedule_backend = backend
+        ep.iterate(max_iter=cfg["n_iter"], callback=PassCallback(), damping=cfg["damping"], update_dA=cfg["update_dA"])
+        assert type(ep._host).__name__ == ("DeviceSchedule" if backend == "device" else "FactorSchedule")
+        out[backend] = (ep.get_variables_data(), {k: dict(ep._host.edges[k]) for k in ep._host.edges}, ep.log_evidence())
+    (d_dev, e_dev, A_dev), (d_host, e_host, A_host) = out["device"], out["host"]
+    for vid in ("x", "z"):
+        assert_allclose(d_dev[vid]["r"], d_host[vid]["r"], rtol=1e-10, atol=1e-12)
+        assert_allclose(d_dev[vid]["v"], d_host[vid]["v"], rtol=1e-10)
+    for k in e_host:
+        assert_allclose(e_dev[k]["a"], e_host[k]["a"], rtol=1e-10)
+        assert_allclose(e_dev[k]["b"], e_host[k]["b"], rtol=1e-10, atol=1e-12)
+        assert e_dev[k]["n_iter"] == e_host[k]["n_iter"]
+        if cfg["damping"] == "adaptive":
+            assert e_dev[k]["beta"] == e_host[k]["beta"]
+    assert_allclose(A_dev, A_host, rtol=1e-10)
+
+
 def test_track_overlaps_and_objective_on_device_path(sw):
     """TrackOverlaps / TrackObjective are ordinary (synchronous) callbacks on the
     device path; A_model equals log_evidence()."""

@@ -65,6 +65,11 @@ def test_adaptive_damping_and_dA_match_reference(emulated_device, ad, idx):  # n
     G.test_adaptive_damping_and_dA_match_reference(ad, idx)
 
 
+@pytest.mark.parametrize("idx", [0, 2])
+def test_adaptive_schedule_device_and_host_backends_agree(emulated_device, ad, idx):  # noqa: F811
+    G.test_adaptive_schedule_device_and_host_backends_agree(ad, idx)
+
+
 def test_host_path_then_device_warm_start(emulated_device, ad):  # noqa: F811
     G.test_host_path_then_device_warm_start(ad)
 

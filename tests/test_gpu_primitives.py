@@ -258,3 +258,60 @@ def test_gemv_wide_operators_use_column_panels(ops, shape):
     assert_allclose(_np(t), np.einsum("brn,bn->br", A, x), rtol=1e-11, atol=1e-10)
     out = ops.lin_expand(A_d, R, n, ops.to_dev(c), B)
     assert_allclose(_np(out)[:, :n], np.einsum("brn,br->bn", A, c), rtol=1e-11, atol=1e-10)
+
+
+@pytest.mark.parametrize("shape", [(1, 37, 21), (5, 300, 140), (3, 64, 64), (2, 50, 90)])
+def test_schedule_primitives_vs_numpy(ops, shape):
+    """The device building blocks of the factor-by-factor schedule (trb_adaptive.cu) against the
+    reference's own expressions: Variable.compute_log_partition (base.py:146-155),
+    LinearChannel.compute_log_partition (linear_channel.py:127-132, dense W), compute_ab_new
+    (base.py:250-255), the trial message of the adaptive damping (message_passing.py:169-171)."""
+    import torch
+    B, N, M = shape
+    rng = np.random.RandomState(B * 1000 + N)
+    W = rng.randn(B, M, N) / np.sqrt(N)
+    a1, a2 = rng.rand(B) + 0.2, rng.rand(B) * 3 + 0.1
+    b1, b2 = rng.randn(B, N), rng.randn(B, N)
+    bx = rng.randn(B, M)
+    d = lambda x: ops.padded(x) if np.ndim(x) == 2 else ops.to_dev(x)      # noqa: E731
+    # variable objective (and +inf for a non-positive precision)
+    A = _np(ops.variable_log_partition(d(a1), d(b1), d(a2), d(b2), N))
+    ref = 0.5 * np.sum((b1 + b2)**2 / (a1 + a2)[:, None] + np.log(2 * np.pi / (a1 + a2))[:, None], axis=1)
+    assert_allclose(A, ref, rtol=1e-12)
+    assert np.all(np.isinf(_np(ops.variable_log_partition(d(-a1), d(b1), d(0 * a2), d(b2), N))))
+    # channel objective from the singular-basis vectors, against the dense formula
+    from tramp_b200.channels import LinearChannel
+    lin = LinearChannel(W)
+    lin._setup()
+    tz = ops.lin_project(lin.Vt, lin.R, N, ops.padded(b1, lin.ldn), B)
+    tx = ops.lin_project(lin.Ut, lin.R, M, ops.padded(bx, lin.ldm), B)
+    bz2 = ops.row_dot(d(b1), d(b1), N)
+    assert_allclose(_np(bz2), np.sum(b1 * b1, axis=1), rtol=1e-13)
+    A_lin = _np(ops.lin_log_partition(lin.s, lin.s2, N, d(a1), d(a2), tz, tx, bz2 if lin.R < N else None))
+    for i in range(B):
+        C = W[i].T @ W[i]
+        b = b1[i] + W[i].T @ bx[i]
+        rz = np.linalg.solve(a1[i] * np.identity(N) + a2[i] * C, b)
+        spectrum = np.clip(np.linalg.eigvalsh(C), 0, None)
+        ref_i = 0.5 * np.sum(b * rz) + 0.5 * np.sum(np.log(2 * np.pi / (a1[i] + a2[i] * spectrum)))
+        assert_allclose(A_lin[i], ref_i, rtol=1e-10)
+    # trial message, per-instance and scalar step size
+    beta = rng.rand(B)
+    a_out, b_out = torch.empty_like(d(a1)), torch.zeros_like(d(b1))
+    ops.message_trial(d(a1), d(b1), d(a2), d(b2), N, d(beta), a_out, b_out)
+    assert_allclose(_np(b_out)[:, :N], b1 + beta[:, None] * (b2 - b1), rtol=1e-14, atol=1e-15)
+    assert_allclose(_np(a_out), a1 + beta * (a2 - a1), rtol=1e-14)
+    ops.message_trial(d(a1), d(b1), d(a2), d(b2), N, 0.25, a_out, b_out)
+    assert_allclose(_np(b_out)[:, :N], b1 + 0.25 * (b2 - b1), rtol=1e-14, atol=1e-15)
+    # compute_ab_new with the clip
+    r, v = rng.randn(B, N), np.array([1e-25, 0.5, 1e13, 0.3, 2.0])[:B]
+    a_new, b_new = ops.message_from_posterior(d(r), d(v), d(a1), d(b1), N)
+    an_ref = np.clip(1 / np.maximum(v, 1e-20) - a1, 1e-11, 1e11)
+    assert_allclose(_np(a_new), an_ref, rtol=1e-14)
+    assert_allclose(_np(b_new)[:, :N], r * (a1 + an_ref)[:, None] - b1, rtol=1e-13, atol=1e-13)
+    # masked row copy
+    mask = (np.arange(B) % 2 == 0)
+    dst_a, dst_b = d(a2).clone(), d(b2).clone()
+    ops.rows_select(ops.to_dev(mask.astype(np.float64)).to(torch.int32), d(a1), d(b1), dst_a, dst_b, N)
+    assert_allclose(_np(dst_b)[:, :N], np.where(mask[:, None], b1, b2))
+    assert_allclose(_np(dst_a), np.where(mask, a1, a2))

@@ -122,6 +122,12 @@ SIGNATURES = {
     "trb_lin_project_gemm": (_I, [_P, _I, _I, _I, _I, _P, _I, _P, _P]),
     "trb_lin_expand_gemm": (_I, [_P, _I, _I, _I, _I, _P, _P, _I, _P]),
     "trb_gemm_set_variant": (None, [_I]),
+    "trb_message_trial": (_I, [_I, _I, _I, _P, _P, _P, _P, _P, _D, _P, _P, _P]),
+    "trb_variable_log_partition": (_I, [_I, _I, _I, _P, _P, _P, _P, _P, _P]),
+    "trb_lin_log_partition": (_I, [_I, _I, _I, _P, _P, _L, _P, _P, _P, _P, _P, _P, _P]),
+    "trb_row_dot": (_I, [_I, _I, _I, _P, _P, _P, _P]),
+    "trb_message_from_posterior": (_I, [_I, _I, _I, _P, _P, _P, _P, _D, _D, _P, _P, _P]),
+    "trb_rows_select": (_I, [_I, _I, _I, _P, _P, _P, _P, _P, _P]),
     "trb_jacobi_zsplit": (_I, [_I, _I, _I]),
     "trb_jacobi_set_waves": (None, [_I]),
     "trb_jacobi_sweep": (_I, [_P, _L, _I, _I, _I, _P, _P, _P, _P, _D, _I, _P]),

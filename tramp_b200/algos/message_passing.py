@@ -505,33 +505,47 @@ class MessagePassing():
 
     # ------------------------------------------- host-driven factor-by-factor path
     def _iterate_host(self, max_iter, callback, previous):
-        """damping="adaptive" / update_dA (reference :129-185): the reference's
-        node-by-node loop on the host, every factor evaluated by the CUDA kernels
-        through the factor API (algos/factor_schedule.py)."""
-        from .factor_schedule import FactorSchedule
+        """damping="adaptive" / update_dA (reference :129-185): the reference's node-by-node loop,
+        enqueued from the host.  `schedule_backend = "device"` (default): all eight messages stay on
+        the device and every step is a kernel launch (algos/device_schedule.py); "host": the same
+        schedule through the numpy factor API (algos/factor_schedule.py), the cross-check."""
         if getattr(self.linear, "group", None) is not None:
             raise NotImplementedError("adaptive damping / update_dA on a row-sharded operator")
+        backend = getattr(self, "schedule_backend", "device")
+        if backend not in ("device", "host"):
+            raise ValueError(f"unknown schedule_backend {backend!r}")
         st = self._state
         if previous is not None:
             host = previous
-            for name in host.edges:      # a new iterate() may change the constant damping
-                host.edges[name]["damping"] = self.damp.get(name) or None
+            for name in ("e1", "e2", "e3", "e4", "e5", "e6", "e7", "e8"):   # a new iterate() may change the constant damping
+                if hasattr(host, "set_damping"):
+                    host.set_damping(name, self.damp.get(name) or None)
+                else:
+                    host.edges[name]["damping"] = self.damp.get(name) or None
         else:
             edges = {}
             src = {"e1": "b1", "e2": "b1", "e3": "b3", "e4": "b3", "e5": "b5", "e6": "b6_init",
                    "e7": "b7", "e8": "b8_init"}
-            a_all = st["edge_a"].cpu().numpy()
+            a_all = st["edge_a"].cpu().numpy() if backend == "host" else None
             for name, role, direction, idx in EDGES:
                 t = st.get(src[name])
                 if t is None:
                     t = st["b5" if name == "e6" else "b7"]
                 n = self.N if role == "x" else self.M
+                if backend == "device":
+                    edges[name] = dict(a=st["edge_a"][idx], b=t, n_iter=0, damping=self.damp.get(name) or None)
+                    continue
                 b_host = t[:, :n].cpu().numpy().copy()
                 edges[name] = dict(a=a_all[idx].copy() if self.batched else float(a_all[idx, 0]),
                                    b=b_host if self.batched else b_host[0],
                                    direction=direction, n_iter=0,
                                    damping=self.damp.get(name) or None)
-            host = FactorSchedule(self, edges)
+            if backend == "device":
+                from .device_schedule import DeviceSchedule
+                host = DeviceSchedule(self, edges)
+            else:
+                from .factor_schedule import FactorSchedule
+                host = FactorSchedule(self, edges)
         self._host = host
         try:
             for i in range(max_iter):
@@ -550,6 +564,9 @@ class MessagePassing():
         get_variables_data / snapshots / a later device-path warm start see them."""
         st = self._state
         t = ops.torch()
+        if hasattr(host, "mirror_into"):            # the device schedule: device-to-device copies
+            host.mirror_into(st)
+            return
         e = host.edges
         st["edge_a"].copy_(t.as_tensor(np.stack([np.broadcast_to(np.asarray(e[n]["a"], dtype=np.float64), (self.B,))
                                                   for n, _, _, _ in EDGES]), dtype=t.float64))
@@ -566,11 +583,16 @@ class MessagePassing():
         """Warm start of the device sweep from messages the host path produced: the
         pass-through edges must again be copies of their sources (they always are
         unless adaptive damping held one of them back)."""
-        e = host.edges
-        for cp, srcn in (("e2", "e1"), ("e4", "e3"), ("e6", "e5"), ("e8", "e7")):
-            if np.any(e[cp]["a"] != e[srcn]["a"]) or not np.array_equal(e[cp]["b"], e[srcn]["b"]):
-                raise NotImplementedError(
-                    f"device-path warm start needs {cp} == {srcn}; adaptive damping left them different")
+        if hasattr(host, "aliases_hold"):
+            if not host.aliases_hold():
+                raise NotImplementedError("device-path warm start needs e2 == e1, e4 == e3, e6 == e5, e8 == e7; "
+                                          "adaptive damping left them different")
+        else:
+            e = host.edges
+            for cp, srcn in (("e2", "e1"), ("e4", "e3"), ("e6", "e5"), ("e8", "e7")):
+                if np.any(e[cp]["a"] != e[srcn]["a"]) or not np.array_equal(e[cp]["b"], e[srcn]["b"]):
+                    raise NotImplementedError(
+                        f"device-path warm start needs {cp} == {srcn}; adaptive damping left them different")
         self._host_to_device(host)
         st = self._state
         st["b6_init"] = st["b8_init"] = None

@@ -209,6 +209,65 @@ def lin_rescale(direction, B, R, Nz, Nx, rank, s, s2, az, ax, tz, tx, active=Non
 
 
 # ---------------------------------------------------------------------------
+# factor-by-factor schedule on the device (trb_adaptive.cu)
+# ---------------------------------------------------------------------------
+def message_trial(a_old, b_old, a_new, b_new, n, beta, a_out, b_out):
+    """(a_out, b_out) = old + beta (new - old); beta a float or a device tensor [B]."""
+    B, ld = b_old.shape
+    per_instance = is_tensor(beta)
+    check(_lib.load().trb_message_trial(B, n, ld, ptr(a_old), ptr(b_old), ptr(a_new), ptr(b_new),
+                                        ptr(beta) if per_instance else None, 0.0 if per_instance else float(beta),
+                                        ptr(a_out), ptr(b_out), current_stream()))
+    return a_out, b_out
+
+
+def variable_log_partition(a1, b1, a2, b2, n):
+    """A[B] of the variable on which the messages (a1, b1) and (a2, b2) meet (a SUM over components)."""
+    t = torch()
+    B, ld = b1.shape
+    A = t.empty(B, dtype=t.float64, device=b1.device)
+    check(_lib.load().trb_variable_log_partition(B, n, ld, ptr(a1), ptr(b1), ptr(a2), ptr(b2), ptr(A),
+                                                 current_stream()))
+    return A
+
+
+def lin_log_partition(s, s2, Nz, az, ax, tz, tx, bz2):
+    t = torch()
+    B, R = tz.shape
+    stride = 0 if s.shape[0] == 1 else s.stride(0)
+    A = t.empty(B, dtype=t.float64, device=tz.device)
+    check(_lib.load().trb_lin_log_partition(B, R, Nz, ptr(s), ptr(s2), stride, ptr(az), ptr(ax), ptr(tz), ptr(tx),
+                                            ptr(bz2), ptr(A), current_stream()))
+    return A
+
+
+def row_dot(x, y, n):
+    t = torch()
+    B, ld = x.shape
+    out = t.empty(B, dtype=t.float64, device=x.device)
+    check(_lib.load().trb_row_dot(B, n, ld, ptr(x), ptr(y), ptr(out), current_stream()))
+    return out
+
+
+def message_from_posterior(r, v, a_in, b_in, n, amin=AMIN, amax=AMAX):
+    """compute_ab_new: the (a_new [B], b_new [B, ld]) a channel sends, from its posterior (r, v)."""
+    t = torch()
+    B, ld = b_in.shape
+    a_new = t.empty(B, dtype=t.float64, device=b_in.device)
+    b_new = t.zeros_like(b_in)
+    check(_lib.load().trb_message_from_posterior(B, n, ld, ptr(r), ptr(v), ptr(a_in), ptr(b_in), float(amin),
+                                                 float(amax), ptr(a_new), ptr(b_new), current_stream()))
+    return a_new, b_new
+
+
+def rows_select(mask, src_a, src_b, dst_a, dst_b, n):
+    """dst[b] = src[b] for the instances with mask[b] != 0 (mask: int32 device tensor [B])."""
+    B, ld = src_b.shape
+    check(_lib.load().trb_rows_select(B, n, ld, ptr(mask), ptr(src_a), ptr(src_b), ptr(dst_a), ptr(dst_b),
+                                      current_stream()))
+
+
+# ---------------------------------------------------------------------------
 # LinearChannel set-up: block-Jacobi orthogonalisation of rows (trb_setup.cu)
 # ---------------------------------------------------------------------------
 JACOBI_ROWS = 32    # rows of a block pair: the row count of the work matrix is a multiple of it
