@@ -27,6 +27,7 @@
 // global load; the rows of a pair cross HBM twice in and once out per round:
 // arithmetic intensity 16/4 = 4 flop/B for the rotation (HBM-bound on B200 unless the
 // instance stays in L2) and (10/16)*4 for the Gram (upper-triangular tiles only).
+#include <stdlib.h>
 #include "trb_common.cuh"
 
 using namespace trb;
@@ -443,17 +444,9 @@ extern "C" int trb_jacobi_zsplit(int B, int np, int ld) {
   return (int)z;
 }
 
-extern "C" int trb_jacobi_sweep(double* A, int64_t strideA, int B, int np, int ld, double* Swork, double* Jwork,
-                                int* rot_flag, double* offmax, double skip_tol, int max_inner, void* stream) {
-  TRB_CHECK_ARG(A && Swork && Jwork && rot_flag && offmax, "null pointer");
-  TRB_CHECK_ARG(B > 0 && np >= kPV && np % kPV == 0, "np must be a positive multiple of 32");
-  TRB_CHECK_ARG(ld >= kStagePos && ld % kStagePos == 0, "ld must be a positive multiple of 64");
-  TRB_CHECK_ARG(strideA >= (int64_t)np * ld && (strideA % 2) == 0, "strideA too small");
-  TRB_CHECK_ARG(((uintptr_t)A % 16) == 0, "A must be 16-byte aligned");
-  TRB_CHECK_ARG(B <= 65535, "B > 65535");
-  int rc = setup_attrs();
-  if (rc) return rc;
-  cudaStream_t st = (cudaStream_t)stream;
+// all rounds of one sweep, enqueued on `st`
+static int enqueue_jacobi_sweep(double* A, int64_t strideA, int B, int np, int ld, double* Swork, double* Jwork,
+                                int* rot_flag, double* offmax, double skip_tol, int max_inner, cudaStream_t st) {
   const int nb = np / kBS, npairs = nb / 2;
   // Swork holds up to trb_jacobi_zsplit() partial Grams per pair
   const int chunk = ((ld / kStagePos + trb_jacobi_zsplit(B, np, ld) - 1) / trb_jacobi_zsplit(B, np, ld)) * kStagePos;
@@ -479,6 +472,90 @@ extern "C" int trb_jacobi_sweep(double* A, int64_t strideA, int B, int np, int l
   }
   TRB_CHECK_LAUNCH();
   return TRB_OK;
+}
+
+// A sweep over a few small matrices is 3 (np/16 - 1) launches of a few microseconds each: launch
+// latency, not HBM or the DMMA pipe, bounds it.  Such sweeps are captured once into a CUDA graph
+// (on a private stream: torch's default stream is the legacy stream, which cannot be captured) and
+// replayed -- every sweep of a factorisation has the same arguments.  The last graph is cached per
+// host thread.
+namespace {
+struct JacobiGraphKey {
+  double* A; int64_t strideA; int B, np, ld; double* S; double* J; int* flag; double* off; double skip_tol;
+  int max_inner, waves;
+};
+struct JacobiGraphCache {
+  JacobiGraphKey key = {};
+  cudaGraphExec_t exec = nullptr;
+  cudaStream_t capture_stream = nullptr;
+};
+thread_local JacobiGraphCache g_jacobi_graph;
+int g_jacobi_graphs = -1;
+constexpr double kJacobiGraphMaxBytes = 48e6;  // rows of all instances: beyond it a round streams for > 20 us
+}  // namespace
+
+static int jacobi_sweep_graph(const JacobiGraphKey& key, cudaStream_t st) {
+  JacobiGraphCache& gc = g_jacobi_graph;
+  if (!gc.exec || memcmp(&gc.key, &key, sizeof(key)) != 0) {
+    if (gc.exec) {
+      cudaGraphExecDestroy(gc.exec);
+      gc.exec = nullptr;
+    }
+    if (!gc.capture_stream && cudaStreamCreateWithFlags(&gc.capture_stream, cudaStreamNonBlocking) != cudaSuccess) {
+      cudaGetLastError();
+      return TRB_ERR_UNSUPPORTED;
+    }
+    if (cudaStreamBeginCapture(gc.capture_stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+      cudaGetLastError();
+      return TRB_ERR_UNSUPPORTED;
+    }
+    const int rc = enqueue_jacobi_sweep(key.A, key.strideA, key.B, key.np, key.ld, key.S, key.J, key.flag, key.off,
+                                        key.skip_tol, key.max_inner, gc.capture_stream);
+    cudaGraph_t graph = nullptr;
+    const cudaError_t ce = cudaStreamEndCapture(gc.capture_stream, &graph);
+    if (rc != TRB_OK || ce != cudaSuccess || !graph) {
+      if (graph) cudaGraphDestroy(graph);
+      cudaGetLastError();
+      return rc != TRB_OK ? rc : TRB_ERR_UNSUPPORTED;
+    }
+    const cudaError_t ie = cudaGraphInstantiate(&gc.exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (ie != cudaSuccess) {
+      gc.exec = nullptr;
+      cudaGetLastError();
+      return TRB_ERR_UNSUPPORTED;
+    }
+    gc.key = key;
+  }
+  const cudaError_t le = cudaGraphLaunch(gc.exec, st);
+  if (le != cudaSuccess) return trb_set_error(TRB_ERR_CUDA, "trb_jacobi_sweep: graph launch: %s", cudaGetErrorString(le));
+  return TRB_OK;
+}
+
+extern "C" int trb_jacobi_sweep(double* A, int64_t strideA, int B, int np, int ld, double* Swork, double* Jwork,
+                                int* rot_flag, double* offmax, double skip_tol, int max_inner, void* stream) {
+  TRB_CHECK_ARG(A && Swork && Jwork && rot_flag && offmax, "null pointer");
+  TRB_CHECK_ARG(B > 0 && np >= kPV && np % kPV == 0, "np must be a positive multiple of 32");
+  TRB_CHECK_ARG(ld >= kStagePos && ld % kStagePos == 0, "ld must be a positive multiple of 64");
+  TRB_CHECK_ARG(strideA >= (int64_t)np * ld && (strideA % 2) == 0, "strideA too small");
+  TRB_CHECK_ARG(((uintptr_t)A % 16) == 0, "A must be 16-byte aligned");
+  TRB_CHECK_ARG(B <= 65535, "B > 65535");
+  int rc = setup_attrs();
+  if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (g_jacobi_graphs < 0) {
+    const char* e = getenv("TRB_CUDA_GRAPHS");
+    g_jacobi_graphs = (e && e[0] == '0') ? 0 : 1;
+  }
+  if (g_jacobi_graphs && np > kPV && (double)B * np * ld * 8.0 <= kJacobiGraphMaxBytes) {
+    JacobiGraphKey key = {};  // zero the padding: the key is compared bytewise
+    key.A = A, key.strideA = strideA, key.B = B, key.np = np, key.ld = ld, key.S = Swork, key.J = Jwork;
+    key.flag = rot_flag, key.off = offmax, key.skip_tol = skip_tol, key.max_inner = max_inner;
+    key.waves = g_jacobi_waves;
+    rc = jacobi_sweep_graph(key, st);
+    if (rc != TRB_ERR_UNSUPPORTED) return rc;  // else: plain launches
+  }
+  return enqueue_jacobi_sweep(A, strideA, B, np, ld, Swork, Jwork, rot_flag, offmax, skip_tol, max_inner, st);
 }
 
 extern "C" int trb_row_norms(const double* A, int64_t strideA, int B, int rows, int n, int ld, double* norms,
