@@ -239,6 +239,9 @@ int trb_jacobi_zsplit(int B, int np, int ld);
 /* tuning: the column range of a pair is split over CTAs until the grid holds about `waves`
  * waves of resident CTAs (default 4; fewer waves = longer CTAs, more tail) */
 void trb_jacobi_set_waves(int waves);
+/* rows of at most 768 doubles: Gram, eigenvectors and rotation of a pair run as ONE kernel per round
+ * with the pair resident in shared memory (default on; 0 = always the three-kernel path) */
+void trb_jacobi_set_fused(int enabled);
 int trb_jacobi_sweep(double* A, int64_t strideA, int B, int np, int ld, double* Swork,
                      double* Jwork, int* rot_flag, double* offmax, double skip_tol,
                      int max_inner, void* stream);

@@ -255,11 +255,14 @@ def test_options_reach_the_right_edges(emulated_device, seed):  # noqa: F811
             init_by_edge[e] = (0.2, np.full(n, 0.05))
     else:
         a_init, b_init = [], []
+        chosen = {}
         for vid, direction in [pairs[k] for k in rng.choice(4, size=2, replace=False)]:
             n = N if vid == "x" else M
             a0, b0 = float(rng.uniform(0.1, 1.0)), 0.1 * rng.randn(n)
             a_init.append((vid, direction, a0))
             b_init.append((vid, direction, b0))
+            chosen[vid] = (direction, a0, b0)       # the reference keeps ONE entry per variable id: the last
+        for vid, (direction, a0, b0) in chosen.items():
             for e in EDGE_OF[(vid, direction)]:
                 init_by_edge[e] = (a0, b0)
         initializer = CustomInit(a_init=a_init, b_init=b_init)

@@ -113,6 +113,7 @@ def main():
     ap.add_argument("--direct", action="store_true", help="also time the route on W itself")
     ap.add_argument("--waves", type=int, default=0, help="trb_jacobi_set_waves (0: library default)")
     ap.add_argument("--inner", type=int, default=0, help="sweeps of the inner 32 x 32 Jacobi (0: default)")
+    ap.add_argument("--no-fused", action="store_true", help="rows <= 768: use the three-kernel path anyway")
     args = ap.parse_args()
     assert torch.cuda.is_available(), "needs a CUDA device"
     from tramp_b200 import _lib
@@ -120,6 +121,8 @@ def main():
         _lib.load().trb_jacobi_set_waves(args.waves)
     if args.inner:
         lc.JACOBI_INNER_SWEEPS = args.inner
+    if args.no_fused:
+        _lib.load().trb_jacobi_set_fused(0)
     B, N = args.batch, args.n
     M = int(args.alpha * N)
     gen = torch.Generator(device="cuda").manual_seed(0)

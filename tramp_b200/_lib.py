@@ -130,6 +130,7 @@ SIGNATURES = {
     "trb_rows_select": (_I, [_I, _I, _I, _P, _P, _P, _P, _P, _P]),
     "trb_jacobi_zsplit": (_I, [_I, _I, _I]),
     "trb_jacobi_set_waves": (None, [_I]),
+    "trb_jacobi_set_fused": (None, [_I]),
     "trb_jacobi_sweep": (_I, [_P, _L, _I, _I, _I, _P, _P, _P, _P, _D, _I, _P]),
     "trb_row_norms": (_I, [_P, _L, _I, _I, _I, _I, _P, _P]),
     "trb_rows_gather_scale": (_I, [_P, _L, _I, _P, _P, _I, _I, _I, _P, _L, _I, _P]),

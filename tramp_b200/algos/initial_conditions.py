@@ -67,7 +67,11 @@ class CustomInit(InitialConditions):
 
     a_init / b_init: lists of (variable id, direction, value); an entry applies to
     both edges of that variable with that direction (factor -> variable and
-    variable -> factor).  a, b: the constants used for every other edge."""
+    variable -> factor).  a, b: the constants used for every other edge.
+
+    Like the reference (`{id: {direction: a} for id, direction, a in a_init}`, :63-66), ONE entry
+    per variable id is kept: a later entry for the same id replaces an earlier one, also when its
+    direction differs."""
 
     def __init__(self, a_init=None, b_init=None, a=0, b=0):
         self.a_init = self._table(a_init)
@@ -77,10 +81,7 @@ class CustomInit(InitialConditions):
 
     @staticmethod
     def _table(entries):
-        table = {}
-        for variable_id, direction, value in (entries or []):
-            table.setdefault(variable_id, {})[direction] = value
-        return table
+        return {variable_id: {direction: value} for variable_id, direction, value in (entries or [])}
 
     def init_a(self, shape, id, direction):
         return self.a_init.get(id, {}).get(direction, self.a)

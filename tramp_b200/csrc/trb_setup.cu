@@ -210,71 +210,62 @@ __device__ __forceinline__ unsigned long long as_ull(double v) {
   return (unsigned long long)__double_as_longlong(v);
 }
 
-__global__ void __launch_bounds__(256, 7)
-k_jacobi_eig(const double* __restrict__ S, int zsplit, double* __restrict__ Jm, int* __restrict__ rot_flag,
-             unsigned long long* __restrict__ offmax, double skip_tol, int max_inner) {
-  __shared__ double sS[kPV][kPV + 1];
-  __shared__ double sJ[kPV][kPV + 1];
-  __shared__ double sc[kBS], ss[kBS];
-  __shared__ double sred[8];
-  const int tid = threadIdx.x;
-  const int pair = blockIdx.x, b = blockIdx.y, npairs = gridDim.x;
-  const double* in = S + ((size_t)b * npairs + pair) * zsplit * (kPV * kPV);
-  for (int e = tid; e < kPV * kPV; e += 256) {
-    double v = 0.0;
-    for (int z = 0; z < zsplit; ++z) v += in[(size_t)z * (kPV * kPV) + e];
-    sS[e >> 5][e & 31] = v;
-    sJ[e >> 5][e & 31] = ((e >> 5) == (e & 31)) ? 1.0 : 0.0;
-  }
-  __syncthreads();
-  // largest |cos| between two rows
-  __shared__ double sinv[kPV];
+// Shared-memory working set of the 32 x 32 eigen-problem of a pair
+struct EigSmem {
+  double S[kPV][kPV + 1];
+  double J[kPV][kPV + 1];
+  double c[kBS], s[kBS];
+  double inv[kPV];
+  double red[8];
+  uchar2 pair[kPV - 1][kBS];  // the 31 x 16 index pairs of the inner round-robin, as (p, q) bytes
+};
+
+// Largest |cos| between two rows of the pair whose Gram matrix is in m.S (256 threads; ends with a
+// barrier).  Rows whose norm is below 1e-13 of the pair's largest are rounding noise (padding
+// rows, the null directions of a rank-deficient matrix): their direction means nothing and they
+// are left out of the convergence measure.
+__device__ __forceinline__ double pair_max_cosine(EigSmem& m, int tid) {
   if (tid < kPV) {
-    // rows whose norm is below 1e-13 of the pair's largest are rounding noise (padding rows, the
-    // null directions of a rank-deficient matrix): their direction means nothing and they are left
-    // out of the convergence measure
-    const double d = sS[tid][tid];
+    const double d = m.S[tid][tid];
     double dmax = d;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) dmax = fmax(dmax, __shfl_xor_sync(0xffffffffu, dmax, o));
-    sinv[tid] = (d > 1e-26 * dmax && d > 0.0) ? rsqrt(d) : 0.0;
+    m.inv[tid] = (d > 1e-26 * dmax && d > 0.0) ? rsqrt(d) : 0.0;
   }
   __syncthreads();
   double off = 0.0;
   for (int e = tid; e < kPV * kPV; e += 256) {
     const int i = e >> 5, j = e & 31;
-    if (i < j) off = fmax(off, fabs(sS[i][j]) * sinv[i] * sinv[j]);
+    if (i < j) off = fmax(off, fabs(m.S[i][j]) * m.inv[i] * m.inv[j]);
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) off = fmax(off, __shfl_xor_sync(0xffffffffu, off, o));
-  if ((tid & 31) == 0) sred[tid >> 5] = off;
+  if ((tid & 31) == 0) m.red[tid >> 5] = off;
   __syncthreads();
-  off = sred[0];
+  off = m.red[0];
 #pragma unroll
-  for (int w = 1; w < 8; ++w) off = fmax(off, sred[w]);
-  if (tid == 0) {
-    atomicMax(offmax + b, as_ull(off));  // non-negative doubles order like their bit patterns
-    rot_flag[(size_t)b * npairs + pair] = (off > skip_tol) ? 1 : 0;
-  }
-  if (!(off > skip_tol)) return;
+  for (int w = 1; w < 8; ++w) off = fmax(off, m.red[w]);
+  return off;
+}
 
-  // the 31 x 16 index pairs of the inner round-robin, as (p, q) bytes
-  __shared__ uchar2 spair[kPV - 1][kBS];
+// m.S <- J^T m.S J (nearly) diagonal, m.J <- J, by `max_inner` sweeps of cyclic two-sided Jacobi
+// (256 threads; m.J must hold the identity on entry; ends with a barrier).
+__device__ __forceinline__ void pair_eigenvectors(EigSmem& m, int tid, int max_inner) {
   for (int e = tid; e < (kPV - 1) * kBS; e += 256) {
     int p, q;
     rr_pair(kPV, e >> 4, e & 15, p, q);
-    spair[e >> 4][e & 15] = make_uchar2((unsigned char)p, (unsigned char)q);
+    m.pair[e >> 4][e & 15] = make_uchar2((unsigned char)p, (unsigned char)q);
   }
   __syncthreads();
-  const int k = tid >> 4, m = tid & 15;
+  const int k = tid >> 4, mm = tid & 15;
   for (int sweep = 0; sweep < max_inner; ++sweep) {
     int rotated = 0;
     for (int step = 0; step < kPV - 1; ++step) {
-      const uchar2 ik = spair[step][k], im = spair[step][m];
+      const uchar2 ik = m.pair[step][k], im = m.pair[step][mm];
       const int pk = ik.x, qk = ik.y, pm = im.x, qm = im.y;
       if (tid < kBS) {
-        const int p = pm, q = qm;  // tid < 16: m == tid
-        const double app = sS[p][p], aqq = sS[q][q], apq = sS[p][q];
+        const int p = pm, q = qm;  // tid < 16: mm == tid
+        const double app = m.S[p][p], aqq = m.S[q][q], apq = m.S[p][q];
         double c = 1.0, s = 0.0;
         if (fabs(apq) > 1.1e-16 * sqrt(fabs(app * aqq)) && apq != 0.0) {
           // small root of t^2 + 2 tau t - 1 = 0, tau = (aqq - app) / (2 apq), written without
@@ -287,29 +278,166 @@ k_jacobi_eig(const double* __restrict__ S, int zsplit, double* __restrict__ Jm, 
           s = tt * c;
           rotated = 1;
         }
-        sc[tid] = c;
-        ss[tid] = s;
+        m.c[tid] = c;
+        m.s[tid] = s;
       }
       __syncthreads();
-      const double ck = sc[k], sk = ss[k], cm = sc[m], sm = ss[m];
+      const double ck = m.c[k], sk = m.s[k], cm = m.c[mm], sm = m.s[mm];
       // S' = R_k^T S R_m on the 2x2 block, R = [[c, s], [-s, c]]
-      const double a00 = sS[pk][pm], a01 = sS[pk][qm], a10 = sS[qk][pm], a11 = sS[qk][qm];
+      const double a00 = m.S[pk][pm], a01 = m.S[pk][qm], a10 = m.S[qk][pm], a11 = m.S[qk][qm];
       const double t00 = ck * a00 - sk * a10, t01 = ck * a01 - sk * a11;
       const double t10 = sk * a00 + ck * a10, t11 = sk * a01 + ck * a11;
       double n00 = cm * t00 - sm * t01, n01 = sm * t00 + cm * t01;
       double n10 = cm * t10 - sm * t11, n11 = sm * t10 + cm * t11;
-      if (k == m && (ck != 1.0 || sk != 0.0)) n01 = n10 = 0.0;  // annihilated by construction
+      if (k == mm && (ck != 1.0 || sk != 0.0)) n01 = n10 = 0.0;  // annihilated by construction
       // J' = J R_m on rows 2k, 2k+1
-      const double j00 = sJ[2 * k][pm], j01 = sJ[2 * k][qm], j10 = sJ[2 * k + 1][pm], j11 = sJ[2 * k + 1][qm];
-      sS[pk][pm] = n00, sS[pk][qm] = n01, sS[qk][pm] = n10, sS[qk][qm] = n11;
-      sJ[2 * k][pm] = cm * j00 - sm * j01, sJ[2 * k][qm] = sm * j00 + cm * j01;
-      sJ[2 * k + 1][pm] = cm * j10 - sm * j11, sJ[2 * k + 1][qm] = sm * j10 + cm * j11;
+      const double j00 = m.J[2 * k][pm], j01 = m.J[2 * k][qm], j10 = m.J[2 * k + 1][pm], j11 = m.J[2 * k + 1][qm];
+      m.S[pk][pm] = n00, m.S[pk][qm] = n01, m.S[qk][pm] = n10, m.S[qk][qm] = n11;
+      m.J[2 * k][pm] = cm * j00 - sm * j01, m.J[2 * k][qm] = sm * j00 + cm * j01;
+      m.J[2 * k + 1][pm] = cm * j10 - sm * j11, m.J[2 * k + 1][qm] = sm * j10 + cm * j11;
       __syncthreads();
     }
     if (sweep + 1 < max_inner && !__syncthreads_or(rotated)) break;
   }
+}
+
+__global__ void __launch_bounds__(256, 7)
+k_jacobi_eig(const double* __restrict__ S, int zsplit, double* __restrict__ Jm, int* __restrict__ rot_flag,
+             unsigned long long* __restrict__ offmax, double skip_tol, int max_inner) {
+  __shared__ EigSmem m;
+  const int tid = threadIdx.x;
+  const int pair = blockIdx.x, b = blockIdx.y, npairs = gridDim.x;
+  const double* in = S + ((size_t)b * npairs + pair) * zsplit * (kPV * kPV);
+  for (int e = tid; e < kPV * kPV; e += 256) {
+    double v = 0.0;
+    for (int z = 0; z < zsplit; ++z) v += in[(size_t)z * (kPV * kPV) + e];
+    m.S[e >> 5][e & 31] = v;
+    m.J[e >> 5][e & 31] = ((e >> 5) == (e & 31)) ? 1.0 : 0.0;
+  }
+  __syncthreads();
+  const double off = pair_max_cosine(m, tid);
+  if (tid == 0) {
+    atomicMax(offmax + b, as_ull(off));  // non-negative doubles order like their bit patterns
+    rot_flag[(size_t)b * npairs + pair] = (off > skip_tol) ? 1 : 0;
+  }
+  if (!(off > skip_tol)) return;
+  pair_eigenvectors(m, tid, max_inner);
   double* out = Jm + ((size_t)b * npairs + pair) * (kPV * kPV);
-  for (int e = tid; e < kPV * kPV; e += 256) out[e] = sJ[e >> 5][e & 31];
+  for (int e = tid; e < kPV * kPV; e += 256) out[e] = m.J[e >> 5][e & 31];
+}
+
+// ---------------------------------------------------------- a whole round in one kernel
+// Short rows (ld <= kFusedMaxLd): the 32 rows of a pair fit in the shared memory of one CTA, so
+// Gram, eigenvectors and rotation are ONE launch per round and the rows cross HBM once in, once
+// out.  grid (pairs, B), 256 threads = 8 DMMA warps; warp w owns the 16-position units w, w + 8, ...
+constexpr int kFusedMaxLd = 768;
+__host__ __device__ constexpr int fused_stride(int ld) { return ld + 4; }  // = 32 B mod 128: see kRotStride
+
+__global__ void __launch_bounds__(256, 1)
+k_jacobi_round_fused(double* __restrict__ A, int64_t strideA, int ld, int nb, int round,
+                     unsigned long long* __restrict__ offmax, double skip_tol, int max_inner) {
+  extern __shared__ __align__(128) double X[];  // 32 rows x fused_stride(ld)
+  __shared__ EigSmem m;
+  __shared__ __align__(8) uint64_t bar;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int b = blockIdx.y;
+  const int XS = fused_stride(ld);
+  int p, q;
+  rr_pair(nb, round, blockIdx.x, p, q);
+  double* Ab = A + (size_t)b * strideA;
+  if (tid == 0) {
+    mbar_init(&bar, 1);
+    fence_mbar_init();
+  }
+  for (int e = tid; e < kPV * kPV; e += 256) {
+    m.S[e >> 5][e & 31] = 0.0;
+    m.J[e >> 5][e & 31] = ((e >> 5) == (e & 31)) ? 1.0 : 0.0;
+  }
+  __syncthreads();
+  if (warp == 0) {  // one bulk copy per row
+    if (lane == 0) mbar_arrive_expect_tx(&bar, (uint32_t)(kPV * ld * 8));
+    __syncwarp();
+    bulk_g2s(X + (size_t)lane * XS, Ab + (size_t)pair_row(p, q, lane) * ld, (uint32_t)(ld * 8), &bar);
+  }
+  mbar_wait(&bar, 0);
+  const int g = lane >> 2, t = lane & 3;
+  const int units = ld / 16;
+  {
+    // ---- Gram: upper-triangular 8 x 8 tiles, as in k_jacobi_gram
+    double acc[10][2];
+#pragma unroll
+    for (int k = 0; k < 10; ++k) acc[k][0] = acc[k][1] = 0.0;
+    for (int u = warp; u < units; u += 8) {
+      const double* st = X + 16 * u + 4 * t;
+      double x[4][4];
+#pragma unroll
+      for (int I = 0; I < 4; ++I) {
+        const double2 lo = *reinterpret_cast<const double2*>(st + (size_t)(8 * I + g) * XS);
+        const double2 hi = *reinterpret_cast<const double2*>(st + (size_t)(8 * I + g) * XS + 2);
+        x[I][0] = lo.x, x[I][1] = lo.y, x[I][2] = hi.x, x[I][3] = hi.y;
+      }
+#pragma unroll
+      for (int s = 0; s < 4; ++s) {
+        int k = 0;
+#pragma unroll
+        for (int I = 0; I < 4; ++I)
+#pragma unroll
+          for (int J = I; J < 4; ++J, ++k) dmma884(acc[k][0], acc[k][1], x[I][s], x[J][s]);
+      }
+    }
+    // the warps add their partial tiles one after the other: a fixed order, bit-reproducible
+    for (int w = 0; w < 8; ++w) {
+      if (warp == w) {
+        int k = 0;
+#pragma unroll
+        for (int I = 0; I < 4; ++I)
+#pragma unroll
+          for (int J = I; J < 4; ++J, ++k) {
+            m.S[8 * I + g][8 * J + 2 * t] += acc[k][0];
+            m.S[8 * I + g][8 * J + 2 * t + 1] += acc[k][1];
+          }
+      }
+      __syncthreads();
+    }
+  }
+  for (int e = tid; e < kPV * kPV; e += 256) {  // mirror the lower tiles
+    const int i = e >> 5, j = e & 31;
+    if ((i >> 3) > (j >> 3)) m.S[i][j] = m.S[j][i];
+  }
+  __syncthreads();
+  const double off = pair_max_cosine(m, tid);
+  if (tid == 0) atomicMax(offmax + b, as_ull(off));
+  if (!(off > skip_tol)) return;  // rows already orthogonal
+  pair_eigenvectors(m, tid, max_inner);
+  // ---- rotation X <- J^T X from shared memory straight to global memory (in place: the whole
+  // pair has been read), as in k_jacobi_rotate
+  double af[4][8];
+#pragma unroll
+  for (int I = 0; I < 4; ++I)
+#pragma unroll
+    for (int K = 0; K < 8; ++K) af[I][K] = m.J[4 * K + t][8 * I + g];
+  for (int u = warp; u < units; u += 8) {
+    const double* st = X + 16 * u + 2 * g;
+    double2 bf[8];
+#pragma unroll
+    for (int K = 0; K < 8; ++K) bf[K] = *reinterpret_cast<const double2*>(st + (size_t)(4 * K + t) * XS);
+    double acc[4][2][2];
+#pragma unroll
+    for (int I = 0; I < 4; ++I) acc[I][0][0] = acc[I][0][1] = acc[I][1][0] = acc[I][1][1] = 0.0;
+#pragma unroll
+    for (int K = 0; K < 8; ++K)
+#pragma unroll
+      for (int I = 0; I < 4; ++I) {
+        dmma884(acc[I][0][0], acc[I][0][1], af[I][K], bf[K].x);
+        dmma884(acc[I][1][0], acc[I][1][1], af[I][K], bf[K].y);
+      }
+#pragma unroll
+    for (int I = 0; I < 4; ++I) {
+      double2* o = reinterpret_cast<double2*>(Ab + (size_t)pair_row(p, q, 8 * I + g) * ld + 16 * u + 4 * t);
+      o[0] = make_double2(acc[I][0][0], acc[I][1][0]);
+      o[1] = make_double2(acc[I][0][1], acc[I][1][1]);
+    }
+  }
 }
 
 // --------------------------------------------------------------- rotation of a pair
@@ -422,6 +550,9 @@ int setup_attrs() {
   if (e == cudaSuccess)
     e = cudaFuncSetAttribute(k_jacobi_rotate, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              kRingStages * kPV * kRotStride * 8);
+  if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(k_jacobi_round_fused, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             kPV * fused_stride(kFusedMaxLd) * 8);
   if (e != cudaSuccess) return trb_set_error(TRB_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
   g_setup_attr_done = true;
   return TRB_OK;
@@ -429,6 +560,8 @@ int setup_attrs() {
 
 }  // namespace
 
+int g_jacobi_fused = 1;
+extern "C" void trb_jacobi_set_fused(int enabled) { g_jacobi_fused = enabled ? 1 : 0; }
 int g_jacobi_waves = 4;  // measured on B200 (B = 16, 2048 x 2048): 4 waves 43.8 ms, 8 waves 47.0, 2 waves 44.8, 16 waves 52.9 per instance
 extern "C" void trb_jacobi_set_waves(int waves) { g_jacobi_waves = waves > 0 ? waves : 4; }
 
@@ -448,6 +581,16 @@ extern "C" int trb_jacobi_zsplit(int B, int np, int ld) {
 static int enqueue_jacobi_sweep(double* A, int64_t strideA, int B, int np, int ld, double* Swork, double* Jwork,
                                 int* rot_flag, double* offmax, double skip_tol, int max_inner, cudaStream_t st) {
   const int nb = np / kBS, npairs = nb / 2;
+  if (g_jacobi_fused && ld <= kFusedMaxLd) {  // short rows: one launch per round, the pair in shared memory
+    cudaMemsetAsync(offmax, 0, sizeof(double) * B, st);
+    for (int round = 0; round < nb - 1; ++round) {
+      trb_launch_scope scope_(2, st);
+      k_jacobi_round_fused<<<dim3(npairs, B), 256, kPV * fused_stride(ld) * 8, st>>>(
+          A, strideA, ld, nb, round, reinterpret_cast<unsigned long long*>(offmax), skip_tol, max_inner);
+    }
+    TRB_CHECK_LAUNCH();
+    return TRB_OK;
+  }
   // Swork holds up to trb_jacobi_zsplit() partial Grams per pair
   const int chunk = ((ld / kStagePos + trb_jacobi_zsplit(B, np, ld) - 1) / trb_jacobi_zsplit(B, np, ld)) * kStagePos;
   const int zsplit = (ld + chunk - 1) / chunk;
@@ -482,7 +625,7 @@ static int enqueue_jacobi_sweep(double* A, int64_t strideA, int B, int np, int l
 namespace {
 struct JacobiGraphKey {
   double* A; int64_t strideA; int B, np, ld; double* S; double* J; int* flag; double* off; double skip_tol;
-  int max_inner, waves;
+  int max_inner, waves, fused;
 };
 struct JacobiGraphCache {
   JacobiGraphKey key = {};
@@ -552,6 +695,7 @@ extern "C" int trb_jacobi_sweep(double* A, int64_t strideA, int B, int np, int l
     key.A = A, key.strideA = strideA, key.B = B, key.np = np, key.ld = ld, key.S = Swork, key.J = Jwork;
     key.flag = rot_flag, key.off = offmax, key.skip_tol = skip_tol, key.max_inner = max_inner;
     key.waves = g_jacobi_waves;
+    key.fused = g_jacobi_fused;
     rc = jacobi_sweep_graph(key, st);
     if (rc != TRB_ERR_UNSUPPORTED) return rc;  // else: plain launches
   }

@@ -408,6 +408,12 @@ int trb_lin_rescale_snap(int dir, int B, int R, int Nz, int Nx, int rank, int nu
                          const double* s, const double* s2, int64_t stride_s, const double* az,
                          const double* ax, const double* tz, const double* tx, double* coef, double* v,
                          const int* active, double* snap_tx, void* stream);
+// The push is NOT gated by `active`: every rank takes the same stop decision in the same
+// iteration (the update kernels are computed redundantly on bit-identical sums), and a stopped
+// instance's `part` is no longer rewritten by trb_lin_expand, so the ranks go on pushing and
+// publishing identical stale vectors for the rest of the call while the consumers return before
+// peers_wait -- the sequence numbers keep advancing in lock step on all ranks, which is what the
+// double buffering of trb_comm.cu relies on.
 static int exchange_expansion(const trb_sweep* sw, int n, int ld, cudaStream_t st) {
   trb_comm* comm = sw->comm;
   TRB_CHECK_ARG((size_t)sw->B * ld <= trb_comm_capacity(comm), "exchange buffer too small");
