@@ -250,7 +250,7 @@ __device__ __forceinline__ double pair_max_cosine(EigSmem& m, int tid) {
 
 // m.S <- J^T m.S J (nearly) diagonal, m.J <- J, by `max_inner` sweeps of cyclic two-sided Jacobi
 // (256 threads; m.J must hold the identity on entry; ends with a barrier).
-__device__ __forceinline__ void pair_eigenvectors(EigSmem& m, int tid, int max_inner) {
+__device__ __forceinline__ void pair_eigenvectors(EigSmem& m, int tid, int max_inner, bool precise) {
   for (int e = tid; e < (kPV - 1) * kBS; e += 256) {
     int p, q;
     rr_pair(kPV, e >> 4, e & 15, p, q);
@@ -267,13 +267,26 @@ __device__ __forceinline__ void pair_eigenvectors(EigSmem& m, int tid, int max_i
         const int p = pm, q = qm;  // tid < 16: mm == tid
         const double app = m.S[p][p], aqq = m.S[q][q], apq = m.S[p][q];
         double c = 1.0, s = 0.0;
-        if (fabs(apq) > 1.1e-16 * sqrt(fabs(app * aqq)) && apq != 0.0) {
+        if (apq * apq > 1.21e-32 * fabs(app * aqq) && apq != 0.0) {
           // small root of t^2 + 2 tau t - 1 = 0, tau = (aqq - app) / (2 apq), written without
-          // forming tau: t = sgn(d h) |h| / (|d| + sqrt(d^2 + h^2)).  Only c has to be exact to
-          // the last bit (c^2 + s^2 = c^2 (1 + t^2) = 1 keeps J orthogonal); an ulp or two in t
-          // merely leaves |apq| * 1e-16 un-annihilated.
+          // forming tau: t = sgn(d h) |h| / (|d| + sqrt(d^2 + h^2)).  This serial step is the
+          // latency of the whole kernel (31 dependent steps), and FP64 square roots and divisions
+          // are long dependent chains: the tangent is therefore evaluated in FP32 on operands
+          // scaled to [1/2, 1) -- its 6e-8 relative error only leaves 6e-8 |apq| un-annihilated --
+          // while the pair is far from orthogonal (`precise` = its largest cosine is below 1e-3:
+          // the last, quadratically converging sweeps use the FP64 tangent), and ONLY c, which
+          // decides how orthogonal J is (c^2 + s^2 = c^2 (1 + t^2) = 1), is always computed in
+          // full precision.
           const double d = aqq - app, h = 2.0 * apq;
-          const double tt = copysign(fabs(h) / (fabs(d) + sqrt(fma(d, d, h * h))), (d >= 0.0) ? h : -h);
+          double tt;
+          if (precise) {
+            tt = copysign(fabs(h) / (fabs(d) + sqrt(fma(d, d, h * h))), (d >= 0.0) ? h : -h);
+          } else {
+            const int ex = ilogb(fmax(fabs(d), fabs(h)));
+            const float df = (float)scalbn(d, -ex - 1), hf = (float)scalbn(h, -ex - 1);
+            const float tf = fabsf(hf) / (fabsf(df) + sqrtf(fmaf(df, df, hf * hf)));
+            tt = copysign((double)tf, (d >= 0.0) ? h : -h);
+          }
           c = rsqrt(fma(tt, tt, 1.0));
           s = tt * c;
           rotated = 1;
@@ -321,7 +334,7 @@ k_jacobi_eig(const double* __restrict__ S, int zsplit, double* __restrict__ Jm, 
     rot_flag[(size_t)b * npairs + pair] = (off > skip_tol) ? 1 : 0;
   }
   if (!(off > skip_tol)) return;
-  pair_eigenvectors(m, tid, max_inner);
+  pair_eigenvectors(m, tid, max_inner, off < 1e-3);
   double* out = Jm + ((size_t)b * npairs + pair) * (kPV * kPV);
   for (int e = tid; e < kPV * kPV; e += 256) out[e] = m.J[e >> 5][e & 31];
 }
@@ -408,7 +421,7 @@ k_jacobi_round_fused(double* __restrict__ A, int64_t strideA, int ld, int nb, in
   const double off = pair_max_cosine(m, tid);
   if (tid == 0) atomicMax(offmax + b, as_ull(off));
   if (!(off > skip_tol)) return;  // rows already orthogonal
-  pair_eigenvectors(m, tid, max_inner);
+  pair_eigenvectors(m, tid, max_inner, off < 1e-3);
   // ---- rotation X <- J^T X from shared memory straight to global memory (in place: the whole
   // pair has been read), as in k_jacobi_rotate
   double af[4][8];
@@ -581,7 +594,14 @@ extern "C" int trb_jacobi_zsplit(int B, int np, int ld) {
 static int enqueue_jacobi_sweep(double* A, int64_t strideA, int B, int np, int ld, double* Swork, double* Jwork,
                                 int* rot_flag, double* offmax, double skip_tol, int max_inner, cudaStream_t st) {
   const int nb = np / kBS, npairs = nb / 2;
-  if (g_jacobi_fused && ld <= kFusedMaxLd) {  // short rows: one launch per round, the pair in shared memory
+  // Short rows AND few pairs (one wave of CTAs: the launch-bound regime): one launch per round with
+  // the pair in shared memory.  With many pairs the three-kernel path is faster, because its
+  // eigenvector kernel runs 8 CTAs per SM and hides the latency of the serial inner Jacobi, which
+  // a CTA holding 100-200 KB of rows cannot (measured, 500 x 500: B = 1 / 8 / 64 instances 13.8 /
+  // 1.96 / 1.66 ms each fused against 15.5 / 2.41 / 1.34 unfused).
+  const int fused_per_sm = (int)(220000 / ((size_t)kPV * fused_stride(ld) * 8 + sizeof(EigSmem) + 64));
+  if (g_jacobi_fused && ld <= kFusedMaxLd &&
+      (long long)npairs * B <= (long long)trb_sm_count_cached() * (fused_per_sm < 1 ? 1 : fused_per_sm)) {
     cudaMemsetAsync(offmax, 0, sizeof(double) * B, st);
     for (int round = 0; round < nb - 1; ++round) {
       trb_launch_scope scope_(2, st);
