@@ -250,7 +250,7 @@ __device__ __forceinline__ double pair_max_cosine(EigSmem& m, int tid) {
 
 // m.S <- J^T m.S J (nearly) diagonal, m.J <- J, by `max_inner` sweeps of cyclic two-sided Jacobi
 // (256 threads; m.J must hold the identity on entry; ends with a barrier).
-__device__ __forceinline__ void pair_eigenvectors(EigSmem& m, int tid, int max_inner, bool precise) {
+__device__ __forceinline__ void pair_eigenvectors(EigSmem& m, int tid, int max_inner) {
   for (int e = tid; e < (kPV - 1) * kBS; e += 256) {
     int p, q;
     rr_pair(kPV, e >> 4, e & 15, p, q);
@@ -269,24 +269,12 @@ __device__ __forceinline__ void pair_eigenvectors(EigSmem& m, int tid, int max_i
         double c = 1.0, s = 0.0;
         if (apq * apq > 1.21e-32 * fabs(app * aqq) && apq != 0.0) {
           // small root of t^2 + 2 tau t - 1 = 0, tau = (aqq - app) / (2 apq), written without
-          // forming tau: t = sgn(d h) |h| / (|d| + sqrt(d^2 + h^2)).  This serial step is the
-          // latency of the whole kernel (31 dependent steps), and FP64 square roots and divisions
-          // are long dependent chains: the tangent is therefore evaluated in FP32 on operands
-          // scaled to [1/2, 1) -- its 6e-8 relative error only leaves 6e-8 |apq| un-annihilated --
-          // while the pair is far from orthogonal (`precise` = its largest cosine is below 1e-3:
-          // the last, quadratically converging sweeps use the FP64 tangent), and ONLY c, which
-          // decides how orthogonal J is (c^2 + s^2 = c^2 (1 + t^2) = 1), is always computed in
-          // full precision.
+          // forming tau: t = sgn(d h) |h| / (|d| + sqrt(d^2 + h^2)).  Only c has to be exact to
+          // the last bit (c^2 + s^2 = c^2 (1 + t^2) = 1 keeps J orthogonal); an ulp or two in t
+          // merely leaves |apq| * 1e-16 un-annihilated.  (An FP32 tangent was tried to shorten this
+          // serial step: no gain on B200, and one more outer sweep.)
           const double d = aqq - app, h = 2.0 * apq;
-          double tt;
-          if (precise) {
-            tt = copysign(fabs(h) / (fabs(d) + sqrt(fma(d, d, h * h))), (d >= 0.0) ? h : -h);
-          } else {
-            const int ex = ilogb(fmax(fabs(d), fabs(h)));
-            const float df = (float)scalbn(d, -ex - 1), hf = (float)scalbn(h, -ex - 1);
-            const float tf = fabsf(hf) / (fabsf(df) + sqrtf(fmaf(df, df, hf * hf)));
-            tt = copysign((double)tf, (d >= 0.0) ? h : -h);
-          }
+          const double tt = copysign(fabs(h) / (fabs(d) + sqrt(fma(d, d, h * h))), (d >= 0.0) ? h : -h);
           c = rsqrt(fma(tt, tt, 1.0));
           s = tt * c;
           rotated = 1;
@@ -334,7 +322,7 @@ k_jacobi_eig(const double* __restrict__ S, int zsplit, double* __restrict__ Jm, 
     rot_flag[(size_t)b * npairs + pair] = (off > skip_tol) ? 1 : 0;
   }
   if (!(off > skip_tol)) return;
-  pair_eigenvectors(m, tid, max_inner, off < 1e-3);
+  pair_eigenvectors(m, tid, max_inner);
   double* out = Jm + ((size_t)b * npairs + pair) * (kPV * kPV);
   for (int e = tid; e < kPV * kPV; e += 256) out[e] = m.J[e >> 5][e & 31];
 }
@@ -421,7 +409,7 @@ k_jacobi_round_fused(double* __restrict__ A, int64_t strideA, int ld, int nb, in
   const double off = pair_max_cosine(m, tid);
   if (tid == 0) atomicMax(offmax + b, as_ull(off));
   if (!(off > skip_tol)) return;  // rows already orthogonal
-  pair_eigenvectors(m, tid, max_inner, off < 1e-3);
+  pair_eigenvectors(m, tid, max_inner);
   // ---- rotation X <- J^T X from shared memory straight to global memory (in place: the whole
   // pair has been read), as in k_jacobi_rotate
   double af[4][8];
