@@ -111,3 +111,27 @@ def test_fused_round_kernel_matches_three_kernel_path():
     # same subspaces: |<u_i, u_i'>| = 1 up to the sign convention of each run
     dots = np.abs(np.einsum("brm,brm->br", out[1][0], out[0][0]))
     assert_allclose(dots, 1.0, atol=1e-8)
+
+
+def test_rank_deficient_and_ill_conditioned_matrices():
+    """`svd_method="auto"`: a wide matrix with two equal rows (rank deficient: the Gram route is
+    rejected on its condition number, the direct route on its smallest singular value, the library
+    SVD takes over) and a nearly square one (direct route) still give the reference's rank
+    (np.linalg.matrix_rank, linear_channel.py:37) and a usable factorisation."""
+    from tramp_b200.channels import LinearChannel
+    from tramp_b200.channels.linear_channel import LAST_SETUP_STATS
+    rng = np.random.RandomState(21)
+    W = rng.randn(60, 120) / np.sqrt(120)
+    W[-1] = W[0]
+    lin = LinearChannel(W)
+    lin._setup()
+    assert lin.rank == np.linalg.matrix_rank(W) == 59
+    s = lin.s.cpu().numpy()[0]
+    assert_allclose(s[:59], np.linalg.svd(W, compute_uv=False)[:59], rtol=1e-10)
+    rec = (lin.Ut[0, :, :60].T * lin.s[0]) @ lin.Vt[0, :, :120]
+    assert_allclose(rec.cpu().numpy(), W, atol=1e-12)
+    Wsq = rng.randn(200, 210) / np.sqrt(210)                  # aspect 0.95: cond^2 > 1e4
+    lin2 = LinearChannel(Wsq)
+    lin2._setup()
+    assert LAST_SETUP_STATS["route"] == "direct" and lin2.rank == 200
+    assert_allclose(lin2.s.cpu().numpy()[0], np.linalg.svd(Wsq, compute_uv=False), rtol=1e-10)
