@@ -437,28 +437,54 @@ k_lin_rescale(int dir, int R, int Nz, int Nx, int rank, int null_space_flag,
   const double* sb = s + (size_t)b * stride_s;
   const double* s2b = s2 + (size_t)b * stride_s;
   const size_t off = (size_t)b * R;
-  // ---- variance
+  // ---- one pass over the spectrum: the coefficients in the singular basis AND the sum the
+  // variance needs (they do not depend on each other; a second pass only added latency)
   double az_v = az;
   if (dir == 1) az_v = (az != az) ? az : fmax(1e-11, az);  // :94 np.maximum(1e-11, az)
+  const double ratio = az_v / ax;
+  // which sum: 1 = sum of the spectrum (:100-102, dir 0 and ax == 0), 2 = sum s2 / (ratio + s2)
+  // (:66-67), 0 = none (:60-65: ax == 0 or ratio == 0)
+  const int sum_mode = (dir == 0 && ax == 0) ? 1 : ((ax == 0 || ratio == 0) ? 0 : 2);
+  const bool null_space = null_space_flag != 0;
+  double part = 0.0;
+  for (int i = gtid; i < R; i += T_) {
+    const double s2i = s2b[i];
+    if (i < rank) {
+      if (sum_mode == 1) part += s2i;
+      else if (sum_mode == 2) part += s2i / (ratio + s2i);
+    }
+    if (coef) {
+      const double si = sb[i];
+      const double res = 1 / (az + ax * s2i);  // :74
+      const double tzi = tz[off + i], txi = tx[off + i];
+      if (snap_tx) snap_tx[off + i] = txi;
+      double c;
+      if (dir == 0) {
+        c = si * (res * (tzi + si * txi));
+      } else if (!null_space) {
+        c = res * (tzi + si * txi);
+      } else {
+        // res - 1/az = -(ax*s2/az)*res, applied to tz; the bz/az term is added
+        // by the consumer of the expansion
+        c = res * (si * txi - (ax * s2i / az) * tzi);
+      }
+      coef[off + i] = c;
+    }
+  }
+  if (!v_out) return;
+  // ---- variance
   double v;
-  if (dir == 0 && ax == 0) {  // :100-102
-    double part = 0.0;
-    for (int i = gtid; i < rank; i += T_) part += s2b[i];
+  if (sum_mode == 1) {  // :100-102
     const double s_mean = cluster_sum(part, sh) / rank;
     v = s_mean * rank / (Nx * az);
   } else {
     double n_eff;
     if (ax == 0) {  // :60-62
       n_eff = 0.;
-    } else {
-      const double ratio = az_v / ax;
-      if (ratio == 0) {  // :63-65
-        n_eff = (double)rank / Nz;
-      } else {  // :66-67
-        double part = 0.0;
-        for (int i = gtid; i < rank; i += T_) part += s2b[i] / (ratio + s2b[i]);
-        n_eff = cluster_sum(part, sh) / Nz;
-      }
+    } else if (ratio == 0) {  // :63-65
+      n_eff = (double)rank / Nz;
+    } else {  // :66-67
+      n_eff = cluster_sum(part, sh) / Nz;
     }
     if (dir == 0) {
       const double alpha = (double)Nx / Nz;
@@ -467,27 +493,7 @@ k_lin_rescale(int dir, int R, int Nz, int Nx, int rank, int null_space_flag,
       v = (1 - n_eff) / az_v;  // :95-97
     }
   }
-  if (gtid == 0 && v_out) v_out[b] = v;
-  if (!coef) return;
-  // ---- coefficients in the singular basis
-  const bool null_space = null_space_flag != 0;
-  for (int i = gtid; i < R; i += T_) {
-    const double si = sb[i], s2i = s2b[i];
-    const double res = 1 / (az + ax * s2i);  // :74
-    const double tzi = tz[off + i], txi = tx[off + i];
-    if (snap_tx) snap_tx[off + i] = txi;
-    double c;
-    if (dir == 0) {
-      c = si * (res * (tzi + si * txi));
-    } else if (!null_space) {
-      c = res * (tzi + si * txi);
-    } else {
-      // res - 1/az = -(ax*s2/az)*res, applied to tz; the bz/az term is added
-      // by the consumer of the expansion
-      c = res * (si * txi - (ax * s2i / az) * tzi);
-    }
-    coef[off + i] = c;
-  }
+  if (gtid == 0) v_out[b] = v;
 }
 
 int pick_nb(int ld, int threads, int max_nb) {
