@@ -230,7 +230,8 @@ int trb_rows_select(int B, int n, int ld, const int* mask, const double* src_a, 
  * shared memory, pair rotation on DMMA).
  *   Swork  [B, np/32, trb_jacobi_zsplit(B, np, ld), 1024]   partial pair Grams
  *   Jwork  [B, np/32, 1024]                                 pair rotations
- *   rot_flag [B, np/32] int                                 0: pair already orthogonal, skipped
+ *   rot_flag [2, B, np/32] int                              [0]: 0 = pair already orthogonal, skipped;
+ *                                                           [1]: scratch (arrival counters of a pair's CTAs)
  *   offmax [B]  out: largest |cos| between two rows of a pair BEFORE its rotation
  *   skip_tol   pairs whose largest |cos| is <= skip_tol are left untouched
  *   max_inner  sweeps of the inner 32 x 32 Jacobi (2 is enough: the outer sweeps converge
@@ -239,9 +240,11 @@ int trb_jacobi_zsplit(int B, int np, int ld);
 /* tuning: the column range of a pair is split over CTAs until the grid holds about `waves`
  * waves of resident CTAs (default 4; fewer waves = longer CTAs, more tail) */
 void trb_jacobi_set_waves(int waves);
-/* rows of at most 768 doubles: Gram, eigenvectors and rotation of a pair run as ONE kernel per round
- * with the pair resident in shared memory (default on; 0 = always the three-kernel path) */
-void trb_jacobi_set_fused(int enabled);
+/* kernel fusion (tuning / A-B tests), a bit mask, default 3: bit 0 = rows of at most 768 doubles and
+ * one wave of pairs: Gram, eigenvectors and rotation of a pair as ONE kernel per round, the pair
+ * resident in shared memory; bit 1 = Gram and eigenvectors in one kernel (the CTA that completes a
+ * pair's Gram matrix goes on to its eigen-solve); 0 = three launches per round */
+void trb_jacobi_set_fused(int mask);
 int trb_jacobi_sweep(double* A, int64_t strideA, int B, int np, int ld, double* Swork,
                      double* Jwork, int* rot_flag, double* offmax, double skip_tol,
                      int max_inner, void* stream);

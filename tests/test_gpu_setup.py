@@ -88,29 +88,32 @@ def test_north_star_shape_real_W_setup_and_sweep():
     assert_allclose(mse, np.array(ref["traj"]["mse_x"]), rtol=1e-9)
 
 
-def test_fused_round_kernel_matches_three_kernel_path():
-    """Rows of at most 768 doubles take the one-kernel-per-round path (the pair resident in shared
-    memory); the three-kernel path on the same matrices gives the same factorisation."""
-    import torch
+@pytest.mark.parametrize("shape", [(5, 300, 700), (40, 200, 300), (3, 1100, 2300)])
+def test_fused_kernels_match_three_kernel_path(shape):
+    """The kernel fusions of the set-up (trb_jacobi_set_fused: one kernel per round for short rows
+    and few pairs; Gram + eigenvectors in one kernel, with one or several CTAs per pair) against
+    the plain three-launches-per-round path on the same matrices: same factorisation."""
     from tramp_b200 import _lib, ops
     from tramp_b200.channels.linear_channel import thin_svd_device, LAST_SETUP_STATS
     lib = _lib.load()
-    W = np.random.RandomState(11).randn(5, 300, 700) / np.sqrt(700)
+    W = np.random.RandomState(11).randn(*shape) / np.sqrt(shape[2])
     out = {}
     try:
-        for fused in (1, 0):
-            lib.trb_jacobi_set_fused(fused)
+        for mask in (3, 2, 1, 0):
+            lib.trb_jacobi_set_fused(mask)
             Ut, s, Vt = thin_svd_device(ops.to_dev(W), "jacobi")
-            out[fused] = (Ut.cpu().numpy(), s.cpu().numpy(), Vt.cpu().numpy(), LAST_SETUP_STATS["sweeps"])
+            out[mask] = (Ut.cpu().numpy(), s.cpu().numpy(), Vt.cpu().numpy(), LAST_SETUP_STATS["sweeps"])
     finally:
-        lib.trb_jacobi_set_fused(1)
+        lib.trb_jacobi_set_fused(3)
     s_ref = np.linalg.svd(W, compute_uv=False)
-    for fused in (1, 0):
-        assert_allclose(out[fused][1], s_ref, rtol=1e-11)
-    assert abs(out[1][3] - out[0][3]) <= 1
-    # same subspaces: |<u_i, u_i'>| = 1 up to the sign convention of each run
-    dots = np.abs(np.einsum("brm,brm->br", out[1][0], out[0][0]))
-    assert_allclose(dots, 1.0, atol=1e-8)
+    for mask in (3, 2, 1):
+        assert_allclose(out[mask][1], s_ref, rtol=1e-11)
+        assert abs(out[mask][3] - out[0][3]) <= 1
+        # same subspaces: |<u_i, u_i'>| = 1 up to the sign convention of each run
+        dots = np.abs(np.einsum("brm,brm->br", out[mask][0], out[0][0]))
+        assert_allclose(dots, 1.0, atol=1e-8)
+    # Gram + eigenvectors fused is the same arithmetic in the same order as the two launches
+    assert np.array_equal(out[2][1], out[0][1])
 
 
 def test_rank_deficient_and_ill_conditioned_matrices():

@@ -113,7 +113,7 @@ def main():
     ap.add_argument("--direct", action="store_true", help="also time the route on W itself")
     ap.add_argument("--waves", type=int, default=0, help="trb_jacobi_set_waves (0: library default)")
     ap.add_argument("--inner", type=int, default=0, help="sweeps of the inner 32 x 32 Jacobi (0: default)")
-    ap.add_argument("--no-fused", action="store_true", help="rows <= 768: use the three-kernel path anyway")
+    ap.add_argument("--fused-mask", type=int, default=-1, help="trb_jacobi_set_fused (-1: library default 3)")
     args = ap.parse_args()
     assert torch.cuda.is_available(), "needs a CUDA device"
     from tramp_b200 import _lib
@@ -121,13 +121,14 @@ def main():
         _lib.load().trb_jacobi_set_waves(args.waves)
     if args.inner:
         lc.JACOBI_INNER_SWEEPS = args.inner
-    if args.no_fused:
-        _lib.load().trb_jacobi_set_fused(0)
+    if args.fused_mask >= 0:
+        _lib.load().trb_jacobi_set_fused(args.fused_mask)
     B, N = args.batch, args.n
     M = int(args.alpha * N)
     gen = torch.Generator(device="cuda").manual_seed(0)
     W = torch.randn((B, M, N), dtype=torch.float64, device="cuda", generator=gen) / N**0.5
     line = {"tool": "bench_setup", "B": B, "M": M, "N": N, "waves": args.waves, "inner": lc.JACOBI_INNER_SWEEPS,
+            "fused_mask": args.fused_mask,
             "variants": {}}
     wide = W if M <= N else W.transpose(1, 2).contiguous()
 

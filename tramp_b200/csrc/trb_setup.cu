@@ -79,7 +79,7 @@ __device__ __forceinline__ void mma_bar() {
 
 // Producer warp: streams positions [c0, c1) of the 32 rows of the pair into the ring,
 // one 512-byte bulk copy per row and stage (lane r copies row r).
-template <int STRIDE>
+template <int STRIDE, int STAGES = kRingStages>
 __device__ __forceinline__ void produce_pair(const double* Ab, int ld, int p, int q, int c0, int c1,
                                              double* ring, uint64_t* full_bar, uint64_t* empty_bar) {
   const int lane = threadIdx.x & 31;
@@ -93,16 +93,17 @@ __device__ __forceinline__ void produce_pair(const double* Ab, int ld, int p, in
     }
     __syncwarp();
     bulk_g2s(ring + ((size_t)stage * kPV + lane) * STRIDE, src + c, kStagePos * 8u, &full_bar[stage]);
-    if (++stage == kRingStages) {
+    if (++stage == STAGES) {
       stage = 0;
       phase ^= 1u;
     }
   }
 }
 
+template <int STAGES = kRingStages>
 __device__ __forceinline__ void ring_init(uint64_t* full_bar, uint64_t* empty_bar) {
   if (threadIdx.x == 0) {
-    for (int s = 0; s < kRingStages; ++s) {
+    for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], kMmaWarps);
     }
@@ -324,6 +325,124 @@ k_jacobi_eig(const double* __restrict__ S, int zsplit, double* __restrict__ Jm, 
   if (!(off > skip_tol)) return;
   pair_eigenvectors(m, tid, max_inner);
   double* out = Jm + ((size_t)b * npairs + pair) * (kPV * kPV);
+  for (int e = tid; e < kPV * kPV; e += 256) out[e] = m.J[e >> 5][e & 31];
+}
+
+// ------------------------------------------------- Gram + eigenvectors in one kernel
+// grid (pairs, B, zsplit), 256 threads: warps 0-3 are the DMMA consumers of k_jacobi_gram, warp 4
+// the TMA producer, warps 5-7 only join for the eigen-solve.  The CTA that finishes the pair's
+// Gram matrix (the only one when zsplit = 1, else the last of the pair's zsplit CTAs to arrive:
+// an arrival counter per pair, partial sums added in chunk order, so the result does not depend
+// on which CTA is last) goes straight on to the 32 x 32 Jacobi.  That kernel is bound by
+// instruction issue and FP64 latency, this one by HBM: with three CTAs per SM in different phases
+// the eigen-solves run in the shadow of the other CTAs' streaming instead of in a launch of
+// their own (measured: Gram 110 us + eigenvectors 70 us per 1024 pairs as two launches).
+constexpr int kGeStages = 3;
+__global__ void __launch_bounds__(256, 3)
+k_jacobi_gram_eig(const double* __restrict__ A, int64_t strideA, int ld, int nb, int round, int chunk,
+                  double* __restrict__ S, unsigned int* __restrict__ arrivals, double* __restrict__ Jm,
+                  int* __restrict__ rot_flag, unsigned long long* __restrict__ offmax, double skip_tol,
+                  int max_inner) {
+  extern __shared__ __align__(128) double ring[];  // kGeStages * 32 * kGramStride; reused for the reduction
+  __shared__ EigSmem m;
+  __shared__ __align__(8) uint64_t full_bar[kGeStages];
+  __shared__ __align__(8) uint64_t empty_bar[kGeStages];
+  __shared__ int s_last;
+  ring_init<kGeStages>(full_bar, empty_bar);
+
+  int p, q;
+  rr_pair(nb, round, blockIdx.x, p, q);
+  const int b = blockIdx.y, npairs = nb / 2, zsplit = gridDim.z;
+  const int c0 = blockIdx.z * chunk;
+  const int c1 = min(ld, c0 + chunk);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const double* Ab = A + (size_t)b * strideA;
+  const int g = lane >> 2, t = lane & 3;
+  double acc[10][2];
+#pragma unroll
+  for (int k = 0; k < 10; ++k) acc[k][0] = acc[k][1] = 0.0;
+  if (warp == kMmaWarps) {
+    produce_pair<kGramStride, kGeStages>(Ab, ld, p, q, c0, c1, ring, full_bar, empty_bar);
+  } else if (warp < kMmaWarps) {
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int c = c0; c < c1; c += kStagePos) {
+      mbar_wait(&full_bar[stage], phase);
+      const double* st = ring + (size_t)stage * kPV * kGramStride + 16 * warp + 4 * t;
+      double x[4][4];
+#pragma unroll
+      for (int I = 0; I < 4; ++I) {
+        const double2 lo = *reinterpret_cast<const double2*>(st + (8 * I + g) * kGramStride);
+        const double2 hi = *reinterpret_cast<const double2*>(st + (8 * I + g) * kGramStride + 2);
+        x[I][0] = lo.x, x[I][1] = lo.y, x[I][2] = hi.x, x[I][3] = hi.y;
+      }
+#pragma unroll
+      for (int s = 0; s < 4; ++s) {
+        int k = 0;
+#pragma unroll
+        for (int I = 0; I < 4; ++I)
+#pragma unroll
+          for (int J = I; J < 4; ++J, ++k) dmma884(acc[k][0], acc[k][1], x[I][s], x[J][s]);
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty_bar[stage]);
+      if (++stage == kGeStages) {
+        stage = 0;
+        phase ^= 1u;
+      }
+    }
+  }
+  __syncthreads();  // every stage was consumed: the ring is free for the reduction
+  double* red = ring;  // [4][32][33]
+  if (warp < kMmaWarps) {
+    int k = 0;
+#pragma unroll
+    for (int I = 0; I < 4; ++I)
+#pragma unroll
+      for (int J = I; J < 4; ++J, ++k) {
+        double* d = red + ((size_t)warp * kPV + 8 * I + g) * 33 + 8 * J + 2 * t;
+        d[0] = acc[k][0];
+        d[1] = acc[k][1];
+      }
+  }
+  __syncthreads();
+  const size_t pair_id = (size_t)b * npairs + blockIdx.x;
+  for (int e = tid; e < kPV * kPV; e += 256) {
+    int i = e >> 5, j = e & 31;
+    if ((i >> 3) > (j >> 3)) {  // lower tile: mirror
+      const int tmp = i;
+      i = j, j = tmp;
+    }
+    double v = 0.0;
+#pragma unroll
+    for (int w = 0; w < kMmaWarps; ++w) v += red[((size_t)w * kPV + i) * 33 + j];
+    if (zsplit == 1) m.S[e >> 5][e & 31] = v;
+    else S[(pair_id * zsplit + blockIdx.z) * (kPV * kPV) + e] = v;
+  }
+  if (zsplit > 1) {
+    __threadfence();  // the partial Gram is visible before the arrival is
+    __syncthreads();
+    if (tid == 0) s_last = (atomicAdd(arrivals + pair_id, 1u) == (unsigned)(zsplit - 1));
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    for (int e = tid; e < kPV * kPV; e += 256) {
+      double v = 0.0;
+      for (int z = 0; z < zsplit; ++z) v += __ldcg(S + (pair_id * zsplit + z) * (kPV * kPV) + e);
+      m.S[e >> 5][e & 31] = v;
+    }
+    if (tid == 0) arrivals[pair_id] = 0;  // ready for the next round
+  }
+  for (int e = tid; e < kPV * kPV; e += 256) m.J[e >> 5][e & 31] = ((e >> 5) == (e & 31)) ? 1.0 : 0.0;
+  __syncthreads();
+  const double off = pair_max_cosine(m, tid);
+  if (tid == 0) {
+    atomicMax(offmax + b, as_ull(off));
+    rot_flag[pair_id] = (off > skip_tol) ? 1 : 0;
+  }
+  if (!(off > skip_tol)) return;
+  pair_eigenvectors(m, tid, max_inner);
+  double* out = Jm + pair_id * (kPV * kPV);
   for (int e = tid; e < kPV * kPV; e += 256) out[e] = m.J[e >> 5][e & 31];
 }
 
@@ -552,6 +671,9 @@ int setup_attrs() {
     e = cudaFuncSetAttribute(k_jacobi_rotate, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              kRingStages * kPV * kRotStride * 8);
   if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(k_jacobi_gram_eig, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             kGeStages * kPV * kGramStride * 8);
+  if (e == cudaSuccess)
     e = cudaFuncSetAttribute(k_jacobi_round_fused, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              kPV * fused_stride(kFusedMaxLd) * 8);
   if (e != cudaSuccess) return trb_set_error(TRB_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
@@ -561,8 +683,8 @@ int setup_attrs() {
 
 }  // namespace
 
-int g_jacobi_fused = 1;
-extern "C" void trb_jacobi_set_fused(int enabled) { g_jacobi_fused = enabled ? 1 : 0; }
+int g_jacobi_fused = 3;  // bit 0: one kernel per round for short rows; bit 1: Gram + eigenvectors in one kernel
+extern "C" void trb_jacobi_set_fused(int mask) { g_jacobi_fused = mask & 3; }
 int g_jacobi_waves = 4;  // measured on B200 (B = 16, 2048 x 2048): 4 waves 43.8 ms, 8 waves 47.0, 2 waves 44.8, 16 waves 52.9 per instance
 extern "C" void trb_jacobi_set_waves(int waves) { g_jacobi_waves = waves > 0 ? waves : 4; }
 
@@ -588,7 +710,7 @@ static int enqueue_jacobi_sweep(double* A, int64_t strideA, int B, int np, int l
   // a CTA holding 100-200 KB of rows cannot (measured, 500 x 500: B = 1 / 8 / 64 instances 13.8 /
   // 1.96 / 1.66 ms each fused against 15.5 / 2.41 / 1.34 unfused).
   const int fused_per_sm = (int)(220000 / ((size_t)kPV * fused_stride(ld) * 8 + sizeof(EigSmem) + 64));
-  if (g_jacobi_fused && ld <= kFusedMaxLd &&
+  if ((g_jacobi_fused & 1) && ld <= kFusedMaxLd &&
       (long long)npairs * B <= (long long)trb_sm_count_cached() * (fused_per_sm < 1 ? 1 : fused_per_sm)) {
     cudaMemsetAsync(offmax, 0, sizeof(double) * B, st);
     for (int round = 0; round < nb - 1; ++round) {
@@ -604,16 +726,27 @@ static int enqueue_jacobi_sweep(double* A, int64_t strideA, int B, int np, int l
   const int zsplit = (ld + chunk - 1) / chunk;
   const dim3 grid(npairs, B, zsplit);
   cudaMemsetAsync(offmax, 0, sizeof(double) * B, st);
+  // rot_flag holds 2 * B * npairs ints: the rotate flags, then the per-pair arrival counters
+  unsigned int* arrivals = reinterpret_cast<unsigned int*>(rot_flag + (size_t)B * npairs);
+  if (g_jacobi_fused & 2) cudaMemsetAsync(arrivals, 0, sizeof(unsigned int) * (size_t)B * npairs, st);
   for (int round = 0; round < nb - 1; ++round) {
-    {
+    if (g_jacobi_fused & 2) {  // Gram and eigenvectors in one launch
       trb_launch_scope scope_(2, st);
-      k_jacobi_gram<<<grid, kSetupThreads, kRingStages * kPV * kGramStride * 8, st>>>(A, strideA, ld, nb, round, chunk,
-                                                                                     Swork);
-    }
-    {
-      trb_launch_scope scope_(2, st);
-      k_jacobi_eig<<<dim3(npairs, B), 256, 0, st>>>(Swork, zsplit, Jwork, rot_flag,
-                                                     reinterpret_cast<unsigned long long*>(offmax), skip_tol, max_inner);
+      k_jacobi_gram_eig<<<grid, 256, kGeStages * kPV * kGramStride * 8, st>>>(
+          A, strideA, ld, nb, round, chunk, Swork, arrivals, Jwork, rot_flag,
+          reinterpret_cast<unsigned long long*>(offmax), skip_tol, max_inner);
+    } else {
+      {
+        trb_launch_scope scope_(2, st);
+        k_jacobi_gram<<<grid, kSetupThreads, kRingStages * kPV * kGramStride * 8, st>>>(A, strideA, ld, nb, round,
+                                                                                       chunk, Swork);
+      }
+      {
+        trb_launch_scope scope_(2, st);
+        k_jacobi_eig<<<dim3(npairs, B), 256, 0, st>>>(Swork, zsplit, Jwork, rot_flag,
+                                                       reinterpret_cast<unsigned long long*>(offmax), skip_tol,
+                                                       max_inner);
+      }
     }
     {
       trb_launch_scope scope_(2, st);

@@ -282,7 +282,7 @@ def jacobi_workspace(B, n_rows, ld, dev):
     z = lib.trb_jacobi_zsplit(B, n_rows, ld)
     return dict(S=t.empty((B, pairs, z, JACOBI_ROWS * JACOBI_ROWS), dtype=t.float64, device=dev),
                 J=t.empty((B, pairs, JACOBI_ROWS * JACOBI_ROWS), dtype=t.float64, device=dev),
-                flag=t.zeros((B, pairs), dtype=t.int32, device=dev),
+                flag=t.zeros((2, B, pairs), dtype=t.int32, device=dev),     # rotate flags + arrival counters
                 off=t.zeros(B, dtype=t.float64, device=dev))
 
 
