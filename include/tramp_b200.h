@@ -240,10 +240,11 @@ int trb_jacobi_zsplit(int B, int np, int ld);
 /* tuning: the column range of a pair is split over CTAs until the grid holds about `waves`
  * waves of resident CTAs (default 4; fewer waves = longer CTAs, more tail) */
 void trb_jacobi_set_waves(int waves);
-/* kernel fusion (tuning / A-B tests), a bit mask, default 3: bit 0 = rows of at most 768 doubles and
+/* kernel fusion (tuning / A-B tests), a bit mask, default 1: bit 0 = rows of at most 768 doubles and
  * one wave of pairs: Gram, eigenvectors and rotation of a pair as ONE kernel per round, the pair
  * resident in shared memory; bit 1 = Gram and eigenvectors in one kernel (the CTA that completes a
- * pair's Gram matrix goes on to its eigen-solve); 0 = three launches per round */
+ * pair's Gram matrix goes on to its eigen-solve; measured no faster, off by default); 0 = three
+ * launches per round */
 void trb_jacobi_set_fused(int mask);
 int trb_jacobi_sweep(double* A, int64_t strideA, int B, int np, int ld, double* Swork,
                      double* Jwork, int* rot_flag, double* offmax, double skip_tol,

@@ -104,7 +104,7 @@ def test_fused_kernels_match_three_kernel_path(shape):
             Ut, s, Vt = thin_svd_device(ops.to_dev(W), "jacobi")
             out[mask] = (Ut.cpu().numpy(), s.cpu().numpy(), Vt.cpu().numpy(), LAST_SETUP_STATS["sweeps"])
     finally:
-        lib.trb_jacobi_set_fused(3)
+        lib.trb_jacobi_set_fused(1)
     s_ref = np.linalg.svd(W, compute_uv=False)
     for mask in (3, 2, 1):
         assert_allclose(out[mask][1], s_ref, rtol=1e-11)

@@ -113,7 +113,7 @@ def main():
     ap.add_argument("--direct", action="store_true", help="also time the route on W itself")
     ap.add_argument("--waves", type=int, default=0, help="trb_jacobi_set_waves (0: library default)")
     ap.add_argument("--inner", type=int, default=0, help="sweeps of the inner 32 x 32 Jacobi (0: default)")
-    ap.add_argument("--fused-mask", type=int, default=-1, help="trb_jacobi_set_fused (-1: library default 3)")
+    ap.add_argument("--fused-mask", type=int, default=-1, help="trb_jacobi_set_fused (-1: library default 1)")
     args = ap.parse_args()
     assert torch.cuda.is_available(), "needs a CUDA device"
     from tramp_b200 import _lib

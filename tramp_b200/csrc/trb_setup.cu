@@ -335,8 +335,9 @@ k_jacobi_eig(const double* __restrict__ S, int zsplit, double* __restrict__ Jm, 
 // an arrival counter per pair, partial sums added in chunk order, so the result does not depend
 // on which CTA is last) goes straight on to the 32 x 32 Jacobi.  That kernel is bound by
 // instruction issue and FP64 latency, this one by HBM: with three CTAs per SM in different phases
-// the eigen-solves run in the shadow of the other CTAs' streaming instead of in a launch of
-// their own (measured: Gram 110 us + eigenvectors 70 us per 1024 pairs as two launches).
+// the eigen-solves were meant to run in the shadow of the other CTAs' streaming.  Measured: no gain
+// (see g_jacobi_fused), so the variant is kept as an option (trb_jacobi_set_fused bit 1), off by
+// default.
 constexpr int kGeStages = 3;
 __global__ void __launch_bounds__(256, 3)
 k_jacobi_gram_eig(const double* __restrict__ A, int64_t strideA, int ld, int nb, int round, int chunk,
@@ -683,7 +684,12 @@ int setup_attrs() {
 
 }  // namespace
 
-int g_jacobi_fused = 3;  // bit 0: one kernel per round for short rows; bit 1: Gram + eigenvectors in one kernel
+// bit 0: one kernel per round for short rows and few pairs (default on); bit 1: Gram + eigenvectors in
+// one kernel (default OFF: measured on B200 at 2048 x 2048, B = 64 / 16: 184.9 / 51.2 ms per sweep
+// fused against 180.9 / 48.1 with the eigen-solves in a launch of their own -- at 3 CTAs per SM the
+// 31 dependent steps of the inner Jacobi are latency-bound, ~25 us per pair, and leave the memory
+// pipe idle about as long as the separate launch takes)
+int g_jacobi_fused = 1;
 extern "C" void trb_jacobi_set_fused(int mask) { g_jacobi_fused = mask & 3; }
 int g_jacobi_waves = 4;  // measured on B200 (B = 16, 2048 x 2048): 4 waves 43.8 ms, 8 waves 47.0, 2 waves 44.8, 16 waves 52.9 per instance
 extern "C" void trb_jacobi_set_waves(int waves) { g_jacobi_waves = waves > 0 ? waves : 4; }
