@@ -327,7 +327,8 @@ typedef struct {
   /* posteriors (update_variables): rx [B, ldn], rz [B, ldm], vx, vz [B] */
   double* rx; double* rz; double* vx; double* vz;
   /* scratch: tz, tx, coef: [B, R]; part: [B, nslots, max(ldn, ldm)];
-   * scr_n: [B, ldn]; scr_m: [B, ldm]; vlin: [B]; stats: [B, 4] */
+   * scr_n: [B, ldn]; scr_m: [B, ldm]; vlin: [B]; stats: [B, 4] (columns 0, 1: tolerance sums of z;
+   * columns 2, 3: reserved for the library) */
   double* tz; double* tx; double* coef; double* part;
   double* scr_n; double* scr_m; double* vlin; double* stats;
   /* per-instance control/status: active[B] (1 = iterate), flags[B],
@@ -418,6 +419,22 @@ int trb_sweep_run(const trb_sweep* sw, int it0, int n_iter, int fresh, void* str
  * (less than ~1 GB of operator traffic per iteration) as a CUDA graph; 0 turns
  * that off (default on; the environment variable TRB_CUDA_GRAPHS=0 does the same). */
 void trb_set_cuda_graphs(int enabled);
+
+/* trb_sweep_run runs the rescale stages S1 / S2 as an epilogue of the GEMV projections P1 / P3
+ * (the CTA that projects the last rows of an instance rescales it: 7 launches per iteration
+ * instead of 9) whenever the operator passes are TMA GEMVs of one column panel and the sweep is not
+ * row-sharded; 0 turns that off (default on; TRB_FUSE_RESCALE=0 does the same).  The arrival
+ * counters live in columns 2, 3 of `stats`, which trb_sweep_run zeroes itself. */
+void trb_set_fused_rescale(int enabled);
+
+/* The x update (bit 0), the z update with a Gaussian likelihood (bit 1) and the prior's message
+ * (bit 2, non-constant priors) run as CHUNKED kernels inside the sweep: 1024 elements per CTA,
+ * every load of a thread issued at once, the chunk sums added in chunk order by the CTA that
+ * arrives last (arrival counters in columns 2, 3 of `stats`; the chunk sums borrow scr_n / scr_m).  A
+ * cleared bit selects the one-CTA(-cluster)-per-instance kernel instead; -1 = default (all;
+ * TRB_UPDATE_KERNELS=<mask> does the same).  Callers of trb_sweep_stage zero `stats` once
+ * before the first stage; trb_sweep_run does it itself. */
+void trb_set_update_kernels(int mask);
 
 /* A single instance (B = 1) whose iteration is launch-bound runs ALL its
  * iterations inside one cooperative launch of one CTA per SM, four grid-wide

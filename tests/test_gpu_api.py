@@ -791,6 +791,105 @@ def test_cuda_graph_replay_is_bitwise_identical_to_plain_launches(sw):
         assert out[0][5] == out[1][5]      # the launch accounting counts replayed kernels too
 
 
+def _sweep_with_and_without(lib, setter, on, off, build, run):
+    """The same model iterated twice, with one kernel choice of trb_sweep_run switched on / off."""
+    out = []
+    for value in (on, off):
+        getattr(lib, setter)(value)
+        lib.trb_set_persistent_sweep(0)
+        try:
+            ep = build()
+            lib.trb_profile_reset(0)
+            track = run(ep)
+            d = ep.get_variables_data()
+            out.append(dict(rx=d["x"]["r"], rz=d["z"]["r"], vx=d["x"]["v"], vz=d["z"]["v"],
+                            mse=np.array([e["mse"] for e in track.errors]),
+                            n_iter=np.array(ep.n_iter_per_instance),
+                            launches=int(lib.trb_profile_launches(-1))))
+        finally:
+            getattr(lib, setter)(on)
+            lib.trb_set_persistent_sweep(-1)
+    assert np.array_equal(out[0]["n_iter"], out[1]["n_iter"])
+    return out
+
+
+def _kernel_choice_cases(sw):
+    """(build, run) pairs: single instances spread over many CTAs (golden configs) and a batch
+    whose instances stop at different iterations."""
+    from tramp_b200.priors import GaussBernoulliPrior
+    from tramp_b200.likelihoods import GaussianLikelihood
+    from tramp_b200.channels import LinearChannel
+    from tramp_b200.variables import SISOVariable as V
+    from tramp_b200.algos import ExpectationPropagation, TrackErrors, EarlyStoppingEP, JoinCallback
+    cases = []
+    for idx in (0, 2, 4, 6):
+        cfg = _configs(sw)[idx]
+        name = cfg["name"]
+
+        def run(ep, cfg=cfg, name=name):
+            track = TrackErrors({"x": sw[name + "_x"]})
+            ep.iterate(max_iter=cfg["n_iter"], callback=track, damping=cfg["damping"])
+            return track
+        cases.append((lambda cfg=cfg, name=name: ExpectationPropagation(_build(cfg, sw, name)), run, False))
+    rng = np.random.RandomState(19)
+    B, N, M = 7, 2500, 1300            # three chunks of x, two of z per instance
+    W = rng.randn(B, M, N) / np.sqrt(N)
+    x = rng.randn(B, N) * (rng.rand(B, N) < 0.1)
+    y = np.einsum("bmn,bn->bm", W, x) + 0.1 * rng.randn(B, M)
+    lin = LinearChannel(W)
+    lin._setup()                       # factorise once, outside the launch counts
+
+    def build():
+        return ExpectationPropagation((GaussBernoulliPrior(size=N, rho=0.1, batch=B) @ V("x") @ lin @ V("z")
+                                       @ GaussianLikelihood(y=y, var=1e-2)).to_model())
+
+    def run_es(ep):
+        track = TrackErrors({"x": x})
+        ep.schedule = "general"
+        ep.iterate(max_iter=200, callback=JoinCallback([track, EarlyStoppingEP(tol=1e-6)]))
+        return track
+    cases.append((build, run_es, True))
+    return cases
+
+
+def test_rescale_as_projection_epilogue_equals_separate_launches(sw):
+    """trb_sweep_run runs the rescale stages S1 / S2 inside the GEMV projections P1 / P3 (the CTA
+    that completes an instance rescales it).  Same arithmetic per coefficient; only the order of
+    the spectrum sum behind the variance differs: 1e-12 against the nine-launch iteration, with
+    two launches fewer per iteration."""
+    from tramp_b200 import _lib
+    lib = _lib.load()
+    for build, run, batch in _kernel_choice_cases(sw):
+        a, b = _sweep_with_and_without(lib, "trb_set_fused_rescale", 1, 0, build, run)
+        for k in ("rx", "rz", "vx", "vz", "mse"):       # mse: NaN once an instance has stopped
+            assert_allclose(a[k], b[k], rtol=1e-12, atol=1e-12 * np.nanmax(np.abs(b[k])), err_msg=k)
+        assert a["launches"] < b["launches"]
+        if batch:
+            assert len(set(a["n_iter"].tolist())) > 1     # the instances did stop at different iterations
+
+
+def test_chunked_update_kernels_equal_one_cta_per_instance(sw):
+    """The chunked x / z updates (1024 elements per CTA, the last-arriving CTA adds the chunk sums)
+    do the arithmetic of k_x_update / k_z_update element for element: messages and posteriors
+    are bit-identical; only the sums behind the recorded mse / tolerance are added in another
+    order.  The chunked prior message against the one-CTA kernel: 1e-10."""
+    from tramp_b200 import _lib
+    lib = _lib.load()
+    for build, run, batch in _kernel_choice_cases(sw):
+        for mask in (4, 5, 6):
+            a, b = _sweep_with_and_without(lib, "trb_set_update_kernels", -1, mask, build, run)
+            for k in ("rx", "rz", "vx", "vz"):
+                assert np.array_equal(a[k], b[k]), (mask, k)
+            assert_allclose(a["mse"], b["mse"], rtol=1e-12)
+            assert a["launches"] == b["launches"]
+        # the chunked prior adds its chunk sums of v in another order than the one-CTA kernel:
+        # the mean variance, and with it everything downstream, moves in the last bits
+        a, b = _sweep_with_and_without(lib, "trb_set_update_kernels", -1, 3, build, run)
+        for k in ("rx", "rz", "vx", "vz", "mse"):
+            assert_allclose(a[k], b[k], rtol=1e-10, atol=1e-12 * np.nanmax(np.abs(b[k])), err_msg=k)
+        assert a["launches"] == b["launches"]
+
+
 @pytest.mark.parametrize("idx", range(9))
 def test_persistent_sweep_matches_launch_per_stage_path(sw, idx):
     """One instance runs all its iterations inside ONE launch (trb_persist.cu, four

@@ -141,6 +141,8 @@ SIGNATURES = {
     "trb_comm_destroy": (_I, [_P]),
     "trb_comm_all_reduce": (_I, [_P, _P, C.c_size_t, _P, _P]),
     "trb_set_cuda_graphs": (None, [_I]),
+    "trb_set_fused_rescale": (None, [_I]),
+    "trb_set_update_kernels": (None, [_I]),
     "trb_set_persistent_sweep": (None, [_I]),
     "trb_sweep_run": (_I, [C.POINTER(TrbSweep), _I, _I, _I, _P]),
     "trb_sweep_stage": (_I, [C.POINTER(TrbSweep), _I, _I, _I, _I, _P]),

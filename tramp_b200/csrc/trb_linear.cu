@@ -185,7 +185,124 @@ __device__ __forceinline__ void consumer_bar() {
   asm volatile("bar.sync 1, %0;" ::"n"(kConsumers) : "memory");
 }
 
-template <int NB, bool EXPAND>
+// ---- rescale in the singular basis (linear_channel.py:58-67 compute_n_eff, :74 resolvent,
+// :91-105 variances), shared by k_lin_rescale and by the epilogue of the fused projection
+struct RescalePlan {
+  double az_v, ratio;
+  int sum_mode;  // 1 = sum of the spectrum (:100-102, dir 0 and ax == 0), 2 = sum s2 / (ratio + s2)
+                 // (:66-67), 0 = none (:60-65: ax == 0 or ratio == 0)
+};
+
+__device__ __forceinline__ RescalePlan rescale_plan(int dir, double az, double ax) {
+  RescalePlan p;
+  p.az_v = az;
+  if (dir == 1) p.az_v = (az != az) ? az : fmax(1e-11, az);  // :94 np.maximum(1e-11, az)
+  p.ratio = p.az_v / ax;
+  p.sum_mode = (dir == 0 && ax == 0) ? 1 : ((ax == 0 || p.ratio == 0) ? 0 : 2);
+  return p;
+}
+
+// One thread's share (i = first, first + stride, ...) of one pass over the spectrum: the
+// coefficients in the singular basis AND the sum the variance needs (they do not depend on each
+// other).  U elements at a time, all their loads issued before the first store (the stores would
+// otherwise serialise the loads: one memory round trip per element).  CG: tz / tx were written
+// by other CTAs of this launch -> read them from L2.
+template <bool CG, int U>
+__device__ __forceinline__ double rescale_share(int dir, int R, int rank, bool null_space,
+                                                const RescalePlan& pl, const double* __restrict__ sb,
+                                                const double* __restrict__ s2b, double az, double ax,
+                                                const double* tz, const double* tx, double* coef,
+                                                double* snap_tx, int first, int stride) {
+  double part = 0.0;
+  for (int i0 = first; i0 < R; i0 += stride * U) {
+    double s2v[U], sv[U], tzv[U], txv[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int i = i0 + u * stride;
+      if (i < R) {
+        s2v[u] = s2b[i];
+        if (coef) {
+          sv[u] = sb[i];
+          tzv[u] = CG ? __ldcg(tz + i) : tz[i];
+          txv[u] = CG ? __ldcg(tx + i) : tx[i];
+        }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int i = i0 + u * stride;
+      if (i < R) {
+        const double s2i = s2v[u];
+        if (i < rank) {
+          if (pl.sum_mode == 1) part += s2i;
+          else if (pl.sum_mode == 2) part += s2i / (pl.ratio + s2i);
+        }
+        if (coef) {
+          const double si = sv[u];
+          const double res = 1 / (az + ax * s2i);  // :74
+          const double tzi = tzv[u], txi = txv[u];
+          if (snap_tx) snap_tx[i] = txi;
+          double c;
+          if (dir == 0) {
+            c = si * (res * (tzi + si * txi));
+          } else if (!null_space) {
+            c = res * (tzi + si * txi);
+          } else {
+            // res - 1/az = -(ax*s2/az)*res, applied to tz; the bz/az term is added
+            // by the consumer of the expansion
+            c = res * (si * txi - (ax * s2i / az) * tzi);
+          }
+          coef[i] = c;
+        }
+      }
+    }
+  }
+  return part;
+}
+
+// total = the instance-wide sum of rescale_share (ignored when sum_mode == 0)
+__device__ __forceinline__ double rescale_variance(int dir, int Nz, int Nx, int rank,
+                                                   const RescalePlan& pl, double az, double ax,
+                                                   double total) {
+  if (pl.sum_mode == 1) {  // :100-102
+    const double s_mean = total / rank;
+    return s_mean * rank / (Nx * az);
+  }
+  double n_eff;
+  if (ax == 0) {  // :60-62
+    n_eff = 0.;
+  } else if (pl.ratio == 0) {  // :63-65
+    n_eff = (double)rank / Nz;
+  } else {  // :66-67
+    n_eff = total / Nz;
+  }
+  if (dir == 0) {
+    const double alpha = (double)Nx / Nz;
+    return n_eff / (alpha * ax);  // :103-105
+  }
+  return (1 - n_eff) / pl.az_v;  // :95-97
+}
+
+// Epilogue of a projection whose result feeds the rescale directly (sweep stages P1+S1, P3+S2):
+// the CTA that completes the last rows of an instance computes that instance's coefficients and
+// variance while the other CTAs go on streaming -- no separate launch, no idle GPU in between.
+struct RescaleEpi {
+  unsigned int* counter;  // rows of instance b projected so far: counter[b * counter_stride], zero on entry
+  int counter_stride;
+  int dir, Nz, Nx, rank, null_space;
+  const double* s;
+  const double* s2;
+  int64_t stride_s;
+  const double* az;       // [B]
+  const double* ax;       // [B]
+  const double* t_other;  // the projection this launch does not write (dir 0: tx, dir 1: tz), [B, R]
+  double* coef;           // [B, R]
+  double* v_out;          // [B]
+  double* snap_tx;        // nullable, [B, R]
+};
+
+// MODE: 0 project, 1 expand, 2 project + rescale epilogue
+template <int NB, int MODE>
 __global__ void __launch_bounds__(kTmaThreads, 1)
 k_gemv_tma(const double* __restrict__ A, int64_t strideA, int R, int n, int ld, int B,
            const double* __restrict__ vec, int ldvec,  // project: input vector; expand: coef [B,R]
@@ -195,12 +312,14 @@ k_gemv_tma(const double* __restrict__ A, int64_t strideA, int R, int n, int ld, 
            int out_ld,       // expand: leading dimension of `part`
            int npanels,      // > 1: A is npanels column panels of `ld` doubles (the last one may be
                              // narrower: full_ld, full_n); every CTA walks its rows once per panel
-           int full_ld, int full_n) {
+           int full_ld, int full_n, RescaleEpi epi) {
+  constexpr bool EXPAND = MODE == 1;
   constexpr int RC = TmaCfg<NB>::RC;
   extern __shared__ __align__(128) double ring[];  // nstages * stage_doubles
   __shared__ __align__(8) uint64_t full_bar[kMaxStages];
   __shared__ __align__(8) uint64_t empty_bar[kMaxStages];
   __shared__ double red[2][kConsumers / 32][kGroupRows];
+  __shared__ int sh_last;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (tid == 0) {
@@ -322,6 +441,49 @@ k_gemv_tma(const double* __restrict__ A, int64_t strideA, int R, int n, int ld, 
         }
         red_buf ^= 1;
       }
+      if constexpr (MODE == 2) {
+        // ---- this CTA's rows of instance s.b are written: count them in; the CTA that
+        // completes the instance rescales it (threadfence + atomic: the writers' stores are
+        // visible to whoever observes the full count)
+        __threadfence();
+        consumer_bar();
+        if (tid == 0) {
+          const unsigned int rows = (unsigned int)(s.i1 - s.i0);
+          unsigned int* cnt = epi.counter + (size_t)s.b * epi.counter_stride;
+          __threadfence();
+          const unsigned int before = atomicAdd(cnt, rows);
+          const int last = (before + rows == (unsigned int)R);
+          if (last) {
+            *cnt = 0;  // nobody else touches this instance's counter before the next launch
+            __threadfence();
+          }
+          sh_last = last;
+        }
+        consumer_bar();
+        if (sh_last) {  // uniform over the consumers
+          const int b = s.b;
+          const double az = epi.az[b], ax = epi.ax[b];
+          const RescalePlan pl = rescale_plan(epi.dir, az, ax);
+          const size_t o = (size_t)b * R;
+          const double* t_mine = out + o;
+          const double* t_oth = epi.t_other + o;
+          const double part = rescale_share<true, 8>(
+              epi.dir, R, epi.rank, epi.null_space != 0, pl, epi.s + (size_t)b * epi.stride_s,
+              epi.s2 + (size_t)b * epi.stride_s, az, ax, epi.dir == 0 ? t_mine : t_oth,
+              epi.dir == 0 ? t_oth : t_mine, epi.coef + o, epi.snap_tx ? epi.snap_tx + o : nullptr, tid,
+              kConsumers);
+          double tot = warp_sum(part);
+          if (lane == 0) red[red_buf][warp][0] = tot;
+          consumer_bar();
+          if (tid == 0) {
+            tot = 0.0;
+#pragma unroll
+            for (int w = 0; w < kConsumers / 32; ++w) tot += red[red_buf][w][0];
+            epi.v_out[b] = rescale_variance(epi.dir, epi.Nz, epi.Nx, epi.rank, pl, az, ax, tot);
+          }
+          red_buf ^= 1;
+        }
+      }
     } else {
       // ---- expand: column accumulators in registers for the whole segment
       double2 acc[NB];
@@ -437,62 +599,14 @@ k_lin_rescale(int dir, int R, int Nz, int Nx, int rank, int null_space_flag,
   const double* sb = s + (size_t)b * stride_s;
   const double* s2b = s2 + (size_t)b * stride_s;
   const size_t off = (size_t)b * R;
-  // ---- one pass over the spectrum: the coefficients in the singular basis AND the sum the
-  // variance needs (they do not depend on each other; a second pass only added latency)
-  double az_v = az;
-  if (dir == 1) az_v = (az != az) ? az : fmax(1e-11, az);  // :94 np.maximum(1e-11, az)
-  const double ratio = az_v / ax;
-  // which sum: 1 = sum of the spectrum (:100-102, dir 0 and ax == 0), 2 = sum s2 / (ratio + s2)
-  // (:66-67), 0 = none (:60-65: ax == 0 or ratio == 0)
-  const int sum_mode = (dir == 0 && ax == 0) ? 1 : ((ax == 0 || ratio == 0) ? 0 : 2);
-  const bool null_space = null_space_flag != 0;
-  double part = 0.0;
-  for (int i = gtid; i < R; i += T_) {
-    const double s2i = s2b[i];
-    if (i < rank) {
-      if (sum_mode == 1) part += s2i;
-      else if (sum_mode == 2) part += s2i / (ratio + s2i);
-    }
-    if (coef) {
-      const double si = sb[i];
-      const double res = 1 / (az + ax * s2i);  // :74
-      const double tzi = tz[off + i], txi = tx[off + i];
-      if (snap_tx) snap_tx[off + i] = txi;
-      double c;
-      if (dir == 0) {
-        c = si * (res * (tzi + si * txi));
-      } else if (!null_space) {
-        c = res * (tzi + si * txi);
-      } else {
-        // res - 1/az = -(ax*s2/az)*res, applied to tz; the bz/az term is added
-        // by the consumer of the expansion
-        c = res * (si * txi - (ax * s2i / az) * tzi);
-      }
-      coef[off + i] = c;
-    }
-  }
+  const RescalePlan pl = rescale_plan(dir, az, ax);
+  const double part = rescale_share<false, 4>(dir, R, rank, null_space_flag != 0, pl, sb, s2b, az, ax,
+                                           tz ? tz + off : nullptr, tx ? tx + off : nullptr,
+                                           coef ? coef + off : nullptr, snap_tx ? snap_tx + off : nullptr,
+                                           gtid, T_);
   if (!v_out) return;
-  // ---- variance
-  double v;
-  if (sum_mode == 1) {  // :100-102
-    const double s_mean = cluster_sum(part, sh) / rank;
-    v = s_mean * rank / (Nx * az);
-  } else {
-    double n_eff;
-    if (ax == 0) {  // :60-62
-      n_eff = 0.;
-    } else if (ratio == 0) {  // :63-65
-      n_eff = (double)rank / Nz;
-    } else {  // :66-67
-      n_eff = cluster_sum(part, sh) / Nz;
-    }
-    if (dir == 0) {
-      const double alpha = (double)Nx / Nz;
-      v = n_eff / (alpha * ax);  // :103-105
-    } else {
-      v = (1 - n_eff) / az_v;  // :95-97
-    }
-  }
+  const double total = pl.sum_mode ? cluster_sum(part, sh) : 0.0;
+  const double v = rescale_variance(dir, Nz, Nx, rank, pl, az, ax, total);
   if (gtid == 0) v_out[b] = v;
 }
 
@@ -522,11 +636,12 @@ bool plan_tma(int ld, TmaPlan& p) {
   return true;
 }
 
-template <int NB, bool EXPAND>
+template <int NB, int MODE>
 int launch_tma(const TmaPlan& p, int G, const double* A, int64_t strideA, int R, int n, int ld,
                int B, const double* vec, int ldvec, double* out, int nslots, const int* active,
-               cudaStream_t st, int row_stride, int out_ld, int npanels, int full_ld, int full_n) {
-  auto kern = k_gemv_tma<NB, EXPAND>;
+               cudaStream_t st, int row_stride, int out_ld, int npanels, int full_ld, int full_n,
+               const RescaleEpi& epi) {
+  auto kern = k_gemv_tma<NB, MODE>;
   static bool configured = false;  // per instantiation
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -537,18 +652,19 @@ int launch_tma(const TmaPlan& p, int G, const double* A, int64_t strideA, int R,
   }
   kern<<<G, kTmaThreads, p.smem, st>>>(A, strideA, R, n, ld, B, vec, ldvec, out, nslots, active,
                                        p.stages, p.stage_doubles, row_stride, out_ld, npanels, full_ld,
-                                       full_n);
+                                       full_n, epi);
   return TRB_OK;
 }
 
-template <bool EXPAND>
+template <int MODE>
 int dispatch_tma(const TmaPlan& p, int G, const double* A, int64_t strideA, int R, int n, int ld,
                  int B, const double* vec, int ldvec, double* out, int nslots, const int* active,
-                 cudaStream_t st, int row_stride, int out_ld, int npanels, int full_ld, int full_n) {
-#define TRB_TMA_CASE(NB_)                                                                          \
-  case NB_:                                                                                        \
-    return launch_tma<NB_, EXPAND>(p, G, A, strideA, R, n, ld, B, vec, ldvec, out, nslots, active, \
-                                   st, row_stride, out_ld, npanels, full_ld, full_n);
+                 cudaStream_t st, int row_stride, int out_ld, int npanels, int full_ld, int full_n,
+                 const RescaleEpi& epi = RescaleEpi()) {
+#define TRB_TMA_CASE(NB_)                                                                        \
+  case NB_:                                                                                      \
+    return launch_tma<NB_, MODE>(p, G, A, strideA, R, n, ld, B, vec, ldvec, out, nslots, active, \
+                                 st, row_stride, out_ld, npanels, full_ld, full_n, epi);
   switch (p.nb) {
     TRB_TMA_CASE(1)
     TRB_TMA_CASE(2)
@@ -629,11 +745,11 @@ extern "C" int trb_lin_project(const double* A, int64_t strideA, int R, int n, i
     TmaPlan pq;
     if (!plan_tma(pan.width, pq) || pq.nb < 8)
       return trb_set_error(TRB_ERR_UNSUPPORTED, "trb_lin_project: cannot panel ld=%d", ld);
-    rc = dispatch_tma<false>(pq, geo.G, A, strideA, R, n, pan.width, B, vec, ldvec, t, 0, active, st,
+    rc = dispatch_tma<0>(pq, geo.G, A, strideA, R, n, pan.width, B, vec, ldvec, t, 0, active, st,
                              ld, 0, pan.count, ld, n);
     if (rc) return rc;
   } else if (impl == 2) {
-    rc = dispatch_tma<false>(p, geo.G, A, strideA, R, n, ld, B, vec, ldvec, t, 0, active, st, ld, 0,
+    rc = dispatch_tma<0>(p, geo.G, A, strideA, R, n, ld, B, vec, ldvec, t, 0, active, st, ld, 0,
                              1, ld, n);
     if (rc) return rc;
   } else {
@@ -647,6 +763,60 @@ extern "C" int trb_lin_project(const double* A, int64_t strideA, int R, int n, i
     }
     k_project_ldg<<<geo.G, kLdgThreads, smem, st>>>(A, strideA, R, n, ld, B, vec, ldvec, t, active);
   }
+  TRB_CHECK_LAUNCH();
+  return TRB_OK;
+}
+
+// rows of `ld` doubles fit one stage of the TMA ring (no column panels)
+bool trb_lin_single_panel(int ld) {
+  TmaPlan p;
+  return ld > 0 && ld % 2 == 0 && plan_tma(ld, p);
+}
+
+// trb_lin_project followed by trb_lin_rescale in ONE launch (sweep stages P1+S1 and P3+S2): the
+// CTA that projects the last rows of an instance rescales it (RescaleEpi above).  dir 0: t_out is
+// tz and t_other tx; dir 1: t_out is tx and t_other tz.  counter: one unsigned per instance
+// (counter[b * counter_stride]), zero on entry and zero again on exit.  TRB_ERR_UNSUPPORTED
+// (nothing launched) when the rows are too wide for one ring stage: the caller launches the two
+// kernels instead.
+int trb_lin_project_rescale(const double* A, int64_t strideA, int R, int n, int ld, int B,
+                            const double* vec, int ldvec, double* t_out, const int* active, int dir,
+                            int Nz, int Nx, int rank, int null_space, const double* s, const double* s2,
+                            int64_t stride_s, const double* az, const double* ax, const double* t_other,
+                            double* coef, double* v, double* snap_tx, unsigned int* counter,
+                            int counter_stride, void* stream) {
+  int rc = check_gemv_args(A, R, n, ld, B, vec, t_out);
+  if (rc) return rc;
+  TRB_CHECK_ARG(strideA % 2 == 0, "strideA must be even");
+  TRB_CHECK_ARG(ldvec >= n, "ldvec < n");
+  TRB_CHECK_ARG(s && s2 && az && ax && t_other && coef && v && counter, "null pointer");
+  TRB_CHECK_ARG(dir == 0 || dir == 1, "dir must be 0 or 1");
+  TRB_CHECK_ARG(R <= Nz && R <= Nx && rank >= 0 && rank <= R && counter_stride > 0, "bad shape");
+  TmaPlan p;
+  if (!plan_tma(ld, p)) return TRB_ERR_UNSUPPORTED;
+  cudaStream_t st = (cudaStream_t)stream;
+  const trb_expand_geom geo = trb_expand_geometry(B, R);
+  RescaleEpi epi;
+  epi.counter = counter;
+  epi.counter_stride = counter_stride;
+  epi.dir = dir;
+  epi.Nz = Nz;
+  epi.Nx = Nx;
+  epi.rank = rank;
+  epi.null_space = null_space;
+  epi.s = s;
+  epi.s2 = s2;
+  epi.stride_s = stride_s;
+  epi.az = az;
+  epi.ax = ax;
+  epi.t_other = t_other;
+  epi.coef = coef;
+  epi.v_out = v;
+  epi.snap_tx = snap_tx;
+  trb_launch_scope scope_(1, st);
+  rc = dispatch_tma<2>(p, geo.G, A, strideA, R, n, ld, B, vec, ldvec, t_out, 0, active, st, ld, 0, 1, ld,
+                       n, epi);
+  if (rc) return rc;
   TRB_CHECK_LAUNCH();
   return TRB_OK;
 }
@@ -668,11 +838,11 @@ extern "C" int trb_lin_expand(const double* A, int64_t strideA, int R, int n, in
     TmaPlan pq;
     if (!plan_tma(pan.width, pq) || pq.nb < 8)
       return trb_set_error(TRB_ERR_UNSUPPORTED, "trb_lin_expand: cannot panel ld=%d", ld);
-    rc = dispatch_tma<true>(pq, geo.G, A, strideA, R, n, pan.width, B, coef, 0, part, geo.nslots,
+    rc = dispatch_tma<1>(pq, geo.G, A, strideA, R, n, pan.width, B, coef, 0, part, geo.nslots,
                             active, st, ld, ld, pan.count, ld, ld);
     if (rc) return rc;
   } else if (impl == 2) {
-    rc = dispatch_tma<true>(p, geo.G, A, strideA, R, n, ld, B, coef, 0, part, geo.nslots, active, st,
+    rc = dispatch_tma<1>(p, geo.G, A, strideA, R, n, ld, B, coef, 0, part, geo.nslots, active, st,
                             ld, ld, 1, ld, n);
     if (rc) return rc;
   } else {

@@ -4,8 +4,9 @@
 // backward pass, update_variables), :70-127 (constant damping), :187-209 (NaN
 // check); algos/callbacks.py:250-286 (EarlyStoppingEP); algos/metrics.py:5-14.
 //
-// One iteration = 9 launches on one stream, B instances in lock step, no host
-// round trip (edge numbering e1..e8 as in SURVEY 3.3):
+// One iteration = 9 stages on one stream (7 launches: S1 and S2 run as epilogues of P1 and P3
+// when the operator passes are GEMVs), B instances in lock step, no host round trip (edge
+// numbering e1..e8 as in SURVEY 3.3):
 //   F1  factor_message(prior)   e8 -> e1 (=e2)
 //   P1  project  V_R^T b2       -> tz
 //   S1  rescale fwd             -> coef, vx(lin)
@@ -18,24 +19,13 @@
 // Each operator is streamed exactly twice per iteration (once as A^T x, once
 // as A c): 16*R*(N+M) bytes per instance-iteration.
 #include "trb_moments.cuh"
+#include "trb_updates.cuh"
 
 using namespace trb;
 
 namespace {
 
 constexpr int kUpThreads = 512;
-
-struct SlotInfo {
-  int ns;
-};
-
-__device__ __forceinline__ int slots_of(int b, int R, int B, int G) {
-  if (G <= 0) return 1;  // pre-reduced: the full sum sits in slot 0
-  const int64_t T = (int64_t)B * R;
-  const int kf = (int)part_owner((int64_t)b * R, T, G);
-  const int kl = (int)part_owner((int64_t)b * R + R - 1, T, G);
-  return kl - kf + 1;
-}
 
 constexpr int kUnroll = 2;  // elements per thread whose loads are issued together (2 CTAs of 512 threads per SM)
 
@@ -155,22 +145,7 @@ k_z_update(trb_sweep sw, int G, int first, int light, double* __restrict__ stats
   if (a3n != a3n || a5n != a5n) flag |= TRB_FLAG_NAN_A;
   if (a3n < 0 || a5n < 0) flag |= TRB_FLAG_NEG_A;
   const int all = cluster_or(flag, &sh_flag);
-  if (gtid == 0) {
-    if (snap) {
-      for (int e = 2; e < 6; ++e) sw.snap_edge_a[e * B + b] = ea[e * B + b];
-      sw.snap_vz[b] = sw.vz[b];
-    }
-    ea[2 * B + b] = a3;
-    ea[3 * B + b] = a3;  // e4 = e3 (sub_variables.py:21-25)
-    ea[4 * B + b] = a5;
-    ea[5 * B + b] = a5;  // e6 = e5 (sub_variables.py:27-31)
-    sw.vz[b] = 1. / a_hat;
-    if (!light) {
-      stats[b * 4 + 0] = red[0];
-      stats[b * 4 + 1] = red[1];
-    }
-    if (all) atomicOr(&sw.flags[b], all);
-  }
+  if (gtid == 0) z_tail(sw, b, light, stats, a3, a5, a_hat, all, red[0], red[1]);
 }
 
 __global__ void __launch_bounds__(kUpThreads, 2)
@@ -249,58 +224,107 @@ k_x_update(trb_sweep sw, int G, int it_host, double* __restrict__ stats, trb_pee
   if (a7n != a7n) flag |= TRB_FLAG_NAN_A;
   if (a7n < 0) flag |= TRB_FLAG_NEG_A;
   const int all = cluster_or(flag, &sh_flag);
-  if (gtid == 0) {
-    if (snap) {
-      sw.snap_edge_a[6 * B + b] = ea[6 * B + b];
-      sw.snap_edge_a[7 * B + b] = ea[7 * B + b];
-      sw.snap_vx[b] = sw.vx[b];
+  if (gtid == 0) x_tail(sw, b, it, stats, a7, a_hat, all, d2, n2, e_pos, e_neg);
+}
+
+// ---- chunked update kernels ---------------------------------------------------------------
+// The z / x updates are maps over the instance vector plus a few sums.  One CTA (or cluster) per
+// instance walks its vector in rounds of a few loads per thread, and the rounds' latencies add
+// up: ~80 KB in flight per SM where HBM needs ~150 KB (Little).  Here an instance is cut into
+// chunks of kChunk elements, one small CTA each (grid (chunks, B), 4 CTAs per SM), every thread
+// issues ALL its loads at once, and the chunk sums go to a scratch row of the instance; the CTA
+// that arrives last (threadfence + counter, columns 3 of `stats`) adds them in chunk order -- the
+// result does not depend on the arrival order -- and writes the instance's scalars (z_tail /
+// x_tail).  Per element the arithmetic is that of k_z_update / k_x_update, bit for bit.
+constexpr int kChThreads = 256;
+constexpr int kChE = 4;  // elements per thread
+constexpr int kChunk = kChThreads * kChE;
+constexpr int kZPartials = 3, kXPartials = 5;  // sums + flags per chunk
+
+// whole CTA; thread 0 has written this chunk's partial sums.  True in the CTA that arrives last.
+__device__ __forceinline__ bool chunk_arrive_last(unsigned int* cnt, int nchunk, int* sh_last) {
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const unsigned int before = atomicAdd(cnt, 1u);
+    const int last = (before + 1u == (unsigned int)nchunk);
+    if (last) {
+      *cnt = 0;  // nobody else touches the counter before the next launch
+      __threadfence();
     }
-    ea[6 * B + b] = a7;
-    ea[7 * B + b] = a7;  // e8 = e7
-    const double vx = 1. / a_hat;
-    sw.vx[b] = vx;
-    if (all) atomicOr(&sw.flags[b], all);
-    sw.n_iter[b] += 1;
-    const bool rec = it < sw.max_records;
-    if (rec && sw.rec_vx) sw.rec_vx[(size_t)it * B + b] = vx;
-    if (rec && sw.rec_vz) sw.rec_vz[(size_t)it * B + b] = sw.vz[b];
-    if (sw.x_true) {
-      const double mse = e_pos / N, mse_neg = e_neg / N;
-      if (rec && sw.rec_mse) sw.rec_mse[(size_t)it * B + b] = mse;
-      if (rec && sw.rec_smse) sw.rec_smse[(size_t)it * B + b] = fmin(mse, mse_neg);
+    *sh_last = last;
+  }
+  __syncthreads();
+  return *sh_last != 0;
+}
+
+// Gaussian likelihood (constant message e5, gaussian_likelihood.py:68-71): no sum is needed
+// before the second half of the update, so the whole z update is one pass.
+__global__ void __launch_bounds__(kChThreads, 4)
+k_z_update_chunked(trb_sweep sw, int G, int first, double* __restrict__ stats, trb_peers peers) {
+  __shared__ double sh[33 * 2];
+  __shared__ int sh_flag, sh_last;
+  const int b = blockIdx.y, chunk = blockIdx.x, nchunk = gridDim.x;
+  if (sw.active && !sw.active[b]) return;
+  const ZScalars z = z_scalars(sw, b);
+  int flag = z_scalar_flags(z);
+  if (peers.n > 0 && !peers_wait(peers)) flag |= TRB_FLAG_COMM_TIMEOUT;
+  double red[2] = {0.0, 0.0};
+  z_elements<kChE, false>(sw, b, slots_of(b, sw.R, sw.B, G), first, peers, z,
+                          chunk * kChunk + (int)threadIdx.x, kChThreads, red, flag);
+  block_sum_n<2>(red, sh);
+  const int all_cta = block_or(flag, &sh_flag);
+  double* partials = sw.scr_m + (size_t)b * sw.ldm;  // free here: the likelihood parks nothing
+  if (threadIdx.x == 0) {
+    partials[chunk * kZPartials + 0] = red[0];
+    partials[chunk * kZPartials + 1] = red[1];
+    partials[chunk * kZPartials + 2] = (double)all_cta;
+  }
+  unsigned int* cnt = reinterpret_cast<unsigned int*>(stats) + (size_t)b * 8 + 6;
+  if (!chunk_arrive_last(cnt, nchunk, &sh_last)) return;
+  if (threadIdx.x == 0) {
+    double d2 = 0.0, n2 = 0.0;
+    int all = 0;
+    for (int c = 0; c < nchunk; ++c) {
+      d2 += __ldcg(partials + c * kZPartials + 0);
+      n2 += __ldcg(partials + c * kZPartials + 1);
+      all |= (int)__ldcg(partials + c * kZPartials + 2);
     }
-    // EarlyStoppingEP, callbacks.py:258-286: tol = rms(new-old)/rms(new), max over the
-    // tracked variables; needs a previous estimate, i.e. it > 0.
-    double tol = nan("");
-    if (sw.es_mode == 1 && sw.es_tol >= 0) {
-      // EarlyStopping on the variances (callbacks.py:206-243); the previous values are the
-      // one-iteration-back state's (snap_vx: saved above, snap_vz: saved by k_z_update)
-      const int vars = sw.es_vars ? sw.es_vars : 3;
-      const int stop = early_stopping_variance(vars, it, vx, sw.vz[b], sw.snap_vx[b], sw.snap_vz[b],
-                                               sw.es_tol, sw.es_min_variance, sw.es_max_increase,
-                                               sw.es_wait_increase, &tol);
-      if (stop) {
-        sw.active[b] = 0;
-        atomicOr(&sw.flags[b], stop);
-      }
-    } else if (it > 0) {
-      const double tol_x = sqrt(d2 / N) / sqrt(n2 / N);
-      const double tol_z = sqrt(stats[b * 4 + 0] / sw.M) / sqrt(stats[b * 4 + 1] / sw.M);
-      const int vars = sw.es_vars ? sw.es_vars : 3;
-      tol = (vars & 1) ? tol_x : tol_z;
-      if ((vars & 2) && tol_z > tol) tol = tol_z;
-      if (sw.es_tol >= 0) {
-        if (tol < sw.es_tol) {
-          sw.active[b] = 0;
-          atomicOr(&sw.flags[b], TRB_FLAG_CONVERGED);
-        } else if (it > sw.es_wait_increase && tol > sw.es_max_increase) {
-          sw.active[b] = 0;
-          atomicOr(&sw.flags[b], TRB_FLAG_DIVERGED);
-        }
-      }
+    z_tail(sw, b, 0, stats, z.a3, z.a5, z.a_hat, all, d2, n2);
+  }
+}
+
+__global__ void __launch_bounds__(kChThreads, 4)
+k_x_update_chunked(trb_sweep sw, int G, int it_host, double* __restrict__ stats, trb_peers peers) {
+  __shared__ double sh[33 * 4];
+  __shared__ int sh_flag, sh_last;
+  const int b = blockIdx.y, chunk = blockIdx.x, nchunk = gridDim.x;
+  if (sw.active && !sw.active[b]) return;
+  const int it = it_host >= 0 ? it_host : sw.n_iter[b];  // see k_x_update
+  const XScalars x = x_scalars(sw, b);
+  int flag = x_scalar_flags(x);
+  if (peers.n > 0 && !peers_wait(peers)) flag |= TRB_FLAG_COMM_TIMEOUT;
+  double red[4] = {0.0, 0.0, 0.0, 0.0};
+  x_elements<kChE, false>(sw, b, slots_of(b, sw.R, sw.B, G), peers, x, chunk * kChunk + (int)threadIdx.x,
+                          kChThreads, red, flag);
+  block_sum_n<4>(red, sh);
+  const int all_cta = block_or(flag, &sh_flag);
+  double* partials = sw.scr_n + (size_t)b * sw.ldn;  // free here: the prior's scratch, rewritten by the next F1
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) partials[chunk * kXPartials + k] = red[k];
+    partials[chunk * kXPartials + 4] = (double)all_cta;
+  }
+  unsigned int* cnt = reinterpret_cast<unsigned int*>(stats) + (size_t)b * 8 + 7;
+  if (!chunk_arrive_last(cnt, nchunk, &sh_last)) return;
+  if (threadIdx.x == 0) {
+    double t[4] = {0.0, 0.0, 0.0, 0.0};
+    int all = 0;
+    for (int c = 0; c < nchunk; ++c) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) t[k] += __ldcg(partials + c * kXPartials + k);
+      all |= (int)__ldcg(partials + c * kXPartials + 4);
     }
-    if (rec && sw.rec_tol) sw.rec_tol[(size_t)it * B + b] = tol;
-    if (all & (TRB_FLAG_NAN_A | TRB_FLAG_NAN_B)) sw.active[b] = 0;
+    x_tail(sw, b, it, stats, x.a7, x.a_hat, all, t[0], t[1], t[2], t[3]);
   }
 }
 
@@ -368,6 +392,21 @@ k_tx_recur(trb_sweep sw) {
 
 }  // namespace
 
+// Which update kernels run chunked (bit 0: x, bit 1: z with a Gaussian likelihood, bit 2: the
+// prior's moments); the others are one CTA / cluster per instance.  Default: all; TRB_UPDATE_KERNELS=<mask> or
+// trb_set_update_kernels(mask) select.
+static int g_update_kernels = -1;
+
+static int update_kernels() {
+  if (g_update_kernels < 0) {
+    const char* e = getenv("TRB_UPDATE_KERNELS");
+    g_update_kernels = e ? (atoi(e) & 7) : 7;
+  }
+  return g_update_kernels;
+}
+
+extern "C" void trb_set_update_kernels(int mask) { g_update_kernels = mask < 0 ? -1 : (mask & 7); }
+
 #define TRB_TRY(expr)      \
   do {                     \
     int rc_ = (expr);      \
@@ -408,6 +447,19 @@ int trb_lin_rescale_snap(int dir, int B, int R, int Nz, int Nx, int rank, int nu
                          const double* s, const double* s2, int64_t stride_s, const double* az,
                          const double* ax, const double* tz, const double* tx, double* coef, double* v,
                          const int* active, double* snap_tx, void* stream);
+int trb_factor_message_chunked(const trb_factor* f, int B, int n, int ld, const double* a_in,
+                               const double* b_in, const double* y, double* a_io, double* b_io,
+                               double* a_copy, double damping, double* scratch, int* flags,
+                               const int* active, double* snap_b, double* snap_a, double* snap_a_copy,
+                               unsigned int* counter, int counter_stride, double* partials,
+                               int partials_ld, void* stream);
+int trb_lin_project_rescale(const double* A, int64_t strideA, int R, int n, int ld, int B,
+                            const double* vec, int ldvec, double* t_out, const int* active, int dir,
+                            int Nz, int Nx, int rank, int null_space, const double* s, const double* s2,
+                            int64_t stride_s, const double* az, const double* ax, const double* t_other,
+                            double* coef, double* v, double* snap_tx, unsigned int* counter,
+                            int counter_stride, void* stream);
+bool trb_lin_single_panel(int ld);
 // The push is NOT gated by `active`: every rank takes the same stop decision in the same
 // iteration (the update kernels are computed redundantly on bit-identical sums), and a stopped
 // instance's `part` is no longer rewritten by trb_lin_expand, so the ranks go on pushing and
@@ -468,6 +520,14 @@ extern "C" int trb_sweep_stage(const trb_sweep* sw, int stage, int it, int first
     case TRB_STAGE_PRIOR: {  // F1: reads e8, writes e1 and its pass-through copy e2
       const double* b8 = (first && sw->b8_init) ? sw->b8_init : sw->b7;
       double* sa = sw->snap_edge_a;
+      if (update_kernels() & 4) {  // chunked moments; the partial sums borrow the z scratch
+        rc = trb_factor_message_chunked(&sw->prior, B, sw->N, sw->ldn, ea + 7 * B, b8, nullptr, ea + 0 * B,
+                                        sw->b1, ea + 1 * B, sw->damp1, sw->scr_n, sw->flags, sw->active,
+                                        sa ? sw->snap_b1 : nullptr, sa, sa ? sa + 1 * B : nullptr,
+                                        reinterpret_cast<unsigned int*>(sw->stats) + 6, 8, sw->scr_m,
+                                        sw->ldm, stream);
+        if (rc != TRB_ERR_UNSUPPORTED) return rc;
+      }
       return trb_factor_message_snap(&sw->prior, B, sw->N, sw->ldn, ea + 7 * B, b8, nullptr, ea + 0 * B,
                                      sw->b1, ea + 1 * B, sw->damp1, sw->scr_n, sw->flags, sw->active,
                                      sa ? sw->snap_b1 : nullptr, sa, sa ? sa + 1 * B : nullptr, stream);
@@ -527,6 +587,13 @@ extern "C" int trb_sweep_stage(const trb_sweep* sw, int stage, int it, int first
       trb_launch_scope scope_(0, st);
       trb_peers peers = {};
       if (comm && !light) peers = *trb_comm_last(comm);
+      const int zchunks = (sw->M + kChunk - 1) / kChunk;
+      if ((update_kernels() & 2) && !light && sw->lik.kind == TRB_GAUSSIAN_LIKELIHOOD &&
+          zchunks * kZPartials <= sw->ldm) {
+        k_z_update_chunked<<<dim3(zchunks, B), kChThreads, 0, st>>>(*sw, G, first, sw->stats, peers);
+        TRB_CHECK_LAUNCH();
+        return TRB_OK;
+      }
       cudaError_t le = trb_launch_cluster(k_z_update, trb_cluster_size(B, sw->M), B, kUpThreads, st,
                                           *sw, G, first, light, sw->stats, peers);
       if (le != cudaSuccess)
@@ -570,6 +637,12 @@ case TRB_STAGE_EXPAND_Z:  // P4: rz = [b2/a2 +] V_R coef
       trb_launch_scope scope_(0, st);
       trb_peers peers = {};
       if (comm) peers = *trb_comm_last(comm);
+      const int xchunks = (sw->N + kChunk - 1) / kChunk;
+      if ((update_kernels() & 1) && xchunks * kXPartials <= sw->ldn) {
+        k_x_update_chunked<<<dim3(xchunks, B), kChThreads, 0, st>>>(*sw, G, it, sw->stats, peers);
+        TRB_CHECK_LAUNCH();
+        return TRB_OK;
+      }
       cudaError_t le = trb_launch_cluster(k_x_update, trb_cluster_size(B, sw->N), B, kUpThreads, st,
                                           *sw, G, it, sw->stats, peers);
       if (le != cudaSuccess)
@@ -594,29 +667,78 @@ case TRB_STAGE_EXPAND_Z:  // P4: rz = [b2/a2 +] V_R coef
   return trb_set_error(TRB_ERR_INVALID, "trb_sweep_stage: unknown stage %d", stage);
 }
 
+// ---- projection + rescale in one launch (P1+S1, P3+S2) ------------------------------
+// The rescale is 4 vectors of R per instance: as a kernel of its own it costs a launch and an
+// idle GPU on both sides (~15 us at the north-star size, twice per iteration).  The GEMV
+// projection takes it as an epilogue of the CTA that finishes an instance (trb_linear.cu).
+// Arrival counters: columns 2, 3 of `stats` ([B, 4] doubles), zeroed by trb_sweep_run.
+static int g_fuse_rescale = -1;
+
+extern "C" void trb_set_fused_rescale(int enabled) { g_fuse_rescale = enabled ? 1 : 0; }
+
+static bool rescale_fusable(const trb_sweep* sw) {
+  if (g_fuse_rescale < 0) {
+    const char* e = getenv("TRB_FUSE_RESCALE");
+    g_fuse_rescale = (e && e[0] == '0') ? 0 : 1;
+  }
+  if (!g_fuse_rescale || sw->comm || !sw->s || !sw->s2 || !sw->Vt || !sw->Ut) return false;
+  const bool shared_ops = sw->strideV == 0 && sw->strideU == 0;
+  if (shared_ops && (sw->gemv_impl == 3 || (sw->gemv_impl == 0 && sw->B >= 16))) return false;  // GEMM passes
+  if (sw->gemv_impl != 0 && sw->gemv_impl != 2) return false;
+  return trb_lin_single_panel(sw->ldn) && trb_lin_single_panel(sw->ldm);
+}
+
+static int project_and_rescale(const trb_sweep* sw, int dir, cudaStream_t st) {
+  const int B = sw->B;
+  double* ea = sw->edge_a;
+  const int R_total = sw->R_total > 0 ? sw->R_total : sw->R;
+  const int null_space = R_total < sw->N;
+  unsigned int* counters = reinterpret_cast<unsigned int*>(sw->stats) + 4;  // columns 2, 3 of stats
+  if (dir == 0)  // P1 + S1: tz = V_R^T b2, coef = s res (tz + s tx), forward variance
+    return trb_lin_project_rescale(sw->Vt, sw->strideV, sw->R, sw->N, sw->ldn, B, sw->b1, sw->ldn, sw->tz,
+                                   sw->active, 0, sw->N, sw->M, sw->rank, null_space, sw->s, sw->s2,
+                                   sw->stride_s, ea + 1 * B, ea + 5 * B, sw->tx, sw->coef, sw->vlin,
+                                   (sw->schedule == 0 && sw->snap_edge_a) ? sw->snap_tx : nullptr, counters,
+                                   8, (void*)st);
+  // P3 + S2: tx = U_R^T b6 (new), coef for rz, backward variance
+  return trb_lin_project_rescale(sw->Ut, sw->strideU, sw->R, sw->M, sw->ldm, B, sw->b5, sw->ldm, sw->tx,
+                                 sw->active, 1, sw->N, sw->M, sw->rank, null_space, sw->s, sw->s2,
+                                 sw->stride_s, ea + 1 * B, ea + 5 * B, sw->tz, sw->coef, sw->vlin, nullptr,
+                                 counters + 1, 8, (void*)st);
+}
+
 // One whole iteration, stage by stage (see the header comment of this file).
 static int enqueue_iteration(const trb_sweep* sw, int it, int first, int fresh, bool light,
                              cudaStream_t st) {
   void* stream = (void*)st;
   const int schedule = sw->schedule;
+  const bool fuse = rescale_fusable(sw);
   TRB_TRY(trb_sweep_stage(sw, TRB_STAGE_PRIOR, it, first, 0, stream));
-  TRB_TRY(trb_sweep_stage(sw, TRB_STAGE_PROJECT_Z, it, first, 0, stream));
-  if (first) {
-    if (fresh == 2) {  // e6 was initialised to b = 0: U_R^T 0 = 0, no pass over U needed
-      cudaError_t e = cudaMemsetAsync(sw->tx, 0, sizeof(double) * (size_t)sw->B * sw->R, st);
-      if (e != cudaSuccess)
-        return trb_set_error(TRB_ERR_CUDA, "trb_sweep_run: %s", cudaGetErrorString(e));
-    } else {
-      TRB_TRY(trb_sweep_stage(sw, TRB_STAGE_PROJECT_X_INIT, it, first, 0, stream));
+  if (fuse && !first) {  // the first iteration still has to produce tx before S1
+    TRB_TRY(project_and_rescale(sw, 0, st));
+  } else {
+    TRB_TRY(trb_sweep_stage(sw, TRB_STAGE_PROJECT_Z, it, first, 0, stream));
+    if (first) {
+      if (fresh == 2) {  // e6 was initialised to b = 0: U_R^T 0 = 0, no pass over U needed
+        cudaError_t e = cudaMemsetAsync(sw->tx, 0, sizeof(double) * (size_t)sw->B * sw->R, st);
+        if (e != cudaSuccess)
+          return trb_set_error(TRB_ERR_CUDA, "trb_sweep_run: %s", cudaGetErrorString(e));
+      } else {
+        TRB_TRY(trb_sweep_stage(sw, TRB_STAGE_PROJECT_X_INIT, it, first, 0, stream));
+      }
     }
+    TRB_TRY(trb_sweep_stage(sw, TRB_STAGE_RESCALE_FWD, it, first, 0, stream));
   }
-  TRB_TRY(trb_sweep_stage(sw, TRB_STAGE_RESCALE_FWD, it, first, 0, stream));
   if (!light) TRB_TRY(trb_sweep_stage(sw, TRB_STAGE_EXPAND_X, it, first, 0, stream));
   TRB_TRY(trb_sweep_stage(sw, light ? TRB_STAGE_Z_UPDATE_LIGHT : TRB_STAGE_Z_UPDATE, it, first, 0,
                           stream));
-  TRB_TRY(trb_sweep_stage(sw, schedule ? TRB_STAGE_TX_RECUR : TRB_STAGE_PROJECT_X, it, first, 0,
-                          stream));
-  TRB_TRY(trb_sweep_stage(sw, TRB_STAGE_RESCALE_BWD, it, first, 0, stream));
+  if (fuse && schedule == 0) {
+    TRB_TRY(project_and_rescale(sw, 1, st));
+  } else {
+    TRB_TRY(trb_sweep_stage(sw, schedule ? TRB_STAGE_TX_RECUR : TRB_STAGE_PROJECT_X, it, first, 0,
+                            stream));
+    TRB_TRY(trb_sweep_stage(sw, TRB_STAGE_RESCALE_BWD, it, first, 0, stream));
+  }
   TRB_TRY(trb_sweep_stage(sw, TRB_STAGE_EXPAND_Z, it, first, 0, stream));
   TRB_TRY(trb_sweep_stage(sw, TRB_STAGE_X_UPDATE, it, first, 0, stream));
   // The update kernels copy every value they overwrite to the one-iteration-back state, so a
@@ -654,6 +776,7 @@ static bool graph_eligible(const trb_sweep* sw) {
 struct GraphCache {
   trb_sweep key;
   int light = 0;
+  int kernel_choice = -1;  // fused rescale / chunked updates at capture time
   cudaGraphExec_t exec = nullptr;
   long long launches[2] = {0, 0};
   cudaStream_t capture_stream = nullptr;
@@ -662,7 +785,9 @@ static thread_local GraphCache g_graph;
 
 static int run_graph(const trb_sweep* sw, bool light, int count, cudaStream_t st) {
   GraphCache& gc = g_graph;
-  if (!gc.exec || gc.light != (int)light || memcmp(&gc.key, sw, sizeof(trb_sweep)) != 0) {
+  const int kernel_choice = update_kernels() | (rescale_fusable(sw) ? 8 : 0);
+  if (!gc.exec || gc.light != (int)light || gc.kernel_choice != kernel_choice ||
+      memcmp(&gc.key, sw, sizeof(trb_sweep)) != 0) {
     if (gc.exec) {
       cudaGraphExecDestroy(gc.exec);
       gc.exec = nullptr;
@@ -697,6 +822,7 @@ static int run_graph(const trb_sweep* sw, bool light, int count, cudaStream_t st
     }
     gc.key = *sw;
     gc.light = (int)light;
+    gc.kernel_choice = kernel_choice;
   }
   for (int i = 0; i < count; ++i) {
     const cudaError_t le = cudaGraphLaunch(gc.exec, st);
@@ -729,6 +855,10 @@ extern "C" int trb_sweep_run(const trb_sweep* sw, int it0, int n_iter, int fresh
   {
     const int rc_p = trb_sweep_run_persistent(sw, it0, n_iter, fresh, st);
     if (rc_p != TRB_ERR_UNSUPPORTED) return rc_p;
+  }
+  if (n_iter > 0) {  // arrival counters (fused projections, chunked updates): stats[:, 2:4]
+    const cudaError_t e = cudaMemset2DAsync(reinterpret_cast<char*>(sw->stats) + 16, 32, 0, 16, sw->B, st);
+    if (e != cudaSuccess) return trb_set_error(TRB_ERR_CUDA, "trb_sweep_run: %s", cudaGetErrorString(e));
   }
   int k = 0;
   while (k < n_iter) {
