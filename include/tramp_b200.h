@@ -427,13 +427,19 @@ void trb_set_cuda_graphs(int enabled);
  * counters live in columns 2, 3 of `stats`, which trb_sweep_run zeroes itself. */
 void trb_set_fused_rescale(int enabled);
 
-/* The x update (bit 0), the z update with a Gaussian likelihood (bit 1) and the prior's message
- * (bit 2, non-constant priors) run as CHUNKED kernels inside the sweep: 1024 elements per CTA,
- * every load of a thread issued at once, the chunk sums added in chunk order by the CTA that
- * arrives last (arrival counters in columns 2, 3 of `stats`; the chunk sums borrow scr_n / scr_m).  A
- * cleared bit selects the one-CTA(-cluster)-per-instance kernel instead; -1 = default (all;
- * TRB_UPDATE_KERNELS=<mask> does the same).  Callers of trb_sweep_stage zero `stats` once
- * before the first stage; trb_sweep_run does it itself. */
+/* How the sweep runs its O(N) updates (a bit mask; -1 = default = all bits;
+ * TRB_UPDATE_KERNELS=<mask> does the same):
+ *   bit 0  x update chunked              bit 3  x update as the epilogue of the expansion P4
+ *   bit 1  z update chunked (Gaussian    bit 4  z update as the epilogue of the expansion P2
+ *          likelihood)                          (Gaussian likelihood)
+ *   bit 2  prior message chunked (non-constant priors)
+ * Chunked: 1024 elements per CTA, every load of a thread issued at once, the chunk sums added in
+ * chunk order by the CTA that arrives last.  Epilogue (trb_sweep_run only; GEMV passes of one
+ * column panel, instances of up to 8192 elements, not row-sharded): the CTA that stores the last
+ * slot of an instance's expansion updates the instance in the same launch.  A cleared bit selects
+ * the one-CTA(-cluster)-per-instance kernel.  Arrival counters: columns 2, 3 of `stats`; the chunk
+ * sums borrow scr_n / scr_m.  Callers of trb_sweep_stage zero `stats` once before the first stage;
+ * trb_sweep_run does it itself. */
 void trb_set_update_kernels(int mask);
 
 /* A single instance (B = 1) whose iteration is launch-bound runs ALL its

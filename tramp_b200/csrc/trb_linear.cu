@@ -16,6 +16,7 @@
 //            ring guarded by mbarriers; 8 consumer warps own column slices
 //   0  default = TMA when the shape allows it, else LDG
 #include "trb_common.cuh"
+#include "trb_updates.cuh"
 
 using namespace trb;
 
@@ -301,7 +302,53 @@ struct RescaleEpi {
   double* snap_tx;        // nullable, [B, R]
 };
 
-// MODE: 0 project, 1 expand, 2 project + rescale epilogue
+// Epilogue of an expansion whose result feeds the z / x update directly (sweep stages P2+Z,
+// P4+X): the CTA that stores the last slot of an instance updates that instance -- messages,
+// posterior, tolerance sums, early-stopping decision -- while the other CTAs go on streaming.
+// One CTA holds the whole instance, so the sums need no second kernel and no atomics on doubles.
+struct UpdateEpi {
+  trb_sweep sw;
+  int which;              // 0: z update (Gaussian likelihood), 1: x update
+  int G, first, it;       // geometry of the slots; first iteration (b6_init); iteration index or -1
+  double* stats;
+  unsigned int* counter;  // rows of instance b expanded so far: counter[b * counter_stride], zero on entry
+  int counter_stride;
+};
+
+constexpr int kEpiE = 4;  // elements per thread and batch in the update epilogue
+
+// sums / ORs over the consumer warps (named barrier 1); sh: K * 8 doubles, shi: 8 ints
+template <int K>
+__device__ __forceinline__ void consumer_sum_n(double (&v)[K], double* sh, int warp, int lane) {
+#pragma unroll
+  for (int k = 0; k < K; ++k) v[k] = warp_sum(v[k]);
+  consumer_bar();
+  if (lane == 0) {
+#pragma unroll
+    for (int k = 0; k < K; ++k) sh[k * 8 + warp] = v[k];
+  }
+  consumer_bar();
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    double t = 0.0;
+#pragma unroll
+    for (int w = 0; w < kConsumers / 32; ++w) t += sh[k * 8 + w];
+    v[k] = t;
+  }
+}
+
+__device__ __forceinline__ int consumer_or(int v, int* shi, int warp, int lane) {
+  v = __reduce_or_sync(0xffffffffu, v);
+  consumer_bar();
+  if (lane == 0) shi[warp] = v;
+  consumer_bar();
+  int all = 0;
+#pragma unroll
+  for (int w = 0; w < kConsumers / 32; ++w) all |= shi[w];
+  return all;
+}
+
+// MODE: 0 project, 1 expand, 2 project + rescale epilogue, 3 expand + update epilogue
 template <int NB, int MODE>
 __global__ void __launch_bounds__(kTmaThreads, 1)
 k_gemv_tma(const double* __restrict__ A, int64_t strideA, int R, int n, int ld, int B,
@@ -312,14 +359,16 @@ k_gemv_tma(const double* __restrict__ A, int64_t strideA, int R, int n, int ld, 
            int out_ld,       // expand: leading dimension of `part`
            int npanels,      // > 1: A is npanels column panels of `ld` doubles (the last one may be
                              // narrower: full_ld, full_n); every CTA walks its rows once per panel
-           int full_ld, int full_n, RescaleEpi epi) {
-  constexpr bool EXPAND = MODE == 1;
+           int full_ld, int full_n, RescaleEpi epi, UpdateEpi upd) {
+  constexpr bool EXPAND = MODE == 1 || MODE == 3;
   constexpr int RC = TmaCfg<NB>::RC;
   extern __shared__ __align__(128) double ring[];  // nstages * stage_doubles
   __shared__ __align__(8) uint64_t full_bar[kMaxStages];
   __shared__ __align__(8) uint64_t empty_bar[kMaxStages];
   __shared__ double red[2][kConsumers / 32][kGroupRows];
   __shared__ int sh_last;
+  __shared__ double epi_sh[4 * 8];
+  __shared__ int epi_shi[8];
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (tid == 0) {
@@ -525,6 +574,50 @@ k_gemv_tma(const double* __restrict__ A, int64_t strideA, int R, int n, int ld, 
         const int p = tid + k * kConsumers;
         if (p < npair) *reinterpret_cast<double2*>(o + 2 * p) = acc[k];
       }
+      if constexpr (MODE == 3) {
+        // ---- this CTA's slot of instance s.b is stored: count its rows in; the CTA that
+        // completes the instance updates it (threadfence + atomic, as in MODE 2)
+        __threadfence();
+        consumer_bar();
+        if (tid == 0) {
+          const unsigned int rows = (unsigned int)(s.i1 - s.i0);
+          unsigned int* cnt = upd.counter + (size_t)s.b * upd.counter_stride;
+          __threadfence();
+          const unsigned int before = atomicAdd(cnt, rows);
+          const int last = (before + rows == (unsigned int)R);
+          if (last) {
+            *cnt = 0;
+            __threadfence();
+          }
+          sh_last = last;
+        }
+        consumer_bar();
+        if (sh_last) {  // uniform over the consumers
+          const trb_sweep& sw = upd.sw;
+          const int b = s.b;
+          const int ns = slots_of(b, R, B, upd.G);
+          if (upd.which == 0) {
+            const ZScalars z = z_scalars(sw, b);
+            int flag = z_scalar_flags(z);
+            double r2[2] = {0.0, 0.0};
+            for (int start = tid; start < sw.M; start += kConsumers * kEpiE)
+              z_elements<kEpiE, true>(sw, b, ns, upd.first, nullptr, z, start, kConsumers, r2, flag);
+            consumer_sum_n<2>(r2, epi_sh, warp, lane);
+            const int all = consumer_or(flag, epi_shi, warp, lane);
+            if (tid == 0) z_tail(sw, b, 0, upd.stats, z.a3, z.a5, z.a_hat, all, r2[0], r2[1]);
+          } else {
+            const int it = upd.it >= 0 ? upd.it : sw.n_iter[b];  // see k_x_update
+            const XScalars x = x_scalars(sw, b);
+            int flag = x_scalar_flags(x);
+            double r4[4] = {0.0, 0.0, 0.0, 0.0};
+            for (int start = tid; start < sw.N; start += kConsumers * kEpiE)
+              x_elements<kEpiE, true>(sw, b, ns, nullptr, x, start, kConsumers, r4, flag);
+            consumer_sum_n<4>(r4, epi_sh, warp, lane);
+            const int all = consumer_or(flag, epi_shi, warp, lane);
+            if (tid == 0) x_tail(sw, b, it, upd.stats, x.a7, x.a_hat, all, r4[0], r4[1], r4[2], r4[3]);
+          }
+        }
+      }
     }
   }
   }  // panels
@@ -640,7 +733,7 @@ template <int NB, int MODE>
 int launch_tma(const TmaPlan& p, int G, const double* A, int64_t strideA, int R, int n, int ld,
                int B, const double* vec, int ldvec, double* out, int nslots, const int* active,
                cudaStream_t st, int row_stride, int out_ld, int npanels, int full_ld, int full_n,
-               const RescaleEpi& epi) {
+               const RescaleEpi& epi, const UpdateEpi& upd) {
   auto kern = k_gemv_tma<NB, MODE>;
   static bool configured = false;  // per instantiation
   if (!configured) {
@@ -652,7 +745,7 @@ int launch_tma(const TmaPlan& p, int G, const double* A, int64_t strideA, int R,
   }
   kern<<<G, kTmaThreads, p.smem, st>>>(A, strideA, R, n, ld, B, vec, ldvec, out, nslots, active,
                                        p.stages, p.stage_doubles, row_stride, out_ld, npanels, full_ld,
-                                       full_n, epi);
+                                       full_n, epi, upd);
   return TRB_OK;
 }
 
@@ -660,11 +753,11 @@ template <int MODE>
 int dispatch_tma(const TmaPlan& p, int G, const double* A, int64_t strideA, int R, int n, int ld,
                  int B, const double* vec, int ldvec, double* out, int nslots, const int* active,
                  cudaStream_t st, int row_stride, int out_ld, int npanels, int full_ld, int full_n,
-                 const RescaleEpi& epi = RescaleEpi()) {
+                 const RescaleEpi& epi = RescaleEpi(), const UpdateEpi& upd = UpdateEpi()) {
 #define TRB_TMA_CASE(NB_)                                                                        \
   case NB_:                                                                                      \
     return launch_tma<NB_, MODE>(p, G, A, strideA, R, n, ld, B, vec, ldvec, out, nslots, active, \
-                                 st, row_stride, out_ld, npanels, full_ld, full_n, epi);
+                                 st, row_stride, out_ld, npanels, full_ld, full_n, epi, upd);
   switch (p.nb) {
     TRB_TMA_CASE(1)
     TRB_TMA_CASE(2)
@@ -816,6 +909,40 @@ int trb_lin_project_rescale(const double* A, int64_t strideA, int R, int n, int 
   trb_launch_scope scope_(1, st);
   rc = dispatch_tma<2>(p, geo.G, A, strideA, R, n, ld, B, vec, ldvec, t_out, 0, active, st, ld, 0, 1, ld,
                        n, epi);
+  if (rc) return rc;
+  TRB_CHECK_LAUNCH();
+  return TRB_OK;
+}
+
+// trb_lin_expand followed by the z (which = 0) or x (which = 1) update of the sweep in ONE launch
+// (UpdateEpi above).  counter: one unsigned per instance, zero on entry and zero again on exit.
+// TRB_ERR_UNSUPPORTED (nothing launched) when the rows need column panels or an instance may
+// span more than kTrbDirectSlots CTAs: the caller launches the kernels one by one instead.
+int trb_lin_expand_update(const double* A, int64_t strideA, int R, int n, int ld, int B,
+                          const double* coef, double* part, const int* active, const trb_sweep* sw,
+                          int which, int first, int it, double* stats, unsigned int* counter,
+                          int counter_stride, void* stream) {
+  int rc = check_gemv_args(A, R, n, ld, B, coef, part);
+  if (rc) return rc;
+  TRB_CHECK_ARG(strideA % 2 == 0, "strideA must be even");
+  TRB_CHECK_ARG(sw && stats && counter && counter_stride > 0 && (which == 0 || which == 1), "bad epilogue");
+  TRB_CHECK_ARG(part == sw->part, "the expansion must land in the sweep's slots");
+  TmaPlan p;
+  const trb_expand_geom geo = trb_expand_geometry(B, R);
+  if (!plan_tma(ld, p) || geo.nslots > kTrbDirectSlots || geo.nslots != sw->nslots) return TRB_ERR_UNSUPPORTED;
+  cudaStream_t st = (cudaStream_t)stream;
+  UpdateEpi upd;
+  upd.sw = *sw;
+  upd.which = which;
+  upd.G = geo.G;
+  upd.first = first;
+  upd.it = it;
+  upd.stats = stats;
+  upd.counter = counter;
+  upd.counter_stride = counter_stride;
+  trb_launch_scope scope_(1, st);
+  rc = dispatch_tma<3>(p, geo.G, A, strideA, R, n, ld, B, coef, 0, part, geo.nslots, active, st, ld, ld, 1,
+                       ld, n, RescaleEpi(), upd);
   if (rc) return rc;
   TRB_CHECK_LAUNCH();
   return TRB_OK;

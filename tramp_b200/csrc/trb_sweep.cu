@@ -269,7 +269,7 @@ k_z_update_chunked(trb_sweep sw, int G, int first, double* __restrict__ stats, t
   int flag = z_scalar_flags(z);
   if (peers.n > 0 && !peers_wait(peers)) flag |= TRB_FLAG_COMM_TIMEOUT;
   double red[2] = {0.0, 0.0};
-  z_elements<kChE, false>(sw, b, slots_of(b, sw.R, sw.B, G), first, peers, z,
+  z_elements<kChE, false>(sw, b, slots_of(b, sw.R, sw.B, G), first, &peers, z,
                           chunk * kChunk + (int)threadIdx.x, kChThreads, red, flag);
   block_sum_n<2>(red, sh);
   const int all_cta = block_or(flag, &sh_flag);
@@ -304,7 +304,7 @@ k_x_update_chunked(trb_sweep sw, int G, int it_host, double* __restrict__ stats,
   int flag = x_scalar_flags(x);
   if (peers.n > 0 && !peers_wait(peers)) flag |= TRB_FLAG_COMM_TIMEOUT;
   double red[4] = {0.0, 0.0, 0.0, 0.0};
-  x_elements<kChE, false>(sw, b, slots_of(b, sw.R, sw.B, G), peers, x, chunk * kChunk + (int)threadIdx.x,
+  x_elements<kChE, false>(sw, b, slots_of(b, sw.R, sw.B, G), &peers, x, chunk * kChunk + (int)threadIdx.x,
                           kChThreads, red, flag);
   block_sum_n<4>(red, sh);
   const int all_cta = block_or(flag, &sh_flag);
@@ -392,20 +392,27 @@ k_tx_recur(trb_sweep sw) {
 
 }  // namespace
 
-// Which update kernels run chunked (bit 0: x, bit 1: z with a Gaussian likelihood, bit 2: the
-// prior's moments); the others are one CTA / cluster per instance.  Default: all; TRB_UPDATE_KERNELS=<mask> or
-// trb_set_update_kernels(mask) select.
+// How the z / x / prior updates run (trb_set_update_kernels, TRB_UPDATE_KERNELS=<mask>):
+//   bit 0   x update chunked            bit 3   x update as the epilogue of the expansion P4
+//   bit 1   z update chunked (Gaussian  bit 4   z update as the epilogue of the expansion P2
+//           likelihood)                         (Gaussian likelihood)
+//   bit 2   prior's moments chunked
+// A cleared bit: one CTA / cluster per instance.  The epilogue wins over the chunked kernel where
+// both are set and the epilogue applies (trb_sweep_run only).  Default: all.
+constexpr int kUpdateKernelsAll = 31;
 static int g_update_kernels = -1;
 
 static int update_kernels() {
   if (g_update_kernels < 0) {
     const char* e = getenv("TRB_UPDATE_KERNELS");
-    g_update_kernels = e ? (atoi(e) & 7) : 7;
+    g_update_kernels = e ? (atoi(e) & kUpdateKernelsAll) : kUpdateKernelsAll;
   }
   return g_update_kernels;
 }
 
-extern "C" void trb_set_update_kernels(int mask) { g_update_kernels = mask < 0 ? -1 : (mask & 7); }
+extern "C" void trb_set_update_kernels(int mask) {
+  g_update_kernels = mask < 0 ? -1 : (mask & kUpdateKernelsAll);
+}
 
 #define TRB_TRY(expr)      \
   do {                     \
@@ -460,6 +467,10 @@ int trb_lin_project_rescale(const double* A, int64_t strideA, int R, int n, int 
                             double* coef, double* v, double* snap_tx, unsigned int* counter,
                             int counter_stride, void* stream);
 bool trb_lin_single_panel(int ld);
+int trb_lin_expand_update(const double* A, int64_t strideA, int R, int n, int ld, int B,
+                          const double* coef, double* part, const int* active, const trb_sweep* sw,
+                          int which, int first, int it, double* stats, unsigned int* counter,
+                          int counter_stride, void* stream);
 // The push is NOT gated by `active`: every rank takes the same stop decision in the same
 // iteration (the update kernels are computed redundantly on bit-identical sums), and a stopped
 // instance's `part` is no longer rewritten by trb_lin_expand, so the ranks go on pushing and
@@ -707,6 +718,33 @@ static int project_and_rescale(const trb_sweep* sw, int dir, cudaStream_t st) {
                                  counters + 1, 8, (void*)st);
 }
 
+// ---- expansion + update in one launch (P2+Z, P4+X) -----------------------------------
+// The CTA that stores the last slot of an instance holds everything the z / x update needs; it
+// updates the instance on the spot (trb_linear.cu, UpdateEpi) instead of a kernel of its own
+// reading the slots back after a launch gap.  One CTA walks the whole instance vector, so the
+// epilogue is for instances of up to kFoldMaxElems elements; larger ones keep the chunked kernels.
+constexpr int kFoldMaxElems = 8192;
+
+static bool update_foldable(const trb_sweep* sw, int which) {
+  if (!(update_kernels() & (which == 0 ? 16 : 8)) || sw->comm || !sw->Vt || !sw->Ut) return false;
+  const bool shared_ops = sw->strideV == 0 && sw->strideU == 0;
+  if (shared_ops && (sw->gemv_impl == 3 || (sw->gemv_impl == 0 && sw->B >= 16))) return false;  // GEMM passes
+  if (sw->gemv_impl != 0 && sw->gemv_impl != 2) return false;
+  if (sw->nslots > kTrbDirectSlots) return false;  // the slots are reduced by a kernel of their own first
+  if (which == 0)
+    return sw->lik.kind == TRB_GAUSSIAN_LIKELIHOOD && sw->M <= kFoldMaxElems && trb_lin_single_panel(sw->ldm);
+  return sw->N <= kFoldMaxElems && trb_lin_single_panel(sw->ldn);
+}
+
+static int expand_and_update(const trb_sweep* sw, int which, int first, int it, cudaStream_t st) {
+  unsigned int* counters = reinterpret_cast<unsigned int*>(sw->stats) + 6;  // column 3 of stats
+  if (which == 0)  // P2 + Z
+    return trb_lin_expand_update(sw->Ut, sw->strideU, sw->R, sw->M, sw->ldm, sw->B, sw->coef, sw->part,
+                                 sw->active, sw, 0, first, it, sw->stats, counters, 8, (void*)st);
+  return trb_lin_expand_update(sw->Vt, sw->strideV, sw->R, sw->N, sw->ldn, sw->B, sw->coef, sw->part,
+                               sw->active, sw, 1, first, it, sw->stats, counters + 1, 8, (void*)st);
+}
+
 // One whole iteration, stage by stage (see the header comment of this file).
 static int enqueue_iteration(const trb_sweep* sw, int it, int first, int fresh, bool light,
                              cudaStream_t st) {
@@ -729,9 +767,16 @@ static int enqueue_iteration(const trb_sweep* sw, int it, int first, int fresh, 
     }
     TRB_TRY(trb_sweep_stage(sw, TRB_STAGE_RESCALE_FWD, it, first, 0, stream));
   }
-  if (!light) TRB_TRY(trb_sweep_stage(sw, TRB_STAGE_EXPAND_X, it, first, 0, stream));
-  TRB_TRY(trb_sweep_stage(sw, light ? TRB_STAGE_Z_UPDATE_LIGHT : TRB_STAGE_Z_UPDATE, it, first, 0,
-                          stream));
+  int folded = TRB_ERR_UNSUPPORTED;
+  if (!light && update_foldable(sw, 0)) {
+    folded = expand_and_update(sw, 0, first, it, st);
+    if (folded != TRB_OK && folded != TRB_ERR_UNSUPPORTED) return folded;
+  }
+  if (folded != TRB_OK) {
+    if (!light) TRB_TRY(trb_sweep_stage(sw, TRB_STAGE_EXPAND_X, it, first, 0, stream));
+    TRB_TRY(trb_sweep_stage(sw, light ? TRB_STAGE_Z_UPDATE_LIGHT : TRB_STAGE_Z_UPDATE, it, first, 0,
+                            stream));
+  }
   if (fuse && schedule == 0) {
     TRB_TRY(project_and_rescale(sw, 1, st));
   } else {
@@ -739,8 +784,15 @@ static int enqueue_iteration(const trb_sweep* sw, int it, int first, int fresh, 
                             stream));
     TRB_TRY(trb_sweep_stage(sw, TRB_STAGE_RESCALE_BWD, it, first, 0, stream));
   }
-  TRB_TRY(trb_sweep_stage(sw, TRB_STAGE_EXPAND_Z, it, first, 0, stream));
-  TRB_TRY(trb_sweep_stage(sw, TRB_STAGE_X_UPDATE, it, first, 0, stream));
+  folded = TRB_ERR_UNSUPPORTED;
+  if (update_foldable(sw, 1)) {
+    folded = expand_and_update(sw, 1, first, it, st);
+    if (folded != TRB_OK && folded != TRB_ERR_UNSUPPORTED) return folded;
+  }
+  if (folded != TRB_OK) {
+    TRB_TRY(trb_sweep_stage(sw, TRB_STAGE_EXPAND_Z, it, first, 0, stream));
+    TRB_TRY(trb_sweep_stage(sw, TRB_STAGE_X_UPDATE, it, first, 0, stream));
+  }
   // The update kernels copy every value they overwrite to the one-iteration-back state, so a
   // stopped instance is rolled back once, at the end of trb_sweep_run.  Schedule 2 skips the z
   // branch (b3, rz are not rewritten every iteration) and keeps the copy kernel.
@@ -785,7 +837,7 @@ static thread_local GraphCache g_graph;
 
 static int run_graph(const trb_sweep* sw, bool light, int count, cudaStream_t st) {
   GraphCache& gc = g_graph;
-  const int kernel_choice = update_kernels() | (rescale_fusable(sw) ? 8 : 0);
+  const int kernel_choice = update_kernels() | (rescale_fusable(sw) ? 32 : 0);
   if (!gc.exec || gc.light != (int)light || gc.kernel_choice != kernel_choice ||
       memcmp(&gc.key, sw, sizeof(trb_sweep)) != 0) {
     if (gc.exec) {

@@ -129,7 +129,7 @@ __device__ __forceinline__ int z_scalar_flags(const ZScalars& z) {
 // by other CTAs of this launch -> read them from L2.
 template <int E, bool CG>
 __device__ __forceinline__ void z_elements(const trb_sweep& sw, int b, int ns, int first,
-                                           const trb_peers& peers, const ZScalars& z, int start,
+                                           const trb_peers* peers, const ZScalars& z, int start,
                                            int stride, double (&red)[2], int& flag) {
   const int M = sw.M, ld = sw.ldm;
   const size_t off = (size_t)b * ld;
@@ -140,14 +140,14 @@ __device__ __forceinline__ void z_elements(const trb_sweep& sw, int b, int ns, i
   double* rz = sw.rz + off;
   const double* y = sw.y + off;
   const bool snap = sw.snap_edge_a != nullptr;
-  const bool use_peers = peers.n > 0;
+  const bool use_peers = peers != nullptr && peers->n > 0;
   double rx[E], b6v[E], b3o[E], yv[E], b5o[E], ro[E];
 #pragma unroll
   for (int u = 0; u < E; ++u) {
     const int i = start + u * stride;
     rx[u] = 0.0;
     if (i < M) {
-      rx[u] = use_peers ? peers_sum(peers, off + i) : (CG ? __ldcg(part + i) : part[i]);
+      rx[u] = use_peers ? peers_sum(*peers, off + i) : (CG ? __ldcg(part + i) : part[i]);
       b6v[u] = b6[i];
       b3o[u] = b3[i];
       yv[u] = y[i];
@@ -215,7 +215,7 @@ __device__ __forceinline__ int x_scalar_flags(const XScalars& x) {
 
 // red: sum dr^2, sum r^2, sum (r - x)^2, sum (r + x)^2
 template <int E, bool CG>
-__device__ __forceinline__ void x_elements(const trb_sweep& sw, int b, int ns, const trb_peers& peers,
+__device__ __forceinline__ void x_elements(const trb_sweep& sw, int b, int ns, const trb_peers* peers,
                                            const XScalars& x, int start, int stride, double (&red)[4],
                                            int& flag) {
   const int N = sw.N, ld = sw.ldn;
@@ -227,7 +227,7 @@ __device__ __forceinline__ void x_elements(const trb_sweep& sw, int b, int ns, c
   double* rx = sw.rx + off;
   const double* xt = sw.x_true ? sw.x_true + off : nullptr;
   const bool snap = sw.snap_edge_a != nullptr;
-  const bool use_peers = peers.n > 0;
+  const bool use_peers = peers != nullptr && peers->n > 0;
   double rzv[E], b1v[E], b7o[E], ro[E], xv[E];
 #pragma unroll
   for (int u = 0; u < E; ++u) {
@@ -235,7 +235,7 @@ __device__ __forceinline__ void x_elements(const trb_sweep& sw, int b, int ns, c
     rzv[u] = 0.0;
     xv[u] = 0.0;
     if (i < N) {
-      rzv[u] = use_peers ? peers_sum(peers, off + i) : (CG ? __ldcg(part + i) : part[i]);
+      rzv[u] = use_peers ? peers_sum(*peers, off + i) : (CG ? __ldcg(part + i) : part[i]);
       b1v[u] = b1[i];
       b7o[u] = b7[i];
       ro[u] = rx[i];
