@@ -420,26 +420,20 @@ int trb_sweep_run(const trb_sweep* sw, int it0, int n_iter, int fresh, void* str
  * that off (default on; the environment variable TRB_CUDA_GRAPHS=0 does the same). */
 void trb_set_cuda_graphs(int enabled);
 
-/* trb_sweep_run runs the rescale stages S1 / S2 as an epilogue of the GEMV projections P1 / P3
- * (the CTA that projects the last rows of an instance rescales it: 7 launches per iteration
- * instead of 9) whenever the operator passes are TMA GEMVs of one column panel and the sweep is not
- * row-sharded; 0 turns that off (default on; TRB_FUSE_RESCALE=0 does the same).  The arrival
- * counters live in columns 2, 3 of `stats`, which trb_sweep_run zeroes itself. */
+/* trb_sweep_run runs the rescale stages S1 / S2 INSIDE the GEMV expansions P2 / P4 that consume
+ * them (every consumer warp computes the coefficients of its next 32 rows from tz, tx and the
+ * spectrum, one block ahead of the rows it streams; the variance comes from the CTA that owns the
+ * instance's first row): 7 launches per iteration instead of 9, no coefficient vector in HBM.
+ * Applies when the operator passes are TMA GEMVs and the sweep is not row-sharded; 0 turns it off
+ * (default on; TRB_FUSE_RESCALE=0 does the same). */
 void trb_set_fused_rescale(int enabled);
 
-/* How the sweep runs its O(N) updates (a bit mask; -1 = default = all bits;
- * TRB_UPDATE_KERNELS=<mask> does the same):
- *   bit 0  x update chunked              bit 3  x update as the epilogue of the expansion P4
- *   bit 1  z update chunked (Gaussian    bit 4  z update as the epilogue of the expansion P2
- *          likelihood)                          (Gaussian likelihood)
- *   bit 2  prior message chunked (non-constant priors)
- * Chunked: 1024 elements per CTA, every load of a thread issued at once, the chunk sums added in
- * chunk order by the CTA that arrives last.  Epilogue (trb_sweep_run only; GEMV passes of one
- * column panel, instances of up to 8192 elements, not row-sharded): the CTA that stores the last
- * slot of an instance's expansion updates the instance in the same launch.  A cleared bit selects
- * the one-CTA(-cluster)-per-instance kernel.  Arrival counters: columns 2, 3 of `stats`; the chunk
- * sums borrow scr_n / scr_m.  Callers of trb_sweep_stage zero `stats` once before the first stage;
- * trb_sweep_run does it itself. */
+/* The x update (bit 0) and the z update with a Gaussian likelihood (bit 1) run as CHUNKED
+ * kernels: 1024 elements per CTA, every load of a thread issued at once, the chunk sums added in
+ * chunk order by the CTA that arrives last (arrival counters in columns 2, 3 of `stats`, the chunk
+ * sums borrow scr_n / scr_m).  A cleared bit selects the one-CTA(-cluster)-per-instance kernel
+ * instead; -1 = default (both; TRB_UPDATE_KERNELS=<mask> does the same).  Callers of
+ * trb_sweep_stage zero `stats` once before the first stage; trb_sweep_run does it itself. */
 void trb_set_update_kernels(int mask);
 
 /* A single instance (B = 1) whose iteration is launch-bound runs ALL its

@@ -279,116 +279,6 @@ k_factor_message(trb_factor f, int n, int ld, const double* __restrict__ a_in,
   }
 }
 
-// ---- the same message, chunked (sweep only) ------------------------------------------------
-// Pass 1 (moments: the FP64-heavy part) runs on chunks of 1024 elements, one 256-thread CTA each,
-// every load issued at once; r is parked in `scratch`, the chunk's sum of v in `partials`.  The CTA
-// that arrives last (threadfence + counter) adds the chunk sums in chunk order, clips, and writes
-// the whole instance's message (pass 2 is one FMA per element) while the other CTAs of the SM go
-// on with other instances' moments.  Non-constant messages only.
-constexpr int kFcThreads = 256;
-constexpr int kFcE = 4;
-constexpr int kFcChunk = kFcThreads * kFcE;
-
-__global__ void __launch_bounds__(kFcThreads, 4)
-k_factor_message_chunked(trb_factor f, int n, int ld, const double* __restrict__ a_in,
-                         const double* __restrict__ b_in, const double* __restrict__ y, double* a_io,
-                         double* b_io, double* a_copy, double damping, double* scratch, int* flags,
-                         const int* __restrict__ active, double* __restrict__ snap_b,
-                         double* __restrict__ snap_a, double* __restrict__ snap_a_copy,
-                         unsigned int* counter, int counter_stride, double* partials, int partials_ld) {
-  __shared__ double sh[33];
-  __shared__ int sh_flag, sh_last;
-  const int inst = blockIdx.y, chunk = blockIdx.x, nchunk = gridDim.x;
-  if (active && !active[inst]) return;
-  const size_t off = (size_t)inst * ld;
-  const double a = a_in[inst];
-  {
-    const int base = chunk * kFcChunk + threadIdx.x;
-    double bv[kFcE], yv[kFcE];
-#pragma unroll
-    for (int u = 0; u < kFcE; ++u) {
-      const int i = base + u * kFcThreads;
-      if (i < n) {
-        bv[u] = b_in[off + i];
-        yv[u] = y ? y[off + i] : 0.0;
-      }
-    }
-    double vsum = 0.0;
-#pragma unroll
-    for (int u = 0; u < kFcE; ++u) {
-      const int i = base + u * kFcThreads;
-      if (i < n) {
-        const RV m = factor_moments(f, a, bv[u], yv[u]);
-        scratch[off + i] = m.r;
-        vsum += m.v;
-      }
-    }
-    vsum = block_sum(vsum, sh);
-    double* mine = partials + (size_t)inst * partials_ld;
-    if (threadIdx.x == 0) {
-      mine[chunk] = vsum;
-      __threadfence();
-    }
-    // every thread's r must be visible to the last CTA: fence, then the CTA-wide barrier, then count
-    __threadfence();
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      unsigned int* cnt = counter + (size_t)inst * counter_stride;
-      const unsigned int before = atomicAdd(cnt, 1u);
-      const int last = (before + 1u == (unsigned int)nchunk);
-      if (last) {
-        *cnt = 0;
-        __threadfence();
-      }
-      sh_last = last;
-    }
-    __syncthreads();
-    if (!sh_last) return;
-  }
-  const double* mine = partials + (size_t)inst * partials_ld;
-  double tot = 0.0;
-  for (int c = 0; c < nchunk; ++c) tot += __ldcg(mine + c);  // same order in every thread
-  const double v = tot / n;
-  const double a_new = clip_a_new(v, a, f.amin, f.amax);
-  const double ainv = a + a_new;
-  int flag = 0;
-  constexpr int U = 8;
-  for (int base = threadIdx.x; base < n; base += kFcThreads * U) {
-    double rv[U], bv[U], bo[U];
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const int i = base + u * kFcThreads;
-      if (i < n) {
-        rv[u] = __ldcg(scratch + off + i);
-        bv[u] = b_in[off + i];
-        bo[u] = b_io[off + i];
-      }
-    }
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const int i = base + u * kFcThreads;
-      if (i < n) {
-        const double bn = rv[u] * ainv - bv[u];
-        if (snap_b) snap_b[off + i] = bo[u];
-        b_io[off + i] = damp(damping, bo[u], bn);
-        if (bn != bn) flag |= TRB_FLAG_NAN_B;
-      }
-    }
-  }
-  if (a_new != a_new) flag |= TRB_FLAG_NAN_A;
-  if (a_new < 0) flag |= TRB_FLAG_NEG_A;
-  const int all = block_or(flag, &sh_flag);
-  if (threadIdx.x == 0) {
-    const double a_old = a_io[inst];
-    if (snap_a) snap_a[inst] = a_old;
-    if (snap_a_copy && a_copy) snap_a_copy[inst] = a_copy[inst];
-    const double ad = damp(damping, a_old, a_new);
-    a_io[inst] = ad;
-    if (a_copy) a_copy[inst] = ad;
-    if (flags && all) atomicOr(&flags[inst], all);
-  }
-}
-
 __global__ void k_truncated_normal(int n, const double* __restrict__ r0,
                                    const double* __restrict__ v0, double zmin, double zmax,
                                    double* mean, double* var, double* logZ, double* proba) {
@@ -477,31 +367,6 @@ int trb_factor_message_snap(const trb_factor* f, int B, int n, int ld, const dou
                                       a_copy, damping, scratch, flags, active, snap_b, snap_a, snap_a_copy);
   if (le != cudaSuccess)
     return trb_set_error(TRB_ERR_CUDA, "trb_factor_message: %s", cudaGetErrorString(le));
-  TRB_CHECK_LAUNCH();
-  return TRB_OK;
-}
-
-// trb_factor_message_snap as chunked kernels (see k_factor_message_chunked): `counter` (one zeroed
-// unsigned per instance, stride counter_stride, zero again on return) and `partials`
-// ([B, partials_ld] doubles, partials_ld >= chunks) come from the sweep.  TRB_ERR_UNSUPPORTED
-// (nothing launched) for constant messages or too small a partials row.
-int trb_factor_message_chunked(const trb_factor* f, int B, int n, int ld, const double* a_in,
-                               const double* b_in, const double* y, double* a_io, double* b_io,
-                               double* a_copy, double damping, double* scratch, int* flags,
-                               const int* active, double* snap_b, double* snap_a, double* snap_a_copy,
-                               unsigned int* counter, int counter_stride, double* partials,
-                               int partials_ld, void* stream) {
-  TRB_CHECK_ARG(f && a_in && b_in && a_io && b_io && scratch && counter && partials, "null pointer");
-  TRB_CHECK_ARG(B > 0 && B <= 65535 && n > 0 && ld >= n, "bad shape");
-  TRB_CHECK_ARG(f->kind >= 0 && f->kind <= TRB_ABS_LIKELIHOOD, "unknown factor kind");
-  TRB_CHECK_ARG(!needs_y(f->kind) || y, "likelihood needs y");
-  const int chunks = (n + kFcChunk - 1) / kFcChunk;
-  if (f->kind == TRB_GAUSSIAN_PRIOR || f->kind == TRB_GAUSSIAN_LIKELIHOOD || chunks > partials_ld)
-    return TRB_ERR_UNSUPPORTED;
-  trb_launch_scope scope_(0, (cudaStream_t)stream);
-  k_factor_message_chunked<<<dim3(chunks, B), kFcThreads, 0, (cudaStream_t)stream>>>(
-      *f, n, ld, a_in, b_in, y, a_io, b_io, a_copy, damping, scratch, flags, active, snap_b, snap_a,
-      snap_a_copy, counter, counter_stride, partials, partials_ld);
   TRB_CHECK_LAUNCH();
   return TRB_OK;
 }

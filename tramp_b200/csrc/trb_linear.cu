@@ -16,7 +16,6 @@
 //            ring guarded by mbarriers; 8 consumer warps own column slices
 //   0  default = TMA when the shape allows it, else LDG
 #include "trb_common.cuh"
-#include "trb_updates.cuh"
 
 using namespace trb;
 
@@ -203,6 +202,17 @@ __device__ __forceinline__ RescalePlan rescale_plan(int dir, double az, double a
   return p;
 }
 
+// coefficient of one singular direction (linear_channel.py:74 resolvent, :69-89 means)
+__device__ __forceinline__ double rescale_coef(int dir, bool null_space, double az, double ax, double si,
+                                               double s2i, double tzi, double txi) {
+  const double res = 1 / (az + ax * s2i);  // :74
+  if (dir == 0) return si * (res * (tzi + si * txi));
+  if (!null_space) return res * (tzi + si * txi);
+  // res - 1/az = -(ax*s2/az)*res, applied to tz; the bz/az term is added by the consumer of the
+  // expansion
+  return res * (si * txi - (ax * s2i / az) * tzi);
+}
+
 // One thread's share (i = first, first + stride, ...) of one pass over the spectrum: the
 // coefficients in the singular basis AND the sum the variance needs (they do not depend on each
 // other).  U elements at a time, all their loads issued before the first store (the stores would
@@ -239,21 +249,8 @@ __device__ __forceinline__ double rescale_share(int dir, int R, int rank, bool n
           else if (pl.sum_mode == 2) part += s2i / (pl.ratio + s2i);
         }
         if (coef) {
-          const double si = sv[u];
-          const double res = 1 / (az + ax * s2i);  // :74
-          const double tzi = tzv[u], txi = txv[u];
-          if (snap_tx) snap_tx[i] = txi;
-          double c;
-          if (dir == 0) {
-            c = si * (res * (tzi + si * txi));
-          } else if (!null_space) {
-            c = res * (tzi + si * txi);
-          } else {
-            // res - 1/az = -(ax*s2/az)*res, applied to tz; the bz/az term is added
-            // by the consumer of the expansion
-            c = res * (si * txi - (ax * s2i / az) * tzi);
-          }
-          coef[i] = c;
+          if (snap_tx) snap_tx[i] = txv[u];
+          coef[i] = rescale_coef(dir, null_space, az, ax, sv[u], s2i, tzv[u], txv[u]);
         }
       }
     }
@@ -284,71 +281,30 @@ __device__ __forceinline__ double rescale_variance(int dir, int Nz, int Nx, int 
   return (1 - n_eff) / pl.az_v;  // :95-97
 }
 
-// Epilogue of a projection whose result feeds the rescale directly (sweep stages P1+S1, P3+S2):
-// the CTA that completes the last rows of an instance computes that instance's coefficients and
-// variance while the other CTAs go on streaming -- no separate launch, no idle GPU in between.
-struct RescaleEpi {
-  unsigned int* counter;  // rows of instance b projected so far: counter[b * counter_stride], zero on entry
-  int counter_stride;
+// The rescale stage (S1 / S2 of the sweep) inside the expansion that consumes it (P2 / P4): the
+// coefficient of row i depends on row i only -- tz_i, tx_i, s_i and the instance's (az, ax) -- so
+// every consumer warp computes the coefficients of its next 32 rows itself (lane = row), one block
+// ahead of the rows it is streaming, and hands them out by shuffle; the variance needs the
+// spectrum only and is computed by the CTA that owns the instance's first row from values it
+// loaded a segment earlier.  No coefficient vector in HBM, no launch, and -- unlike an epilogue
+// that waits for other CTAs (measured: every dependent access inside a kernel that saturates HBM
+// queues behind ~30 MB of ring traffic, ~4 us) -- no memory round trip on the critical path.
+struct RescaleFused {
   int dir, Nz, Nx, rank, null_space;
   const double* s;
   const double* s2;
   int64_t stride_s;
-  const double* az;       // [B]
-  const double* ax;       // [B]
-  const double* t_other;  // the projection this launch does not write (dir 0: tx, dir 1: tz), [B, R]
-  double* coef;           // [B, R]
-  double* v_out;          // [B]
-  double* snap_tx;        // nullable, [B, R]
+  const double* az;  // [B]
+  const double* ax;  // [B]
+  const double* tz;  // [B, R]
+  const double* tx;  // [B, R]
+  double* v_out;     // [B]
+  double* snap_tx;   // nullable, [B, R]: receives a copy of tx (one-iteration-back state)
 };
 
-// Epilogue of an expansion whose result feeds the z / x update directly (sweep stages P2+Z,
-// P4+X): the CTA that stores the last slot of an instance updates that instance -- messages,
-// posterior, tolerance sums, early-stopping decision -- while the other CTAs go on streaming.
-// One CTA holds the whole instance, so the sums need no second kernel and no atomics on doubles.
-struct UpdateEpi {
-  trb_sweep sw;
-  int which;              // 0: z update (Gaussian likelihood), 1: x update
-  int G, first, it;       // geometry of the slots; first iteration (b6_init); iteration index or -1
-  double* stats;
-  unsigned int* counter;  // rows of instance b expanded so far: counter[b * counter_stride], zero on entry
-  int counter_stride;
-};
+constexpr int kVarRegs = 8;  // spectrum values per thread kept in flight for the next instance's variance
 
-constexpr int kEpiE = 4;  // elements per thread and batch in the update epilogue
-
-// sums / ORs over the consumer warps (named barrier 1); sh: K * 8 doubles, shi: 8 ints
-template <int K>
-__device__ __forceinline__ void consumer_sum_n(double (&v)[K], double* sh, int warp, int lane) {
-#pragma unroll
-  for (int k = 0; k < K; ++k) v[k] = warp_sum(v[k]);
-  consumer_bar();
-  if (lane == 0) {
-#pragma unroll
-    for (int k = 0; k < K; ++k) sh[k * 8 + warp] = v[k];
-  }
-  consumer_bar();
-#pragma unroll
-  for (int k = 0; k < K; ++k) {
-    double t = 0.0;
-#pragma unroll
-    for (int w = 0; w < kConsumers / 32; ++w) t += sh[k * 8 + w];
-    v[k] = t;
-  }
-}
-
-__device__ __forceinline__ int consumer_or(int v, int* shi, int warp, int lane) {
-  v = __reduce_or_sync(0xffffffffu, v);
-  consumer_bar();
-  if (lane == 0) shi[warp] = v;
-  consumer_bar();
-  int all = 0;
-#pragma unroll
-  for (int w = 0; w < kConsumers / 32; ++w) all |= shi[w];
-  return all;
-}
-
-// MODE: 0 project, 1 expand, 2 project + rescale epilogue, 3 expand + update epilogue
+// MODE: 0 project, 1 expand, 2 expand with the rescale inside (coefficients and variance on the fly)
 template <int NB, int MODE>
 __global__ void __launch_bounds__(kTmaThreads, 1)
 k_gemv_tma(const double* __restrict__ A, int64_t strideA, int R, int n, int ld, int B,
@@ -359,16 +315,13 @@ k_gemv_tma(const double* __restrict__ A, int64_t strideA, int R, int n, int ld, 
            int out_ld,       // expand: leading dimension of `part`
            int npanels,      // > 1: A is npanels column panels of `ld` doubles (the last one may be
                              // narrower: full_ld, full_n); every CTA walks its rows once per panel
-           int full_ld, int full_n, RescaleEpi epi, UpdateEpi upd) {
-  constexpr bool EXPAND = MODE == 1 || MODE == 3;
+           int full_ld, int full_n, RescaleFused rf) {
+  constexpr bool EXPAND = MODE != 0;
   constexpr int RC = TmaCfg<NB>::RC;
   extern __shared__ __align__(128) double ring[];  // nstages * stage_doubles
   __shared__ __align__(8) uint64_t full_bar[kMaxStages];
   __shared__ __align__(8) uint64_t empty_bar[kMaxStages];
   __shared__ double red[2][kConsumers / 32][kGroupRows];
-  __shared__ int sh_last;
-  __shared__ double epi_sh[4 * 8];
-  __shared__ int epi_shi[8];
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (tid == 0) {
@@ -418,6 +371,42 @@ k_gemv_tma(const double* __restrict__ A, int64_t strideA, int R, int n, int ld, 
 
   // -------------------------------------------------------------- consumers
   int red_buf = 0;
+  // MODE 2 (see RescaleFused): inputs of the next coefficient block (row nb_row + lane of instance
+  // nb_b) and of the next instance's variance (instance nv_b), in flight while rows stream
+  [[maybe_unused]] double nb_s = 0.0, nb_s2 = 0.0, nb_tz = 0.0, nb_tx = 0.0, nb_az = 0.0, nb_ax = 0.0;
+  [[maybe_unused]] int nb_b = -1, nb_row = 0;
+  [[maybe_unused]] double nv_s2[kVarRegs], nv_az = 0.0, nv_ax = 0.0;
+  [[maybe_unused]] int nv_b = -1;
+  [[maybe_unused]] auto block_issue = [&](int bn, int row, int end) {
+    nb_b = bn;
+    nb_row = row;
+    nb_az = rf.az[bn];
+    nb_ax = rf.ax[bn];
+    const int r = row + lane;
+    if (r < end) {
+      nb_s = rf.s[(size_t)bn * rf.stride_s + r];
+      nb_s2 = rf.s2[(size_t)bn * rf.stride_s + r];
+      nb_tz = rf.tz[(size_t)bn * R + r];
+      nb_tx = rf.tx[(size_t)bn * R + r];
+    }
+  };
+  // coefficient of row nb_row + lane of the block in flight (0 past the end of the segment)
+  [[maybe_unused]] auto block_finish = [&](int end) -> double {
+    const int r = nb_row + lane;
+    if (r >= end) return 0.0;
+    if (warp == 0 && rf.snap_tx) rf.snap_tx[(size_t)nb_b * R + r] = nb_tx;  // every row once: its segment's CTA
+    return rescale_coef(rf.dir, rf.null_space != 0, nb_az, nb_ax, nb_s, nb_s2, nb_tz, nb_tx);
+  };
+  [[maybe_unused]] auto var_issue = [&](int bn) {
+    nv_b = bn;
+    nv_az = rf.az[bn];
+    nv_ax = rf.ax[bn];
+#pragma unroll
+    for (int u = 0; u < kVarRegs; ++u) {
+      const int i = tid + u * kConsumers;
+      nv_s2[u] = (i < R) ? rf.s2[(size_t)bn * rf.stride_s + i] : 0.0;
+    }
+  };
   for (int pq = 0; pq < npanels; ++pq) {
   const int c0 = pq * panel_ld;
   if (npanels > 1) {  // this panel's extent
@@ -490,60 +479,75 @@ k_gemv_tma(const double* __restrict__ A, int64_t strideA, int R, int n, int ld, 
         }
         red_buf ^= 1;
       }
-      if constexpr (MODE == 2) {
-        // ---- this CTA's rows of instance s.b are written: count them in; the CTA that
-        // completes the instance rescales it (threadfence + atomic: the writers' stores are
-        // visible to whoever observes the full count)
-        __threadfence();
-        consumer_bar();
-        if (tid == 0) {
-          const unsigned int rows = (unsigned int)(s.i1 - s.i0);
-          unsigned int* cnt = epi.counter + (size_t)s.b * epi.counter_stride;
-          __threadfence();
-          const unsigned int before = atomicAdd(cnt, rows);
-          const int last = (before + rows == (unsigned int)R);
-          if (last) {
-            *cnt = 0;  // nobody else touches this instance's counter before the next launch
-            __threadfence();
-          }
-          sh_last = last;
-        }
-        consumer_bar();
-        if (sh_last) {  // uniform over the consumers
-          const int b = s.b;
-          const double az = epi.az[b], ax = epi.ax[b];
-          const RescalePlan pl = rescale_plan(epi.dir, az, ax);
-          const size_t o = (size_t)b * R;
-          const double* t_mine = out + o;
-          const double* t_oth = epi.t_other + o;
-          const double part = rescale_share<true, 8>(
-              epi.dir, R, epi.rank, epi.null_space != 0, pl, epi.s + (size_t)b * epi.stride_s,
-              epi.s2 + (size_t)b * epi.stride_s, az, ax, epi.dir == 0 ? t_mine : t_oth,
-              epi.dir == 0 ? t_oth : t_mine, epi.coef + o, epi.snap_tx ? epi.snap_tx + o : nullptr, tid,
-              kConsumers);
-          double tot = warp_sum(part);
-          if (lane == 0) red[red_buf][warp][0] = tot;
-          consumer_bar();
-          if (tid == 0) {
-            tot = 0.0;
-#pragma unroll
-            for (int w = 0; w < kConsumers / 32; ++w) tot += red[red_buf][w][0];
-            epi.v_out[b] = rescale_variance(epi.dir, epi.Nz, epi.Nx, epi.rank, pl, az, ax, tot);
-          }
-          red_buf ^= 1;
-        }
-      }
     } else {
       // ---- expand: column accumulators in registers for the whole segment
       double2 acc[NB];
 #pragma unroll
       for (int k = 0; k < NB; ++k) acc[k] = make_double2(0.0, 0.0);
       const double* cb = vec + (size_t)s.b * R;
+      [[maybe_unused]] int blk_row = s.i0;
+      [[maybe_unused]] double cblk = 0.0;
+      if constexpr (MODE == 2) {
+        // after this segment the CTA goes on with row 0 of the next instance, if its range goes on
+        const bool more = (s.i1 == R) && (g < g1);
+        const int next_end = more ? ((g1 - g < (int64_t)R) ? (int)(g1 - g) : R) : 0;
+        if (s.i0 == 0 && pq == 0) {
+          // ---- this CTA owns the instance's first row: its variance (spectrum only), from the
+          // values loaded during the previous segment (the CTA's first segment loads them here)
+          if (nv_b != s.b) var_issue(s.b);
+          const RescalePlan pl = rescale_plan(rf.dir, nv_az, nv_ax);
+          double part = 0.0;
+#pragma unroll
+          for (int u = 0; u < kVarRegs; ++u) {
+            const int i = tid + u * kConsumers;
+            if (i < R && i < rf.rank) {
+              if (pl.sum_mode == 1) part += nv_s2[u];
+              else if (pl.sum_mode == 2) part += nv_s2[u] / (pl.ratio + nv_s2[u]);
+            }
+          }
+          for (int i = tid + kVarRegs * kConsumers; i < R && i < rf.rank; i += kConsumers) {
+            const double s2i = rf.s2[(size_t)s.b * rf.stride_s + i];
+            if (pl.sum_mode == 1) part += s2i;
+            else if (pl.sum_mode == 2) part += s2i / (pl.ratio + s2i);
+          }
+          part = warp_sum(part);
+          consumer_bar();
+          if (lane == 0) red[0][warp][0] = part;
+          consumer_bar();
+          if (tid == 0) {
+            double tot = 0.0;
+#pragma unroll
+            for (int w = 0; w < kConsumers / 32; ++w) tot += red[0][w][0];
+            rf.v_out[s.b] = rescale_variance(rf.dir, rf.Nz, rf.Nx, rf.rank, pl, nv_az, nv_ax, tot);
+          }
+        }
+        if (more && pq == 0) var_issue(s.b + 1);
+        // ---- coefficients: the block of this segment's first 32 rows (in flight since the previous
+        // segment, else loaded here), then always one block ahead
+        if (!(nb_b == s.b && nb_row == s.i0)) block_issue(s.b, s.i0, s.i1);
+        cblk = block_finish(s.i1);
+        if (blk_row + 32 < s.i1) block_issue(s.b, blk_row + 32, s.i1);
+        else if (more) block_issue(s.b + 1, 0, next_end);
+      }
       for (int i = s.i0; i < s.i1; i += RC) {
         const int rows = (s.i1 - i < RC) ? (s.i1 - i) : RC;
         double c[RC];
+        if constexpr (MODE == 2) {
+          if (i - blk_row == 32) {  // RC divides 32: a stage never straddles two blocks
+            blk_row = i;
+            cblk = block_finish(s.i1);
+            if (blk_row + 32 < s.i1) {
+              block_issue(s.b, blk_row + 32, s.i1);
+            } else if ((s.i1 == R) && (g < g1)) {
+              block_issue(s.b + 1, 0, (g1 - g < (int64_t)R) ? (int)(g1 - g) : R);
+            }
+          }
 #pragma unroll
-        for (int rr = 0; rr < RC; ++rr) c[rr] = (rr < rows) ? __ldg(cb + i + rr) : 0.0;
+          for (int rr = 0; rr < RC; ++rr) c[rr] = __shfl_sync(0xffffffffu, cblk, (i - blk_row) + rr);
+        } else {
+#pragma unroll
+          for (int rr = 0; rr < RC; ++rr) c[rr] = (rr < rows) ? __ldg(cb + i + rr) : 0.0;
+        }
         mbar_wait(&full_bar[stage], phase);
         const double2* st = reinterpret_cast<const double2*>(ring + (size_t)stage * stage_doubles);
 #pragma unroll
@@ -573,50 +577,6 @@ k_gemv_tma(const double* __restrict__ A, int64_t strideA, int R, int n, int ld, 
       for (int k = 0; k < NB; ++k) {
         const int p = tid + k * kConsumers;
         if (p < npair) *reinterpret_cast<double2*>(o + 2 * p) = acc[k];
-      }
-      if constexpr (MODE == 3) {
-        // ---- this CTA's slot of instance s.b is stored: count its rows in; the CTA that
-        // completes the instance updates it (threadfence + atomic, as in MODE 2)
-        __threadfence();
-        consumer_bar();
-        if (tid == 0) {
-          const unsigned int rows = (unsigned int)(s.i1 - s.i0);
-          unsigned int* cnt = upd.counter + (size_t)s.b * upd.counter_stride;
-          __threadfence();
-          const unsigned int before = atomicAdd(cnt, rows);
-          const int last = (before + rows == (unsigned int)R);
-          if (last) {
-            *cnt = 0;
-            __threadfence();
-          }
-          sh_last = last;
-        }
-        consumer_bar();
-        if (sh_last) {  // uniform over the consumers
-          const trb_sweep& sw = upd.sw;
-          const int b = s.b;
-          const int ns = slots_of(b, R, B, upd.G);
-          if (upd.which == 0) {
-            const ZScalars z = z_scalars(sw, b);
-            int flag = z_scalar_flags(z);
-            double r2[2] = {0.0, 0.0};
-            for (int start = tid; start < sw.M; start += kConsumers * kEpiE)
-              z_elements<kEpiE, true>(sw, b, ns, upd.first, nullptr, z, start, kConsumers, r2, flag);
-            consumer_sum_n<2>(r2, epi_sh, warp, lane);
-            const int all = consumer_or(flag, epi_shi, warp, lane);
-            if (tid == 0) z_tail(sw, b, 0, upd.stats, z.a3, z.a5, z.a_hat, all, r2[0], r2[1]);
-          } else {
-            const int it = upd.it >= 0 ? upd.it : sw.n_iter[b];  // see k_x_update
-            const XScalars x = x_scalars(sw, b);
-            int flag = x_scalar_flags(x);
-            double r4[4] = {0.0, 0.0, 0.0, 0.0};
-            for (int start = tid; start < sw.N; start += kConsumers * kEpiE)
-              x_elements<kEpiE, true>(sw, b, ns, nullptr, x, start, kConsumers, r4, flag);
-            consumer_sum_n<4>(r4, epi_sh, warp, lane);
-            const int all = consumer_or(flag, epi_shi, warp, lane);
-            if (tid == 0) x_tail(sw, b, it, upd.stats, x.a7, x.a_hat, all, r4[0], r4[1], r4[2], r4[3]);
-          }
-        }
       }
     }
   }
@@ -733,7 +693,7 @@ template <int NB, int MODE>
 int launch_tma(const TmaPlan& p, int G, const double* A, int64_t strideA, int R, int n, int ld,
                int B, const double* vec, int ldvec, double* out, int nslots, const int* active,
                cudaStream_t st, int row_stride, int out_ld, int npanels, int full_ld, int full_n,
-               const RescaleEpi& epi, const UpdateEpi& upd) {
+               const RescaleFused& rf) {
   auto kern = k_gemv_tma<NB, MODE>;
   static bool configured = false;  // per instantiation
   if (!configured) {
@@ -745,7 +705,7 @@ int launch_tma(const TmaPlan& p, int G, const double* A, int64_t strideA, int R,
   }
   kern<<<G, kTmaThreads, p.smem, st>>>(A, strideA, R, n, ld, B, vec, ldvec, out, nslots, active,
                                        p.stages, p.stage_doubles, row_stride, out_ld, npanels, full_ld,
-                                       full_n, epi, upd);
+                                       full_n, rf);
   return TRB_OK;
 }
 
@@ -753,11 +713,11 @@ template <int MODE>
 int dispatch_tma(const TmaPlan& p, int G, const double* A, int64_t strideA, int R, int n, int ld,
                  int B, const double* vec, int ldvec, double* out, int nslots, const int* active,
                  cudaStream_t st, int row_stride, int out_ld, int npanels, int full_ld, int full_n,
-                 const RescaleEpi& epi = RescaleEpi(), const UpdateEpi& upd = UpdateEpi()) {
+                 const RescaleFused& rf = RescaleFused()) {
 #define TRB_TMA_CASE(NB_)                                                                        \
   case NB_:                                                                                      \
     return launch_tma<NB_, MODE>(p, G, A, strideA, R, n, ld, B, vec, ldvec, out, nslots, active, \
-                                 st, row_stride, out_ld, npanels, full_ld, full_n, epi, upd);
+                                 st, row_stride, out_ld, npanels, full_ld, full_n, rf);
   switch (p.nb) {
     TRB_TMA_CASE(1)
     TRB_TMA_CASE(2)
@@ -860,89 +820,50 @@ extern "C" int trb_lin_project(const double* A, int64_t strideA, int R, int n, i
   return TRB_OK;
 }
 
-// rows of `ld` doubles fit one stage of the TMA ring (no column panels)
-bool trb_lin_single_panel(int ld) {
-  TmaPlan p;
-  return ld > 0 && ld % 2 == 0 && plan_tma(ld, p);
-}
-
-// trb_lin_project followed by trb_lin_rescale in ONE launch (sweep stages P1+S1 and P3+S2): the
-// CTA that projects the last rows of an instance rescales it (RescaleEpi above).  dir 0: t_out is
-// tz and t_other tx; dir 1: t_out is tx and t_other tz.  counter: one unsigned per instance
-// (counter[b * counter_stride]), zero on entry and zero again on exit.  TRB_ERR_UNSUPPORTED
-// (nothing launched) when the rows are too wide for one ring stage: the caller launches the two
-// kernels instead.
-int trb_lin_project_rescale(const double* A, int64_t strideA, int R, int n, int ld, int B,
-                            const double* vec, int ldvec, double* t_out, const int* active, int dir,
-                            int Nz, int Nx, int rank, int null_space, const double* s, const double* s2,
-                            int64_t stride_s, const double* az, const double* ax, const double* t_other,
-                            double* coef, double* v, double* snap_tx, unsigned int* counter,
-                            int counter_stride, void* stream) {
-  int rc = check_gemv_args(A, R, n, ld, B, vec, t_out);
+// trb_lin_rescale followed by trb_lin_expand in ONE launch (sweep stages S1+P2 and S2+P4): the
+// coefficients are computed inside the expansion from tz, tx and the spectrum (RescaleFused above),
+// the variance goes to v.  snap_tx (nullable) receives a copy of tx.  TMA GEMV only:
+// TRB_ERR_UNSUPPORTED (nothing launched) when the shape has no TMA plan.
+int trb_lin_rescale_expand(int dir, const double* A, int64_t strideA, int R, int n, int ld, int B,
+                           double* part, const int* active, int Nz, int Nx, int rank, int null_space,
+                           const double* s, const double* s2, int64_t stride_s, const double* az,
+                           const double* ax, const double* tz, const double* tx, double* v,
+                           double* snap_tx, void* stream) {
+  int rc = check_gemv_args(A, R, n, ld, B, tz, part);
   if (rc) return rc;
   TRB_CHECK_ARG(strideA % 2 == 0, "strideA must be even");
-  TRB_CHECK_ARG(ldvec >= n, "ldvec < n");
-  TRB_CHECK_ARG(s && s2 && az && ax && t_other && coef && v && counter, "null pointer");
+  TRB_CHECK_ARG(s && s2 && az && ax && tz && tx && v, "null pointer");
   TRB_CHECK_ARG(dir == 0 || dir == 1, "dir must be 0 or 1");
-  TRB_CHECK_ARG(R <= Nz && R <= Nx && rank >= 0 && rank <= R && counter_stride > 0, "bad shape");
-  TmaPlan p;
-  if (!plan_tma(ld, p)) return TRB_ERR_UNSUPPORTED;
+  TRB_CHECK_ARG(R <= Nz && R <= Nx && rank >= 0 && rank <= R, "bad shape");
   cudaStream_t st = (cudaStream_t)stream;
   const trb_expand_geom geo = trb_expand_geometry(B, R);
-  RescaleEpi epi;
-  epi.counter = counter;
-  epi.counter_stride = counter_stride;
-  epi.dir = dir;
-  epi.Nz = Nz;
-  epi.Nx = Nx;
-  epi.rank = rank;
-  epi.null_space = null_space;
-  epi.s = s;
-  epi.s2 = s2;
-  epi.stride_s = stride_s;
-  epi.az = az;
-  epi.ax = ax;
-  epi.t_other = t_other;
-  epi.coef = coef;
-  epi.v_out = v;
-  epi.snap_tx = snap_tx;
+  RescaleFused rf;
+  rf.dir = dir;
+  rf.Nz = Nz;
+  rf.Nx = Nx;
+  rf.rank = rank;
+  rf.null_space = null_space;
+  rf.s = s;
+  rf.s2 = s2;
+  rf.stride_s = stride_s;
+  rf.az = az;
+  rf.ax = ax;
+  rf.tz = tz;
+  rf.tx = tx;
+  rf.v_out = v;
+  rf.snap_tx = snap_tx;
+  TmaPlan p, pq;
+  const bool one_panel = plan_tma(ld, p);
+  const Panels pan = plan_panels(ld);
+  if (!one_panel && (!plan_tma(pan.width, pq) || pq.nb < 8)) return TRB_ERR_UNSUPPORTED;
   trb_launch_scope scope_(1, st);
-  rc = dispatch_tma<2>(p, geo.G, A, strideA, R, n, ld, B, vec, ldvec, t_out, 0, active, st, ld, 0, 1, ld,
-                       n, epi);
-  if (rc) return rc;
-  TRB_CHECK_LAUNCH();
-  return TRB_OK;
-}
-
-// trb_lin_expand followed by the z (which = 0) or x (which = 1) update of the sweep in ONE launch
-// (UpdateEpi above).  counter: one unsigned per instance, zero on entry and zero again on exit.
-// TRB_ERR_UNSUPPORTED (nothing launched) when the rows need column panels or an instance may
-// span more than kTrbDirectSlots CTAs: the caller launches the kernels one by one instead.
-int trb_lin_expand_update(const double* A, int64_t strideA, int R, int n, int ld, int B,
-                          const double* coef, double* part, const int* active, const trb_sweep* sw,
-                          int which, int first, int it, double* stats, unsigned int* counter,
-                          int counter_stride, void* stream) {
-  int rc = check_gemv_args(A, R, n, ld, B, coef, part);
-  if (rc) return rc;
-  TRB_CHECK_ARG(strideA % 2 == 0, "strideA must be even");
-  TRB_CHECK_ARG(sw && stats && counter && counter_stride > 0 && (which == 0 || which == 1), "bad epilogue");
-  TRB_CHECK_ARG(part == sw->part, "the expansion must land in the sweep's slots");
-  TmaPlan p;
-  const trb_expand_geom geo = trb_expand_geometry(B, R);
-  if (!plan_tma(ld, p) || geo.nslots > kTrbDirectSlots || geo.nslots != sw->nslots) return TRB_ERR_UNSUPPORTED;
-  cudaStream_t st = (cudaStream_t)stream;
-  UpdateEpi upd;
-  upd.sw = *sw;
-  upd.which = which;
-  upd.G = geo.G;
-  upd.first = first;
-  upd.it = it;
-  upd.stats = stats;
-  upd.counter = counter;
-  upd.counter_stride = counter_stride;
-  trb_launch_scope scope_(1, st);
-  rc = dispatch_tma<3>(p, geo.G, A, strideA, R, n, ld, B, coef, 0, part, geo.nslots, active, st, ld, ld, 1,
-                       ld, n, RescaleEpi(), upd);
+  if (one_panel) {
+    rc = dispatch_tma<2>(p, geo.G, A, strideA, R, n, ld, B, tz, 0, part, geo.nslots, active, st, ld, ld, 1,
+                         ld, n, rf);
+  } else {
+    rc = dispatch_tma<2>(pq, geo.G, A, strideA, R, n, pan.width, B, tz, 0, part, geo.nslots, active, st, ld,
+                         ld, pan.count, ld, ld, rf);
+  }
   if (rc) return rc;
   TRB_CHECK_LAUNCH();
   return TRB_OK;

@@ -4,7 +4,7 @@
 // backward pass, update_variables), :70-127 (constant damping), :187-209 (NaN
 // check); algos/callbacks.py:250-286 (EarlyStoppingEP); algos/metrics.py:5-14.
 //
-// One iteration = 9 stages on one stream (7 launches: S1 and S2 run as epilogues of P1 and P3
+// One iteration = 9 stages on one stream (7 launches: S1 and S2 run inside the expansions P2 and P4
 // when the operator passes are GEMVs), B instances in lock step, no host round trip (edge
 // numbering e1..e8 as in SURVEY 3.3):
 //   F1  factor_message(prior)   e8 -> e1 (=e2)
@@ -233,7 +233,7 @@ k_x_update(trb_sweep sw, int G, int it_host, double* __restrict__ stats, trb_pee
 // up: ~80 KB in flight per SM where HBM needs ~150 KB (Little).  Here an instance is cut into
 // chunks of kChunk elements, one small CTA each (grid (chunks, B), 4 CTAs per SM), every thread
 // issues ALL its loads at once, and the chunk sums go to a scratch row of the instance; the CTA
-// that arrives last (threadfence + counter, columns 3 of `stats`) adds them in chunk order -- the
+// that arrives last (threadfence + counter, column 3 of `stats`) adds them in chunk order -- the
 // result does not depend on the arrival order -- and writes the instance's scalars (z_tail /
 // x_tail).  Per element the arithmetic is that of k_z_update / k_x_update, bit for bit.
 constexpr int kChThreads = 256;
@@ -392,14 +392,10 @@ k_tx_recur(trb_sweep sw) {
 
 }  // namespace
 
-// How the z / x / prior updates run (trb_set_update_kernels, TRB_UPDATE_KERNELS=<mask>):
-//   bit 0   x update chunked            bit 3   x update as the epilogue of the expansion P4
-//   bit 1   z update chunked (Gaussian  bit 4   z update as the epilogue of the expansion P2
-//           likelihood)                         (Gaussian likelihood)
-//   bit 2   prior's moments chunked
-// A cleared bit: one CTA / cluster per instance.  The epilogue wins over the chunked kernel where
-// both are set and the epilogue applies (trb_sweep_run only).  Default: all.
-constexpr int kUpdateKernelsAll = 31;
+// Which update kernels run chunked (trb_set_update_kernels, TRB_UPDATE_KERNELS=<mask>): bit 0 the x
+// update, bit 1 the z update with a Gaussian likelihood.  A cleared bit: one CTA / cluster per
+// instance.  Default: both.
+constexpr int kUpdateKernelsAll = 3;
 static int g_update_kernels = -1;
 
 static int update_kernels() {
@@ -454,23 +450,12 @@ int trb_lin_rescale_snap(int dir, int B, int R, int Nz, int Nx, int rank, int nu
                          const double* s, const double* s2, int64_t stride_s, const double* az,
                          const double* ax, const double* tz, const double* tx, double* coef, double* v,
                          const int* active, double* snap_tx, void* stream);
-int trb_factor_message_chunked(const trb_factor* f, int B, int n, int ld, const double* a_in,
-                               const double* b_in, const double* y, double* a_io, double* b_io,
-                               double* a_copy, double damping, double* scratch, int* flags,
-                               const int* active, double* snap_b, double* snap_a, double* snap_a_copy,
-                               unsigned int* counter, int counter_stride, double* partials,
-                               int partials_ld, void* stream);
-int trb_lin_project_rescale(const double* A, int64_t strideA, int R, int n, int ld, int B,
-                            const double* vec, int ldvec, double* t_out, const int* active, int dir,
-                            int Nz, int Nx, int rank, int null_space, const double* s, const double* s2,
-                            int64_t stride_s, const double* az, const double* ax, const double* t_other,
-                            double* coef, double* v, double* snap_tx, unsigned int* counter,
-                            int counter_stride, void* stream);
-bool trb_lin_single_panel(int ld);
-int trb_lin_expand_update(const double* A, int64_t strideA, int R, int n, int ld, int B,
-                          const double* coef, double* part, const int* active, const trb_sweep* sw,
-                          int which, int first, int it, double* stats, unsigned int* counter,
-                          int counter_stride, void* stream);
+int trb_lin_rescale_expand(int dir, const double* A, int64_t strideA, int R, int n, int ld, int B,
+                           double* part, const int* active, int Nz, int Nx, int rank, int null_space,
+                           const double* s, const double* s2, int64_t stride_s, const double* az,
+                           const double* ax, const double* tz, const double* tx, double* v,
+                           double* snap_tx, void* stream);
+int trb_reduce_slots_inplace(int B, int R, int n, int ld, double* part, void* stream);
 // The push is NOT gated by `active`: every rank takes the same stop decision in the same
 // iteration (the update kernels are computed redundantly on bit-identical sums), and a stopped
 // instance's `part` is no longer rewritten by trb_lin_expand, so the ranks go on pushing and
@@ -531,14 +516,6 @@ extern "C" int trb_sweep_stage(const trb_sweep* sw, int stage, int it, int first
     case TRB_STAGE_PRIOR: {  // F1: reads e8, writes e1 and its pass-through copy e2
       const double* b8 = (first && sw->b8_init) ? sw->b8_init : sw->b7;
       double* sa = sw->snap_edge_a;
-      if (update_kernels() & 4) {  // chunked moments; the partial sums borrow the z scratch
-        rc = trb_factor_message_chunked(&sw->prior, B, sw->N, sw->ldn, ea + 7 * B, b8, nullptr, ea + 0 * B,
-                                        sw->b1, ea + 1 * B, sw->damp1, sw->scr_n, sw->flags, sw->active,
-                                        sa ? sw->snap_b1 : nullptr, sa, sa ? sa + 1 * B : nullptr,
-                                        reinterpret_cast<unsigned int*>(sw->stats) + 6, 8, sw->scr_m,
-                                        sw->ldm, stream);
-        if (rc != TRB_ERR_UNSUPPORTED) return rc;
-      }
       return trb_factor_message_snap(&sw->prior, B, sw->N, sw->ldn, ea + 7 * B, b8, nullptr, ea + 0 * B,
                                      sw->b1, ea + 1 * B, sw->damp1, sw->scr_n, sw->flags, sw->active,
                                      sa ? sw->snap_b1 : nullptr, sa, sa ? sa + 1 * B : nullptr, stream);
@@ -678,11 +655,11 @@ case TRB_STAGE_EXPAND_Z:  // P4: rz = [b2/a2 +] V_R coef
   return trb_set_error(TRB_ERR_INVALID, "trb_sweep_stage: unknown stage %d", stage);
 }
 
-// ---- projection + rescale in one launch (P1+S1, P3+S2) ------------------------------
-// The rescale is 4 vectors of R per instance: as a kernel of its own it costs a launch and an
-// idle GPU on both sides (~15 us at the north-star size, twice per iteration).  The GEMV
-// projection takes it as an epilogue of the CTA that finishes an instance (trb_linear.cu).
-// Arrival counters: columns 2, 3 of `stats` ([B, 4] doubles), zeroed by trb_sweep_run.
+// ---- rescale inside the expansion (S1+P2, S2+P4) --------------------------------------
+// The rescale is 4 vectors of R per instance: as a kernel of its own it costs a launch and an idle
+// GPU on both sides (~18 us at the north-star size, twice per iteration).  The expanding GEMV
+// computes the coefficients itself, one block of rows ahead of the rows it streams, and the
+// variance from the spectrum (trb_linear.cu, RescaleFused): no coefficient vector, no launch.
 static int g_fuse_rescale = -1;
 
 extern "C" void trb_set_fused_rescale(int enabled) { g_fuse_rescale = enabled ? 1 : 0; }
@@ -695,54 +672,30 @@ static bool rescale_fusable(const trb_sweep* sw) {
   if (!g_fuse_rescale || sw->comm || !sw->s || !sw->s2 || !sw->Vt || !sw->Ut) return false;
   const bool shared_ops = sw->strideV == 0 && sw->strideU == 0;
   if (shared_ops && (sw->gemv_impl == 3 || (sw->gemv_impl == 0 && sw->B >= 16))) return false;  // GEMM passes
-  if (sw->gemv_impl != 0 && sw->gemv_impl != 2) return false;
-  return trb_lin_single_panel(sw->ldn) && trb_lin_single_panel(sw->ldm);
+  return sw->gemv_impl == 0 || sw->gemv_impl == 2;
 }
 
-static int project_and_rescale(const trb_sweep* sw, int dir, cudaStream_t st) {
+// TRB_ERR_UNSUPPORTED: nothing was launched, the caller runs the two stages one by one
+static int rescale_and_expand(const trb_sweep* sw, int dir, cudaStream_t st) {
   const int B = sw->B;
   double* ea = sw->edge_a;
   const int R_total = sw->R_total > 0 ? sw->R_total : sw->R;
   const int null_space = R_total < sw->N;
-  unsigned int* counters = reinterpret_cast<unsigned int*>(sw->stats) + 4;  // columns 2, 3 of stats
-  if (dir == 0)  // P1 + S1: tz = V_R^T b2, coef = s res (tz + s tx), forward variance
-    return trb_lin_project_rescale(sw->Vt, sw->strideV, sw->R, sw->N, sw->ldn, B, sw->b1, sw->ldn, sw->tz,
-                                   sw->active, 0, sw->N, sw->M, sw->rank, null_space, sw->s, sw->s2,
-                                   sw->stride_s, ea + 1 * B, ea + 5 * B, sw->tx, sw->coef, sw->vlin,
-                                   (sw->schedule == 0 && sw->snap_edge_a) ? sw->snap_tx : nullptr, counters,
-                                   8, (void*)st);
-  // P3 + S2: tx = U_R^T b6 (new), coef for rz, backward variance
-  return trb_lin_project_rescale(sw->Ut, sw->strideU, sw->R, sw->M, sw->ldm, B, sw->b5, sw->ldm, sw->tx,
-                                 sw->active, 1, sw->N, sw->M, sw->rank, null_space, sw->s, sw->s2,
-                                 sw->stride_s, ea + 1 * B, ea + 5 * B, sw->tz, sw->coef, sw->vlin, nullptr,
-                                 counters + 1, 8, (void*)st);
-}
-
-// ---- expansion + update in one launch (P2+Z, P4+X) -----------------------------------
-// The CTA that stores the last slot of an instance holds everything the z / x update needs; it
-// updates the instance on the spot (trb_linear.cu, UpdateEpi) instead of a kernel of its own
-// reading the slots back after a launch gap.  One CTA walks the whole instance vector, so the
-// epilogue is for instances of up to kFoldMaxElems elements; larger ones keep the chunked kernels.
-constexpr int kFoldMaxElems = 8192;
-
-static bool update_foldable(const trb_sweep* sw, int which) {
-  if (!(update_kernels() & (which == 0 ? 16 : 8)) || sw->comm || !sw->Vt || !sw->Ut) return false;
-  const bool shared_ops = sw->strideV == 0 && sw->strideU == 0;
-  if (shared_ops && (sw->gemv_impl == 3 || (sw->gemv_impl == 0 && sw->B >= 16))) return false;  // GEMM passes
-  if (sw->gemv_impl != 0 && sw->gemv_impl != 2) return false;
-  if (sw->nslots > kTrbDirectSlots) return false;  // the slots are reduced by a kernel of their own first
-  if (which == 0)
-    return sw->lik.kind == TRB_GAUSSIAN_LIKELIHOOD && sw->M <= kFoldMaxElems && trb_lin_single_panel(sw->ldm);
-  return sw->N <= kFoldMaxElems && trb_lin_single_panel(sw->ldn);
-}
-
-static int expand_and_update(const trb_sweep* sw, int which, int first, int it, cudaStream_t st) {
-  unsigned int* counters = reinterpret_cast<unsigned int*>(sw->stats) + 6;  // column 3 of stats
-  if (which == 0)  // P2 + Z
-    return trb_lin_expand_update(sw->Ut, sw->strideU, sw->R, sw->M, sw->ldm, sw->B, sw->coef, sw->part,
-                                 sw->active, sw, 0, first, it, sw->stats, counters, 8, (void*)st);
-  return trb_lin_expand_update(sw->Vt, sw->strideV, sw->R, sw->N, sw->ldn, sw->B, sw->coef, sw->part,
-                               sw->active, sw, 1, first, it, sw->stats, counters + 1, 8, (void*)st);
+  int rc;
+  if (dir == 0)  // S1 + P2: coef = s res (tz + s tx), forward variance, rx = U_R coef
+    rc = trb_lin_rescale_expand(0, sw->Ut, sw->strideU, sw->R, sw->M, sw->ldm, B, sw->part, sw->active,
+                                sw->N, sw->M, sw->rank, null_space, sw->s, sw->s2, sw->stride_s,
+                                ea + 1 * B, ea + 5 * B, sw->tz, sw->tx, sw->vlin,
+                                (sw->schedule == 0 && sw->snap_edge_a) ? sw->snap_tx : nullptr, (void*)st);
+  else  // S2 + P4: coef for rz, backward variance, rz = [b2/a2 +] V_R coef
+    rc = trb_lin_rescale_expand(1, sw->Vt, sw->strideV, sw->R, sw->N, sw->ldn, B, sw->part, sw->active,
+                                sw->N, sw->M, sw->rank, null_space, sw->s, sw->s2, sw->stride_s,
+                                ea + 1 * B, ea + 5 * B, sw->tz, sw->tx, sw->vlin, nullptr, (void*)st);
+  if (rc) return rc;
+  if (sw->nslots > kTrbDirectSlots)  // few instances over many CTAs: leave the slot sum in slot 0
+    return trb_reduce_slots_inplace(B, sw->R, dir == 0 ? sw->M : sw->N, dir == 0 ? sw->ldm : sw->ldn,
+                                    sw->part, (void*)st);
+  return TRB_OK;
 }
 
 // One whole iteration, stage by stage (see the header comment of this file).
@@ -752,47 +705,39 @@ static int enqueue_iteration(const trb_sweep* sw, int it, int first, int fresh, 
   const int schedule = sw->schedule;
   const bool fuse = rescale_fusable(sw);
   TRB_TRY(trb_sweep_stage(sw, TRB_STAGE_PRIOR, it, first, 0, stream));
-  if (fuse && !first) {  // the first iteration still has to produce tx before S1
-    TRB_TRY(project_and_rescale(sw, 0, st));
-  } else {
-    TRB_TRY(trb_sweep_stage(sw, TRB_STAGE_PROJECT_Z, it, first, 0, stream));
-    if (first) {
-      if (fresh == 2) {  // e6 was initialised to b = 0: U_R^T 0 = 0, no pass over U needed
-        cudaError_t e = cudaMemsetAsync(sw->tx, 0, sizeof(double) * (size_t)sw->B * sw->R, st);
-        if (e != cudaSuccess)
-          return trb_set_error(TRB_ERR_CUDA, "trb_sweep_run: %s", cudaGetErrorString(e));
-      } else {
-        TRB_TRY(trb_sweep_stage(sw, TRB_STAGE_PROJECT_X_INIT, it, first, 0, stream));
-      }
+  TRB_TRY(trb_sweep_stage(sw, TRB_STAGE_PROJECT_Z, it, first, 0, stream));
+  if (first) {
+    if (fresh == 2) {  // e6 was initialised to b = 0: U_R^T 0 = 0, no pass over U needed
+      cudaError_t e = cudaMemsetAsync(sw->tx, 0, sizeof(double) * (size_t)sw->B * sw->R, st);
+      if (e != cudaSuccess)
+        return trb_set_error(TRB_ERR_CUDA, "trb_sweep_run: %s", cudaGetErrorString(e));
+    } else {
+      TRB_TRY(trb_sweep_stage(sw, TRB_STAGE_PROJECT_X_INIT, it, first, 0, stream));
     }
+  }
+  int fused = TRB_ERR_UNSUPPORTED;
+  if (fuse && !light) {
+    fused = rescale_and_expand(sw, 0, st);
+    if (fused != TRB_OK && fused != TRB_ERR_UNSUPPORTED) return fused;
+  }
+  if (fused != TRB_OK) {
     TRB_TRY(trb_sweep_stage(sw, TRB_STAGE_RESCALE_FWD, it, first, 0, stream));
-  }
-  int folded = TRB_ERR_UNSUPPORTED;
-  if (!light && update_foldable(sw, 0)) {
-    folded = expand_and_update(sw, 0, first, it, st);
-    if (folded != TRB_OK && folded != TRB_ERR_UNSUPPORTED) return folded;
-  }
-  if (folded != TRB_OK) {
     if (!light) TRB_TRY(trb_sweep_stage(sw, TRB_STAGE_EXPAND_X, it, first, 0, stream));
-    TRB_TRY(trb_sweep_stage(sw, light ? TRB_STAGE_Z_UPDATE_LIGHT : TRB_STAGE_Z_UPDATE, it, first, 0,
-                            stream));
   }
-  if (fuse && schedule == 0) {
-    TRB_TRY(project_and_rescale(sw, 1, st));
-  } else {
-    TRB_TRY(trb_sweep_stage(sw, schedule ? TRB_STAGE_TX_RECUR : TRB_STAGE_PROJECT_X, it, first, 0,
-                            stream));
+  TRB_TRY(trb_sweep_stage(sw, light ? TRB_STAGE_Z_UPDATE_LIGHT : TRB_STAGE_Z_UPDATE, it, first, 0,
+                          stream));
+  TRB_TRY(trb_sweep_stage(sw, schedule ? TRB_STAGE_TX_RECUR : TRB_STAGE_PROJECT_X, it, first, 0,
+                          stream));
+  fused = TRB_ERR_UNSUPPORTED;
+  if (fuse) {
+    fused = rescale_and_expand(sw, 1, st);
+    if (fused != TRB_OK && fused != TRB_ERR_UNSUPPORTED) return fused;
+  }
+  if (fused != TRB_OK) {
     TRB_TRY(trb_sweep_stage(sw, TRB_STAGE_RESCALE_BWD, it, first, 0, stream));
-  }
-  folded = TRB_ERR_UNSUPPORTED;
-  if (update_foldable(sw, 1)) {
-    folded = expand_and_update(sw, 1, first, it, st);
-    if (folded != TRB_OK && folded != TRB_ERR_UNSUPPORTED) return folded;
-  }
-  if (folded != TRB_OK) {
     TRB_TRY(trb_sweep_stage(sw, TRB_STAGE_EXPAND_Z, it, first, 0, stream));
-    TRB_TRY(trb_sweep_stage(sw, TRB_STAGE_X_UPDATE, it, first, 0, stream));
   }
+  TRB_TRY(trb_sweep_stage(sw, TRB_STAGE_X_UPDATE, it, first, 0, stream));
   // The update kernels copy every value they overwrite to the one-iteration-back state, so a
   // stopped instance is rolled back once, at the end of trb_sweep_run.  Schedule 2 skips the z
   // branch (b3, rz are not rewritten every iteration) and keeps the copy kernel.
@@ -837,7 +782,7 @@ static thread_local GraphCache g_graph;
 
 static int run_graph(const trb_sweep* sw, bool light, int count, cudaStream_t st) {
   GraphCache& gc = g_graph;
-  const int kernel_choice = update_kernels() | (rescale_fusable(sw) ? 32 : 0);
+  const int kernel_choice = update_kernels() | (rescale_fusable(sw) ? 4 : 0);
   if (!gc.exec || gc.light != (int)light || gc.kernel_choice != kernel_choice ||
       memcmp(&gc.key, sw, sizeof(trb_sweep)) != 0) {
     if (gc.exec) {
@@ -908,7 +853,7 @@ extern "C" int trb_sweep_run(const trb_sweep* sw, int it0, int n_iter, int fresh
     const int rc_p = trb_sweep_run_persistent(sw, it0, n_iter, fresh, st);
     if (rc_p != TRB_ERR_UNSUPPORTED) return rc_p;
   }
-  if (n_iter > 0) {  // arrival counters (fused projections, chunked updates): stats[:, 2:4]
+  if (n_iter > 0) {  // arrival counters of the chunked updates: stats[:, 2:4]
     const cudaError_t e = cudaMemset2DAsync(reinterpret_cast<char*>(sw->stats) + 16, 32, 0, 16, sw->B, st);
     if (e != cudaSuccess) return trb_set_error(TRB_ERR_CUDA, "trb_sweep_run: %s", cudaGetErrorString(e));
   }
