@@ -85,7 +85,7 @@ size_t trb_sizeof_sweep(void);
 int trb_device_sm_count(void);
 
 /* Launch accounting for benchmarks: trb_profile_reset(enable_events) zeroes the
- * counters (and, if enable_events, brackets every GEMV launch with CUDA events
+ * counters (and, if enable_events, brackets every launch of the sweep with CUDA events
  * on its stream); trb_profile_launches(kind) = kernels launched since then
  * (kind 0 elementwise/update, 1 operator pass = GEMV or shared-operator GEMM,
  * 2 LinearChannel set-up kernels (trb_jacobi_sweep, ...), -1 = 0 and 1 together: the EP
@@ -94,6 +94,10 @@ int trb_device_sm_count(void);
 void trb_profile_reset(int enable_events);
 long long trb_profile_launches(int kind);
 int trb_profile_gemv_ms(double* total_ms);
+/* With events enabled every sweep launch is bracketed: the durations in launch order (ms[i];
+ * kinds[i] = 0 update kernel, 1 operator pass).  Returns how many launches were timed since the
+ * reset; at most `cap` entries are written. */
+int trb_profile_timeline(double* ms, int* kinds, int cap);
 
 /* ---- elementwise moment kernels ------------------------------------------
  * a_mode: 0 = one precision per instance a[B] (isotropic beliefs), 1 = one per
@@ -420,12 +424,12 @@ int trb_sweep_run(const trb_sweep* sw, int it0, int n_iter, int fresh, void* str
  * that off (default on; the environment variable TRB_CUDA_GRAPHS=0 does the same). */
 void trb_set_cuda_graphs(int enabled);
 
-/* trb_sweep_run runs the rescale stages S1 / S2 INSIDE the GEMV expansions P2 / P4 that consume
- * them (every consumer warp computes the coefficients of its next 32 rows from tz, tx and the
- * spectrum, one block ahead of the rows it streams; the variance comes from the CTA that owns the
- * instance's first row): 7 launches per iteration instead of 9, no coefficient vector in HBM.
- * Applies when the operator passes are TMA GEMVs and the sweep is not row-sharded; 0 turns it off
- * (default on; TRB_FUSE_RESCALE=0 does the same). */
+/* trb_sweep_run runs the rescale stages S1 / S2 INSIDE the GEMV projections P1 / P3 that feed
+ * them (the thread that finishes the block reduction of a row writes the row's coefficient next
+ * to its projection, from operands loaded while the row streamed; the variance comes from the CTA
+ * that owns the instance's first row): 7 launches per iteration instead of 9.  Applies when the
+ * operator passes are TMA GEMVs and the sweep is not row-sharded; 0 turns it off (default on;
+ * TRB_FUSE_RESCALE=0 does the same). */
 void trb_set_fused_rescale(int enabled);
 
 /* The x update (bit 0) and the z update with a Gaussian likelihood (bit 1) run as CHUNKED

@@ -852,10 +852,10 @@ def _kernel_choice_cases(sw):
     return cases
 
 
-def test_rescale_inside_the_expansion_equals_separate_launches(sw):
-    """trb_sweep_run runs the rescale stages S1 / S2 inside the GEMV expansions P2 / P4 (every
-    consumer warp computes the coefficients of its next rows itself; the CTA that owns an
-    instance's first row computes the variance).  Same arithmetic per coefficient; only the
+def test_rescale_inside_the_projection_equals_separate_launches(sw):
+    """trb_sweep_run runs the rescale stages S1 / S2 inside the GEMV projections P1 / P3 (the
+    thread that finishes a row's block reduction writes the row's coefficient; the CTA that owns
+    an instance's first row computes the variance).  Same arithmetic per coefficient; only the
     order of the spectrum sum behind the variance differs: 1e-12 against the nine-launch
     iteration, with two launches fewer per iteration."""
     from tramp_b200 import _lib

@@ -111,6 +111,7 @@ SIGNATURES = {
     "trb_profile_reset": (None, [_I]),
     "trb_profile_launches": (C.c_longlong, [_I]),
     "trb_profile_gemv_ms": (_I, [C.POINTER(C.c_double)]),
+    "trb_profile_timeline": (_I, [_P, _P, _I]),
     "trb_factor_posterior": (_I, [_FP, _I, _I, _I, _P, _I, _P, _P, _P, _P, _I, _P]),
     "trb_factor_log_partition": (_I, [_FP, _I, _I, _I, _P, _I, _P, _P, _P, _I, _P]),
     "trb_factor_message": (_I, [_FP, _I, _I, _I, _P, _P, _P, _P, _P, _P, _D, _P, _P, _P, _P]),

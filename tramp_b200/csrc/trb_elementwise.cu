@@ -38,6 +38,7 @@ struct ProfileState {
   long long launches[3] = {0, 0, 0};  // update kernels, operator passes, set-up (trb_setup.cu)
   std::vector<cudaEvent_t> pool;         // recycled events
   std::vector<cudaEvent_t> begin[2], end[2];
+  std::vector<int> order;                // kinds of the timed launches (0 / 1), in launch order
 };
 ProfileState g_prof;
 cudaEvent_t prof_event() {
@@ -54,10 +55,11 @@ cudaEvent_t prof_event() {
 
 void trb_note_launch(int kind, cudaStream_t st, bool before) {
   if (before) g_prof.launches[kind] += 1;
-  if (!g_prof.enabled || kind != 1) return;
+  if (!g_prof.enabled || kind > 1) return;
   cudaEvent_t e = prof_event();
   cudaEventRecord(e, st);
   (before ? g_prof.begin[kind] : g_prof.end[kind]).push_back(e);
+  if (before) g_prof.order.push_back(kind);
 }
 
 bool trb_profile_events_enabled() { return g_prof.enabled; }
@@ -76,6 +78,7 @@ extern "C" void trb_profile_reset(int enable_events) {
     g_prof.begin[k].clear();
     g_prof.end[k].clear();
   }
+  g_prof.order.clear();
   g_prof.enabled = enable_events != 0;
 }
 
@@ -95,6 +98,28 @@ extern "C" int trb_profile_gemv_ms(double* total_ms) {
   }
   if (total_ms) *total_ms = tot;
   return (int)n;
+}
+
+// The event-timed launches since the last reset, in launch order: ms[i] = duration, kinds[i] = 0
+// (update kernel) or 1 (operator pass).  Waits for the last one; returns how many there are (at
+// most `cap` are written).
+extern "C" int trb_profile_timeline(double* ms, int* kinds, int cap) {
+  size_t next[2] = {0, 0};
+  int n = 0;
+  for (size_t i = 0; i < g_prof.order.size(); ++i) {
+    const int k = g_prof.order[i];
+    const size_t j = next[k]++;
+    if (j >= g_prof.end[k].size()) break;
+    if (n < cap) {
+      float t = 0.f;
+      cudaEventSynchronize(g_prof.end[k][j]);
+      if (cudaEventElapsedTime(&t, g_prof.begin[k][j], g_prof.end[k][j]) != cudaSuccess) t = -1.f;
+      if (ms) ms[n] = t;
+      if (kinds) kinds[n] = k;
+    }
+    ++n;
+  }
+  return n;
 }
 
 extern "C" const char* trb_last_error(void) { return trb_err_buf; }

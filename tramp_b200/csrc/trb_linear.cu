@@ -281,30 +281,30 @@ __device__ __forceinline__ double rescale_variance(int dir, int Nz, int Nx, int 
   return (1 - n_eff) / pl.az_v;  // :95-97
 }
 
-// The rescale stage (S1 / S2 of the sweep) inside the expansion that consumes it (P2 / P4): the
-// coefficient of row i depends on row i only -- tz_i, tx_i, s_i and the instance's (az, ax) -- so
-// every consumer warp computes the coefficients of its next 32 rows itself (lane = row), one block
-// ahead of the rows it is streaming, and hands them out by shuffle; the variance needs the
-// spectrum only and is computed by the CTA that owns the instance's first row from values it
-// loaded a segment earlier.  No coefficient vector in HBM, no launch, and -- unlike an epilogue
-// that waits for other CTAs (measured: every dependent access inside a kernel that saturates HBM
-// queues behind ~30 MB of ring traffic, ~4 us) -- no memory round trip on the critical path.
+// The rescale stage (S1 / S2 of the sweep) inside the projection that feeds it (P1 / P3): the
+// coefficient of row i depends on row i only -- its own projection, the other projection, s_i and
+// the instance's (az, ax) -- so the thread that finishes the block reduction of a row writes the
+// coefficient next to the projection, from operands it loaded while the row was streaming; the
+// variance needs the spectrum only and is computed by the CTA that owns the instance's first row
+// from values it loaded a segment earlier.  No launch, no wait on other CTAs -- measured: a
+// dependent access inside a kernel that saturates HBM queues behind ~30 MB of ring traffic
+// (~4 us), which is what made the "last-arriving CTA rescales the instance" epilogue lose.
 struct RescaleFused {
   int dir, Nz, Nx, rank, null_space;
   const double* s;
   const double* s2;
   int64_t stride_s;
-  const double* az;  // [B]
-  const double* ax;  // [B]
-  const double* tz;  // [B, R]
-  const double* tx;  // [B, R]
-  double* v_out;     // [B]
-  double* snap_tx;   // nullable, [B, R]: receives a copy of tx (one-iteration-back state)
+  const double* az;       // [B]
+  const double* ax;       // [B]
+  const double* t_other;  // the projection this launch does not write (dir 0: tx, dir 1: tz), [B, R]
+  double* coef;           // [B, R]
+  double* v_out;          // [B]
+  double* snap_tx;        // nullable, [B, R]: receives a copy of tx (dir 0 only)
 };
 
 constexpr int kVarRegs = 8;  // spectrum values per thread kept in flight for the next instance's variance
 
-// MODE: 0 project, 1 expand, 2 expand with the rescale inside (coefficients and variance on the fly)
+// MODE: 0 project, 1 expand, 2 project with the rescale inside (coefficients and variance)
 template <int NB, int MODE>
 __global__ void __launch_bounds__(kTmaThreads, 1)
 k_gemv_tma(const double* __restrict__ A, int64_t strideA, int R, int n, int ld, int B,
@@ -316,7 +316,7 @@ k_gemv_tma(const double* __restrict__ A, int64_t strideA, int R, int n, int ld, 
            int npanels,      // > 1: A is npanels column panels of `ld` doubles (the last one may be
                              // narrower: full_ld, full_n); every CTA walks its rows once per panel
            int full_ld, int full_n, RescaleFused rf) {
-  constexpr bool EXPAND = MODE != 0;
+  constexpr bool EXPAND = MODE == 1;
   constexpr int RC = TmaCfg<NB>::RC;
   extern __shared__ __align__(128) double ring[];  // nstages * stage_doubles
   __shared__ __align__(8) uint64_t full_bar[kMaxStages];
@@ -371,32 +371,9 @@ k_gemv_tma(const double* __restrict__ A, int64_t strideA, int R, int n, int ld, 
 
   // -------------------------------------------------------------- consumers
   int red_buf = 0;
-  // MODE 2 (see RescaleFused): inputs of the next coefficient block (row nb_row + lane of instance
-  // nb_b) and of the next instance's variance (instance nv_b), in flight while rows stream
-  [[maybe_unused]] double nb_s = 0.0, nb_s2 = 0.0, nb_tz = 0.0, nb_tx = 0.0, nb_az = 0.0, nb_ax = 0.0;
-  [[maybe_unused]] int nb_b = -1, nb_row = 0;
+  // MODE 2 (see RescaleFused): the spectrum of the next instance, in flight while rows stream
   [[maybe_unused]] double nv_s2[kVarRegs], nv_az = 0.0, nv_ax = 0.0;
   [[maybe_unused]] int nv_b = -1;
-  [[maybe_unused]] auto block_issue = [&](int bn, int row, int end) {
-    nb_b = bn;
-    nb_row = row;
-    nb_az = rf.az[bn];
-    nb_ax = rf.ax[bn];
-    const int r = row + lane;
-    if (r < end) {
-      nb_s = rf.s[(size_t)bn * rf.stride_s + r];
-      nb_s2 = rf.s2[(size_t)bn * rf.stride_s + r];
-      nb_tz = rf.tz[(size_t)bn * R + r];
-      nb_tx = rf.tx[(size_t)bn * R + r];
-    }
-  };
-  // coefficient of row nb_row + lane of the block in flight (0 past the end of the segment)
-  [[maybe_unused]] auto block_finish = [&](int end) -> double {
-    const int r = nb_row + lane;
-    if (r >= end) return 0.0;
-    if (warp == 0 && rf.snap_tx) rf.snap_tx[(size_t)nb_b * R + r] = nb_tx;  // every row once: its segment's CTA
-    return rescale_coef(rf.dir, rf.null_space != 0, nb_az, nb_ax, nb_s, nb_s2, nb_tz, nb_tx);
-  };
   [[maybe_unused]] auto var_issue = [&](int bn) {
     nv_b = bn;
     nv_az = rf.az[bn];
@@ -420,6 +397,45 @@ k_gemv_tma(const double* __restrict__ A, int64_t strideA, int R, int n, int ld, 
   while (next_segment(g, g1, R, s)) {
     if (active && !active[s.b]) continue;
     if constexpr (!EXPAND) {
+      [[maybe_unused]] double seg_az = 0.0, seg_ax = 0.0;
+      if constexpr (MODE == 2) {
+        seg_az = rf.az[s.b];
+        seg_ax = rf.ax[s.b];
+        // after this segment the CTA goes on with row 0 of the next instance, if its range goes on
+        const bool more = (s.i1 == R) && (g < g1);
+        if (s.i0 == 0 && pq == 0) {
+          // ---- this CTA owns the instance's first row: its variance (spectrum only), from the
+          // values loaded during the previous segment (the CTA's first segment loads them here)
+          if (nv_b != s.b) var_issue(s.b);
+          const RescalePlan pl = rescale_plan(rf.dir, nv_az, nv_ax);
+          double part = 0.0;
+#pragma unroll
+          for (int u = 0; u < kVarRegs; ++u) {
+            const int i = tid + u * kConsumers;
+            if (i < R && i < rf.rank) {
+              if (pl.sum_mode == 1) part += nv_s2[u];
+              else if (pl.sum_mode == 2) part += nv_s2[u] / (pl.ratio + nv_s2[u]);
+            }
+          }
+          for (int i = tid + kVarRegs * kConsumers; i < R && i < rf.rank; i += kConsumers) {
+            const double s2i = rf.s2[(size_t)s.b * rf.stride_s + i];
+            if (pl.sum_mode == 1) part += s2i;
+            else if (pl.sum_mode == 2) part += s2i / (pl.ratio + s2i);
+          }
+          part = warp_sum(part);
+          consumer_bar();  // red is free: the previous segment's last group has been read
+          if (lane == 0) red[red_buf][warp][0] = part;
+          consumer_bar();
+          if (tid == 0) {
+            double tot = 0.0;
+#pragma unroll
+            for (int w = 0; w < kConsumers / 32; ++w) tot += red[red_buf][w][0];
+            rf.v_out[s.b] = rescale_variance(rf.dir, rf.Nz, rf.Nx, rf.rank, pl, nv_az, nv_ax, tot);
+          }
+          red_buf ^= 1;
+        }
+        if (more && pq == 0) var_issue(s.b + 1);
+      }
       // ---- project: x slice in registers, 8-row groups, block reduction
       double2 x[NB];
 #pragma unroll
@@ -433,6 +449,16 @@ k_gemv_tma(const double* __restrict__ A, int64_t strideA, int R, int n, int ld, 
         double acc[kGroupRows];
 #pragma unroll
         for (int q = 0; q < kGroupRows; ++q) acc[q] = 0.0;
+        // MODE 2: what the coefficient of this thread's row needs besides the projection, loaded
+        // while the group's rows stream
+        [[maybe_unused]] double pf_s = 0.0, pf_s2 = 0.0, pf_other = 0.0;
+        if constexpr (MODE == 2) {
+          if (pq == npanels - 1 && tid < kGroupRows && ig + tid < s.i1) {
+            pf_s = rf.s[(size_t)s.b * rf.stride_s + ig + tid];
+            pf_s2 = rf.s2[(size_t)s.b * rf.stride_s + ig + tid];
+            pf_other = rf.t_other[(size_t)s.b * R + ig + tid];
+          }
+        }
 #pragma unroll
         for (int c = 0; c < kGroupRows / RC; ++c) {
           const int i = ig + c * RC;
@@ -475,7 +501,16 @@ k_gemv_tma(const double* __restrict__ A, int64_t strideA, int R, int n, int ld, 
 #pragma unroll
           for (int w = 0; w < kConsumers / 32; ++w) tot += red[red_buf][w][tid];
           double* dst = out + (size_t)s.b * R + ig + tid;
-          *dst = accumulate ? *dst + tot : tot;
+          if (accumulate) tot = *dst + tot;
+          *dst = tot;
+          if constexpr (MODE == 2) {
+            if (pq == npanels - 1) {  // the projection of this row is complete: its coefficient
+              const size_t o = (size_t)s.b * R + ig + tid;
+              if (rf.snap_tx) rf.snap_tx[o] = pf_other;  // dir 0: t_other is tx
+              rf.coef[o] = rescale_coef(rf.dir, rf.null_space != 0, seg_az, seg_ax, pf_s, pf_s2,
+                                        rf.dir == 0 ? tot : pf_other, rf.dir == 0 ? pf_other : tot);
+            }
+          }
         }
         red_buf ^= 1;
       }
@@ -485,69 +520,11 @@ k_gemv_tma(const double* __restrict__ A, int64_t strideA, int R, int n, int ld, 
 #pragma unroll
       for (int k = 0; k < NB; ++k) acc[k] = make_double2(0.0, 0.0);
       const double* cb = vec + (size_t)s.b * R;
-      [[maybe_unused]] int blk_row = s.i0;
-      [[maybe_unused]] double cblk = 0.0;
-      if constexpr (MODE == 2) {
-        // after this segment the CTA goes on with row 0 of the next instance, if its range goes on
-        const bool more = (s.i1 == R) && (g < g1);
-        const int next_end = more ? ((g1 - g < (int64_t)R) ? (int)(g1 - g) : R) : 0;
-        if (s.i0 == 0 && pq == 0) {
-          // ---- this CTA owns the instance's first row: its variance (spectrum only), from the
-          // values loaded during the previous segment (the CTA's first segment loads them here)
-          if (nv_b != s.b) var_issue(s.b);
-          const RescalePlan pl = rescale_plan(rf.dir, nv_az, nv_ax);
-          double part = 0.0;
-#pragma unroll
-          for (int u = 0; u < kVarRegs; ++u) {
-            const int i = tid + u * kConsumers;
-            if (i < R && i < rf.rank) {
-              if (pl.sum_mode == 1) part += nv_s2[u];
-              else if (pl.sum_mode == 2) part += nv_s2[u] / (pl.ratio + nv_s2[u]);
-            }
-          }
-          for (int i = tid + kVarRegs * kConsumers; i < R && i < rf.rank; i += kConsumers) {
-            const double s2i = rf.s2[(size_t)s.b * rf.stride_s + i];
-            if (pl.sum_mode == 1) part += s2i;
-            else if (pl.sum_mode == 2) part += s2i / (pl.ratio + s2i);
-          }
-          part = warp_sum(part);
-          consumer_bar();
-          if (lane == 0) red[0][warp][0] = part;
-          consumer_bar();
-          if (tid == 0) {
-            double tot = 0.0;
-#pragma unroll
-            for (int w = 0; w < kConsumers / 32; ++w) tot += red[0][w][0];
-            rf.v_out[s.b] = rescale_variance(rf.dir, rf.Nz, rf.Nx, rf.rank, pl, nv_az, nv_ax, tot);
-          }
-        }
-        if (more && pq == 0) var_issue(s.b + 1);
-        // ---- coefficients: the block of this segment's first 32 rows (in flight since the previous
-        // segment, else loaded here), then always one block ahead
-        if (!(nb_b == s.b && nb_row == s.i0)) block_issue(s.b, s.i0, s.i1);
-        cblk = block_finish(s.i1);
-        if (blk_row + 32 < s.i1) block_issue(s.b, blk_row + 32, s.i1);
-        else if (more) block_issue(s.b + 1, 0, next_end);
-      }
       for (int i = s.i0; i < s.i1; i += RC) {
         const int rows = (s.i1 - i < RC) ? (s.i1 - i) : RC;
         double c[RC];
-        if constexpr (MODE == 2) {
-          if (i - blk_row == 32) {  // RC divides 32: a stage never straddles two blocks
-            blk_row = i;
-            cblk = block_finish(s.i1);
-            if (blk_row + 32 < s.i1) {
-              block_issue(s.b, blk_row + 32, s.i1);
-            } else if ((s.i1 == R) && (g < g1)) {
-              block_issue(s.b + 1, 0, (g1 - g < (int64_t)R) ? (int)(g1 - g) : R);
-            }
-          }
 #pragma unroll
-          for (int rr = 0; rr < RC; ++rr) c[rr] = __shfl_sync(0xffffffffu, cblk, (i - blk_row) + rr);
-        } else {
-#pragma unroll
-          for (int rr = 0; rr < RC; ++rr) c[rr] = (rr < rows) ? __ldg(cb + i + rr) : 0.0;
-        }
+        for (int rr = 0; rr < RC; ++rr) c[rr] = (rr < rows) ? __ldg(cb + i + rr) : 0.0;
         mbar_wait(&full_bar[stage], phase);
         const double2* st = reinterpret_cast<const double2*>(ring + (size_t)stage * stage_doubles);
 #pragma unroll
@@ -820,20 +797,22 @@ extern "C" int trb_lin_project(const double* A, int64_t strideA, int R, int n, i
   return TRB_OK;
 }
 
-// trb_lin_rescale followed by trb_lin_expand in ONE launch (sweep stages S1+P2 and S2+P4): the
-// coefficients are computed inside the expansion from tz, tx and the spectrum (RescaleFused above),
-// the variance goes to v.  snap_tx (nullable) receives a copy of tx.  TMA GEMV only:
-// TRB_ERR_UNSUPPORTED (nothing launched) when the shape has no TMA plan.
-int trb_lin_rescale_expand(int dir, const double* A, int64_t strideA, int R, int n, int ld, int B,
-                           double* part, const int* active, int Nz, int Nx, int rank, int null_space,
-                           const double* s, const double* s2, int64_t stride_s, const double* az,
-                           const double* ax, const double* tz, const double* tx, double* v,
-                           double* snap_tx, void* stream) {
-  int rc = check_gemv_args(A, R, n, ld, B, tz, part);
+// trb_lin_project followed by trb_lin_rescale in ONE launch (sweep stages P1+S1 and P3+S2, see
+// RescaleFused).  dir 0: t_out is tz and t_other tx; dir 1: t_out is tx and t_other tz.  snap_tx
+// (nullable, dir 0) receives a copy of tx.  TMA GEMV only: TRB_ERR_UNSUPPORTED (nothing launched)
+// when the shape has no TMA plan.
+int trb_lin_project_rescale(const double* A, int64_t strideA, int R, int n, int ld, int B,
+                            const double* vec, int ldvec, double* t_out, const int* active, int dir,
+                            int Nz, int Nx, int rank, int null_space, const double* s, const double* s2,
+                            int64_t stride_s, const double* az, const double* ax, const double* t_other,
+                            double* coef, double* v, double* snap_tx, void* stream) {
+  int rc = check_gemv_args(A, R, n, ld, B, vec, t_out);
   if (rc) return rc;
   TRB_CHECK_ARG(strideA % 2 == 0, "strideA must be even");
-  TRB_CHECK_ARG(s && s2 && az && ax && tz && tx && v, "null pointer");
+  TRB_CHECK_ARG(ldvec >= n, "ldvec < n");
+  TRB_CHECK_ARG(s && s2 && az && ax && t_other && coef && v, "null pointer");
   TRB_CHECK_ARG(dir == 0 || dir == 1, "dir must be 0 or 1");
+  TRB_CHECK_ARG(dir == 0 || !snap_tx, "snap_tx is the copy of tx taken by the forward rescale");
   TRB_CHECK_ARG(R <= Nz && R <= Nx && rank >= 0 && rank <= R, "bad shape");
   cudaStream_t st = (cudaStream_t)stream;
   const trb_expand_geom geo = trb_expand_geometry(B, R);
@@ -848,8 +827,8 @@ int trb_lin_rescale_expand(int dir, const double* A, int64_t strideA, int R, int
   rf.stride_s = stride_s;
   rf.az = az;
   rf.ax = ax;
-  rf.tz = tz;
-  rf.tx = tx;
+  rf.t_other = t_other;
+  rf.coef = coef;
   rf.v_out = v;
   rf.snap_tx = snap_tx;
   TmaPlan p, pq;
@@ -858,11 +837,11 @@ int trb_lin_rescale_expand(int dir, const double* A, int64_t strideA, int R, int
   if (!one_panel && (!plan_tma(pan.width, pq) || pq.nb < 8)) return TRB_ERR_UNSUPPORTED;
   trb_launch_scope scope_(1, st);
   if (one_panel) {
-    rc = dispatch_tma<2>(p, geo.G, A, strideA, R, n, ld, B, tz, 0, part, geo.nslots, active, st, ld, ld, 1,
-                         ld, n, rf);
+    rc = dispatch_tma<2>(p, geo.G, A, strideA, R, n, ld, B, vec, ldvec, t_out, 0, active, st, ld, 0, 1, ld,
+                         n, rf);
   } else {
-    rc = dispatch_tma<2>(pq, geo.G, A, strideA, R, n, pan.width, B, tz, 0, part, geo.nslots, active, st, ld,
-                         ld, pan.count, ld, ld, rf);
+    rc = dispatch_tma<2>(pq, geo.G, A, strideA, R, n, pan.width, B, vec, ldvec, t_out, 0, active, st, ld, 0,
+                         pan.count, ld, n, rf);
   }
   if (rc) return rc;
   TRB_CHECK_LAUNCH();

@@ -4,7 +4,7 @@
 // backward pass, update_variables), :70-127 (constant damping), :187-209 (NaN
 // check); algos/callbacks.py:250-286 (EarlyStoppingEP); algos/metrics.py:5-14.
 //
-// One iteration = 9 stages on one stream (7 launches: S1 and S2 run inside the expansions P2 and P4
+// One iteration = 9 stages on one stream (7 launches: S1 and S2 run inside the projections P1 and P3
 // when the operator passes are GEMVs), B instances in lock step, no host round trip (edge
 // numbering e1..e8 as in SURVEY 3.3):
 //   F1  factor_message(prior)   e8 -> e1 (=e2)
@@ -450,12 +450,11 @@ int trb_lin_rescale_snap(int dir, int B, int R, int Nz, int Nx, int rank, int nu
                          const double* s, const double* s2, int64_t stride_s, const double* az,
                          const double* ax, const double* tz, const double* tx, double* coef, double* v,
                          const int* active, double* snap_tx, void* stream);
-int trb_lin_rescale_expand(int dir, const double* A, int64_t strideA, int R, int n, int ld, int B,
-                           double* part, const int* active, int Nz, int Nx, int rank, int null_space,
-                           const double* s, const double* s2, int64_t stride_s, const double* az,
-                           const double* ax, const double* tz, const double* tx, double* v,
-                           double* snap_tx, void* stream);
-int trb_reduce_slots_inplace(int B, int R, int n, int ld, double* part, void* stream);
+int trb_lin_project_rescale(const double* A, int64_t strideA, int R, int n, int ld, int B,
+                            const double* vec, int ldvec, double* t_out, const int* active, int dir,
+                            int Nz, int Nx, int rank, int null_space, const double* s, const double* s2,
+                            int64_t stride_s, const double* az, const double* ax, const double* t_other,
+                            double* coef, double* v, double* snap_tx, void* stream);
 // The push is NOT gated by `active`: every rank takes the same stop decision in the same
 // iteration (the update kernels are computed redundantly on bit-identical sums), and a stopped
 // instance's `part` is no longer rewritten by trb_lin_expand, so the ranks go on pushing and
@@ -655,11 +654,11 @@ case TRB_STAGE_EXPAND_Z:  // P4: rz = [b2/a2 +] V_R coef
   return trb_set_error(TRB_ERR_INVALID, "trb_sweep_stage: unknown stage %d", stage);
 }
 
-// ---- rescale inside the expansion (S1+P2, S2+P4) --------------------------------------
+// ---- rescale inside the projection (P1+S1, P3+S2) --------------------------------------
 // The rescale is 4 vectors of R per instance: as a kernel of its own it costs a launch and an idle
-// GPU on both sides (~18 us at the north-star size, twice per iteration).  The expanding GEMV
-// computes the coefficients itself, one block of rows ahead of the rows it streams, and the
-// variance from the spectrum (trb_linear.cu, RescaleFused): no coefficient vector, no launch.
+// GPU on both sides (~18 us at the north-star size, twice per iteration).  The projecting GEMV
+// writes the coefficient of a row next to its projection and the variance from the spectrum
+// (trb_linear.cu, RescaleFused): no launch, no wait on other CTAs.
 static int g_fuse_rescale = -1;
 
 extern "C" void trb_set_fused_rescale(int enabled) { g_fuse_rescale = enabled ? 1 : 0; }
@@ -676,26 +675,21 @@ static bool rescale_fusable(const trb_sweep* sw) {
 }
 
 // TRB_ERR_UNSUPPORTED: nothing was launched, the caller runs the two stages one by one
-static int rescale_and_expand(const trb_sweep* sw, int dir, cudaStream_t st) {
+static int project_and_rescale(const trb_sweep* sw, int dir, cudaStream_t st) {
   const int B = sw->B;
   double* ea = sw->edge_a;
   const int R_total = sw->R_total > 0 ? sw->R_total : sw->R;
   const int null_space = R_total < sw->N;
-  int rc;
-  if (dir == 0)  // S1 + P2: coef = s res (tz + s tx), forward variance, rx = U_R coef
-    rc = trb_lin_rescale_expand(0, sw->Ut, sw->strideU, sw->R, sw->M, sw->ldm, B, sw->part, sw->active,
-                                sw->N, sw->M, sw->rank, null_space, sw->s, sw->s2, sw->stride_s,
-                                ea + 1 * B, ea + 5 * B, sw->tz, sw->tx, sw->vlin,
-                                (sw->schedule == 0 && sw->snap_edge_a) ? sw->snap_tx : nullptr, (void*)st);
-  else  // S2 + P4: coef for rz, backward variance, rz = [b2/a2 +] V_R coef
-    rc = trb_lin_rescale_expand(1, sw->Vt, sw->strideV, sw->R, sw->N, sw->ldn, B, sw->part, sw->active,
-                                sw->N, sw->M, sw->rank, null_space, sw->s, sw->s2, sw->stride_s,
-                                ea + 1 * B, ea + 5 * B, sw->tz, sw->tx, sw->vlin, nullptr, (void*)st);
-  if (rc) return rc;
-  if (sw->nslots > kTrbDirectSlots)  // few instances over many CTAs: leave the slot sum in slot 0
-    return trb_reduce_slots_inplace(B, sw->R, dir == 0 ? sw->M : sw->N, dir == 0 ? sw->ldm : sw->ldn,
-                                    sw->part, (void*)st);
-  return TRB_OK;
+  if (dir == 0)  // P1 + S1: tz = V_R^T b2, coef = s res (tz + s tx), forward variance
+    return trb_lin_project_rescale(sw->Vt, sw->strideV, sw->R, sw->N, sw->ldn, B, sw->b1, sw->ldn, sw->tz,
+                                   sw->active, 0, sw->N, sw->M, sw->rank, null_space, sw->s, sw->s2,
+                                   sw->stride_s, ea + 1 * B, ea + 5 * B, sw->tx, sw->coef, sw->vlin,
+                                   (sw->schedule == 0 && sw->snap_edge_a) ? sw->snap_tx : nullptr, (void*)st);
+  // P3 + S2: tx = U_R^T b6 (new), coef for rz, backward variance
+  return trb_lin_project_rescale(sw->Ut, sw->strideU, sw->R, sw->M, sw->ldm, B, sw->b5, sw->ldm, sw->tx,
+                                 sw->active, 1, sw->N, sw->M, sw->rank, null_space, sw->s, sw->s2,
+                                 sw->stride_s, ea + 1 * B, ea + 5 * B, sw->tz, sw->coef, sw->vlin, nullptr,
+                                 (void*)st);
 }
 
 // One whole iteration, stage by stage (see the header comment of this file).
@@ -705,8 +699,7 @@ static int enqueue_iteration(const trb_sweep* sw, int it, int first, int fresh, 
   const int schedule = sw->schedule;
   const bool fuse = rescale_fusable(sw);
   TRB_TRY(trb_sweep_stage(sw, TRB_STAGE_PRIOR, it, first, 0, stream));
-  TRB_TRY(trb_sweep_stage(sw, TRB_STAGE_PROJECT_Z, it, first, 0, stream));
-  if (first) {
+  if (first) {  // tx of the initial e6 (S1 needs it)
     if (fresh == 2) {  // e6 was initialised to b = 0: U_R^T 0 = 0, no pass over U needed
       cudaError_t e = cudaMemsetAsync(sw->tx, 0, sizeof(double) * (size_t)sw->B * sw->R, st);
       if (e != cudaSuccess)
@@ -715,28 +708,23 @@ static int enqueue_iteration(const trb_sweep* sw, int it, int first, int fresh, 
       TRB_TRY(trb_sweep_stage(sw, TRB_STAGE_PROJECT_X_INIT, it, first, 0, stream));
     }
   }
-  int fused = TRB_ERR_UNSUPPORTED;
-  if (fuse && !light) {
-    fused = rescale_and_expand(sw, 0, st);
-    if (fused != TRB_OK && fused != TRB_ERR_UNSUPPORTED) return fused;
-  }
+  int fused = fuse ? project_and_rescale(sw, 0, st) : TRB_ERR_UNSUPPORTED;
+  if (fused != TRB_OK && fused != TRB_ERR_UNSUPPORTED) return fused;
   if (fused != TRB_OK) {
+    TRB_TRY(trb_sweep_stage(sw, TRB_STAGE_PROJECT_Z, it, first, 0, stream));
     TRB_TRY(trb_sweep_stage(sw, TRB_STAGE_RESCALE_FWD, it, first, 0, stream));
-    if (!light) TRB_TRY(trb_sweep_stage(sw, TRB_STAGE_EXPAND_X, it, first, 0, stream));
   }
+  if (!light) TRB_TRY(trb_sweep_stage(sw, TRB_STAGE_EXPAND_X, it, first, 0, stream));
   TRB_TRY(trb_sweep_stage(sw, light ? TRB_STAGE_Z_UPDATE_LIGHT : TRB_STAGE_Z_UPDATE, it, first, 0,
                           stream));
-  TRB_TRY(trb_sweep_stage(sw, schedule ? TRB_STAGE_TX_RECUR : TRB_STAGE_PROJECT_X, it, first, 0,
-                          stream));
-  fused = TRB_ERR_UNSUPPORTED;
-  if (fuse) {
-    fused = rescale_and_expand(sw, 1, st);
-    if (fused != TRB_OK && fused != TRB_ERR_UNSUPPORTED) return fused;
-  }
+  fused = (fuse && schedule == 0) ? project_and_rescale(sw, 1, st) : TRB_ERR_UNSUPPORTED;
+  if (fused != TRB_OK && fused != TRB_ERR_UNSUPPORTED) return fused;
   if (fused != TRB_OK) {
+    TRB_TRY(trb_sweep_stage(sw, schedule ? TRB_STAGE_TX_RECUR : TRB_STAGE_PROJECT_X, it, first, 0,
+                            stream));
     TRB_TRY(trb_sweep_stage(sw, TRB_STAGE_RESCALE_BWD, it, first, 0, stream));
-    TRB_TRY(trb_sweep_stage(sw, TRB_STAGE_EXPAND_Z, it, first, 0, stream));
   }
+  TRB_TRY(trb_sweep_stage(sw, TRB_STAGE_EXPAND_Z, it, first, 0, stream));
   TRB_TRY(trb_sweep_stage(sw, TRB_STAGE_X_UPDATE, it, first, 0, stream));
   // The update kernels copy every value they overwrite to the one-iteration-back state, so a
   // stopped instance is rolled back once, at the end of trb_sweep_run.  Schedule 2 skips the z
