@@ -222,11 +222,12 @@ k_factor_message(trb_factor f, int n, int ld, const double* __restrict__ a_in,
   __shared__ double sh[33];
   __shared__ int sh_flag;
   const int inst = blockIdx.y;
-  if (active && !active[inst]) return;  // uniform over the cluster
+  const int act = active ? active[inst] : 1;  // issued together with a: one round trip, not two
+  const double a = a_in[inst];
+  if (!act) return;  // uniform over the cluster
   const int T = blockDim.x * cluster_nctarank();
   const int gtid = cluster_ctarank() * blockDim.x + threadIdx.x;
   const size_t off = (size_t)inst * ld;
-  const double a = a_in[inst];
   double a_new;
   int flag = 0;
   if (factor_is_constant_message(f.kind)) {
@@ -387,7 +388,12 @@ int trb_factor_message_snap(const trb_factor* f, int B, int n, int ld, const dou
   TRB_CHECK_ARG(f->kind >= 0 && f->kind <= TRB_ABS_LIKELIHOOD, "unknown factor kind");
   TRB_CHECK_ARG(!needs_y(f->kind) || y, "likelihood needs y");
   trb_launch_scope scope_(0, (cudaStream_t)stream);
-  cudaError_t le = trb_launch_cluster(k_factor_message, trb_cluster_size(B, n), B, kEwThreads,
+  // 64 registers per thread: 2 CTAs of 512 threads or 4 of 256 per SM.  A batch that needs more
+  // than one wave of 512-thread CTAs runs as half as many waves of 256-thread CTAs: the fixed part
+  // of a CTA's life (launch, first loads, the reduction, the tail) is paid half as often.
+  const int C = trb_cluster_size(B, n);
+  const int threads = ((long long)B * C > 2LL * trb_sm_count_cached()) ? kEwThreads / 2 : kEwThreads;
+  cudaError_t le = trb_launch_cluster(k_factor_message, C, B, threads,
                                       (cudaStream_t)stream, *f, n, ld, a_in, b_in, y, a_io, b_io,
                                       a_copy, damping, scratch, flags, active, snap_b, snap_a, snap_a_copy);
   if (le != cudaSuccess)

@@ -232,100 +232,89 @@ k_x_update(trb_sweep sw, int G, int it_host, double* __restrict__ stats, trb_pee
 // instance walks its vector in rounds of a few loads per thread, and the rounds' latencies add
 // up: ~80 KB in flight per SM where HBM needs ~150 KB (Little).  Here an instance is cut into
 // chunks of kChunk elements, one small CTA each (grid (chunks, B), 4 CTAs per SM), every thread
-// issues ALL its loads at once, and the chunk sums go to a scratch row of the instance; the CTA
-// that arrives last (threadfence + counter, column 3 of `stats`) adds them in chunk order -- the
+// issues ALL its loads at once -- flag, scalars and elements (trb_updates.cuh) -- the CTA's sums
+// meet in thread 0 after ONE barrier, and go to a scratch row of the instance; the thread whose
+// chunk arrives last (acq_rel counter, column 3 of `stats`) adds the chunks in chunk order -- the
 // result does not depend on the arrival order -- and writes the instance's scalars (z_tail /
 // x_tail).  Per element the arithmetic is that of k_z_update / k_x_update, bit for bit.
 constexpr int kChThreads = 256;
 constexpr int kChE = 4;  // elements per thread
 constexpr int kChunk = kChThreads * kChE;
+constexpr int kChCtasPerSm = 3;  // 85 registers per thread: the loads of a thread all stay in registers
 constexpr int kZPartials = 3, kXPartials = 5;  // sums + flags per chunk
-
-// whole CTA; thread 0 has written this chunk's partial sums.  True in the CTA that arrives last.
-__device__ __forceinline__ bool chunk_arrive_last(unsigned int* cnt, int nchunk, int* sh_last) {
-  if (threadIdx.x == 0) {
-    __threadfence();
-    const unsigned int before = atomicAdd(cnt, 1u);
-    const int last = (before + 1u == (unsigned int)nchunk);
-    if (last) {
-      *cnt = 0;  // nobody else touches the counter before the next launch
-      __threadfence();
-    }
-    *sh_last = last;
-  }
-  __syncthreads();
-  return *sh_last != 0;
-}
 
 // Gaussian likelihood (constant message e5, gaussian_likelihood.py:68-71): no sum is needed
 // before the second half of the update, so the whole z update is one pass.
-__global__ void __launch_bounds__(kChThreads, 4)
+__global__ void __launch_bounds__(kChThreads, kChCtasPerSm)
 k_z_update_chunked(trb_sweep sw, int G, int first, double* __restrict__ stats, trb_peers peers) {
-  __shared__ double sh[33 * 2];
-  __shared__ int sh_flag, sh_last;
+  __shared__ double sh[2 * 8];
+  __shared__ int shi[8];
   const int b = blockIdx.y, chunk = blockIdx.x, nchunk = gridDim.x;
-  if (sw.active && !sw.active[b]) return;
-  const ZScalars z = z_scalars(sw, b);
+  // every load first: flag, scalars, elements (independent addresses), then the first look
+  const int act = sw.active ? sw.active[b] : 1;
+  const ZRaw raw = z_raw(sw, b);
+  const int ns = slots_of(b, sw.R, sw.B, G);
+  const int start = chunk * kChunk + (int)threadIdx.x;
+  ZLoads<kChE> l;
+  z_load<kChE>(sw, b, ns, first, &peers, start, kChThreads, l);
+  if (!act) return;
+  const ZScalars z = z_scalars(sw, raw);
   int flag = z_scalar_flags(z);
   if (peers.n > 0 && !peers_wait(peers)) flag |= TRB_FLAG_COMM_TIMEOUT;
   double red[2] = {0.0, 0.0};
-  z_elements<kChE, false>(sw, b, slots_of(b, sw.R, sw.B, G), first, &peers, z,
-                          chunk * kChunk + (int)threadIdx.x, kChThreads, red, flag);
-  block_sum_n<2>(red, sh);
-  const int all_cta = block_or(flag, &sh_flag);
+  z_compute<kChE>(sw, b, ns, &peers, z, start, kChThreads, l, red, flag);
+  cta_sums_to_thread0<2>(red, flag, sh, shi);
+  if (threadIdx.x != 0) return;
   double* partials = sw.scr_m + (size_t)b * sw.ldm;  // free here: the likelihood parks nothing
-  if (threadIdx.x == 0) {
-    partials[chunk * kZPartials + 0] = red[0];
-    partials[chunk * kZPartials + 1] = red[1];
-    partials[chunk * kZPartials + 2] = (double)all_cta;
-  }
+  partials[chunk * kZPartials + 0] = red[0];
+  partials[chunk * kZPartials + 1] = red[1];
+  partials[chunk * kZPartials + 2] = (double)flag;
   unsigned int* cnt = reinterpret_cast<unsigned int*>(stats) + (size_t)b * 8 + 6;
-  if (!chunk_arrive_last(cnt, nchunk, &sh_last)) return;
-  if (threadIdx.x == 0) {
-    double d2 = 0.0, n2 = 0.0;
-    int all = 0;
-    for (int c = 0; c < nchunk; ++c) {
-      d2 += __ldcg(partials + c * kZPartials + 0);
-      n2 += __ldcg(partials + c * kZPartials + 1);
-      all |= (int)__ldcg(partials + c * kZPartials + 2);
-    }
-    z_tail(sw, b, 0, stats, z.a3, z.a5, z.a_hat, all, d2, n2);
+  if (!chunk_arrive_last(cnt, nchunk)) return;
+  double d2 = 0.0, n2 = 0.0;
+  int all = 0;
+  for (int c = 0; c < nchunk; ++c) {
+    d2 += __ldcg(partials + c * kZPartials + 0);
+    n2 += __ldcg(partials + c * kZPartials + 1);
+    all |= (int)__ldcg(partials + c * kZPartials + 2);
   }
+  z_tail(sw, b, 0, stats, z.a3, z.a5, z.a_hat, all, d2, n2);
 }
 
-__global__ void __launch_bounds__(kChThreads, 4)
+__global__ void __launch_bounds__(kChThreads, kChCtasPerSm)
 k_x_update_chunked(trb_sweep sw, int G, int it_host, double* __restrict__ stats, trb_peers peers) {
-  __shared__ double sh[33 * 4];
-  __shared__ int sh_flag, sh_last;
+  __shared__ double sh[4 * 8];
+  __shared__ int shi[8];
   const int b = blockIdx.y, chunk = blockIdx.x, nchunk = gridDim.x;
-  if (sw.active && !sw.active[b]) return;
-  const int it = it_host >= 0 ? it_host : sw.n_iter[b];  // see k_x_update
-  const XScalars x = x_scalars(sw, b);
+  const int act = sw.active ? sw.active[b] : 1;
+  const XRaw raw = x_raw(sw, b);
+  const int ns = slots_of(b, sw.R, sw.B, G);
+  const int start = chunk * kChunk + (int)threadIdx.x;
+  XLoads<kChE> l;
+  x_load<kChE>(sw, b, ns, &peers, start, kChThreads, l);
+  if (!act) return;
+  const XScalars x = x_scalars(sw, raw);
   int flag = x_scalar_flags(x);
   if (peers.n > 0 && !peers_wait(peers)) flag |= TRB_FLAG_COMM_TIMEOUT;
   double red[4] = {0.0, 0.0, 0.0, 0.0};
-  x_elements<kChE, false>(sw, b, slots_of(b, sw.R, sw.B, G), &peers, x, chunk * kChunk + (int)threadIdx.x,
-                          kChThreads, red, flag);
-  block_sum_n<4>(red, sh);
-  const int all_cta = block_or(flag, &sh_flag);
+  x_compute<kChE>(sw, b, ns, &peers, x, start, kChThreads, l, red, flag);
+  cta_sums_to_thread0<4>(red, flag, sh, shi);
+  if (threadIdx.x != 0) return;
   double* partials = sw.scr_n + (size_t)b * sw.ldn;  // free here: the prior's scratch, rewritten by the next F1
-  if (threadIdx.x == 0) {
 #pragma unroll
-    for (int k = 0; k < 4; ++k) partials[chunk * kXPartials + k] = red[k];
-    partials[chunk * kXPartials + 4] = (double)all_cta;
-  }
+  for (int k = 0; k < 4; ++k) partials[chunk * kXPartials + k] = red[k];
+  partials[chunk * kXPartials + 4] = (double)flag;
   unsigned int* cnt = reinterpret_cast<unsigned int*>(stats) + (size_t)b * 8 + 7;
-  if (!chunk_arrive_last(cnt, nchunk, &sh_last)) return;
-  if (threadIdx.x == 0) {
-    double t[4] = {0.0, 0.0, 0.0, 0.0};
-    int all = 0;
-    for (int c = 0; c < nchunk; ++c) {
+  if (!chunk_arrive_last(cnt, nchunk)) return;
+  const int it = it_host >= 0 ? it_host : sw.n_iter[b];  // see k_x_update
+  double t[4] = {0.0, 0.0, 0.0, 0.0};
+  int all = 0;
+  for (int c = 0; c < nchunk; ++c) {
 #pragma unroll
-      for (int k = 0; k < 4; ++k) t[k] += __ldcg(partials + c * kXPartials + k);
-      all |= (int)__ldcg(partials + c * kXPartials + 4);
-    }
-    x_tail(sw, b, it, stats, x.a7, x.a_hat, all, t[0], t[1], t[2], t[3]);
+    for (int k = 0; k < 4; ++k) t[k] += __ldcg(partials + c * kXPartials + k);
+    all |= (int)__ldcg(partials + c * kXPartials + 4);
   }
+  x_tail(sw, b, it, stats, x.a7, x.a_hat, all, t[0], t[1], t[2], t[3]);
 }
 
 // One-iteration-back snapshot of the message state, per instance:
