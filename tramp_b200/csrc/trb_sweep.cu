@@ -229,9 +229,11 @@ k_x_update(trb_sweep sw, int G, int it_host, double* __restrict__ stats, trb_pee
 
 // ---- chunked update kernels ---------------------------------------------------------------
 // The z / x updates are maps over the instance vector plus a few sums.  One CTA (or cluster) per
-// instance walks its vector in rounds of a few loads per thread, and the rounds' latencies add
-// up: ~80 KB in flight per SM where HBM needs ~150 KB (Little).  Here an instance is cut into
-// chunks of kChunk elements, one small CTA each (grid (chunks, B), 4 CTAs per SM), every thread
+// instance walks its vector in rounds of a few loads per thread behind a chain of dependent
+// accesses (flag -> scalars -> elements -> further slots), and the latencies add up (ncu,
+// profiles/r02c_ncu_update_kernels.json: these kernels follow the SM clock and the length of that
+// chain, not HBM).  Here an instance is cut into chunks of kChunk elements, one small CTA each
+// (grid (chunks, B), kChCtasPerSm CTAs per SM), every thread
 // issues ALL its loads at once -- flag, scalars and elements (trb_updates.cuh) -- the CTA's sums
 // meet in thread 0 after ONE barrier, and go to a scratch row of the instance; the thread whose
 // chunk arrives last (acq_rel counter, column 3 of `stats`) adds the chunks in chunk order -- the
