@@ -233,21 +233,24 @@ k_x_update(trb_sweep sw, int G, int it_host, double* __restrict__ stats, trb_pee
 // accesses (flag -> scalars -> elements -> further slots), and the latencies add up (ncu,
 // profiles/r02c_ncu_update_kernels.json: these kernels follow the SM clock and the length of that
 // chain, not HBM).  Here an instance is cut into chunks of kChunk elements, one small CTA each
-// (grid (chunks, B), kChCtasPerSm CTAs per SM), every thread
+// (grid (chunks, B), 3-4 CTAs per SM), every thread
 // issues ALL its loads at once -- flag, scalars and elements (trb_updates.cuh) -- the CTA's sums
 // meet in thread 0 after ONE barrier, and go to a scratch row of the instance; the thread whose
 // chunk arrives last (acq_rel counter, column 3 of `stats`) adds the chunks in chunk order -- the
 // result does not depend on the arrival order -- and writes the instance's scalars (z_tail /
 // x_tail).  Per element the arithmetic is that of k_z_update / k_x_update, bit for bit.
-constexpr int kChThreads = 256;
-constexpr int kChE = 4;  // elements per thread
-constexpr int kChunk = kChThreads * kChE;
-constexpr int kChCtasPerSm = 3;  // 85 registers per thread: the loads of a thread all stay in registers
+// Chunk = 1024 elements for both; threads x elements per thread as measured at the north-star
+// shape (ncu, us per launch): z 256 x 4 22.7 (128 x 8: 25.4), x 128 x 8 40.1 (256 x 4: 41.6) -- the
+// x update has the longer per-thread prologue to amortise.  Registers: all loads of a thread stay
+// in registers (85 at 3 CTAs per SM, 128 at 4).
+constexpr int kChunk = 1024;
+constexpr int kZcThreads = 256, kZcE = kChunk / kZcThreads, kZcCtasPerSm = 3;
+constexpr int kXcThreads = 128, kXcE = kChunk / kXcThreads, kXcCtasPerSm = 4;
 constexpr int kZPartials = 3, kXPartials = 5;  // sums + flags per chunk
 
 // Gaussian likelihood (constant message e5, gaussian_likelihood.py:68-71): no sum is needed
 // before the second half of the update, so the whole z update is one pass.
-__global__ void __launch_bounds__(kChThreads, kChCtasPerSm)
+__global__ void __launch_bounds__(kZcThreads, kZcCtasPerSm)
 k_z_update_chunked(trb_sweep sw, int G, int first, double* __restrict__ stats, trb_peers peers) {
   __shared__ double sh[2 * 8];
   __shared__ int shi[8];
@@ -257,14 +260,14 @@ k_z_update_chunked(trb_sweep sw, int G, int first, double* __restrict__ stats, t
   const ZRaw raw = z_raw(sw, b);
   const int ns = slots_of(b, sw.R, sw.B, G);
   const int start = chunk * kChunk + (int)threadIdx.x;
-  ZLoads<kChE> l;
-  z_load<kChE>(sw, b, ns, first, &peers, start, kChThreads, l);
+  ZLoads<kZcE> l;
+  z_load<kZcE>(sw, b, ns, first, &peers, start, kZcThreads, l);
   if (!act) return;
   const ZScalars z = z_scalars(sw, raw);
   int flag = z_scalar_flags(z);
   if (peers.n > 0 && !peers_wait(peers)) flag |= TRB_FLAG_COMM_TIMEOUT;
   double red[2] = {0.0, 0.0};
-  z_compute<kChE>(sw, b, ns, &peers, z, start, kChThreads, l, red, flag);
+  z_compute<kZcE>(sw, b, ns, &peers, z, start, kZcThreads, l, red, flag);
   cta_sums_to_thread0<2>(red, flag, sh, shi);
   if (threadIdx.x != 0) return;
   double* partials = sw.scr_m + (size_t)b * sw.ldm;  // free here: the likelihood parks nothing
@@ -283,7 +286,7 @@ k_z_update_chunked(trb_sweep sw, int G, int first, double* __restrict__ stats, t
   z_tail(sw, b, 0, stats, z.a3, z.a5, z.a_hat, all, d2, n2);
 }
 
-__global__ void __launch_bounds__(kChThreads, kChCtasPerSm)
+__global__ void __launch_bounds__(kXcThreads, kXcCtasPerSm)
 k_x_update_chunked(trb_sweep sw, int G, int it_host, double* __restrict__ stats, trb_peers peers) {
   __shared__ double sh[4 * 8];
   __shared__ int shi[8];
@@ -292,14 +295,14 @@ k_x_update_chunked(trb_sweep sw, int G, int it_host, double* __restrict__ stats,
   const XRaw raw = x_raw(sw, b);
   const int ns = slots_of(b, sw.R, sw.B, G);
   const int start = chunk * kChunk + (int)threadIdx.x;
-  XLoads<kChE> l;
-  x_load<kChE>(sw, b, ns, &peers, start, kChThreads, l);
+  XLoads<kXcE> l;
+  x_load<kXcE>(sw, b, ns, &peers, start, kXcThreads, l);
   if (!act) return;
   const XScalars x = x_scalars(sw, raw);
   int flag = x_scalar_flags(x);
   if (peers.n > 0 && !peers_wait(peers)) flag |= TRB_FLAG_COMM_TIMEOUT;
   double red[4] = {0.0, 0.0, 0.0, 0.0};
-  x_compute<kChE>(sw, b, ns, &peers, x, start, kChThreads, l, red, flag);
+  x_compute<kXcE>(sw, b, ns, &peers, x, start, kXcThreads, l, red, flag);
   cta_sums_to_thread0<4>(red, flag, sh, shi);
   if (threadIdx.x != 0) return;
   double* partials = sw.scr_n + (size_t)b * sw.ldn;  // free here: the prior's scratch, rewritten by the next F1
@@ -568,7 +571,7 @@ extern "C" int trb_sweep_stage(const trb_sweep* sw, int stage, int it, int first
       const int zchunks = (sw->M + kChunk - 1) / kChunk;
       if ((update_kernels() & 2) && !light && sw->lik.kind == TRB_GAUSSIAN_LIKELIHOOD &&
           zchunks * kZPartials <= sw->ldm) {
-        k_z_update_chunked<<<dim3(zchunks, B), kChThreads, 0, st>>>(*sw, G, first, sw->stats, peers);
+        k_z_update_chunked<<<dim3(zchunks, B), kZcThreads, 0, st>>>(*sw, G, first, sw->stats, peers);
         TRB_CHECK_LAUNCH();
         return TRB_OK;
       }
@@ -617,7 +620,7 @@ case TRB_STAGE_EXPAND_Z:  // P4: rz = [b2/a2 +] V_R coef
       if (comm) peers = *trb_comm_last(comm);
       const int xchunks = (sw->N + kChunk - 1) / kChunk;
       if ((update_kernels() & 1) && xchunks * kXPartials <= sw->ldn) {
-        k_x_update_chunked<<<dim3(xchunks, B), kChThreads, 0, st>>>(*sw, G, it, sw->stats, peers);
+        k_x_update_chunked<<<dim3(xchunks, B), kXcThreads, 0, st>>>(*sw, G, it, sw->stats, peers);
         TRB_CHECK_LAUNCH();
         return TRB_OK;
       }
