@@ -849,6 +849,25 @@ def _kernel_choice_cases(sw):
         ep.iterate(max_iter=200, callback=JoinCallback([track, EarlyStoppingEP(tol=1e-6)]))
         return track
     cases.append((build, run_es, True))
+    # rows wider than one stage of the TMA ring: the projection of V walks two column panels and
+    # the coefficient is written with the last one
+    B2, N2, M2 = 2, 8300, 48
+    W2 = rng.randn(B2, M2, N2) / np.sqrt(N2)
+    x2 = rng.randn(B2, N2) * (rng.rand(B2, N2) < 0.05)
+    y2 = np.einsum("bmn,bn->bm", W2, x2) + 0.1 * rng.randn(B2, M2)
+    lin2 = LinearChannel(W2)
+    lin2._setup()
+
+    def build2():
+        return ExpectationPropagation((GaussBernoulliPrior(size=N2, rho=0.05, batch=B2) @ V("x") @ lin2 @ V("z")
+                                       @ GaussianLikelihood(y=y2, var=1e-2)).to_model())
+
+    def run2(ep):
+        track = TrackErrors({"x": x2})
+        ep.schedule = "general"
+        ep.iterate(max_iter=12, callback=track, damping=0.1)
+        return track
+    cases.append((build2, run2, False))
     return cases
 
 

@@ -40,6 +40,21 @@ def test_argument_errors_do_not_need_a_gpu():
     assert lib.trb_lin_expand_slots(0, 4) == -1
 
 
+def test_kernel_choice_switches_and_timeline_without_a_gpu():
+    """The switches of trb_sweep_run (rescale inside the projections, chunked updates) and the
+    launch timeline are plain host state: callable without a device, and empty before any launch."""
+    from tramp_b200 import _lib
+    lib = _lib.load()
+    for value in (0, 1):
+        lib.trb_set_fused_rescale(value)
+    for mask in (0, 1, 2, 3, -1):
+        lib.trb_set_update_kernels(mask)
+    lib.trb_profile_reset(0)
+    ms, kinds = (ctypes.c_double * 4)(), (ctypes.c_int * 4)()
+    assert lib.trb_profile_timeline(ms, kinds, 4) == 0
+    assert lib.trb_profile_launches(-1) == 0
+
+
 def test_no_cpu_fallback():
     import torch
     if torch.cuda.is_available():
